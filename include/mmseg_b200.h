@@ -1,0 +1,178 @@
+/*
+ * mmseg_b200 — C ABI of the B200 (sm_100a) kernels behind the multimodal-organ-segmentation hot path.
+ *
+ * The reference (wittyseok/multimodal-organ-segmentation) is pure PyTorch and has no FFI of its own; the
+ * boundary it binds for this path is "torch.nn module -> ATen op".  Each entry point below therefore cites
+ * the reference call site whose ATen ops it replaces (paths relative to the reference root).  INTEGRATION.md
+ * shows the ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain C types only: device pointers as void*, sizes as int32/int64, the CUDA stream as void* (cudaStream_t).
+ *  - the caller (PyTorch) owns ALL memory, including workspaces; the library never allocates device memory.
+ *  - every call is asynchronous on `stream`; return 0 on success, negative mmseg_status on rejected arguments or
+ *    launch failure; mmseg_last_error() returns a thread-local message.  No exceptions cross the ABI.
+ *  - spatial axes are named (Z, Y, X) = tensor dims (2, 3, 4) of the reference's [B, C, H, W, D]; X is stride-1.
+ *
+ * Device data layouts
+ *  - "blocked" activations: [n_img * cbt][Z][Y][X][8] bf16 — channels in blocks of 8 (16 bytes per voxel per block);
+ *    cbt = channel blocks per image held by the buffer (a buffer may hold a concat of several producers, and, in the
+ *    3-pass "parity" numeric mode, a bf16 hi plane followed by a bf16 lo plane of the same channels).
+ *  - raw conv output before InstanceNorm: same blocked shape, bf16 (fast mode) or fp32 (parity mode).
+ *  - packed conv weights: [n_ntiles][n_kchunks][taps][2][NT][8] bf16 (K-major, SWIZZLE_NONE UMMA core matrices).
+ */
+#ifndef MMSEG_B200_H_
+#define MMSEG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMSEG_ABI_VERSION 1
+#define MMSEG_MAX_KCHUNKS 96
+
+typedef enum {
+  MMSEG_OK = 0,
+  MMSEG_ERR_INVALID_ARG = -1,
+  MMSEG_ERR_UNSUPPORTED = -2,
+  MMSEG_ERR_CUDA = -3,
+  MMSEG_ERR_NO_DRIVER = -4
+} mmseg_status;
+
+/* epilogue / output modes of mmseg_conv3d_fwd */
+enum {
+  MMSEG_OUT_BLOCKED_BF16 = 0,   /* blocked bf16 (raw conv output in fast mode, or activation)            */
+  MMSEG_OUT_BLOCKED_F32 = 1,    /* blocked fp32 (raw conv output in parity mode)                          */
+  MMSEG_OUT_BLOCKED_BF16_HILO = 2, /* blocked bf16 hi plane + lo plane at dst_lo_off (activation, parity) */
+  MMSEG_OUT_CONVT_K2S2 = 3,     /* ConvTranspose3d(k2,s2) pixel-shuffle scatter into a blocked bf16 buffer */
+  MMSEG_OUT_NCDHW_F32 = 4       /* [n_img][out_channels][Z][Y][X] fp32 (logits)                            */
+};
+
+int mmseg_version(void);
+const char* mmseg_last_error(void);
+/* 1 when the process can see a CUDA device of compute capability 10.x, else 0 (never raises). */
+int mmseg_device_ok(void);
+
+/*
+ * Conv3d forward as a tcgen05/TMEM implicit GEMM fed by TMA halo tiles.
+ * Replaces: nn.Conv3d(k=3,p=1) in ConvBlock3D (src/models/backbones/unet.py:26-27,54,57), nn.Conv3d(k=1)
+ * (unet.py:163; src/models/backbones/dual_encoder.py:75,84; src/models/fusion/attention_fusion.py:108-113) and, with
+ * MMSEG_OUT_CONVT_K2S2, nn.ConvTranspose3d(k=2,s=2) in UpBlock3D (unet.py:95,105).  torch.cat([up, skip], 1)
+ * (unet.py:111) costs nothing: a_cb[] lets one conv read its K chunks from any channel blocks of a shared buffer.
+ *
+ * GEMM view: M = output voxels (128-row tiles over a flattened halo tile), N = NT output channels per CTA,
+ * K = taps x 16-channel chunks.  Accumulators stay in TMEM for the whole K loop.
+ * stats_partial (optional): per-CTA per-channel (sum, sum of squares) of the fp32 accumulators over valid voxels —
+ * the InstanceNorm3d statistics (unet.py:34-35) are produced by the conv epilogue, deterministically (no atomics).
+ */
+typedef struct {
+  const void* src;       /* blocked bf16 [n_img*src_cbt][Z][Y][X][8]                                  */
+  const void* weights;   /* packed bf16, see layout above                                             */
+  const float* bias;     /* [n_ntiles*NT] fp32 or NULL                                                */
+  void* dst;             /* per out_mode                                                              */
+  float* stats_partial;  /* [n_img][tiles_per_img][n_ntiles*NT][2] fp32 or NULL                       */
+  int32_t n_img, Z, Y, X;
+  int32_t src_cbt;       /* channel blocks per image in src                                           */
+  int32_t ksize;         /* 3 (padding 1) or 1                                                        */
+  int32_t n_kchunks;     /* K chunks of 16 channels (<= MMSEG_MAX_KCHUNKS)                            */
+  int32_t NT, n_ntiles;  /* N tile (multiple of 16, <= 256) and number of N tiles (grid.y)            */
+  int32_t TX, TY, TZ;    /* output tile per CTA; TX + 2*(ksize/2) <= 128                              */
+  int32_t stages;        /* depth of the activation-plane ring in shared memory (>= 2)                */
+  int32_t out_mode;
+  int32_t out_channels;  /* real channels (masks N padding); for CONVT: channels per tap              */
+  int32_t dst_cbt, dst_cb_off, dst_lo_off; /* blocked destinations: blocks per image, first block, lo-plane offset */
+  int32_t flags;         /* bit0: debug — swap LBO/SBO in the smem descriptors                        */
+  int16_t a_cb[MMSEG_MAX_KCHUNKS]; /* first channel block (of 2) in src for each K chunk              */
+} mmseg_conv_args;
+
+int mmseg_conv3d_fwd(const mmseg_conv_args* args, void* stream);
+/* bytes of dynamic shared memory / TMEM columns / CTAs the call would use; <0 when the tiling is rejected */
+int64_t mmseg_conv3d_smem_bytes(const mmseg_conv_args* args);
+int32_t mmseg_conv3d_tiles_per_img(const mmseg_conv_args* args);
+
+/*
+ * InstanceNorm3d(affine=False, eps) statistics: reduce the conv epilogue's per-CTA partials in a fixed order (fp64)
+ * into mean / rstd per (image, channel).  Replaces the statistics half of nn.InstanceNorm3d (unet.py:34-35,55,58).
+ */
+int mmseg_instnorm_finalize(const float* stats_partial, int32_t n_img, int32_t tiles_per_img, int32_t channels,
+                            int64_t voxels, float eps, float* mean_rstd /* [n_img][channels][2] */, void* stream);
+
+/*
+ * y = act((x - mean) * rstd) over a blocked tensor, act = ReLU (slope 0) / LeakyReLU(slope); writes bf16 (hi[, lo]).
+ * Replaces nn.InstanceNorm3d apply + nn.ReLU (unet.py:45,55-59).  src_is_f32 selects the raw dtype.
+ * pooled (optional): also writes MaxPool3d(2) (unet.py:73,77) of y into a second blocked buffer.
+ */
+typedef struct {
+  const void* src;         /* raw conv output, blocked [n_img*cb][Z][Y][X][8] bf16 or fp32                 */
+  const float* mean_rstd;  /* [n_img][cb*8][2]                                                             */
+  void* dst;               /* blocked bf16 [n_img*dst_cbt]...                                              */
+  void* pooled;            /* blocked bf16 [n_img*pool_cbt][Z/2][Y/2][X/2][8] or NULL                      */
+  int32_t n_img, cb, Z, Y, X;
+  int32_t src_is_f32;
+  int32_t dst_cbt, dst_cb_off, dst_lo_off;
+  int32_t pool_cbt, pool_cb_off, pool_lo_off;
+  float slope;
+} mmseg_norm_args;
+int mmseg_instnorm_act_apply(const mmseg_norm_args* args, void* stream);
+
+/* NCDHW fp32 [n_img][C][Z][Y][X] -> blocked bf16 (hi[, lo]) with channels zero-padded to cb*8.  Module boundary. */
+int mmseg_pack_ncdhw(const float* src, void* dst, int32_t n_img, int32_t C, int32_t Z, int32_t Y, int32_t X,
+                     int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, int32_t cb, void* stream);
+/* blocked bf16 (hi[, lo]) -> NCDHW fp32 (feature taps for return_features / hooks). */
+int mmseg_unpack_ncdhw(const void* src, float* dst, int32_t n_img, int32_t C, int32_t Z, int32_t Y, int32_t X,
+                       int32_t src_cbt, int32_t src_cb_off, int32_t src_lo_off, void* stream);
+
+/*
+ * Sliding-window inference pieces (monai.inferers.sliding_window_inference as called at
+ * src/trainer/trainer.py:381-392; algorithm in SURVEY.md Appendix C).
+ *  gather:  windows of the NCDHW fp32 volume -> blocked bf16 batch (one image per window).
+ *  blend:   out[:, window] += w * logits[window]; count[window] += w — windows applied in index order per voxel,
+ *           one owner thread per voxel (deterministic, same order as the reference loop; no atomics).
+ *  finalize: out / count (in place, optional) and argmax over channels -> uint8 labels (trainer.py:364-367).
+ */
+int mmseg_swi_gather(const float* volume, int32_t C, int32_t VZ, int32_t VY, int32_t VX, const int32_t* starts_dev,
+                     int32_t n_win, int32_t RZ, int32_t RY, int32_t RX, void* dst, int32_t dst_cbt, int32_t dst_lo_off,
+                     int32_t cb, void* stream);
+int mmseg_swi_blend(const float* win_logits /* [n_win][K][RZ][RY][RX] */, const int32_t* starts_dev, int32_t n_win,
+                    int32_t K, int32_t RZ, int32_t RY, int32_t RX, const float* wz, const float* wy, const float* wx,
+                    float w_floor, float* out /* [K][VZ][VY][VX] */, float* count /* [VZ][VY][VX] */, int32_t VZ,
+                    int32_t VY, int32_t VX, int32_t bz0, int32_t bz1, int32_t by0, int32_t by1, int32_t bx0,
+                    int32_t bx1, void* stream);
+int mmseg_swi_finalize(float* out, const float* count, int32_t K, int64_t voxels, int32_t normalize_in_place,
+                       uint8_t* labels /* or NULL */, void* stream);
+
+/*
+ * DiceCE forward in one pass over the logits (src/trainer/losses.py:216-228, DiceLoss :39-80, CrossEntropyLoss).
+ * result[0..2] = total, dice part, ce part.  C in {2,3,4,8,16}.
+ */
+int mmseg_dicece_fwd(const float* logits /* [B][C][N] */, const int64_t* target /* [B][N] */, int32_t B, int32_t C,
+                     int64_t N, float dice_weight, float ce_weight, float smooth, int32_t include_background,
+                     const float* class_weights /* [C] or NULL */, float* partial /* [B][n_blocks][3*C+2] */,
+                     int32_t n_blocks, float* result /* [3] */, void* stream);
+
+/*
+ * DualEncoder modality fusion (src/models/backbones/dual_encoder.py:167-199, CrossModalAttention :207-254; same maths
+ * as AttentionFusion, src/models/fusion/attention_fusion.py:48-74).  The M encoders write their level outputs into one
+ * blocked buffer, modality-major (channel m*C + c), so torch.stack / torch.cat cost nothing.
+ *  channel_mean:     AdaptiveAvgPool3d(1) per (image, channel), deterministic two-stage reduction.
+ *  gate_mlp:         Linear(MC, MC/4) -> ReLU -> Linear(MC/4, M) -> Softmax over modalities.
+ *  modality_combine: dst[b,c] = sum_m w[b,m] * src[b, m*C + c]  (w = gate, or uniform 1/M for mean, 1 for add).
+ *  maxpool3d_2:      nn.MaxPool3d(2) (unet.py:73,77) on a blocked tensor (stand-alone DownBlock3D).
+ */
+int mmseg_channel_mean(const void* src, int32_t n_img, int32_t src_cbt, int32_t cb_off, int32_t lo_off, int32_t cb,
+                       int64_t voxels, float* partial /* [n_img*cb][n_chunks][8] */, int32_t n_chunks,
+                       float* mean /* [n_img][cb*8] */, void* stream);
+int mmseg_gate_mlp(const float* pooled, const float* w1, const float* b1, const float* w2, const float* b2,
+                   int32_t n_img, int32_t MC, int32_t H, int32_t M, float* weights /* [n_img][M] */, void* stream);
+int mmseg_modality_combine(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_lo_off, int32_t M, int32_t cb,
+                           int64_t voxels, const float* weights /* [n_img][M] or NULL */, float uniform_weight,
+                           void* dst, int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, void* stream);
+int mmseg_maxpool3d_2(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_cb_off, int32_t src_lo_off,
+                      int32_t cb, int32_t Z, int32_t Y, int32_t X, void* dst, int32_t dst_cbt, int32_t dst_cb_off,
+                      int32_t dst_lo_off, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMSEG_B200_H_ */

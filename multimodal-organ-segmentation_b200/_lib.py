@@ -1,0 +1,102 @@
+"""ctypes binding of libmmseg_b200.so (the C ABI declared in include/mmseg_b200.h).
+
+There is no fallback: if the shared library is missing the import of this module raises, and every compute entry
+point raises RuntimeError when the call is rejected or no sm_100 device is present.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmseg_b200.so")
+
+MAX_KCHUNKS = 96
+
+OUT_BLOCKED_BF16 = 0
+OUT_BLOCKED_F32 = 1
+OUT_BLOCKED_BF16_HILO = 2
+OUT_CONVT_K2S2 = 3
+OUT_NCDHW_F32 = 4
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("weights", C.c_void_p), ("bias", C.c_void_p), ("dst", C.c_void_p),
+        ("stats_partial", C.c_void_p),
+        ("n_img", C.c_int32), ("Z", C.c_int32), ("Y", C.c_int32), ("X", C.c_int32),
+        ("src_cbt", C.c_int32), ("ksize", C.c_int32), ("n_kchunks", C.c_int32),
+        ("NT", C.c_int32), ("n_ntiles", C.c_int32),
+        ("TX", C.c_int32), ("TY", C.c_int32), ("TZ", C.c_int32),
+        ("stages", C.c_int32), ("out_mode", C.c_int32), ("out_channels", C.c_int32),
+        ("dst_cbt", C.c_int32), ("dst_cb_off", C.c_int32), ("dst_lo_off", C.c_int32),
+        ("flags", C.c_int32),
+        ("a_cb", C.c_int16 * MAX_KCHUNKS),
+    ]
+
+
+class NormArgs(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("mean_rstd", C.c_void_p), ("dst", C.c_void_p), ("pooled", C.c_void_p),
+        ("n_img", C.c_int32), ("cb", C.c_int32), ("Z", C.c_int32), ("Y", C.c_int32), ("X", C.c_int32),
+        ("src_is_f32", C.c_int32),
+        ("dst_cbt", C.c_int32), ("dst_cb_off", C.c_int32), ("dst_lo_off", C.c_int32),
+        ("pool_cbt", C.c_int32), ("pool_cb_off", C.c_int32), ("pool_lo_off", C.c_int32),
+        ("slope", C.c_float),
+    ]
+
+
+# every symbol include/mmseg_b200.h declares: name -> (restype, argtypes)
+_i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+SYMBOLS = {
+    "mmseg_version": (C.c_int, []),
+    "mmseg_last_error": (C.c_char_p, []),
+    "mmseg_device_ok": (C.c_int, []),
+    "mmseg_conv3d_fwd": (C.c_int, [C.POINTER(ConvArgs), _vp]),
+    "mmseg_conv3d_smem_bytes": (_i64, [C.POINTER(ConvArgs)]),
+    "mmseg_conv3d_tiles_per_img": (_i32, [C.POINTER(ConvArgs)]),
+    "mmseg_instnorm_finalize": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _f32, _vp, _vp]),
+    "mmseg_instnorm_act_apply": (C.c_int, [C.POINTER(NormArgs), _vp]),
+    "mmseg_pack_ncdhw": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "mmseg_unpack_ncdhw": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "mmseg_swi_gather": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
+    "mmseg_swi_blend": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _vp,
+                                  _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "mmseg_swi_finalize": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp]),
+    "mmseg_dicece_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _f32, _f32, _f32, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "mmseg_channel_mean": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _vp]),
+    "mmseg_gate_mlp": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "mmseg_modality_combine": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _f32, _vp, _i32, _i32, _i32, _vp]),
+    "mmseg_maxpool3d_2": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
+}
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(or `make -C multimodal-organ-segmentation_b200/csrc`). There is no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+for _name, (_res, _args) in SYMBOLS.items():
+    _fn = getattr(lib, _name)  # AttributeError if the library does not export a declared symbol
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error() -> str:
+    return lib.mmseg_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (status {rc}): {last_error()}")
+
+
+_device_ok = None
+
+
+def require_device() -> None:
+    """Fail loudly when there is no B200-class device: the product path has no CPU route."""
+    global _device_ok
+    if _device_ok is None:
+        _device_ok = bool(lib.mmseg_device_ok())
+    if not _device_ok:
+        raise RuntimeError("mmseg_b200 needs a CUDA device of compute capability 10.x (sm_100a); none is visible "
+                           "and there is no CPU fallback")

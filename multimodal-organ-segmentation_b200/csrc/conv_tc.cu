@@ -1,0 +1,457 @@
+// Conv3d forward (k=3 pad 1, k=1, and ConvTranspose3d k2 s2 as a 1x1 GEMM + pixel shuffle) as a tcgen05 / TMEM
+// implicit GEMM for sm_100a.  See include/mmseg_b200.h for the contract and DESIGN.md for the derivation.
+//
+// One CTA owns an output tile of TZ x TY x TX voxels x NT channels.
+//   * activations live in HBM as [cb][Z][Y][X][8] bf16 ("blocked"); a TMA box (2 channel blocks x PY x PX voxels,
+//     zero-filled outside the volume = the conv's zero padding) lands in shared memory as two contiguous planes of
+//     16-byte voxel rows, which IS the SWIZZLE_NONE K-major UMMA operand layout (row pitch 16 B, LBO = plane size).
+//   * every filter tap is the same smem plane read at a row offset (dy*PX + dx): the A descriptor's start address
+//     moves, nothing is re-loaded.  128-row M tiles run over the flattened (y, x) plane; rows that fall in the halo
+//     columns are computed and discarded (2/PX of the rows).
+//   * K loop = 16-channel chunks (outer) x input z-planes (ring of `stages` smem slots) x taps; the TZ*mt
+//     accumulators (NT fp32 columns each, <= 512 columns) stay resident in TMEM for the whole loop.
+//   * warp 0: TMA producer, warp 1: MMA issuer (one elected lane each), warps 2-5: epilogue (TMEM -> registers ->
+//     HBM, plus per-channel sum / sum-of-squares partials for InstanceNorm).
+#include <cuda.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mmseg {
+
+struct ConvKParams {
+  int X, Y, Z, n_img;
+  int TX, TY, TZ, PX, PY;
+  int tiles_x, tiles_y, tiles_z;
+  int halo;
+  int mt, NT, n_kchunks, src_cbt, stages, n_ntiles;
+  uint32_t stage_bytes, w_bytes, plane_bytes, a_tx_bytes, tmem_cols;
+  uint32_t w_off, a_off;  // smem offsets (from the 128-aligned base)
+  int out_mode, out_channels, dst_cbt, dst_cb_off, dst_lo_off;
+  int desc_swap;
+  const uint8_t* W;
+  const float* bias;
+  void* dst;
+  float* stats;
+  int16_t a_cb[MMSEG_MAX_KCHUNKS];
+};
+
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 192;
+// smem header: barriers + tmem pointer + stats scratch
+struct __align__(16) SmemHeader {
+  uint64_t a_full[kMaxStages];
+  uint64_t a_empty[kMaxStages];
+  uint64_t w_full[2];
+  uint64_t w_empty[2];
+  uint64_t acc_full;
+  uint32_t tmem_ptr;
+  uint32_t pad;
+  float red[4][32];
+};
+constexpr uint32_t kHeaderBytes = 1024;
+static_assert(sizeof(SmemHeader) <= kHeaderBytes, "header too large");
+
+__device__ __forceinline__ size_t blocked_off(int blk, int Z, int Y, int X, int z, int y, int x) {
+  return ((((size_t)blk * Z + z) * Y + y) * X + x) * 8;
+}
+
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]);
+  __nv_bfloat162 d = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 r;
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  r.z = *reinterpret_cast<uint32_t*>(&c);
+  r.w = *reinterpret_cast<uint32_t*>(&d);
+  return r;
+}
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  float h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat16 bh = __float2bfloat16_rn(v[i]);
+    h[i] = __bfloat162float(bh);
+    l[i] = v[i] - h[i];
+  }
+  hi = pack8_bf16(h);
+  lo = pack8_bf16(l);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t w_smem = smem_base + p.w_off;
+  const uint32_t a_smem = smem_base + p.a_off;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  int t = blockIdx.x;
+  const int tx = t % p.tiles_x; t /= p.tiles_x;
+  const int ty = t % p.tiles_y; t /= p.tiles_y;
+  const int tz = t % p.tiles_z;
+  const int img = t / p.tiles_z;
+  const int tile_in_img = blockIdx.x - img * (p.tiles_x * p.tiles_y * p.tiles_z);
+  const int nt = blockIdx.y;
+  const int x0 = tx * p.TX, y0 = ty * p.TY, z0 = tz * p.TZ;
+  const int n_planes = p.TZ + 2 * p.halo;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&hdr->a_full[s]), 1);
+      mbar_init(smem_u32(&hdr->a_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&hdr->w_full[s]), 1);
+      mbar_init(smem_u32(&hdr->w_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&hdr->acc_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmA);
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&hdr->tmem_ptr), p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int kc = 0; kc < p.n_kchunks; ++kc) {
+        const int ws = kc & 1;
+        const uint32_t wph = (kc >> 1) & 1;
+        const uint32_t wfull = smem_u32(&hdr->w_full[ws]);
+        mbar_wait(smem_u32(&hdr->w_empty[ws]), wph ^ 1);
+        mbar_arrive_expect_tx(wfull, p.w_bytes);
+        bulk_load_1d(w_smem + ws * p.w_bytes, p.W + ((size_t)nt * p.n_kchunks + kc) * p.w_bytes, p.w_bytes, wfull);
+        const int cb = img * p.src_cbt + p.a_cb[kc];
+        for (int pl = 0; pl < n_planes; ++pl) {
+          const int z = z0 - p.halo + pl;
+          if (z < 0 || z >= p.Z) continue;
+          const uint32_t afull = smem_u32(&hdr->a_full[stage]);
+          mbar_wait(smem_u32(&hdr->a_empty[stage]), ph ^ 1);
+          mbar_arrive_expect_tx(afull, p.a_tx_bytes);
+          tma_load_4d(a_smem + stage * p.stage_bytes, &tmA, afull, 2 * (x0 - p.halo), y0 - p.halo, z, cb);
+          if (++stage == p.stages) { stage = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.NT);
+      const uint32_t a_lbo = p.desc_swap ? 128u : p.plane_bytes;
+      const uint32_t a_sbo = p.desc_swap ? p.plane_bytes : 128u;
+      const uint32_t b_lbo = p.desc_swap ? 128u : (uint32_t)p.NT * 16u;
+      const uint32_t b_sbo = p.desc_swap ? (uint32_t)p.NT * 16u : 128u;
+      const uint64_t a_desc_hi = make_smem_desc(0, a_lbo, a_sbo);
+      const uint64_t b_desc_hi = make_smem_desc(0, b_lbo, b_sbo);
+      const int ktaps = p.halo ? 3 : 1;
+      uint32_t inited = 0;
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int kc = 0; kc < p.n_kchunks; ++kc) {
+        const int ws = kc & 1;
+        const uint32_t wph = (kc >> 1) & 1;
+        mbar_wait(smem_u32(&hdr->w_full[ws]), wph);
+        const uint32_t wb = w_smem + ws * p.w_bytes;
+        for (int pl = 0; pl < n_planes; ++pl) {
+          const int z = z0 - p.halo + pl;
+          if (z < 0 || z >= p.Z) continue;
+          mbar_wait(smem_u32(&hdr->a_full[stage]), ph);
+          tc_fence_after();
+          const uint32_t ab = a_smem + stage * p.stage_bytes;
+          for (int dz = 0; dz < ktaps; ++dz) {
+            const int zo = pl - dz;
+            if (zo < 0 || zo >= p.TZ || z0 + zo >= p.Z) continue;
+            for (int dy = 0; dy < ktaps; ++dy) {
+              for (int dx = 0; dx < ktaps; ++dx) {
+                const int tap = (dz * ktaps + dy) * ktaps + dx;
+                const uint64_t bdesc = b_desc_hi | (uint64_t)(((wb + (uint32_t)tap * p.NT * 32u) >> 4) & 0x3FFF);
+                const uint32_t arow = ab + (uint32_t)(dy * p.PX + dx) * 16u;
+                for (int m = 0; m < p.mt; ++m) {
+                  const int idx = zo * p.mt + m;
+                  const uint64_t adesc = a_desc_hi | (uint64_t)(((arow + (uint32_t)m * 2048u) >> 4) & 0x3FFF);
+                  umma_bf16(tmem_base + (uint32_t)(idx * p.NT), adesc, bdesc, idesc, (inited >> idx) & 1u);
+                  inited |= 1u << idx;
+                }
+              }
+            }
+          }
+          umma_commit(smem_u32(&hdr->a_empty[stage]));
+          if (++stage == p.stages) { stage = 0; ph ^= 1; }
+        }
+        umma_commit(smem_u32(&hdr->w_empty[ws]));
+      }
+      umma_commit(smem_u32(&hdr->acc_full));
+    }
+  } else {
+    // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+    const int q = warp & 3;
+    const int ew = warp - 2;
+    mbar_wait(smem_u32(&hdr->acc_full), 0);
+    tc_fence_after();
+    const int n_base = nt * p.NT;
+    const bool want_stats = p.stats != nullptr;
+    const int n_cg = p.NT / 16;
+    for (int cg = 0; cg < n_cg; ++cg) {
+      const int n0 = n_base + cg * 16;
+      float bias_v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) bias_v[i] = p.bias ? p.bias[n0 + i] : 0.f;
+      float s1[16], s2[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+      for (int zo = 0; zo < p.TZ; ++zo) {
+        const int z = z0 + zo;
+        if (z >= p.Z) break;
+        for (int m = 0; m < p.mt; ++m) {
+          const int L = m * 128 + q * 32 + lane;
+          const int yy = L / p.PX;
+          const int xx = L - yy * p.PX;
+          const int y = y0 + yy, x = x0 + xx;
+          const bool valid = (xx < p.TX) && (yy < p.TY) && (x < p.X) && (y < p.Y);
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((zo * p.mt + m) * p.NT + cg * 16), v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += bias_v[i];
+          if (valid) {
+            if (want_stats) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { s1[i] += v[i]; s2[i] = fmaf(v[i], v[i], s2[i]); }
+            }
+            if (p.out_mode == MMSEG_OUT_BLOCKED_BF16) {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst);
+              const int blk = img * p.dst_cbt + p.dst_cb_off + (n0 >> 3);
+              *reinterpret_cast<uint4*>(o + blocked_off(blk, p.Z, p.Y, p.X, z, y, x)) = pack8_bf16(v);
+              *reinterpret_cast<uint4*>(o + blocked_off(blk + 1, p.Z, p.Y, p.X, z, y, x)) = pack8_bf16(v + 8);
+            } else if (p.out_mode == MMSEG_OUT_BLOCKED_F32) {
+              float* o = reinterpret_cast<float*>(p.dst);
+              const int blk = img * p.dst_cbt + p.dst_cb_off + (n0 >> 3);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                float4* d = reinterpret_cast<float4*>(o + blocked_off(blk + h, p.Z, p.Y, p.X, z, y, x));
+                d[0] = make_float4(v[8 * h + 0], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3]);
+                d[1] = make_float4(v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]);
+              }
+            } else if (p.out_mode == MMSEG_OUT_BLOCKED_BF16_HILO) {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst);
+              const int blk = img * p.dst_cbt + p.dst_cb_off + (n0 >> 3);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint4 hi, lo;
+                split8(v + 8 * h, hi, lo);
+                *reinterpret_cast<uint4*>(o + blocked_off(blk + h, p.Z, p.Y, p.X, z, y, x)) = hi;
+                *reinterpret_cast<uint4*>(o + blocked_off(blk + h + p.dst_lo_off, p.Z, p.Y, p.X, z, y, x)) = lo;
+              }
+            } else if (p.out_mode == MMSEG_OUT_CONVT_K2S2) {
+              // column n = tap * out_channels + co; tap = (a, b, c) offsets inside the 2x2x2 output cell
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst);
+              const int tap = n0 / p.out_channels;
+              const int co = n0 - tap * p.out_channels;
+              const int oz = 2 * z + (tap >> 2), oy = 2 * y + ((tap >> 1) & 1), ox = 2 * x + (tap & 1);
+              const int blk = img * p.dst_cbt + p.dst_cb_off + (co >> 3);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const size_t off = blocked_off(blk + h, 2 * p.Z, 2 * p.Y, 2 * p.X, oz, oy, ox);
+                if (p.dst_lo_off > 0) {
+                  uint4 hi, lo;
+                  split8(v + 8 * h, hi, lo);
+                  *reinterpret_cast<uint4*>(o + off) = hi;
+                  *reinterpret_cast<uint4*>(o + blocked_off(blk + h + p.dst_lo_off, 2 * p.Z, 2 * p.Y, 2 * p.X, oz, oy, ox)) = lo;
+                } else {
+                  *reinterpret_cast<uint4*>(o + off) = pack8_bf16(v + 8 * h);
+                }
+              }
+            } else {  // MMSEG_OUT_NCDHW_F32
+              float* o = reinterpret_cast<float*>(p.dst);
+              const size_t vox = ((size_t)z * p.Y + y) * p.X + x;
+              const size_t nvox = (size_t)p.Z * p.Y * p.X;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                if (n0 + i < p.out_channels) o[((size_t)img * p.out_channels + n0 + i) * nvox + vox] = v[i];
+              }
+            }
+          }
+        }
+      }
+      if (want_stats) {
+        // lanes -> one value per lane pair of arrays; 4 warps -> smem -> fixed-order sum -> global partial
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
+            s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+          }
+        }
+        named_bar_sync(1, 128);  // previous column group's readers are done with hdr->red
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { hdr->red[ew][i] = s1[i]; hdr->red[ew][16 + i] = s2[i]; }
+        }
+        named_bar_sync(1, 128);
+        if (ew == 0) {
+          const float tot = hdr->red[0][lane] + hdr->red[1][lane] + hdr->red[2][lane] + hdr->red[3][lane];
+          const int ch = n0 + (lane & 15);
+          const int C = p.n_ntiles * p.NT;
+          const size_t tiles_per_img = (size_t)p.tiles_x * p.tiles_y * p.tiles_z;
+          float* dstp = p.stats + (((size_t)img * tiles_per_img + tile_in_img) * C + ch) * 2 + (lane >> 4);
+          *dstp = tot;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_encodeTiled>(f);
+    }
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+static inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+struct ConvPlan {
+  ConvKParams k;
+  uint32_t smem_bytes;
+};
+
+static int plan_conv(const mmseg_conv_args* a, ConvPlan* out) {
+  if (!a) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: null args");
+  if (a->ksize != 1 && a->ksize != 3) return fail(MMSEG_ERR_UNSUPPORTED, "conv3d: ksize %d (only 1, 3)", a->ksize);
+  if (a->n_img < 1 || a->X < 1 || a->Y < 1 || a->Z < 1) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: bad extents");
+  if (a->NT < 16 || a->NT > 256 || (a->NT % 16)) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: NT=%d must be a multiple of 16 in [16,256]", a->NT);
+  if (a->n_ntiles < 1) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: n_ntiles");
+  if (a->n_kchunks < 1 || a->n_kchunks > MMSEG_MAX_KCHUNKS) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: n_kchunks=%d", a->n_kchunks);
+  if (a->TX < 1 || a->TY < 1 || a->TZ < 1) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: bad tile");
+  if (a->stages < 2 || a->stages > kMaxStages) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: stages=%d", a->stages);
+  if (a->out_mode < 0 || a->out_mode > MMSEG_OUT_NCDHW_F32) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: out_mode");
+  if (a->out_mode == MMSEG_OUT_CONVT_K2S2 && (a->out_channels % 16)) return fail(MMSEG_ERR_UNSUPPORTED, "convT: out_channels must be a multiple of 16");
+  if (a->out_mode == MMSEG_OUT_CONVT_K2S2 && a->ksize != 1) return fail(MMSEG_ERR_INVALID_ARG, "convT runs as ksize 1");
+  for (int i = 0; i < a->n_kchunks; ++i)
+    if (a->a_cb[i] < 0 || a->a_cb[i] + 2 > a->src_cbt) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: a_cb[%d]=%d outside src_cbt=%d", i, a->a_cb[i], a->src_cbt);
+  ConvKParams& k = out->k;
+  k.X = a->X; k.Y = a->Y; k.Z = a->Z; k.n_img = a->n_img;
+  k.halo = a->ksize / 2;
+  k.TX = a->TX; k.TY = a->TY; k.TZ = a->TZ;
+  k.PX = a->TX + 2 * k.halo; k.PY = a->TY + 2 * k.halo;
+  if (k.PX > 128) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: TX+halo=%d > 128 (TMA box limit)", k.PX);
+  if (k.PY > 256) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: TY too large");
+  k.tiles_x = (a->X + a->TX - 1) / a->TX;
+  k.tiles_y = (a->Y + a->TY - 1) / a->TY;
+  k.tiles_z = (a->Z + a->TZ - 1) / a->TZ;
+  const int flat = (a->TY - 1) * k.PX + a->TX;
+  k.mt = (flat + 127) / 128;
+  const int n_acc = k.mt * a->TZ;
+  if (n_acc > 32) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: %d accumulators > 32", n_acc);
+  const int cols = n_acc * a->NT;
+  if (cols > 512) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: %d TMEM columns > 512", cols);
+  uint32_t tc = 32;
+  while ((int)tc < cols) tc <<= 1;
+  k.tmem_cols = tc;
+  k.NT = a->NT; k.n_ntiles = a->n_ntiles; k.n_kchunks = a->n_kchunks; k.src_cbt = a->src_cbt; k.stages = a->stages;
+  const int taps = a->ksize * a->ksize * a->ksize;
+  k.w_bytes = (uint32_t)taps * a->NT * 32u;
+  k.plane_bytes = (uint32_t)k.PX * k.PY * 16u;
+  if ((k.plane_bytes >> 4) > 0x3FFF) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: plane too large for LBO");
+  k.a_tx_bytes = 2u * k.plane_bytes;
+  k.stage_bytes = round_up(k.a_tx_bytes, 128);
+  const uint32_t rows_needed = (uint32_t)(k.mt * 128 + 2 * k.halo * k.PX + 2 * k.halo);
+  const uint32_t overflow = rows_needed * 16u > k.plane_bytes ? rows_needed * 16u - k.plane_bytes : 0u;
+  k.w_off = kHeaderBytes;
+  k.a_off = k.w_off + 2 * round_up(k.w_bytes, 128);
+  const uint32_t total = k.a_off + a->stages * k.stage_bytes + round_up(overflow, 128) + 128 /*align slack*/;
+  if (total > 227u * 1024u) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: %u bytes of shared memory > 227 KB", total);
+  if (k.w_bytes >= (1u << 20) || k.a_tx_bytes >= (1u << 20)) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: tx bytes");
+  out->smem_bytes = total;
+  k.out_mode = a->out_mode; k.out_channels = a->out_channels;
+  k.dst_cbt = a->dst_cbt; k.dst_cb_off = a->dst_cb_off; k.dst_lo_off = a->dst_lo_off;
+  k.desc_swap = a->flags & 1;
+  k.W = reinterpret_cast<const uint8_t*>(a->weights); k.bias = a->bias; k.dst = a->dst; k.stats = a->stats_partial;
+  for (int i = 0; i < MMSEG_MAX_KCHUNKS; ++i) k.a_cb[i] = i < a->n_kchunks ? a->a_cb[i] : 0;
+  return MMSEG_OK;
+}
+
+}  // namespace mmseg
+
+using namespace mmseg;
+
+extern "C" int64_t mmseg_conv3d_smem_bytes(const mmseg_conv_args* a) {
+  ConvPlan pl;
+  int rc = plan_conv(a, &pl);
+  if (rc != MMSEG_OK) return rc;
+  return pl.smem_bytes;
+}
+
+extern "C" int32_t mmseg_conv3d_tiles_per_img(const mmseg_conv_args* a) {
+  ConvPlan pl;
+  int rc = plan_conv(a, &pl);
+  if (rc != MMSEG_OK) return rc;
+  return pl.k.tiles_x * pl.k.tiles_y * pl.k.tiles_z;
+}
+
+extern "C" int mmseg_conv3d_fwd(const mmseg_conv_args* a, void* stream) {
+  ConvPlan pl;
+  int rc = plan_conv(a, &pl);
+  if (rc != MMSEG_OK) return rc;
+  if (!a->src || !a->weights || !a->dst) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: null pointer");
+  if ((reinterpret_cast<uintptr_t>(a->src) & 15) || (reinterpret_cast<uintptr_t>(a->weights) & 15) ||
+      (reinterpret_cast<uintptr_t>(a->dst) & 15))
+    return fail(MMSEG_ERR_INVALID_ARG, "conv3d: pointers must be 16-byte aligned");
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return fail(MMSEG_ERR_NO_DRIVER, "conv3d: cuTensorMapEncodeTiled unavailable (no CUDA driver)");
+  const ConvKParams& k = pl.k;
+  CUtensorMap tm;
+  // activations viewed as 8-byte elements: dim0 = 2*X (one voxel's 8 bf16 channels = 2 elements)
+  cuuint64_t dims[4] = {(cuuint64_t)2 * k.X, (cuuint64_t)k.Y, (cuuint64_t)k.Z, (cuuint64_t)k.n_img * k.src_cbt};
+  cuuint64_t strides[3] = {(cuuint64_t)k.X * 16, (cuuint64_t)k.X * k.Y * 16, (cuuint64_t)k.X * k.Y * k.Z * 16};
+  cuuint32_t box[4] = {(cuuint32_t)(2 * k.PX), (cuuint32_t)k.PY, 1, 2};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(a->src), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(MMSEG_ERR_CUDA, "conv3d: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return fail(MMSEG_ERR_CUDA, "conv3d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(k.tiles_x * k.tiles_y * k.tiles_z * k.n_img), (unsigned)k.n_ntiles);
+  conv3d_tc_kernel<<<grid, kThreads, pl.smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tm, k);
+  return check_launch("conv3d_tc_kernel");
+}

@@ -1,0 +1,139 @@
+// One-pass DiceCE forward: read logits + labels once, per-voxel softmax in registers, per-(batch, class) sums of
+// p, p*onehot, onehot and the (weighted) negative log-likelihood; deterministic two-stage reduction (no atomics).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mmseg {
+
+constexpr int kMaxC = 16;
+
+// grid: (n_blocks, B).  partial layout per (b, block): [3*C + 2] = I[c], P[c], T[c], nll_sum, weight_sum
+template <int C>
+__global__ void __launch_bounds__(256)
+dicece_partial_kernel(const float* __restrict__ logits, const long long* __restrict__ target, size_t N,
+                      const float* __restrict__ cw, float* __restrict__ partial) {
+  const int b = blockIdx.y;
+  const float* lg = logits + (size_t)b * C * N;
+  const long long* tg = target + (size_t)b * N;
+  float aI[C], aP[C], aT[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) { aI[c] = 0.f; aP[c] = 0.f; aT[c] = 0.f; }
+  float nll = 0.f, wsum = 0.f;
+  for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (size_t)gridDim.x * blockDim.x) {
+    float z[C];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { z[c] = lg[(size_t)c * N + n]; mx = fmaxf(mx, z[c]); }
+    const int t = (int)tg[n];
+    float se = 0.f, zt = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float e = expf(z[c] - mx);
+      if (c == t) zt = z[c] - mx;
+      z[c] = e;
+      se += e;
+    }
+    const float inv = 1.f / se;
+    const float w = cw ? cw[t] : 1.f;
+    nll += w * (logf(se) - zt);
+    wsum += w;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float p = z[c] * inv;
+      aP[c] += p;
+      if (c == t) { aI[c] += p; aT[c] += 1.f; }
+    }
+  }
+  __shared__ float red[8][3 * C + 2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      aI[c] += __shfl_xor_sync(0xffffffffu, aI[c], o);
+      aP[c] += __shfl_xor_sync(0xffffffffu, aP[c], o);
+      aT[c] += __shfl_xor_sync(0xffffffffu, aT[c], o);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nll += __shfl_xor_sync(0xffffffffu, nll, o);
+    wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) { red[warp][c] = aI[c]; red[warp][C + c] = aP[c]; red[warp][2 * C + c] = aT[c]; }
+    red[warp][3 * C] = nll;
+    red[warp][3 * C + 1] = wsum;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 * C + 2) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    partial[((size_t)b * gridDim.x + blockIdx.x) * (3 * C + 2) + threadIdx.x] = s;
+  }
+}
+
+// single block: fixed-order fp64 reduction over blocks, then the loss.
+__global__ void dicece_final_kernel(const float* __restrict__ partial, int B, int C, int n_blocks, float dice_w,
+                                    float ce_w, float smooth, int include_bg, float* __restrict__ result) {
+  __shared__ double acc[4 * (3 * kMaxC + 2)];  // B <= 4 per pass handled by loop below
+  __shared__ double dice_sum, nll_sum, w_sum;
+  const int stride = 3 * C + 2;
+  if (threadIdx.x == 0) { dice_sum = 0.0; nll_sum = 0.0; w_sum = 0.0; }
+  __syncthreads();
+  for (int b = 0; b < B; ++b) {
+    if (threadIdx.x < stride) {
+      double s = 0.0;
+      for (int k = 0; k < n_blocks; ++k) s += (double)partial[((size_t)b * n_blocks + k) * stride + threadIdx.x];
+      acc[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int c = include_bg ? 0 : 1; c < C; ++c) {
+        const double I = acc[c], P = acc[C + c], T = acc[2 * C + c];
+        dice_sum += 1.0 - (2.0 * I + smooth) / (P + T + smooth);
+      }
+      nll_sum += acc[3 * C];
+      w_sum += acc[3 * C + 1];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int nc = include_bg ? C : C - 1;
+    const double dice = dice_sum / (double)(B * nc);
+    const double ce = nll_sum / w_sum;
+    result[0] = (float)(dice_w * dice + ce_w * ce);
+    result[1] = (float)dice;
+    result[2] = (float)ce;
+  }
+}
+
+}  // namespace mmseg
+
+using namespace mmseg;
+
+extern "C" int mmseg_dicece_fwd(const float* logits, const int64_t* target, int32_t B, int32_t C, int64_t N,
+                                float dice_weight, float ce_weight, float smooth, int32_t include_background,
+                                const float* class_weights, float* partial, int32_t n_blocks, float* result,
+                                void* stream) {
+  if (!logits || !target || !partial || !result || B < 1 || N < 1 || n_blocks < 1 || n_blocks > 65535)
+    return fail(MMSEG_ERR_INVALID_ARG, "dicece_fwd: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(n_blocks, B);
+  const long long* tg = reinterpret_cast<const long long*>(target);
+  switch (C) {
+    case 2: dicece_partial_kernel<2><<<grid, 256, 0, st>>>(logits, tg, (size_t)N, class_weights, partial); break;
+    case 3: dicece_partial_kernel<3><<<grid, 256, 0, st>>>(logits, tg, (size_t)N, class_weights, partial); break;
+    case 4: dicece_partial_kernel<4><<<grid, 256, 0, st>>>(logits, tg, (size_t)N, class_weights, partial); break;
+    case 8: dicece_partial_kernel<8><<<grid, 256, 0, st>>>(logits, tg, (size_t)N, class_weights, partial); break;
+    case 16: dicece_partial_kernel<16><<<grid, 256, 0, st>>>(logits, tg, (size_t)N, class_weights, partial); break;
+    default: return fail(MMSEG_ERR_UNSUPPORTED, "dicece_fwd: C=%d (supported: 2,3,4,8,16)", C);
+  }
+  int rc = check_launch("dicece_partial_kernel");
+  if (rc != MMSEG_OK) return rc;
+  dicece_final_kernel<<<1, 64, 0, st>>>(partial, B, C, n_blocks, dice_weight, ce_weight, smooth, include_background,
+                                        result);
+  return check_launch("dicece_final_kernel");
+}

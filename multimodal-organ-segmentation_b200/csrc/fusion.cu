@@ -1,0 +1,258 @@
+// Modality fusion kernels for DualEncoder: per-channel global average pool (deterministic two-stage), the SE-style
+// gate MLP + softmax over modalities, the weighted sum over modalities (mean / add / gate), and a stand-alone
+// MaxPool3d(2) on blocked tensors.  All HBM-bound, 16-byte vectors.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mmseg {
+
+int num_sms();
+
+__device__ __forceinline__ void ld8_bf16(const __nv_bfloat16* p, float* v) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ uint4 pk8(const float* v) {
+  uint4 r;
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+  r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
+  r.z = *reinterpret_cast<uint32_t*>(&c); r.w = *reinterpret_cast<uint32_t*>(&d);
+  return r;
+}
+__device__ __forceinline__ void st8_act(__nv_bfloat16* dst, size_t off, size_t lo_delta, const float* y) {
+  if (lo_delta == 0) {
+    *reinterpret_cast<uint4*>(dst + off) = pk8(y);
+  } else {
+    float h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      h[i] = __bfloat162float(__float2bfloat16_rn(y[i]));
+      l[i] = y[i] - h[i];
+    }
+    *reinterpret_cast<uint4*>(dst + off) = pk8(h);
+    *reinterpret_cast<uint4*>(dst + off + lo_delta) = pk8(l);
+  }
+}
+
+// grid (n_chunks, n_img*cb): per-chunk partial sums of 8 channels -> partial[(blk*n_chunks + chunk)*8 + i]
+__global__ void __launch_bounds__(256)
+channel_sum_partial_kernel(const __nv_bfloat16* __restrict__ src, int src_cbt, int cb_off, int lo_off, int cb,
+                           size_t nvox, float* __restrict__ partial) {
+  const int blk = blockIdx.y;
+  const int img = blk / cb, c = blk - img * cb;
+  const size_t base = (size_t)(img * src_cbt + cb_off + c) * nvox * 8;
+  const size_t lo_delta = (size_t)lo_off * nvox * 8;
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
+    float x[8];
+    ld8_bf16(src + base + v * 8, x);
+    if (lo_delta) {
+      float l[8];
+      ld8_bf16(src + base + lo_delta + v * 8, l);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] += l[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] += x[i];
+  }
+  __shared__ float red[8][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[warp][i] = s[i];
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    partial[((size_t)blk * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = t;
+  }
+}
+
+__global__ void channel_mean_final_kernel(const float* __restrict__ partial, int n_rows /*n_img*cb*/, int n_chunks,
+                                          double inv_n, float* __restrict__ mean) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over n_rows*8
+  if (idx >= n_rows * 8) return;
+  const int blk = idx >> 3, i = idx & 7;
+  double s = 0.0;
+  for (int k = 0; k < n_chunks; ++k) s += (double)partial[((size_t)blk * n_chunks + k) * 8 + i];
+  mean[idx] = (float)(s * inv_n);
+}
+
+// one block per image: h = relu(W1 p + b1); logits = W2 h + b2; softmax over M  (reference dual_encoder.py:226-254)
+__global__ void gate_mlp_kernel(const float* __restrict__ pooled, const float* __restrict__ w1,
+                                const float* __restrict__ b1, const float* __restrict__ w2,
+                                const float* __restrict__ b2, int MC, int H, int M, float* __restrict__ weights) {
+  extern __shared__ float sh[];  // H hidden + M logits
+  float* hid = sh;
+  float* lg = sh + H;
+  const int img = blockIdx.x;
+  const float* p = pooled + (size_t)img * MC;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    float acc = b1[j];
+    const float* w = w1 + (size_t)j * MC;
+    for (int k = 0; k < MC; ++k) acc = fmaf(w[k], p[k], acc);
+    hid[j] = acc > 0.f ? acc : 0.f;
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    float acc = b2[m];
+    const float* w = w2 + (size_t)m * H;
+    for (int k = 0; k < H; ++k) acc = fmaf(w[k], hid[k], acc);
+    lg[m] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mx = -INFINITY;
+    for (int m = 0; m < M; ++m) mx = fmaxf(mx, lg[m]);
+    float se = 0.f;
+    for (int m = 0; m < M; ++m) se += expf(lg[m] - mx);
+    for (int m = 0; m < M; ++m) weights[(size_t)img * M + m] = expf(lg[m] - mx) / se;
+  }
+}
+
+// dst[b, c] = sum_m w[b, m] * src[b, m*cb + c]; grid (chunks, n_img*cb)
+__global__ void __launch_bounds__(256)
+modality_combine_kernel(const __nv_bfloat16* __restrict__ src, int src_cbt, int src_lo_off, int M, int cb, size_t nvox,
+                        const float* __restrict__ weights, float uniform_w, __nv_bfloat16* __restrict__ dst,
+                        int dst_cbt, int dst_cb_off, int dst_lo_off) {
+  const int blk = blockIdx.y;
+  const int img = blk / cb, c = blk - img * cb;
+  const size_t src_lo = (size_t)src_lo_off * nvox * 8;
+  const size_t dst_base = (size_t)(img * dst_cbt + dst_cb_off + c) * nvox * 8;
+  const size_t dst_lo = (size_t)dst_lo_off * nvox * 8;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int m = 0; m < M; ++m) {
+      const float w = weights ? weights[(size_t)img * M + m] : uniform_w;
+      const size_t base = (size_t)(img * src_cbt + m * cb + c) * nvox * 8 + v * 8;
+      float x[8];
+      ld8_bf16(src + base, x);
+      if (src_lo) {
+        float l[8];
+        ld8_bf16(src + base + src_lo, l);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] += l[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, x[i], acc[i]);
+    }
+    st8_act(dst, dst_base + v * 8, dst_lo, acc);
+  }
+}
+
+// MaxPool3d(2) on a blocked tensor (stand-alone DownBlock3D use); grid (chunks, n_img*cb)
+__global__ void __launch_bounds__(256)
+maxpool2_kernel(const __nv_bfloat16* __restrict__ src, int src_cbt, int src_cb_off, int src_lo_off, int cb, int Z, int Y,
+                int X, __nv_bfloat16* __restrict__ dst, int dst_cbt, int dst_cb_off, int dst_lo_off) {
+  const int blk = blockIdx.y;
+  const int img = blk / cb, c = blk - img * cb;
+  const int Zh = Z / 2, Yh = Y / 2, Xh = X / 2;
+  const size_t nvox = (size_t)Z * Y * X, ncell = (size_t)Zh * Yh * Xh;
+  const size_t sbase = (size_t)(img * src_cbt + src_cb_off + c) * nvox * 8;
+  const size_t slo = (size_t)src_lo_off * nvox * 8;
+  const size_t dbase = (size_t)(img * dst_cbt + dst_cb_off + c) * ncell * 8;
+  const size_t dlo = (size_t)dst_lo_off * ncell * 8;
+  for (size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x; cell < ncell;
+       cell += (size_t)gridDim.x * blockDim.x) {
+    const int xh = (int)(cell % Xh);
+    const size_t r = cell / Xh;
+    const int yh = (int)(r % Yh), zh = (int)(r / Yh);
+    float mx[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
+    for (int d = 0; d < 8; ++d) {
+      const size_t v = ((size_t)(2 * zh + (d >> 2)) * Y + (2 * yh + ((d >> 1) & 1))) * X + (2 * xh + (d & 1));
+      float x[8];
+      ld8_bf16(src + sbase + v * 8, x);
+      if (slo) {
+        float l[8];
+        ld8_bf16(src + sbase + slo + v * 8, l);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] += l[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], x[i]);
+    }
+    st8_act(dst, dbase + cell * 8, dlo, mx);
+  }
+}
+
+static unsigned gx_for(size_t items, int rows) {
+  size_t want = ((size_t)num_sms() * 8 + rows - 1) / rows;
+  size_t need = (items + 255) / 256;
+  size_t g = want < need ? want : need;
+  return (unsigned)(g < 1 ? 1 : g);
+}
+
+}  // namespace mmseg
+
+using namespace mmseg;
+
+extern "C" int mmseg_channel_mean(const void* src, int32_t n_img, int32_t src_cbt, int32_t cb_off, int32_t lo_off,
+                                  int32_t cb, int64_t voxels, float* partial, int32_t n_chunks, float* mean,
+                                  void* stream) {
+  if (!src || !partial || !mean || n_img < 1 || cb < 1 || voxels < 1 || n_chunks < 1)
+    return fail(MMSEG_ERR_INVALID_ARG, "channel_mean: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(n_chunks, n_img * cb);
+  channel_sum_partial_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), src_cbt, cb_off,
+                                                   lo_off, cb, (size_t)voxels, partial);
+  int rc = check_launch("channel_sum_partial_kernel");
+  if (rc) return rc;
+  const int n = n_img * cb * 8;
+  channel_mean_final_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, n_img * cb, n_chunks, 1.0 / (double)voxels, mean);
+  return check_launch("channel_mean_final_kernel");
+}
+
+extern "C" int mmseg_gate_mlp(const float* pooled, const float* w1, const float* b1, const float* w2, const float* b2,
+                              int32_t n_img, int32_t MC, int32_t H, int32_t M, float* weights, void* stream) {
+  if (!pooled || !w1 || !b1 || !w2 || !b2 || !weights || n_img < 1 || MC < 1 || H < 1 || M < 1)
+    return fail(MMSEG_ERR_INVALID_ARG, "gate_mlp: bad arguments");
+  const size_t sh = (size_t)(H + M) * sizeof(float);
+  if (sh > 48 * 1024) return fail(MMSEG_ERR_UNSUPPORTED, "gate_mlp: hidden size too large");
+  gate_mlp_kernel<<<n_img, 256, sh, reinterpret_cast<cudaStream_t>(stream)>>>(pooled, w1, b1, w2, b2, MC, H, M, weights);
+  return check_launch("gate_mlp_kernel");
+}
+
+extern "C" int mmseg_modality_combine(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_lo_off, int32_t M,
+                                      int32_t cb, int64_t voxels, const float* weights, float uniform_weight, void* dst,
+                                      int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, void* stream) {
+  if (!src || !dst || n_img < 1 || M < 1 || cb < 1 || voxels < 1)
+    return fail(MMSEG_ERR_INVALID_ARG, "modality_combine: bad arguments");
+  const int rows = n_img * cb;
+  dim3 grid(gx_for((size_t)voxels, rows), rows);
+  modality_combine_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), src_cbt, src_lo_off, M, cb, (size_t)voxels, weights, uniform_weight,
+      reinterpret_cast<__nv_bfloat16*>(dst), dst_cbt, dst_cb_off, dst_lo_off);
+  return check_launch("modality_combine_kernel");
+}
+
+extern "C" int mmseg_maxpool3d_2(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_cb_off,
+                                 int32_t src_lo_off, int32_t cb, int32_t Z, int32_t Y, int32_t X, void* dst,
+                                 int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, void* stream) {
+  if (!src || !dst || n_img < 1 || cb < 1 || Z < 2 || Y < 2 || X < 2)
+    return fail(MMSEG_ERR_INVALID_ARG, "maxpool3d_2: bad arguments");
+  const size_t ncell = (size_t)(Z / 2) * (Y / 2) * (X / 2);
+  const int rows = n_img * cb;
+  dim3 grid(gx_for(ncell, rows), rows);
+  maxpool2_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), src_cbt, src_cb_off, src_lo_off, cb, Z, Y, X,
+      reinterpret_cast<__nv_bfloat16*>(dst), dst_cbt, dst_cb_off, dst_lo_off);
+  return check_launch("maxpool2_kernel");
+}

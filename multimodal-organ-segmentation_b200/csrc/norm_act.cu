@@ -1,0 +1,287 @@
+// InstanceNorm3d statistics finalize + fused normalise / activation / (MaxPool3d(2)) apply, and the NCDHW <-> blocked
+// layout converters at the module boundary.  All HBM-bound: 16-byte vector accesses, grid sized from the SM count.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mmseg {
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+// ---------------------------------------------------------------------------------------------- finalize
+// one thread per (img, channel): fixed-order fp64 sum over the conv CTAs' partials -> mean, rstd
+__global__ void instnorm_finalize_kernel(const float* __restrict__ part, int n_img, int tiles, int C, double inv_n,
+                                         float eps, float* __restrict__ mean_rstd) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_img * C) return;
+  const int img = idx / C, c = idx - img * C;
+  const float* p = part + ((size_t)img * tiles * C + c) * 2;
+  double s1 = 0.0, s2 = 0.0;
+  for (int t = 0; t < tiles; ++t) {
+    const float2 v = *reinterpret_cast<const float2*>(p + (size_t)t * C * 2);
+    s1 += (double)v.x;
+    s2 += (double)v.y;
+  }
+  const double mean = s1 * inv_n;
+  double var = s2 * inv_n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  mean_rstd[2 * idx] = (float)mean;
+  mean_rstd[2 * idx + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ---------------------------------------------------------------------------------------------- apply
+struct NormK {
+  const void* src;
+  const float* mr;
+  __nv_bfloat16* dst;
+  __nv_bfloat16* pooled;
+  int n_img, cb, Z, Y, X;
+  int dst_cbt, dst_cb_off, dst_lo_off;
+  int pool_cbt, pool_cb_off, pool_lo_off;
+  float slope;
+};
+
+template <bool F32>
+__device__ __forceinline__ void load8(const void* base, size_t elem_off, float* v) {
+  if (F32) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off);
+    const float4 a = p[0], b = p[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+}
+
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 r;
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+  r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
+  r.z = *reinterpret_cast<uint32_t*>(&c); r.w = *reinterpret_cast<uint32_t*>(&d);
+  return r;
+}
+
+__device__ __forceinline__ void store_act8(__nv_bfloat16* dst, size_t off, size_t lo_delta, const float* y) {
+  if (lo_delta == 0) {
+    *reinterpret_cast<uint4*>(dst + off) = pack8(y);
+  } else {
+    float h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      h[i] = __bfloat162float(__float2bfloat16_rn(y[i]));
+      l[i] = y[i] - h[i];
+    }
+    *reinterpret_cast<uint4*>(dst + off) = pack8(h);
+    *reinterpret_cast<uint4*>(dst + off + lo_delta) = pack8(l);
+  }
+}
+
+// grid: (chunks over voxels, n_img*cb).  One 8-channel vector per thread-iteration.
+template <bool F32>
+__global__ void __launch_bounds__(256) instnorm_apply_kernel(const NormK k) {
+  const int blk = blockIdx.y;  // img*cb + c
+  const int img = blk / k.cb, c = blk - img * k.cb;
+  float mean[8], rstd[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 m = *reinterpret_cast<const float2*>(k.mr + ((size_t)img * k.cb * 8 + c * 8 + i) * 2);
+    mean[i] = m.x;
+    rstd[i] = m.y;
+  }
+  const size_t nvox = (size_t)k.Z * k.Y * k.X;
+  const size_t src_base = (size_t)blk * nvox * 8;
+  const size_t dst_base = (size_t)(img * k.dst_cbt + k.dst_cb_off + c) * nvox * 8;
+  const size_t lo_delta = (size_t)k.dst_lo_off * nvox * 8;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
+    float x[8];
+    load8<F32>(k.src, src_base + v * 8, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float y = (x[i] - mean[i]) * rstd[i];
+      x[i] = y > 0.f ? y : y * k.slope;
+    }
+    store_act8(k.dst, dst_base + v * 8, lo_delta, x);
+  }
+}
+
+// Variant that also emits MaxPool3d(2): one 2x2x2 cell per thread-iteration (Z, Y, X even).
+template <bool F32>
+__global__ void __launch_bounds__(256) instnorm_apply_pool_kernel(const NormK k) {
+  const int blk = blockIdx.y;
+  const int img = blk / k.cb, c = blk - img * k.cb;
+  float mean[8], rstd[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 m = *reinterpret_cast<const float2*>(k.mr + ((size_t)img * k.cb * 8 + c * 8 + i) * 2);
+    mean[i] = m.x;
+    rstd[i] = m.y;
+  }
+  const int Zh = k.Z / 2, Yh = k.Y / 2, Xh = k.X / 2;
+  const size_t nvox = (size_t)k.Z * k.Y * k.X;
+  const size_t ncell = (size_t)Zh * Yh * Xh;
+  const size_t src_base = (size_t)blk * nvox * 8;
+  const size_t dst_base = (size_t)(img * k.dst_cbt + k.dst_cb_off + c) * nvox * 8;
+  const size_t lo_delta = (size_t)k.dst_lo_off * nvox * 8;
+  const size_t pool_base = (size_t)(img * k.pool_cbt + k.pool_cb_off + c) * ncell * 8;
+  const size_t pool_lo = (size_t)k.pool_lo_off * ncell * 8;
+  for (size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x; cell < ncell;
+       cell += (size_t)gridDim.x * blockDim.x) {
+    const int xh = (int)(cell % Xh);
+    const size_t r = cell / Xh;
+    const int yh = (int)(r % Yh);
+    const int zh = (int)(r / Yh);
+    float mx[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const size_t v = ((size_t)(2 * zh + dz) * k.Y + (2 * yh + dy)) * k.X + (2 * xh + dx);
+          float x[8];
+          load8<F32>(k.src, src_base + v * 8, x);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float y = (x[i] - mean[i]) * rstd[i];
+            x[i] = y > 0.f ? y : y * k.slope;
+            mx[i] = fmaxf(mx[i], x[i]);
+          }
+          store_act8(k.dst, dst_base + v * 8, lo_delta, x);
+        }
+    store_act8(k.pooled, pool_base + cell * 8, pool_lo, mx);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- layout converters
+__global__ void __launch_bounds__(256)
+pack_ncdhw_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n_img, int C, size_t nvox,
+                  int dst_cbt, int dst_cb_off, int dst_lo_off, int cb) {
+  const int blk = blockIdx.y;  // img*cb + c
+  const int img = blk / cb, c = blk - img * cb;
+  const size_t dst_base = (size_t)(img * dst_cbt + dst_cb_off + c) * nvox * 8;
+  const size_t lo_delta = (size_t)dst_lo_off * nvox * 8;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ch = c * 8 + i;
+      x[i] = ch < C ? src[((size_t)img * C + ch) * nvox + v] : 0.f;
+    }
+    store_act8(dst, dst_base + v * 8, lo_delta, x);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+unpack_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int n_img, int C, size_t nvox,
+                    int src_cbt, int src_cb_off, int src_lo_off) {
+  const int cbn = (C + 7) / 8;
+  const int blk = blockIdx.y;
+  const int img = blk / cbn, c = blk - img * cbn;
+  const size_t src_base = (size_t)(img * src_cbt + src_cb_off + c) * nvox * 8;
+  const size_t lo_delta = (size_t)src_lo_off * nvox * 8;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
+    float x[8];
+    load8<false>(src, src_base + v * 8, x);
+    if (lo_delta) {
+      float l[8];
+      load8<false>(src, src_base + lo_delta + v * 8, l);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] += l[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ch = c * 8 + i;
+      if (ch < C) dst[((size_t)img * C + ch) * nvox + v] = x[i];
+    }
+  }
+}
+
+static unsigned grid_x_for(size_t items, int rows) {
+  // enough CTAs for ~8 resident per SM across all rows, never more than the work
+  size_t want = ((size_t)num_sms() * 8 + rows - 1) / rows;
+  size_t need = (items + 255) / 256;
+  size_t g = want < need ? want : need;
+  return (unsigned)(g < 1 ? 1 : g);
+}
+
+}  // namespace mmseg
+
+using namespace mmseg;
+
+extern "C" int mmseg_instnorm_finalize(const float* stats_partial, int32_t n_img, int32_t tiles_per_img,
+                                       int32_t channels, int64_t voxels, float eps, float* mean_rstd, void* stream) {
+  if (!stats_partial || !mean_rstd || n_img < 1 || tiles_per_img < 1 || channels < 1 || voxels < 1)
+    return fail(MMSEG_ERR_INVALID_ARG, "instnorm_finalize: bad arguments");
+  const int n = n_img * channels;
+  instnorm_finalize_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      stats_partial, n_img, tiles_per_img, channels, 1.0 / (double)voxels, eps, mean_rstd);
+  return check_launch("instnorm_finalize_kernel");
+}
+
+extern "C" int mmseg_instnorm_act_apply(const mmseg_norm_args* a, void* stream) {
+  if (!a || !a->src || !a->mean_rstd || !a->dst) return fail(MMSEG_ERR_INVALID_ARG, "instnorm_apply: null pointer");
+  if (a->n_img < 1 || a->cb < 1 || a->Z < 1 || a->Y < 1 || a->X < 1)
+    return fail(MMSEG_ERR_INVALID_ARG, "instnorm_apply: bad extents");
+  NormK k;
+  k.src = a->src; k.mr = a->mean_rstd;
+  k.dst = reinterpret_cast<__nv_bfloat16*>(a->dst);
+  k.pooled = reinterpret_cast<__nv_bfloat16*>(a->pooled);
+  k.n_img = a->n_img; k.cb = a->cb; k.Z = a->Z; k.Y = a->Y; k.X = a->X;
+  k.dst_cbt = a->dst_cbt; k.dst_cb_off = a->dst_cb_off; k.dst_lo_off = a->dst_lo_off;
+  k.pool_cbt = a->pool_cbt; k.pool_cb_off = a->pool_cb_off; k.pool_lo_off = a->pool_lo_off;
+  k.slope = a->slope;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int rows = a->n_img * a->cb;
+  if (a->pooled) {
+    if ((a->Z | a->Y | a->X) & 1) return fail(MMSEG_ERR_UNSUPPORTED, "instnorm_apply: fused MaxPool3d(2) needs even extents");
+    const size_t ncell = (size_t)(a->Z / 2) * (a->Y / 2) * (a->X / 2);
+    dim3 grid(grid_x_for(ncell, rows), rows);
+    if (a->src_is_f32) instnorm_apply_pool_kernel<true><<<grid, 256, 0, st>>>(k);
+    else instnorm_apply_pool_kernel<false><<<grid, 256, 0, st>>>(k);
+  } else {
+    const size_t nvox = (size_t)a->Z * a->Y * a->X;
+    dim3 grid(grid_x_for(nvox, rows), rows);
+    if (a->src_is_f32) instnorm_apply_kernel<true><<<grid, 256, 0, st>>>(k);
+    else instnorm_apply_kernel<false><<<grid, 256, 0, st>>>(k);
+  }
+  return check_launch("instnorm_apply_kernel");
+}
+
+extern "C" int mmseg_pack_ncdhw(const float* src, void* dst, int32_t n_img, int32_t C, int32_t Z, int32_t Y,
+                                int32_t X, int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, int32_t cb,
+                                void* stream) {
+  if (!src || !dst || n_img < 1 || C < 1 || cb * 8 < C) return fail(MMSEG_ERR_INVALID_ARG, "pack_ncdhw: bad arguments");
+  const size_t nvox = (size_t)Z * Y * X;
+  const int rows = n_img * cb;
+  dim3 grid(grid_x_for(nvox, rows), rows);
+  pack_ncdhw_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), n_img, C, nvox, dst_cbt, dst_cb_off, dst_lo_off, cb);
+  return check_launch("pack_ncdhw_kernel");
+}
+
+extern "C" int mmseg_unpack_ncdhw(const void* src, float* dst, int32_t n_img, int32_t C, int32_t Z, int32_t Y,
+                                  int32_t X, int32_t src_cbt, int32_t src_cb_off, int32_t src_lo_off, void* stream) {
+  if (!src || !dst || n_img < 1 || C < 1) return fail(MMSEG_ERR_INVALID_ARG, "unpack_ncdhw: bad arguments");
+  const size_t nvox = (size_t)Z * Y * X;
+  const int rows = n_img * ((C + 7) / 8);
+  dim3 grid(grid_x_for(nvox, rows), rows);
+  unpack_ncdhw_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), dst, n_img, C, nvox, src_cbt, src_cb_off, src_lo_off);
+  return check_launch("unpack_ncdhw_kernel");
+}

@@ -1,0 +1,145 @@
+// Sliding-window inference kernels: window gather (volume -> blocked bf16 batch), importance-weighted accumulation of
+// window logits into the output volume (owner-thread per voxel, windows applied in index order: deterministic and in
+// the same order as the reference loop), and the final normalise + argmax.  HBM-bound, coalesced along X.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mmseg {
+
+int num_sms();
+
+__device__ __forceinline__ uint4 pack8s(const float* v) {
+  uint4 r;
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+  r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
+  r.z = *reinterpret_cast<uint32_t*>(&c); r.w = *reinterpret_cast<uint32_t*>(&d);
+  return r;
+}
+
+// grid: (x-chunks, RZ*RY rows, n_win*cb)
+__global__ void __launch_bounds__(128)
+swi_gather_kernel(const float* __restrict__ vol, int C, int VZ, int VY, int VX, const int* __restrict__ starts,
+                  int RZ, int RY, int RX, __nv_bfloat16* __restrict__ dst, int dst_cbt, int dst_lo_off, int cb) {
+  const int wc = blockIdx.z;
+  const int win = wc / cb, c = wc - win * cb;
+  const int row = blockIdx.y;
+  const int lz = row / RY, ly = row - lz * RY;
+  const int sz = starts[win * 3 + 0], sy = starts[win * 3 + 1], sx = starts[win * 3 + 2];
+  const int gz = sz + lz, gy = sy + ly;
+  const bool row_in = (gz >= 0) && (gz < VZ) && (gy >= 0) && (gy < VY);
+  const size_t nvox_v = (size_t)VZ * VY * VX;
+  const size_t nvox_r = (size_t)RZ * RY * RX;
+  const size_t dst_base = ((size_t)(win * dst_cbt + c) * nvox_r + ((size_t)lz * RY + ly) * RX) * 8;
+  const size_t lo_delta = (size_t)dst_lo_off * nvox_r * 8;
+  for (int lx = blockIdx.x * blockDim.x + threadIdx.x; lx < RX; lx += gridDim.x * blockDim.x) {
+    const int gx = sx + lx;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ch = c * 8 + i;
+      v[i] = (row_in && gx >= 0 && gx < VX && ch < C)
+                 ? vol[(size_t)ch * nvox_v + ((size_t)gz * VY + gy) * VX + gx]
+                 : 0.f;
+    }
+    if (lo_delta == 0) {
+      *reinterpret_cast<uint4*>(dst + dst_base + (size_t)lx * 8) = pack8s(v);
+    } else {
+      float h[8], l[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        h[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+        l[i] = v[i] - h[i];
+      }
+      *reinterpret_cast<uint4*>(dst + dst_base + (size_t)lx * 8) = pack8s(h);
+      *reinterpret_cast<uint4*>(dst + dst_base + lo_delta + (size_t)lx * 8) = pack8s(l);
+    }
+  }
+}
+
+// One owner thread per output voxel of the box; loops over the batch's windows in index order.
+// seg*w and the accumulate are separate roundings (__fmul_rn / __fadd_rn) exactly like `seg *= w; out += seg`.
+__global__ void __launch_bounds__(128)
+swi_blend_kernel(const float* __restrict__ logits, const int* __restrict__ starts, int n_win, int K, int RZ, int RY,
+                 int RX, const float* __restrict__ wz, const float* __restrict__ wy, const float* __restrict__ wx,
+                 float w_floor, float* __restrict__ out, float* __restrict__ count, int VZ, int VY, int VX, int bz0,
+                 int by0, int bx0, int bx1, int by_n) {
+  const int row = blockIdx.y;
+  const int z = bz0 + row / by_n, y = by0 + row % by_n;
+  const size_t nvox_v = (size_t)VZ * VY * VX;
+  const size_t nvox_r = (size_t)RZ * RY * RX;
+  for (int x = bx0 + blockIdx.x * blockDim.x + threadIdx.x; x < bx1; x += gridDim.x * blockDim.x) {
+    const size_t vox = ((size_t)z * VY + y) * VX + x;
+    for (int j = 0; j < n_win; ++j) {
+      const int lz = z - starts[j * 3 + 0], ly = y - starts[j * 3 + 1], lx = x - starts[j * 3 + 2];
+      if (lz < 0 || lz >= RZ || ly < 0 || ly >= RY || lx < 0 || lx >= RX) continue;
+      const float w = fmaxf(__fmul_rn(__fmul_rn(wz[lz], wy[ly]), wx[lx]), w_floor);
+      const float* seg = logits + (size_t)j * K * nvox_r + ((size_t)lz * RY + ly) * RX + lx;
+      for (int c = 0; c < K; ++c) {
+        float* o = out + (size_t)c * nvox_v + vox;
+        *o = __fadd_rn(*o, __fmul_rn(seg[(size_t)c * nvox_r], w));
+      }
+      count[vox] = __fadd_rn(count[vox], w);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+swi_finalize_kernel(float* __restrict__ out, const float* __restrict__ count, int K, size_t nvox, int normalize,
+                    uint8_t* __restrict__ labels) {
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
+    const float cnt = count[v];
+    float best = -INFINITY;
+    int arg = 0;
+    for (int c = 0; c < K; ++c) {
+      const float q = __fdiv_rn(out[(size_t)c * nvox + v], cnt);
+      if (normalize) out[(size_t)c * nvox + v] = q;
+      if (q > best) { best = q; arg = c; }
+    }
+    if (labels) labels[v] = (uint8_t)arg;
+  }
+}
+
+}  // namespace mmseg
+
+using namespace mmseg;
+
+extern "C" int mmseg_swi_gather(const float* volume, int32_t C, int32_t VZ, int32_t VY, int32_t VX,
+                                const int32_t* starts_dev, int32_t n_win, int32_t RZ, int32_t RY, int32_t RX,
+                                void* dst, int32_t dst_cbt, int32_t dst_lo_off, int32_t cb, void* stream) {
+  if (!volume || !starts_dev || !dst || n_win < 1 || C < 1 || cb * 8 < C || RZ * RY > 65535 || n_win * cb > 65535)
+    return fail(MMSEG_ERR_INVALID_ARG, "swi_gather: bad arguments");
+  dim3 grid((RX + 127) / 128, RZ * RY, n_win * cb);
+  swi_gather_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      volume, C, VZ, VY, VX, starts_dev, RZ, RY, RX, reinterpret_cast<__nv_bfloat16*>(dst), dst_cbt, dst_lo_off, cb);
+  return check_launch("swi_gather_kernel");
+}
+
+extern "C" int mmseg_swi_blend(const float* win_logits, const int32_t* starts_dev, int32_t n_win, int32_t K,
+                               int32_t RZ, int32_t RY, int32_t RX, const float* wz, const float* wy, const float* wx,
+                               float w_floor, float* out, float* count, int32_t VZ, int32_t VY, int32_t VX,
+                               int32_t bz0, int32_t bz1, int32_t by0, int32_t by1, int32_t bx0, int32_t bx1,
+                               void* stream) {
+  if (!win_logits || !starts_dev || !wz || !wy || !wx || !out || !count || n_win < 1 || K < 1)
+    return fail(MMSEG_ERR_INVALID_ARG, "swi_blend: bad arguments");
+  if (bz0 < 0 || by0 < 0 || bx0 < 0 || bz1 > VZ || by1 > VY || bx1 > VX || bz1 <= bz0 || by1 <= by0 || bx1 <= bx0)
+    return fail(MMSEG_ERR_INVALID_ARG, "swi_blend: box outside the volume");
+  const int64_t rows = (int64_t)(bz1 - bz0) * (by1 - by0);
+  if (rows > 65535) return fail(MMSEG_ERR_INVALID_ARG, "swi_blend: box has too many rows for one launch");
+  dim3 grid((bx1 - bx0 + 127) / 128, (unsigned)rows);
+  swi_blend_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      win_logits, starts_dev, n_win, K, RZ, RY, RX, wz, wy, wx, w_floor, out, count, VZ, VY, VX, bz0, by0, bx0, bx1,
+      by1 - by0);
+  return check_launch("swi_blend_kernel");
+}
+
+extern "C" int mmseg_swi_finalize(float* out, const float* count, int32_t K, int64_t voxels,
+                                  int32_t normalize_in_place, uint8_t* labels, void* stream) {
+  if (!out || !count || K < 1 || voxels < 1) return fail(MMSEG_ERR_INVALID_ARG, "swi_finalize: bad arguments");
+  int64_t blocks = (voxels + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  swi_finalize_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      out, count, K, (size_t)voxels, normalize_in_place, labels);
+  return check_launch("swi_finalize_kernel");
+}

@@ -1,0 +1,218 @@
+"""Forward engines: the launch sequences that evaluate UNet3D / DualEncoder with the sm_100a kernels.
+
+An engine owns (a) kernel-layout copies of the module's weights (derived caches, rebuilt when a parameter changes)
+and (b) the activation workspaces for one (n_img, Z, Y, X) problem size.  It issues only C-ABI kernel launches on
+the current stream, so a whole forward can be captured in a CUDA graph.
+
+Numeric modes
+  * "bf16"   — bf16 operands, fp32 accumulate (north_star's throughput mode); raw conv outputs stored bf16.
+  * "parity" — 3-pass split-bf16 (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, fp32 accumulate), activations stored as
+               bf16 hi+lo pairs and raw conv outputs as fp32: ~2^-16 relative operand error, which is what the
+               stated logit/label tolerances need.
+"""
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from . import kernels as K
+from .kernels import Blocked, PackedConv
+
+Tensor = torch.Tensor
+
+
+class _Workspace:
+    """Named scratch tensors that keep their address across calls (graph-capture safe)."""
+
+    def __init__(self, device):
+        self.device = device
+        self._t: Dict[str, Tensor] = {}
+
+    def get(self, name: str, numel: int, dtype) -> Tensor:
+        t = self._t.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = torch.empty(numel, dtype=dtype, device=self.device)
+            self._t[name] = t
+        return t
+
+
+class ConvRunner:
+    """conv (+ InstanceNorm statistics) -> finalize -> normalise/activate(/pool), on blocked buffers."""
+
+    def __init__(self, split: bool, device):
+        self.split = split
+        self.device = device
+        self.ws = _Workspace(device)
+        self.launches = 0
+
+    # K segments: list of (first channel in src, real channels)
+    def conv_norm_act(self, src: Blocked, segs: Sequence[Tuple[int, int]], pw: PackedConv, dst: Blocked, dst_c0: int = 0,
+                      pooled: Optional[Blocked] = None, pooled_c0: int = 0, slope: float = 0.0, tag: str = "") -> None:
+        a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], self.split)
+        n, Z, Y, X = src.n_img, src.Z, src.Y, src.X
+        cout = pw.n_out
+        raw_f32 = self.split
+        raw = self.ws.get("raw", n * cout * Z * Y * X, torch.float32 if raw_f32 else torch.bfloat16)
+        tile = K.plan_conv(X, Y, Z, n, pw.n_kchunks, pw.n_out, pw.ksize, pw.NT)
+        stats = self.ws.get("stats", n * tile.tiles_per_img * cout * 2, torch.float32)
+        mr = self.ws.get("mean_rstd", n * cout * 2, torch.float32)
+        K.conv3d(src, pw, a_cb, raw, _lib.OUT_BLOCKED_F32 if raw_f32 else _lib.OUT_BLOCKED_BF16, stats=stats,
+                 dst_cbt=cout // 8, tile=tile)
+        K.instnorm_finalize(stats, n, tile.tiles_per_img, cout, Z * Y * X, mr)
+        K.instnorm_act_apply(raw, raw_f32, mr, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, pooled_c0)
+        self.launches += 3
+
+    def conv_transpose(self, src: Blocked, segs, pw: PackedConv, dst: Blocked, dst_c0: int = 0) -> None:
+        a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], self.split)
+        K.conv3d(src, pw, a_cb, dst.t, _lib.OUT_CONVT_K2S2, dst_cbt=dst.cbt, dst_cb_off=dst_c0 // 8,
+                 dst_lo_off=dst.lo_off)
+        self.launches += 1
+
+    def conv_act(self, src: Blocked, segs, pw: PackedConv, dst: Blocked, dst_c0: int = 0) -> None:
+        """conv + bias straight to an activation buffer (no norm): 1x1 fusion projections."""
+        a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], self.split)
+        K.conv3d(src, pw, a_cb, dst.t, _lib.OUT_BLOCKED_BF16_HILO if self.split else _lib.OUT_BLOCKED_BF16,
+                 dst_cbt=dst.cbt, dst_cb_off=dst_c0 // 8, dst_lo_off=dst.lo_off)
+        self.launches += 1
+
+    def conv_logits(self, src: Blocked, segs, pw: PackedConv, out: Tensor) -> None:
+        a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], self.split)
+        K.conv3d(src, pw, a_cb, out, _lib.OUT_NCDHW_F32)
+        self.launches += 1
+
+
+def _param_version(params: Sequence[Tensor]) -> Tuple:
+    return tuple((p.data_ptr(), p._version) for p in params)
+
+
+class UNet3DEngine:
+    """UNet3D.forward (reference src/models/backbones/unet.py:165-200) on blocked buffers.
+
+    `module` is the drop-in UNet3D nn.Module (same attribute tree / state_dict as the reference); only its
+    parameters are read.  Dropout is applied by the caller (it is the identity in eval / p=0).
+    """
+
+    def __init__(self, module, mode: str = "bf16"):
+        assert mode in ("bf16", "parity")
+        self.module = module
+        self.mode = mode
+        self.split = mode == "parity"
+        self._packed: Optional[Dict[str, PackedConv]] = None
+        self._packed_version = None
+        self._bufs: Dict[Tuple, Dict[str, object]] = {}
+        self._runner: Optional[ConvRunner] = None
+
+    # ---------------------------------------------------------------- weights
+    def _pack(self) -> Dict[str, PackedConv]:
+        m = self.module
+        params = list(m.parameters())
+        ver = _param_version(params)
+        if self._packed is not None and ver == self._packed_version:
+            return self._packed
+        f = m.features
+        sp = self.split
+        P: Dict[str, PackedConv] = {}
+
+        def block(name: str, blk, segs1):
+            # bias of a conv that feeds InstanceNorm(affine=False) is cancelled exactly by the mean subtraction
+            P[name + ".conv1"] = K.pack_conv_weight(blk.conv1.weight, None, sp, segs1, use_bias=False)
+            P[name + ".conv2"] = K.pack_conv_weight(blk.conv2.weight, None, sp, None, use_bias=False)
+
+        block("init_conv", m.init_conv, [m.in_channels])
+        for i, enc in enumerate(m.encoders):
+            block(f"encoders.{i}", enc.conv, [f[i]])
+        for j, dec in enumerate(m.decoders):
+            lvl = len(f) - 2 - j
+            P[f"decoders.{j}.up"] = K.pack_conv_weight(dec.up.weight, dec.up.bias, sp, None, transposed=True)
+            block(f"decoders.{j}", dec.conv, [f[lvl], f[lvl]])
+        P["out_conv"] = K.pack_conv_weight(m.out_conv.weight, m.out_conv.bias, sp, None)
+        self._packed, self._packed_version = P, ver
+        return P
+
+    # ---------------------------------------------------------------- buffers
+    def _buffers(self, n: int, Z: int, Y: int, X: int, device) -> Dict[str, object]:
+        key = (n, Z, Y, X)
+        b = self._bufs.get(key)
+        if b is not None:
+            return b
+        f = self.module.features
+        L = len(f)
+        if any(d % (1 << (L - 1)) for d in (Z, Y, X)):
+            raise NotImplementedError(
+                f"spatial size {(Z, Y, X)} is not divisible by {1 << (L - 1)}: the trilinear resize branch of "
+                "UpBlock3D (reference unet.py:108-109) is not implemented in the sm_100a path")
+        sp = self.split
+        b = {"in": Blocked(n, (self.module.in_channels + 15) // 16 * 16, Z, Y, X, sp, device)}
+        for l in range(L):
+            z, y, x = Z >> l, Y >> l, X >> l
+            b[f"mid{l}"] = Blocked(n, f[l], z, y, x, sp, device)            # ConvBlock3D conv1 output
+            if l < L - 1:
+                b[f"cat{l}"] = Blocked(n, 2 * f[l], z, y, x, sp, device)     # [up | skip]
+                b[f"dec{l}"] = Blocked(n, f[l], z, y, x, sp, device)         # decoder block output
+            else:
+                b[f"bott"] = Blocked(n, f[l], z, y, x, sp, device)
+            if l > 0:
+                b[f"pool{l}"] = Blocked(n, f[l - 1], z, y, x, sp, device)    # MaxPool3d(2) of level l-1
+        self._bufs[key] = b
+        return b
+
+    def input_buffer(self, n: int, Z: int, Y: int, X: int, device) -> Blocked:
+        return self._buffers(n, Z, Y, X, device)["in"]
+
+    # ---------------------------------------------------------------- forward
+    @torch.no_grad()
+    def forward_blocked(self, n: int, Z: int, Y: int, X: int, logits: Tensor) -> Tensor:
+        """Runs the net on the engine's input buffer; writes NCDHW fp32 logits [n, out_channels, Z, Y, X]."""
+        _lib.require_device()
+        m = self.module
+        f = m.features
+        L = len(f)
+        P = self._pack()
+        b = self._buffers(n, Z, Y, X, logits.device)
+        if self._runner is None:
+            self._runner = ConvRunner(self.split, logits.device)
+        r = self._runner
+        cin_p = (m.in_channels + 15) // 16 * 16
+        # encoder (unet.py:181-187); each block's output lands in the skip half of its level's concat buffer
+        r.conv_norm_act(b["in"], [(0, m.in_channels)], P["init_conv.conv1"], b["mid0"])
+        for l in range(L):
+            last = l == L - 1
+            if l > 0:
+                r.conv_norm_act(b[f"pool{l}"], [(0, f[l - 1])], P[f"encoders.{l - 1}.conv1"], b[f"mid{l}"])
+                name2 = f"encoders.{l - 1}.conv2"
+            else:
+                name2 = "init_conv.conv2"
+            if last:
+                r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[name2], b["bott"])
+            else:
+                r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[name2], b[f"cat{l}"], dst_c0=f[l],
+                                pooled=b[f"pool{l + 1}"])
+        # decoder (unet.py:190-192): up -> cat([up, skip]) -> ConvBlock3D
+        cur = b["bott"]
+        for j in range(L - 1):
+            l = L - 2 - j
+            r.conv_transpose(cur, [(0, f[l + 1])], P[f"decoders.{j}.up"], b[f"cat{l}"], dst_c0=0)
+            r.conv_norm_act(b[f"cat{l}"], [(0, f[l]), (f[l], f[l])], P[f"decoders.{j}.conv1"], b[f"mid{l}"])
+            r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[f"decoders.{j}.conv2"], b[f"dec{l}"])
+            cur = b[f"dec{l}"]
+        r.conv_logits(cur, [(0, f[0])], P["out_conv"], logits)
+        return logits
+
+    @torch.no_grad()
+    def forward(self, x: Tensor) -> Tensor:
+        _lib.require_device()
+        if not x.is_cuda:
+            raise RuntimeError("mmseg_b200 engines run on CUDA tensors only (no CPU fallback)")
+        x = x.contiguous().float()
+        n, _, Z, Y, X = x.shape
+        K.pack_ncdhw(x, self.input_buffer(n, Z, Y, X, x.device))
+        logits = torch.empty((n, self.module.out_channels, Z, Y, X), dtype=torch.float32, device=x.device)
+        return self.forward_blocked(n, Z, Y, X, logits)
+
+    def feature_ncdhw(self, n, Z, Y, X, level: int) -> Tensor:
+        """Encoder feature of `level` (the skip half of the concat buffer) as NCDHW fp32 — return_features."""
+        f = self.module.features
+        b = self._bufs[(n, Z, Y, X)]
+        if level == len(f) - 1:
+            return b["bott"].to_ncdhw()
+        return b[f"cat{level}"].to_ncdhw(f[level], f[level])

@@ -1,0 +1,277 @@
+"""Torch-facing wrappers over the C ABI: blocked activation buffers, weight packing, and one function per kernel.
+
+PyTorch only provides device memory and the current stream here; all arithmetic happens in libmmseg_b200.so.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+from .tiling import plan_conv, ConvTile
+
+Tensor = torch.Tensor
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+# --------------------------------------------------------------------------------------------- blocked buffers
+class Blocked:
+    """A blocked activation buffer [n_img, cbt, Z, Y, X, 8] bf16.
+
+    `cb` channel blocks of real data per numeric plane; in split ("parity") mode the buffer holds a hi plane
+    (blocks [0, cb)) followed by a lo plane (blocks [cb, 2cb)), i.e. lo_off == cb.
+    """
+
+    def __init__(self, n_img: int, channels: int, Z: int, Y: int, X: int, split: bool, device):
+        assert channels % 8 == 0
+        self.n_img, self.channels, self.Z, self.Y, self.X = n_img, channels, Z, Y, X
+        self.cb = channels // 8
+        self.split = split
+        self.cbt = self.cb * (2 if split else 1)
+        self.lo_off = self.cb if split else 0
+        self.t = torch.empty((n_img, self.cbt, Z, Y, X, 8), dtype=torch.bfloat16, device=device)
+
+    @property
+    def nvox(self) -> int:
+        return self.Z * self.Y * self.X
+
+    def to_ncdhw(self, c0: int = 0, channels: Optional[int] = None) -> Tensor:
+        """fp32 NCDHW copy of channels [c0, c0+channels) (hi+lo summed) via the unpack kernel."""
+        channels = self.channels - c0 if channels is None else channels
+        assert c0 % 8 == 0
+        out = torch.empty((self.n_img, channels, self.Z, self.Y, self.X), dtype=torch.float32, device=self.t.device)
+        check(lib.mmseg_unpack_ncdhw(_ptr(self.t), _ptr(out), self.n_img, channels, self.Z, self.Y, self.X,
+                                     self.cbt, c0 // 8, self.lo_off, _stream()), "mmseg_unpack_ncdhw")
+        return out
+
+
+def pack_ncdhw(x: Tensor, dst: Blocked, c0: int = 0) -> None:
+    """NCDHW fp32 -> blocked (channels zero-padded up to a multiple of 16 so a K chunk is always whole)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    n, Cc, Z, Y, X = x.shape
+    cb = ((Cc + 15) // 16) * 2
+    assert (n, Z, Y, X) == (dst.n_img, dst.Z, dst.Y, dst.X) and c0 % 8 == 0 and c0 // 8 + cb <= dst.cb
+    check(lib.mmseg_pack_ncdhw(_ptr(x), _ptr(dst.t), n, Cc, Z, Y, X, dst.cbt, c0 // 8, dst.lo_off, cb, _stream()),
+          "mmseg_pack_ncdhw")
+
+
+# --------------------------------------------------------------------------------------------- weight packing
+@dataclass
+class PackedConv:
+    """Kernel-layout weights of one conv (a derived cache; never saved in a state_dict)."""
+    w: Tensor                 # bf16 [n_ntiles, n_kchunks, taps, 2, NT, 8]
+    bias: Optional[Tensor]    # fp32 [n_ntiles*NT] or None
+    ksize: int
+    cin: int                  # real input channels (sum of segments)
+    n_out: int                # GEMM columns, padded to a multiple of 16
+    out_channels: int         # real output channels (per tap for convT)
+    NT: int
+    n_ntiles: int
+    n_kchunks: int            # including the 3x of split mode
+    split: bool
+    is_convt: bool = False
+
+
+def _pack_gemm_weight(wmat: Tensor, NT: int) -> Tensor:
+    """wmat [n_out, cin_p, taps] fp32 (cin_p multiple of 16) -> bf16 [n_ntiles, n_kc, taps, 2, NT, 8]."""
+    n_out, cin_p, taps = wmat.shape
+    v = wmat.reshape(n_out // NT, NT, cin_p // 16, 2, 8, taps)
+    return v.permute(0, 2, 5, 3, 1, 4).contiguous()
+
+
+def pack_conv_weight(weight: Tensor, bias: Optional[Tensor], split: bool, seg_channels: Optional[Sequence[int]] = None,
+                     use_bias: bool = True, nt_cap: int = 64, transposed: bool = False) -> PackedConv:
+    """Repack an nn.Conv3d / nn.ConvTranspose3d(k2,s2) weight for conv_tc.cu.
+
+    seg_channels: real channels of each input segment (concat order); each segment is zero-padded to a multiple
+    of 16 channels so that a 16-channel K chunk never straddles two producers.
+    Split mode appends K chunks: [W_hi | W_hi | W_lo] to be paired with activations [A_hi | A_lo | A_hi].
+    """
+    w = weight.detach().float()
+    if transposed:  # [Cin, Cout, 2,2,2] -> GEMM columns n = tap*Cout + co
+        cin, cout = w.shape[0], w.shape[1]
+        assert tuple(w.shape[2:]) == (2, 2, 2) and cout % 16 == 0
+        wm = w.reshape(cin, cout, 8).permute(2, 1, 0).reshape(8 * cout, cin, 1)
+        b = None if bias is None else bias.detach().float().repeat(8)
+        ksize, out_channels = 1, cout
+    else:
+        cout, cin = w.shape[0], w.shape[1]
+        ksize = w.shape[2]
+        assert ksize in (1, 3) and tuple(w.shape[2:]) == (ksize,) * 3
+        wm = w.reshape(cout, cin, ksize ** 3)
+        b = None if bias is None else bias.detach().float()
+        out_channels = cout
+    n_real = wm.shape[0]
+    n_out = (n_real + 15) // 16 * 16
+    seg = list(seg_channels) if seg_channels is not None else [cin]
+    assert sum(seg) == cin
+    parts, c = [], 0
+    for s in seg:
+        sp = (s + 15) // 16 * 16
+        blk = torch.zeros((n_out, sp, wm.shape[2]), dtype=torch.float32, device=w.device)
+        blk[:n_real, :s] = wm[:, c:c + s]
+        parts.append(blk)
+        c += s
+    wp = torch.cat(parts, dim=1)
+    NT = min(n_out, nt_cap)
+    while n_out % NT:
+        NT -= 16
+    if split:
+        hi = wp.to(torch.bfloat16)
+        lo = (wp - hi.float()).to(torch.bfloat16)
+        packed = torch.cat([_pack_gemm_weight(hi.float(), NT).to(torch.bfloat16)] * 2 +
+                           [_pack_gemm_weight(lo.float(), NT).to(torch.bfloat16)], dim=1).contiguous()
+    else:
+        packed = _pack_gemm_weight(wp, NT).to(torch.bfloat16).contiguous()
+    bias_p = None
+    if use_bias and b is not None:
+        bias_p = torch.zeros(n_out, dtype=torch.float32, device=w.device)
+        bias_p[:n_real] = b
+    return PackedConv(packed, bias_p, ksize, cin, n_out, out_channels, NT, n_out // NT, packed.shape[1], split,
+                      transposed)
+
+
+def a_chunk_table(src: Blocked, seg_c0: Sequence[int], seg_channels: Sequence[int], split: bool) -> List[int]:
+    """First channel block of every K chunk, in the order pack_conv_weight laid the chunks out."""
+    hi = []
+    for c0, s in zip(seg_c0, seg_channels):
+        assert c0 % 16 == 0
+        for j in range((s + 15) // 16):
+            hi.append(c0 // 8 + 2 * j)
+    if not split:
+        return hi
+    lo = [b + src.lo_off for b in hi]
+    return hi + lo + hi
+
+
+# --------------------------------------------------------------------------------------------- kernels
+def conv3d(src: Blocked, pw: PackedConv, a_cb: Sequence[int], dst: Tensor, out_mode: int, *,
+           stats: Optional[Tensor] = None, dst_cbt: int = 0, dst_cb_off: int = 0, dst_lo_off: int = 0,
+           tile: Optional[ConvTile] = None, flags: int = 0) -> ConvTile:
+    """Launch mmseg_conv3d_fwd.  Returns the tile plan used (stats must hold tiles_per_img partial rows)."""
+    _lib.require_device()
+    assert len(a_cb) == pw.n_kchunks, (len(a_cb), pw.n_kchunks)
+    if tile is None:
+        tile = plan_conv(src.X, src.Y, src.Z, src.n_img, pw.n_kchunks, pw.n_out, pw.ksize, pw.NT)
+    a = _lib.ConvArgs()
+    a.src, a.weights, a.bias, a.dst = src.t.data_ptr(), pw.w.data_ptr(), (pw.bias.data_ptr() if pw.bias is not None else None), dst.data_ptr()
+    a.stats_partial = stats.data_ptr() if stats is not None else None
+    a.n_img, a.Z, a.Y, a.X = src.n_img, src.Z, src.Y, src.X
+    a.src_cbt, a.ksize, a.n_kchunks = src.cbt, pw.ksize, pw.n_kchunks
+    a.NT, a.n_ntiles = tile.NT, tile.n_ntiles
+    a.TX, a.TY, a.TZ, a.stages = tile.TX, tile.TY, tile.TZ, tile.stages
+    a.out_mode, a.out_channels = out_mode, pw.out_channels
+    a.dst_cbt, a.dst_cb_off, a.dst_lo_off = dst_cbt, dst_cb_off, dst_lo_off
+    a.flags = flags
+    for i, v in enumerate(a_cb):
+        a.a_cb[i] = v
+    if stats is not None:
+        need = src.n_img * tile.tiles_per_img * pw.n_out * 2
+        assert stats.numel() >= need and stats.dtype == torch.float32
+    check(lib.mmseg_conv3d_fwd(C.byref(a), _stream()), "mmseg_conv3d_fwd")
+    return tile
+
+
+def instnorm_finalize(stats: Tensor, n_img: int, tiles_per_img: int, channels: int, voxels: int, mean_rstd: Tensor,
+                      eps: float = 1e-5) -> None:
+    check(lib.mmseg_instnorm_finalize(_ptr(stats), n_img, tiles_per_img, channels, voxels, eps, _ptr(mean_rstd),
+                                      _stream()), "mmseg_instnorm_finalize")
+
+
+def instnorm_act_apply(raw: Tensor, raw_is_f32: bool, mean_rstd: Tensor, n_img: int, channels: int,
+                       Z: int, Y: int, X: int, dst: Blocked, dst_c0: int = 0, slope: float = 0.0,
+                       pooled: Optional[Blocked] = None, pooled_c0: int = 0) -> None:
+    a = _lib.NormArgs()
+    a.src, a.mean_rstd, a.dst = raw.data_ptr(), mean_rstd.data_ptr(), dst.t.data_ptr()
+    a.pooled = pooled.t.data_ptr() if pooled is not None else None
+    a.n_img, a.cb, a.Z, a.Y, a.X = n_img, channels // 8, Z, Y, X
+    a.src_is_f32 = 1 if raw_is_f32 else 0
+    a.dst_cbt, a.dst_cb_off, a.dst_lo_off = dst.cbt, dst_c0 // 8, dst.lo_off
+    if pooled is not None:
+        a.pool_cbt, a.pool_cb_off, a.pool_lo_off = pooled.cbt, pooled_c0 // 8, pooled.lo_off
+    a.slope = slope
+    check(lib.mmseg_instnorm_act_apply(C.byref(a), _stream()), "mmseg_instnorm_act_apply")
+
+
+def swi_gather(volume: Tensor, starts_dev: Tensor, n_win: int, roi: Tuple[int, int, int], dst: Blocked) -> None:
+    Cc, VZ, VY, VX = volume.shape
+    cb = ((Cc + 15) // 16) * 2
+    check(lib.mmseg_swi_gather(_ptr(volume), Cc, VZ, VY, VX, _ptr(starts_dev), n_win, roi[0], roi[1], roi[2],
+                               _ptr(dst.t), dst.cbt, dst.lo_off, cb, _stream()), "mmseg_swi_gather")
+
+
+def swi_blend(win_logits: Tensor, starts_dev: Tensor, n_win: int, wz: Tensor, wy: Tensor, wx: Tensor, w_floor: float,
+              out: Tensor, count: Tensor, box: Tuple[int, int, int, int, int, int]) -> None:
+    K, VZ, VY, VX = out.shape
+    _, _, RZ, RY, RX = win_logits.shape
+    check(lib.mmseg_swi_blend(_ptr(win_logits), _ptr(starts_dev), n_win, K, RZ, RY, RX, _ptr(wz), _ptr(wy), _ptr(wx),
+                              w_floor, _ptr(out), _ptr(count), VZ, VY, VX, *box, _stream()), "mmseg_swi_blend")
+
+
+def swi_finalize(out: Tensor, count: Tensor, normalize_in_place: bool, labels: Optional[Tensor]) -> None:
+    K = out.shape[0]
+    vox = count.numel()
+    check(lib.mmseg_swi_finalize(_ptr(out), _ptr(count), K, vox, 1 if normalize_in_place else 0, _ptr(labels),
+                                 _stream()), "mmseg_swi_finalize")
+
+
+def dicece_fwd(logits: Tensor, target: Tensor, dice_weight: float, ce_weight: float, smooth: float = 1.0,
+               include_background: bool = True, class_weights: Optional[Tensor] = None) -> Tensor:
+    """Returns a 3-vector (total, dice, ce) on the device."""
+    _lib.require_device()
+    assert logits.is_cuda and logits.dtype == torch.float32 and logits.is_contiguous()
+    assert target.dtype == torch.int64 and target.is_contiguous()
+    B, Cc = logits.shape[:2]
+    N = logits[0, 0].numel()
+    n_blocks = max(1, min(148 * 4, (N + 255) // 256))
+    partial = torch.empty((B, n_blocks, 3 * Cc + 2), dtype=torch.float32, device=logits.device)
+    result = torch.empty(3, dtype=torch.float32, device=logits.device)
+    cw = None if class_weights is None else class_weights.to(logits.device, torch.float32).contiguous()
+    check(lib.mmseg_dicece_fwd(_ptr(logits), _ptr(target), B, Cc, N, dice_weight, ce_weight, smooth,
+                               1 if include_background else 0, _ptr(cw), _ptr(partial), n_blocks, _ptr(result),
+                               _stream()), "mmseg_dicece_fwd")
+    return result
+
+
+def channel_mean(src: Blocked, c0: int, channels: int) -> Tensor:
+    """Global average pool per (image, channel) of channels [c0, c0+channels) -> fp32 [n_img, channels]."""
+    cb = channels // 8
+    n_chunks = max(1, min(64, (src.nvox + 4095) // 4096))
+    partial = torch.empty((src.n_img * cb, n_chunks, 8), dtype=torch.float32, device=src.t.device)
+    mean = torch.empty((src.n_img, channels), dtype=torch.float32, device=src.t.device)
+    check(lib.mmseg_channel_mean(_ptr(src.t), src.n_img, src.cbt, c0 // 8, src.lo_off, cb, src.nvox, _ptr(partial),
+                                 n_chunks, _ptr(mean), _stream()), "mmseg_channel_mean")
+    return mean
+
+
+def gate_mlp(pooled: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor) -> Tensor:
+    n, MC = pooled.shape
+    H, M = w1.shape[0], w2.shape[0]
+    out = torch.empty((n, M), dtype=torch.float32, device=pooled.device)
+    f = lambda t: t.detach().float().contiguous()
+    w1, b1, w2, b2 = f(w1), f(b1), f(w2), f(b2)
+    check(lib.mmseg_gate_mlp(_ptr(pooled), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), n, MC, H, M, _ptr(out), _stream()),
+          "mmseg_gate_mlp")
+    return out
+
+
+def modality_combine(src: Blocked, M: int, channels: int, dst: Blocked, dst_c0: int, weights: Optional[Tensor],
+                     uniform_weight: float = 1.0) -> None:
+    check(lib.mmseg_modality_combine(_ptr(src.t), src.n_img, src.cbt, src.lo_off, M, channels // 8, src.nvox,
+                                     _ptr(weights), uniform_weight, _ptr(dst.t), dst.cbt, dst_c0 // 8, dst.lo_off,
+                                     _stream()), "mmseg_modality_combine")
+
+
+def maxpool3d_2(src: Blocked, dst: Blocked, channels: Optional[int] = None, src_c0: int = 0, dst_c0: int = 0) -> None:
+    channels = src.channels if channels is None else channels
+    check(lib.mmseg_maxpool3d_2(_ptr(src.t), src.n_img, src.cbt, src_c0 // 8, src.lo_off, channels // 8, src.Z, src.Y,
+                                src.X, _ptr(dst.t), dst.cbt, dst_c0 // 8, dst.lo_off, _stream()), "mmseg_maxpool3d_2")

@@ -1,0 +1,230 @@
+"""3D U-Net backbone — drop-in mirror of the reference's src/models/backbones/unet.py.
+
+Same class names, constructor arguments, attribute tree and state_dict keys/shapes so a
+reference checkpoint loads unchanged; the arithmetic runs in the sm_100a kernels (engine.py).  There is no
+PyTorch/CPU route: a forward on a non-CUDA tensor, or with an option the kernels do not cover, raises.
+"""
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from ....engine import ConvRunner, UNet3DEngine
+from .... import kernels as K
+from .... import _lib
+from ....kernels import Blocked
+
+_DEFAULT_MODE = "bf16"
+
+
+def _require_cuda(x: torch.Tensor) -> None:
+    if not x.is_cuda:
+        raise RuntimeError("mmseg_b200 modules run on CUDA (sm_100a) tensors only; there is no CPU fallback")
+
+
+def _no_autograd(module: nn.Module, x: torch.Tensor) -> None:
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters())):
+        raise NotImplementedError(
+            "backward (dgrad/wgrad) kernels are not built yet: call under torch.no_grad() / model.eval() inference. "
+            "Training parity is scheduled after the forward/sliding-window path (DESIGN.md, scope row (f)).")
+
+
+class ConvBlock3D(nn.Module):
+    """(Conv3d k3 p1 -> InstanceNorm3d -> act) x 2 — reference unet.py:12-60."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int = 3, padding: int = 1,
+                 norm: str = "instance", activation: str = "relu"):
+        super().__init__()
+        self.conv1 = nn.Conv3d(in_channels, out_channels, kernel_size, padding=padding)
+        self.conv2 = nn.Conv3d(out_channels, out_channels, kernel_size, padding=padding)
+        if norm == "batch":
+            self.norm1, self.norm2 = nn.BatchNorm3d(out_channels), nn.BatchNorm3d(out_channels)
+        elif norm == "instance":
+            self.norm1, self.norm2 = nn.InstanceNorm3d(out_channels), nn.InstanceNorm3d(out_channels)
+        elif norm == "group":
+            self.norm1, self.norm2 = nn.GroupNorm(8, out_channels), nn.GroupNorm(8, out_channels)
+        else:
+            self.norm1, self.norm2 = nn.Identity(), nn.Identity()
+        if activation == "leaky_relu":
+            self.act = nn.LeakyReLU(0.2, inplace=True)
+        elif activation == "gelu":
+            self.act = nn.GELU()
+        else:
+            self.act = nn.ReLU(inplace=True)
+        self.norm_type = norm
+        self.activation = activation if activation in ("leaky_relu", "gelu") else "relu"
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.numeric_mode = _DEFAULT_MODE
+        self._runner: Optional[ConvRunner] = None
+        self._packed = None
+
+    def kernel_supported(self) -> None:
+        if self.norm_type != "instance" or self.activation == "gelu" or self.conv1.kernel_size != (3, 3, 3) \
+                or self.conv1.padding != (1, 1, 1) or self.out_channels % 16:
+            raise NotImplementedError(
+                f"ConvBlock3D(norm={self.norm_type!r}, activation={self.activation!r}, k={self.conv1.kernel_size}, "
+                f"C_out={self.out_channels}) has no sm_100a kernel (covered: instance norm, relu/leaky_relu, k=3 p=1, "
+                "C_out % 16 == 0)")
+
+    @property
+    def slope(self) -> float:
+        return 0.2 if self.activation == "leaky_relu" else 0.0
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        _require_cuda(x)
+        _no_autograd(self, x)
+        self.kernel_supported()
+        split = self.numeric_mode == "parity"
+        with torch.no_grad():
+            x = x.contiguous().float()
+            n, c, Z, Y, X = x.shape
+            ver = (self.conv1.weight._version, self.conv2.weight._version, split)
+            if self._packed is None or self._packed[0] != ver:
+                self._packed = (ver, K.pack_conv_weight(self.conv1.weight, None, split, [c], use_bias=False),
+                                K.pack_conv_weight(self.conv2.weight, None, split, None, use_bias=False))
+            if self._runner is None or self._runner.split != split:
+                self._runner = ConvRunner(split, x.device)
+            src = Blocked(n, (c + 15) // 16 * 16, Z, Y, X, split, x.device)
+            K.pack_ncdhw(x, src)
+            mid = Blocked(n, self.out_channels, Z, Y, X, split, x.device)
+            out = Blocked(n, self.out_channels, Z, Y, X, split, x.device)
+            self._runner.conv_norm_act(src, [(0, c)], self._packed[1], mid, slope=self.slope)
+            self._runner.conv_norm_act(mid, [(0, self.out_channels)], self._packed[2], out, slope=self.slope)
+            return out.to_ncdhw()
+
+
+class DownBlock3D(nn.Module):
+    """MaxPool3d(2) -> ConvBlock3D; returns (x_conv, x_pool) — reference unet.py:63-79."""
+
+    def __init__(self, in_channels: int, out_channels: int, norm: str = "instance"):
+        super().__init__()
+        self.pool = nn.MaxPool3d(2)
+        self.conv = ConvBlock3D(in_channels, out_channels, norm=norm)
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        _require_cuda(x)
+        _no_autograd(self, x)
+        # standalone use only (UNet3D / DualEncoder run the fused engine): pooling is a layout-only op here
+        x_pool = torch.nn.functional.max_pool3d(x, 2)
+        return self.conv(x_pool), x_pool
+
+
+class UpBlock3D(nn.Module):
+    """ConvTranspose3d(k2,s2) -> cat([up, skip]) -> ConvBlock3D — reference unet.py:82-113."""
+
+    def __init__(self, in_channels: int, out_channels: int, norm: str = "instance", mode: str = "transpose"):
+        super().__init__()
+        if mode == "transpose":
+            self.up = nn.ConvTranspose3d(in_channels, in_channels // 2, kernel_size=2, stride=2)
+        else:
+            self.up = nn.Sequential(
+                nn.Upsample(scale_factor=2, mode="trilinear", align_corners=True),
+                nn.Conv3d(in_channels, in_channels // 2, kernel_size=1),
+            )
+        self.mode = mode
+        self.conv = ConvBlock3D(in_channels, out_channels, norm=norm)
+        self.numeric_mode = _DEFAULT_MODE
+        self._runner: Optional[ConvRunner] = None
+        self._packed = None
+
+    def forward(self, x: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
+        _require_cuda(x)
+        _no_autograd(self, x)
+        if self.mode != "transpose":
+            raise NotImplementedError("UpBlock3D(mode != 'transpose') is never selected by the reference's builders "
+                                      "(unet.py:149) and has no sm_100a kernel")
+        self.conv.kernel_supported()
+        split = self.numeric_mode == "parity"
+        with torch.no_grad():
+            x = x.contiguous().float()
+            skip = skip.contiguous().float()
+            n, c, Z, Y, X = x.shape
+            if tuple(skip.shape[2:]) != (2 * Z, 2 * Y, 2 * X):
+                raise NotImplementedError("trilinear resize to the skip shape (reference unet.py:108-109) is not "
+                                          "implemented; use spatial sizes divisible by 2**levels")
+            half = c // 2
+            ver = (self.up.weight._version, self.conv.conv1.weight._version, self.conv.conv2.weight._version, split)
+            if self._packed is None or self._packed[0] != ver:
+                self._packed = (ver,
+                                K.pack_conv_weight(self.up.weight, self.up.bias, split, None, transposed=True),
+                                K.pack_conv_weight(self.conv.conv1.weight, None, split, [half, skip.shape[1]], use_bias=False),
+                                K.pack_conv_weight(self.conv.conv2.weight, None, split, None, use_bias=False))
+            if self._runner is None or self._runner.split != split:
+                self._runner = ConvRunner(split, x.device)
+            r = self._runner
+            src = Blocked(n, c, Z, Y, X, split, x.device)
+            K.pack_ncdhw(x, src)
+            cat = Blocked(n, half + skip.shape[1], 2 * Z, 2 * Y, 2 * X, split, x.device)
+            K.pack_ncdhw(skip, cat, c0=half)
+            r.conv_transpose(src, [(0, c)], self._packed[1], cat, 0)
+            co = self.conv.out_channels
+            mid = Blocked(n, co, 2 * Z, 2 * Y, 2 * X, split, x.device)
+            out = Blocked(n, co, 2 * Z, 2 * Y, 2 * X, split, x.device)
+            r.conv_norm_act(cat, [(0, half), (half, skip.shape[1])], self._packed[2], mid, slope=self.conv.slope)
+            r.conv_norm_act(mid, [(0, co)], self._packed[3], out, slope=self.conv.slope)
+            return out.to_ncdhw()
+
+
+class UNet3D(nn.Module):
+    """3D UNet — reference unet.py:116-205 (same ctor / forward / encoder_channels)."""
+
+    def __init__(self, in_channels: int = 1, out_channels: int = 8, features: List[int] = [32, 64, 128, 256, 512],
+                 norm: str = "instance", dropout: float = 0.0, **kwargs):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.features = list(features)
+        self.init_conv = ConvBlock3D(in_channels, features[0], norm=norm)
+        self.encoders = nn.ModuleList()
+        for i in range(len(features) - 1):
+            self.encoders.append(DownBlock3D(features[i], features[i + 1], norm=norm))
+        self.decoders = nn.ModuleList()
+        for i in range(len(features) - 1, 0, -1):
+            self.decoders.append(UpBlock3D(features[i], features[i - 1], norm=norm))
+        self.dropout = nn.Dropout3d(dropout) if dropout > 0 else nn.Identity()
+        self.out_conv = nn.Conv3d(features[0], out_channels, kernel_size=1)
+        self.numeric_mode = _DEFAULT_MODE
+        self._engines: Dict[str, UNet3DEngine] = {}
+
+    def set_numeric_mode(self, mode: str) -> "UNet3D":
+        """'bf16' (throughput) or 'parity' (3-pass split-bf16; meets the stated logit / label tolerances)."""
+        assert mode in ("bf16", "parity")
+        self.numeric_mode = mode
+        return self
+
+    def engine(self) -> UNet3DEngine:
+        e = self._engines.get(self.numeric_mode)
+        if e is None:
+            e = self._engines[self.numeric_mode] = UNet3DEngine(self, self.numeric_mode)
+        return e
+
+    def forward(self, x: torch.Tensor, return_features: bool = False
+                ) -> Union[torch.Tensor, Tuple[torch.Tensor, List[torch.Tensor]]]:
+        _require_cuda(x)
+        _no_autograd(self, x)
+        self.init_conv.kernel_supported()
+        if self.training and isinstance(self.dropout, nn.Dropout3d) and self.dropout.p > 0:
+            raise NotImplementedError("Dropout3d before out_conv in train mode belongs to the training path")
+        eng = self.engine()
+        logits = eng.forward(x)
+        if return_features:
+            n, _, Z, Y, X = x.shape
+            feats = [eng.feature_ncdhw(n, Z, Y, X, l) for l in range(len(self.features) - 1)]
+            return logits, feats
+        return logits
+
+    @property
+    def encoder_channels(self) -> List[int]:
+        return self.features
+
+
+def build_unet3d(config: Dict[str, Any]) -> UNet3D:
+    """reference unet.py:208-226."""
+    backbone_config = config.get("model", {}).get("backbone", {})
+    return UNet3D(
+        in_channels=config["model"]["in_channels"],
+        out_channels=config["model"]["out_channels"],
+        features=backbone_config.get("features", [32, 64, 128, 256, 512]),
+        norm=backbone_config.get("norm", "instance"),
+        dropout=config["model"].get("head", {}).get("dropout", 0.0),
+    )

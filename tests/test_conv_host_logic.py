@@ -1,0 +1,103 @@
+"""Host logic of the conv path (packing, K-chunk tables, planner) checked by emulating the kernel's data path."""
+import types
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import mmseg_b200  # noqa: F401
+from mmseg_b200 import kernels as K
+from mmseg_b200.tiling import plan_conv, smem_bytes, ConvTile
+from tests.emulate import emulate_conv, to_blocked
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("cin,cout,shape,tile", [
+    (2, 16, (5, 6, 7), None),
+    (16, 32, (4, 9, 10), (10, 4, 2)),
+    (32, 16, (3, 5, 20), (10, 3, 2)),      # ragged x/y/z tiles
+])
+def test_conv3x3_emulated(cin, cout, shape, tile):
+    torch.manual_seed(0)
+    Z, Y, X = shape
+    x = _bf(torch.randn(2, cin, Z, Y, X))
+    w = _bf(torch.randn(cout, cin, 3, 3, 3) * 0.2)
+    pw = K.pack_conv_weight(w, None, False, [cin], use_bias=False)
+    stub = types.SimpleNamespace(lo_off=0)
+    a_cb = K.a_chunk_table(stub, [0], [cin], False)
+    if tile is None:
+        t = plan_conv(X, Y, Z, 2, pw.n_kchunks, pw.n_out, 3, pw.NT)
+    else:
+        TX, TY, TZ = tile
+        mt = ((TY - 1) * (TX + 2) + TX + 127) // 128
+        t = ConvTile(TX, TY, TZ, pw.NT, pw.n_ntiles, 2, mt, 0, 0, 0.0)
+    src = to_blocked(x)
+    got = emulate_conv(src, src.shape[1], pw, a_cb, t, 2, Z, Y, X)[:, :cout]
+    ref = F.conv3d(x, w, padding=1)
+    assert torch.allclose(got, ref, atol=1e-3, rtol=1e-4), (got - ref).abs().max()
+
+
+def test_concat_segments_and_split_mode():
+    """Two-segment K (cat([up, skip])) with hi/lo split operands reproduces the fp32 conv to ~2^-16."""
+    torch.manual_seed(1)
+    Z, Y, X = 3, 4, 6
+    up, skip = torch.randn(1, 16, Z, Y, X), torch.randn(1, 16, Z, Y, X)
+    w = torch.randn(16, 32, 3, 3, 3) * 0.1
+    pw = K.pack_conv_weight(w, None, True, [16, 16], use_bias=False)
+    assert pw.n_kchunks == 6
+    # buffer = [hi(up) hi(skip) | lo(up) lo(skip)], cb = 4 per plane
+    cat = torch.cat([up, skip], 1)
+    hi = _bf(cat)
+    lo = _bf(cat - hi)
+    src = torch.cat([to_blocked(hi), to_blocked(lo)], dim=1)
+    stub = types.SimpleNamespace(lo_off=4)
+    a_cb = K.a_chunk_table(stub, [0, 16], [16, 16], True)
+    assert a_cb == [0, 2, 4, 6, 0, 2]
+    t = plan_conv(X, Y, Z, 1, pw.n_kchunks, pw.n_out, 3, pw.NT)
+    got = emulate_conv(src, 8, pw, a_cb, t, 1, Z, Y, X)[:, :16]
+    ref = F.conv3d(cat, w, padding=1)
+    assert (got - ref).abs().max() < 2e-4 * ref.abs().max()
+
+
+def test_conv_transpose_as_gemm():
+    torch.manual_seed(2)
+    Z, Y, X = 2, 3, 4
+    x = _bf(torch.randn(1, 32, Z, Y, X))
+    w = _bf(torch.randn(32, 16, 2, 2, 2) * 0.2)
+    b = torch.randn(16)
+    pw = K.pack_conv_weight(w, b, False, None, transposed=True)
+    assert pw.n_out == 128 and pw.ksize == 1
+    stub = types.SimpleNamespace(lo_off=0)
+    a_cb = K.a_chunk_table(stub, [0], [32], False)
+    t = plan_conv(X, Y, Z, 1, pw.n_kchunks, pw.n_out, 1, pw.NT)
+    g = emulate_conv(to_blocked(x), 4, pw, a_cb, t, 1, Z, Y, X)  # [1, 8*16, Z, Y, X], column = tap*16 + co
+    g = g + pw.bias.view(1, -1, 1, 1, 1)
+    out = torch.zeros(1, 16, 2 * Z, 2 * Y, 2 * X)
+    for tap in range(8):
+        a, bb, c = tap >> 2, (tap >> 1) & 1, tap & 1
+        out[:, :, a::2, bb::2, c::2] = g[:, tap * 16:(tap + 1) * 16]
+    ref = F.conv_transpose3d(x, w, b, stride=2)
+    assert torch.allclose(out, ref, atol=1e-3, rtol=1e-4)
+
+
+def test_planner_matches_library_limits():
+    """Every plan the Python planner emits must be accepted by the C-side plan_conv (same smem arithmetic)."""
+    import ctypes as C
+    from mmseg_b200 import _lib
+    for (X, Y, Z, n, kc, nout, ks) in [(96, 96, 96, 1, 2, 32, 3), (96, 96, 96, 4, 4, 32, 3), (48, 48, 48, 1, 2, 64, 3),
+                                        (24, 24, 24, 2, 8, 128, 3), (12, 12, 12, 1, 16, 256, 3), (6, 6, 6, 1, 32, 512, 3),
+                                        (6, 6, 6, 1, 32, 2048, 1), (96, 96, 96, 1, 2, 16, 1), (128, 128, 128, 2, 2, 32, 3)]:
+        t = plan_conv(X, Y, Z, n, kc, nout, ks)
+        a = _lib.ConvArgs()
+        a.n_img, a.Z, a.Y, a.X = n, Z, Y, X
+        a.src_cbt, a.ksize, a.n_kchunks = 2 * kc, ks, kc
+        a.NT, a.n_ntiles, a.TX, a.TY, a.TZ, a.stages = t.NT, t.n_ntiles, t.TX, t.TY, t.TZ, t.stages
+        a.out_mode, a.out_channels = 0, nout
+        for i in range(kc):
+            a.a_cb[i] = 2 * i
+        got = _lib.lib.mmseg_conv3d_smem_bytes(C.byref(a))
+        assert got == t.smem_bytes, (X, ks, nout, got, t, _lib.last_error())
+        assert _lib.lib.mmseg_conv3d_tiles_per_img(C.byref(a)) == t.tiles_per_img
