@@ -129,6 +129,9 @@ int mmseg_unpack_ncdhw(const void* src, float* dst, int32_t n_img, int32_t C, in
  *  gather:  windows of the NCDHW fp32 volume -> blocked bf16 batch (one image per window).
  *  blend:   out[:, window] += w * logits[window]; count[window] += w — windows applied in index order per voxel,
  *           one owner thread per voxel (deterministic, same order as the reference loop; no atomics).
+ *           Box mode (bz0 >= 0): the launch covers the box [bz0,bz1)x[by0,by1)x[bx0,bx1) and loops over n_win windows.
+ *           Window mode (bz0 < 0, n_win == 1): the launch covers the window whose origin is read from starts_dev —
+ *           all launch arguments are batch-independent, so the call can be captured in a CUDA graph.
  *  finalize: out / count (in place, optional) and argmax over channels -> uint8 labels (trainer.py:364-367).
  */
 int mmseg_swi_gather(const float* volume, int32_t C, int32_t VZ, int32_t VY, int32_t VX, const int32_t* starts_dev,
@@ -149,7 +152,11 @@ int mmseg_swi_finalize(float* out, const float* count, int32_t K, int64_t voxels
 int mmseg_dicece_fwd(const float* logits /* [B][C][N] */, const int64_t* target /* [B][N] */, int32_t B, int32_t C,
                      int64_t N, float dice_weight, float ce_weight, float smooth, int32_t include_background,
                      const float* class_weights /* [C] or NULL */, float* partial /* [B][n_blocks][3*C+2] */,
-                     int32_t n_blocks, float* result /* [3] */, void* stream);
+                     int32_t n_blocks, float* result /* [3] */, float* sums /* [B][3*C+2] or NULL */, void* stream);
+/* d(DiceCE)/d(logits) * grad_out[0]; `sums` is the forward's per-batch (I, P, T, nll, weight) reduction. */
+int mmseg_dicece_bwd(const float* logits, const int64_t* target, int32_t B, int32_t C, int64_t N, float dice_weight,
+                     float ce_weight, float smooth, int32_t include_background, const float* class_weights,
+                     const float* sums, const float* grad_out /* [1] or NULL */, float* dlogits, void* stream);
 
 /*
  * DualEncoder modality fusion (src/models/backbones/dual_encoder.py:167-199, CrossModalAttention :207-254; same maths

@@ -61,7 +61,8 @@ SYMBOLS = {
     "mmseg_swi_blend": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _vp,
                                   _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "mmseg_swi_finalize": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp]),
-    "mmseg_dicece_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _f32, _f32, _f32, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "mmseg_dicece_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _f32, _f32, _f32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "mmseg_dicece_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _f32, _f32, _f32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mmseg_channel_mean": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _vp]),
     "mmseg_gate_mlp": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mmseg_modality_combine": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _f32, _vp, _i32, _i32, _i32, _vp]),

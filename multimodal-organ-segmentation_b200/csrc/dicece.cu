@@ -77,7 +77,8 @@ dicece_partial_kernel(const float* __restrict__ logits, const long long* __restr
 
 // single block: fixed-order fp64 reduction over blocks, then the loss.
 __global__ void dicece_final_kernel(const float* __restrict__ partial, int B, int C, int n_blocks, float dice_w,
-                                    float ce_w, float smooth, int include_bg, float* __restrict__ result) {
+                                    float ce_w, float smooth, int include_bg, float* __restrict__ result,
+                                    float* __restrict__ sums) {
   __shared__ double acc[4 * (3 * kMaxC + 2)];  // B <= 4 per pass handled by loop below
   __shared__ double dice_sum, nll_sum, w_sum;
   const int stride = 3 * C + 2;
@@ -88,6 +89,7 @@ __global__ void dicece_final_kernel(const float* __restrict__ partial, int B, in
       double s = 0.0;
       for (int k = 0; k < n_blocks; ++k) s += (double)partial[((size_t)b * n_blocks + k) * stride + threadIdx.x];
       acc[threadIdx.x] = s;
+      if (sums) sums[(size_t)b * stride + threadIdx.x] = (float)s;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -110,6 +112,60 @@ __global__ void dicece_final_kernel(const float* __restrict__ partial, int B, in
   }
 }
 
+// Backward: dz_c = go * [ dice_w * p_c (g_c - sum_k g_k p_k) + ce_w * w_t (p_c - t_c) / W ],
+// g_c = -(2 t_c (U_c + s) - (2 I_c + s)) / (B nc (U_c + s)^2)   (losses.py:39-80,216-228)
+template <int C>
+__global__ void __launch_bounds__(256)
+dicece_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target, size_t N, int B,
+                  const float* __restrict__ cw, const float* __restrict__ sums, float dice_w, float ce_w, float smooth,
+                  int include_bg, const float* __restrict__ grad_out, float* __restrict__ dlogits) {
+  const int b = blockIdx.y;
+  const float go = grad_out ? grad_out[0] : 1.f;
+  const int stride = 3 * C + 2;
+  float gA[C], gB[C];
+  const int nc = include_bg ? C : C - 1;
+  float wtot = 0.f;
+  for (int bb = 0; bb < B; ++bb) wtot += sums[(size_t)bb * stride + 3 * C + 1];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float I = sums[(size_t)b * stride + c];
+    const float U = sums[(size_t)b * stride + C + c] + sums[(size_t)b * stride + 2 * C + c];
+    const float den = U + smooth;
+    const float k = 1.f / ((float)(B * nc) * den * den);
+    const bool on = include_bg || c > 0;
+    gA[c] = on ? -2.f * den * k : 0.f;         // multiplies t_c
+    gB[c] = on ? (2.f * I + smooth) * k : 0.f;  // constant part
+  }
+  const float* lg = logits + (size_t)b * C * N;
+  float* dl = dlogits + (size_t)b * C * N;
+  const long long* tg = target + (size_t)b * N;
+  for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (size_t)gridDim.x * blockDim.x) {
+    float z[C];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { z[c] = lg[(size_t)c * N + n]; mx = fmaxf(mx, z[c]); }
+    const int t = (int)tg[n];
+    float se = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { z[c] = expf(z[c] - mx); se += z[c]; }
+    const float inv = 1.f / se;
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      z[c] *= inv;
+      const float g = gB[c] + (c == t ? gA[c] : 0.f);
+      dot = fmaf(g, z[c], dot);
+    }
+    const float wce = ce_w * (cw ? cw[t] : 1.f) / wtot;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float g = gB[c] + (c == t ? gA[c] : 0.f);
+      const float d = dice_w * z[c] * (g - dot) + wce * (z[c] - (c == t ? 1.f : 0.f));
+      dl[(size_t)c * N + n] = go * d;
+    }
+  }
+}
+
 }  // namespace mmseg
 
 using namespace mmseg;
@@ -117,7 +173,7 @@ using namespace mmseg;
 extern "C" int mmseg_dicece_fwd(const float* logits, const int64_t* target, int32_t B, int32_t C, int64_t N,
                                 float dice_weight, float ce_weight, float smooth, int32_t include_background,
                                 const float* class_weights, float* partial, int32_t n_blocks, float* result,
-                                void* stream) {
+                                float* sums, void* stream) {
   if (!logits || !target || !partial || !result || B < 1 || N < 1 || n_blocks < 1 || n_blocks > 65535)
     return fail(MMSEG_ERR_INVALID_ARG, "dicece_fwd: bad arguments");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -134,6 +190,32 @@ extern "C" int mmseg_dicece_fwd(const float* logits, const int64_t* target, int3
   int rc = check_launch("dicece_partial_kernel");
   if (rc != MMSEG_OK) return rc;
   dicece_final_kernel<<<1, 64, 0, st>>>(partial, B, C, n_blocks, dice_weight, ce_weight, smooth, include_background,
-                                        result);
+                                        result, sums);
   return check_launch("dicece_final_kernel");
+}
+
+extern "C" int mmseg_dicece_bwd(const float* logits, const int64_t* target, int32_t B, int32_t C, int64_t N,
+                                float dice_weight, float ce_weight, float smooth, int32_t include_background,
+                                const float* class_weights, const float* sums, const float* grad_out, float* dlogits,
+                                void* stream) {
+  if (!logits || !target || !sums || !dlogits || B < 1 || N < 1)
+    return fail(MMSEG_ERR_INVALID_ARG, "dicece_bwd: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int64_t nb = (N + 255) / 256;
+  if (nb > 148 * 8) nb = 148 * 8;
+  dim3 grid((unsigned)nb, B);
+  const long long* tg = reinterpret_cast<const long long*>(target);
+#define MMSEG_BWD(CC)                                                                                              \
+  dicece_bwd_kernel<CC><<<grid, 256, 0, st>>>(logits, tg, (size_t)N, B, class_weights, sums, dice_weight, ce_weight, \
+                                              smooth, include_background, grad_out, dlogits)
+  switch (C) {
+    case 2: MMSEG_BWD(2); break;
+    case 3: MMSEG_BWD(3); break;
+    case 4: MMSEG_BWD(4); break;
+    case 8: MMSEG_BWD(8); break;
+    case 16: MMSEG_BWD(16); break;
+    default: return fail(MMSEG_ERR_UNSUPPORTED, "dicece_bwd: C=%d (supported: 2,3,4,8,16)", C);
+  }
+#undef MMSEG_BWD
+  return check_launch("dicece_bwd_kernel");
 }

@@ -84,6 +84,33 @@ swi_blend_kernel(const float* __restrict__ logits, const int* __restrict__ start
   }
 }
 
+// Window mode: the launch covers exactly one window (extent read from starts on the device, so the launch arguments
+// are batch-independent and the call can sit in a CUDA graph).  grid: (x-chunks, RZ*RY)
+__global__ void __launch_bounds__(128)
+swi_blend_window_kernel(const float* __restrict__ logits, const int* __restrict__ starts, int K, int RZ, int RY, int RX,
+                        const float* __restrict__ wz, const float* __restrict__ wy, const float* __restrict__ wx,
+                        float w_floor, float* __restrict__ out, float* __restrict__ count, int VZ, int VY, int VX) {
+  const int lz = blockIdx.y / RY, ly = blockIdx.y - lz * RY;
+  const int z = starts[0] + lz, y = starts[1] + ly;
+  if (z < 0 || z >= VZ || y < 0 || y >= VY) return;
+  const int sx = starts[2];
+  const size_t nvox_v = (size_t)VZ * VY * VX;
+  const size_t nvox_r = (size_t)RZ * RY * RX;
+  const float wzy = __fmul_rn(wz[lz], wy[ly]);
+  for (int lx = blockIdx.x * blockDim.x + threadIdx.x; lx < RX; lx += gridDim.x * blockDim.x) {
+    const int x = sx + lx;
+    if (x < 0 || x >= VX) continue;
+    const size_t vox = ((size_t)z * VY + y) * VX + x;
+    const float w = fmaxf(__fmul_rn(wzy, wx[lx]), w_floor);
+    const float* seg = logits + ((size_t)lz * RY + ly) * RX + lx;
+    for (int c = 0; c < K; ++c) {
+      float* o = out + (size_t)c * nvox_v + vox;
+      *o = __fadd_rn(*o, __fmul_rn(seg[(size_t)c * nvox_r], w));
+    }
+    count[vox] = __fadd_rn(count[vox], w);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 swi_finalize_kernel(float* __restrict__ out, const float* __restrict__ count, int K, size_t nvox, int normalize,
                     uint8_t* __restrict__ labels) {
@@ -122,6 +149,14 @@ extern "C" int mmseg_swi_blend(const float* win_logits, const int32_t* starts_de
                                void* stream) {
   if (!win_logits || !starts_dev || !wz || !wy || !wx || !out || !count || n_win < 1 || K < 1)
     return fail(MMSEG_ERR_INVALID_ARG, "swi_blend: bad arguments");
+  if (bz0 < 0) {  // window mode: one window, extent taken from starts_dev on the device
+    if (n_win != 1) return fail(MMSEG_ERR_INVALID_ARG, "swi_blend: window mode takes exactly one window");
+    if ((int64_t)RZ * RY > 65535) return fail(MMSEG_ERR_INVALID_ARG, "swi_blend: roi has too many rows");
+    dim3 wgrid((RX + 127) / 128, RZ * RY);
+    swi_blend_window_kernel<<<wgrid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        win_logits, starts_dev, K, RZ, RY, RX, wz, wy, wx, w_floor, out, count, VZ, VY, VX);
+    return check_launch("swi_blend_window_kernel");
+  }
   if (bz0 < 0 || by0 < 0 || bx0 < 0 || bz1 > VZ || by1 > VY || bx1 > VX || bz1 <= bz0 || by1 <= by0 || bx1 <= bx0)
     return fail(MMSEG_ERR_INVALID_ARG, "swi_blend: box outside the volume");
   const int64_t rows = (int64_t)(bz1 - bz0) * (by1 - by0);

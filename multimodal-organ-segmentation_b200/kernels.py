@@ -225,8 +225,8 @@ def swi_finalize(out: Tensor, count: Tensor, normalize_in_place: bool, labels: O
 
 
 def dicece_fwd(logits: Tensor, target: Tensor, dice_weight: float, ce_weight: float, smooth: float = 1.0,
-               include_background: bool = True, class_weights: Optional[Tensor] = None) -> Tensor:
-    """Returns a 3-vector (total, dice, ce) on the device."""
+               include_background: bool = True, class_weights: Optional[Tensor] = None):
+    """Returns (result[3] = (total, dice, ce), sums[B, 3C+2]) on the device."""
     _lib.require_device()
     assert logits.is_cuda and logits.dtype == torch.float32 and logits.is_contiguous()
     assert target.dtype == torch.int64 and target.is_contiguous()
@@ -235,11 +235,24 @@ def dicece_fwd(logits: Tensor, target: Tensor, dice_weight: float, ce_weight: fl
     n_blocks = max(1, min(148 * 4, (N + 255) // 256))
     partial = torch.empty((B, n_blocks, 3 * Cc + 2), dtype=torch.float32, device=logits.device)
     result = torch.empty(3, dtype=torch.float32, device=logits.device)
-    cw = None if class_weights is None else class_weights.to(logits.device, torch.float32).contiguous()
+    sums = torch.empty((B, 3 * Cc + 2), dtype=torch.float32, device=logits.device)
     check(lib.mmseg_dicece_fwd(_ptr(logits), _ptr(target), B, Cc, N, dice_weight, ce_weight, smooth,
-                               1 if include_background else 0, _ptr(cw), _ptr(partial), n_blocks, _ptr(result),
-                               _stream()), "mmseg_dicece_fwd")
-    return result
+                               1 if include_background else 0, _ptr(class_weights), _ptr(partial), n_blocks,
+                               _ptr(result), _ptr(sums), _stream()), "mmseg_dicece_fwd")
+    return result, sums
+
+
+def dicece_bwd(logits: Tensor, target: Tensor, sums: Tensor, grad_out: Optional[Tensor], dice_weight: float,
+               ce_weight: float, smooth: float = 1.0, include_background: bool = True,
+               class_weights: Optional[Tensor] = None) -> Tensor:
+    B, Cc = logits.shape[:2]
+    N = logits[0, 0].numel()
+    dl = torch.empty_like(logits)
+    go = None if grad_out is None else grad_out.reshape(1).float().contiguous()
+    check(lib.mmseg_dicece_bwd(_ptr(logits), _ptr(target), B, Cc, N, dice_weight, ce_weight, smooth,
+                               1 if include_background else 0, _ptr(class_weights), _ptr(sums), _ptr(go), _ptr(dl),
+                               _stream()), "mmseg_dicece_bwd")
+    return dl
 
 
 def channel_mean(src: Blocked, c0: int, channels: int) -> Tensor:

@@ -1,0 +1,281 @@
+"""Sliding-window inference on B200 — drop-in for the call at reference src/trainer/trainer.py:381-392.
+
+`sliding_window_inference` keeps MONAI's call signature (the only API the reference uses) and semantics
+(SURVEY.md Appendix C): window grid with clamped last window, constant / gaussian importance map with the
+max(min, 1e-3) floor, weighted accumulation in window order, division by the count map.
+
+Engine path (predictor is a drop-in model with `.engine()`): windows are gathered straight into the engine's blocked
+input buffer by a kernel, evaluated `engine_batch` at a time (the result does not depend on the batch size because
+InstanceNorm statistics are per window), and blended by an owner-thread kernel in window order — no atomics, same
+accumulation order as the reference loop.  One batch = gather + forward + blend is captured in a CUDA graph.
+
+Multi-GPU (`shard_windows`): the ordered window list is cut into `world` contiguous chunks (axis-0 slabs); every
+rank accumulates its chunk locally, then each rank receives — in rank order — the other ranks' partial sums that
+fall into the axis-0 slab it owns, finalises that slab and the uint8 labels are all-gathered.
+"""
+import math
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+
+from ... import kernels as K
+from ... import _lib
+
+Tensor = torch.Tensor
+
+
+# ------------------------------------------------------------------------------------------ window arithmetic (host)
+def _scan_interval(image_size, roi_size, overlap) -> List[int]:
+    out = []
+    for im, r in zip(image_size, roi_size):
+        if r == im:
+            out.append(int(r))
+        else:
+            iv = int(r * (1 - overlap))
+            out.append(iv if iv > 0 else 1)
+    return out
+
+
+def window_starts(image_size: Sequence[int], roi_size: Sequence[int], overlap: float) -> List[Tuple[int, ...]]:
+    """Window origins in MONAI order (axis 0 slowest, last axis fastest), last window clamped to the border."""
+    per_axis = []
+    for im, r, iv in zip(image_size, roi_size, _scan_interval(image_size, roi_size, overlap)):
+        num = int(math.ceil(float(im) / iv))
+        n = 1
+        for d in range(num):
+            if d * iv + r >= im:
+                n = d + 1
+                break
+        per_axis.append([min(d * iv, im - r) for d in range(n)])
+    out: List[Tuple[int, ...]] = [()]
+    for starts in per_axis:
+        out = [o + (s,) for o in out for s in starts]
+    return out
+
+
+def importance_tables(roi_size: Sequence[int], mode: str, sigma_scale: float = 0.125):
+    """Separable factors of the importance map and the clamp floor.
+
+    gaussian: w[z,y,x] = max((g_z*g_y)*g_x, floor), g[i] = exp(-(i-(r-1)/2)^2 / (2 (sigma_scale r)^2)) in fp32,
+    floor = max(min(w), 1e-3) — identical arithmetic (and association order) to the fp32 tensor MONAI builds.
+    """
+    tabs = []
+    if mode == "constant":
+        for r in roi_size:
+            tabs.append(torch.ones(r, dtype=torch.float32))
+        return tabs, 1.0
+    if mode != "gaussian":
+        raise ValueError(f"unsupported blend mode {mode!r} (constant | gaussian)")
+    for r in roi_size:
+        sigma = r * sigma_scale
+        x = torch.arange(-(r - 1) / 2.0, (r - 1) / 2.0 + 1, dtype=torch.float32)
+        tabs.append(torch.exp(x ** 2 / (-2 * sigma ** 2)))
+    wmin = (tabs[0].min() * tabs[1].min()) * tabs[2].min()
+    return tabs, max(float(wmin), 1e-3)
+
+
+def shard_windows(n_windows: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous chunk [lo, hi) of the ordered window list owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n_windows, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def owned_slabs(starts: Sequence[Tuple[int, ...]], roi0: int, size0: int, world: int) -> List[Tuple[int, int]]:
+    """Axis-0 partition [lo, hi) per rank: rank r owns from its first window's origin to the next rank's."""
+    cuts = []
+    for r in range(world):
+        lo, hi = shard_windows(len(starts), world, r)
+        cuts.append(min(s[0] for s in starts[lo:hi]) if hi > lo else None)
+    out = []
+    for r in range(world):
+        if cuts[r] is None:
+            out.append((size0, size0))
+            continue
+        lo = 0 if r == 0 else cuts[r]
+        nxt = next((cuts[q] for q in range(r + 1, world) if cuts[q] is not None), size0)
+        out.append((lo, max(lo, nxt)))
+    # make the slabs a partition even when consecutive ranks start at the same origin
+    fixed, prev_hi = [], 0
+    for lo, hi in out:
+        lo = max(lo, prev_hi) if hi > prev_hi else prev_hi
+        hi = max(hi, lo)
+        fixed.append((lo, hi))
+        prev_hi = hi
+    fixed[-1] = (fixed[-1][0], size0)
+    return fixed
+
+
+def touched_range(starts: Sequence[Tuple[int, ...]], lo: int, hi: int, roi0: int) -> Tuple[int, int]:
+    """Axis-0 range written by windows [lo, hi)."""
+    if hi <= lo:
+        return (0, 0)
+    s = [st[0] for st in starts[lo:hi]]
+    return min(s), max(s) + roi0
+
+
+# ------------------------------------------------------------------------------------------ the inferer
+class SlidingWindowInferer:
+    """Stateful sliding-window engine for one (volume shape, roi, overlap, mode)."""
+
+    def __init__(self, model, roi_size=(96, 96, 96), overlap: float = 0.5, mode: str = "constant",
+                 sigma_scale: float = 0.125, engine_batch: int = 8, use_graph: bool = True):
+        self.model = model
+        self.roi = tuple(int(r) for r in roi_size)
+        self.overlap, self.mode, self.sigma_scale = overlap, mode, sigma_scale
+        self.engine_batch = engine_batch
+        self.use_graph = use_graph
+        self._state = None
+        self.launches_last = 0
+
+    # -- helpers
+    def _backbone(self):
+        m = self.model
+        return m.backbone if hasattr(m, "backbone") else m
+
+    def _setup(self, C: int, vol_shape, device):
+        key = (C, tuple(vol_shape), str(device), self._backbone().numeric_mode)
+        if self._state is not None and self._state["key"] == key:
+            return self._state
+        bb = self._backbone()
+        eng = bb.engine()
+        K_out = bb.out_channels
+        VZ, VY, VX = vol_shape
+        starts = window_starts(vol_shape, self.roi, self.overlap)
+        tabs, floor = importance_tables(self.roi, self.mode, self.sigma_scale)
+        nb = min(self.engine_batch, len(starts))
+        st = {
+            "key": key, "eng": eng, "starts": starts, "nb": nb, "K": K_out,
+            "wz": tabs[0].to(device), "wy": tabs[1].to(device), "wx": tabs[2].to(device), "floor": floor,
+            # all window origins live on the device; each batch is a stream-ordered D2D copy into the fixed
+            # `starts_dev` slot the (graph-captured) kernels read, so no host sync sits between batches
+            "starts_all": torch.tensor(starts, dtype=torch.int32).to(device),
+            "starts_dev": torch.zeros((nb, 3), dtype=torch.int32, device=device),
+            "logits": torch.empty((nb, K_out, *self.roi), dtype=torch.float32, device=device),
+            "out": torch.empty((K_out, VZ, VY, VX), dtype=torch.float32, device=device),
+            "count": torch.empty((VZ, VY, VX), dtype=torch.float32, device=device),
+            "graph": None, "vol_ptr": None,
+        }
+        self._state = st
+        return st
+
+    def _run_batch(self, st, volume: Tensor, n: int) -> None:
+        """gather -> forward -> blend for the n windows whose origins are in starts_dev[:n]."""
+        eng = st["eng"]
+        rz, ry, rx = self.roi
+        buf = eng.input_buffer(n, rz, ry, rx, volume.device)
+        K.swi_gather(volume, st["starts_dev"], n, self.roi, buf)
+        logits = st["logits"][:n]
+        eng.forward_blocked(n, rz, ry, rx, logits)
+        for j in range(n):
+            K.swi_blend(logits[j:j + 1], st["starts_dev"][j], 1, st["wz"], st["wy"], st["wx"], st["floor"], st["out"],
+                        st["count"], (-1, 0, 0, 0, 0, 0))
+
+    @torch.no_grad()
+    def accumulate(self, volume: Tensor, lo: int = 0, hi: Optional[int] = None) -> None:
+        """Accumulate windows [lo, hi) of `volume` [C, VZ, VY, VX] (fp32, CUDA) into out / count (zeroed first)."""
+        _lib.require_device()
+        assert volume.dim() == 4 and volume.is_cuda and volume.dtype == torch.float32 and volume.is_contiguous()
+        st = self._setup(volume.shape[0], volume.shape[1:], volume.device)
+        starts = st["starts"]
+        hi = len(starts) if hi is None else hi
+        st["out"].zero_()
+        st["count"].zero_()
+        nb = st["nb"]
+        i = lo
+        while i < hi:
+            n = min(nb, hi - i)
+            st["starts_dev"][:n].copy_(st["starts_all"][i:i + n], non_blocking=True)
+            if self.use_graph and n == nb:
+                if st["graph"] is None or st["vol_ptr"] != volume.data_ptr():
+                    self._run_batch(st, volume, n)  # warm-up: allocates workspaces, packs weights
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    # the warm-up already accumulated this batch: capture replays nothing until g.replay()
+                    with torch.cuda.graph(g, stream=None):
+                        self._run_batch(st, volume, n)
+                    st["graph"], st["vol_ptr"] = g, volume.data_ptr()
+                else:
+                    st["graph"].replay()
+            else:
+                self._run_batch(st, volume, n)
+            i += n
+
+    @torch.no_grad()
+    def finalize(self, normalize: bool = True, labels: bool = True, z0: int = 0, z1: Optional[int] = None):
+        """out /= count (in place) and / or argmax -> uint8 over the axis-0 slab [z0, z1)."""
+        st = self._state
+        VZ = st["out"].shape[1]
+        z1 = VZ if z1 is None else z1
+        lab = None
+        if z1 > z0:
+            if z0 == 0 and z1 == VZ:
+                out_v, cnt_v = st["out"], st["count"]
+            else:
+                # a z-slab of [K, VZ, VY, VX] is not contiguous across K: finalize works on a packed copy
+                out_v = st["out"][:, z0:z1].contiguous()
+                cnt_v = st["count"][z0:z1].contiguous()
+            lab = torch.empty(cnt_v.shape, dtype=torch.uint8, device=cnt_v.device) if labels else None
+            K.swi_finalize(out_v, cnt_v, normalize, lab)
+            if normalize and out_v is not st["out"]:
+                st["out"][:, z0:z1].copy_(out_v)
+        return (st["out"] if normalize else None), lab
+
+    @torch.no_grad()
+    def __call__(self, inputs: Tensor, return_labels: bool = False):
+        """inputs [1, C, H, W, D] -> logits [1, K, H, W, D] (input dtype fp32) or uint8 labels [H, W, D]."""
+        assert inputs.dim() == 5 and inputs.shape[0] == 1, "engine path takes one volume at a time (trainer.py:357)"
+        vol = inputs[0].contiguous().float()
+        self.accumulate(vol)
+        out, lab = self.finalize(normalize=not return_labels, labels=return_labels)
+        return lab if return_labels else out.unsqueeze(0)
+
+
+def _pad_to_roi(inputs: Tensor, roi: Sequence[int], cval: float):
+    nsp = inputs.dim() - 2
+    pad = []
+    for k in range(nsp - 1, -1, -1):
+        diff = max(roi[k] - inputs.shape[k + 2], 0)
+        half = diff // 2
+        pad.extend([half, diff - half])
+    if not any(pad):
+        return inputs, None
+    return torch.nn.functional.pad(inputs, pad, mode="constant", value=cval), pad
+
+
+_INFERERS = {}
+
+
+def sliding_window_inference(inputs: Tensor, roi_size, sw_batch_size: int, predictor: Callable, overlap: float = 0.25,
+                             mode: str = "constant", sigma_scale: float = 0.125, padding_mode: str = "constant",
+                             cval: float = 0.0, **kwargs) -> Tensor:
+    """Signature-compatible with monai.inferers.sliding_window_inference as called by the reference.
+
+    `sw_batch_size` is accepted for compatibility; the engine picks its own batch (the result is independent of it).
+    """
+    if not inputs.is_cuda:
+        raise RuntimeError("mmseg_b200 sliding_window_inference runs on CUDA tensors only (no CPU fallback)")
+    if padding_mode != "constant":
+        raise NotImplementedError("only padding_mode='constant' (the reference's default) is implemented")
+    bb = predictor.backbone if hasattr(predictor, "backbone") else predictor
+    if not hasattr(bb, "engine"):
+        raise NotImplementedError("predictor must be a mmseg_b200 drop-in model (UNet3D / DualEncoder)")
+    roi = [int(r) if r and r > 0 else int(s) for r, s in zip(roi_size, inputs.shape[2:])]
+    orig = inputs.shape[2:]
+    inputs, pad = _pad_to_roi(inputs.float(), roi, cval)
+    key = (id(predictor), tuple(roi), overlap, mode, sigma_scale)
+    inf = _INFERERS.get(key)
+    if inf is None:
+        inf = _INFERERS[key] = SlidingWindowInferer(predictor, roi, overlap, mode, sigma_scale)
+    outs = []
+    for b in range(inputs.shape[0]):
+        outs.append(inf(inputs[b:b + 1]).clone() if inputs.shape[0] > 1 else inf(inputs[b:b + 1]))
+    out = torch.cat(outs) if len(outs) > 1 else outs[0]
+    if pad is not None:
+        nsp = len(orig)
+        crop = [slice(None), slice(None)]
+        for k in range(nsp):
+            before = pad[2 * (nsp - 1 - k)]
+            crop.append(slice(before, before + orig[k]))
+        out = out[tuple(crop)]
+    return out

@@ -12,7 +12,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = {
     "conv0": [
         "conv_case(16, 32, (4, 6, 20), name='first')",
-        "conv_case(16, 32, (4, 6, 20), flags=1, name='first-swapped-desc')",
     ],
     "conv": [
         "conv_case(16, 32, (8, 12, 20))",
