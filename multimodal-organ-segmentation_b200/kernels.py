@@ -23,6 +23,28 @@ def _ptr(t: Optional[Tensor]) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
+# kernels launched by each C-ABI entry point (bench.py reports the count as `gpu_launches`)
+KERNELS_PER_CALL = {"mmseg_dicece_fwd": 2, "mmseg_channel_mean": 2}
+LAUNCHES = [0]
+# when a list, every C-ABI call is bracketed by CUDA events on the current stream: (name, info, ev0, ev1)
+PROFILE: Optional[list] = None
+_INFO = [None]
+
+
+def _call(name: str, *args) -> None:
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    rc = getattr(lib, name)(*args)
+    if prof is not None:
+        e1.record()
+        prof.append((name, _INFO[0], e0, e1))
+        _INFO[0] = None
+    check(rc, name)
+    LAUNCHES[0] += KERNELS_PER_CALL.get(name, 1)
+
+
 # --------------------------------------------------------------------------------------------- blocked buffers
 class Blocked:
     """A blocked activation buffer [n_img, cbt, Z, Y, X, 8] bf16.
@@ -49,8 +71,8 @@ class Blocked:
         channels = self.channels - c0 if channels is None else channels
         assert c0 % 8 == 0
         out = torch.empty((self.n_img, channels, self.Z, self.Y, self.X), dtype=torch.float32, device=self.t.device)
-        check(lib.mmseg_unpack_ncdhw(_ptr(self.t), _ptr(out), self.n_img, channels, self.Z, self.Y, self.X,
-                                     self.cbt, c0 // 8, self.lo_off, _stream()), "mmseg_unpack_ncdhw")
+        _call("mmseg_unpack_ncdhw", _ptr(self.t), _ptr(out), self.n_img, channels, self.Z, self.Y, self.X,
+                                     self.cbt, c0 // 8, self.lo_off, _stream())
         return out
 
 
@@ -60,8 +82,7 @@ def pack_ncdhw(x: Tensor, dst: Blocked, c0: int = 0) -> None:
     n, Cc, Z, Y, X = x.shape
     cb = ((Cc + 15) // 16) * 2
     assert (n, Z, Y, X) == (dst.n_img, dst.Z, dst.Y, dst.X) and c0 % 8 == 0 and c0 // 8 + cb <= dst.cb
-    check(lib.mmseg_pack_ncdhw(_ptr(x), _ptr(dst.t), n, Cc, Z, Y, X, dst.cbt, c0 // 8, dst.lo_off, cb, _stream()),
-          "mmseg_pack_ncdhw")
+    _call("mmseg_pack_ncdhw", _ptr(x), _ptr(dst.t), n, Cc, Z, Y, X, dst.cbt, c0 // 8, dst.lo_off, cb, _stream())
 
 
 # --------------------------------------------------------------------------------------------- weight packing
@@ -177,14 +198,21 @@ def conv3d(src: Blocked, pw: PackedConv, a_cb: Sequence[int], dst: Tensor, out_m
     if stats is not None:
         need = src.n_img * tile.tiles_per_img * pw.n_out * 2
         assert stats.numel() >= need and stats.dtype == torch.float32
-    check(lib.mmseg_conv3d_fwd(C.byref(a), _stream()), "mmseg_conv3d_fwd")
+    if PROFILE is not None:
+        n_real = pw.out_channels * (8 if pw.is_convt else 1)
+        _INFO[0] = {"flops": 2.0 * src.n_img * src.nvox * pw.cin * n_real * pw.ksize ** 3,
+                    "issued_flops": 2.0 * src.n_img * src.nvox * pw.n_kchunks * 16 * pw.n_out * pw.ksize ** 3,
+                    "layer": f"k{pw.ksize} cin{pw.cin} n{n_real} {src.Z}x{src.Y}x{src.X} img{src.n_img}",
+                    "tile": (tile.TX, tile.TY, tile.TZ, tile.NT, tile.stages),
+                    "ctas": tile.tiles_per_img * src.n_img * tile.n_ntiles}
+    _call("mmseg_conv3d_fwd", C.byref(a), _stream())
     return tile
 
 
 def instnorm_finalize(stats: Tensor, n_img: int, tiles_per_img: int, channels: int, voxels: int, mean_rstd: Tensor,
                       eps: float = 1e-5) -> None:
-    check(lib.mmseg_instnorm_finalize(_ptr(stats), n_img, tiles_per_img, channels, voxels, eps, _ptr(mean_rstd),
-                                      _stream()), "mmseg_instnorm_finalize")
+    _call("mmseg_instnorm_finalize", _ptr(stats), n_img, tiles_per_img, channels, voxels, eps, _ptr(mean_rstd),
+                                      _stream())
 
 
 def instnorm_act_apply(raw: Tensor, raw_is_f32: bool, mean_rstd: Tensor, n_img: int, channels: int,
@@ -199,29 +227,34 @@ def instnorm_act_apply(raw: Tensor, raw_is_f32: bool, mean_rstd: Tensor, n_img: 
     if pooled is not None:
         a.pool_cbt, a.pool_cb_off, a.pool_lo_off = pooled.cbt, pooled_c0 // 8, pooled.lo_off
     a.slope = slope
-    check(lib.mmseg_instnorm_act_apply(C.byref(a), _stream()), "mmseg_instnorm_act_apply")
+    if PROFILE is not None:
+        nel = n_img * channels * Z * Y * X
+        out_b = 2 * (2 if dst.split else 1)
+        _INFO[0] = {"bytes": nel * ((4 if raw_is_f32 else 2) + out_b) + (nel // 8 * out_b if pooled is not None else 0),
+                    "layer": f"c{channels} {Z}x{Y}x{X} img{n_img} pool{int(pooled is not None)}"}
+    _call("mmseg_instnorm_act_apply", C.byref(a), _stream())
 
 
 def swi_gather(volume: Tensor, starts_dev: Tensor, n_win: int, roi: Tuple[int, int, int], dst: Blocked) -> None:
     Cc, VZ, VY, VX = volume.shape
     cb = ((Cc + 15) // 16) * 2
-    check(lib.mmseg_swi_gather(_ptr(volume), Cc, VZ, VY, VX, _ptr(starts_dev), n_win, roi[0], roi[1], roi[2],
-                               _ptr(dst.t), dst.cbt, dst.lo_off, cb, _stream()), "mmseg_swi_gather")
+    _call("mmseg_swi_gather", _ptr(volume), Cc, VZ, VY, VX, _ptr(starts_dev), n_win, roi[0], roi[1], roi[2],
+                               _ptr(dst.t), dst.cbt, dst.lo_off, cb, _stream())
 
 
 def swi_blend(win_logits: Tensor, starts_dev: Tensor, n_win: int, wz: Tensor, wy: Tensor, wx: Tensor, w_floor: float,
               out: Tensor, count: Tensor, box: Tuple[int, int, int, int, int, int]) -> None:
     K, VZ, VY, VX = out.shape
     _, _, RZ, RY, RX = win_logits.shape
-    check(lib.mmseg_swi_blend(_ptr(win_logits), _ptr(starts_dev), n_win, K, RZ, RY, RX, _ptr(wz), _ptr(wy), _ptr(wx),
-                              w_floor, _ptr(out), _ptr(count), VZ, VY, VX, *box, _stream()), "mmseg_swi_blend")
+    _call("mmseg_swi_blend", _ptr(win_logits), _ptr(starts_dev), n_win, K, RZ, RY, RX, _ptr(wz), _ptr(wy), _ptr(wx),
+                              w_floor, _ptr(out), _ptr(count), VZ, VY, VX, *box, _stream())
 
 
 def swi_finalize(out: Tensor, count: Tensor, normalize_in_place: bool, labels: Optional[Tensor]) -> None:
     K = out.shape[0]
     vox = count.numel()
-    check(lib.mmseg_swi_finalize(_ptr(out), _ptr(count), K, vox, 1 if normalize_in_place else 0, _ptr(labels),
-                                 _stream()), "mmseg_swi_finalize")
+    _call("mmseg_swi_finalize", _ptr(out), _ptr(count), K, vox, 1 if normalize_in_place else 0, _ptr(labels),
+                                 _stream())
 
 
 def dicece_fwd(logits: Tensor, target: Tensor, dice_weight: float, ce_weight: float, smooth: float = 1.0,
@@ -236,9 +269,9 @@ def dicece_fwd(logits: Tensor, target: Tensor, dice_weight: float, ce_weight: fl
     partial = torch.empty((B, n_blocks, 3 * Cc + 2), dtype=torch.float32, device=logits.device)
     result = torch.empty(3, dtype=torch.float32, device=logits.device)
     sums = torch.empty((B, 3 * Cc + 2), dtype=torch.float32, device=logits.device)
-    check(lib.mmseg_dicece_fwd(_ptr(logits), _ptr(target), B, Cc, N, dice_weight, ce_weight, smooth,
+    _call("mmseg_dicece_fwd", _ptr(logits), _ptr(target), B, Cc, N, dice_weight, ce_weight, smooth,
                                1 if include_background else 0, _ptr(class_weights), _ptr(partial), n_blocks,
-                               _ptr(result), _ptr(sums), _stream()), "mmseg_dicece_fwd")
+                               _ptr(result), _ptr(sums), _stream())
     return result, sums
 
 
@@ -249,9 +282,9 @@ def dicece_bwd(logits: Tensor, target: Tensor, sums: Tensor, grad_out: Optional[
     N = logits[0, 0].numel()
     dl = torch.empty_like(logits)
     go = None if grad_out is None else grad_out.reshape(1).float().contiguous()
-    check(lib.mmseg_dicece_bwd(_ptr(logits), _ptr(target), B, Cc, N, dice_weight, ce_weight, smooth,
+    _call("mmseg_dicece_bwd", _ptr(logits), _ptr(target), B, Cc, N, dice_weight, ce_weight, smooth,
                                1 if include_background else 0, _ptr(class_weights), _ptr(sums), _ptr(go), _ptr(dl),
-                               _stream()), "mmseg_dicece_bwd")
+                               _stream())
     return dl
 
 
@@ -261,8 +294,8 @@ def channel_mean(src: Blocked, c0: int, channels: int) -> Tensor:
     n_chunks = max(1, min(64, (src.nvox + 4095) // 4096))
     partial = torch.empty((src.n_img * cb, n_chunks, 8), dtype=torch.float32, device=src.t.device)
     mean = torch.empty((src.n_img, channels), dtype=torch.float32, device=src.t.device)
-    check(lib.mmseg_channel_mean(_ptr(src.t), src.n_img, src.cbt, c0 // 8, src.lo_off, cb, src.nvox, _ptr(partial),
-                                 n_chunks, _ptr(mean), _stream()), "mmseg_channel_mean")
+    _call("mmseg_channel_mean", _ptr(src.t), src.n_img, src.cbt, c0 // 8, src.lo_off, cb, src.nvox, _ptr(partial),
+                                 n_chunks, _ptr(mean), _stream())
     return mean
 
 
@@ -272,19 +305,18 @@ def gate_mlp(pooled: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor) -> 
     out = torch.empty((n, M), dtype=torch.float32, device=pooled.device)
     f = lambda t: t.detach().float().contiguous()
     w1, b1, w2, b2 = f(w1), f(b1), f(w2), f(b2)
-    check(lib.mmseg_gate_mlp(_ptr(pooled), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), n, MC, H, M, _ptr(out), _stream()),
-          "mmseg_gate_mlp")
+    _call("mmseg_gate_mlp", _ptr(pooled), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), n, MC, H, M, _ptr(out), _stream())
     return out
 
 
 def modality_combine(src: Blocked, M: int, channels: int, dst: Blocked, dst_c0: int, weights: Optional[Tensor],
                      uniform_weight: float = 1.0) -> None:
-    check(lib.mmseg_modality_combine(_ptr(src.t), src.n_img, src.cbt, src.lo_off, M, channels // 8, src.nvox,
+    _call("mmseg_modality_combine", _ptr(src.t), src.n_img, src.cbt, src.lo_off, M, channels // 8, src.nvox,
                                      _ptr(weights), uniform_weight, _ptr(dst.t), dst.cbt, dst_c0 // 8, dst.lo_off,
-                                     _stream()), "mmseg_modality_combine")
+                                     _stream())
 
 
 def maxpool3d_2(src: Blocked, dst: Blocked, channels: Optional[int] = None, src_c0: int = 0, dst_c0: int = 0) -> None:
     channels = src.channels if channels is None else channels
-    check(lib.mmseg_maxpool3d_2(_ptr(src.t), src.n_img, src.cbt, src_c0 // 8, src.lo_off, channels // 8, src.Z, src.Y,
-                                src.X, _ptr(dst.t), dst.cbt, dst_c0 // 8, dst.lo_off, _stream()), "mmseg_maxpool3d_2")
+    _call("mmseg_maxpool3d_2", _ptr(src.t), src.n_img, src.cbt, src_c0 // 8, src.lo_off, channels // 8, src.Z, src.Y,
+                                src.X, _ptr(dst.t), dst.cbt, dst_c0 // 8, dst.lo_off, _stream())

@@ -133,6 +133,13 @@ class SlidingWindowInferer:
         m = self.model
         return m.backbone if hasattr(m, "backbone") else m
 
+    def device_volume(self, shape, device) -> Tensor:
+        """A persistent device staging buffer for host volumes of `shape` (keeps its address: graph-safe)."""
+        v = getattr(self, "_dev_vol", None)
+        if v is None or tuple(v.shape) != tuple(shape) or v.device != device:
+            v = self._dev_vol = torch.zeros(tuple(shape), dtype=torch.float32, device=device)
+        return v
+
     def _setup(self, C: int, vol_shape, device):
         key = (C, tuple(vol_shape), str(device), self._backbone().numeric_mode)
         if self._state is not None and self._state["key"] == key:
@@ -152,10 +159,12 @@ class SlidingWindowInferer:
             "starts_all": torch.tensor(starts, dtype=torch.int32).to(device),
             "starts_dev": torch.zeros((nb, 3), dtype=torch.int32, device=device),
             "logits": torch.empty((nb, K_out, *self.roi), dtype=torch.float32, device=device),
-            "out": torch.empty((K_out, VZ, VY, VX), dtype=torch.float32, device=device),
-            "count": torch.empty((VZ, VY, VX), dtype=torch.float32, device=device),
-            "graph": None, "vol_ptr": None,
+            # weighted-logit accumulator and the count map share one allocation: acc[:K] = out, acc[K] = count,
+            # so a rank's partial result travels as ONE tensor in the sharded exchange
+            "acc": torch.empty((K_out + 1, VZ, VY, VX), dtype=torch.float32, device=device),
+            "graph": None, "vol_ptr": None, "launches_per_batch": 0,
         }
+        st["out"], st["count"] = st["acc"][:K_out], st["acc"][K_out]
         self._state = st
         return st
 
@@ -179,8 +188,7 @@ class SlidingWindowInferer:
         st = self._setup(volume.shape[0], volume.shape[1:], volume.device)
         starts = st["starts"]
         hi = len(starts) if hi is None else hi
-        st["out"].zero_()
-        st["count"].zero_()
+        st["acc"].zero_()
         nb = st["nb"]
         i = lo
         while i < hi:
@@ -191,12 +199,16 @@ class SlidingWindowInferer:
                     self._run_batch(st, volume, n)  # warm-up: allocates workspaces, packs weights
                     torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
-                    # the warm-up already accumulated this batch: capture replays nothing until g.replay()
+                    l0 = K.LAUNCHES[0]
+                    # capture records the launches without running them (the warm-up already did this batch)
                     with torch.cuda.graph(g, stream=None):
                         self._run_batch(st, volume, n)
+                    st["launches_per_batch"] = K.LAUNCHES[0] - l0
+                    K.LAUNCHES[0] = l0
                     st["graph"], st["vol_ptr"] = g, volume.data_ptr()
                 else:
                     st["graph"].replay()
+                    K.LAUNCHES[0] += st["launches_per_batch"]
             else:
                 self._run_batch(st, volume, n)
             i += n
@@ -229,6 +241,132 @@ class SlidingWindowInferer:
         self.accumulate(vol)
         out, lab = self.finalize(normalize=not return_labels, labels=return_labels)
         return lab if return_labels else out.unsqueeze(0)
+
+
+    # ------------------------------------------------------------------ multi-GPU: window chunks + one exchange
+    @torch.no_grad()
+    def run_sharded(self, volume: Tensor, group=None, want: str = "labels"):
+        """One volume over all ranks of `group`: rank r evaluates its contiguous chunk of the ordered window list,
+        then ONE exchange moves every partial (weighted logits + count, K+1 channels) that falls into another rank's
+        axis-0 slab to that owner, which adds them in rank order (deterministic), finalises its slab, and the uint8
+        labels are all-gathered.  `volume` must hold valid data at least over this rank's input range
+        (see `input_range`).  Returns uint8 labels [VZ, VY, VX] on every rank."""
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        st = self._setup(volume.shape[0], volume.shape[1:], volume.device)
+        starts = st["starts"]
+        lo, hi = shard_windows(len(starts), world, rank)
+        self.accumulate(volume, lo, hi)
+        if world == 1:
+            return self.finalize(normalize=False, labels=True)[1]
+        VZ = st["acc"].shape[1]
+        plan = exchange_plan(starts, self.roi[0], VZ, world)
+        exchange_partials(st["acc"], plan, rank, world, group)
+        z0, z1 = plan["slabs"][rank]
+        _, lab = self.finalize(normalize=False, labels=True, z0=z0, z1=z1)
+        return gather_label_slabs(lab, plan["slabs"], st["acc"].shape[1:], rank, world, group, volume.device)
+
+    def input_range(self, vol_shape, world: int, rank: int) -> Tuple[int, int]:
+        """Axis-0 range of the input volume that rank's window chunk reads."""
+        starts = window_starts(vol_shape, self.roi, self.overlap)
+        lo, hi = shard_windows(len(starts), world, rank)
+        return touched_range(starts, lo, hi, self.roi[0])
+
+
+def exchange_plan(starts, roi0: int, size0: int, world: int):
+    """Who sends which axis-0 range to whom: sends[src][dst] = (z0, z1) = touched(src) ∩ slab(dst), src != dst."""
+    slabs = owned_slabs(starts, roi0, size0, world)
+    touched = [touched_range(starts, *shard_windows(len(starts), world, r), roi0) for r in range(world)]
+    sends = [[None] * world for _ in range(world)]
+    for src in range(world):
+        for dst in range(world):
+            if src == dst:
+                continue
+            z0, z1 = max(touched[src][0], slabs[dst][0]), min(touched[src][1], slabs[dst][1])
+            if z1 > z0:
+                sends[src][dst] = (z0, z1)
+    return {"slabs": slabs, "touched": touched, "sends": sends}
+
+
+def exchange_partials(acc: Tensor, plan, rank: int, world: int, group=None) -> None:
+    """The single data-path exchange of sharded inference: point-to-point sends of overlap regions to their owner
+    (NCCL over NVLink on GPUs, gloo in the CPU tests), then a rank-ordered add on the owner."""
+    import torch.distributed as dist
+    sends = plan["sends"]
+    ops, recv_bufs, send_bufs = [], {}, []
+    for src in range(world):
+        rng = sends[src][rank]
+        if rng is not None:
+            buf = torch.empty((acc.shape[0], rng[1] - rng[0], *acc.shape[2:]), dtype=acc.dtype, device=acc.device)
+            recv_bufs[src] = (rng, buf)
+            ops.append(dist.P2POp(dist.irecv, buf, src if group is None else dist.get_global_rank(group, src), group))
+    for dst in range(world):
+        rng = sends[rank][dst]
+        if rng is not None:
+            buf = acc[:, rng[0]:rng[1]].contiguous()
+            send_bufs.append(buf)
+            ops.append(dist.P2POp(dist.isend, buf, dst if group is None else dist.get_global_rank(group, dst), group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    for src in sorted(recv_bufs):  # fixed (rank) order -> deterministic sums
+        (z0, z1), buf = recv_bufs[src]
+        acc[:, z0:z1] += buf
+
+
+def gather_label_slabs(lab: Optional[Tensor], slabs, vol_shape, rank: int, world: int, group, device) -> Tensor:
+    """all-gather of the per-rank uint8 label slabs (padded to the largest slab) into the full label volume."""
+    import torch.distributed as dist
+    VZ, VY, VX = vol_shape
+    zmax = max(z1 - z0 for z0, z1 in slabs)
+    mine = torch.zeros((zmax, VY, VX), dtype=torch.uint8, device=device)
+    z0, z1 = slabs[rank]
+    if z1 > z0:
+        mine[:z1 - z0] = lab
+    flat = torch.empty((world * zmax, VY, VX), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(flat, mine, group=group)
+    allb = flat.view(world, zmax, VY, VX)
+    full = torch.empty((VZ, VY, VX), dtype=torch.uint8, device=device)
+    for r, (a, b) in enumerate(slabs):
+        if b > a:
+            full[a:b] = allb[r, :b - a]
+    return full
+
+
+@torch.no_grad()
+def predict_volume(model, image_host: Tensor, roi_size=(96, 96, 96), overlap: float = 0.5, mode: str = "constant",
+                   engine_batch: int = 8, group=None, out_host: Optional[Tensor] = None) -> Tensor:
+    """Host-to-host inference of one volume — the arithmetic of Trainer.predict (reference trainer.py:357-367):
+    image [C, H, W, D] fp32 in (pinned) host memory -> uint8 label map [H, W, D] in host memory.
+
+    Every step is stream-ordered: H2D copy of the input range this rank needs, sliding-window accumulation, the
+    sharded exchange when torch.distributed is initialised with more than one rank, finalize + argmax, D2H of labels.
+    """
+    import torch.distributed as dist
+    dev = next(model.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("predict_volume needs the model on a CUDA device (no CPU fallback)")
+    assert image_host.dim() == 4 and image_host.dtype == torch.float32 and not image_host.is_cuda
+    key = (id(model), tuple(roi_size), overlap, mode, engine_batch)
+    inf = _INFERERS.get(key)
+    if inf is None:
+        inf = _INFERERS[key] = SlidingWindowInferer(model, roi_size, overlap, mode, engine_batch=engine_batch)
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    vol = inf.device_volume(image_host.shape, dev)
+    z0, z1 = inf.input_range(image_host.shape[1:], world, rank)
+    vol[:, z0:z1].copy_(image_host[:, z0:z1], non_blocking=True)
+    if world > 1:
+        lab = inf.run_sharded(vol, group)
+    else:
+        inf.accumulate(vol)
+        lab = inf.finalize(normalize=False, labels=True)[1]
+    if out_host is None:
+        out_host = torch.empty(lab.shape, dtype=torch.uint8, pin_memory=True)
+    out_host.copy_(lab, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return out_host
 
 
 def _pad_to_roi(inputs: Tensor, roi: Sequence[int], cval: float):

@@ -149,6 +149,15 @@ def cross_attention_fusion(sd: SD, q_feat: Tensor, kv_feat: Tensor, num_heads: i
     return F.instance_norm(q_feat + out, eps=1e-5)
 
 
+def bidirectional_cross_attention(sd: SD, f1: Tensor, f2: Tensor, num_heads: int = 4, prefix: str = "",
+                                  dtype=torch.float32) -> Tensor:
+    """BidirectionalCrossAttention.forward — attention_fusion.py:193-216 (both directions, cat, 1x1 conv, IN, ReLU)."""
+    a = cross_attention_fusion(sd, f1, f2, num_heads, prefix + "cross_attn_1to2.", dtype)
+    b = cross_attention_fusion(sd, f2, f1, num_heads, prefix + "cross_attn_2to1.", dtype)
+    y = F.conv3d(torch.cat([a, b], 1), _p(sd, prefix + "fusion.0.weight", dtype), _p(sd, prefix + "fusion.0.bias", dtype))
+    return F.relu(F.instance_norm(y, eps=1e-5))
+
+
 def attention_fusion(sd: SD, feats: Sequence[Tensor], prefix: str = "", dtype=torch.float32) -> Tensor:
     """AttentionFusion.forward — attention_fusion.py:48-74 (same maths as CrossModalAttention)."""
     feats = [f.detach().to("cpu", dtype) for f in feats]

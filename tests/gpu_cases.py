@@ -220,3 +220,134 @@ def unet_time_case(n_img=1, S=96, mode="bf16", iters=5):
           f"{n_img * S ** 3 / ms / 1e3:.2f} Mvox/s", flush=True)
     assert torch.isfinite(y).all()
     return ms
+
+
+# ------------------------------------------------------------------------------------------------ golden vectors
+import os as _os
+
+_GOLD = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+
+
+def _gold(name):
+    return torch.load(_os.path.join(_GOLD, name + ".pt"), weights_only=False)
+
+
+def unet_golden_case(mode="parity"):
+    """Drop-in model built by OUR build_model from the reference's config + state_dict vs the reference's logits."""
+    import copy
+    from mmseg_b200.src.models.build import build_model
+    g = _gold("unet_small")
+    cfg = copy.deepcopy(g["config"])
+    cfg["hardware"]["device"] = "cuda"
+    m = build_model(cfg).eval()
+    missing = m.load_state_dict(g["state_dict"], strict=True)
+    m.set_numeric_mode(mode)
+    with torch.no_grad():
+        got, feats = m(g["x"].to(DEV), return_features=True)
+    max_abs, rel_l2, agree = _metrics(got.cpu(), g["logits"])
+    print(f"[unet golden mode={mode}] max_abs={max_abs:.3e} rel_l2={rel_l2:.3e} label_agree={agree * 100:.4f}%", flush=True)
+    if mode == "parity":
+        assert max_abs <= 2e-2 and rel_l2 <= 1e-3 and agree >= 0.999
+        for f, mean in zip(feats, g["feat_means"]):
+            assert abs(f.mean().item() - mean) < 1e-3
+    else:
+        assert max_abs <= 2e-1 and rel_l2 <= 5e-2 and agree >= 0.95
+
+
+# ------------------------------------------------------------------------------------------------ DiceCE
+def dicece_case(B=2, C=8, shape=(12, 10, 14), weights=False, include_background=True, seed=0):
+    from oracle import losses as OL
+    torch.manual_seed(seed)
+    lg = torch.randn(B, C, *shape) * 2
+    tg = torch.randint(0, C, (B, *shape))
+    cw = torch.rand(C) + 0.5 if weights else None
+    dw, cwt = (0.3, 0.7) if weights else (0.5, 0.5)
+    want, d, c = OL.dice_ce_loss(lg, tg, dw, cwt, class_weights=cw, include_background=include_background,
+                                 dtype=torch.float64)
+    res, sums = K.dicece_fwd(lg.to(DEV), tg.to(DEV), dw, cwt, 1.0, include_background,
+                             None if cw is None else cw.to(DEV))
+    r = res.cpu().double()
+    print(f"[dicece B={B} C={C} {shape} w={weights} bg={include_background}] got {r.tolist()} want "
+          f"{[want.item(), d.item(), c.item()]}", flush=True)
+    assert abs(r[0] - want) / abs(want) < 1e-5 and abs(r[1] - d) < 1e-5 and abs(r[2] - c) / abs(c) < 1e-5
+    if not weights and include_background:
+        gref = OL.dice_ce_grad(lg, tg, dw, cwt)
+        gout = torch.tensor([1.7], device=DEV)
+        got = K.dicece_bwd(lg.to(DEV), tg.to(DEV), sums, gout, dw, cwt).cpu().double() / 1.7
+        e = (got - gref).abs().max().item() / gref.abs().max().item()
+        print(f"   grad rel err {e:.2e}", flush=True)
+        assert e < 1e-4
+
+
+def dicece_golden_case():
+    g = _gold("losses")
+    lg, tg, R = g["logits"], g["target"], g["results"]
+    res, sums = K.dicece_fwd(lg.to(DEV), tg.to(DEV), 0.5, 0.5)
+    assert abs(res[0].item() - R["dicece"]["value"]) < 1e-3 * R["dicece"]["value"]
+    got = K.dicece_bwd(lg.to(DEV), tg.to(DEV), sums, None, 0.5, 0.5).cpu()
+    e = (got - R["dicece"]["grad"]).abs().max().item() / R["dicece"]["grad"].abs().max().item()
+    print(f"[dicece golden] loss {res[0].item():.7f} vs {R['dicece']['value']:.7f}; grad rel err {e:.2e}", flush=True)
+    assert e < 1e-4
+    k = _gold("loss_kat_seed7")
+    res, _ = K.dicece_fwd(k["logits"].to(DEV), k["target"].to(DEV), 0.5, 0.5)
+    assert abs(res[0].item() - 1.0275284) < 2e-6 and abs(res[1].item() - 0.5845465) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------ sliding window
+def swi_case(vol_shape=(48, 40, 36), roi=(32, 32, 32), mode="gaussian", net="unet", features=(16, 32), nmode="parity",
+             overlap=0.5, engine_batch=4):
+    """Engine sliding-window inference vs the oracle restatement with the oracle model as predictor."""
+    from mmseg_b200.src.models.backbones.unet import UNet3D
+    from mmseg_b200.src.trainer.inference import SlidingWindowInferer
+    from oracle.models import unet3d_forward
+    from oracle.sliding_window import sliding_window_inference as oswi
+    torch.manual_seed(0)
+    m = UNet3D(in_channels=2, out_channels=8, features=list(features)).eval()
+    sd = {"backbone." + k: v.clone() for k, v in m.state_dict().items()}
+    vol = torch.randn(1, 2, *vol_shape)
+    want = oswi(vol, roi, 4, lambda w: unet3d_forward(sd, w), overlap=overlap, mode=mode)
+    m = m.to(DEV).set_numeric_mode(nmode)
+    inf = SlidingWindowInferer(m, roi, overlap, mode, engine_batch=engine_batch)
+    got = inf(vol.to(DEV)).cpu()
+    lab = inf(vol.to(DEV), return_labels=True).cpu()
+    max_abs, rel_l2, agree = _metrics(got, want)
+    agree_lab = (lab.long() == want.argmax(1)[0]).double().mean().item()
+    print(f"[swi {vol_shape} roi={roi} {mode} {nmode}] max_abs={max_abs:.3e} rel_l2={rel_l2:.3e} "
+          f"label_agree={agree * 100:.4f}% uint8_labels={agree_lab * 100:.4f}%", flush=True)
+    if nmode == "parity":
+        assert max_abs <= 2e-2 and rel_l2 <= 1e-3 and agree >= 0.999 and agree_lab >= 0.999
+    else:
+        assert rel_l2 <= 5e-2 and agree >= 0.95
+
+
+def swi_constant_predictor_case():
+    """Blend/finalize kernels alone: accumulate a constant per class -> output is that constant, bit-exactly reproducible."""
+    from mmseg_b200.src.trainer.inference import window_starts, importance_tables
+    VZ, VY, VX = 50, 41, 70
+    roi = (32, 32, 32)
+    starts = window_starts((VZ, VY, VX), roi, 0.5)
+    tabs, floor = importance_tables(roi, "gaussian")
+    wz, wy, wx = (t.to(DEV) for t in tabs)
+    out = torch.zeros(3, VZ, VY, VX, device=DEV)
+    cnt = torch.zeros(VZ, VY, VX, device=DEV)
+    logits = torch.empty(1, 3, *roi, device=DEV)
+    for c in range(3):
+        logits[0, c] = float(c) - 0.75
+    sd = torch.tensor(starts, dtype=torch.int32, device=DEV)
+    for j in range(len(starts)):
+        K.swi_blend(logits, sd[j], 1, wz, wy, wx, floor, out, cnt, (-1, 0, 0, 0, 0, 0))
+    lab = torch.empty(VZ, VY, VX, dtype=torch.uint8, device=DEV)
+    K.swi_finalize(out, cnt, True, lab)
+    torch.cuda.synchronize()
+    assert (cnt > 0).all()
+    for c in range(3):
+        assert (out[c] - (c - 0.75)).abs().max().item() < 1e-5
+    assert (lab == 2).all()
+    # count map equals the oracle's (sum of shifted importance maps), same association order -> bit exact
+    from oracle.sliding_window import importance_map
+    w = importance_map(roi, "gaussian")
+    ref = torch.zeros(VZ, VY, VX)
+    for s in starts:
+        ref[s[0]:s[0] + 32, s[1]:s[1] + 32, s[2]:s[2] + 32] += w
+    assert torch.equal(cnt.cpu(), ref), (cnt.cpu() - ref).abs().max()
+    print("[swi constant predictor] exact", flush=True)
