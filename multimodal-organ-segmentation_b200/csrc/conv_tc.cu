@@ -8,8 +8,9 @@
 //   * every filter tap is the same smem plane read at a row offset (dy*PX + dx): the A descriptor's start address
 //     moves, nothing is re-loaded.  128-row M tiles run over the flattened (y, x) plane; rows that fall in the halo
 //     columns are computed and discarded (2/PX of the rows).
-//   * K loop = 16-channel chunks (outer) x input z-planes (ring of `stages` smem slots) x taps; the TZ*mt
-//     accumulators (NT fp32 columns each, <= 512 columns) stay resident in TMEM for the whole loop.
+//   * K loop = 16-channel chunks (outer) x input z-planes (ring of `stages` smem slots) x (dy, dx) taps; the TZ*mt
+//     accumulators (NT fp32 columns each, <= 512 columns) stay resident in TMEM for the whole loop.  The dz taps are
+//     folded into the MMA N dimension: one MMA adds an input plane to up to three adjacent output-plane accumulators.
 //   * warp 0: TMA producer, warp 1: MMA issuer (one elected lane each), warps 2-5: epilogue (TMEM -> registers ->
 //     HBM, plus per-channel sum / sum-of-squares partials for InstanceNorm).
 #include <cuda.h>
@@ -38,6 +39,7 @@ struct ConvKParams {
 
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
+constexpr int kMaxMT = 8;
 // smem header: barriers + tmem pointer + stats scratch
 struct __align__(16) SmemHeader {
   uint64_t a_full[kMaxStages];
@@ -45,6 +47,7 @@ struct __align__(16) SmemHeader {
   uint64_t w_full[2];
   uint64_t w_empty[2];
   uint64_t acc_full;
+  uint64_t acc_zero;
   uint32_t tmem_ptr;
   uint32_t pad;
   float red[4][32];
@@ -80,8 +83,30 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   lo = pack8_bf16(l);
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// UMMA with the two descriptor words passed separately: only the low word (start address) changes per MMA.
+__device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
+      : "memory");
+}
+
+// MT = 128-row M tiles per output plane, KS = filter size (3: padding 1, taps along z folded into the MMA N dimension).
+//
+// Accumulator (m, zo) lives at TMEM column (m*TZ + zo)*NT, so the accumulators of consecutive output planes are
+// adjacent: ONE MMA of N = nz*NT columns adds input plane `pl`'s contribution for the filter taps dz = dz_hi..dz_lo to the
+// nz output planes zo = pl-dz_hi .. pl-dz_lo (the weight rows are stored dz-descending).  This triples the MMA N for
+// the C_out = 32 / 64 layers (an M=128, K=16 MMA costs >= ~51 clk whatever N is, measured).  All accumulators are
+// zeroed by the epilogue warps while the first TMA loads are in flight, so every MMA accumulates.
+template <int MT, int KS>
+__global__ void __launch_bounds__(kThreads, 2)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ ConvKParams p) {
+  constexpr int KT = KS;  // taps per axis
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
@@ -101,6 +126,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int nt = blockIdx.y;
   const int x0 = tx * p.TX, y0 = ty * p.TY, z0 = tz * p.TZ;
   const int n_planes = p.TZ + 2 * p.halo;
+  const int tz_valid = min(p.TZ, p.Z - z0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -112,6 +138,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(smem_u32(&hdr->w_empty[s]), 1);
     }
     mbar_init(smem_u32(&hdr->acc_full), 1);
+    mbar_init(smem_u32(&hdr->acc_zero), 128);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmA);
@@ -151,42 +178,44 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.NT);
-      const uint32_t a_lbo = p.desc_swap ? 128u : p.plane_bytes;
-      const uint32_t a_sbo = p.desc_swap ? p.plane_bytes : 128u;
-      const uint32_t b_lbo = p.desc_swap ? 128u : (uint32_t)p.NT * 16u;
-      const uint32_t b_sbo = p.desc_swap ? (uint32_t)p.NT * 16u : 128u;
-      const uint64_t a_desc_hi = make_smem_desc(0, a_lbo, a_sbo);
-      const uint64_t b_desc_hi = make_smem_desc(0, b_lbo, b_sbo);
-      const int ktaps = p.halo ? 3 : 1;
-      uint32_t inited = 0;
+      const uint32_t NT = (uint32_t)p.NT;
+      const uint32_t brows = (uint32_t)KT * NT;                   // weight rows per (tap9, k half): dz-descending x NT
+      const uint32_t a_hi = (128u >> 4) | (1u << 14);             // SBO = 128 B, descriptor version 1
+      const uint32_t b_hi = a_hi;
+      const uint32_t a_lbo = (p.plane_bytes >> 4) << 16;          // K halves one plane apart
+      const uint32_t b_lbo = ((brows * 16u) >> 4) << 16;
+      const uint32_t m_cols = (uint32_t)p.TZ * NT;                // TMEM columns between consecutive m tiles
+      const uint32_t PX = (uint32_t)p.PX;
       int stage = 0;
       uint32_t ph = 0;
+      mbar_wait(smem_u32(&hdr->acc_zero), 0);
+      tc_fence_after();
       for (int kc = 0; kc < p.n_kchunks; ++kc) {
         const int ws = kc & 1;
         const uint32_t wph = (kc >> 1) & 1;
         mbar_wait(smem_u32(&hdr->w_full[ws]), wph);
-        const uint32_t wb = w_smem + ws * p.w_bytes;
+        const uint32_t b_base = (((w_smem + ws * p.w_bytes) >> 4) & 0x3FFFu) | b_lbo;
         for (int pl = 0; pl < n_planes; ++pl) {
           const int z = z0 - p.halo + pl;
           if (z < 0 || z >= p.Z) continue;
           mbar_wait(smem_u32(&hdr->a_full[stage]), ph);
           tc_fence_after();
-          const uint32_t ab = a_smem + stage * p.stage_bytes;
-          for (int dz = 0; dz < ktaps; ++dz) {
-            const int zo = pl - dz;
-            if (zo < 0 || zo >= p.TZ || z0 + zo >= p.Z) continue;
-            for (int dy = 0; dy < ktaps; ++dy) {
-              for (int dx = 0; dx < ktaps; ++dx) {
-                const int tap = (dz * ktaps + dy) * ktaps + dx;
-                const uint64_t bdesc = b_desc_hi | (uint64_t)(((wb + (uint32_t)tap * p.NT * 32u) >> 4) & 0x3FFF);
-                const uint32_t arow = ab + (uint32_t)(dy * p.PX + dx) * 16u;
-                for (int m = 0; m < p.mt; ++m) {
-                  const int idx = zo * p.mt + m;
-                  const uint64_t adesc = a_desc_hi | (uint64_t)(((arow + (uint32_t)m * 2048u) >> 4) & 0x3FFF);
-                  umma_bf16(tmem_base + (uint32_t)(idx * p.NT), adesc, bdesc, idesc, (inited >> idx) & 1u);
-                  inited |= 1u << idx;
-                }
+          const int dz_hi = min(KT - 1, pl);
+          const int dz_lo = max(0, pl - tz_valid + 1);
+          if (dz_hi >= dz_lo) {
+            const uint32_t nz = (uint32_t)(dz_hi - dz_lo + 1);
+            const uint32_t idesc = make_idesc_bf16(128, nz * NT);
+            const uint32_t d0 = tmem_base + (uint32_t)(pl - dz_hi) * NT;
+            const uint32_t a_base = (((a_smem + stage * p.stage_bytes) >> 4) & 0x3FFFu) | a_lbo;
+            const uint32_t b_pl = b_base + (uint32_t)(KT - 1 - dz_hi) * NT;   // first weight row of the dz range
+#pragma unroll
+            for (int dy = 0; dy < KT; ++dy) {
+#pragma unroll
+              for (int dx = 0; dx < KT; ++dx) {
+                const uint32_t a_t = a_base + (uint32_t)dy * PX + (uint32_t)dx;
+                const uint32_t b_t = b_pl + (uint32_t)(dy * KT + dx) * 2u * brows;
+#pragma unroll
+                for (int m = 0; m < MT; ++m) umma_lohi(d0 + (uint32_t)m * m_cols, a_t + (uint32_t)m * 128u, a_hi, b_t, b_hi, idesc);
               }
             }
           }
@@ -201,6 +230,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
     const int q = warp & 3;
     const int ew = warp - 2;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    // zero this warp's quarter of every accumulator while the first loads are in flight
+    for (uint32_t c = 0; c < p.tmem_cols; c += 16) tmem_st16_zero(lane_base + c);
+    tmem_wait_st();
+    tc_fence_before();
+    mbar_arrive(smem_u32(&hdr->acc_zero));
+
     mbar_wait(smem_u32(&hdr->acc_full), 0);
     tc_fence_after();
     const int n_base = nt * p.NT;
@@ -214,17 +250,17 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float s1[16], s2[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-      for (int zo = 0; zo < p.TZ; ++zo) {
+      for (int zo = 0; zo < tz_valid; ++zo) {
         const int z = z0 + zo;
-        if (z >= p.Z) break;
-        for (int m = 0; m < p.mt; ++m) {
+#pragma unroll 1
+        for (int m = 0; m < MT; ++m) {
           const int L = m * 128 + q * 32 + lane;
           const int yy = L / p.PX;
           const int xx = L - yy * p.PX;
           const int y = y0 + yy, x = x0 + xx;
           const bool valid = (xx < p.TX) && (yy < p.TY) && (x < p.X) && (y < p.Y);
           float v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((zo * p.mt + m) * p.NT + cg * 16), v);
+          tmem_ld16(lane_base + (uint32_t)((m * p.TZ + zo) * p.NT + cg * 16), v);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += bias_v[i];
           if (valid) {
@@ -377,7 +413,8 @@ static int plan_conv(const mmseg_conv_args* a, ConvPlan* out) {
   const int flat = (a->TY - 1) * k.PX + a->TX;
   k.mt = (flat + 127) / 128;
   const int n_acc = k.mt * a->TZ;
-  if (n_acc > 32) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: %d accumulators > 32", n_acc);
+  if (k.mt > kMaxMT) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: %d M tiles per plane > %d", k.mt, kMaxMT);
+  if (a->ksize == 3 && 3 * a->NT > 256) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: NT=%d > 80 with ksize 3 (folded MMA N = 3*NT <= 256)", a->NT);
   const int cols = n_acc * a->NT;
   if (cols > 512) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: %d TMEM columns > 512", cols);
   uint32_t tc = 32;
@@ -394,7 +431,10 @@ static int plan_conv(const mmseg_conv_args* a, ConvPlan* out) {
   const uint32_t overflow = rows_needed * 16u > k.plane_bytes ? rows_needed * 16u - k.plane_bytes : 0u;
   k.w_off = kHeaderBytes;
   k.a_off = k.w_off + 2 * round_up(k.w_bytes, 128);
-  const uint32_t total = k.a_off + a->stages * k.stage_bytes + round_up(overflow, 128) + 128 /*align slack*/;
+  uint32_t total = k.a_off + a->stages * k.stage_bytes + round_up(overflow, 128) + 128 /*align slack*/;
+  // two CTAs share an SM only when both fit in TMEM: a CTA that needs more than 256 columns asks for more than half of
+  // the shared memory so that a second CTA can never be co-resident and block in tcgen05.alloc
+  if (tc > 256 && total < 116u * 1024u) total = 116u * 1024u;
   if (total > 227u * 1024u) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: %u bytes of shared memory > 227 KB", total);
   if (k.w_bytes >= (1u << 20) || k.a_tx_bytes >= (1u << 20)) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: tx bytes");
   out->smem_bytes = total;
@@ -445,13 +485,22 @@ extern "C" int mmseg_conv3d_fwd(const mmseg_conv_args* a, void* stream) {
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(MMSEG_ERR_CUDA, "conv3d: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  typedef void (*KernelFn)(const CUtensorMap, const ConvKParams);
+  static const KernelFn table[2][kMaxMT] = {
+      {conv3d_tc_kernel<1, 1>, conv3d_tc_kernel<2, 1>, conv3d_tc_kernel<3, 1>, conv3d_tc_kernel<4, 1>,
+       conv3d_tc_kernel<5, 1>, conv3d_tc_kernel<6, 1>, conv3d_tc_kernel<7, 1>, conv3d_tc_kernel<8, 1>},
+      {conv3d_tc_kernel<1, 3>, conv3d_tc_kernel<2, 3>, conv3d_tc_kernel<3, 3>, conv3d_tc_kernel<4, 3>,
+       conv3d_tc_kernel<5, 3>, conv3d_tc_kernel<6, 3>, conv3d_tc_kernel<7, 3>, conv3d_tc_kernel<8, 3>}};
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return fail(MMSEG_ERR_CUDA, "conv3d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < kMaxMT; ++j) {
+        cudaError_t e = cudaFuncSetAttribute(table[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return fail(MMSEG_ERR_CUDA, "conv3d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      }
     attr_set = true;
   }
   dim3 grid((unsigned)(k.tiles_x * k.tiles_y * k.tiles_z * k.n_img), (unsigned)k.n_ntiles);
-  conv3d_tc_kernel<<<grid, kThreads, pl.smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tm, k);
+  table[a->ksize == 3 ? 1 : 0][k.mt - 1]<<<grid, kThreads, pl.smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tm, k);
   return check_launch("conv3d_tc_kernel");
 }

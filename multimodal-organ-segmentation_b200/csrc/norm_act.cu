@@ -16,24 +16,34 @@ int num_sms() {
 }
 
 // ---------------------------------------------------------------------------------------------- finalize
-// one thread per (img, channel): fixed-order fp64 sum over the conv CTAs' partials -> mean, rstd
-__global__ void instnorm_finalize_kernel(const float* __restrict__ part, int n_img, int tiles, int C, double inv_n,
-                                         float eps, float* __restrict__ mean_rstd) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per (img, channel): lanes stride over the conv CTAs' partials (fp64), fixed-order shuffle tree -> mean, rstd.
+// Deterministic: the lane a partial lands in and the tree order depend only on the tile count.
+__global__ void __launch_bounds__(256)
+instnorm_finalize_kernel(const float* __restrict__ part, int n_img, int tiles, int C, double inv_n, float eps,
+                         float* __restrict__ mean_rstd) {
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (idx >= n_img * C) return;
   const int img = idx / C, c = idx - img * C;
   const float* p = part + ((size_t)img * tiles * C + c) * 2;
   double s1 = 0.0, s2 = 0.0;
-  for (int t = 0; t < tiles; ++t) {
+  for (int t = lane; t < tiles; t += 32) {
     const float2 v = *reinterpret_cast<const float2*>(p + (size_t)t * C * 2);
     s1 += (double)v.x;
     s2 += (double)v.y;
   }
-  const double mean = s1 * inv_n;
-  double var = s2 * inv_n - mean * mean;
-  if (var < 0.0) var = 0.0;
-  mean_rstd[2 * idx] = (float)mean;
-  mean_rstd[2 * idx + 1] = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane == 0) {
+    const double mean = s1 * inv_n;
+    double var = s2 * inv_n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_rstd[2 * idx] = (float)mean;
+    mean_rstd[2 * idx + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- apply
@@ -229,7 +239,7 @@ extern "C" int mmseg_instnorm_finalize(const float* stats_partial, int32_t n_img
   if (!stats_partial || !mean_rstd || n_img < 1 || tiles_per_img < 1 || channels < 1 || voxels < 1)
     return fail(MMSEG_ERR_INVALID_ARG, "instnorm_finalize: bad arguments");
   const int n = n_img * channels;
-  instnorm_finalize_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  instnorm_finalize_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       stats_partial, n_img, tiles_per_img, channels, 1.0 / (double)voxels, eps, mean_rstd);
   return check_launch("instnorm_finalize_kernel");
 }

@@ -103,10 +103,22 @@ class PackedConv:
 
 
 def _pack_gemm_weight(wmat: Tensor, NT: int) -> Tensor:
-    """wmat [n_out, cin_p, taps] fp32 (cin_p multiple of 16) -> bf16 [n_ntiles, n_kc, taps, 2, NT, 8]."""
+    """wmat [n_out, cin_p, taps] fp32 (cin_p multiple of 16) -> kernel layout (K-major SWIZZLE_NONE core matrices).
+
+    taps == 1:  [n_ntiles, n_kc, 1, 2, NT, 8]
+    taps == 27: [n_ntiles, n_kc, 9 (dy, dx), 2 (k half), 3*NT rows, 8] with row = (2 - dz)*NT + n, i.e. the z taps are
+                stored dz-DESCENDING so that a contiguous row range is a range of consecutive output planes
+                (conv_tc.cu folds dz into the MMA N dimension).
+    """
     n_out, cin_p, taps = wmat.shape
-    v = wmat.reshape(n_out // NT, NT, cin_p // 16, 2, 8, taps)
-    return v.permute(0, 2, 5, 3, 1, 4).contiguous()
+    if taps == 1:
+        v = wmat.reshape(n_out // NT, NT, cin_p // 16, 2, 8, 1)
+        return v.permute(0, 2, 5, 3, 1, 4).contiguous()
+    assert taps == 27
+    v = wmat.reshape(n_out // NT, NT, cin_p // 16, 2, 8, 3, 3, 3)      # [nt, n, kc, half, k8, dz, dy, dx]
+    v = v.flip(5)                                                       # dz descending
+    v = v.permute(0, 2, 6, 7, 3, 5, 1, 4)                               # [nt, kc, dy, dx, half, dzr, n, k8]
+    return v.reshape(n_out // NT, cin_p // 16, 9, 2, 3 * NT, 8).contiguous()
 
 
 def pack_conv_weight(weight: Tensor, bias: Optional[Tensor], split: bool, seg_channels: Optional[Sequence[int]] = None,

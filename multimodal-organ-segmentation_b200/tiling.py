@@ -2,8 +2,9 @@
 
 Pure integer arithmetic — mirrors plan_conv() in conv_tc.cu so that a plan chosen here is accepted there — plus a
 small cycle model used to pick (TX, TY, TZ, NT, stages) per layer.  Hardware constants are B200's: 148 SMs,
-227 KB shared memory per CTA, 512 TMEM columns, 4096 bf16 MAC/clk/SM, 128 B/clk shared-memory read, and
-~40 B/clk/SM of L2->SM bandwidth when every SM is loading.
+227 KB shared memory per SM, 512 TMEM columns per SM, 4096 bf16 MAC/clk/SM; measured on B200 (tools/micro/umma_bench.cu):
+an M=128, K=16 tcgen05.mma costs max(51, N/2) clk, i.e. the tensor pipe is only saturated for N >= ~104, which is why
+the kernel folds the three z taps into N (N = 3*NT for interior planes).
 """
 from dataclasses import dataclass
 from functools import lru_cache
@@ -11,9 +12,12 @@ from typing import Optional
 
 NUM_SMS = 148
 SMEM_LIMIT = 227 * 1024
+SMEM_HALF = 113 * 1024       # two CTAs per SM
 HEADER_BYTES = 1024
 TMEM_COLS = 512
-MAX_ACC = 32
+MAX_MT = 8
+MMA_MIN_CYCLES = 51.0
+L2_BYTES_PER_CLK_SM = 36.0   # L2 -> SM when every SM is loading (~6300 B/clk chip-wide)
 
 
 def _round_up(v: int, a: int) -> int:
@@ -38,13 +42,22 @@ class ConvTile:
     est_cycles: float
 
 
-def smem_bytes(ksize: int, TX: int, TY: int, NT: int, stages: int) -> Optional[int]:
+def tmem_cols(mt: int, TZ: int, NT: int) -> int:
+    cols, tc = mt * TZ * NT, 32
+    while tc < cols:
+        tc <<= 1
+    return tc
+
+
+def smem_bytes(ksize: int, TX: int, TY: int, NT: int, stages: int, TZ: int = 1) -> Optional[int]:
     """Dynamic shared memory of one CTA, or None if the tiling is invalid (same arithmetic as plan_conv)."""
     h = ksize // 2
     PX, PY = TX + 2 * h, TY + 2 * h
     if PX > 128 or PY > 256:
         return None
     mt = _cdiv((TY - 1) * PX + TX, 128)
+    if mt > MAX_MT or mt * TZ * NT > TMEM_COLS or (ksize == 3 and 3 * NT > 256):
+        return None
     taps = ksize ** 3
     w_bytes = taps * NT * 32
     plane = PX * PY * 16
@@ -55,58 +68,75 @@ def smem_bytes(ksize: int, TX: int, TY: int, NT: int, stages: int) -> Optional[i
     rows_needed = mt * 128 + 2 * h * PX + 2 * h
     overflow = max(rows_needed * 16 - plane, 0)
     total = HEADER_BYTES + 2 * _round_up(w_bytes, 128) + stages * stage + _round_up(overflow, 128) + 128
+    if tmem_cols(mt, TZ, NT) > 256 and total < 116 * 1024:
+        total = 116 * 1024
     if total > SMEM_LIMIT or w_bytes >= (1 << 20) or a_tx >= (1 << 20):
         return None
     return total
 
 
-def _mma_cycles(NT: int) -> float:
-    # one UMMA 128 x NT x 16: tensor floor NT/2 clk; shared-memory operand read (4 KB of A + NT*32 B of B) at 128 B/clk
-    return max(NT / 2.0, (4096 + NT * 32) / 128.0)
+def _mma_cycles(n: int) -> float:
+    return max(MMA_MIN_CYCLES, n / 2.0)
 
 
 @lru_cache(maxsize=None)
 def plan_conv(X: int, Y: int, Z: int, n_img: int, n_kchunks: int, n_out: int, ksize: int,
-              nt_cap: int = 64) -> ConvTile:
+              nt_cap: int = 64, epi_cost: float = 150.0) -> ConvTile:
     """Pick a tiling for a conv with n_out GEMM columns (already padded to a multiple of 16)."""
     h = ksize // 2
     NT = min(n_out, nt_cap)
     while n_out % NT:
         NT -= 16
     n_ntiles = n_out // NT
-    max_acc = min(MAX_ACC, TMEM_COLS // NT)
-    # X tiling: whole rows when the TMA box allows it, otherwise equal parts
-    nx = 1
-    while _cdiv(X, nx) + 2 * h > 128:
-        nx += 1
-    TX = _cdiv(X, nx)
-    PX = TX + 2 * h
     best = None
-    for TY in range(1, Y + 1):
-        mt = _cdiv((TY - 1) * PX + TX, 128)
-        if mt > max_acc:
-            break
-        for TZ in range(1, min(Z, max_acc // mt) + 1):
-            for stages in (4, 3, 2):
-                sb = smem_bytes(ksize, TX, TY, NT, stages)
-                if sb is not None:
-                    break
-            else:
-                continue
-            ty, tz = _cdiv(Y, TY), _cdiv(Z, TZ)
-            n_cta = nx * ty * tz * n_img * n_ntiles
-            # per-CTA work for a full interior tile
-            pairs = TZ * (3 if h else 1)            # (input plane, dz) pairs that issue MMAs
-            mma = n_kchunks * pairs * (9 if h else 1) * mt * _mma_cycles(NT)
-            planes = TZ + 2 * h
-            load = n_kchunks * (planes * 2 * PX * (TY + 2 * h) * 16 + ksize ** 3 * NT * 32) / 40.0
-            epi = TZ * mt * NT * 8.0 + 2000.0
-            t_cta = max(mma, load) + epi
-            waves = _cdiv(n_cta, NUM_SMS)
-            est = waves * t_cta
-            cand = (est, -TY * TZ)
-            if best is None or cand < best[0]:
-                best = (cand, ConvTile(TX, TY, TZ, NT, n_ntiles, stages, mt, sb, nx * ty * tz, est))
+    nx_min = 1
+    while _cdiv(X, nx_min) + 2 * h > 128:
+        nx_min += 1
+    for nx in range(nx_min, min(nx_min + 3, X) + 1):
+        TX = _cdiv(X, nx)
+        PX = TX + 2 * h
+        for TY in range(1, Y + 1):
+            mt = _cdiv((TY - 1) * PX + TX, 128)
+            if mt > MAX_MT or mt * NT > TMEM_COLS:
+                break
+            for TZ in range(1, min(Z, TMEM_COLS // (mt * NT)) + 1):
+                tc = tmem_cols(mt, TZ, NT)
+                sb, stages = None, 0
+                if tc <= 256:  # try to fit two CTAs per SM first
+                    for st in (4, 3, 2):
+                        s_ = smem_bytes(ksize, TX, TY, NT, st, TZ)
+                        if s_ is not None and s_ <= SMEM_HALF:
+                            sb, stages = s_, st
+                            break
+                if sb is None:
+                    for st in (4, 3, 2):
+                        s_ = smem_bytes(ksize, TX, TY, NT, st, TZ)
+                        if s_ is not None:
+                            sb, stages = s_, st
+                            break
+                if sb is None:
+                    continue
+                occ = 2 if (tc <= 256 and sb <= SMEM_HALF) else 1
+                tx_n, ty_n, tz_n = _cdiv(X, TX), _cdiv(Y, TY), _cdiv(Z, TZ)
+                n_cta = tx_n * ty_n * tz_n * n_img * n_ntiles
+                if h:
+                    per_tap = sum(_mma_cycles(NT * (min(2, pl) - max(0, pl - TZ + 1) + 1)) for pl in range(TZ + 2))
+                    mma = n_kchunks * 9 * mt * (per_tap + 0.0)
+                else:
+                    mma = n_kchunks * TZ * mt * _mma_cycles(NT)
+                planes = TZ + 2 * h
+                load = n_kchunks * (planes * 2 * PX * (TY + 2 * h) * 16 + ksize ** 3 * NT * 32) / L2_BYTES_PER_CLK_SM
+                epi = TZ * mt * (NT // 16) * epi_cost + 1000.0
+                fixed = 3000.0
+                if occ == 2:
+                    eff = max(mma, load, (max(mma, load) + epi + fixed) / 2.0)
+                else:
+                    eff = max(mma, load) + epi + fixed
+                waves = _cdiv(n_cta, NUM_SMS * occ)
+                est = waves * occ * eff
+                cand = (est, -TY * TZ * TX)
+                if best is None or cand < best[0]:
+                    best = (cand, ConvTile(TX, TY, TZ, NT, n_ntiles, stages, mt, sb, tx_n * ty_n * tz_n, est))
     if best is None:
         raise ValueError(f"no valid conv tiling for X={X} Y={Y} Z={Z} n_out={n_out} ksize={ksize}")
     return best[1]

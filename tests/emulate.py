@@ -8,21 +8,26 @@ import torch
 
 
 def emulate_conv(src_t, src_cbt, pw, a_cb, tile, n_img, Z, Y, X, garbage=1e4):
-    """src_t: float tensor [n_img, cbt, Z, Y, X, 8].  Returns fp32 GEMM output [n_img, n_out, Z, Y, X]."""
+    """src_t: float tensor [n_img, cbt, Z, Y, X, 8].  Returns fp32 GEMM output [n_img, n_out, Z, Y, X].
+
+    Mirrors the kernel: accumulator (m, zo) at TMEM column (m*TZ + zo)*NT; for ksize 3 one MMA per (plane, dy, dx, m)
+    covers the dz range [dz_lo, dz_hi] = output planes pl-dz_hi .. pl-dz_lo with weight rows stored dz-descending.
+    """
     h = pw.ksize // 2
     kt = pw.ksize
     TX, TY, TZ, NT, mt = tile.TX, tile.TY, tile.TZ, tile.NT, tile.mt
     PX, PY = TX + 2 * h, TY + 2 * h
     rows_needed = mt * 128 + 2 * h * PX + 2 * h
-    w = pw.w.float()  # [n_ntiles, n_kc, taps, 2, NT, 8]
+    w = pw.w.float()  # [n_ntiles, n_kc, kt*kt, 2, kt*NT, 8]
     out = torch.zeros((n_img, pw.n_out, Z, Y, X))
-    g = torch.Generator().manual_seed(1)
     for img in range(n_img):
         for z0 in range(0, Z, TZ):
+            tz_valid = min(TZ, Z - z0)
             for y0 in range(0, Y, TY):
                 for x0 in range(0, X, TX):
                     for nt in range(pw.n_out // NT):
-                        acc = torch.zeros((TZ, mt * 128, NT))
+                        tmem = torch.zeros((mt * 128, mt * TZ * NT))  # [lane row within m tile..., columns]
+                        acc = torch.zeros((128, mt * TZ * NT))          # lanes x columns, as in TMEM
                         for kc in range(pw.n_kchunks):
                             for pl in range(TZ + 2 * h):
                                 z = z0 - h + pl
@@ -39,27 +44,30 @@ def emulate_conv(src_t, src_cbt, pw, a_cb, tile, n_img, Z, Y, X, garbage=1e4):
                                         stage[kb, yy, xs0 - (x0 - h):xs1 - (x0 - h)] = src_t[img, blk, z, y, xs0:xs1]
                                 flat = torch.full((2, max(rows_needed, PY * PX), 8), garbage)
                                 flat[:, :PY * PX] = stage.reshape(2, PY * PX, 8)
-                                for dz in range(kt):
-                                    zo = pl - dz
-                                    if zo < 0 or zo >= TZ or z0 + zo >= Z:
-                                        continue
-                                    for dy in range(kt):
-                                        for dx in range(kt):
-                                            tap = (dz * kt + dy) * kt + dx
-                                            B = w[nt, kc, tap].permute(1, 0, 2).reshape(NT, 16)
-                                            for m in range(mt):
-                                                r0 = m * 128 + dy * PX + dx
-                                                A = flat[:, r0:r0 + 128].permute(1, 0, 2).reshape(128, 16)
-                                                acc[zo, m * 128:(m + 1) * 128] += A @ B.T
-                        for zo in range(TZ):
+                                dz_hi, dz_lo = min(kt - 1, pl), max(0, pl - tz_valid + 1)
+                                if dz_hi < dz_lo:
+                                    continue
+                                nz = dz_hi - dz_lo + 1
+                                r0 = (kt - 1 - dz_hi) * NT
+                                c0 = (pl - dz_hi) * NT
+                                for dy in range(kt):
+                                    for dx in range(kt):
+                                        B = w[nt, kc, dy * kt + dx][:, r0:r0 + nz * NT].permute(1, 0, 2).reshape(nz * NT, 16)
+                                        for m in range(mt):
+                                            a0 = m * 128 + dy * PX + dx
+                                            A = flat[:, a0:a0 + 128].permute(1, 0, 2).reshape(128, 16)
+                                            cc = m * TZ * NT + c0
+                                            acc[:, cc:cc + nz * NT] += A @ B.T
+                        for zo in range(tz_valid):
                             z = z0 + zo
-                            if z >= Z:
-                                break
-                            for L in range(mt * 128):
-                                yy, xx = divmod(L, PX)
-                                y, x = y0 + yy, x0 + xx
-                                if xx < TX and yy < TY and x < X and y < Y:
-                                    out[img, nt * NT:(nt + 1) * NT, z, y, x] = acc[zo, L]
+                            for m in range(mt):
+                                cc = (m * TZ + zo) * NT
+                                for r in range(128):
+                                    L = m * 128 + r
+                                    yy, xx = divmod(L, PX)
+                                    y, x = y0 + yy, x0 + xx
+                                    if xx < TX and yy < TY and x < X and y < Y:
+                                        out[img, nt * NT:(nt + 1) * NT, z, y, x] = acc[r, cc:cc + NT]
     return out
 
 
