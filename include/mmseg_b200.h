@@ -31,6 +31,7 @@ extern "C" {
 
 #define MMSEG_ABI_VERSION 1
 #define MMSEG_MAX_KCHUNKS 96
+#define MMSEG_MAX_WGRAD_GROUPS 64
 
 typedef enum {
   MMSEG_OK = 0,
@@ -90,6 +91,40 @@ int mmseg_conv3d_fwd(const mmseg_conv_args* args, void* stream);
 /* bytes of dynamic shared memory / TMEM columns / CTAs the call would use; <0 when the tiling is rejected */
 int64_t mmseg_conv3d_smem_bytes(const mmseg_conv_args* args);
 int32_t mmseg_conv3d_tiles_per_img(const mmseg_conv_args* args);
+
+/*
+ * Conv3d weight gradient (the wgrad half of autograd's convolution_backward for nn.Conv3d k=3 p=1 / k=1 at
+ * src/models/backbones/unet.py:26-27,54,57,163 and, through the k=1 GEMM view, nn.ConvTranspose3d(k2,s2) at unet.py:95;
+ * the reference reaches it via loss.backward(), src/trainer/trainer.py:243).
+ *   dW[co, ci, tap] = sum over images and voxels of dY[vox, co] * X[vox + tap, ci]
+ * tcgen05 GEMM with the voxels as the contraction dimension, both operands MN-major straight from the blocked layout.
+ * grid = n_part persistent CTAs x (n_cig * n_cot) channel-group pairs; every CTA sweeps its share of the voxel tiles
+ * with the accumulators resident in TMEM and writes ONE fp32 partial; mmseg_wgrad_reduce sums the partials in a fixed
+ * order (deterministic split-K) into the PyTorch-layout gradient.  dgrad needs no entry point of its own: it is
+ * mmseg_conv3d_fwd with the spatially flipped, channel-transposed weights.
+ */
+typedef struct {
+  const void* x;        /* conv input, blocked bf16 [n_img*x_cbt][Z][Y][X][8]                                 */
+  const void* dy;       /* gradient of the raw conv output, blocked bf16 [n_img*y_cbt][Z][Y][X][8]            */
+  float* partial;       /* workspace [n_cig*n_cot][n_part][128][ksize^2 * cot_blocks*8] fp32                  */
+  int32_t n_img, Z, Y, X;
+  int32_t ksize;        /* 3 (padding 1) or 1                                                                 */
+  int32_t TX, TY, TZ;   /* voxel tile per sweep step; TX*TY % 16 == 0, TX <= 128                              */
+  int32_t cig_blocks;   /* input-channel blocks (of 8) per group; ksize*cig_blocks <= 16                      */
+  int32_t cot_blocks;   /* output-channel blocks per group (even); ksize*cot_blocks*8 <= 256                  */
+  int32_t n_cig, n_cot; /* number of input / output channel groups                                            */
+  int32_t x_cbt, y_cbt; /* channel blocks per image in x / dy                                                 */
+  int32_t y_cb0;        /* first channel block of dy used                                                     */
+  int32_t n_part;       /* persistent CTAs per group pair                                                     */
+  int16_t x_cb[MMSEG_MAX_WGRAD_GROUPS]; /* first channel block in x of each input-channel group (concat-aware) */
+} mmseg_wgrad_args;
+int mmseg_conv3d_wgrad(const mmseg_wgrad_args* args, void* stream);
+int64_t mmseg_conv3d_wgrad_smem_bytes(const mmseg_wgrad_args* args);
+/* ci_map[ci] = group*CIG + index inside the group for weight input channel ci.  transposed: ConvTranspose3d(k2,s2)
+ * layout [Cin][Cout][2][2][2] from the GEMM columns n = tap8*Cout + co (Cout_gemm = 8*Cout). */
+int mmseg_wgrad_reduce(const float* partial, int32_t n_part, int32_t ksize, int32_t cig_blocks, int32_t cot_blocks,
+                       int32_t n_cot, int32_t Cin, int32_t Cout_gemm, int32_t Cout, int32_t transposed,
+                       const int32_t* ci_map, float* dst, void* stream);
 
 /*
  * InstanceNorm3d(affine=False, eps) statistics: reduce the conv epilogue's per-CTA partials in a fixed order (fp64)

@@ -33,6 +33,20 @@ class ConvArgs(C.Structure):
     ]
 
 
+MAX_WGRAD_GROUPS = 64
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("dy", C.c_void_p), ("partial", C.c_void_p),
+        ("n_img", C.c_int32), ("Z", C.c_int32), ("Y", C.c_int32), ("X", C.c_int32),
+        ("ksize", C.c_int32), ("TX", C.c_int32), ("TY", C.c_int32), ("TZ", C.c_int32),
+        ("cig_blocks", C.c_int32), ("cot_blocks", C.c_int32), ("n_cig", C.c_int32), ("n_cot", C.c_int32),
+        ("x_cbt", C.c_int32), ("y_cbt", C.c_int32), ("y_cb0", C.c_int32), ("n_part", C.c_int32),
+        ("x_cb", C.c_int16 * MAX_WGRAD_GROUPS),
+    ]
+
+
 class NormArgs(C.Structure):
     _fields_ = [
         ("src", C.c_void_p), ("mean_rstd", C.c_void_p), ("dst", C.c_void_p), ("pooled", C.c_void_p),
@@ -53,6 +67,9 @@ SYMBOLS = {
     "mmseg_conv3d_fwd": (C.c_int, [C.POINTER(ConvArgs), _vp]),
     "mmseg_conv3d_smem_bytes": (_i64, [C.POINTER(ConvArgs)]),
     "mmseg_conv3d_tiles_per_img": (_i32, [C.POINTER(ConvArgs)]),
+    "mmseg_conv3d_wgrad": (C.c_int, [C.POINTER(WgradArgs), _vp]),
+    "mmseg_conv3d_wgrad_smem_bytes": (_i64, [C.POINTER(WgradArgs)]),
+    "mmseg_wgrad_reduce": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "mmseg_instnorm_finalize": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _f32, _vp, _vp]),
     "mmseg_instnorm_act_apply": (C.c_int, [C.POINTER(NormArgs), _vp]),
     "mmseg_pack_ncdhw": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -216,3 +216,145 @@ class UNet3DEngine:
         if level == len(f) - 1:
             return b["bott"].to_ncdhw()
         return b[f"cat{level}"].to_ncdhw(f[level], f[level])
+
+
+class DualEncoderEngine:
+    """DualEncoder.forward (reference src/models/backbones/dual_encoder.py:112-199) on blocked buffers.
+
+    The M per-modality encoders write every level's output modality-major into ONE blocked "stack" buffer
+    (channel m*C_l + c), so torch.stack / torch.cat of the reference cost nothing; the level fusion then reads it once:
+      * mean (anything the reference does not special-case: 'early', 'late', 'cross_attention'), 'add':
+        weighted sum kernel with a uniform weight;
+      * 'attention' (CrossModalAttention, :207-254): channel means -> gate MLP + softmax -> weighted sum;
+      * 'concat' (:179-182): a 1x1 conv (tcgen05 GEMM) whose K runs over all M*C_l stack channels.
+    The fused feature lands directly in the skip half of that level's decoder concat buffer.
+    """
+
+    def __init__(self, module, mode: str = "bf16"):
+        assert mode in ("bf16", "parity")
+        self.module = module
+        self.mode = mode
+        self.split = mode == "parity"
+        self._packed = None
+        self._packed_version = None
+        self._bufs: Dict[Tuple, Dict[str, object]] = {}
+        self._runner: Optional[ConvRunner] = None
+        self.last_gate_weights: List[Tensor] = []
+
+    def _pack(self) -> Dict[str, PackedConv]:
+        m = self.module
+        ver = _param_version(list(m.parameters()))
+        if self._packed is not None and ver == self._packed_version:
+            return self._packed
+        f, sp, M = m.features, self.split, m.num_modalities
+        P: Dict[str, PackedConv] = {}
+
+        def block(name, blk, segs1):
+            P[name + ".conv1"] = K.pack_conv_weight(blk.conv1.weight, None, sp, segs1, use_bias=False)
+            P[name + ".conv2"] = K.pack_conv_weight(blk.conv2.weight, None, sp, None, use_bias=False)
+
+        for i, enc in enumerate(m.encoders):
+            block(f"enc{i}.init", enc["init_conv"], [m.in_channels_per_modality])
+            for l, blk in enumerate(enc["blocks"]):
+                block(f"enc{i}.blocks.{l}", blk.conv, [f[l]])
+        if m.fusion_type == "concat":
+            for l, proj in enumerate(m.fusion_proj):
+                P[f"fusion_proj.{l}"] = K.pack_conv_weight(proj.weight, proj.bias, sp, [f[l]] * M)
+        for j, dec in enumerate(m.decoder):
+            lvl = len(f) - 2 - j
+            P[f"decoder.{j}.up"] = K.pack_conv_weight(dec.up.weight, dec.up.bias, sp, None, transposed=True)
+            block(f"decoder.{j}", dec.conv, [f[lvl], f[lvl]])
+        P["out_conv"] = K.pack_conv_weight(m.out_conv.weight, m.out_conv.bias, sp, None)
+        self._packed, self._packed_version = P, ver
+        return P
+
+    def _buffers(self, n, Z, Y, X, device):
+        key = (n, Z, Y, X)
+        b = self._bufs.get(key)
+        if b is not None:
+            return b
+        m = self.module
+        f, L, M, sp = m.features, len(m.features), m.num_modalities, self.split
+        if any(d % (1 << (L - 1)) for d in (Z, Y, X)):
+            raise NotImplementedError(f"spatial size {(Z, Y, X)} is not divisible by {1 << (L - 1)} (trilinear resize "
+                                      "branch of UpBlock3D, reference unet.py:108-109, is not implemented)")
+        b = {"in": Blocked(n, (m.in_channels_per_modality + 15) // 16 * 16, Z, Y, X, sp, device)}
+        for l in range(L):
+            z, y, x = Z >> l, Y >> l, X >> l
+            b[f"mid{l}"] = Blocked(n, f[l], z, y, x, sp, device)
+            b[f"stack{l}"] = Blocked(n, M * f[l], z, y, x, sp, device)       # every modality's level-l output
+            if l < L - 1:
+                b[f"cat{l}"] = Blocked(n, 2 * f[l], z, y, x, sp, device)     # [up | fused skip]
+                b[f"dec{l}"] = Blocked(n, f[l], z, y, x, sp, device)
+            else:
+                b["bott"] = Blocked(n, f[l], z, y, x, sp, device)
+            if l > 0:
+                b[f"pool{l}"] = Blocked(n, f[l - 1], z, y, x, sp, device)
+        self._bufs[key] = b
+        return b
+
+    @torch.no_grad()
+    def forward(self, x: Tensor) -> Tensor:
+        _lib.require_device()
+        if not x.is_cuda:
+            raise RuntimeError("mmseg_b200 engines run on CUDA tensors only (no CPU fallback)")
+        m = self.module
+        f, L, M = m.features, len(m.features), m.num_modalities
+        x = x.contiguous().float()
+        n, cin, Z, Y, X = x.shape
+        cpm = m.in_channels_per_modality
+        assert cin == M * cpm, f"expected {M * cpm} input channels, got {cin}"
+        P = self._pack()
+        b = self._buffers(n, Z, Y, X, x.device)
+        if self._runner is None:
+            self._runner = ConvRunner(self.split, x.device)
+        r = self._runner
+        # encoders (dual_encoder.py:131-144): modality i reads x[:, i*cpm:(i+1)*cpm]
+        for i in range(M):
+            K.pack_ncdhw(x[:, i * cpm:(i + 1) * cpm].contiguous(), b["in"])
+            r.conv_norm_act(b["in"], [(0, cpm)], P[f"enc{i}.init.conv1"], b["mid0"])
+            for l in range(L):
+                if l > 0:
+                    r.conv_norm_act(b[f"pool{l}"], [(0, f[l - 1])], P[f"enc{i}.blocks.{l - 1}.conv1"], b[f"mid{l}"])
+                    name2 = f"enc{i}.blocks.{l - 1}.conv2"
+                else:
+                    name2 = f"enc{i}.init.conv2"
+                r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[name2], b[f"stack{l}"], dst_c0=i * f[l],
+                                pooled=b[f"pool{l + 1}"] if l < L - 1 else None)
+        # level fusion (_fuse_features, :167-199) into the skip half of the concat buffers / the bottleneck
+        self.last_gate_weights = []
+        for l in range(L):
+            dst, c0 = (b["bott"], 0) if l == L - 1 else (b[f"cat{l}"], f[l])
+            st = b[f"stack{l}"]
+            if m.fusion_type == "concat":
+                r.conv_act(st, [(i * f[l], f[l]) for i in range(M)], P[f"fusion_proj.{l}"], dst, dst_c0=c0)
+            elif m.fusion_type == "add":
+                K.modality_combine(st, M, f[l], dst, c0, None, 1.0)
+            elif m.fusion_type == "attention":
+                att = m.fusion_layers[l].attention
+                pooled = K.channel_mean(st, 0, M * f[l])
+                w = K.gate_mlp(pooled, att[2].weight, att[2].bias, att[4].weight, att[4].bias)
+                self.last_gate_weights.append(w)
+                K.modality_combine(st, M, f[l], dst, c0, w)
+            else:
+                K.modality_combine(st, M, f[l], dst, c0, None, 1.0 / M)
+        # shared decoder (:147-152)
+        cur = b["bott"]
+        for j in range(L - 1):
+            l = L - 2 - j
+            r.conv_transpose(cur, [(0, f[l + 1])], P[f"decoder.{j}.up"], b[f"cat{l}"], dst_c0=0)
+            r.conv_norm_act(b[f"cat{l}"], [(0, f[l]), (f[l], f[l])], P[f"decoder.{j}.conv1"], b[f"mid{l}"])
+            r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[f"decoder.{j}.conv2"], b[f"dec{l}"])
+            cur = b[f"dec{l}"]
+        logits = torch.empty((n, m.out_channels, Z, Y, X), dtype=torch.float32, device=x.device)
+        r.conv_logits(cur, [(0, f[0])], P["out_conv"], logits)
+        return logits
+
+    def features_ncdhw(self, n, Z, Y, X):
+        """(encoder_features[m][l], fused_features[l]) as NCDHW fp32 copies — the return_features dict."""
+        m = self.module
+        f, L, M = m.features, len(m.features), m.num_modalities
+        b = self._bufs[(n, Z, Y, X)]
+        enc = [[b[f"stack{l}"].to_ncdhw(i * f[l], f[l]) for l in range(L)] for i in range(M)]
+        fused = [b["bott"].to_ncdhw() if l == L - 1 else b[f"cat{l}"].to_ncdhw(f[l], f[l]) for l in range(L)]
+        return enc, fused

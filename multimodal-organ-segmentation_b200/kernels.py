@@ -4,6 +4,7 @@ PyTorch only provides device memory and the current stream here; all arithmetic 
 """
 import ctypes as C
 from dataclasses import dataclass
+from functools import lru_cache
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -332,3 +333,91 @@ def maxpool3d_2(src: Blocked, dst: Blocked, channels: Optional[int] = None, src_
     channels = src.channels if channels is None else channels
     _call("mmseg_maxpool3d_2", _ptr(src.t), src.n_img, src.cbt, src_c0 // 8, src.lo_off, channels // 8, src.Z, src.Y,
                                 src.X, _ptr(dst.t), dst.cbt, dst_c0 // 8, dst.lo_off, _stream())
+
+
+# --------------------------------------------------------------------------------------------- weight gradient
+def _largest_divisor(cands, values):
+    for c in cands:
+        if all(v % c == 0 for v in values):
+            return c
+    raise ValueError(f"no channel group size in {cands} divides {values}")
+
+
+@lru_cache(maxsize=None)
+def _plan_wgrad_tile(X: int, Y: int, Z: int, ksize: int, cig_blocks: int, cot_blocks: int) -> Tuple[int, int, int]:
+    """(TX, TY, TZ) accepted by the library: largest K rows per plane (TX*TY, multiple of 16) that fits shared memory."""
+    best = None
+    for nx in range(1, X + 1):
+        TX = (X + nx - 1) // nx
+        if TX > 128:
+            continue
+        for TY in range(min(Y, 32), 0, -1):
+            if (TX * TY) % 16:
+                continue
+            a = _lib.WgradArgs()
+            a.n_img, a.Z, a.Y, a.X, a.ksize = 1, Z, Y, X, ksize
+            a.TX, a.TY, a.TZ = TX, TY, min(Z, 8)
+            a.cig_blocks, a.cot_blocks, a.n_cig, a.n_cot = cig_blocks, cot_blocks, 1, 1
+            a.x_cbt, a.y_cbt, a.y_cb0, a.n_part = cig_blocks, cot_blocks, 0, 1
+            if lib.mmseg_conv3d_wgrad_smem_bytes(C.byref(a)) > 0:
+                rows = TX * TY
+                waste = ((X + TX - 1) // TX * TX) * ((Y + TY - 1) // TY * TY) / float(X * Y)
+                score = (min(rows, 512) / waste, -nx)
+                if best is None or score > best[0]:
+                    best = (score, (TX, TY, min(Z, 8)))
+                break
+        if best is not None and nx >= 4:
+            break
+    if best is None:
+        # rows must be a multiple of 16: pad the tile beyond the volume (TMA zero-fills, so the sum is unchanged)
+        TX = min(X, 16) if X >= 16 else 16
+        TY = max(1, 16 // TX) if TX * max(1, 16 // TX) % 16 == 0 else 16
+        best = (None, (TX, TY, min(Z, 8)))
+    return best[1]
+
+
+def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt: int, dy_cb0: int, cout_gemm: int,
+                 ksize: int, weight_shape, transposed: bool = False) -> Tensor:
+    """dW (fp32, PyTorch weight layout `weight_shape`) of a conv whose input is `x` (channel segments `segs` in concat
+    order) and whose raw-output gradient is `dy` (blocked bf16, `dy_cbt` channel blocks per image, first block dy_cb0)."""
+    _lib.require_device()
+    assert not x.split, "the backward path runs in bf16 mode"
+    seg_ch = [s[1] for s in segs]
+    seg_pad = [(s + 15) // 16 * 16 for s in seg_ch]
+    cin = sum(seg_ch)
+    cig = _largest_divisor((32, 16) if ksize == 3 else (128, 64, 32, 16), seg_pad)
+    ntc = _largest_divisor((32, 16) if ksize == 3 else (256, 128, 64, 32, 16), [(cout_gemm + 15) // 16 * 16])
+    cout_pad = (cout_gemm + 15) // 16 * 16
+    groups, ci_map = [], []
+    for (c0, s), sp in zip(segs, seg_pad):
+        assert c0 % 8 == 0
+        for j in range(sp // cig):
+            groups.append((c0 + j * cig) // 8)
+        base = (len(groups) - sp // cig) * cig
+        ci_map.extend(base + i for i in range(s))
+    n_cig, n_cot = len(groups), cout_pad // ntc
+    assert n_cig <= _lib.MAX_WGRAD_GROUPS
+    TX, TY, TZ = _plan_wgrad_tile(x.X, x.Y, x.Z, ksize, cig // 8, ntc // 8)
+    n_tiles = -(-x.X // TX) * -(-x.Y // TY) * -(-x.Z // TZ) * x.n_img
+    n_part = max(1, min(n_tiles, 148 // (n_cig * n_cot)))
+    ncols = ksize * ksize * ntc
+    partial = torch.empty((n_cig * n_cot, n_part, 128, ncols), dtype=torch.float32, device=x.t.device)
+    a = _lib.WgradArgs()
+    a.x, a.dy, a.partial = x.t.data_ptr(), dy.data_ptr(), partial.data_ptr()
+    a.n_img, a.Z, a.Y, a.X, a.ksize = x.n_img, x.Z, x.Y, x.X, ksize
+    a.TX, a.TY, a.TZ = TX, TY, TZ
+    a.cig_blocks, a.cot_blocks, a.n_cig, a.n_cot = cig // 8, ntc // 8, n_cig, n_cot
+    a.x_cbt, a.y_cbt, a.y_cb0, a.n_part = x.cbt, dy_cbt, dy_cb0, n_part
+    for i, g in enumerate(groups):
+        a.x_cb[i] = g
+    if PROFILE is not None:
+        _INFO[0] = {"flops": 2.0 * x.n_img * x.nvox * cin * cout_gemm * ksize ** 3,
+                    "layer": f"wgrad k{ksize} cin{cin} n{cout_gemm} {x.Z}x{x.Y}x{x.X} img{x.n_img}",
+                    "tile": (TX, TY, TZ, ntc, cig), "ctas": n_part * n_cig * n_cot}
+    _call("mmseg_conv3d_wgrad", C.byref(a), _stream())
+    dw = torch.empty(tuple(weight_shape), dtype=torch.float32, device=x.t.device)
+    cm = torch.tensor(ci_map, dtype=torch.int32, device=x.t.device)
+    cout = weight_shape[1] if transposed else weight_shape[0]
+    _call("mmseg_wgrad_reduce", _ptr(partial), n_part, ksize, cig // 8, ntc // 8, n_cot, cin, cout_gemm, cout,
+          1 if transposed else 0, _ptr(cm), _ptr(dw), _stream())
+    return dw

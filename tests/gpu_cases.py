@@ -351,3 +351,32 @@ def swi_constant_predictor_case():
         ref[s[0]:s[0] + 32, s[1]:s[1] + 32, s[2]:s[2] + 32] += w
     assert torch.equal(cnt.cpu(), ref), (cnt.cpu() - ref).abs().max()
     print("[swi constant predictor] exact", flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ backward kernels
+def wgrad_case(cin, cout, shape, n_img=1, ks=3, segs=None, seed=0):
+    """tcgen05 wgrad (voxel-contraction GEMM, MN-major operands) vs autograd of F.conv3d in fp64."""
+    torch.manual_seed(seed)
+    Z, Y, X = shape
+    x = _bf(torch.randn(n_img, cin, Z, Y, X, device=DEV))
+    dy = _bf(torch.randn(n_img, cout, Z, Y, X, device=DEV))
+    segs = segs or [(0, cin)]
+    tot = max(c0 + (s + 15) // 16 * 16 for c0, s in segs)
+    xb = Blocked(n_img, tot, Z, Y, X, False, DEV)
+    xb.t.zero_()
+    c = 0
+    for c0, s in segs:
+        K.pack_ncdhw(x[:, c:c + s].contiguous(), xb, c0=c0)
+        c += s
+    dyb = Blocked(n_img, (cout + 15) // 16 * 16, Z, Y, X, False, DEV)
+    K.pack_ncdhw(dy, dyb)
+    got = K.conv3d_wgrad(xb, segs, dyb.t, dyb.cbt, 0, cout, ks, (cout, cin, ks, ks, ks))
+    torch.cuda.synchronize()
+    w = torch.zeros(cout, cin, ks, ks, ks, device=DEV, dtype=torch.float64, requires_grad=True)
+    F.conv3d(x.double(), w, padding=ks // 2).backward(dy.double())
+    ref = w.grad.float()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"[wgrad k{ks} cin={cin} cout={cout} {shape} n={n_img} segs={segs}] max|err|={err:.3e} (ref max {scale:.3e})", flush=True)
+    assert torch.isfinite(got).all()
+    assert err <= 2e-3 * scale + 1e-4
