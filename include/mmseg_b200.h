@@ -151,6 +151,34 @@ typedef struct {
 } mmseg_norm_args;
 int mmseg_instnorm_act_apply(const mmseg_norm_args* args, void* stream);
 
+/*
+ * Backward of InstanceNorm3d(affine=False) + ReLU/LeakyReLU (+ the MaxPool3d(2) that may follow) — the
+ * native_batch_norm_backward / threshold_backward / max_pool3d_with_indices_backward ops autograd issues for
+ * ConvBlock3D / DownBlock3D (unet.py:53-60,76-79 via trainer.py:243).  Two launches: _reduce writes per-block partial
+ * sums of g' and g'*y^, _apply re-reduces them in a fixed order and writes dx (bf16, blocked) = gradient of the raw
+ * conv output.  gA: gradient w.r.t. the activation (scaled by gA_scale, e.g. 1/M for DualEncoder's mean fusion);
+ * gP: gradient w.r.t. the pooled activation (routed to the first maximum of each 2x2x2 cell).  Either may be NULL.
+ */
+typedef struct {
+  const void* x;           /* raw conv output saved by the forward, blocked bf16 [n_img*cb][Z][Y][X][8]       */
+  const float* mean_rstd;  /* [n_img][cb*8][2] saved by the forward                                           */
+  const void* gA;          /* blocked bf16 [n_img*gA_cbt][Z][Y][X][8] or NULL                                 */
+  const void* gP;          /* blocked bf16 [n_img*gP_cbt][Z/2][Y/2][X/2][8] or NULL                           */
+  float* partial;          /* [n_img*cb][n_chunks][16] fp32                                                   */
+  void* dx;                /* blocked bf16 [n_img*dx_cbt][Z][Y][X][8] (apply only)                            */
+  const float* chan_scale; /* optional [n_img][cb*8] multiplier of gA (Dropout3d mask * 1/(1-p)) or NULL      */
+  int32_t n_img, cb, Z, Y, X;
+  int32_t gA_cbt, gA_cb_off, gP_cbt, gP_cb_off, dx_cbt, dx_cb_off;
+  int32_t n_chunks;
+  float gA_scale, slope;
+} mmseg_norm_bwd_args;
+int mmseg_instnorm_act_bwd_reduce(const mmseg_norm_bwd_args* args, void* stream);
+int mmseg_instnorm_act_bwd_apply(const mmseg_norm_bwd_args* args, void* stream);
+/* Gradient of a ConvTranspose3d(k2,s2) output (blocked, high resolution, channel blocks [src_cb_off, +cb)) -> its k=1
+ * GEMM view at low resolution with channel = tap*C + co: the dY operand of the transposed conv's dgrad / wgrad. */
+int mmseg_unshuffle_k2s2(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_cb_off, int32_t cb, int32_t Z,
+                         int32_t Y, int32_t X, void* dst, void* stream);
+
 /* NCDHW fp32 [n_img][C][Z][Y][X] -> blocked bf16 (hi[, lo]) with channels zero-padded to cb*8.  Module boundary. */
 int mmseg_pack_ncdhw(const float* src, void* dst, int32_t n_img, int32_t C, int32_t Z, int32_t Y, int32_t X,
                      int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, int32_t cb, void* stream);

@@ -47,6 +47,17 @@ class WgradArgs(C.Structure):
     ]
 
 
+class NormBwdArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("mean_rstd", C.c_void_p), ("gA", C.c_void_p), ("gP", C.c_void_p),
+        ("partial", C.c_void_p), ("dx", C.c_void_p), ("chan_scale", C.c_void_p),
+        ("n_img", C.c_int32), ("cb", C.c_int32), ("Z", C.c_int32), ("Y", C.c_int32), ("X", C.c_int32),
+        ("gA_cbt", C.c_int32), ("gA_cb_off", C.c_int32), ("gP_cbt", C.c_int32), ("gP_cb_off", C.c_int32),
+        ("dx_cbt", C.c_int32), ("dx_cb_off", C.c_int32), ("n_chunks", C.c_int32),
+        ("gA_scale", C.c_float), ("slope", C.c_float),
+    ]
+
+
 class NormArgs(C.Structure):
     _fields_ = [
         ("src", C.c_void_p), ("mean_rstd", C.c_void_p), ("dst", C.c_void_p), ("pooled", C.c_void_p),
@@ -72,6 +83,9 @@ SYMBOLS = {
     "mmseg_wgrad_reduce": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "mmseg_instnorm_finalize": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _f32, _vp, _vp]),
     "mmseg_instnorm_act_apply": (C.c_int, [C.POINTER(NormArgs), _vp]),
+    "mmseg_instnorm_act_bwd_reduce": (C.c_int, [C.POINTER(NormBwdArgs), _vp]),
+    "mmseg_instnorm_act_bwd_apply": (C.c_int, [C.POINTER(NormBwdArgs), _vp]),
+    "mmseg_unshuffle_k2s2": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mmseg_pack_ncdhw": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "mmseg_unpack_ncdhw": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "mmseg_swi_gather": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),

@@ -1,0 +1,276 @@
+// Backward of InstanceNorm3d(affine=False) + ReLU/LeakyReLU (+ the MaxPool3d(2) that may follow) on blocked tensors,
+// and the pixel-unshuffle that turns the gradient of a ConvTranspose3d(k2,s2) output into its k=1 GEMM view.
+// HBM-bound: 16-byte vectors, two-stage deterministic reductions (no atomics).
+//
+//   y^ = (x - mean) * rstd,  a = act(y^),  g' = (s * gA [+ route(gP)]) * act'(y^)
+//   dx = rstd * (g' - mean_v(g') - y^ * mean_v(g' * y^))            
+// route(gP): MaxPool3d(2) backward — the pooled gradient goes to the first maximum of each 2x2x2 cell in scan order.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mmseg {
+
+int num_sms();
+
+struct NormBwdK {
+  const __nv_bfloat16* x;
+  const float* mr;
+  const __nv_bfloat16* gA;
+  const __nv_bfloat16* gP;
+  float* partial;
+  __nv_bfloat16* dx;
+  const float* chan_scale;
+  int n_img, cb, Z, Y, X;
+  int gA_cbt, gA_cb_off, gP_cbt, gP_cb_off, dx_cbt, dx_cb_off;
+  int n_chunks;
+  float gA_scale, slope;
+};
+
+__device__ __forceinline__ void ldb8(const __nv_bfloat16* p, float* v) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ uint4 pkb8(const float* v) {
+  uint4 r;
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+  r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
+  r.z = *reinterpret_cast<uint32_t*>(&c); r.w = *reinterpret_cast<uint32_t*>(&d);
+  return r;
+}
+
+// Per-thread work item: one voxel (POOL = false) or one 2x2x2 cell (POOL = true).  Calls f(voxel_index, yhat[8], gprime[8]).
+template <bool POOL, typename F>
+__device__ __forceinline__ void for_each_item(const NormBwdK& k, int img, int c, const float* mean, const float* rstd, F f) {
+  const size_t nvox = (size_t)k.Z * k.Y * k.X;
+  float cs[8];  // gA_scale x optional per-(image, channel) scale (Dropout3d: 0 or 1/(1-p))
+#pragma unroll
+  for (int i = 0; i < 8; ++i) cs[i] = k.gA_scale * (k.chan_scale ? k.chan_scale[(size_t)img * k.cb * 8 + c * 8 + i] : 1.f);
+  const size_t xbase = (size_t)(img * k.cb + c) * nvox * 8;
+  const size_t abase = (size_t)(img * k.gA_cbt + k.gA_cb_off + c) * nvox * 8;
+  if (!POOL) {
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
+      float x[8], g[8];
+      ldb8(k.x + xbase + v * 8, x);
+      ldb8(k.gA + abase + v * 8, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        x[i] = (x[i] - mean[i]) * rstd[i];
+        g[i] = g[i] * cs[i] * (x[i] > 0.f ? 1.f : k.slope);
+      }
+      f(v, x, g);
+    }
+  } else {
+    const int Zh = k.Z / 2, Yh = k.Y / 2, Xh = k.X / 2;
+    const size_t ncell = (size_t)Zh * Yh * Xh;
+    const size_t pbase = (size_t)(img * k.gP_cbt + k.gP_cb_off + c) * ncell * 8;
+    for (size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x; cell < ncell;
+         cell += (size_t)gridDim.x * blockDim.x) {
+      const int xh = (int)(cell % Xh);
+      const size_t r = cell / Xh;
+      const int yh = (int)(r % Yh), zh = (int)(r / Yh);
+      float gp[8];
+      ldb8(k.gP + pbase + cell * 8, gp);
+      float yh8[8][8];
+      float mx[8];
+      int arg[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { mx[i] = -INFINITY; arg[i] = 0; }
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        const size_t v = ((size_t)(2 * zh + (d >> 2)) * k.Y + (2 * yh + ((d >> 1) & 1))) * k.X + (2 * xh + (d & 1));
+        float x[8];
+        ldb8(k.x + xbase + v * 8, x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float y = (x[i] - mean[i]) * rstd[i];
+          yh8[d][i] = y;
+          const float a = y > 0.f ? y : y * k.slope;
+          if (a > mx[i]) { mx[i] = a; arg[i] = d; }   // strict > keeps the first maximum in scan order
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        const size_t v = ((size_t)(2 * zh + (d >> 2)) * k.Y + (2 * yh + ((d >> 1) & 1))) * k.X + (2 * xh + (d & 1));
+        float g[8];
+        if (k.gA) {
+          ldb8(k.gA + abase + v * 8, g);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] *= cs[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (arg[i] == d) g[i] += gp[i];
+          g[i] *= (yh8[d][i] > 0.f ? 1.f : k.slope);
+        }
+        f(v, yh8[d], g);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void load_mr(const NormBwdK& k, int img, int c, float* mean, float* rstd) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 m = *reinterpret_cast<const float2*>(k.mr + ((size_t)img * k.cb * 8 + c * 8 + i) * 2);
+    mean[i] = m.x;
+    rstd[i] = m.y;
+  }
+}
+
+// grid (n_chunks, n_img*cb): partial[(blk*n_chunks + chunk)*16 + {i, 8+i}] = sum g', sum g'*y^
+template <bool POOL>
+__global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdK k) {
+  const int blk = blockIdx.y;
+  const int img = blk / k.cb, c = blk - img * k.cb;
+  float mean[8], rstd[8];
+  load_mr(k, img, c, mean, rstd);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+  for_each_item<POOL>(k, img, c, mean, rstd, [&](size_t, const float* y, const float* g) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s1[i] += g[i]; s2[i] = fmaf(g[i], y[i], s2[i]); }
+  });
+  __shared__ float red[8][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
+      s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+    }
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { red[warp][i] = s1[i]; red[warp][8 + i] = s2[i]; }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    k.partial[((size_t)blk * gridDim.x + blockIdx.x) * 16 + threadIdx.x] = t;
+  }
+}
+
+// grid (any, n_img*cb): every block first re-reduces the n_chunks partials of its (img, cb) in a fixed order
+template <bool POOL>
+__global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdK k) {
+  const int blk = blockIdx.y;
+  const int img = blk / k.cb, c = blk - img * k.cb;
+  __shared__ float m12[16];
+  if (threadIdx.x < 16) {
+    double s = 0.0;
+    for (int j = 0; j < k.n_chunks; ++j) s += (double)k.partial[((size_t)blk * k.n_chunks + j) * 16 + threadIdx.x];
+    m12[threadIdx.x] = (float)(s / ((double)k.Z * k.Y * k.X));
+  }
+  __syncthreads();
+  float mean[8], rstd[8], m1[8], m2[8];
+  load_mr(k, img, c, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { m1[i] = m12[i]; m2[i] = m12[8 + i]; }
+  const size_t nvox = (size_t)k.Z * k.Y * k.X;
+  const size_t dbase = (size_t)(img * k.dx_cbt + k.dx_cb_off + c) * nvox * 8;
+  for_each_item<POOL>(k, img, c, mean, rstd, [&](size_t v, const float* y, const float* g) {
+    float d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = rstd[i] * (g[i] - m1[i] - y[i] * m2[i]);
+    *reinterpret_cast<uint4*>(k.dx + dbase + v * 8) = pkb8(d);
+  });
+}
+
+// gradient of a ConvTranspose3d(k2,s2) output [n_img*src_cbt][2Z][2Y][2X][8] (channels cb_off*8 .. +C) ->
+// its GEMM view [n_img*8*cb][Z][Y][X][8] with channel = tap*C + co, tap = (dz*2 + dy)*2 + dx
+__global__ void __launch_bounds__(256)
+unshuffle_k2s2_kernel(const __nv_bfloat16* __restrict__ src, int src_cbt, int src_cb_off, int cb, int Z, int Y, int X,
+                      __nv_bfloat16* __restrict__ dst) {
+  const int blk = blockIdx.y;  // img*cb + c
+  const int img = blk / cb, c = blk - img * cb;
+  const size_t nlo = (size_t)Z * Y * X;
+  const size_t sbase = (size_t)(img * src_cbt + src_cb_off + c) * nlo * 8 * 8;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nlo; v += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(v % X);
+    const size_t r = v / X;
+    const int y = (int)(r % Y), z = (int)(r / Y);
+#pragma unroll
+    for (int tap = 0; tap < 8; ++tap) {
+      const size_t sv = ((size_t)(2 * z + (tap >> 2)) * (2 * Y) + (2 * y + ((tap >> 1) & 1))) * (2 * X) + (2 * x + (tap & 1));
+      const uint4 u = *reinterpret_cast<const uint4*>(src + sbase + sv * 8);
+      *reinterpret_cast<uint4*>(dst + ((size_t)(img * 8 * cb + tap * cb + c) * nlo + v) * 8) = u;
+    }
+  }
+}
+
+static unsigned gxb(size_t items, int rows, int cap_per_row) {
+  size_t want = ((size_t)num_sms() * 8 + rows - 1) / rows;
+  size_t need = (items + 255) / 256;
+  size_t g = want < need ? want : need;
+  if (g > (size_t)cap_per_row) g = cap_per_row;
+  return (unsigned)(g < 1 ? 1 : g);
+}
+
+static int fill_norm_bwd(const mmseg_norm_bwd_args* a, NormBwdK* k) {
+  if (!a || !a->x || !a->mean_rstd || !a->partial) return fail(MMSEG_ERR_INVALID_ARG, "instnorm_act_bwd: null pointer");
+  if (!a->gA && !a->gP) return fail(MMSEG_ERR_INVALID_ARG, "instnorm_act_bwd: no incoming gradient");
+  if (a->n_img < 1 || a->cb < 1 || a->Z < 1 || a->Y < 1 || a->X < 1 || a->n_chunks < 1)
+    return fail(MMSEG_ERR_INVALID_ARG, "instnorm_act_bwd: bad extents");
+  if (a->gP && ((a->Z | a->Y | a->X) & 1)) return fail(MMSEG_ERR_UNSUPPORTED, "instnorm_act_bwd: MaxPool3d(2) routing needs even extents");
+  k->x = reinterpret_cast<const __nv_bfloat16*>(a->x); k->mr = a->mean_rstd;
+  k->gA = reinterpret_cast<const __nv_bfloat16*>(a->gA); k->gP = reinterpret_cast<const __nv_bfloat16*>(a->gP);
+  k->partial = a->partial; k->dx = reinterpret_cast<__nv_bfloat16*>(a->dx);
+  k->n_img = a->n_img; k->cb = a->cb; k->Z = a->Z; k->Y = a->Y; k->X = a->X;
+  k->gA_cbt = a->gA_cbt; k->gA_cb_off = a->gA_cb_off; k->gP_cbt = a->gP_cbt; k->gP_cb_off = a->gP_cb_off;
+  k->dx_cbt = a->dx_cbt; k->dx_cb_off = a->dx_cb_off; k->n_chunks = a->n_chunks;
+  k->gA_scale = a->gA_scale; k->slope = a->slope; k->chan_scale = a->chan_scale;
+  return MMSEG_OK;
+}
+
+}  // namespace mmseg
+
+using namespace mmseg;
+
+extern "C" int mmseg_instnorm_act_bwd_reduce(const mmseg_norm_bwd_args* a, void* stream) {
+  NormBwdK k;
+  int rc = fill_norm_bwd(a, &k);
+  if (rc) return rc;
+  dim3 grid((unsigned)a->n_chunks, (unsigned)(a->n_img * a->cb));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->gP) norm_bwd_reduce_kernel<true><<<grid, 256, 0, st>>>(k);
+  else norm_bwd_reduce_kernel<false><<<grid, 256, 0, st>>>(k);
+  return check_launch("norm_bwd_reduce_kernel");
+}
+
+extern "C" int mmseg_instnorm_act_bwd_apply(const mmseg_norm_bwd_args* a, void* stream) {
+  NormBwdK k;
+  int rc = fill_norm_bwd(a, &k);
+  if (rc) return rc;
+  if (!a->dx) return fail(MMSEG_ERR_INVALID_ARG, "instnorm_act_bwd_apply: null dx");
+  const int rows = a->n_img * a->cb;
+  const size_t items = a->gP ? (size_t)(a->Z / 2) * (a->Y / 2) * (a->X / 2) : (size_t)a->Z * a->Y * a->X;
+  dim3 grid(gxb(items, rows, 65535), (unsigned)rows);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->gP) norm_bwd_apply_kernel<true><<<grid, 256, 0, st>>>(k);
+  else norm_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(k);
+  return check_launch("norm_bwd_apply_kernel");
+}
+
+extern "C" int mmseg_unshuffle_k2s2(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_cb_off, int32_t cb,
+                                    int32_t Z, int32_t Y, int32_t X, void* dst, void* stream) {
+  if (!src || !dst || n_img < 1 || cb < 1 || Z < 1 || Y < 1 || X < 1)
+    return fail(MMSEG_ERR_INVALID_ARG, "unshuffle_k2s2: bad arguments");
+  const int rows = n_img * cb;
+  dim3 grid(gxb((size_t)Z * Y * X, rows, 65535), (unsigned)rows);
+  unshuffle_k2s2_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), src_cbt, src_cb_off, cb, Z, Y, X,
+      reinterpret_cast<__nv_bfloat16*>(dst));
+  return check_launch("unshuffle_k2s2_kernel");
+}

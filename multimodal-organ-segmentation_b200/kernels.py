@@ -421,3 +421,37 @@ def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt
     _call("mmseg_wgrad_reduce", _ptr(partial), n_part, ksize, cig // 8, ntc // 8, n_cot, cin, cout_gemm, cout,
           1 if transposed else 0, _ptr(cm), _ptr(dw), _stream())
     return dw
+
+
+# --------------------------------------------------------------------------------------------- backward (elementwise)
+def instnorm_act_bwd(raw: Tensor, mean_rstd: Tensor, n_img: int, channels: int, Z: int, Y: int, X: int,
+                     gA: Optional[Blocked], gA_c0: int, gA_scale: float, gP: Optional[Blocked], gP_c0: int,
+                     dx: Tensor, slope: float = 0.0, chan_scale: Optional[Tensor] = None) -> None:
+    """dx (blocked bf16 [n_img, channels/8, Z, Y, X, 8]) = gradient of the raw conv output; see mmseg_norm_bwd_args."""
+    a = _lib.NormBwdArgs()
+    nvox = Z * Y * X
+    n_chunks = max(1, min(64, (nvox + 8191) // 8192))
+    partial = torch.empty((n_img * channels // 8, n_chunks, 16), dtype=torch.float32, device=raw.device)
+    a.x, a.mean_rstd, a.partial, a.dx = raw.data_ptr(), mean_rstd.data_ptr(), partial.data_ptr(), dx.data_ptr()
+    a.gA = gA.t.data_ptr() if gA is not None else None
+    a.gP = gP.t.data_ptr() if gP is not None else None
+    a.chan_scale = chan_scale.data_ptr() if chan_scale is not None else None
+    a.n_img, a.cb, a.Z, a.Y, a.X = n_img, channels // 8, Z, Y, X
+    if gA is not None:
+        a.gA_cbt, a.gA_cb_off = gA.cbt, gA_c0 // 8
+    if gP is not None:
+        a.gP_cbt, a.gP_cb_off = gP.cbt, gP_c0 // 8
+    a.dx_cbt, a.dx_cb_off, a.n_chunks = channels // 8, 0, n_chunks
+    a.gA_scale, a.slope = gA_scale, slope
+    if PROFILE is not None:
+        _INFO[0] = {"bytes": n_img * channels * nvox * 4.0, "layer": f"bwd-reduce c{channels} {Z}x{Y}x{X}"}
+    _call("mmseg_instnorm_act_bwd_reduce", C.byref(a), _stream())
+    if PROFILE is not None:
+        _INFO[0] = {"bytes": n_img * channels * nvox * 6.0, "layer": f"bwd-apply c{channels} {Z}x{Y}x{X}"}
+    _call("mmseg_instnorm_act_bwd_apply", C.byref(a), _stream())
+
+
+def unshuffle_k2s2(src: Blocked, c0: int, channels: int, dst: Tensor) -> None:
+    """src: high-res blocked gradient (channels [c0, c0+channels)) -> dst blocked [n_img, 8*channels/8, Z/2, Y/2, X/2, 8]."""
+    _call("mmseg_unshuffle_k2s2", _ptr(src.t), src.n_img, src.cbt, c0 // 8, channels // 8, src.Z // 2, src.Y // 2,
+          src.X // 2, _ptr(dst), _stream())

@@ -9,7 +9,8 @@ from typing import Any, Dict, List, Tuple, Union
 import torch
 import torch.nn as nn
 
-from .unet import ConvBlock3D, DownBlock3D, UpBlock3D, _require_cuda, _no_autograd, _DEFAULT_MODE
+from .unet import (ConvBlock3D, DownBlock3D, UpBlock3D, _require_cuda, _no_autograd, _wants_grad, _train_step_forward,
+                   _DEFAULT_MODE)
 from ....engine import DualEncoderEngine
 from .... import kernels as K
 from ....kernels import Blocked
@@ -106,10 +107,13 @@ class DualEncoder(nn.Module):
     def forward(self, x: torch.Tensor, return_features: bool = False
                 ) -> Union[torch.Tensor, Tuple[torch.Tensor, Dict[str, List[torch.Tensor]]]]:
         _require_cuda(x)
-        _no_autograd(self, x)
         self.encoders[0]["init_conv"].kernel_supported()
+        if _wants_grad(self, x):
+            if return_features:
+                raise NotImplementedError("return_features is an inference-path option")
+            return _train_step_forward(self, "dual", x)
         if self.training and isinstance(self.dropout, nn.Dropout3d) and self.dropout.p > 0:
-            raise NotImplementedError("Dropout3d before out_conv in train mode belongs to the training path")
+            raise NotImplementedError("train-mode Dropout3d under no_grad: call model.eval() for inference")
         eng = self.engine()
         logits = eng.forward(x)
         if return_features:

@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 
 from ....engine import ConvRunner, UNet3DEngine
+from ....train_engine import TrainEngine, train_forward
 from .... import kernels as K
 from .... import _lib
 from ....kernels import Blocked
@@ -22,11 +23,36 @@ def _require_cuda(x: torch.Tensor) -> None:
         raise RuntimeError("mmseg_b200 modules run on CUDA (sm_100a) tensors only; there is no CPU fallback")
 
 
+def _wants_grad(module: nn.Module, x: torch.Tensor) -> bool:
+    return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters()))
+
+
 def _no_autograd(module: nn.Module, x: torch.Tensor) -> None:
-    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters())):
+    """Stand-alone building blocks are forward-only; whole models (UNet3D / DualEncoder) train through TrainEngine."""
+    if _wants_grad(module, x):
         raise NotImplementedError(
-            "backward (dgrad/wgrad) kernels are not built yet: call under torch.no_grad() / model.eval() inference. "
-            "Training parity is scheduled after the forward/sliding-window path (DESIGN.md, scope row (f)).")
+            "this stand-alone block has no backward of its own: wrap the call in torch.no_grad(), or train the whole "
+            "UNet3D / DualEncoder (their backward runs in the sm_100a dgrad / wgrad / norm-backward kernels)")
+
+
+def _train_step_forward(model: nn.Module, kind: str, x: torch.Tensor) -> torch.Tensor:
+    """Forward that records the tape for the kernel backward (parameters get gradients; the input does not)."""
+    if x.requires_grad:
+        raise NotImplementedError("gradients w.r.t. the input volume (first-layer dgrad) are not built: x.requires_grad "
+                                  "must be False")
+    if model.numeric_mode != "bf16":
+        raise NotImplementedError("the backward path runs in bf16 mode (north_star: bf16 training step); call "
+                                  "set_numeric_mode('bf16') before training")
+    eng = model.__dict__.get("_train_engine")
+    if eng is None:
+        eng = model.__dict__["_train_engine"] = TrainEngine(model, kind)
+    drop = None
+    if model.training and isinstance(model.dropout, nn.Dropout3d) and model.dropout.p > 0:
+        # same draw as nn.Dropout3d (feature dropout): one Bernoulli(1-p) per (sample, channel), scaled by 1/(1-p)
+        p = model.dropout.p
+        noise = torch.empty((x.shape[0], model.features[0]), dtype=torch.float32, device=x.device).bernoulli_(1 - p)
+        drop = noise / (1 - p)
+    return train_forward(eng, x, drop)
 
 
 class ConvBlock3D(nn.Module):
@@ -201,10 +227,13 @@ class UNet3D(nn.Module):
     def forward(self, x: torch.Tensor, return_features: bool = False
                 ) -> Union[torch.Tensor, Tuple[torch.Tensor, List[torch.Tensor]]]:
         _require_cuda(x)
-        _no_autograd(self, x)
         self.init_conv.kernel_supported()
+        if _wants_grad(self, x):
+            if return_features:
+                raise NotImplementedError("return_features is an inference-path option")
+            return _train_step_forward(self, "unet", x)
         if self.training and isinstance(self.dropout, nn.Dropout3d) and self.dropout.p > 0:
-            raise NotImplementedError("Dropout3d before out_conv in train mode belongs to the training path")
+            raise NotImplementedError("train-mode Dropout3d under no_grad: call model.eval() for inference")
         eng = self.engine()
         logits = eng.forward(x)
         if return_features:

@@ -1,0 +1,316 @@
+"""Training engine: forward with saved state + backward (dgrad / wgrad / norm-act-pool backward) for UNet3D and
+DualEncoder, entirely in the sm_100a kernels (bf16 operands, fp32 accumulation, fp32 weight gradients).
+
+The forward records a tape of ops; `backward(dlogits)` walks it in reverse.  Every activation buffer has a gradient
+buffer of the same blocked shape; each region of a gradient buffer is written by exactly one dgrad launch, and the
+two consumers of an encoder output (skip connection + MaxPool path) are merged inside the norm-backward kernel, so no
+gradient accumulation pass (and no float atomic) exists anywhere — the whole step is deterministic
+(works under torch.use_deterministic_algorithms(True), unlike the reference).
+
+Reference semantics: autograd through UNet3D.forward (src/models/backbones/unet.py:165-200) / DualEncoder.forward
+(src/models/backbones/dual_encoder.py:112-199) as driven by Trainer._train_epoch (src/trainer/trainer.py:237-243).
+"""
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from . import kernels as K
+from .kernels import Blocked
+
+Tensor = torch.Tensor
+
+
+def _wrap(t: Tensor, n: int, channels: int, Z: int, Y: int, X: int) -> Blocked:
+    """A Blocked view over an existing bf16 tensor [n, channels/8, Z, Y, X, 8] (no allocation)."""
+    b = Blocked.__new__(Blocked)
+    b.n_img, b.channels, b.Z, b.Y, b.X = n, channels, Z, Y, X
+    b.cb = b.cbt = channels // 8
+    b.split, b.lo_off = False, 0
+    b.t = t
+    return b
+
+
+class TrainEngine:
+    def __init__(self, module, kind: str):
+        assert kind in ("unet", "dual")
+        self.module, self.kind = module, kind
+        self._shape = None
+        self.A: Dict[str, Blocked] = {}      # activations
+        self.G: Dict[str, Blocked] = {}      # gradients w.r.t. activations
+        self.S: Dict[str, Tensor] = {}       # per-op saved tensors (raw conv outputs, mean/rstd) and workspaces
+        self.tape: List[dict] = []
+        self.grads: Dict[Tensor, Tensor] = {}
+
+    # ---------------------------------------------------------------- buffers
+    def _reset(self, n, Z, Y, X, device):
+        if self._shape != (n, Z, Y, X, str(device)):
+            self.A.clear(); self.G.clear(); self.S.clear()
+            self._shape = (n, Z, Y, X, str(device))
+        self.device = device
+        self.tape = []
+        self.grads = {}
+
+    def act(self, name: str, n, channels, Z, Y, X) -> Blocked:
+        b = self.A.get(name)
+        if b is None:
+            b = self.A[name] = Blocked(n, channels, Z, Y, X, False, self.device)
+            b.name = name
+        return b
+
+    def grad_of(self, a: Blocked) -> Blocked:
+        g = self.G.get(a.name)
+        if g is None:
+            g = self.G[a.name] = Blocked(a.n_img, a.channels, a.Z, a.Y, a.X, False, self.device)
+            g.name = "g_" + a.name
+        return g
+
+    def saved(self, name: str, shape, dtype) -> Tensor:
+        t = self.S.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = self.S[name] = torch.empty(shape, dtype=dtype, device=self.device)
+        return t
+
+    # ---------------------------------------------------------------- forward ops
+    def conv_norm_act(self, name: str, src: Blocked, segs, conv, dst: Blocked, dst_c0: int = 0,
+                      pooled: Optional[Blocked] = None, slope: float = 0.0, gspec=None, need_dgrad: bool = True,
+                      chan_scale: Optional[Tensor] = None):
+        n, Z, Y, X = src.n_img, src.Z, src.Y, src.X
+        cout = conv.weight.shape[0]
+        pw = K.pack_conv_weight(conv.weight, None, False, [s[1] for s in segs], use_bias=False)
+        a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], False)
+        tile = K.plan_conv(X, Y, Z, n, pw.n_kchunks, pw.n_out, pw.ksize, pw.NT)
+        raw = self.saved(name + ".raw", (n, cout // 8, Z, Y, X, 8), torch.bfloat16)
+        stats = self.saved("ws.stats", (n * tile.tiles_per_img * cout * 2,), torch.float32)
+        mr = self.saved(name + ".mr", (n, cout, 2), torch.float32)
+        K.conv3d(src, pw, a_cb, raw, _lib.OUT_BLOCKED_BF16, stats=stats, dst_cbt=cout // 8, tile=tile)
+        K.instnorm_finalize(stats, n, tile.tiles_per_img, cout, Z * Y * X, mr)
+        mr_apply = mr
+        if chan_scale is not None:  # Dropout3d: relu(y^) * s == relu(y^ * s) for s >= 0 -> fold s into rstd
+            mr_apply = self.saved(name + ".mr_drop", (n, cout, 2), torch.float32)
+            mr_apply.copy_(mr)
+            mr_apply[:, :, 1] *= chan_scale
+        K.instnorm_act_apply(raw, False, mr_apply, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, 0)
+        self.tape.append(dict(kind="cna", name=name, src=src, segs=list(segs), conv=conv, dst=dst, dst_c0=dst_c0,
+                              pooled=pooled, slope=slope, raw=raw, mr=mr, gspec=gspec, need_dgrad=need_dgrad,
+                              chan_scale=chan_scale))
+
+    def conv_transpose(self, name: str, src: Blocked, up, dst: Blocked):
+        cin = up.weight.shape[0]
+        pw = K.pack_conv_weight(up.weight, up.bias, False, None, transposed=True)
+        a_cb = K.a_chunk_table(src, [0], [cin], False)
+        K.conv3d(src, pw, a_cb, dst.t, _lib.OUT_CONVT_K2S2, dst_cbt=dst.cbt, dst_cb_off=0, dst_lo_off=0)
+        self.tape.append(dict(kind="convt", name=name, src=src, up=up, dst=dst))
+
+    def conv_logits(self, name: str, src: Blocked, conv, logits: Tensor):
+        cin = conv.weight.shape[1]
+        pw = K.pack_conv_weight(conv.weight, conv.bias, False, None)
+        a_cb = K.a_chunk_table(src, [0], [cin], False)
+        K.conv3d(src, pw, a_cb, logits, _lib.OUT_NCDHW_F32)
+        self.tape.append(dict(kind="logits", name=name, src=src, conv=conv))
+
+    def conv_bias(self, name: str, src: Blocked, segs, conv, dst: Blocked, dst_c0: int):
+        """1x1 conv + bias straight into an activation buffer (DualEncoder 'concat' fusion_proj)."""
+        pw = K.pack_conv_weight(conv.weight, conv.bias, False, [s[1] for s in segs])
+        a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], False)
+        K.conv3d(src, pw, a_cb, dst.t, _lib.OUT_BLOCKED_BF16, dst_cbt=dst.cbt, dst_cb_off=dst_c0 // 8)
+        self.tape.append(dict(kind="convb", name=name, src=src, segs=list(segs), conv=conv, dst=dst, dst_c0=dst_c0))
+
+    # ---------------------------------------------------------------- backward ops
+    def _dgrad(self, dy: Blocked, dy_channels: int, w_as_conv: Tensor, dst: Blocked, dst_c0: int):
+        """dst[:, dst_c0 : dst_c0 + Cout'] = conv(dy, w_as_conv) with the forward tcgen05 kernel."""
+        pw = K.pack_conv_weight(w_as_conv, None, False, [dy_channels], use_bias=False)
+        a_cb = K.a_chunk_table(dy, [0], [dy_channels], False)
+        K.conv3d(dy, pw, a_cb, dst.t, _lib.OUT_BLOCKED_BF16, dst_cbt=dst.cbt, dst_cb_off=dst_c0 // 8)
+
+    def _channel_sums(self, b: Blocked, c0: int, channels: int) -> Tensor:
+        """[channels] fp32 sums over images and voxels (bias gradients)."""
+        return (K.channel_mean(b, c0, channels) * float(b.nvox)).sum(0)
+
+    def _bwd_cna(self, op):
+        src, dst, conv = op["src"], op["dst"], op["conv"]
+        n, Z, Y, X = src.n_img, src.Z, src.Y, src.X
+        cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+        if op["gspec"] is not None:
+            gA, gA_c0, scale = op["gspec"]
+        else:
+            gA, gA_c0, scale = self.grad_of(dst), op["dst_c0"], 1.0
+        gP = self.grad_of(op["pooled"]) if op["pooled"] is not None else None
+        draw_t = self.saved("ws.draw", (n * cout * Z * Y * X,), torch.bfloat16).view(n, cout // 8, Z, Y, X, 8)
+        K.instnorm_act_bwd(op["raw"], op["mr"], n, cout, Z, Y, X, gA, gA_c0, scale, gP, 0, draw_t, op["slope"],
+                           op["chan_scale"])
+        draw = _wrap(draw_t, n, cout, Z, Y, X)
+        ks = conv.weight.shape[2]
+        self.grads[conv.weight] = K.conv3d_wgrad(src, op["segs"], draw_t, cout // 8, 0, cout, ks, conv.weight.shape)
+        if conv.bias is not None:  # cancelled exactly by the InstanceNorm mean subtraction
+            self.grads[conv.bias] = torch.zeros_like(conv.bias, dtype=torch.float32)
+        if op["need_dgrad"]:
+            segs = op["segs"]
+            assert all(s[1] % 16 == 0 for s in segs) and all(segs[i][0] + segs[i][1] == segs[i + 1][0] for i in range(len(segs) - 1)), \
+                "dgrad needs contiguous 16-channel-aligned input segments"
+            wd = conv.weight.detach().float().flip(2, 3, 4).transpose(0, 1).contiguous()   # [cin, cout, k, k, k]
+            self._dgrad(draw, cout, wd, self.grad_of(src), segs[0][0])
+
+    def _bwd_convt(self, op):
+        src, dst, up = op["src"], op["dst"], op["up"]
+        cin, f = up.weight.shape[0], up.weight.shape[1]
+        n, Z, Y, X = src.n_img, src.Z, src.Y, src.X
+        gdst = self.grad_of(dst)
+        dyu_t = self.saved("ws.dyu", (n * 8 * f * Z * Y * X,), torch.bfloat16).view(n, f, Z, Y, X, 8)  # 8f/8 = f blocks
+        K.unshuffle_k2s2(gdst, 0, f, dyu_t)
+        dyu = _wrap(dyu_t, n, 8 * f, Z, Y, X)
+        self.grads[up.weight] = K.conv3d_wgrad(src, [(0, cin)], dyu_t, f, 0, 8 * f, 1, up.weight.shape, transposed=True)
+        if up.bias is not None:
+            self.grads[up.bias] = self._channel_sums(dyu, 0, 8 * f).view(8, f).sum(0)
+        wd = up.weight.detach().float().reshape(cin, f, 8).permute(0, 2, 1).reshape(cin, 8 * f, 1, 1, 1).contiguous()
+        self._dgrad(dyu, 8 * f, wd, self.grad_of(src), 0)
+
+    def _bwd_logits(self, op, dlogits: Tensor):
+        src, conv = op["src"], op["conv"]
+        k, cin = conv.weight.shape[0], conv.weight.shape[1]
+        n, Z, Y, X = src.n_img, src.Z, src.Y, src.X
+        kp = (k + 15) // 16 * 16
+        dl = self.act("ws.dlogits", n, kp, Z, Y, X)
+        K.pack_ncdhw(dlogits.contiguous().float(), dl)
+        self.grads[conv.weight] = K.conv3d_wgrad(src, [(0, cin)], dl.t, dl.cbt, 0, k, 1, conv.weight.shape)
+        if conv.bias is not None:
+            self.grads[conv.bias] = self._channel_sums(dl, 0, kp)[:k]
+        wd = conv.weight.detach().float().reshape(k, cin).t().reshape(cin, k, 1, 1, 1).contiguous()
+        pw = K.pack_conv_weight(wd, None, False, [k], use_bias=False)
+        a_cb = K.a_chunk_table(dl, [0], [k], False)
+        g = self.grad_of(src)
+        K.conv3d(dl, pw, a_cb, g.t, _lib.OUT_BLOCKED_BF16, dst_cbt=g.cbt, dst_cb_off=0)
+
+    def _bwd_convb(self, op):
+        src, dst, conv, c0 = op["src"], op["dst"], op["conv"], op["dst_c0"]
+        cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+        g = self.grad_of(dst)
+        self.grads[conv.weight] = K.conv3d_wgrad(src, op["segs"], g.t, g.cbt, c0 // 8, cout, 1, conv.weight.shape)
+        if conv.bias is not None:
+            self.grads[conv.bias] = self._channel_sums(g, c0, cout)
+        # dgrad reads the gradient region in place: view it as a blocked tensor through the K-chunk table
+        wd = conv.weight.detach().float().reshape(cout, cin).t().reshape(cin, cout, 1, 1, 1).contiguous()
+        pw = K.pack_conv_weight(wd, None, False, [cout], use_bias=False)
+        a_cb = K.a_chunk_table(g, [c0], [cout], False)
+        gs = self.grad_of(src)
+        K.conv3d(g, pw, a_cb, gs.t, _lib.OUT_BLOCKED_BF16, dst_cbt=gs.cbt, dst_cb_off=op["segs"][0][0] // 8)
+
+    @torch.no_grad()
+    def backward(self, dlogits: Tensor) -> Dict[Tensor, Tensor]:
+        for op in reversed(self.tape):
+            kind = op["kind"]
+            if kind == "cna":
+                self._bwd_cna(op)
+            elif kind == "convt":
+                self._bwd_convt(op)
+            elif kind == "logits":
+                self._bwd_logits(op, dlogits)
+            elif kind == "convb":
+                self._bwd_convb(op)
+        return self.grads
+
+    # ---------------------------------------------------------------- model forwards
+    @torch.no_grad()
+    def forward(self, x: Tensor, drop_scale: Optional[Tensor] = None) -> Tensor:
+        """x NCDHW fp32 (CUDA) -> logits NCDHW fp32; records the tape.  drop_scale [n, f0]: Dropout3d mask * 1/(1-p)."""
+        _lib.require_device()
+        if not x.is_cuda:
+            raise RuntimeError("mmseg_b200 engines run on CUDA tensors only (no CPU fallback)")
+        x = x.contiguous().float()
+        n, _, Z, Y, X = x.shape
+        self._reset(n, Z, Y, X, x.device)
+        m = self.module
+        f, L = m.features, len(m.features)
+        if any(d % (1 << (L - 1)) for d in (Z, Y, X)):
+            raise NotImplementedError(f"spatial size {(Z, Y, X)} is not divisible by {1 << (L - 1)}")
+        A = lambda name, ch, l: self.act(name, n, ch, Z >> l, Y >> l, X >> l)
+        for l in range(L - 1):
+            A(f"cat{l}", 2 * f[l], l)
+        bott = A("bott", f[L - 1], L - 1)
+        fused = lambda l: (bott, 0) if l == L - 1 else (self.A[f"cat{l}"], f[l])
+
+        if self.kind == "unet":
+            cin = m.in_channels
+            a_in = A("in", (cin + 15) // 16 * 16, 0)
+            K.pack_ncdhw(x, a_in)
+            self.conv_norm_act("init.c1", a_in, [(0, cin)], m.init_conv.conv1, A("e0.mid", f[0], 0), need_dgrad=False)
+            for l in range(L):
+                blk = m.init_conv if l == 0 else m.encoders[l - 1].conv
+                if l > 0:
+                    self.conv_norm_act(f"e{l}.c1", self.A[f"pool{l}"], [(0, f[l - 1])], blk.conv1, A(f"e{l}.mid", f[l], l))
+                dst, c0 = fused(l)
+                self.conv_norm_act(f"e{l}.c2", self.A[f"e{l}.mid"], [(0, f[l])], blk.conv2, dst, c0,
+                                   pooled=A(f"pool{l + 1}", f[l], l + 1) if l < L - 1 else None)
+            decoders = m.decoders
+        else:
+            M, cpm = m.num_modalities, m.in_channels_per_modality
+            if m.fusion_type == "attention":
+                raise NotImplementedError("training through CrossModalAttention (fusion.type='attention') is not built yet: "
+                                          "the gate's backward kernel is scope row (f); use mean/add/concat fusion")
+            for l in range(L):
+                A(f"stack{l}", M * f[l], l)
+            scale = {"add": 1.0}.get(m.fusion_type, 1.0 / M)
+            for i in range(M):
+                a_in = A(f"m{i}.in", (cpm + 15) // 16 * 16, 0)
+                K.pack_ncdhw(x[:, i * cpm:(i + 1) * cpm].contiguous(), a_in)
+                enc = m.encoders[i]
+                self.conv_norm_act(f"m{i}.init.c1", a_in, [(0, cpm)], enc["init_conv"].conv1, A(f"m{i}.e0.mid", f[0], 0),
+                                   need_dgrad=False)
+                for l in range(L):
+                    blk = enc["init_conv"] if l == 0 else enc["blocks"][l - 1].conv
+                    if l > 0:
+                        self.conv_norm_act(f"m{i}.e{l}.c1", self.A[f"m{i}.pool{l}"], [(0, f[l - 1])], blk.conv1,
+                                           A(f"m{i}.e{l}.mid", f[l], l))
+                    gspec = None
+                    if m.fusion_type != "concat":  # mean / add: the stack gradient is the fused gradient times `scale`
+                        fd, fc0 = fused(l)
+                        gspec = (self.grad_of(fd), fc0, scale)
+                    self.conv_norm_act(f"m{i}.e{l}.c2", self.A[f"m{i}.e{l}.mid"], [(0, f[l])], blk.conv2,
+                                       self.A[f"stack{l}"], i * f[l],
+                                       pooled=A(f"m{i}.pool{l + 1}", f[l], l + 1) if l < L - 1 else None, gspec=gspec)
+            for l in range(L):
+                dst, c0 = fused(l)
+                st = self.A[f"stack{l}"]
+                if m.fusion_type == "concat":
+                    self.conv_bias(f"fuse{l}", st, [(i * f[l], f[l]) for i in range(M)], m.fusion_proj[l], dst, c0)
+                else:
+                    K.modality_combine(st, M, f[l], dst, c0, None, scale)
+            decoders = m.decoder
+
+        cur = bott
+        for j in range(L - 1):
+            l = L - 2 - j
+            dec = decoders[j]
+            cat = self.A[f"cat{l}"]
+            self.conv_transpose(f"d{l}.up", cur, dec.up, cat)
+            self.conv_norm_act(f"d{l}.c1", cat, [(0, f[l]), (f[l], f[l])], dec.conv.conv1, A(f"d{l}.mid", f[l], l))
+            last = l == 0
+            self.conv_norm_act(f"d{l}.c2", self.A[f"d{l}.mid"], [(0, f[l])], dec.conv.conv2, A(f"d{l}.out", f[l], l),
+                               chan_scale=drop_scale if last else None)
+            cur = self.A[f"d{l}.out"]
+        logits = torch.empty((n, m.out_channels, Z, Y, X), dtype=torch.float32, device=x.device)
+        self.conv_logits("out", cur, m.out_conv, logits)
+        return logits
+
+
+class _ModelFunction(torch.autograd.Function):
+    """logits = model(x) with the whole backward in the sm_100a kernels; parameters receive fp32 gradients."""
+
+    @staticmethod
+    def forward(ctx, engine: TrainEngine, x: Tensor, drop_scale: Optional[Tensor], *params: Tensor) -> Tensor:
+        ctx.engine, ctx.params = engine, params
+        return engine.forward(x, drop_scale)
+
+    @staticmethod
+    def backward(ctx, dlogits: Tensor):
+        grads = ctx.engine.backward(dlogits)
+        out = []
+        for p in ctx.params:
+            g = grads.get(p)
+            out.append(None if g is None or not p.requires_grad else g.to(p.dtype).view_as(p))
+        return (None, None, None, *out)
+
+
+def train_forward(engine: TrainEngine, x: Tensor, drop_scale: Optional[Tensor] = None) -> Tensor:
+    params = [p for p in engine.module.parameters()]
+    return _ModelFunction.apply(engine, x, drop_scale, *params)

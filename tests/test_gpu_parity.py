@@ -90,3 +90,52 @@ def test_swi_blend_finalize_exact():
                                 dict(nmode="bf16")])
 def test_sliding_window_vs_oracle(kw):
     _c().swi_case(**kw)
+
+
+# ------------------------------------------------------------------------------------------------ backward / training
+@pytest.mark.parametrize("args,kw", [
+    ((32, 32, (4, 8, 16)), {}),
+    ((32, 32, (9, 12, 20)), dict(n_img=2)),                       # ragged tiles, several images
+    ((16, 32, (8, 8, 8)), {}),
+    ((2, 32, (6, 10, 24)), {}),                                   # first layer (2 real input channels)
+    ((64, 64, (8, 8, 8)), {}),
+    ((64, 32, (6, 16, 16)), dict(segs=[(0, 32), (32, 32)])),      # concat input [up | skip]
+    ((32, 8, (6, 7, 20)), dict(ks=1)),                            # out_conv
+    ((64, 256, (4, 4, 8)), dict(ks=1)),                           # ConvTranspose GEMM view
+    ((32, 32, (24, 24, 24)), dict(n_img=2)),
+    ((256, 128, (4, 4, 4)), dict(n_img=2)),
+])
+def test_wgrad_tcgen05(args, kw):
+    _c().wgrad_case(*args, **kw)
+
+
+@pytest.mark.parametrize("kw", [dict(pool=False), dict(pool=True), dict(channels=32, shape=(6, 6, 8), n_img=1, slope=0.2, scale=0.5)])
+def test_instnorm_act_pool_backward(kw):
+    _c().norm_bwd_case(**kw)
+
+
+@pytest.mark.parametrize("args", [(32, 32, (6, 8, 12), 1, 3), (64, 32, (5, 7, 9), 2, 3), (16, 32, (4, 6, 8), 1, 1)])
+def test_dgrad_through_forward_kernel(args):
+    _c().dgrad_case(*args)
+
+
+def test_conv_transpose_backward():
+    _c().convt_bwd_case()
+
+
+@pytest.mark.parametrize("args,kw", [
+    (("unet", (16, 32), 16, 1), {}),
+    (("unet", (16, 32, 64), 16, 2), {}),
+    (("dual", (16, 32), 16, 2), dict(fusion="late")),
+    (("dual", (16, 32), 16, 1), dict(fusion="concat")),
+    (("dual", (16, 32), 16, 1), dict(fusion="add", M=3)),
+])
+def test_training_step_vs_fp64_autograd(args, kw):
+    _c().train_step_case(*args, **kw)
+
+
+@pytest.mark.parametrize("name,fusion", [("dual_attention_2", "attention"), ("dual_concat_2", "concat"),
+                                         ("dual_cross_attention_2", "cross_attention"), ("dual_add_2", "add"),
+                                         ("dual_attention_4", "attention")])
+def test_dual_encoder_golden_from_reference(name, fusion):
+    _c().dual_golden_case(name)
