@@ -257,7 +257,22 @@ def run_ours(args):
            "d2h_bytes_per_step": int(d2h.item()), "ms_per_step": ms_e2e, "steps": e2e_steps}
     log(f"[rank {rank}] e2e: {ms_e2e:.2f} ms/volume -> {e2e['value'] / 1e6:.1f} Mvox/s")
 
+    def secondary_train():
+        """training samples/s (BASELINE.json configs[1]); never allowed to break the headline line"""
+        if args.no_train:
+            return None
+        try:
+            inf._state = None
+            inf._dev_vol = None
+            _INFERERS.clear()
+            torch.cuda.empty_cache()
+            return train_measure(3, 2, world, rank, dev, use_graph=True, cpu=False)
+        except Exception as e:
+            torch.cuda.synchronize()
+            return {"error": f"{type(e).__name__}: {e}"}
+
     if rank != 0:
+        secondary_train()
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -347,6 +362,9 @@ def run_ours(args):
         model.set_numeric_mode(args.mode)
         log("parity vs oracle on the crop:", json.dumps(parity))
 
+    vol_dev = None
+    train_res = secondary_train()
+
     line = {
         "metric": "sliding-window inference voxels/s (CT+PET)", "value": value, "unit": "voxels/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -355,9 +373,153 @@ def run_ours(args):
         "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(),
         "roofline": roofline, "roofline_norm": roofline_norm,
         "step_tflops_per_gpu": step_tf, "step_frac_of_tensor_peak": step_tf / tf_peak,
-        "cpu_baseline": cpu_baseline, "parity": parity,
+        "cpu_baseline": cpu_baseline, "parity": parity, "train": train_res,
     }
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+
+# ------------------------------------------------------------------------------------------------ training workload
+TRAIN_S, TRAIN_B = 128, 2
+TRAIN_GF_PER_STEP = 7394.0 * (TRAIN_B / 2)   # DualEncoder C2 train step, per GPU
+
+
+def train_config(device):
+    return {"model": {"name": "dual_encoder", "in_channels": 2, "out_channels": 8,
+                      "backbone": {"features": FEATURES, "norm": "instance"},
+                      "fusion": {"type": "cross_attention"}, "head": {"dropout": 0.1}},
+            "data": {"modalities": ["CT", "PET"]},
+            "training": {"epochs": 1, "optimizer": {"name": "adamw", "lr": 1e-4, "weight_decay": 1e-5},
+                         "loss": {"name": "dice_ce", "dice_weight": 0.5, "ce_weight": 0.5}, "accumulation_steps": 1},
+            "hardware": {"device": device, "mixed_precision": True, "cuda_graph": True},
+            "experiment": {"output_dir": "/tmp/mmseg_b200_bench", "name": "train"}}
+
+
+def train_measure(steps, warmup, world, rank, dev, use_graph=True, cpu=False):
+    """BASELINE.json configs[1]: DualEncoder (fusion 'cross_attention' == mean over modalities in the reference) on
+    CT+PET 128^3 patches, batch 2 per GPU, bf16 kernels, DiceCE, AdamW; data-parallel over `world` ranks (weak scaling).
+    Returns a dict with device-resident and end-to-end (pinned host batch in, loss out) samples/s."""
+    import torch.distributed as dist
+    import mmseg_b200  # noqa: F401
+    from mmseg_b200 import kernels as K
+    from mmseg_b200.src.models.build import build_model
+    from mmseg_b200.src.trainer.trainer import Trainer
+    torch.manual_seed(0)                       # identical replicas
+    cfg = train_config("cuda")
+    model = build_model(cfg)
+    tr = Trainer(cfg, model)
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.rand((TRAIN_B, 2, TRAIN_S, TRAIN_S, TRAIN_S), generator=g).pin_memory()
+    y_host = torch.randint(0, 8, (TRAIN_B, TRAIN_S, TRAIN_S, TRAIN_S), generator=g).pin_memory()
+    x, y = x_host.to(dev), y_host.to(dev)
+    tr.model.train()
+    mode = "eager"
+    step = lambda a, b: tr.train_step(a, b)
+    if use_graph:
+        try:
+            step = tr.graphed_train_step(x, y)
+            mode = "cuda_graph"
+        except Exception as e:  # capture can fail (e.g. a collective that is not capturable): measure eagerly
+            log(f"[rank {rank}] CUDA-graph capture of the train step failed ({type(e).__name__}: {e}); running eagerly")
+            torch.cuda.synchronize()
+            step = lambda a, b: tr.train_step(a, b)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n, w):
+        for _ in range(w):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / n, out
+
+    l0 = K.LAUNCHES[0]
+    ms, loss = timed(lambda: step(x, y), steps, warmup)
+    launches = (K.LAUNCHES[0] - l0) if mode == "eager" else None
+
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        yd = y_host.to(dev, non_blocking=True)
+        return step(xd, yd).item()          # device->host read of the loss, like trainer.py:260
+    ms_e2e, last = timed(e2e_step, max(1, min(steps, 5)), 1)
+    res = {"metric": "training samples/s (DualEncoder CT+PET 128^3, batch 2/GPU, bf16 step)",
+           "value": world * TRAIN_B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "n_gpus": world,
+           "scaling": "weak", "mode": mode, "loss": float(loss.item() if torch.is_tensor(loss) else loss),
+           "e2e": {"value": world * TRAIN_B / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": world * (x_host.numel() * 4 + y_host.numel() * 8), "d2h_bytes_per_step": world * 4},
+           "tflops_per_gpu": TRAIN_GF_PER_STEP / 1e3 / (ms * 1e-3), "gpu_launches_per_step": None,
+           "config": {"workload": "DualEncoder(fusion=cross_attention -> mean) 2 modalities 128^3, batch 2/GPU, "
+                                  "features 32-512, dropout 0.1, DiceCE, AdamW, fwd+bwd+allreduce+step "
+                                  "(BASELINE.json configs[1])", "parallelism": f"dp{world}"}}
+    # one eager profiled step: per-kernel shares (also counts the launches of a step)
+    K.PROFILE = []
+    l0 = K.LAUNCHES[0]
+    tr.train_step(x, y)
+    torch.cuda.synchronize()
+    res["gpu_launches_per_step"] = K.LAUNCHES[0] - l0
+    prof, K.PROFILE = K.PROFILE, None
+    agg = {}
+    for name, info, a, b in prof:
+        d = agg.setdefault(name, [0.0, 0.0, 0.0])
+        d[0] += a.elapsed_time(b)
+        if info:
+            d[1] += info.get("flops", 0.0)
+            d[2] += info.get("bytes", 0.0)
+    tot = sum(d[0] for d in agg.values())
+    res["kernel_ms"] = {k: round(v[0], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+    res["kernel_tflops"] = {k: round(v[1] / v[0] / 1e9, 1) for k, v in agg.items() if v[1] > 0}
+    res["kernel_gbs"] = {k: round(v[2] / v[0] / 1e6, 0) for k, v in agg.items() if v[2] > 0}
+    if rank == 0:
+        log(f"train step {mode}: {ms:.2f} ms -> {res['value']:.1f} samples/s ({res['tflops_per_gpu']:.0f} TFLOP/s/GPU); "
+            f"e2e {ms_e2e:.2f} ms; kernels {tot:.2f} ms: " + ", ".join(f"{k.replace('mmseg_', '')} {v:.2f}" for k, v in list(res['kernel_ms'].items())[:8]))
+    if cpu and rank == 0 and world == 1:
+        from oracle.train import train_step as oracle_step
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        sd = {k[len("backbone."):]: v.detach().cpu() for k, v in tr.model.state_dict().items()}
+        t0 = time.perf_counter()
+        oracle_step("dual", sd, dict(L=len(FEATURES), M=2, fusion="cross_attention"), x_host[:1], y_host[:1], torch.float32)
+        t = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": 1.0 / t, "unit": "samples/s", "cores": threads, "kind": "port",
+                               "sample": f"one fwd+DiceCE+bwd step at batch 1 ({t:.1f} s) through the oracle (CPU fp32 autograd)"}
+    return res
+
+
+def run_train(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --workload train needs a B200; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local)
+    sampler.start()
+    res = train_measure(args.steps, args.warmup, world, rank, dev, use_graph=not args.no_graph, cpu=not args.no_cpu)
+    sampler.stop_flag = True
+    sampler.join()
+    if rank == 0:
+        res.update({"steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None,
+                    "dtype": "bf16", "data": "synthetic", "clocks": sampler.summary()})
+        print(json.dumps(res), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -372,9 +534,15 @@ def main():
     ap.add_argument("--mode", default="bf16", choices=["bf16", "parity"])
     ap.add_argument("--engine-batch", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline / parity sample")
+    ap.add_argument("--workload", default="inference", choices=["inference", "train"],
+                    help="inference = headline sliding-window voxels/s (default); train = DualEncoder 128^3 samples/s")
+    ap.add_argument("--no-graph", action="store_true", help="train workload: do not capture the step in a CUDA graph")
+    ap.add_argument("--no-train", action="store_true", help="inference workload: skip the short training measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train":
+        run_train(args)
     else:
         run_ours(args)
 

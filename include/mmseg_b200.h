@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 #define MMSEG_ABI_VERSION 1
-#define MMSEG_MAX_KCHUNKS 96
+#define MMSEG_MAX_KCHUNKS 256
 #define MMSEG_MAX_WGRAD_GROUPS 64
 
 typedef enum {
@@ -220,6 +220,14 @@ int mmseg_dicece_fwd(const float* logits /* [B][C][N] */, const int64_t* target 
 int mmseg_dicece_bwd(const float* logits, const int64_t* target, int32_t B, int32_t C, int64_t N, float dice_weight,
                      float ce_weight, float smooth, int32_t include_background, const float* class_weights,
                      const float* sums, const float* grad_out /* [1] or NULL */, float* dlogits, void* stream);
+
+/*
+ * K x K confusion counts (rows = target, columns = prediction) of two label maps in one pass; `counts` accumulates
+ * (zero it first).  DiceMetric.update / ConfusionMatrix.update (src/trainer/metrics.py:42-65,184-196) read their
+ * per-class intersections and unions off this matrix.  pred is int64 or uint8.
+ */
+int mmseg_confusion_hist(const void* pred, int32_t pred_is_u8, const int64_t* target, int64_t N, int32_t K,
+                         uint64_t* counts /* [K*K] */, void* stream);
 
 /*
  * DualEncoder modality fusion (src/models/backbones/dual_encoder.py:167-199, CrossModalAttention :207-254; same maths

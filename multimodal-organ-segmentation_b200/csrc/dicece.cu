@@ -166,9 +166,44 @@ dicece_bwd_kernel(const float* __restrict__ logits, const long long* __restrict_
   }
 }
 
+// One pass over (prediction, target) label maps -> K x K confusion counts (rows = target, columns = prediction).
+// Integer atomics only (associative -> deterministic).  DiceMetric / ConfusionMatrix (src/trainer/metrics.py:42-65,
+// 184-196 — the latter a per-voxel Python loop in the reference) are read off this matrix.
+template <typename PT>
+__global__ void __launch_bounds__(256)
+confusion_kernel(const PT* __restrict__ pred, const long long* __restrict__ target, size_t N, int K,
+                 unsigned long long* __restrict__ counts) {
+  extern __shared__ unsigned int hist[];  // K*K
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x) hist[i] = 0u;
+  __syncthreads();
+  for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (size_t)gridDim.x * blockDim.x) {
+    const int p = (int)pred[n], t = (int)target[n];
+    if (p >= 0 && p < K && t >= 0 && t < K) atomicAdd(&hist[t * K + p], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x)
+    if (hist[i]) atomicAdd(&counts[i], (unsigned long long)hist[i]);
+}
+
 }  // namespace mmseg
 
 using namespace mmseg;
+
+extern "C" int mmseg_confusion_hist(const void* pred, int32_t pred_is_u8, const int64_t* target, int64_t N, int32_t K,
+                                    uint64_t* counts, void* stream) {
+  if (!pred || !target || !counts || N < 1 || K < 1 || K > 64)
+    return fail(MMSEG_ERR_INVALID_ARG, "confusion_hist: bad arguments");
+  int64_t nb = (N + 255) / 256;
+  if (nb > 148 * 8) nb = 148 * 8;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t sh = (size_t)K * K * sizeof(unsigned int);
+  const long long* tg = reinterpret_cast<const long long*>(target);
+  unsigned long long* c = reinterpret_cast<unsigned long long*>(counts);
+  // blocks cover at most 2^32 voxels each in a 32-bit smem counter: N / nb < 2^32 always holds here
+  if (pred_is_u8) confusion_kernel<uint8_t><<<(unsigned)nb, 256, sh, st>>>(reinterpret_cast<const uint8_t*>(pred), tg, (size_t)N, K, c);
+  else confusion_kernel<long long><<<(unsigned)nb, 256, sh, st>>>(reinterpret_cast<const long long*>(pred), tg, (size_t)N, K, c);
+  return check_launch("confusion_kernel");
+}
 
 extern "C" int mmseg_dicece_fwd(const float* logits, const int64_t* target, int32_t B, int32_t C, int64_t N,
                                 float dice_weight, float ce_weight, float smooth, int32_t include_background,

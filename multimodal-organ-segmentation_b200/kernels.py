@@ -376,6 +376,9 @@ def _plan_wgrad_tile(X: int, Y: int, Z: int, ksize: int, cig_blocks: int, cot_bl
     return best[1]
 
 
+_CI_MAPS: dict = {}
+
+
 def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt: int, dy_cb0: int, cout_gemm: int,
                  ksize: int, weight_shape, transposed: bool = False) -> Tensor:
     """dW (fp32, PyTorch weight layout `weight_shape`) of a conv whose input is `x` (channel segments `segs` in concat
@@ -416,7 +419,10 @@ def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt
                     "tile": (TX, TY, TZ, ntc, cig), "ctas": n_part * n_cig * n_cot}
     _call("mmseg_conv3d_wgrad", C.byref(a), _stream())
     dw = torch.empty(tuple(weight_shape), dtype=torch.float32, device=x.t.device)
-    cm = torch.tensor(ci_map, dtype=torch.int32, device=x.t.device)
+    key = (tuple(ci_map), str(x.t.device))
+    cm = _CI_MAPS.get(key)
+    if cm is None:  # cached: a host->device copy per call would also break CUDA-graph capture of the training step
+        cm = _CI_MAPS[key] = torch.tensor(ci_map, dtype=torch.int32, device=x.t.device)
     cout = weight_shape[1] if transposed else weight_shape[0]
     _call("mmseg_wgrad_reduce", _ptr(partial), n_part, ksize, cig // 8, ntc // 8, n_cot, cin, cout_gemm, cout,
           1 if transposed else 0, _ptr(cm), _ptr(dw), _stream())
@@ -455,3 +461,13 @@ def unshuffle_k2s2(src: Blocked, c0: int, channels: int, dst: Tensor) -> None:
     """src: high-res blocked gradient (channels [c0, c0+channels)) -> dst blocked [n_img, 8*channels/8, Z/2, Y/2, X/2, 8]."""
     _call("mmseg_unshuffle_k2s2", _ptr(src.t), src.n_img, src.cbt, c0 // 8, channels // 8, src.Z // 2, src.Y // 2,
           src.X // 2, _ptr(dst), _stream())
+
+
+def confusion_hist(pred: Tensor, target: Tensor, num_classes: int, counts: Tensor) -> None:
+    """counts [K, K] int64 (rows = target, columns = prediction) += histogram of (target, pred) pairs."""
+    _lib.require_device()
+    assert pred.is_cuda and target.is_cuda and counts.dtype == torch.int64 and counts.is_contiguous()
+    assert pred.dtype in (torch.int64, torch.uint8)
+    pred, target = pred.contiguous(), target.contiguous().long()
+    _call("mmseg_confusion_hist", _ptr(pred), 1 if pred.dtype == torch.uint8 else 0, _ptr(target), pred.numel(),
+          num_classes, _ptr(counts), _stream())

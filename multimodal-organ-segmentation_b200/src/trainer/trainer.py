@@ -1,0 +1,278 @@
+"""Trainer — drop-in mirror of the reference's src/trainer/trainer.py for the hot path: same constructor, `train()`,
+`evaluate()`, `predict()`, checkpoint files and history; the model / loss / metrics it drives are the sm_100a drop-ins.
+
+Differences that are deliberate (documented in DESIGN.md):
+  * mixed precision: the kernels compute in bf16 with fp32 accumulation, so `hardware.mixed_precision` needs neither
+    autocast nor a GradScaler (reference: fp16 autocast + GradScaler, trainer.py:74-75,237-248);
+  * sliding-window inference honours `inference.sliding_window.mode` (the reference never passes it to MONAI, so its
+    YAML value "gaussian" is dead config and MONAI's default "constant" applies; set the key to "constant" for that);
+  * data-parallel training: when torch.distributed is initialised, gradients are averaged with a bucketed all-reduce
+    that overlaps the backward kernels (parallel.GradBucketReducer); the reference has no distributed path.
+"""
+from pathlib import Path
+from typing import Any, Dict, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from ..models.build import load_checkpoint, save_checkpoint
+from .inference import sliding_window_inference
+from .losses import get_loss
+from .metrics import DiceMetric, get_metrics
+from ...parallel import GradBucketReducer
+
+
+def _progress(it, desc=""):
+    try:
+        from tqdm import tqdm
+        return tqdm(it, desc=desc)
+    except Exception:  # tqdm is cosmetic
+        return it
+
+
+class Trainer:
+    def __init__(self, config: Dict[str, Any], model: nn.Module, train_loader=None, val_loader=None,
+                 logger: Optional[Any] = None, resume_from: Optional[str] = None):
+        self.config = config
+        self.model = model
+        self.train_loader = train_loader
+        self.val_loader = val_loader
+        self.logger = logger
+        self.epochs = config["training"]["epochs"]
+        self.device = self._get_device()
+        self.model = self.model.to(self.device)
+        self.optimizer = self._setup_optimizer()
+        self.scheduler = self._setup_scheduler()
+        self.criterion = get_loss(config).to(self.device)
+        self.metrics = get_metrics(config)
+        self.use_amp = config["hardware"].get("mixed_precision", False)
+        self.scaler = None  # bf16 kernels: no loss scaling
+        self.accumulation_steps = config["training"].get("accumulation_steps", 1)
+        self.output_dir = Path(config["experiment"]["output_dir"]) / config["experiment"]["name"]
+        self.output_dir.mkdir(parents=True, exist_ok=True)
+        self.current_epoch = 0
+        self.best_metric = 0.0
+        self.history = {"train_loss": [], "val_loss": [], "val_dice": []}
+        self.reducer = None
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            self.reducer = GradBucketReducer(self.model)
+        if resume_from:
+            self._resume(resume_from)
+
+    def _get_device(self) -> torch.device:
+        device_str = self.config["hardware"]["device"]
+        if device_str == "cuda" and torch.cuda.is_available():
+            return torch.device("cuda", torch.cuda.current_device())
+        raise RuntimeError(f"mmseg_b200 Trainer needs hardware.device='cuda' on a B200 (got {device_str!r}, "
+                           f"cuda available: {torch.cuda.is_available()}); there is no CPU fallback")
+
+    def _setup_optimizer(self) -> torch.optim.Optimizer:
+        opt_config = self.config["training"]["optimizer"]
+        opt_name = opt_config["name"].lower()
+        params = self.model.parameters()
+        lr = opt_config["lr"]
+        weight_decay = opt_config.get("weight_decay", 0)
+        if opt_name == "adam":
+            return torch.optim.Adam(params, lr=lr, weight_decay=weight_decay)
+        elif opt_name == "adamw":
+            betas = tuple(opt_config.get("betas", [0.9, 0.999]))
+            return torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, betas=betas,
+                                     capturable=bool(self.config["hardware"].get("cuda_graph", False)))
+        elif opt_name == "sgd":
+            return torch.optim.SGD(params, lr=lr, momentum=opt_config.get("momentum", 0.9), weight_decay=weight_decay)
+        return torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay)
+
+    def _setup_scheduler(self):
+        sched_config = self.config["training"].get("scheduler", {})
+        sched_name = sched_config.get("name", "cosine").lower()
+        if sched_name == "cosine":
+            warmup = sched_config.get("warmup_epochs", 0)
+            return torch.optim.lr_scheduler.CosineAnnealingLR(self.optimizer, T_max=self.epochs - warmup,
+                                                              eta_min=sched_config.get("min_lr", 1e-6))
+        elif sched_name == "step":
+            return torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=sched_config.get("step_size", 30),
+                                                   gamma=sched_config.get("gamma", 0.1))
+        elif sched_name == "plateau":
+            return torch.optim.lr_scheduler.ReduceLROnPlateau(self.optimizer, mode="max",
+                                                              patience=sched_config.get("patience", 10),
+                                                              factor=sched_config.get("factor", 0.1))
+        return None
+
+    def _resume(self, checkpoint_path: str) -> None:
+        checkpoint = load_checkpoint(self.model, checkpoint_path)
+        if "optimizer_state_dict" in checkpoint:
+            self.optimizer.load_state_dict(checkpoint["optimizer_state_dict"])
+        if "epoch" in checkpoint:
+            self.current_epoch = checkpoint["epoch"]
+        if "best_metric" in checkpoint:
+            self.best_metric = checkpoint["best_metric"]
+        if self.logger:
+            self.logger.info(f"Resumed from epoch {self.current_epoch}")
+
+    # ------------------------------------------------------------------ reference trainer.py:166-220
+    def train(self) -> Dict[str, Any]:
+        early_stop_config = self.config["training"].get("early_stopping", {})
+        patience = early_stop_config.get("patience", 30)
+        no_improve_count = 0
+        for epoch in range(self.current_epoch, self.epochs):
+            self.current_epoch = epoch
+            train_loss = self._train_epoch()
+            self.history["train_loss"].append(train_loss)
+            val_loss, val_metrics = self._validate()
+            self.history["val_loss"].append(val_loss)
+            self.history["val_dice"].append(val_metrics.get("dice", 0))
+            if self.logger:
+                self.logger.info(f"Epoch [{epoch+1}/{self.epochs}] Train Loss: {train_loss:.4f} "
+                                 f"Val Loss: {val_loss:.4f} Val Dice: {val_metrics.get('dice', 0):.4f}")
+            if self.scheduler is not None:
+                if isinstance(self.scheduler, torch.optim.lr_scheduler.ReduceLROnPlateau):
+                    self.scheduler.step(val_metrics.get("dice", 0))
+                else:
+                    self.scheduler.step()
+            self._save_checkpoints(val_metrics)
+            if val_metrics.get("dice", 0) > self.best_metric:
+                self.best_metric = val_metrics.get("dice", 0)
+                no_improve_count = 0
+            else:
+                no_improve_count += 1
+            if early_stop_config.get("enabled", False) and no_improve_count >= patience:
+                if self.logger:
+                    self.logger.info(f"Early stopping at epoch {epoch+1}")
+                break
+        return self.history
+
+    def train_step(self, images: torch.Tensor, labels: torch.Tensor, step_optimizer: bool = True) -> torch.Tensor:
+        """One micro-batch of trainer.py:233-248: forward, loss / accumulation_steps, backward, (all-reduce,) step.
+        Returns the unscaled loss as a device tensor (no host sync)."""
+        from ... import train_engine
+        outputs = self.model(images)
+        loss = self.criterion(outputs, labels)
+        armed = step_optimizer and self.reducer is not None
+        if armed:   # only the stepping micro-batch exchanges (earlier ones accumulate locally)
+            self.reducer.arm()
+            train_engine.ACTIVE_REDUCER = self.reducer
+        try:
+            (loss / self.accumulation_steps).backward()
+        finally:
+            train_engine.ACTIVE_REDUCER = None
+        if armed:
+            self.reducer.finish()
+        if step_optimizer:
+            self.optimizer.step()
+            self.optimizer.zero_grad()
+        return loss.detach()
+
+    def graphed_train_step(self, images: torch.Tensor, labels: torch.Tensor):
+        """Whole-step CUDA graph (forward, loss, backward, gradient exchange, optimizer) for fixed-shape batches: the
+        ~400 kernel launches of a step are replayed with one host call.  Returns `replay(images, labels) -> loss`.
+        Needs accumulation_steps == 1 and an optimizer constructed with capturable=True."""
+        assert self.accumulation_steps == 1, "graph capture covers one optimizer step per batch"
+        static_x, static_y = images.clone(), labels.clone()
+        self.model.train()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):   # warm-up on a side stream, as torch.cuda.graph requires
+            for _ in range(2):
+                self.train_step(static_x, static_y)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss = self.train_step(static_x, static_y)
+
+        def replay(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+            static_x.copy_(x, non_blocking=True)
+            static_y.copy_(y, non_blocking=True)
+            graph.replay()
+            return static_loss
+        return replay
+
+    def _train_epoch(self) -> float:
+        self.model.train()
+        total_loss = 0.0
+        num_batches = len(self.train_loader)
+        self.optimizer.zero_grad()
+        for batch_idx, batch in enumerate(_progress(self.train_loader, f"Epoch {self.current_epoch+1}")):
+            images = batch["image"].to(self.device, non_blocking=True)
+            labels = batch["label"].to(self.device, non_blocking=True)
+            loss = self.train_step(images, labels, (batch_idx + 1) % self.accumulation_steps == 0)
+            total_loss += loss.item()   # the reference syncs every batch too (trainer.py:260)
+        return total_loss / num_batches
+
+    def _validate(self) -> Tuple[float, Dict[str, float]]:
+        self.model.eval()
+        total_loss = 0.0
+        num_batches = len(self.val_loader)
+        dice_metric = DiceMetric(num_classes=self.config["model"]["out_channels"])
+        with torch.no_grad():
+            for batch in _progress(self.val_loader, "Validation"):
+                images = batch["image"].to(self.device, non_blocking=True)
+                labels = batch["label"].to(self.device, non_blocking=True)
+                outputs = self.model(images)
+                loss = self.criterion(outputs, labels)
+                total_loss += loss.item()
+                dice_metric.update(torch.argmax(outputs, dim=1), labels)
+        return total_loss / num_batches, dice_metric.compute()
+
+    def evaluate(self) -> Dict[str, float]:
+        _, metrics = self._validate()
+        return metrics
+
+    # ------------------------------------------------------------------ reference trainer.py:303-395
+    def predict(self, input_path: Union[str, Path], output_path: Union[str, Path]) -> None:
+        import nibabel as nib   # NIfTI I/O stays on the host, as in the reference
+        import numpy as np
+        self.model.eval()
+        input_path, output_path = Path(input_path), Path(output_path)
+        output_path.mkdir(parents=True, exist_ok=True)
+        modalities = self.config["data"]["modalities"]
+        cases = set()
+        for mod in modalities:
+            mod_dir = input_path / mod.lower()
+            if mod_dir.exists():
+                for f in mod_dir.iterdir():
+                    if f.suffix in [".nii", ".gz"]:
+                        cases.add(f.stem.replace(".nii", ""))
+        with torch.no_grad():
+            for case_id in _progress(sorted(cases), "Inference"):
+                images, affine = [], None
+                for mod in modalities:
+                    mod_path = input_path / mod.lower() / f"{case_id}.nii.gz"
+                    if not mod_path.exists():
+                        mod_path = input_path / mod.lower() / f"{case_id}.nii"
+                    if mod_path.exists():
+                        nii = nib.load(str(mod_path))
+                        images.append(nii.get_fdata().astype(np.float32))
+                        if affine is None:
+                            affine = nii.affine
+                if len(images) != len(modalities):
+                    continue
+                pred = self.predict_array(np.stack(images, axis=0))
+                nib.save(nib.Nifti1Image(pred, affine), str(output_path / f"{case_id}_pred.nii.gz"))
+
+    def predict_array(self, image):
+        """[C, H, W, D] float32 numpy volume -> uint8 label map [H, W, D] (trainer.py:357-367 without the file I/O)."""
+        t = torch.from_numpy(image).unsqueeze(0).to(self.device)
+        output = self._sliding_window_inference(t)
+        return torch.argmax(output, dim=1).squeeze(0).to(torch.uint8).cpu().numpy()
+
+    def _sliding_window_inference(self, image: torch.Tensor) -> torch.Tensor:
+        sw = self.config["inference"]["sliding_window"]
+        return sliding_window_inference(image, roi_size=tuple(sw["roi_size"]),
+                                        sw_batch_size=self.config["inference"].get("batch_size", 4),
+                                        predictor=self.model, overlap=sw["overlap"], mode=sw.get("mode", "constant"))
+
+    def _save_checkpoints(self, metrics: Dict[str, float]) -> None:
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_rank() != 0:
+            return
+        ckpt_config = self.config["training"].get("checkpoint", {})
+        if ckpt_config.get("save_last", True):
+            save_checkpoint(self.model, self.optimizer, self.current_epoch, str(self.output_dir / "last.pth"),
+                            best_metric=self.best_metric, history=self.history)
+        if ckpt_config.get("save_best", True) and metrics.get("dice", 0) >= self.best_metric:
+            save_checkpoint(self.model, self.optimizer, self.current_epoch, str(self.output_dir / "best.pth"),
+                            best_metric=metrics.get("dice", 0), history=self.history)
+        save_every = ckpt_config.get("save_every", 0)
+        if save_every > 0 and (self.current_epoch + 1) % save_every == 0:
+            save_checkpoint(self.model, self.optimizer, self.current_epoch,
+                            str(self.output_dir / f"epoch_{self.current_epoch+1}.pth"), best_metric=self.best_metric)

@@ -196,8 +196,14 @@ class TrainEngine:
         K.conv3d(g, pw, a_cb, gs.t, _lib.OUT_BLOCKED_BF16, dst_cbt=gs.cbt, dst_cb_off=op["segs"][0][0] // 8)
 
     @torch.no_grad()
-    def backward(self, dlogits: Tensor) -> Dict[Tensor, Tensor]:
+    def backward(self, dlogits: Tensor, reducer=None) -> Dict[Tensor, Tensor]:
+        handed = set()
         for op in reversed(self.tape):
+            if reducer is not None:  # gradients produced by the previous op go out while this op's kernels are queued
+                for p, g in self.grads.items():
+                    if p not in handed and p.requires_grad:
+                        reducer.grad_ready(p, g)
+                        handed.add(p)
             kind = op["kind"]
             if kind == "cna":
                 self._bwd_cna(op)
@@ -207,6 +213,10 @@ class TrainEngine:
                 self._bwd_logits(op, dlogits)
             elif kind == "convb":
                 self._bwd_convb(op)
+        if reducer is not None:
+            for p, g in self.grads.items():
+                if p not in handed and p.requires_grad:
+                    reducer.grad_ready(p, g)
         return self.grads
 
     # ---------------------------------------------------------------- model forwards
@@ -293,6 +303,10 @@ class TrainEngine:
         return logits
 
 
+# set by Trainer.train_step on the stepping micro-batch of a data-parallel run (parallel.GradBucketReducer)
+ACTIVE_REDUCER = None
+
+
 class _ModelFunction(torch.autograd.Function):
     """logits = model(x) with the whole backward in the sm_100a kernels; parameters receive fp32 gradients."""
 
@@ -303,11 +317,13 @@ class _ModelFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dlogits: Tensor):
-        grads = ctx.engine.backward(dlogits)
+        red = ACTIVE_REDUCER if (ACTIVE_REDUCER is not None and ACTIVE_REDUCER.armed) else None
+        grads = ctx.engine.backward(dlogits, red)
         out = []
         for p in ctx.params:
             g = grads.get(p)
-            out.append(None if g is None or not p.requires_grad else g.to(p.dtype).view_as(p))
+            # armed data-parallel step: the reducer owns the gradient (bucket -> all-reduce -> .grad in finish())
+            out.append(None if (g is None or not p.requires_grad or red is not None) else g.to(p.dtype).view_as(p))
         return (None, None, None, *out)
 
 

@@ -383,60 +383,8 @@ def wgrad_case(cin, cout, shape, n_img=1, ks=3, segs=None, seed=0):
 
 
 def _ref_train_step(kind, sd, cfgkw, x, y, dtype=torch.float64):
-    """Oracle training step on the CPU: loss + parameter gradients by autograd over the oracle restatement."""
-    from oracle.models import unet3d_forward, dual_encoder_forward
-    from oracle.losses import dice_ce_loss
-    import torch.nn.functional as F2
-    params = {k: v.detach().to("cpu", dtype).requires_grad_(True) for k, v in sd.items()}
-    xx = x.detach().to("cpu", dtype)
-    # the oracle forwards detach their parameters; re-state them here with autograd enabled
-    def block(prefix, t):
-        for i in (1, 2):
-            t = F2.conv3d(t, params[f"{prefix}.conv{i}.weight"], params[f"{prefix}.conv{i}.bias"], padding=1)
-            t = F2.relu(F2.instance_norm(t, eps=1e-5))
-        return t
-    def up(prefix, t, skip):
-        t = F2.conv_transpose3d(t, params[f"{prefix}.up.weight"], params[f"{prefix}.up.bias"], stride=2)
-        return block(f"{prefix}.conv", torch.cat([t, skip], 1))
-    if kind == "unet":
-        L = cfgkw["L"]
-        t = block("init_conv", xx)
-        feats = [t]
-        for i in range(L - 1):
-            t = block(f"encoders.{i}.conv", F2.max_pool3d(t, 2))
-            feats.append(t)
-        dec = "decoders"
-    else:
-        L, M, fusion = cfgkw["L"], cfgkw["M"], cfgkw["fusion"]
-        allf = []
-        for m in range(M):
-            t = block(f"encoders.{m}.init_conv", xx[:, m:m + 1])
-            fl = [t]
-            for i in range(L - 1):
-                t = block(f"encoders.{m}.blocks.{i}.conv", F2.max_pool3d(t, 2))
-                fl.append(t)
-            allf.append(fl)
-        feats = []
-        for l in range(L):
-            lf = [allf[m][l] for m in range(M)]
-            if fusion == "concat":
-                feats.append(F2.conv3d(torch.cat(lf, 1), params[f"fusion_proj.{l}.weight"], params[f"fusion_proj.{l}.bias"]))
-            elif fusion == "add":
-                feats.append(sum(lf))
-            else:
-                feats.append(torch.stack(lf).mean(0))
-        t = feats[-1]
-        dec = "decoder"
-    for j, skip in enumerate(reversed(feats[:-1])):
-        t = up(f"{dec}.{j}", t, skip)
-    logits = F2.conv3d(t, params["out_conv.weight"], params["out_conv.bias"])
-    p = torch.softmax(logits, 1)
-    C = p.shape[1]
-    tt = F2.one_hot(y.cpu().long(), C).movedim(-1, 1).to(dtype)
-    I, U = (p * tt).flatten(2).sum(-1), p.flatten(2).sum(-1) + tt.flatten(2).sum(-1)
-    loss = 0.5 * (1 - (2 * I + 1) / (U + 1)).mean() + 0.5 * F2.cross_entropy(logits, y.cpu().long())
-    loss.backward()
-    return loss.item(), {k: v.grad for k, v in params.items()}, logits.detach()
+    from oracle.train import train_step
+    return train_step(kind, sd, cfgkw, x, y, dtype)
 
 
 def train_step_case(kind="unet", features=(16, 32, 64), S=16, n_img=2, fusion="late", M=2, seed=0):
