@@ -152,14 +152,14 @@ def run_reference(args):
     ms = sum(times) / len(times) * 1e3
     v = full_volume_equiv(ms / 1e3, 4)
     sample = "4 of the 600 windows per step (96x144x144 crop, sw_batch 4), extrapolated x150 to the full volume"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "sliding-window inference voxels/s (CT+PET)", "value": v, "unit": "voxels/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, 1),
         "cpu_baseline": {"value": v, "unit": "voxels/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def workload_config(args, world):
@@ -375,7 +375,7 @@ def run_ours(args):
         "step_tflops_per_gpu": step_tf, "step_frac_of_tensor_peak": step_tf / tf_peak,
         "cpu_baseline": cpu_baseline, "parity": parity, "train": train_res,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -519,13 +519,27 @@ def run_train(args):
     if rank == 0:
         res.update({"steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None,
                     "dtype": "bf16", "data": "synthetic", "clocks": sampler.summary()})
-        print(json.dumps(res), flush=True)
+        emit(res)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's original stdout; everything else (NCCL banners, library chatter)
+    was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -356,7 +356,8 @@ def predict_volume(model, image_host: Tensor, roi_size=(96, 96, 96), overlap: fl
     rank = dist.get_rank(group) if world > 1 else 0
     vol = inf.device_volume(image_host.shape, dev)
     z0, z1 = inf.input_range(image_host.shape[1:], world, rank)
-    vol[:, z0:z1].copy_(image_host[:, z0:z1], non_blocking=True)
+    for c in range(image_host.shape[0]):   # one contiguous slab per channel: plain async H2D copies, no host staging
+        vol[c, z0:z1].copy_(image_host[c, z0:z1], non_blocking=True)
     if world > 1:
         lab = inf.run_sharded(vol, group)
     else:
