@@ -30,6 +30,11 @@ struct ConvKParams {
   uint32_t w_off, a_off;  // smem offsets (from the 128-aligned base)
   int out_mode, out_channels, dst_cbt, dst_cb_off, dst_lo_off;
   int desc_swap;
+  int n_tiles;        // voxel tiles (all images) swept by the persistent CTAs of one N tile
+  int acc_bufs;       // 1 or 2 accumulator sets in TMEM (2: the epilogue of tile i overlaps the MMAs of tile i+1)
+  uint32_t buf_cols;  // TMEM columns between the two sets
+  long long* dbg;     // optional per-CTA cycle counters (flags bit1): MMA warp waits / epilogue waits
+  int dbg_flags;      // timing experiments only (results invalid): bit2 skip epilogue work, bit3 skip TMA after 1st ring pass
   const uint8_t* W;
   const float* bias;
   void* dst;
@@ -37,7 +42,7 @@ struct ConvKParams {
   int16_t a_cb[MMSEG_MAX_KCHUNKS];
 };
 
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 24;
 constexpr int kThreads = 192;
 constexpr int kMaxMT = 8;
 // smem header: barriers + tmem pointer + stats scratch
@@ -46,8 +51,8 @@ struct __align__(16) SmemHeader {
   uint64_t a_empty[kMaxStages];
   uint64_t w_full[2];
   uint64_t w_empty[2];
-  uint64_t acc_full;
-  uint64_t acc_zero;
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
   uint32_t tmem_ptr;
   uint32_t pad;
   float red[4][32];
@@ -117,16 +122,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  int t = blockIdx.x;
-  const int tx = t % p.tiles_x; t /= p.tiles_x;
-  const int ty = t % p.tiles_y; t /= p.tiles_y;
-  const int tz = t % p.tiles_z;
-  const int img = t / p.tiles_z;
-  const int tile_in_img = blockIdx.x - img * (p.tiles_x * p.tiles_y * p.tiles_z);
   const int nt = blockIdx.y;
-  const int x0 = tx * p.TX, y0 = ty * p.TY, z0 = tz * p.TZ;
   const int n_planes = p.TZ + 2 * p.halo;
-  const int tz_valid = min(p.TZ, p.Z - z0);
+  const int tiles_per_img = p.tiles_x * p.tiles_y * p.tiles_z;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -136,9 +134,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&hdr->w_full[s]), 1);
       mbar_init(smem_u32(&hdr->w_empty[s]), 1);
+      mbar_init(smem_u32(&hdr->acc_full[s]), 1);
+      mbar_init(smem_u32(&hdr->acc_empty[s]), 128);
     }
-    mbar_init(smem_u32(&hdr->acc_full), 1);
-    mbar_init(smem_u32(&hdr->acc_zero), 128);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmA);
@@ -151,80 +149,133 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_ptr;
 
+  // PERSISTENT: every role sweeps the same tile sequence blockIdx.x, blockIdx.x + gridDim.x, ...
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       int stage = 0;
-      uint32_t ph = 0;
-      for (int kc = 0; kc < p.n_kchunks; ++kc) {
-        const int ws = kc & 1;
-        const uint32_t wph = (kc >> 1) & 1;
-        const uint32_t wfull = smem_u32(&hdr->w_full[ws]);
-        mbar_wait(smem_u32(&hdr->w_empty[ws]), wph ^ 1);
-        mbar_arrive_expect_tx(wfull, p.w_bytes);
-        bulk_load_1d(w_smem + ws * p.w_bytes, p.W + ((size_t)nt * p.n_kchunks + kc) * p.w_bytes, p.w_bytes, wfull);
-        const int cb = img * p.src_cbt + p.a_cb[kc];
-        for (int pl = 0; pl < n_planes; ++pl) {
-          const int z = z0 - p.halo + pl;
-          if (z < 0 || z >= p.Z) continue;
-          const uint32_t afull = smem_u32(&hdr->a_full[stage]);
-          mbar_wait(smem_u32(&hdr->a_empty[stage]), ph ^ 1);
-          mbar_arrive_expect_tx(afull, p.a_tx_bytes);
-          tma_load_4d(a_smem + stage * p.stage_bytes, &tmA, afull, 2 * (x0 - p.halo), y0 - p.halo, z, cb);
-          if (++stage == p.stages) { stage = 0; ph ^= 1; }
+      uint32_t ph = 0, wc = 0, n_loaded = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int tz = t % p.tiles_z;
+        const int img = t / p.tiles_z;
+        const int x0 = tx * p.TX, y0 = ty * p.TY, z0 = tz * p.TZ;
+        for (int kc = 0; kc < p.n_kchunks; ++kc, ++wc) {
+          const uint32_t ws = wc & 1, wph = (wc >> 1) & 1;
+          const uint32_t wfull = smem_u32(&hdr->w_full[ws]);
+          mbar_wait(smem_u32(&hdr->w_empty[ws]), wph ^ 1);
+          mbar_arrive_expect_tx(wfull, p.w_bytes);
+          bulk_load_1d(w_smem + ws * p.w_bytes, p.W + ((size_t)nt * p.n_kchunks + kc) * p.w_bytes, p.w_bytes, wfull);
+          const int cb = img * p.src_cbt + p.a_cb[kc];
+          for (int pl = 0; pl < n_planes; ++pl) {
+            const int z = z0 - p.halo + pl;
+            if (z < 0 || z >= p.Z) continue;
+            const uint32_t afull = smem_u32(&hdr->a_full[stage]);
+            mbar_wait(smem_u32(&hdr->a_empty[stage]), ph ^ 1);
+            if ((p.dbg_flags & 8) && n_loaded >= (uint32_t)p.stages) {
+              mbar_arrive(afull);
+            } else {
+              mbar_arrive_expect_tx(afull, p.a_tx_bytes);
+              tma_load_4d(a_smem + stage * p.stage_bytes, &tmA, afull, 2 * (x0 - p.halo), y0 - p.halo, z, cb);
+            }
+            ++n_loaded;
+            if (++stage == p.stages) { stage = 0; ph ^= 1; }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (elect_one()) {
-      const uint32_t NT = (uint32_t)p.NT;
-      const uint32_t brows = (uint32_t)KT * NT;                   // weight rows per (tap9, k half): dz-descending x NT
-      const uint32_t a_hi = (128u >> 4) | (1u << 14);             // SBO = 128 B, descriptor version 1
-      const uint32_t b_hi = a_hi;
-      const uint32_t a_lbo = (p.plane_bytes >> 4) << 16;          // K halves one plane apart
-      const uint32_t b_lbo = ((brows * 16u) >> 4) << 16;
-      const uint32_t m_cols = (uint32_t)p.TZ * NT;                // TMEM columns between consecutive m tiles
-      const uint32_t PX = (uint32_t)p.PX;
-      int stage = 0;
-      uint32_t ph = 0;
-      mbar_wait(smem_u32(&hdr->acc_zero), 0);
+    // The whole warp runs the warp-uniform loops (so the descriptor arithmetic stays in the uniform datapath and the
+    // barrier waits are converged); ONE elected lane issues the MMAs and the commits.  The issue stream of that lane is
+    // the critical resource of this kernel (measured: every extra dependent instruction per plane shows up 1:1 in the
+    // kernel time), hence the per-tap offsets are precomputed and only two adds per MMA remain.
+    const bool leader = elect_one();
+    const uint32_t NT = (uint32_t)p.NT;
+    const uint32_t brows = (uint32_t)KT * NT;                   // weight rows per (tap9, k half): dz-descending x NT
+    const uint32_t a_hi = (128u >> 4) | (1u << 14);             // SBO = 128 B, descriptor version 1
+    const uint32_t b_hi = a_hi;
+    const uint32_t a_lbo = (p.plane_bytes >> 4) << 16;          // K halves one plane apart
+    const uint32_t b_lbo = ((brows * 16u) >> 4) << 16;
+    const uint32_t m_cols = (uint32_t)p.TZ * NT;                // TMEM columns between consecutive m tiles
+    uint32_t a_tap[KT * KT], b_tap[KT * KT];
+#pragma unroll
+    for (int i = 0; i < KT * KT; ++i) {
+      a_tap[i] = (uint32_t)((i / KT) * p.PX + (i % KT));         // row offset of tap (dy, dx), in 16-byte units
+      b_tap[i] = (uint32_t)i * 2u * brows;
+    }
+    int stage = 0;
+    uint32_t ph = 0, wc = 0, it = 0;
+    const long long t_begin = clock64();
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int tz = (tile / (p.tiles_x * p.tiles_y)) % p.tiles_z;
+      const int z0 = tz * p.TZ;
+      const int tz_valid = min(p.TZ, p.Z - z0);
+      const uint32_t as = p.acc_bufs == 2 ? (it & 1u) : 0u;
+      const uint32_t aph = p.acc_bufs == 2 ? ((it >> 1) & 1u) : (it & 1u);
+      mbar_wait(smem_u32(&hdr->acc_empty[as]), aph);   // accumulator set drained and re-zeroed by the epilogue
       tc_fence_after();
-      for (int kc = 0; kc < p.n_kchunks; ++kc) {
-        const int ws = kc & 1;
-        const uint32_t wph = (kc >> 1) & 1;
+      const uint32_t acc_base = tmem_base + as * p.buf_cols;
+      for (int kc = 0; kc < p.n_kchunks; ++kc, ++wc) {
+        const uint32_t ws = wc & 1, wph = (wc >> 1) & 1;
         mbar_wait(smem_u32(&hdr->w_full[ws]), wph);
         const uint32_t b_base = (((w_smem + ws * p.w_bytes) >> 4) & 0x3FFFu) | b_lbo;
-        for (int pl = 0; pl < n_planes; ++pl) {
-          const int z = z0 - p.halo + pl;
-          if (z < 0 || z >= p.Z) continue;
+        // planes are processed in PAIRS: both barrier waits and both descriptor set-ups overlap, shrinking the bubble the
+        // single issuing lane leaves in the tensor pipe between planes (measured: -10 % kernel time; groups of 4 and a
+        // generic group loop both compiled to slower issue code)
+        const int pl_lo = max(0, p.halo - z0);                       // first / one-past-last plane inside the volume
+        const int pl_hi = min(n_planes, p.Z - z0 + p.halo);
+        for (int pl = pl_lo; pl < pl_hi; pl += 2) {
+          const bool two = pl + 1 < pl_hi;
+          const int stage2 = (stage + 1 == p.stages) ? 0 : stage + 1;
+          const uint32_t ph2 = (stage + 1 == p.stages) ? (ph ^ 1u) : ph;
           mbar_wait(smem_u32(&hdr->a_full[stage]), ph);
+          if (two) mbar_wait(smem_u32(&hdr->a_full[stage2]), ph2);
           tc_fence_after();
-          const int dz_hi = min(KT - 1, pl);
-          const int dz_lo = max(0, pl - tz_valid + 1);
-          if (dz_hi >= dz_lo) {
-            const uint32_t nz = (uint32_t)(dz_hi - dz_lo + 1);
-            const uint32_t idesc = make_idesc_bf16(128, nz * NT);
-            const uint32_t d0 = tmem_base + (uint32_t)(pl - dz_hi) * NT;
-            const uint32_t a_base = (((a_smem + stage * p.stage_bytes) >> 4) & 0x3FFFu) | a_lbo;
-            const uint32_t b_pl = b_base + (uint32_t)(KT - 1 - dz_hi) * NT;   // first weight row of the dz range
+          uint32_t idesc[2], d0[2], at0[2], bt0[2], nzv[2];
 #pragma unroll
-            for (int dy = 0; dy < KT; ++dy) {
+          for (int h = 0; h < 2; ++h) {
+            const int q = pl + h;
+            const int dz_hi = min(KT - 1, q);
+            const int dz_lo = max(0, q - tz_valid + 1);
+            nzv[h] = (uint32_t)max(dz_hi - dz_lo + 1, 0);
+            idesc[h] = make_idesc_bf16(128, nzv[h] * NT);
+            d0[h] = acc_base + (uint32_t)(q - dz_hi) * NT;
+            at0[h] = (((a_smem + (h ? stage2 : stage) * p.stage_bytes) >> 4) & 0x3FFFu) | a_lbo;
+            bt0[h] = b_base + (uint32_t)(KT - 1 - dz_hi) * NT;   // first weight row of the dz range
+          }
+          const uint32_t abar = smem_u32(&hdr->a_empty[stage]), abar2 = smem_u32(&hdr->a_empty[stage2]);
+          if (leader) {
 #pragma unroll
-              for (int dx = 0; dx < KT; ++dx) {
-                const uint32_t a_t = a_base + (uint32_t)dy * PX + (uint32_t)dx;
-                const uint32_t b_t = b_pl + (uint32_t)(dy * KT + dx) * 2u * brows;
+            for (int h = 0; h < 2; ++h) {
+              if (h == 1 && !two) break;
+              if (nzv[h] > 0) {
 #pragma unroll
-                for (int m = 0; m < MT; ++m) umma_lohi(d0 + (uint32_t)m * m_cols, a_t + (uint32_t)m * 128u, a_hi, b_t, b_hi, idesc);
+                for (int i = 0; i < KT * KT; ++i) {
+#pragma unroll
+                  for (int m = 0; m < MT; ++m)
+                    umma_lohi(d0[h] + (uint32_t)m * m_cols, at0[h] + a_tap[i] + (uint32_t)m * 128u, a_hi, bt0[h] + b_tap[i], b_hi, idesc[h]);
+                }
               }
+              umma_commit(h ? abar2 : abar);
             }
           }
-          umma_commit(smem_u32(&hdr->a_empty[stage]));
-          if (++stage == p.stages) { stage = 0; ph ^= 1; }
+          __syncwarp();
+          const int adv = two ? 2 : 1;
+          for (int a = 0; a < adv; ++a)
+            if (++stage == p.stages) { stage = 0; ph ^= 1; }
         }
-        umma_commit(smem_u32(&hdr->w_empty[ws]));
+        if (leader) umma_commit(smem_u32(&hdr->w_empty[ws]));
+        __syncwarp();
       }
-      umma_commit(smem_u32(&hdr->acc_full));
+      if (leader) umma_commit(smem_u32(&hdr->acc_full[as]));
+      __syncwarp();
+    }
+    if (p.dbg && leader) {
+      long long* d = p.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8;
+      d[0] = clock64() - t_begin;
     }
   } else {
     // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
@@ -235,121 +286,148 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (uint32_t c = 0; c < p.tmem_cols; c += 16) tmem_st16_zero(lane_base + c);
     tmem_wait_st();
     tc_fence_before();
-    mbar_arrive(smem_u32(&hdr->acc_zero));
+    mbar_arrive(smem_u32(&hdr->acc_empty[0]));
+    if (p.acc_bufs == 2) mbar_arrive(smem_u32(&hdr->acc_empty[1]));
 
-    mbar_wait(smem_u32(&hdr->acc_full), 0);
-    tc_fence_after();
     const int n_base = nt * p.NT;
     const bool want_stats = p.stats != nullptr;
     const int n_cg = p.NT / 16;
-    for (int cg = 0; cg < n_cg; ++cg) {
-      const int n0 = n_base + cg * 16;
-      float bias_v[16];
+    uint32_t it = 0;
+    long long e_wait = 0;
+    const long long e_begin = clock64();
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      int t = tile;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; t /= p.tiles_y;
+      const int tz = t % p.tiles_z;
+      const int img = t / p.tiles_z;
+      const int tile_in_img = tile - img * tiles_per_img;
+      const int x0 = tx * p.TX, y0 = ty * p.TY, z0 = tz * p.TZ;
+      const int tz_valid = min(p.TZ, p.Z - z0);
+      const uint32_t as = p.acc_bufs == 2 ? (it & 1u) : 0u;
+      const uint32_t aph = p.acc_bufs == 2 ? ((it >> 1) & 1u) : (it & 1u);
+      const uint32_t acc_lane = lane_base + as * p.buf_cols;
+      const long long eq = clock64();
+      mbar_wait(smem_u32(&hdr->acc_full[as]), aph);
+      tc_fence_after();
+      e_wait += clock64() - eq;
+      for (int cg = 0; cg < ((p.dbg_flags & 4) ? 0 : n_cg); ++cg) {
+        const int n0 = n_base + cg * 16;
+        float bias_v[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) bias_v[i] = p.bias ? p.bias[n0 + i] : 0.f;
-      float s1[16], s2[16];
+        for (int i = 0; i < 16; ++i) bias_v[i] = p.bias ? p.bias[n0 + i] : 0.f;
+        float s1[16], s2[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-      for (int zo = 0; zo < tz_valid; ++zo) {
-        const int z = z0 + zo;
+        for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+        for (int zo = 0; zo < tz_valid; ++zo) {
+          const int z = z0 + zo;
 #pragma unroll 1
-        for (int m = 0; m < MT; ++m) {
-          const int L = m * 128 + q * 32 + lane;
-          const int yy = L / p.PX;
-          const int xx = L - yy * p.PX;
-          const int y = y0 + yy, x = x0 + xx;
-          const bool valid = (xx < p.TX) && (yy < p.TY) && (x < p.X) && (y < p.Y);
-          float v[16];
-          tmem_ld16(lane_base + (uint32_t)((m * p.TZ + zo) * p.NT + cg * 16), v);
+          for (int m = 0; m < MT; ++m) {
+            const int L = m * 128 + q * 32 + lane;
+            const int yy = L / p.PX;
+            const int xx = L - yy * p.PX;
+            const int y = y0 + yy, x = x0 + xx;
+            const bool valid = (xx < p.TX) && (yy < p.TY) && (x < p.X) && (y < p.Y);
+            float v[16];
+            const uint32_t taddr = acc_lane + (uint32_t)((m * p.TZ + zo) * p.NT + cg * 16);
+            tmem_ld16(taddr, v);
+            tmem_st16_zero(taddr);   // re-zero for the tile after next (every MMA accumulates)
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += bias_v[i];
-          if (valid) {
-            if (want_stats) {
+            for (int i = 0; i < 16; ++i) v[i] += bias_v[i];
+            if (valid) {
+              if (want_stats) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) { s1[i] += v[i]; s2[i] = fmaf(v[i], v[i], s2[i]); }
-            }
-            if (p.out_mode == MMSEG_OUT_BLOCKED_BF16) {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst);
-              const int blk = img * p.dst_cbt + p.dst_cb_off + (n0 >> 3);
-              *reinterpret_cast<uint4*>(o + blocked_off(blk, p.Z, p.Y, p.X, z, y, x)) = pack8_bf16(v);
-              *reinterpret_cast<uint4*>(o + blocked_off(blk + 1, p.Z, p.Y, p.X, z, y, x)) = pack8_bf16(v + 8);
-            } else if (p.out_mode == MMSEG_OUT_BLOCKED_F32) {
-              float* o = reinterpret_cast<float*>(p.dst);
-              const int blk = img * p.dst_cbt + p.dst_cb_off + (n0 >> 3);
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                float4* d = reinterpret_cast<float4*>(o + blocked_off(blk + h, p.Z, p.Y, p.X, z, y, x));
-                d[0] = make_float4(v[8 * h + 0], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3]);
-                d[1] = make_float4(v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]);
+                for (int i = 0; i < 16; ++i) { s1[i] += v[i]; s2[i] = fmaf(v[i], v[i], s2[i]); }
               }
-            } else if (p.out_mode == MMSEG_OUT_BLOCKED_BF16_HILO) {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst);
-              const int blk = img * p.dst_cbt + p.dst_cb_off + (n0 >> 3);
+              if (p.out_mode == MMSEG_OUT_BLOCKED_BF16) {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst);
+                const int blk = img * p.dst_cbt + p.dst_cb_off + (n0 >> 3);
+                *reinterpret_cast<uint4*>(o + blocked_off(blk, p.Z, p.Y, p.X, z, y, x)) = pack8_bf16(v);
+                *reinterpret_cast<uint4*>(o + blocked_off(blk + 1, p.Z, p.Y, p.X, z, y, x)) = pack8_bf16(v + 8);
+              } else if (p.out_mode == MMSEG_OUT_BLOCKED_F32) {
+                float* o = reinterpret_cast<float*>(p.dst);
+                const int blk = img * p.dst_cbt + p.dst_cb_off + (n0 >> 3);
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                uint4 hi, lo;
-                split8(v + 8 * h, hi, lo);
-                *reinterpret_cast<uint4*>(o + blocked_off(blk + h, p.Z, p.Y, p.X, z, y, x)) = hi;
-                *reinterpret_cast<uint4*>(o + blocked_off(blk + h + p.dst_lo_off, p.Z, p.Y, p.X, z, y, x)) = lo;
-              }
-            } else if (p.out_mode == MMSEG_OUT_CONVT_K2S2) {
-              // column n = tap * out_channels + co; tap = (a, b, c) offsets inside the 2x2x2 output cell
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst);
-              const int tap = n0 / p.out_channels;
-              const int co = n0 - tap * p.out_channels;
-              const int oz = 2 * z + (tap >> 2), oy = 2 * y + ((tap >> 1) & 1), ox = 2 * x + (tap & 1);
-              const int blk = img * p.dst_cbt + p.dst_cb_off + (co >> 3);
+                for (int h = 0; h < 2; ++h) {
+                  float4* d = reinterpret_cast<float4*>(o + blocked_off(blk + h, p.Z, p.Y, p.X, z, y, x));
+                  d[0] = make_float4(v[8 * h + 0], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3]);
+                  d[1] = make_float4(v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]);
+                }
+              } else if (p.out_mode == MMSEG_OUT_BLOCKED_BF16_HILO) {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst);
+                const int blk = img * p.dst_cbt + p.dst_cb_off + (n0 >> 3);
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const size_t off = blocked_off(blk + h, 2 * p.Z, 2 * p.Y, 2 * p.X, oz, oy, ox);
-                if (p.dst_lo_off > 0) {
+                for (int h = 0; h < 2; ++h) {
                   uint4 hi, lo;
                   split8(v + 8 * h, hi, lo);
-                  *reinterpret_cast<uint4*>(o + off) = hi;
-                  *reinterpret_cast<uint4*>(o + blocked_off(blk + h + p.dst_lo_off, 2 * p.Z, 2 * p.Y, 2 * p.X, oz, oy, ox)) = lo;
-                } else {
-                  *reinterpret_cast<uint4*>(o + off) = pack8_bf16(v + 8 * h);
+                  *reinterpret_cast<uint4*>(o + blocked_off(blk + h, p.Z, p.Y, p.X, z, y, x)) = hi;
+                  *reinterpret_cast<uint4*>(o + blocked_off(blk + h + p.dst_lo_off, p.Z, p.Y, p.X, z, y, x)) = lo;
                 }
-              }
-            } else {  // MMSEG_OUT_NCDHW_F32
-              float* o = reinterpret_cast<float*>(p.dst);
-              const size_t vox = ((size_t)z * p.Y + y) * p.X + x;
-              const size_t nvox = (size_t)p.Z * p.Y * p.X;
+              } else if (p.out_mode == MMSEG_OUT_CONVT_K2S2) {
+                // column n = tap * out_channels + co; tap = (a, b, c) offsets inside the 2x2x2 output cell
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst);
+                const int tap = n0 / p.out_channels;
+                const int co = n0 - tap * p.out_channels;
+                const int oz = 2 * z + (tap >> 2), oy = 2 * y + ((tap >> 1) & 1), ox = 2 * x + (tap & 1);
+                const int blk = img * p.dst_cbt + p.dst_cb_off + (co >> 3);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                if (n0 + i < p.out_channels) o[((size_t)img * p.out_channels + n0 + i) * nvox + vox] = v[i];
+                for (int h = 0; h < 2; ++h) {
+                  const size_t off = blocked_off(blk + h, 2 * p.Z, 2 * p.Y, 2 * p.X, oz, oy, ox);
+                  if (p.dst_lo_off > 0) {
+                    uint4 hi, lo;
+                    split8(v + 8 * h, hi, lo);
+                    *reinterpret_cast<uint4*>(o + off) = hi;
+                    *reinterpret_cast<uint4*>(o + blocked_off(blk + h + p.dst_lo_off, 2 * p.Z, 2 * p.Y, 2 * p.X, oz, oy, ox)) = lo;
+                  } else {
+                    *reinterpret_cast<uint4*>(o + off) = pack8_bf16(v + 8 * h);
+                  }
+                }
+              } else {  // MMSEG_OUT_NCDHW_F32
+                float* o = reinterpret_cast<float*>(p.dst);
+                const size_t vox = ((size_t)z * p.Y + y) * p.X + x;
+                const size_t nvox = (size_t)p.Z * p.Y * p.X;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  if (n0 + i < p.out_channels) o[((size_t)img * p.out_channels + n0 + i) * nvox + vox] = v[i];
+                }
               }
             }
           }
         }
-      }
-      if (want_stats) {
-        // lanes -> one value per lane pair of arrays; 4 warps -> smem -> fixed-order sum -> global partial
+        if (want_stats) {
+          // lanes -> one value per lane pair of arrays; 4 warps -> smem -> fixed-order sum -> global partial
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < 16; ++i) {
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
-            s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+            for (int o = 16; o > 0; o >>= 1) {
+              s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
+              s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+            }
+          }
+          named_bar_sync(1, 128);  // previous column group's readers are done with hdr->red
+          if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { hdr->red[ew][i] = s1[i]; hdr->red[ew][16 + i] = s2[i]; }
+          }
+          named_bar_sync(1, 128);
+          if (ew == 0) {
+            const float tot = hdr->red[0][lane] + hdr->red[1][lane] + hdr->red[2][lane] + hdr->red[3][lane];
+            const int ch = n0 + (lane & 15);
+            const int C = p.n_ntiles * p.NT;
+            float* dstp = p.stats + (((size_t)img * tiles_per_img + tile_in_img) * C + ch) * 2 + (lane >> 4);
+            *dstp = tot;
           }
         }
-        named_bar_sync(1, 128);  // previous column group's readers are done with hdr->red
-        if (lane == 0) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { hdr->red[ew][i] = s1[i]; hdr->red[ew][16 + i] = s2[i]; }
-        }
-        named_bar_sync(1, 128);
-        if (ew == 0) {
-          const float tot = hdr->red[0][lane] + hdr->red[1][lane] + hdr->red[2][lane] + hdr->red[3][lane];
-          const int ch = n0 + (lane & 15);
-          const int C = p.n_ntiles * p.NT;
-          const size_t tiles_per_img = (size_t)p.tiles_x * p.tiles_y * p.tiles_z;
-          float* dstp = p.stats + (((size_t)img * tiles_per_img + tile_in_img) * C + ch) * 2 + (lane >> 4);
-          *dstp = tot;
-        }
       }
+      // (planes zo >= tz_valid never receive MMAs and stay zero) hand the re-zeroed set back to the MMA warp
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&hdr->acc_empty[as]));
     }
-    tc_fence_before();
+    if (p.dbg && warp == 2 && lane == 0) {
+      long long* d = p.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8;
+      d[5] = clock64() - e_begin; d[6] = e_wait;
+    }
   }
   __syncthreads();
   if (warp == 2) {
@@ -417,8 +495,11 @@ static int plan_conv(const mmseg_conv_args* a, ConvPlan* out) {
   if (a->ksize == 3 && 3 * a->NT > 256) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: NT=%d > 80 with ksize 3 (folded MMA N = 3*NT <= 256)", a->NT);
   const int cols = n_acc * a->NT;
   if (cols > 512) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: %d TMEM columns > 512", cols);
+  // two accumulator sets when they fit: the epilogue of one tile overlaps the MMAs of the next
+  k.acc_bufs = (2 * cols <= 512) ? 2 : 1;
+  k.buf_cols = (uint32_t)cols;
   uint32_t tc = 32;
-  while ((int)tc < cols) tc <<= 1;
+  while ((int)tc < cols * k.acc_bufs) tc <<= 1;
   k.tmem_cols = tc;
   k.NT = a->NT; k.n_ntiles = a->n_ntiles; k.n_kchunks = a->n_kchunks; k.src_cbt = a->src_cbt; k.stages = a->stages;
   const int taps = a->ksize * a->ksize * a->ksize;
@@ -441,7 +522,11 @@ static int plan_conv(const mmseg_conv_args* a, ConvPlan* out) {
   k.out_mode = a->out_mode; k.out_channels = a->out_channels;
   k.dst_cbt = a->dst_cbt; k.dst_cb_off = a->dst_cb_off; k.dst_lo_off = a->dst_lo_off;
   k.desc_swap = a->flags & 1;
-  k.W = reinterpret_cast<const uint8_t*>(a->weights); k.bias = a->bias; k.dst = a->dst; k.stats = a->stats_partial;
+  k.dbg_flags = a->flags;
+  k.dbg = (a->flags & 2) ? reinterpret_cast<long long*>(a->stats_partial) : nullptr;  // debug: counters replace stats
+  k.n_tiles = k.tiles_x * k.tiles_y * k.tiles_z * a->n_img;
+  k.W = reinterpret_cast<const uint8_t*>(a->weights); k.bias = a->bias; k.dst = a->dst;
+  k.stats = (a->flags & 2) ? nullptr : a->stats_partial;
   for (int i = 0; i < MMSEG_MAX_KCHUNKS; ++i) k.a_cb[i] = i < a->n_kchunks ? a->a_cb[i] : 0;
   return MMSEG_OK;
 }
@@ -500,7 +585,16 @@ extern "C" int mmseg_conv3d_fwd(const mmseg_conv_args* a, void* stream) {
       }
     attr_set = true;
   }
-  dim3 grid((unsigned)(k.tiles_x * k.tiles_y * k.tiles_z * k.n_img), (unsigned)k.n_ntiles);
+  // persistent CTAs: about one per SM in total, each sweeping its share of the voxel tiles of one N tile
+  static int n_sms = 0;
+  if (n_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sms <= 0) n_sms = 148;
+  }
+  int ctas = n_sms / k.n_ntiles;
+  if (ctas < 1) ctas = 1;
+  if (ctas > k.n_tiles) ctas = k.n_tiles;
+  dim3 grid((unsigned)ctas, (unsigned)k.n_ntiles);
   table[a->ksize == 3 ? 1 : 0][k.mt - 1]<<<grid, kThreads, pl.smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tm, k);
   return check_launch("conv3d_tc_kernel");
 }

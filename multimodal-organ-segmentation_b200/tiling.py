@@ -43,7 +43,10 @@ class ConvTile:
 
 
 def tmem_cols(mt: int, TZ: int, NT: int) -> int:
+    """TMEM allocation: two accumulator sets when they fit in 512 columns (epilogue / MMA overlap), else one."""
     cols, tc = mt * TZ * NT, 32
+    if 2 * cols <= TMEM_COLS:
+        cols *= 2
     while tc < cols:
         tc <<= 1
     return tc
@@ -102,23 +105,18 @@ def plan_conv(X: int, Y: int, Z: int, n_img: int, n_kchunks: int, n_out: int, ks
             for TZ in range(1, min(Z, TMEM_COLS // (mt * NT)) + 1):
                 tc = tmem_cols(mt, TZ, NT)
                 sb, stages = None, 0
-                if tc <= 256:  # try to fit two CTAs per SM first
-                    for st in (4, 3, 2):
-                        s_ = smem_bytes(ksize, TX, TY, NT, st, TZ)
-                        if s_ is not None and s_ <= SMEM_HALF:
-                            sb, stages = s_, st
-                            break
-                if sb is None:
-                    for st in (4, 3, 2):
-                        s_ = smem_bytes(ksize, TX, TY, NT, st, TZ)
-                        if s_ is not None:
-                            sb, stages = s_, st
-                            break
+                # deep ring: one stage is a single small z-plane (a few KB) while a TMA round trip is ~1.5-2 us (a third
+                # of the activation bytes miss L2), so the bytes in flight — ring depth x stage size — bound the load
+                # rate (measured: 8 x 5.8 KB in flight = 20 GB/s per SM = load-bound).  Take the deepest ring that fits.
+                for st in (24, 20, 16, 12, 8, 6, 4, 3, 2):
+                    s_ = smem_bytes(ksize, TX, TY, NT, st, TZ)
+                    if s_ is not None:
+                        sb, stages = s_, st
+                        break
                 if sb is None:
                     continue
-                occ = 2 if (tc <= 256 and sb <= SMEM_HALF) else 1
                 tx_n, ty_n, tz_n = _cdiv(X, TX), _cdiv(Y, TY), _cdiv(Z, TZ)
-                n_cta = tx_n * ty_n * tz_n * n_img * n_ntiles
+                n_tiles = tx_n * ty_n * tz_n * n_img
                 if h:
                     per_tap = sum(_mma_cycles(NT * (min(2, pl) - max(0, pl - TZ + 1) + 1)) for pl in range(TZ + 2))
                     mma = n_kchunks * 9 * mt * (per_tap + 0.0)
@@ -126,14 +124,13 @@ def plan_conv(X: int, Y: int, Z: int, n_img: int, n_kchunks: int, n_out: int, ks
                     mma = n_kchunks * TZ * mt * _mma_cycles(NT)
                 planes = TZ + 2 * h
                 load = n_kchunks * (planes * 2 * PX * (TY + 2 * h) * 16 + ksize ** 3 * NT * 32) / L2_BYTES_PER_CLK_SM
-                epi = TZ * mt * (NT // 16) * epi_cost + 1000.0
-                fixed = 3000.0
-                if occ == 2:
-                    eff = max(mma, load, (max(mma, load) + epi + fixed) / 2.0)
-                else:
-                    eff = max(mma, load) + epi + fixed
-                waves = _cdiv(n_cta, NUM_SMS * occ)
-                est = waves * occ * eff
+                epi = TZ * mt * (NT // 16) * epi_cost + 500.0
+                # persistent CTAs (about one per SM in total): with two accumulator sets the epilogue of a tile hides
+                # behind the MMAs of the next one
+                double = 2 * mt * TZ * NT <= TMEM_COLS
+                per_tile = max(mma, load, epi) + 300.0 if double else max(mma, load) + epi
+                ctas = max(1, min(n_tiles, NUM_SMS // n_ntiles))
+                est = _cdiv(n_tiles, ctas) * per_tile + 4000.0
                 cand = (est, -TY * TZ * TX)
                 if best is None or cand < best[0]:
                     best = (cand, ConvTile(TX, TY, TZ, NT, n_ntiles, stages, mt, sb, tx_n * ty_n * tz_n, est))

@@ -26,6 +26,7 @@ struct Exp {
   uint32_t a_stride;  // bytes added to the A start address per MMA (cycled over 16 positions)
   uint32_t k_adv;     // bytes added per k-step inside a swizzle atom (0: none)
   int n_acc;          // distinct accumulators cycled
+  int commit_every;   // 0: one commit at the end; k: tcgen05.commit to a scratch mbarrier after every k MMAs
 };
 
 __device__ __forceinline__ uint64_t mkdesc(uint32_t addr, uint32_t lbo, uint32_t sbo, int layout) {
@@ -39,13 +40,16 @@ __device__ __forceinline__ uint64_t mkdesc(uint32_t addr, uint32_t lbo, uint32_t
   return d;
 }
 
+template <int CE, int WE>
 __global__ void __launch_bounds__(128, 1) bench(Exp e, int iters, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
+  __shared__ uint64_t scratch_bar;
+  __shared__ uint64_t done_bar;
   __shared__ uint32_t tmem_ptr;
   uint8_t* base = (uint8_t*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
   for (int i = threadIdx.x; i < 180 * 1024 / 4; i += blockDim.x) ((uint32_t*)base)[i] = 0x3c003c00u + (i * 2654435761u & 0x00ff00ffu);
-  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&done_bar), 1); asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&done_bar)) : "memory"); mbar_init(smem_u32(&scratch_bar), 1); mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   if (threadIdx.x < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -64,9 +68,18 @@ __global__ void __launch_bounds__(128, 1) bench(Exp e, int iters, long long* out
       for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const uint32_t aa = a0 + (uint32_t)(j & 15) * e.a_stride + (uint32_t)(j & 3) * e.k_adv;
-          const uint32_t bb = b0 + (uint32_t)(j & 3) * e.k_adv;
+          // a_stride == 1: the conv kernel's real tap pattern (PX = 26): A row offsets (dy*26+dx)*16 B inside a
+          // 5888-byte stage, B advancing by one tap block (2 k-halves x 96 rows x 16 B) per MMA
+          const int tap = j % 9;
+          const uint32_t aa = e.a_stride == 1 ? a0 + (uint32_t)((j / 9) * 5888) + (uint32_t)(((tap / 3) * 26 + tap % 3) * 16)
+                                              : a0 + (uint32_t)(j & 15) * e.a_stride + (uint32_t)(j & 3) * e.k_adv;
+          const uint32_t bb = e.a_stride == 1 ? b0 + (uint32_t)tap * e.k_adv : b0 + (uint32_t)(j & 3) * e.k_adv;
           umma(tm + (uint32_t)((j % e.n_acc) * e.N), mkdesc(aa, e.a_lbo, e.a_sbo, e.layout), mkdesc(bb, e.b_lbo, e.b_sbo, e.layout), idesc, 1u);
+          if (CE > 0 && ((j + 1) % (CE > 0 ? CE : 1)) == 0) commit(smem_u32(&scratch_bar));
+          if (WE > 0 && ((j + 1) % (WE > 0 ? WE : 1)) == 0) {
+            while (!mbar_try(smem_u32(&done_bar), 0)) {}
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
         }
       }
       commit(smem_u32(&bar));
@@ -84,39 +97,30 @@ __global__ void __launch_bounds__(128, 1) bench(Exp e, int iters, long long* out
 int main() {
   long long* d;
   cudaMalloc(&d, 148 * sizeof(long long));
-  cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int iters = 256;
   struct Named { const char* name; Exp e; } exps[] = {
-      // production layout: no swizzle, K halves one plane (17248 B) apart, rows 16 B apart, 8-row groups 128 B apart
-      {"none lbo=plane sbo=128 N=32", {0, 17248, 128, 512, 128, 32, 2048, 0, 14}},
-      {"none lbo=plane sbo=128 N=64", {0, 17248, 128, 1024, 128, 64, 2048, 0, 8}},
-      {"none lbo=plane sbo=128 N=128", {0, 17248, 128, 2048, 128, 128, 2048, 0, 4}},
-      {"none lbo=plane sbo=128 N=256", {0, 17248, 128, 4096, 128, 256, 2048, 0, 2}},
-      {"none lbo=plane(16384) sbo=128 N=32", {0, 16384, 128, 512, 128, 32, 2048, 0, 14}},
-      {"none lbo=plane(16384+64) sbo=128 N=32", {0, 16448, 128, 512, 128, 32, 2048, 0, 14}},
-      // canonical compact no-swizzle: K-adjacent core matrices contiguous (LBO 128), 8-row groups 256 B apart
-      {"none lbo=128 sbo=256 N=32", {0, 128, 256, 128, 256, 32, 4096, 0, 14}},
-      {"none lbo=128 sbo=256 N=64", {0, 128, 256, 128, 256, 64, 4096, 0, 8}},
-      {"none lbo=128 sbo=256 N=128", {0, 128, 256, 128, 256, 128, 4096, 0, 4}},
-      {"none lbo=128 sbo=256 N=256", {0, 128, 256, 128, 256, 256, 4096, 0, 2}},
-      // 128B swizzle, rows 128 B (64 bf16 of K), 8-row groups 1024 B apart; 4 k-steps of 32 B inside the atom
-      {"sw128 sbo=1024 N=32", {2, 16, 1024, 16, 1024, 32, 16384, 32, 14}},
-      {"sw128 sbo=1024 N=64", {2, 16, 1024, 16, 1024, 64, 16384, 32, 8}},
-      {"sw128 sbo=1024 N=128", {2, 16, 1024, 16, 1024, 128, 16384, 32, 4}},
-      {"sw128 sbo=1024 N=256", {2, 16, 1024, 16, 1024, 256, 16384, 32, 2}},
-      {"sw128 sbo=1024 N=32 row-shifted(+128B*j)", {2, 16, 1024, 16, 1024, 32, 128 * 3, 32, 14}},
-      {"sw128 sbo=1024 N=64 row-shifted(+128B*j)", {2, 16, 1024, 16, 1024, 64, 128 * 3, 32, 8}},
-      {"sw64 sbo=512 N=32", {4, 16, 512, 16, 512, 32, 8192, 32, 14}},
-      {"sw64 sbo=512 N=64", {4, 16, 512, 16, 512, 64, 8192, 32, 8}},
-      {"sw32 sbo=256 N=32", {6, 16, 256, 16, 256, 32, 4096, 0, 14}},
-      {"sw32 sbo=256 N=64", {6, 16, 256, 16, 256, 64, 4096, 0, 8}},
-      {"sw32 sbo=256 N=128", {6, 16, 256, 16, 256, 128, 4096, 0, 4}},
-      // same accumulator every time (dependent MMAs) vs cycling: does accumulator reuse serialize?
-      {"sw128 N=64 single accumulator", {2, 16, 1024, 16, 1024, 64, 16384, 32, 1}},
-      {"none lbo=plane N=32 single accumulator", {0, 17248, 128, 512, 128, 32, 2048, 0, 1}},
+      {"none N=96 reference (LBO 17248, stride 2064)", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 0}},
+      {"none N=96 A LBO=2912 (real plane), stride 2064", {0, 2912, 128, 1536, 128, 96, 2048 + 16, 0, 5, 0}},
+      {"none N=96 real tap pattern, A LBO=2912, B tap stride 3072", {0, 2912, 128, 1536, 128, 96, 1, 3072, 1, 0}},
+      {"none N=96 real tap pattern, A LBO=17248", {0, 17248, 128, 1536, 128, 96, 1, 3072, 1, 0}},
+      {"none N=96 real tap pattern, B fixed", {0, 2912, 128, 1536, 128, 96, 1, 0, 1, 0}},
+      {"none N=192 real tap pattern (NT=64: B LBO 3072, tap stride 6144)", {0, 2912, 128, 3072, 128, 192, 1, 6144, 1, 0}},
   };
   for (auto& x : exps) {
-    bench<<<148, 128, 200 * 1024>>>(x.e, iters, d);
+    switch (x.e.commit_every) {
+      case 0: bench<0, 0><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 8: bench<8, 0><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 88: bench<8, 8><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 108: bench<0, 8><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 104: bench<0, 4><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 116: bench<0, 16><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+    }
     cudaError_t err = cudaDeviceSynchronize();
     if (err != cudaSuccess) { printf("%-48s ERROR %s\n", x.name, cudaGetErrorString(err)); return 1; }
     long long h[148];
