@@ -222,6 +222,22 @@ int mmseg_dicece_bwd(const float* logits, const int64_t* target, int32_t B, int3
                      const float* sums, const float* grad_out /* [1] or NULL */, float* dlogits, void* stream);
 
 /*
+ * Fused multi-head cross attention over voxel tokens — the einsum / softmax / einsum of CrossAttentionFusion.forward
+ * (src/models/fusion/attention_fusion.py:144-155) as one flash-style tcgen05 kernel; the q/k/v/out 1x1 projections
+ * (:138-140,159) run through mmseg_conv3d_fwd and the residual + InstanceNorm3d (:162) through mmseg_add_stats +
+ * mmseg_instnorm_finalize + mmseg_instnorm_act_apply (slope 1 = no activation).
+ * q / kv / out: blocked token tensors [n_img * cbt][n_tok][8] bf16; head h owns channel blocks [cb0 + h*head_dim/8, ...).
+ * head_dim in {16, 32, 64, 128} (8 is run zero-padded to 16); scale = real_head_dim^-0.5.
+ */
+int mmseg_cross_attention_fwd(const void* q, int32_t q_cbt, int32_t q_cb0, const void* kv, int32_t kv_cbt,
+                              int32_t k_cb0, int32_t v_cb0, void* out, int32_t o_cbt, int32_t o_cb0, int32_t n_img,
+                              int32_t heads, int32_t head_dim, int64_t n_tok, float scale, void* stream);
+/* y (fp32 blocked [n_img*cb][voxels][8]) = a + b (blocked bf16) and per-chunk (sum, sum of squares) partials
+ * [n_img][n_chunks][cb*8][2] for mmseg_instnorm_finalize. */
+int mmseg_add_stats(const void* a, int32_t a_cbt, int32_t a_cb0, const void* b, int32_t b_cbt, int32_t b_cb0,
+                    int32_t n_img, int32_t cb, int64_t voxels, float* y, float* partial, int32_t n_chunks, void* stream);
+
+/*
  * K x K confusion counts (rows = target, columns = prediction) of two label maps in one pass; `counts` accumulates
  * (zero it first).  DiceMetric.update / ConfusionMatrix.update (src/trainer/metrics.py:42-65,184-196) read their
  * per-class intersections and unions off this matrix.  pred is int64 or uint8.
@@ -246,6 +262,9 @@ int mmseg_gate_mlp(const float* pooled, const float* w1, const float* b1, const 
 int mmseg_modality_combine(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_lo_off, int32_t M, int32_t cb,
                            int64_t voxels, const float* weights /* [n_img][M] or NULL */, float uniform_weight,
                            void* dst, int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, void* stream);
+/* dst[b, c] = max over modalities (LateFusion fusion_method="max", src/models/fusion/late_fusion.py:62-64); bf16 mode. */
+int mmseg_modality_max(const void* src, int32_t n_img, int32_t src_cbt, int32_t M, int32_t cb, int64_t voxels, void* dst,
+                       int32_t dst_cbt, int32_t dst_cb_off, void* stream);
 int mmseg_maxpool3d_2(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_cb_off, int32_t src_lo_off,
                       int32_t cb, int32_t Z, int32_t Y, int32_t X, void* dst, int32_t dst_cbt, int32_t dst_cb_off,
                       int32_t dst_lo_off, void* stream);

@@ -94,10 +94,14 @@ SYMBOLS = {
     "mmseg_swi_finalize": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp]),
     "mmseg_dicece_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _f32, _f32, _f32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "mmseg_dicece_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _f32, _f32, _f32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "mmseg_cross_attention_fwd": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i64,
+                                            _f32, _vp]),
+    "mmseg_add_stats": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _i32, _vp]),
     "mmseg_confusion_hist": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _vp]),
     "mmseg_channel_mean": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _vp]),
     "mmseg_gate_mlp": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mmseg_modality_combine": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _f32, _vp, _i32, _i32, _i32, _vp]),
+    "mmseg_modality_max": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i64, _vp, _i32, _i32, _vp]),
     "mmseg_maxpool3d_2": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
 }
 

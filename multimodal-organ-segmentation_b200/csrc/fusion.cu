@@ -156,6 +156,27 @@ modality_combine_kernel(const __nv_bfloat16* __restrict__ src, int src_cbt, int 
   }
 }
 
+// dst[b, c] = max_m src[b, m*cb + c]  (LateFusion 'max', src/models/fusion/late_fusion.py:62-64); grid (chunks, n_img*cb)
+__global__ void __launch_bounds__(256)
+modality_max_kernel(const __nv_bfloat16* __restrict__ src, int src_cbt, int M, int cb, size_t nvox,
+                    __nv_bfloat16* __restrict__ dst, int dst_cbt, int dst_cb_off) {
+  const int blk = blockIdx.y;
+  const int img = blk / cb, c = blk - img * cb;
+  const size_t dst_base = (size_t)(img * dst_cbt + dst_cb_off + c) * nvox * 8;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = -INFINITY;
+    for (int m = 0; m < M; ++m) {
+      float x[8];
+      ld8_bf16(src + (size_t)(img * src_cbt + m * cb + c) * nvox * 8 + v * 8, x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], x[i]);
+    }
+    st8_act(dst, dst_base + v * 8, 0, acc);
+  }
+}
+
 // MaxPool3d(2) on a blocked tensor (stand-alone DownBlock3D use); grid (chunks, n_img*cb)
 __global__ void __launch_bounds__(256)
 maxpool2_kernel(const __nv_bfloat16* __restrict__ src, int src_cbt, int src_cb_off, int src_lo_off, int cb, int Z, int Y,
@@ -241,6 +262,18 @@ extern "C" int mmseg_modality_combine(const void* src, int32_t n_img, int32_t sr
       reinterpret_cast<const __nv_bfloat16*>(src), src_cbt, src_lo_off, M, cb, (size_t)voxels, weights, uniform_weight,
       reinterpret_cast<__nv_bfloat16*>(dst), dst_cbt, dst_cb_off, dst_lo_off);
   return check_launch("modality_combine_kernel");
+}
+
+extern "C" int mmseg_modality_max(const void* src, int32_t n_img, int32_t src_cbt, int32_t M, int32_t cb, int64_t voxels,
+                                  void* dst, int32_t dst_cbt, int32_t dst_cb_off, void* stream) {
+  if (!src || !dst || n_img < 1 || M < 1 || cb < 1 || voxels < 1)
+    return fail(MMSEG_ERR_INVALID_ARG, "modality_max: bad arguments");
+  const int rows = n_img * cb;
+  dim3 grid(gx_for((size_t)voxels, rows), rows);
+  modality_max_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), src_cbt, M, cb, (size_t)voxels,
+      reinterpret_cast<__nv_bfloat16*>(dst), dst_cbt, dst_cb_off);
+  return check_launch("modality_max_kernel");
 }
 
 extern "C" int mmseg_maxpool3d_2(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_cb_off,

@@ -471,3 +471,33 @@ def confusion_hist(pred: Tensor, target: Tensor, num_classes: int, counts: Tenso
     pred, target = pred.contiguous(), target.contiguous().long()
     _call("mmseg_confusion_hist", _ptr(pred), 1 if pred.dtype == torch.uint8 else 0, _ptr(target), pred.numel(),
           num_classes, _ptr(counts), _stream())
+
+
+# --------------------------------------------------------------------------------------------- token cross attention
+def cross_attention(q: Blocked, q_c0: int, kv: Blocked, k_c0: int, v_c0: int, out: Blocked, o_c0: int, heads: int,
+                    head_dim: int, scale: float) -> None:
+    """out[:, head h] = softmax(Q_h K_h^T * scale) V_h over all voxels; head_dim is the (padded) per-head channel count."""
+    _lib.require_device()
+    assert not (q.split or kv.split or out.split), "the attention kernel runs in bf16 mode"
+    assert q.nvox == kv.nvox == out.nvox and q.n_img == kv.n_img == out.n_img
+    if PROFILE is not None:
+        _INFO[0] = {"flops": 4.0 * q.n_img * heads * q.nvox * q.nvox * head_dim,
+                    "layer": f"attn h{heads} hd{head_dim} N{q.nvox} img{q.n_img}"}
+    _call("mmseg_cross_attention_fwd", _ptr(q.t), q.cbt, q_c0 // 8, _ptr(kv.t), kv.cbt, k_c0 // 8, v_c0 // 8, _ptr(out.t),
+          out.cbt, o_c0 // 8, q.n_img, heads, head_dim, q.nvox, scale, _stream())
+
+
+def add_stats(a: Blocked, a_c0: int, b: Blocked, b_c0: int, channels: int):
+    """(y fp32 blocked [n, channels/8, Z, Y, X, 8] = a + b, stats partial, n_chunks) for the residual + InstanceNorm."""
+    n_chunks = max(1, min(64, (a.nvox + 4095) // 4096))
+    y = torch.empty((a.n_img, channels // 8, a.Z, a.Y, a.X, 8), dtype=torch.float32, device=a.t.device)
+    partial = torch.empty((a.n_img, n_chunks, channels, 2), dtype=torch.float32, device=a.t.device)
+    _call("mmseg_add_stats", _ptr(a.t), a.cbt, a_c0 // 8, _ptr(b.t), b.cbt, b_c0 // 8, a.n_img, channels // 8, a.nvox,
+          _ptr(y), _ptr(partial), n_chunks, _stream())
+    return y, partial, n_chunks
+
+
+def modality_max(src: Blocked, M: int, channels: int, dst: Blocked, dst_c0: int = 0) -> None:
+    assert not src.split and not dst.split
+    _call("mmseg_modality_max", _ptr(src.t), src.n_img, src.cbt, M, channels // 8, src.nvox, _ptr(dst.t), dst.cbt,
+          dst_c0 // 8, _stream())

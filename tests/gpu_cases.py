@@ -529,3 +529,86 @@ def dual_golden_case(name, mode="parity"):
     print(f"[{name} mode={mode}] max_abs={max_abs:.3e} rel_l2={rel_l2:.3e} label_agree={agree * 100:.4f}%", flush=True)
     assert len(feats["encoder_features"]) == len(cfg["data"]["modalities"]) and len(feats["fused_features"]) == 2
     assert max_abs <= 2e-2 and rel_l2 <= 1e-3 and agree >= 0.999
+
+
+# ------------------------------------------------------------------------------------------------ fusion modules
+def cross_attention_golden_case():
+    """CrossAttentionFusion / BidirectionalCrossAttention / AttentionFusion drop-ins vs the reference's own outputs."""
+    from mmseg_b200.src.models.fusion import CrossAttentionFusion, BidirectionalCrossAttention, AttentionFusion
+    g = _gold("cross_attention_fusion")
+    m = CrossAttentionFusion(32, g["num_heads"]).to(DEV).eval()
+    m.load_state_dict(g["state_dict"], strict=True)
+    with torch.no_grad():
+        got = m(g["q"].to(DEV), g["kv"].to(DEV)).cpu()
+    rel = ((got - g["y"]).norm() / g["y"].norm()).item()
+    print(f"[CrossAttentionFusion golden C=32 h=4 N=120] rel_l2={rel:.3e} max_abs={(got - g['y']).abs().max().item():.3e}", flush=True)
+    assert rel < 2e-2
+    g = _gold("bidirectional_cross_attention")
+    m = BidirectionalCrossAttention(32, 4).to(DEV).eval()
+    m.load_state_dict(g["state_dict"], strict=True)
+    with torch.no_grad():
+        got = m(g["f1"].to(DEV), g["f2"].to(DEV)).cpu()
+    rel = ((got - g["y"]).norm() / g["y"].norm()).item()
+    print(f"[BidirectionalCrossAttention golden] rel_l2={rel:.3e}", flush=True)
+    assert rel < 4e-2
+    g = _gold("attention_fusion")
+    m = AttentionFusion(16, 2).to(DEV).eval()
+    m.load_state_dict(g["state_dict"], strict=True)
+    with torch.no_grad():
+        got = m([f.to(DEV) for f in g["feats"]]).cpu()
+    rel = ((got - g["y"]).norm() / g["y"].norm()).item()
+    print(f"[AttentionFusion golden] rel_l2={rel:.3e}", flush=True)
+    assert rel < 1e-2
+
+
+def cross_attention_case(C=64, heads=4, shape=(8, 8, 8), n_img=2, seed=0):
+    """Fused attention path vs the oracle restatement (fp32) on fresh random parameters; several head dims / N."""
+    from mmseg_b200.src.models.fusion import CrossAttentionFusion
+    from oracle.models import cross_attention_fusion
+    torch.manual_seed(seed)
+    m = CrossAttentionFusion(C, heads).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    q, kv = torch.randn(n_img, C, *shape), torch.randn(n_img, C, *shape)
+    ref = cross_attention_fusion(sd, q, kv, heads)
+    m = m.to(DEV)
+    with torch.no_grad():
+        got = m(q.to(DEV), kv.to(DEV)).cpu()
+    rel = ((got - ref).norm() / ref.norm()).item()
+    print(f"[cross attention C={C} h={heads} hd={C // heads} N={shape[0] * shape[1] * shape[2]} n={n_img}] rel_l2={rel:.3e} "
+          f"max_abs={(got - ref).abs().max().item():.3e}", flush=True)
+    assert torch.isfinite(got).all() and rel < 2e-2
+
+
+def late_early_head_case():
+    from mmseg_b200.src.models.fusion import LateFusion, EarlyFusion
+    from mmseg_b200.src.models.heads import SegmentationHead
+    torch.manual_seed(0)
+    feats = [torch.randn(2, 16, 6, 6, 8) for _ in range(3)]
+    for method in ("add", "max", "mean", "concat"):
+        m = LateFusion(16, 3, method).eval()
+        if method == "concat":
+            ref = F.relu(F.instance_norm(F.conv3d(torch.cat(feats, 1), m.proj[0].weight, m.proj[0].bias), eps=1e-5))
+        elif method == "add":
+            ref = sum(feats)
+        elif method == "max":
+            ref = torch.stack(feats).max(0)[0]
+        else:
+            ref = torch.stack(feats).mean(0)
+        with torch.no_grad():
+            got = m.to(DEV)([f.to(DEV) for f in feats]).cpu()
+        rel = ((got - ref.detach()).norm() / ref.detach().norm()).item()
+        print(f"[LateFusion {method}] rel_l2={rel:.3e}", flush=True)
+        assert rel < 2e-2
+    e = EarlyFusion(2, 1, projection=True, out_channels=16).eval()
+    xs = [torch.randn(2, 1, 6, 6, 8) for _ in range(2)]
+    ref = F.relu(F.instance_norm(F.conv3d(torch.cat(xs, 1), e.proj[0].weight, e.proj[0].bias), eps=1e-5)).detach()
+    with torch.no_grad():
+        got = e.to(DEV)([x.to(DEV) for x in xs]).cpu()
+    assert ((got - ref).norm() / ref.norm()).item() < 2e-2
+    h = SegmentationHead(32, 8, kernel_size=3, activation="softmax").eval()
+    x = torch.randn(1, 32, 6, 8, 10)
+    ref = torch.softmax(F.conv3d(x, h.conv.weight, h.conv.bias, padding=1), 1).detach()
+    with torch.no_grad():
+        got = h.to(DEV)(x.to(DEV)).cpu()
+    assert (got - ref).abs().max().item() < 2e-2
+    print("[EarlyFusion / SegmentationHead] ok", flush=True)

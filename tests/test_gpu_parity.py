@@ -139,3 +139,19 @@ def test_training_step_vs_fp64_autograd(args, kw):
                                          ("dual_attention_4", "attention")])
 def test_dual_encoder_golden_from_reference(name, fusion):
     _c().dual_golden_case(name)
+
+
+# ------------------------------------------------------------------------------------------------ fusion modules / attention
+def test_attention_modules_golden_from_reference():
+    _c().cross_attention_golden_case()
+
+
+@pytest.mark.parametrize("kw", [dict(C=64, shape=(8, 8, 8)), dict(C=128, shape=(12, 12, 12), n_img=1),
+                                dict(C=256, shape=(6, 7, 9), n_img=1), dict(C=512, shape=(6, 6, 6), n_img=1),
+                                dict(C=64, heads=2, shape=(5, 5, 5))])
+def test_fused_cross_attention_vs_oracle(kw):
+    _c().cross_attention_case(**kw)
+
+
+def test_late_early_fusion_and_head():
+    _c().late_early_head_case()
