@@ -166,7 +166,8 @@ typedef struct {
   const void* gP;          /* blocked bf16 [n_img*gP_cbt][Z/2][Y/2][X/2][8] or NULL                           */
   float* partial;          /* [n_img*cb][n_chunks][16] fp32                                                   */
   void* dx;                /* blocked bf16 [n_img*dx_cbt][Z][Y][X][8] (apply only)                            */
-  const float* chan_scale; /* optional [n_img][cb*8] multiplier of gA (Dropout3d mask * 1/(1-p)) or NULL      */
+  const float* chan_scale; /* optional [n_img][cb*8] multiplier of gA (Dropout3d mask * 1/(1-p); gate weight) or NULL */
+  const float* chan_bias;  /* optional [n_img][cb*8] constant added to the activation gradient (gate: dpooled/N) or NULL */
   int32_t n_img, cb, Z, Y, X;
   int32_t gA_cbt, gA_cb_off, gP_cbt, gP_cb_off, dx_cbt, dx_cb_off;
   int32_t n_chunks;
@@ -174,6 +175,10 @@ typedef struct {
 } mmseg_norm_bwd_args;
 int mmseg_instnorm_act_bwd_reduce(const mmseg_norm_bwd_args* args, void* stream);
 int mmseg_instnorm_act_bwd_apply(const mmseg_norm_bwd_args* args, void* stream);
+/* out[b][m] = sum over channels and voxels of g[b, c, v] * x[b, m*C + c, v]: gradient w.r.t. the modality-gate weights
+ * of CrossModalAttention (src/models/backbones/dual_encoder.py:251-252).  partial: [n_img*M*cb][n_chunks] fp32. */
+int mmseg_modality_dot(const void* x, int32_t x_cbt, const void* g, int32_t g_cbt, int32_t g_cb_off, int32_t n_img,
+                       int32_t M, int32_t cb, int64_t voxels, float* partial, int32_t n_chunks, float* out, void* stream);
 /* Gradient of a ConvTranspose3d(k2,s2) output (blocked, high resolution, channel blocks [src_cb_off, +cb)) -> its k=1
  * GEMM view at low resolution with channel = tap*C + co: the dY operand of the transposed conv's dgrad / wgrad. */
 int mmseg_unshuffle_k2s2(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_cb_off, int32_t cb, int32_t Z,

@@ -50,7 +50,7 @@ class WgradArgs(C.Structure):
 class NormBwdArgs(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("mean_rstd", C.c_void_p), ("gA", C.c_void_p), ("gP", C.c_void_p),
-        ("partial", C.c_void_p), ("dx", C.c_void_p), ("chan_scale", C.c_void_p),
+        ("partial", C.c_void_p), ("dx", C.c_void_p), ("chan_scale", C.c_void_p), ("chan_bias", C.c_void_p),
         ("n_img", C.c_int32), ("cb", C.c_int32), ("Z", C.c_int32), ("Y", C.c_int32), ("X", C.c_int32),
         ("gA_cbt", C.c_int32), ("gA_cb_off", C.c_int32), ("gP_cbt", C.c_int32), ("gP_cb_off", C.c_int32),
         ("dx_cbt", C.c_int32), ("dx_cb_off", C.c_int32), ("n_chunks", C.c_int32),
@@ -85,6 +85,7 @@ SYMBOLS = {
     "mmseg_instnorm_act_apply": (C.c_int, [C.POINTER(NormArgs), _vp]),
     "mmseg_instnorm_act_bwd_reduce": (C.c_int, [C.POINTER(NormBwdArgs), _vp]),
     "mmseg_instnorm_act_bwd_apply": (C.c_int, [C.POINTER(NormBwdArgs), _vp]),
+    "mmseg_modality_dot": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _vp]),
     "mmseg_unshuffle_k2s2": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mmseg_pack_ncdhw": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "mmseg_unpack_ncdhw": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -20,6 +20,7 @@ struct NormBwdK {
   float* partial;
   __nv_bfloat16* dx;
   const float* chan_scale;
+  const float* chan_bias;
   int n_img, cb, Z, Y, X;
   int gA_cbt, gA_cb_off, gP_cbt, gP_cb_off, dx_cbt, dx_cb_off;
   int n_chunks;
@@ -52,6 +53,9 @@ __device__ __forceinline__ void for_each_item(const NormBwdK& k, int img, int c,
   float cs[8];  // gA_scale x optional per-(image, channel) scale (Dropout3d: 0 or 1/(1-p))
 #pragma unroll
   for (int i = 0; i < 8; ++i) cs[i] = k.gA_scale * (k.chan_scale ? k.chan_scale[(size_t)img * k.cb * 8 + c * 8 + i] : 1.f);
+  float cbias[8];  // optional per-(image, channel) constant added to the activation gradient (gate: d pooled / N)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) cbias[i] = k.chan_bias ? k.chan_bias[(size_t)img * k.cb * 8 + c * 8 + i] : 0.f;
   const size_t xbase = (size_t)(img * k.cb + c) * nvox * 8;
   const size_t abase = (size_t)(img * k.gA_cbt + k.gA_cb_off + c) * nvox * 8;
   if (!POOL) {
@@ -62,7 +66,7 @@ __device__ __forceinline__ void for_each_item(const NormBwdK& k, int img, int c,
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         x[i] = (x[i] - mean[i]) * rstd[i];
-        g[i] = g[i] * cs[i] * (x[i] > 0.f ? 1.f : k.slope);
+        g[i] = (g[i] * cs[i] + cbias[i]) * (x[i] > 0.f ? 1.f : k.slope);
       }
       f(v, x, g);
     }
@@ -102,10 +106,10 @@ __device__ __forceinline__ void for_each_item(const NormBwdK& k, int img, int c,
         if (k.gA) {
           ldb8(k.gA + abase + v * 8, g);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] *= cs[i];
+          for (int i = 0; i < 8; ++i) g[i] = g[i] * cs[i] + cbias[i];
         } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] = 0.f;
+          for (int i = 0; i < 8; ++i) g[i] = cbias[i];
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -210,6 +214,45 @@ unshuffle_k2s2_kernel(const __nv_bfloat16* __restrict__ src, int src_cbt, int sr
   }
 }
 
+// dw[b, m] = sum_{c, v} g[b, c, v] * x[b, m*C + c, v]: gradient of DualEncoder's modality gate weights
+// (dual_encoder.py:251-252).  grid (n_chunks, n_img*M*cb) -> partial[(img*M + m)*cb + c][chunk]
+__global__ void __launch_bounds__(256)
+modality_dot_partial_kernel(const __nv_bfloat16* __restrict__ x, int x_cbt, const __nv_bfloat16* __restrict__ g, int g_cbt,
+                            int g_cb_off, int M, int cb, size_t nvox, float* __restrict__ partial) {
+  const int blk = blockIdx.y;             // (img*M + m)*cb + c
+  const int c = blk % cb;
+  const int im = blk / cb;
+  const int m = im % M, img = im / M;
+  const size_t xbase = (size_t)(img * x_cbt + m * cb + c) * nvox * 8;
+  const size_t gbase = (size_t)(img * g_cbt + g_cb_off + c) * nvox * 8;
+  float s = 0.f;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    ldb8(x + xbase + v * 8, a);
+    ldb8(g + gbase + v * 8, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(a[i], b[i], s);
+  }
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partial[(size_t)blk * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+__global__ void modality_dot_final_kernel(const float* __restrict__ partial, int n, int per, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int k = 0; k < per; ++k) s += (double)partial[(size_t)i * per + k];
+  out[i] = (float)s;
+}
+
 static unsigned gxb(size_t items, int rows, int cap_per_row) {
   size_t want = ((size_t)num_sms() * 8 + rows - 1) / rows;
   size_t need = (items + 255) / 256;
@@ -230,7 +273,7 @@ static int fill_norm_bwd(const mmseg_norm_bwd_args* a, NormBwdK* k) {
   k->n_img = a->n_img; k->cb = a->cb; k->Z = a->Z; k->Y = a->Y; k->X = a->X;
   k->gA_cbt = a->gA_cbt; k->gA_cb_off = a->gA_cb_off; k->gP_cbt = a->gP_cbt; k->gP_cb_off = a->gP_cb_off;
   k->dx_cbt = a->dx_cbt; k->dx_cb_off = a->dx_cb_off; k->n_chunks = a->n_chunks;
-  k->gA_scale = a->gA_scale; k->slope = a->slope; k->chan_scale = a->chan_scale;
+  k->gA_scale = a->gA_scale; k->slope = a->slope; k->chan_scale = a->chan_scale; k->chan_bias = a->chan_bias;
   return MMSEG_OK;
 }
 
@@ -261,6 +304,23 @@ extern "C" int mmseg_instnorm_act_bwd_apply(const mmseg_norm_bwd_args* a, void* 
   if (a->gP) norm_bwd_apply_kernel<true><<<grid, 256, 0, st>>>(k);
   else norm_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(k);
   return check_launch("norm_bwd_apply_kernel");
+}
+
+extern "C" int mmseg_modality_dot(const void* x, int32_t x_cbt, const void* g, int32_t g_cbt, int32_t g_cb_off,
+                                  int32_t n_img, int32_t M, int32_t cb, int64_t voxels, float* partial, int32_t n_chunks,
+                                  float* out, void* stream) {
+  if (!x || !g || !partial || !out || n_img < 1 || M < 1 || cb < 1 || voxels < 1 || n_chunks < 1)
+    return fail(MMSEG_ERR_INVALID_ARG, "modality_dot: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid((unsigned)n_chunks, (unsigned)(n_img * M * cb));
+  modality_dot_partial_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), x_cbt,
+                                                    reinterpret_cast<const __nv_bfloat16*>(g), g_cbt, g_cb_off, M, cb,
+                                                    (size_t)voxels, partial);
+  int rc = check_launch("modality_dot_partial_kernel");
+  if (rc) return rc;
+  const int n = n_img * M;
+  modality_dot_final_kernel<<<(n + 63) / 64, 64, 0, st>>>(partial, n, cb * n_chunks, out);
+  return check_launch("modality_dot_final_kernel");
 }
 
 extern "C" int mmseg_unshuffle_k2s2(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_cb_off, int32_t cb,

@@ -25,7 +25,7 @@ def _ptr(t: Optional[Tensor]) -> C.c_void_p:
 
 
 # kernels launched by each C-ABI entry point (bench.py reports the count as `gpu_launches`)
-KERNELS_PER_CALL = {"mmseg_dicece_fwd": 2, "mmseg_channel_mean": 2}
+KERNELS_PER_CALL = {"mmseg_dicece_fwd": 2, "mmseg_channel_mean": 2, "mmseg_modality_dot": 2}
 LAUNCHES = [0]
 # when a list, every C-ABI call is bracketed by CUDA events on the current stream: (name, info, ev0, ev1)
 PROFILE: Optional[list] = None
@@ -432,7 +432,8 @@ def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt
 # --------------------------------------------------------------------------------------------- backward (elementwise)
 def instnorm_act_bwd(raw: Tensor, mean_rstd: Tensor, n_img: int, channels: int, Z: int, Y: int, X: int,
                      gA: Optional[Blocked], gA_c0: int, gA_scale: float, gP: Optional[Blocked], gP_c0: int,
-                     dx: Tensor, slope: float = 0.0, chan_scale: Optional[Tensor] = None) -> None:
+                     dx: Tensor, slope: float = 0.0, chan_scale: Optional[Tensor] = None,
+                     chan_bias: Optional[Tensor] = None) -> None:
     """dx (blocked bf16 [n_img, channels/8, Z, Y, X, 8]) = gradient of the raw conv output; see mmseg_norm_bwd_args."""
     a = _lib.NormBwdArgs()
     nvox = Z * Y * X
@@ -442,6 +443,7 @@ def instnorm_act_bwd(raw: Tensor, mean_rstd: Tensor, n_img: int, channels: int, 
     a.gA = gA.t.data_ptr() if gA is not None else None
     a.gP = gP.t.data_ptr() if gP is not None else None
     a.chan_scale = chan_scale.data_ptr() if chan_scale is not None else None
+    a.chan_bias = chan_bias.data_ptr() if chan_bias is not None else None
     a.n_img, a.cb, a.Z, a.Y, a.X = n_img, channels // 8, Z, Y, X
     if gA is not None:
         a.gA_cbt, a.gA_cb_off = gA.cbt, gA_c0 // 8
@@ -501,3 +503,14 @@ def modality_max(src: Blocked, M: int, channels: int, dst: Blocked, dst_c0: int 
     assert not src.split and not dst.split
     _call("mmseg_modality_max", _ptr(src.t), src.n_img, src.cbt, M, channels // 8, src.nvox, _ptr(dst.t), dst.cbt,
           dst_c0 // 8, _stream())
+
+
+def modality_dot(stack: Blocked, M: int, channels: int, g: Blocked, g_c0: int) -> Tensor:
+    """[n_img, M] fp32: sum over channels and voxels of g * stack[:, m] (gradient of the modality-gate weights)."""
+    cb = channels // 8
+    n_chunks = max(1, min(32, (stack.nvox + 8191) // 8192))
+    partial = torch.empty((stack.n_img * M * cb, n_chunks), dtype=torch.float32, device=stack.t.device)
+    out = torch.empty((stack.n_img, M), dtype=torch.float32, device=stack.t.device)
+    _call("mmseg_modality_dot", _ptr(stack.t), stack.cbt, _ptr(g.t), g.cbt, g_c0 // 8, stack.n_img, M, cb, stack.nvox,
+          _ptr(partial), n_chunks, _ptr(out), _stream())
+    return out

@@ -74,7 +74,7 @@ class TrainEngine:
     # ---------------------------------------------------------------- forward ops
     def conv_norm_act(self, name: str, src: Blocked, segs, conv, dst: Blocked, dst_c0: int = 0,
                       pooled: Optional[Blocked] = None, slope: float = 0.0, gspec=None, need_dgrad: bool = True,
-                      chan_scale: Optional[Tensor] = None):
+                      chan_scale: Optional[Tensor] = None, gate_ref=None):
         n, Z, Y, X = src.n_img, src.Z, src.Y, src.X
         cout = conv.weight.shape[0]
         pw = K.pack_conv_weight(conv.weight, None, False, [s[1] for s in segs], use_bias=False)
@@ -93,7 +93,7 @@ class TrainEngine:
         K.instnorm_act_apply(raw, False, mr_apply, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, 0)
         self.tape.append(dict(kind="cna", name=name, src=src, segs=list(segs), conv=conv, dst=dst, dst_c0=dst_c0,
                               pooled=pooled, slope=slope, raw=raw, mr=mr, gspec=gspec, need_dgrad=need_dgrad,
-                              chan_scale=chan_scale))
+                              chan_scale=chan_scale, gate_ref=gate_ref))
 
     def conv_transpose(self, name: str, src: Blocked, up, dst: Blocked):
         cin = up.weight.shape[0]
@@ -116,6 +116,31 @@ class TrainEngine:
         K.conv3d(src, pw, a_cb, dst.t, _lib.OUT_BLOCKED_BF16, dst_cbt=dst.cbt, dst_cb_off=dst_c0 // 8)
         self.tape.append(dict(kind="convb", name=name, src=src, segs=list(segs), conv=conv, dst=dst, dst_c0=dst_c0))
 
+    def gate_fuse(self, name: str, stack: Blocked, M: int, C: int, att, dst: Blocked, dst_c0: int) -> dict:
+        """CrossModalAttention forward (dual_encoder.py:243-254): channel means -> MLP + softmax -> weighted sum."""
+        pooled = K.channel_mean(stack, 0, M * C)
+        w = K.gate_mlp(pooled, att[2].weight, att[2].bias, att[4].weight, att[4].bias)
+        K.modality_combine(stack, M, C, dst, dst_c0, w)
+        op = dict(kind="gate", name=name, stack=stack, M=M, C=C, att=att, dst=dst, dst_c0=dst_c0, pooled=pooled, w=w)
+        self.tape.append(op)
+        return op
+
+    def _bwd_gate(self, op):
+        stack, M, C, att = op["stack"], op["M"], op["C"], op["att"]
+        g = self.grad_of(op["dst"])
+        dw = K.modality_dot(stack, M, C, g, op["dst_c0"])                     # [n, M]
+        # the gate MLP is a [n, M*C] -> [n, M] map (a few kFLOP): its backward runs through autograd on those tensors
+        with torch.enable_grad():
+            pooled = op["pooled"].detach().requires_grad_(True)
+            params = [att[2].weight, att[2].bias, att[4].weight, att[4].bias]
+            leaf = [p.detach().float().requires_grad_(True) for p in params]
+            h = torch.relu(torch.nn.functional.linear(pooled, leaf[0], leaf[1]))
+            w = torch.softmax(torch.nn.functional.linear(h, leaf[2], leaf[3]), dim=1)
+            grads = torch.autograd.grad(w, [pooled] + leaf, dw)
+        op["dpooled"] = grads[0]
+        for p, gp in zip(params, grads[1:]):
+            self.grads[p] = gp
+
     # ---------------------------------------------------------------- backward ops
     def _dgrad(self, dy: Blocked, dy_channels: int, w_as_conv: Tensor, dst: Blocked, dst_c0: int):
         """dst[:, dst_c0 : dst_c0 + Cout'] = conv(dy, w_as_conv) with the forward tcgen05 kernel."""
@@ -137,8 +162,13 @@ class TrainEngine:
             gA, gA_c0, scale = self.grad_of(dst), op["dst_c0"], 1.0
         gP = self.grad_of(op["pooled"]) if op["pooled"] is not None else None
         draw_t = self.saved("ws.draw", (n * cout * Z * Y * X,), torch.bfloat16).view(n, cout // 8, Z, Y, X, 8)
+        chan_scale, chan_bias = op["chan_scale"], None
+        if op.get("gate_ref") is not None:   # encoder output feeding a CrossModalAttention gate (modality i)
+            gate, i = op["gate_ref"]
+            chan_scale = gate["w"][:, i:i + 1].expand(n, cout).contiguous()
+            chan_bias = (gate["dpooled"][:, i * cout:(i + 1) * cout] / float(Z * Y * X)).contiguous()
         K.instnorm_act_bwd(op["raw"], op["mr"], n, cout, Z, Y, X, gA, gA_c0, scale, gP, 0, draw_t, op["slope"],
-                           op["chan_scale"])
+                           chan_scale, chan_bias)
         draw = _wrap(draw_t, n, cout, Z, Y, X)
         ks = conv.weight.shape[2]
         self.grads[conv.weight] = K.conv3d_wgrad(src, op["segs"], draw_t, cout // 8, 0, cout, ks, conv.weight.shape)
@@ -213,6 +243,8 @@ class TrainEngine:
                 self._bwd_logits(op, dlogits)
             elif kind == "convb":
                 self._bwd_convb(op)
+            elif kind == "gate":
+                self._bwd_gate(op)
         if reducer is not None:
             for p, g in self.grads.items():
                 if p not in handed and p.requires_grad:
@@ -254,12 +286,10 @@ class TrainEngine:
             decoders = m.decoders
         else:
             M, cpm = m.num_modalities, m.in_channels_per_modality
-            if m.fusion_type == "attention":
-                raise NotImplementedError("training through CrossModalAttention (fusion.type='attention') is not built yet: "
-                                          "the gate's backward kernel is scope row (f); use mean/add/concat fusion")
             for l in range(L):
                 A(f"stack{l}", M * f[l], l)
             scale = {"add": 1.0}.get(m.fusion_type, 1.0 / M)
+            enc_last: Dict[int, list] = {}
             for i in range(M):
                 a_in = A(f"m{i}.in", (cpm + 15) // 16 * 16, 0)
                 K.pack_ncdhw(x[:, i * cpm:(i + 1) * cpm].contiguous(), a_in)
@@ -272,17 +302,26 @@ class TrainEngine:
                         self.conv_norm_act(f"m{i}.e{l}.c1", self.A[f"m{i}.pool{l}"], [(0, f[l - 1])], blk.conv1,
                                            A(f"m{i}.e{l}.mid", f[l], l))
                     gspec = None
-                    if m.fusion_type != "concat":  # mean / add: the stack gradient is the fused gradient times `scale`
+                    if m.fusion_type == "attention":   # scale / bias tables come from the gate op's backward
+                        fd, fc0 = fused(l)
+                        gspec = (self.grad_of(fd), fc0, 1.0)
+                    elif m.fusion_type != "concat":  # mean / add: the stack gradient is the fused gradient times `scale`
                         fd, fc0 = fused(l)
                         gspec = (self.grad_of(fd), fc0, scale)
                     self.conv_norm_act(f"m{i}.e{l}.c2", self.A[f"m{i}.e{l}.mid"], [(0, f[l])], blk.conv2,
                                        self.A[f"stack{l}"], i * f[l],
                                        pooled=A(f"m{i}.pool{l + 1}", f[l], l + 1) if l < L - 1 else None, gspec=gspec)
+                    if m.fusion_type == "attention":
+                        enc_last.setdefault(l, []).append((self.tape[-1], i))
             for l in range(L):
                 dst, c0 = fused(l)
                 st = self.A[f"stack{l}"]
                 if m.fusion_type == "concat":
                     self.conv_bias(f"fuse{l}", st, [(i * f[l], f[l]) for i in range(M)], m.fusion_proj[l], dst, c0)
+                elif m.fusion_type == "attention":
+                    gate = self.gate_fuse(f"gate{l}", st, M, f[l], m.fusion_layers[l].attention, dst, c0)
+                    for op_i, i in enc_last[l]:
+                        op_i["gate_ref"] = (gate, i)
                 else:
                     K.modality_combine(st, M, f[l], dst, c0, None, scale)
             decoders = m.decoder

@@ -47,6 +47,11 @@ def train_step(kind, sd, cfgkw, x, y, dtype=torch.float64, dice_weight=0.5, ce_w
                 feats.append(F2.conv3d(torch.cat(lf, 1), params[f"fusion_proj.{l}.weight"], params[f"fusion_proj.{l}.bias"]))
             elif fusion == "add":
                 feats.append(sum(lf))
+            elif fusion == "attention":  # CrossModalAttention, dual_encoder.py:243-254
+                pooled = torch.cat([t_.mean(dim=(2, 3, 4)) for t_ in lf], dim=1)
+                hdn = F2.relu(F2.linear(pooled, params[f"fusion_layers.{l}.attention.2.weight"], params[f"fusion_layers.{l}.attention.2.bias"]))
+                wts = torch.softmax(F2.linear(hdn, params[f"fusion_layers.{l}.attention.4.weight"], params[f"fusion_layers.{l}.attention.4.bias"]), dim=1)
+                feats.append(sum(wts[:, m_].view(-1, 1, 1, 1, 1) * lf[m_] for m_ in range(M)))
             else:
                 feats.append(torch.stack(lf).mean(0))
         t = feats[-1]

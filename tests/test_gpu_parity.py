@@ -129,6 +129,8 @@ def test_conv_transpose_backward():
     (("dual", (16, 32), 16, 2), dict(fusion="late")),
     (("dual", (16, 32), 16, 1), dict(fusion="concat")),
     (("dual", (16, 32), 16, 1), dict(fusion="add", M=3)),
+    (("dual", (16, 32), 16, 2), dict(fusion="attention")),
+    (("dual", (16, 32), 16, 1), dict(fusion="attention", M=4)),
 ])
 def test_training_step_vs_fp64_autograd(args, kw):
     _c().train_step_case(*args, **kw)
