@@ -227,6 +227,20 @@ int mmseg_dicece_bwd(const float* logits, const int64_t* target, int32_t B, int3
                      const float* sums, const float* grad_out /* [1] or NULL */, float* dlogits, void* stream);
 
 /*
+ * TverskyLoss (src/trainer/losses.py:156-185, reduction mean) from the same one-pass per-class sums, and FocalLoss
+ * (losses.py:106-125, reduction mean, optional class weights alpha) as a one-pass kernel.  mmseg_focal runs the
+ * forward when dlogits is NULL (result[0] = loss) and the backward otherwise.
+ */
+int mmseg_tversky_fwd(const float* logits, const int64_t* target, int32_t B, int32_t C, int64_t N, float alpha, float beta,
+                      float smooth, float* partial /* [B][n_blocks][3*C+2] */, int32_t n_blocks, float* result /* [1] */,
+                      float* sums /* [B][3*C+2] */, void* stream);
+int mmseg_tversky_bwd(const float* logits, const int64_t* target, int32_t B, int32_t C, int64_t N, float alpha, float beta,
+                      float smooth, const float* sums, const float* grad_out, float* dlogits, void* stream);
+int mmseg_focal(const float* logits, const int64_t* target, int32_t B, int32_t C, int64_t N, const float* class_weights,
+                float gamma, float* partial /* [n_blocks] */, int32_t n_blocks, float* result, const float* grad_out,
+                float* dlogits, void* stream);
+
+/*
  * Fused multi-head cross attention over voxel tokens — the einsum / softmax / einsum of CrossAttentionFusion.forward
  * (src/models/fusion/attention_fusion.py:144-155) as one flash-style tcgen05 kernel; the q/k/v/out 1x1 projections
  * (:138-140,159) run through mmseg_conv3d_fwd and the residual + InstanceNorm3d (:162) through mmseg_add_stats +

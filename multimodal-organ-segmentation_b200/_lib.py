@@ -95,6 +95,9 @@ SYMBOLS = {
     "mmseg_swi_finalize": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp]),
     "mmseg_dicece_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _f32, _f32, _f32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "mmseg_dicece_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _f32, _f32, _f32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "mmseg_tversky_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _f32, _f32, _f32, _vp, _i32, _vp, _vp, _vp]),
+    "mmseg_tversky_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
+    "mmseg_focal": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _vp, _f32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "mmseg_cross_attention_fwd": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i64,
                                             _f32, _vp]),
     "mmseg_add_stats": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _i32, _vp]),

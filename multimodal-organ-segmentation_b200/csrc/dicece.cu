@@ -166,6 +166,135 @@ dicece_bwd_kernel(const float* __restrict__ logits, const long long* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------- Tversky / Focal
+// TverskyLoss (src/trainer/losses.py:156-185): tv = (TP + s) / (TP + a FP + b FN + s) per (batch, class) with TP = I,
+// FP = P - I, FN = T - I from the same one-pass sums as Dice; loss = mean(1 - tv).
+__global__ void tversky_final_kernel(const float* __restrict__ partial, int B, int C, int n_blocks, float alpha, float beta,
+                                     float smooth, float* __restrict__ result, float* __restrict__ sums) {
+  __shared__ double acc[3 * kMaxC + 2];
+  __shared__ double tot;
+  const int stride = 3 * C + 2;
+  if (threadIdx.x == 0) tot = 0.0;
+  __syncthreads();
+  for (int b = 0; b < B; ++b) {
+    if (threadIdx.x < stride) {
+      double s = 0.0;
+      for (int k = 0; k < n_blocks; ++k) s += (double)partial[((size_t)b * n_blocks + k) * stride + threadIdx.x];
+      acc[threadIdx.x] = s;
+      if (sums) sums[(size_t)b * stride + threadIdx.x] = (float)s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int c = 0; c < C; ++c) {
+        const double I = acc[c], P = acc[C + c], T = acc[2 * C + c];
+        tot += 1.0 - (I + smooth) / (I + alpha * (P - I) + beta * (T - I) + smooth);
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) result[0] = (float)(tot / (double)(B * C));
+}
+
+// dz_c = go * p_c (g_c - sum_k g_k p_k),  g_c = gB_c + t_c gA_c  with the Tversky coefficients
+template <int C>
+__global__ void __launch_bounds__(256)
+tversky_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target, size_t N, int B,
+                   const float* __restrict__ sums, float alpha, float beta, float smooth,
+                   const float* __restrict__ grad_out, float* __restrict__ dlogits) {
+  const int b = blockIdx.y;
+  const float go = grad_out ? grad_out[0] : 1.f;
+  const int stride = 3 * C + 2;
+  float gA[C], gB[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float I = sums[(size_t)b * stride + c], P = sums[(size_t)b * stride + C + c], T = sums[(size_t)b * stride + 2 * C + c];
+    const float D = I + alpha * (P - I) + beta * (T - I) + smooth;
+    const float k = 1.f / ((float)(B * C) * D * D);
+    gA[c] = -(D - (I + smooth) * (1.f - alpha - beta)) * k;   // multiplies t_c
+    gB[c] = (I + smooth) * alpha * k;
+  }
+  const float* lg = logits + (size_t)b * C * N;
+  float* dl = dlogits + (size_t)b * C * N;
+  const long long* tg = target + (size_t)b * N;
+  for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (size_t)gridDim.x * blockDim.x) {
+    float z[C];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { z[c] = lg[(size_t)c * N + n]; mx = fmaxf(mx, z[c]); }
+    const int t = (int)tg[n];
+    float se = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { z[c] = expf(z[c] - mx); se += z[c]; }
+    const float inv = 1.f / se;
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      z[c] *= inv;
+      dot = fmaf(gB[c] + (c == t ? gA[c] : 0.f), z[c], dot);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) dl[(size_t)c * N + n] = go * z[c] * (gB[c] + (c == t ? gA[c] : 0.f) - dot);
+  }
+}
+
+// FocalLoss (src/trainer/losses.py:106-125): ce = -w_t log p_t, pt = exp(-ce), loss = mean((1 - pt)^gamma ce).
+// grid (n_blocks, 1): per-block partial sums over ALL B*N voxels (logits [B][C][N]).
+template <int C, bool BWD>
+__global__ void __launch_bounds__(256)
+focal_kernel(const float* __restrict__ logits, const long long* __restrict__ target, int B, size_t N,
+             const float* __restrict__ cw, float gamma, const float* __restrict__ grad_out, float* __restrict__ partial,
+             float* __restrict__ dlogits) {
+  const size_t total = (size_t)B * N;
+  const float go = BWD ? (grad_out ? grad_out[0] : 1.f) / (float)total : 0.f;
+  float acc = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / N, n = i - b * N;
+    const float* lg = logits + b * C * N + n;
+    float z[C];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { z[c] = lg[(size_t)c * N]; mx = fmaxf(mx, z[c]); }
+    const int t = (int)target[i];
+    float se = 0.f, zt = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { if (c == t) zt = z[c] - mx; z[c] = expf(z[c] - mx); se += z[c]; }
+    const float w = cw ? cw[t] : 1.f;
+    const float ce = w * (logf(se) - zt);     // = -w log p_t
+    const float pt = expf(-ce);
+    const float om = 1.f - pt;
+    if (!BWD) {
+      acc += powf(om, gamma) * ce;
+    } else {
+      // d/dce [(1-pt)^g ce] = (1-pt)^g + g (1-pt)^(g-1) pt ce ;   dce/dz_c = w (p_c - [c == t])
+      const float dfdce = powf(om, gamma) + (om > 0.f ? gamma * powf(om, gamma - 1.f) * pt * ce : 0.f);
+      const float inv = 1.f / se;
+      float* dl = dlogits + b * C * N + n;
+#pragma unroll
+      for (int c = 0; c < C; ++c) dl[(size_t)c * N] = go * dfdce * w * (z[c] * inv - (c == t ? 1.f : 0.f));
+    }
+  }
+  if (!BWD) {
+    __shared__ float red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w2 = 0; w2 < 8; ++w2) t += red[w2];
+      partial[blockIdx.x] = t;
+    }
+  }
+}
+
+__global__ void focal_final_kernel(const float* __restrict__ partial, int n_blocks, double inv_total, float* __restrict__ result) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int k = 0; k < n_blocks; ++k) s += (double)partial[k];
+    result[0] = (float)(s * inv_total);
+  }
+}
+
 // One pass over (prediction, target) label maps -> K x K confusion counts (rows = target, columns = prediction).
 // Integer atomics only (associative -> deterministic).  DiceMetric / ConfusionMatrix (src/trainer/metrics.py:42-65,
 // 184-196 — the latter a per-voxel Python loop in the reference) are read off this matrix.
@@ -253,4 +382,73 @@ extern "C" int mmseg_dicece_bwd(const float* logits, const int64_t* target, int3
   }
 #undef MMSEG_BWD
   return check_launch("dicece_bwd_kernel");
+}
+
+extern "C" int mmseg_tversky_fwd(const float* logits, const int64_t* target, int32_t B, int32_t C, int64_t N, float alpha,
+                                 float beta, float smooth, float* partial, int32_t n_blocks, float* result, float* sums,
+                                 void* stream) {
+  if (!logits || !target || !partial || !result || !sums || B < 1 || N < 1 || n_blocks < 1 || n_blocks > 65535)
+    return fail(MMSEG_ERR_INVALID_ARG, "tversky_fwd: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(n_blocks, B);
+  const long long* tg = reinterpret_cast<const long long*>(target);
+  switch (C) {
+    case 2: dicece_partial_kernel<2><<<grid, 256, 0, st>>>(logits, tg, (size_t)N, nullptr, partial); break;
+    case 3: dicece_partial_kernel<3><<<grid, 256, 0, st>>>(logits, tg, (size_t)N, nullptr, partial); break;
+    case 4: dicece_partial_kernel<4><<<grid, 256, 0, st>>>(logits, tg, (size_t)N, nullptr, partial); break;
+    case 8: dicece_partial_kernel<8><<<grid, 256, 0, st>>>(logits, tg, (size_t)N, nullptr, partial); break;
+    case 16: dicece_partial_kernel<16><<<grid, 256, 0, st>>>(logits, tg, (size_t)N, nullptr, partial); break;
+    default: return fail(MMSEG_ERR_UNSUPPORTED, "tversky_fwd: C=%d (supported: 2,3,4,8,16)", C);
+  }
+  int rc = check_launch("dicece_partial_kernel");
+  if (rc != MMSEG_OK) return rc;
+  tversky_final_kernel<<<1, 64, 0, st>>>(partial, B, C, n_blocks, alpha, beta, smooth, result, sums);
+  return check_launch("tversky_final_kernel");
+}
+
+extern "C" int mmseg_tversky_bwd(const float* logits, const int64_t* target, int32_t B, int32_t C, int64_t N, float alpha,
+                                 float beta, float smooth, const float* sums, const float* grad_out, float* dlogits,
+                                 void* stream) {
+  if (!logits || !target || !sums || !dlogits || B < 1 || N < 1) return fail(MMSEG_ERR_INVALID_ARG, "tversky_bwd: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int64_t nb = (N + 255) / 256;
+  if (nb > 148 * 8) nb = 148 * 8;
+  dim3 grid((unsigned)nb, B);
+  const long long* tg = reinterpret_cast<const long long*>(target);
+#define MMSEG_TV(CC) tversky_bwd_kernel<CC><<<grid, 256, 0, st>>>(logits, tg, (size_t)N, B, sums, alpha, beta, smooth, grad_out, dlogits)
+  switch (C) {
+    case 2: MMSEG_TV(2); break;
+    case 3: MMSEG_TV(3); break;
+    case 4: MMSEG_TV(4); break;
+    case 8: MMSEG_TV(8); break;
+    case 16: MMSEG_TV(16); break;
+    default: return fail(MMSEG_ERR_UNSUPPORTED, "tversky_bwd: C=%d (supported: 2,3,4,8,16)", C);
+  }
+#undef MMSEG_TV
+  return check_launch("tversky_bwd_kernel");
+}
+
+extern "C" int mmseg_focal(const float* logits, const int64_t* target, int32_t B, int32_t C, int64_t N,
+                           const float* class_weights, float gamma, float* partial, int32_t n_blocks, float* result,
+                           const float* grad_out, float* dlogits, void* stream) {
+  if (!logits || !target || B < 1 || N < 1 || n_blocks < 1) return fail(MMSEG_ERR_INVALID_ARG, "focal: bad arguments");
+  if (!dlogits && (!partial || !result)) return fail(MMSEG_ERR_INVALID_ARG, "focal: forward needs partial and result");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long* tg = reinterpret_cast<const long long*>(target);
+#define MMSEG_FOCAL(CC)                                                                                                  \
+  if (dlogits) focal_kernel<CC, true><<<n_blocks, 256, 0, st>>>(logits, tg, B, (size_t)N, class_weights, gamma, grad_out, partial, dlogits); \
+  else focal_kernel<CC, false><<<n_blocks, 256, 0, st>>>(logits, tg, B, (size_t)N, class_weights, gamma, grad_out, partial, dlogits)
+  switch (C) {
+    case 2: MMSEG_FOCAL(2); break;
+    case 3: MMSEG_FOCAL(3); break;
+    case 4: MMSEG_FOCAL(4); break;
+    case 8: MMSEG_FOCAL(8); break;
+    case 16: MMSEG_FOCAL(16); break;
+    default: return fail(MMSEG_ERR_UNSUPPORTED, "focal: C=%d (supported: 2,3,4,8,16)", C);
+  }
+#undef MMSEG_FOCAL
+  int rc = check_launch("focal_kernel");
+  if (rc != MMSEG_OK || dlogits) return rc;
+  focal_final_kernel<<<1, 32, 0, st>>>(partial, n_blocks, 1.0 / ((double)B * (double)N), result);
+  return check_launch("focal_final_kernel");
 }

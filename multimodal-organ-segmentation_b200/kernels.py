@@ -25,7 +25,7 @@ def _ptr(t: Optional[Tensor]) -> C.c_void_p:
 
 
 # kernels launched by each C-ABI entry point (bench.py reports the count as `gpu_launches`)
-KERNELS_PER_CALL = {"mmseg_dicece_fwd": 2, "mmseg_channel_mean": 2, "mmseg_modality_dot": 2}
+KERNELS_PER_CALL = {"mmseg_dicece_fwd": 2, "mmseg_channel_mean": 2, "mmseg_modality_dot": 2, "mmseg_tversky_fwd": 2}
 LAUNCHES = [0]
 # when a list, every C-ABI call is bracketed by CUDA events on the current stream: (name, info, ev0, ev1)
 PROFILE: Optional[list] = None
@@ -514,3 +514,46 @@ def modality_dot(stack: Blocked, M: int, channels: int, g: Blocked, g_c0: int) -
     _call("mmseg_modality_dot", _ptr(stack.t), stack.cbt, _ptr(g.t), g.cbt, g_c0 // 8, stack.n_img, M, cb, stack.nvox,
           _ptr(partial), n_chunks, _ptr(out), _stream())
     return out
+
+
+# --------------------------------------------------------------------------------------------- Tversky / Focal losses
+def tversky_fwd(logits: Tensor, target: Tensor, alpha: float, beta: float, smooth: float):
+    _lib.require_device()
+    B, Cc = logits.shape[:2]
+    N = logits[0, 0].numel()
+    n_blocks = max(1, min(148 * 4, (N + 255) // 256))
+    partial = torch.empty((B, n_blocks, 3 * Cc + 2), dtype=torch.float32, device=logits.device)
+    result = torch.empty(1, dtype=torch.float32, device=logits.device)
+    sums = torch.empty((B, 3 * Cc + 2), dtype=torch.float32, device=logits.device)
+    _call("mmseg_tversky_fwd", _ptr(logits), _ptr(target), B, Cc, N, alpha, beta, smooth, _ptr(partial), n_blocks,
+          _ptr(result), _ptr(sums), _stream())
+    return result, sums
+
+
+def tversky_bwd(logits: Tensor, target: Tensor, sums: Tensor, grad_out: Tensor, alpha: float, beta: float, smooth: float) -> Tensor:
+    B, Cc = logits.shape[:2]
+    dl = torch.empty_like(logits)
+    go = grad_out.reshape(1).float().contiguous()
+    _call("mmseg_tversky_bwd", _ptr(logits), _ptr(target), B, Cc, logits[0, 0].numel(), alpha, beta, smooth, _ptr(sums),
+          _ptr(go), _ptr(dl), _stream())
+    return dl
+
+
+def focal(logits: Tensor, target: Tensor, class_weights: Optional[Tensor], gamma: float,
+          grad_out: Optional[Tensor] = None, backward: bool = False) -> Tensor:
+    """forward: returns the scalar loss tensor [1]; backward=True: returns dlogits."""
+    _lib.require_device()
+    B, Cc = logits.shape[:2]
+    N = logits[0, 0].numel()
+    n_blocks = max(1, min(148 * 8, (B * N + 255) // 256))
+    if backward:
+        dl = torch.empty_like(logits)
+        go = grad_out.reshape(1).float().contiguous()
+        _call("mmseg_focal", _ptr(logits), _ptr(target), B, Cc, N, _ptr(class_weights), gamma, None, n_blocks, None,
+              _ptr(go), _ptr(dl), _stream())
+        return dl
+    partial = torch.empty(n_blocks, dtype=torch.float32, device=logits.device)
+    result = torch.empty(1, dtype=torch.float32, device=logits.device)
+    _call("mmseg_focal", _ptr(logits), _ptr(target), B, Cc, N, _ptr(class_weights), gamma, _ptr(partial), n_blocks,
+          _ptr(result), None, None, _stream())
+    return result

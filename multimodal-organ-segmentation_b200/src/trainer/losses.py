@@ -54,26 +54,70 @@ class DiceLoss(nn.Module):
         return loss
 
 
+class _FocalFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, alpha, gamma):
+        if not pred.is_cuda:
+            raise RuntimeError("mmseg_b200 losses run on CUDA tensors only (no CPU fallback)")
+        logits = pred.detach().contiguous().float()
+        tgt = target.detach().contiguous().long()
+        cw = None if alpha is None else alpha.detach().to(pred.device, torch.float32).contiguous()
+        ctx.save_for_backward(logits, tgt)
+        ctx.cfg, ctx.in_dtype = (cw, gamma), pred.dtype
+        return K.focal(logits, tgt, cw, gamma)[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        logits, tgt = ctx.saved_tensors
+        cw, gamma = ctx.cfg
+        return K.focal(logits, tgt, cw, gamma, grad_out, backward=True).to(ctx.in_dtype), None, None, None
+
+
 class FocalLoss(nn.Module):
-    """reference losses.py:83-125 — scope row N4 (same traffic pattern as DiceCE); kernel not built yet."""
+    """reference losses.py:83-125 (one-pass sm_100a kernel; reduction mean | sum)."""
 
     def __init__(self, alpha: Optional[torch.Tensor] = None, gamma: float = 2.0, reduction: str = "mean"):
         super().__init__()
         self.alpha, self.gamma, self.reduction = alpha, gamma, reduction
 
     def forward(self, pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-        raise NotImplementedError("FocalLoss has no sm_100a kernel yet (SURVEY.md §8(f) N4); use dice_ce / dice / ce")
+        if self.reduction not in ("mean", "sum"):
+            raise NotImplementedError("FocalLoss(reduction='none') is not built in the sm_100a path (mean | sum)")
+        loss = _FocalFunction.apply(pred, target, self.alpha, self.gamma)
+        return loss * target.numel() if self.reduction == "sum" else loss
+
+
+class _TverskyFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, alpha, beta, smooth):
+        if not pred.is_cuda:
+            raise RuntimeError("mmseg_b200 losses run on CUDA tensors only (no CPU fallback)")
+        logits = pred.detach().contiguous().float()
+        tgt = target.detach().contiguous().long()
+        result, sums = K.tversky_fwd(logits, tgt, alpha, beta, smooth)
+        ctx.save_for_backward(logits, tgt, sums)
+        ctx.cfg, ctx.in_dtype = (alpha, beta, smooth), pred.dtype
+        return result[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        logits, tgt, sums = ctx.saved_tensors
+        a, b, s = ctx.cfg
+        return K.tversky_bwd(logits, tgt, sums, grad_out, a, b, s).to(ctx.in_dtype), None, None, None, None
 
 
 class TverskyLoss(nn.Module):
-    """reference losses.py:128-185 — scope row N4; kernel not built yet."""
+    """reference losses.py:128-185 (same one-pass sums as Dice: TP = I, FP = P - I, FN = T - I; reduction mean | sum)."""
 
-    def __init__(self, alpha: float = 0.5, beta: float = 0.5, smooth: float = 1.0):
+    def __init__(self, alpha: float = 0.5, beta: float = 0.5, smooth: float = 1.0, reduction: str = "mean"):
         super().__init__()
-        self.alpha, self.beta, self.smooth = alpha, beta, smooth
+        self.alpha, self.beta, self.smooth, self.reduction = alpha, beta, smooth, reduction
 
     def forward(self, pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-        raise NotImplementedError("TverskyLoss has no sm_100a kernel yet (SURVEY.md §8(f) N4); use dice_ce / dice / ce")
+        if self.reduction not in ("mean", "sum"):
+            raise NotImplementedError("TverskyLoss(reduction='none') is not built in the sm_100a path (mean | sum)")
+        loss = _TverskyFunction.apply(pred, target, self.alpha, self.beta, self.smooth)
+        return loss * (pred.shape[0] * pred.shape[1]) if self.reduction == "sum" else loss
 
 
 class _CrossEntropy(nn.Module):

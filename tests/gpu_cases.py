@@ -613,3 +613,24 @@ def late_early_head_case():
         got = h.to(DEV)(x.to(DEV)).cpu()
     assert (got - ref).abs().max().item() < 2e-2
     print("[EarlyFusion / SegmentationHead] ok", flush=True)
+
+
+def focal_tversky_golden_case():
+    """Focal / Tversky loss kernels (value + gradient) vs the reference's own outputs (tests/golden/losses.pt)."""
+    from mmseg_b200.src.trainer.losses import FocalLoss, TverskyLoss, get_loss
+    g = _gold("losses")
+    lg, tg, R = g["logits"].to(DEV), g["target"].to(DEV), g["results"]
+    for name, fn in (("focal", FocalLoss()), ("tversky", TverskyLoss(alpha=0.3, beta=0.7))):
+        z = lg.clone().requires_grad_(True)
+        v = fn(z, tg)
+        (v * 1.3).backward()
+        e = (z.grad.cpu() / 1.3 - R[name]["grad"]).abs().max().item() / R[name]["grad"].abs().max().item()
+        print(f"[{name} golden] {v.item():.7f} vs {R[name]['value']:.7f}; grad rel err {e:.2e}", flush=True)
+        assert abs(v.item() - R[name]["value"]) < 1e-5 * max(1.0, abs(R[name]["value"])) and e < 1e-4
+    cfg = {"training": {"loss": {"name": "tversky", "tversky_alpha": 0.3, "tversky_beta": 0.7}}}
+    assert abs(get_loss(cfg)(lg, tg).item() - R["tversky"]["value"]) < 1e-5
+    w = torch.tensor([0.5, 1, 1, 2, 1, 1, 3, 1.0])
+    from oracle.losses import focal_loss
+    want = focal_loss(g["logits"], g["target"], alpha=w, gamma=1.5).item()
+    got = FocalLoss(alpha=w, gamma=1.5)(lg, tg).item()
+    assert abs(got - want) < 1e-5 * max(1.0, abs(want)), (got, want)

@@ -157,3 +157,7 @@ def test_fused_cross_attention_vs_oracle(kw):
 
 def test_late_early_fusion_and_head():
     _c().late_early_head_case()
+
+
+def test_focal_tversky_golden():
+    _c().focal_tversky_golden_case()
