@@ -46,7 +46,8 @@ enum {
   MMSEG_OUT_BLOCKED_BF16 = 0,   /* blocked bf16 (raw conv output in fast mode, or activation)            */
   MMSEG_OUT_BLOCKED_F32 = 1,    /* blocked fp32 (raw conv output in parity mode)                          */
   MMSEG_OUT_BLOCKED_BF16_HILO = 2, /* blocked bf16 hi plane + lo plane at dst_lo_off (activation, parity) */
-  MMSEG_OUT_CONVT_K2S2 = 3,     /* ConvTranspose3d(k2,s2) pixel-shuffle scatter into a blocked bf16 buffer */
+  MMSEG_OUT_CONVT_K2S2 = 3,     /* ConvTranspose3d(k2,s2) pixel-shuffle scatter into a blocked bf16 buffer;
+                                   GEMM column n = (((dz*2+dy)*CB + cb)*2 + dx)*8 + j, CB = out_channels/8        */
   MMSEG_OUT_NCDHW_F32 = 4       /* [n_img][out_channels][Z][Y][X] fp32 (logits)                            */
 };
 

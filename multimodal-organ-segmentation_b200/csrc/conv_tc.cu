@@ -222,50 +222,60 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t ws = wc & 1, wph = (wc >> 1) & 1;
         mbar_wait(smem_u32(&hdr->w_full[ws]), wph);
         const uint32_t b_base = (((w_smem + ws * p.w_bytes) >> 4) & 0x3FFFu) | b_lbo;
-        // planes are processed in PAIRS: both barrier waits and both descriptor set-ups overlap, shrinking the bubble the
-        // single issuing lane leaves in the tensor pipe between planes (measured: -10 % kernel time; groups of 4 and a
-        // generic group loop both compiled to slower issue code)
+        // MEASURED (tools/micro/umma_bench.cu): a pause of the issuing lane between MMAs costs ~390 cycles + the pause
+        // itself (8 back-to-back N=96 MMAs = 448 cycles; with a 100-cycle pause after them = 934), so barrier waits and
+        // descriptor set-up between planes used to double the plane time.  Hence: ALL planes of a K chunk are waited
+        // for at once (lane i polls the barrier of plane i, so the ~100-cycle mbarrier latencies overlap), every
+        // per-plane descriptor is precomputed, and the elected lane then issues the whole group — up to 10 planes x
+        // 9 taps x MT MMAs, with the per-plane commits inline (free) — without a single pause.
+        constexpr int GP = 10;
+        const int gp = min(GP, p.stages);
         const int pl_lo = max(0, p.halo - z0);                       // first / one-past-last plane inside the volume
         const int pl_hi = min(n_planes, p.Z - z0 + p.halo);
-        for (int pl = pl_lo; pl < pl_hi; pl += 2) {
-          const bool two = pl + 1 < pl_hi;
-          const int stage2 = (stage + 1 == p.stages) ? 0 : stage + 1;
-          const uint32_t ph2 = (stage + 1 == p.stages) ? (ph ^ 1u) : ph;
-          mbar_wait(smem_u32(&hdr->a_full[stage]), ph);
-          if (two) mbar_wait(smem_u32(&hdr->a_full[stage2]), ph2);
+        for (int g0 = pl_lo; g0 < pl_hi; g0 += gp) {
+          const int cnt = min(gp, pl_hi - g0);
+          if (lane < cnt) {
+            int si = stage + lane;
+            uint32_t pp = ph;
+            if (si >= p.stages) { si -= p.stages; pp ^= 1u; }
+            mbar_wait(smem_u32(&hdr->a_full[si]), pp);
+          }
+          __syncwarp();
           tc_fence_after();
-          uint32_t idesc[2], d0[2], at0[2], bt0[2], nzv[2];
+          uint32_t idesc[GP], d0[GP], at0[GP], bt0[GP], nzv[GP], abar[GP];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int q = pl + h;
+          for (int h = 0; h < GP; ++h) {
+            int si = stage + h;
+            if (si >= p.stages) si -= p.stages;
+            const int q = g0 + h;
             const int dz_hi = min(KT - 1, q);
             const int dz_lo = max(0, q - tz_valid + 1);
             nzv[h] = (uint32_t)max(dz_hi - dz_lo + 1, 0);
             idesc[h] = make_idesc_bf16(128, nzv[h] * NT);
             d0[h] = acc_base + (uint32_t)(q - dz_hi) * NT;
-            at0[h] = (((a_smem + (h ? stage2 : stage) * p.stage_bytes) >> 4) & 0x3FFFu) | a_lbo;
+            at0[h] = (((a_smem + si * p.stage_bytes) >> 4) & 0x3FFFu) | a_lbo;
             bt0[h] = b_base + (uint32_t)(KT - 1 - dz_hi) * NT;   // first weight row of the dz range
+            abar[h] = smem_u32(&hdr->a_empty[si]);
           }
-          const uint32_t abar = smem_u32(&hdr->a_empty[stage]), abar2 = smem_u32(&hdr->a_empty[stage2]);
           if (leader) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              if (h == 1 && !two) break;
-              if (nzv[h] > 0) {
+            for (int h = 0; h < GP; ++h) {
+              if (h < cnt) {
+                if (nzv[h] > 0) {
 #pragma unroll
-                for (int i = 0; i < KT * KT; ++i) {
+                  for (int i = 0; i < KT * KT; ++i) {
 #pragma unroll
-                  for (int m = 0; m < MT; ++m)
-                    umma_lohi(d0[h] + (uint32_t)m * m_cols, at0[h] + a_tap[i] + (uint32_t)m * 128u, a_hi, bt0[h] + b_tap[i], b_hi, idesc[h]);
+                    for (int m = 0; m < MT; ++m)
+                      umma_lohi(d0[h] + (uint32_t)m * m_cols, at0[h] + a_tap[i] + (uint32_t)m * 128u, a_hi, bt0[h] + b_tap[i], b_hi, idesc[h]);
+                  }
                 }
+                umma_commit(abar[h]);
               }
-              umma_commit(h ? abar2 : abar);
             }
           }
           __syncwarp();
-          const int adv = two ? 2 : 1;
-          for (int a = 0; a < adv; ++a)
-            if (++stage == p.stages) { stage = 0; ph ^= 1; }
+          stage += cnt;
+          if (stage >= p.stages) { stage -= p.stages; ph ^= 1; }
         }
         if (leader) umma_commit(smem_u32(&hdr->w_empty[ws]));
         __syncwarp();
@@ -364,23 +374,27 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   *reinterpret_cast<uint4*>(o + blocked_off(blk + h + p.dst_lo_off, p.Z, p.Y, p.X, z, y, x)) = lo;
                 }
               } else if (p.out_mode == MMSEG_OUT_CONVT_K2S2) {
-                // column n = tap * out_channels + co; tap = (a, b, c) offsets inside the 2x2x2 output cell
+                // column n = (((dz*2 + dy)*CB + cb)*2 + dx)*8 + j: a thread's 16 columns are the SAME 8 output channels
+                // at the two x-adjacent output voxels -> one contiguous 32-byte store per thread, 1 KB per warp
                 __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst);
-                const int tap = n0 / p.out_channels;
-                const int co = n0 - tap * p.out_channels;
-                const int oz = 2 * z + (tap >> 2), oy = 2 * y + ((tap >> 1) & 1), ox = 2 * x + (tap & 1);
-                const int blk = img * p.dst_cbt + p.dst_cb_off + (co >> 3);
+                const int CB = p.out_channels >> 3;
+                const int g = n0 >> 4;
+                const int tzy = g / CB, cb = g - tzy * CB;
+                const int oz = 2 * z + (tzy >> 1), oy = 2 * y + (tzy & 1), ox = 2 * x;
+                const int blk = img * p.dst_cbt + p.dst_cb_off + cb;
+                const size_t off = blocked_off(blk, 2 * p.Z, 2 * p.Y, 2 * p.X, oz, oy, ox);
+                if (p.dst_lo_off > 0) {
+                  const size_t lo = blocked_off(blk + p.dst_lo_off, 2 * p.Z, 2 * p.Y, 2 * p.X, oz, oy, ox);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  const size_t off = blocked_off(blk + h, 2 * p.Z, 2 * p.Y, 2 * p.X, oz, oy, ox);
-                  if (p.dst_lo_off > 0) {
-                    uint4 hi, lo;
-                    split8(v + 8 * h, hi, lo);
-                    *reinterpret_cast<uint4*>(o + off) = hi;
-                    *reinterpret_cast<uint4*>(o + blocked_off(blk + h + p.dst_lo_off, 2 * p.Z, 2 * p.Y, 2 * p.X, oz, oy, ox)) = lo;
-                  } else {
-                    *reinterpret_cast<uint4*>(o + off) = pack8_bf16(v + 8 * h);
+                  for (int h = 0; h < 2; ++h) {
+                    uint4 hi, l;
+                    split8(v + 8 * h, hi, l);
+                    *reinterpret_cast<uint4*>(o + off + 8 * h) = hi;
+                    *reinterpret_cast<uint4*>(o + lo + 8 * h) = l;
                   }
+                } else {
+                  *reinterpret_cast<uint4*>(o + off) = pack8_bf16(v);
+                  *reinterpret_cast<uint4*>(o + off + 8) = pack8_bf16(v + 8);
                 }
               } else {  // MMSEG_OUT_NCDHW_F32
                 float* o = reinterpret_cast<float*>(p.dst);

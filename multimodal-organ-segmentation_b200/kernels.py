@@ -131,11 +131,12 @@ def pack_conv_weight(weight: Tensor, bias: Optional[Tensor], split: bool, seg_ch
     Split mode appends K chunks: [W_hi | W_hi | W_lo] to be paired with activations [A_hi | A_lo | A_hi].
     """
     w = weight.detach().float()
-    if transposed:  # [Cin, Cout, 2,2,2] -> GEMM columns n = tap*Cout + co
+    if transposed:  # [Cin, Cout, 2,2,2] -> GEMM columns n = (((dz*2+dy)*CB + cb)*2 + dx)*8 + j  (co = cb*8 + j)
         cin, cout = w.shape[0], w.shape[1]
         assert tuple(w.shape[2:]) == (2, 2, 2) and cout % 16 == 0
-        wm = w.reshape(cin, cout, 8).permute(2, 1, 0).reshape(8 * cout, cin, 1)
-        b = None if bias is None else bias.detach().float().repeat(8)
+        cbn = cout // 8
+        wm = w.reshape(cin, cbn, 8, 4, 2).permute(3, 1, 4, 2, 0).reshape(8 * cout, cin, 1)
+        b = None if bias is None else bias.detach().float().view(1, cbn, 1, 8).expand(4, cbn, 2, 8).reshape(-1)
         ksize, out_channels = 1, cout
     else:
         cout, cin = w.shape[0], w.shape[1]

@@ -73,12 +73,13 @@ def test_conv_transpose_as_gemm():
     stub = types.SimpleNamespace(lo_off=0)
     a_cb = K.a_chunk_table(stub, [0], [32], False)
     t = plan_conv(X, Y, Z, 1, pw.n_kchunks, pw.n_out, 1, pw.NT)
-    g = emulate_conv(to_blocked(x), 4, pw, a_cb, t, 1, Z, Y, X)  # [1, 8*16, Z, Y, X], column = tap*16 + co
+    g = emulate_conv(to_blocked(x), 4, pw, a_cb, t, 1, Z, Y, X)  # [1, 8*16, Z, Y, X]
     g = g + pw.bias.view(1, -1, 1, 1, 1)
     out = torch.zeros(1, 16, 2 * Z, 2 * Y, 2 * X)
-    for tap in range(8):
-        a, bb, c = tap >> 2, (tap >> 1) & 1, tap & 1
-        out[:, :, a::2, bb::2, c::2] = g[:, tap * 16:(tap + 1) * 16]
+    CB = 2  # 16 output channels = 2 blocks; column n = (((dz*2+dy)*CB + cb)*2 + dx)*8 + j
+    for n in range(128):
+        j, dx, cb, tzy = n % 8, (n // 8) % 2, (n // 16) % CB, n // (16 * CB)
+        out[:, cb * 8 + j, (tzy >> 1)::2, (tzy & 1)::2, dx::2] = g[:, n]
     ref = F.conv_transpose3d(x, w, b, stride=2)
     assert torch.allclose(out, ref, atol=1e-3, rtol=1e-4)
 

@@ -76,6 +76,10 @@ __global__ void __launch_bounds__(128, 1) bench(Exp e, int iters, long long* out
           const uint32_t bb = e.a_stride == 1 ? b0 + (uint32_t)tap * e.k_adv : b0 + (uint32_t)(j & 3) * e.k_adv;
           umma(tm + (uint32_t)((j % e.n_acc) * e.N), mkdesc(aa, e.a_lbo, e.a_sbo, e.layout), mkdesc(bb, e.b_lbo, e.b_sbo, e.layout), idesc, 1u);
           if (CE > 0 && ((j + 1) % (CE > 0 ? CE : 1)) == 0) commit(smem_u32(&scratch_bar));
+          if (WE < 0 && ((j + 1) % 8) == 0) {   // spin -WE cycles in the issuing thread every 8 MMAs
+            const long long ts = clock64();
+            while (clock64() - ts < (long long)(-WE)) {}
+          }
           if (WE > 0 && ((j + 1) % (WE > 0 ? WE : 1)) == 0) {
             while (!mbar_try(smem_u32(&done_bar), 0)) {}
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -103,14 +107,19 @@ int main() {
   cudaFuncSetAttribute(bench<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(bench<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(bench<0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<0, -100>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<0, -200>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<0, -300>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<0, -400>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int iters = 256;
   struct Named { const char* name; Exp e; } exps[] = {
-      {"none N=96 reference (LBO 17248, stride 2064)", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 0}},
-      {"none N=96 A LBO=2912 (real plane), stride 2064", {0, 2912, 128, 1536, 128, 96, 2048 + 16, 0, 5, 0}},
-      {"none N=96 real tap pattern, A LBO=2912, B tap stride 3072", {0, 2912, 128, 1536, 128, 96, 1, 3072, 1, 0}},
-      {"none N=96 real tap pattern, A LBO=17248", {0, 17248, 128, 1536, 128, 96, 1, 3072, 1, 0}},
-      {"none N=96 real tap pattern, B fixed", {0, 2912, 128, 1536, 128, 96, 1, 0, 1, 0}},
-      {"none N=192 real tap pattern (NT=64: B LBO 3072, tap stride 6144)", {0, 2912, 128, 3072, 128, 192, 1, 6144, 1, 0}},
+      // how deep is the MMA queue?  the issuing thread spins D cycles after every 8 MMAs (8 x 56 = 448 cycles of work):
+      // a deep queue hides the spin (56 cyc/MMA), a shallow one exposes it (56 + D/8)
+      {"none N=96 back to back", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 0}},
+      {"none N=96 spin 100 cycles every 8 MMAs", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 1100}},
+      {"none N=96 spin 200 cycles every 8 MMAs", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 1200}},
+      {"none N=96 spin 300 cycles every 8 MMAs", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 1300}},
+      {"none N=96 spin 400 cycles every 8 MMAs", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 1400}},
   };
   for (auto& x : exps) {
     switch (x.e.commit_every) {
@@ -120,6 +129,10 @@ int main() {
       case 108: bench<0, 8><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
       case 104: bench<0, 4><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
       case 116: bench<0, 16><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 1100: bench<0, -100><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 1200: bench<0, -200><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 1300: bench<0, -300><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 1400: bench<0, -400><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
     }
     cudaError_t err = cudaDeviceSynchronize();
     if (err != cudaSuccess) { printf("%-48s ERROR %s\n", x.name, cudaGetErrorString(err)); return 1; }
