@@ -45,7 +45,7 @@ torch.cuda.synchronize()
 prof, K.PROFILE = K.PROFILE, None
 agg = {}
 for name, info, a, b in prof:
-    key = name if not info or "layer" not in info else name + ":" + info["layer"].split(" ")[0]
+    key = name if not info or "layer" not in info else name + ":" + (info["layer"] if "wgrad" in info["layer"] or "conv3d_fwd" in name else info["layer"].split(" ")[0])
     d = agg.setdefault(key, [0.0, 0, 0.0])
     d[0] += a.elapsed_time(b); d[1] += 1
     if info: d[2] += info.get("flops", 0.0)
