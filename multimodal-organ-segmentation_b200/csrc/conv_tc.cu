@@ -30,6 +30,7 @@ struct ConvKParams {
   uint32_t w_off, a_off;  // smem offsets (from the 128-aligned base)
   int out_mode, out_channels, dst_cbt, dst_cb_off, dst_lo_off;
   int desc_swap;
+  int w_stages;       // weight ring slots (2 for k=3: 27 taps per chunk; 8 for k=1: tiny chunks, latency-bound)
   int n_tiles;        // voxel tiles (all images) swept by the persistent CTAs of one N tile
   int acc_bufs;       // 1 or 2 accumulator sets in TMEM (2: the epilogue of tile i overlaps the MMAs of tile i+1)
   uint32_t buf_cols;  // TMEM columns between the two sets
@@ -49,15 +50,15 @@ constexpr int kMaxMT = 8;
 struct __align__(16) SmemHeader {
   uint64_t a_full[kMaxStages];
   uint64_t a_empty[kMaxStages];
-  uint64_t w_full[2];
-  uint64_t w_empty[2];
+  uint64_t w_full[8];
+  uint64_t w_empty[8];
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_ptr;
   uint32_t pad;
   float red[4][32];
 };
-constexpr uint32_t kHeaderBytes = 1024;
+constexpr uint32_t kHeaderBytes = 2048;
 static_assert(sizeof(SmemHeader) <= kHeaderBytes, "header too large");
 
 __device__ __forceinline__ size_t blocked_off(int blk, int Z, int Y, int X, int z, int y, int x) {
@@ -131,9 +132,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(smem_u32(&hdr->a_full[s]), 1);
       mbar_init(smem_u32(&hdr->a_empty[s]), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 8; ++s) {
       mbar_init(smem_u32(&hdr->w_full[s]), 1);
       mbar_init(smem_u32(&hdr->w_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&hdr->acc_full[s]), 1);
       mbar_init(smem_u32(&hdr->acc_empty[s]), 128);
     }
@@ -163,7 +166,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int img = t / p.tiles_z;
         const int x0 = tx * p.TX, y0 = ty * p.TY, z0 = tz * p.TZ;
         for (int kc = 0; kc < p.n_kchunks; ++kc, ++wc) {
-          const uint32_t ws = wc & 1, wph = (wc >> 1) & 1;
+          const uint32_t ws = wc % (uint32_t)p.w_stages, wph = (wc / (uint32_t)p.w_stages) & 1;
           const uint32_t wfull = smem_u32(&hdr->w_full[ws]);
           mbar_wait(smem_u32(&hdr->w_empty[ws]), wph ^ 1);
           mbar_arrive_expect_tx(wfull, p.w_bytes);
@@ -219,7 +222,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t acc_base = tmem_base + as * p.buf_cols;
       for (int kc = 0; kc < p.n_kchunks; ++kc, ++wc) {
-        const uint32_t ws = wc & 1, wph = (wc >> 1) & 1;
+        const uint32_t ws = wc % (uint32_t)p.w_stages, wph = (wc / (uint32_t)p.w_stages) & 1;
         mbar_wait(smem_u32(&hdr->w_full[ws]), wph);
         const uint32_t b_base = (((w_smem + ws * p.w_bytes) >> 4) & 0x3FFFu) | b_lbo;
         // MEASURED (tools/micro/umma_bench.cu): a pause of the issuing lane between MMAs costs ~390 cycles + the pause
@@ -321,6 +324,21 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(smem_u32(&hdr->acc_full[as]), aph);
       tc_fence_after();
       e_wait += clock64() - eq;
+      // per-tile, per-M-tile voxel position of this thread's accumulator row (one integer division per tile, not per
+      // column group: the ConvTranspose / logits / first-layer launches are epilogue-INSTRUCTION-bound, ncu)
+      int py[MT], px[MT];
+      bool ok[MT];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const int L = m * 128 + q * 32 + lane;
+        const int yy = L / p.PX;
+        const int xx = L - yy * p.PX;
+        py[m] = y0 + yy;
+        px[m] = x0 + xx;
+        ok[m] = (xx < p.TX) && (yy < p.TY) && (px[m] < p.X) && (py[m] < p.Y);
+      }
+      const size_t plane = (size_t)p.Y * p.X;
+      const size_t nvox = plane * p.Z;
       for (int cg = 0; cg < ((p.dbg_flags & 4) ? 0 : n_cg); ++cg) {
         const int n0 = n_base + cg * 16;
         float bias_v[16];
@@ -329,80 +347,81 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float s1[16], s2[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+        // destination base of this column group (element offsets), hoisted out of the (zo, m) loops
+        size_t cbase = 0;
+        int ct_dz = 0, ct_dy = 0;
+        if (p.out_mode == MMSEG_OUT_CONVT_K2S2) {
+          const int CB = p.out_channels >> 3;
+          const int g = n0 >> 4;
+          const int tzy = g / CB, cb = g - tzy * CB;
+          ct_dz = tzy >> 1; ct_dy = tzy & 1;
+          cbase = (size_t)(img * p.dst_cbt + p.dst_cb_off + cb) * nvox * 8 * 8;   // output volume is 8x larger
+        } else if (p.out_mode == MMSEG_OUT_NCDHW_F32) {
+          cbase = ((size_t)img * p.out_channels + n0) * nvox;
+        } else {
+          cbase = (size_t)(img * p.dst_cbt + p.dst_cb_off + (n0 >> 3)) * nvox * 8;
+        }
+        const size_t lo_delta = (size_t)p.dst_lo_off * nvox * 8;
         for (int zo = 0; zo < tz_valid; ++zo) {
           const int z = z0 + zo;
-#pragma unroll 1
+          const size_t zoff = (size_t)z * plane;
+#pragma unroll
           for (int m = 0; m < MT; ++m) {
-            const int L = m * 128 + q * 32 + lane;
-            const int yy = L / p.PX;
-            const int xx = L - yy * p.PX;
-            const int y = y0 + yy, x = x0 + xx;
-            const bool valid = (xx < p.TX) && (yy < p.TY) && (x < p.X) && (y < p.Y);
             float v[16];
             const uint32_t taddr = acc_lane + (uint32_t)((m * p.TZ + zo) * p.NT + cg * 16);
             tmem_ld16(taddr, v);
             tmem_st16_zero(taddr);   // re-zero for the tile after next (every MMA accumulates)
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += bias_v[i];
-            if (valid) {
+            if (ok[m]) {
               if (want_stats) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) { s1[i] += v[i]; s2[i] = fmaf(v[i], v[i], s2[i]); }
               }
+              const size_t vox = zoff + (size_t)py[m] * p.X + px[m];
               if (p.out_mode == MMSEG_OUT_BLOCKED_BF16) {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst);
-                const int blk = img * p.dst_cbt + p.dst_cb_off + (n0 >> 3);
-                *reinterpret_cast<uint4*>(o + blocked_off(blk, p.Z, p.Y, p.X, z, y, x)) = pack8_bf16(v);
-                *reinterpret_cast<uint4*>(o + blocked_off(blk + 1, p.Z, p.Y, p.X, z, y, x)) = pack8_bf16(v + 8);
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst) + cbase + vox * 8;
+                *reinterpret_cast<uint4*>(o) = pack8_bf16(v);
+                *reinterpret_cast<uint4*>(o + nvox * 8) = pack8_bf16(v + 8);
               } else if (p.out_mode == MMSEG_OUT_BLOCKED_F32) {
-                float* o = reinterpret_cast<float*>(p.dst);
-                const int blk = img * p.dst_cbt + p.dst_cb_off + (n0 >> 3);
+                float* o = reinterpret_cast<float*>(p.dst) + cbase + vox * 8;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                  float4* d = reinterpret_cast<float4*>(o + blocked_off(blk + h, p.Z, p.Y, p.X, z, y, x));
+                  float4* d = reinterpret_cast<float4*>(o + h * nvox * 8);
                   d[0] = make_float4(v[8 * h + 0], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3]);
                   d[1] = make_float4(v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]);
                 }
               } else if (p.out_mode == MMSEG_OUT_BLOCKED_BF16_HILO) {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst);
-                const int blk = img * p.dst_cbt + p.dst_cb_off + (n0 >> 3);
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst) + cbase + vox * 8;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                   uint4 hi, lo;
                   split8(v + 8 * h, hi, lo);
-                  *reinterpret_cast<uint4*>(o + blocked_off(blk + h, p.Z, p.Y, p.X, z, y, x)) = hi;
-                  *reinterpret_cast<uint4*>(o + blocked_off(blk + h + p.dst_lo_off, p.Z, p.Y, p.X, z, y, x)) = lo;
+                  *reinterpret_cast<uint4*>(o + h * nvox * 8) = hi;
+                  *reinterpret_cast<uint4*>(o + h * nvox * 8 + lo_delta) = lo;
                 }
               } else if (p.out_mode == MMSEG_OUT_CONVT_K2S2) {
                 // column n = (((dz*2 + dy)*CB + cb)*2 + dx)*8 + j: a thread's 16 columns are the SAME 8 output channels
                 // at the two x-adjacent output voxels -> one contiguous 32-byte store per thread, 1 KB per warp
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst);
-                const int CB = p.out_channels >> 3;
-                const int g = n0 >> 4;
-                const int tzy = g / CB, cb = g - tzy * CB;
-                const int oz = 2 * z + (tzy >> 1), oy = 2 * y + (tzy & 1), ox = 2 * x;
-                const int blk = img * p.dst_cbt + p.dst_cb_off + cb;
-                const size_t off = blocked_off(blk, 2 * p.Z, 2 * p.Y, 2 * p.X, oz, oy, ox);
+                const size_t ovox = ((size_t)(2 * z + ct_dz) * (2 * p.Y) + (size_t)(2 * py[m] + ct_dy)) * (2 * p.X) + 2 * px[m];
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst) + cbase + ovox * 8;
                 if (p.dst_lo_off > 0) {
-                  const size_t lo = blocked_off(blk + p.dst_lo_off, 2 * p.Z, 2 * p.Y, 2 * p.X, oz, oy, ox);
 #pragma unroll
                   for (int h = 0; h < 2; ++h) {
                     uint4 hi, l;
                     split8(v + 8 * h, hi, l);
-                    *reinterpret_cast<uint4*>(o + off + 8 * h) = hi;
-                    *reinterpret_cast<uint4*>(o + lo + 8 * h) = l;
+                    *reinterpret_cast<uint4*>(o + 8 * h) = hi;
+                    *reinterpret_cast<uint4*>(o + 8 * h + lo_delta * 8) = l;
                   }
                 } else {
-                  *reinterpret_cast<uint4*>(o + off) = pack8_bf16(v);
-                  *reinterpret_cast<uint4*>(o + off + 8) = pack8_bf16(v + 8);
+                  *reinterpret_cast<uint4*>(o) = pack8_bf16(v);
+                  *reinterpret_cast<uint4*>(o + 8) = pack8_bf16(v + 8);
                 }
               } else {  // MMSEG_OUT_NCDHW_F32
-                float* o = reinterpret_cast<float*>(p.dst);
-                const size_t vox = ((size_t)z * p.Y + y) * p.X + x;
-                const size_t nvox = (size_t)p.Z * p.Y * p.X;
+                float* o = reinterpret_cast<float*>(p.dst) + cbase + vox;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                  if (n0 + i < p.out_channels) o[((size_t)img * p.out_channels + n0 + i) * nvox + vox] = v[i];
+                  if (n0 + i < p.out_channels) o[(size_t)i * nvox] = v[i];
                 }
               }
             }
@@ -525,7 +544,8 @@ static int plan_conv(const mmseg_conv_args* a, ConvPlan* out) {
   const uint32_t rows_needed = (uint32_t)(k.mt * 128 + 2 * k.halo * k.PX + 2 * k.halo);
   const uint32_t overflow = rows_needed * 16u > k.plane_bytes ? rows_needed * 16u - k.plane_bytes : 0u;
   k.w_off = kHeaderBytes;
-  k.a_off = k.w_off + 2 * round_up(k.w_bytes, 128);
+  k.w_stages = a->ksize == 1 ? 8 : 2;
+  k.a_off = k.w_off + k.w_stages * round_up(k.w_bytes, 128);
   uint32_t total = k.a_off + a->stages * k.stage_bytes + round_up(overflow, 128) + 128 /*align slack*/;
   // two CTAs share an SM only when both fit in TMEM: a CTA that needs more than 256 columns asks for more than half of
   // the shared memory so that a second CTA can never be co-resident and block in tcgen05.alloc

@@ -13,7 +13,7 @@ from typing import Optional
 NUM_SMS = 148
 SMEM_LIMIT = 227 * 1024
 SMEM_HALF = 113 * 1024       # two CTAs per SM
-HEADER_BYTES = 1024
+HEADER_BYTES = 2048
 TMEM_COLS = 512
 MAX_MT = 8
 MMA_MIN_CYCLES = 51.0
@@ -70,7 +70,8 @@ def smem_bytes(ksize: int, TX: int, TY: int, NT: int, stages: int, TZ: int = 1) 
     stage = _round_up(a_tx, 128)
     rows_needed = mt * 128 + 2 * h * PX + 2 * h
     overflow = max(rows_needed * 16 - plane, 0)
-    total = HEADER_BYTES + 2 * _round_up(w_bytes, 128) + stages * stage + _round_up(overflow, 128) + 128
+    w_stages = 8 if ksize == 1 else 2
+    total = HEADER_BYTES + w_stages * _round_up(w_bytes, 128) + stages * stage + _round_up(overflow, 128) + 128
     if tmem_cols(mt, TZ, NT) > 256 and total < 116 * 1024:
         total = 116 * 1024
     if total > SMEM_LIMIT or w_bytes >= (1 << 20) or a_tx >= (1 << 20):
