@@ -116,15 +116,27 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const NormK k) {
   const size_t src_base = (size_t)blk * nvox * 8;
   const size_t dst_base = (size_t)(img * k.dst_cbt + k.dst_cb_off + c) * nvox * 8;
   const size_t lo_delta = (size_t)k.dst_lo_off * nvox * 8;
-  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
-    float x[8];
-    load8<F32>(k.src, src_base + v * 8, x);
+  // four voxels per thread and iteration: four independent 16-byte loads in flight (HBM latency hiding)
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t v0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvox; v0 += 4 * stride) {
+    float x[4][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float y = (x[i] - mean[i]) * rstd[i];
-      x[i] = y > 0.f ? y : y * k.slope;
+    for (int u = 0; u < 4; ++u) {
+      const size_t v = v0 + u * stride;
+      if (v < nvox) load8<F32>(k.src, src_base + v * 8, x[u]);
     }
-    store_act8(k.dst, dst_base + v * 8, lo_delta, x);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t v = v0 + u * stride;
+      if (v < nvox) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float y = (x[u][i] - mean[i]) * rstd[i];
+          x[u][i] = y > 0.f ? y : y * k.slope;
+        }
+        store_act8(k.dst, dst_base + v * 8, lo_delta, x[u]);
+      }
+    }
   }
 }
 
