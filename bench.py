@@ -324,8 +324,14 @@ def run_ours(args):
                 f"tile {i['tile']} ctas {i['ctas']}")
         else:
             log(f"  norm {layer:31s} {L['ms'] / L['n']:7.3f} ms  {i['bytes'] / (L['ms'] / L['n'] * 1e-3) / 1e9:7.0f} GB/s")
+    traffic = None   # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture
+    tj = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    if os.path.exists(tj):
+        traffic = json.load(open(tj)).get("dram_bytes_per_launch_avg")
     roofline = {"bound": "tensor", "kernel": "conv3d_tc_kernel", "achieved": conv_tf, "peak": tf_peak, "unit": "TFLOP/s",
-                "frac": conv_tf / tf_peak, "traffic": None, "peak_source": peak_src,
+                "frac": conv_tf / tf_peak, "traffic": traffic,
+                "traffic_note": "average DRAM bytes per conv launch (ncu --set full, same 8-window forward; profiles/r01_final_ncu_conv_launches.csv)",
+                "peak_source": peak_src,
                 "launches": conv["n"] // 3, "avg_launch_ms": conv["ms"] / conv["n"],
                 "share_of_step": conv["ms"] / total_ms,
                 "note": "algorithmic conv FLOPs of one %d-window batch / sum of conv launch durations" % nb}
