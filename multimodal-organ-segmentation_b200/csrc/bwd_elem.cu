@@ -59,6 +59,7 @@ __device__ __forceinline__ void for_each_item(const NormBwdK& k, int img, int c,
   const size_t xbase = (size_t)(img * k.cb + c) * nvox * 8;
   const size_t abase = (size_t)(img * k.gA_cbt + k.gA_cb_off + c) * nvox * 8;
   if (!POOL) {
+    // (a 4-voxel unroll was measured SLOWER here: the per-voxel lambda state pushes the kernel into spills)
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
       float x[8], g[8];
       ldb8(k.x + xbase + v * 8, x);

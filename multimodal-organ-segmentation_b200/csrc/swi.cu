@@ -86,11 +86,14 @@ swi_blend_kernel(const float* __restrict__ logits, const int* __restrict__ start
 
 // Window mode: the launch covers exactly one window (extent read from starts on the device, so the launch arguments
 // are batch-independent and the call can sit in a CUDA graph).  grid: (x-chunks, RZ*RY)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 swi_blend_window_kernel(const float* __restrict__ logits, const int* __restrict__ starts, int K, int RZ, int RY, int RX,
                         const float* __restrict__ wz, const float* __restrict__ wy, const float* __restrict__ wx,
                         float w_floor, float* __restrict__ out, float* __restrict__ count, int VZ, int VY, int VX) {
-  const int lz = blockIdx.y / RY, ly = blockIdx.y - lz * RY;
+  // block = (x lanes, rows): blockDim.y window rows per block so that every lane of every warp has work
+  const int row = blockIdx.y * blockDim.y + threadIdx.y;
+  if (row >= RZ * RY) return;
+  const int lz = row / RY, ly = row - lz * RY;
   const int z = starts[0] + lz, y = starts[1] + ly;
   if (z < 0 || z >= VZ || y < 0 || y >= VY) return;
   const int sx = starts[2];
@@ -179,10 +182,13 @@ extern "C" int mmseg_swi_blend(const float* win_logits, const int32_t* starts_de
   if (bz0 < 0) {  // window mode: one window, extent taken from starts_dev on the device
     if (n_win != 1) return fail(MMSEG_ERR_INVALID_ARG, "swi_blend: window mode takes exactly one window");
     if ((int64_t)RZ * RY > 65535) return fail(MMSEG_ERR_INVALID_ARG, "swi_blend: roi has too many rows");
-    // one warp per window row is enough once every thread handles 4 voxels (RX = 96 -> 24 active lanes)
-    const int bt = RX <= 128 ? 32 : 128;
-    dim3 wgrid((RX + bt - 1) / bt, RZ * RY);
-    swi_blend_window_kernel<<<wgrid, bt, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    // every thread handles 4 voxels of a row (float4) when the row is aligned: RX/4 lanes per row, several rows per block
+    const bool vec_ok = (RX & 3) == 0 && (VX & 3) == 0 && RX / 4 <= 128;
+    const int bx = vec_ok ? RX / 4 : (RX < 128 ? RX : 128);
+    const int by = bx >= 128 ? 1 : 128 / bx;
+    dim3 wblock(bx, by);
+    dim3 wgrid(vec_ok ? 1 : (RX + bx - 1) / bx, (RZ * RY + by - 1) / by);
+    swi_blend_window_kernel<<<wgrid, wblock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         win_logits, starts_dev, K, RZ, RY, RX, wz, wy, wx, w_floor, out, count, VZ, VY, VX);
     return check_launch("swi_blend_window_kernel");
   }

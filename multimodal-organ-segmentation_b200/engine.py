@@ -143,6 +143,7 @@ class UNet3DEngine:
                 "UpBlock3D (reference unet.py:108-109) is not implemented in the sm_100a path")
         sp = self.split
         b = {"in": Blocked(n, (self.module.in_channels + 15) // 16 * 16, Z, Y, X, sp, device)}
+        b["in"].t.zero_()   # the sliding-window gather writes only the blocks with real channels
         for l in range(L):
             z, y, x = Z >> l, Y >> l, X >> l
             b[f"mid{l}"] = Blocked(n, f[l], z, y, x, sp, device)            # ConvBlock3D conv1 output
@@ -158,6 +159,10 @@ class UNet3DEngine:
 
     def input_buffer(self, n: int, Z: int, Y: int, X: int, device) -> Blocked:
         return self._buffers(n, Z, Y, X, device)["in"]
+
+    def gather_windows(self, volume: Tensor, starts_dev: Tensor, n: int, roi) -> None:
+        """Sliding-window gather of n windows of `volume` [C, VZ, VY, VX] straight into the blocked input buffer."""
+        K.swi_gather(volume, starts_dev, n, roi, self.input_buffer(n, roi[0], roi[1], roi[2], volume.device))
 
     # ---------------------------------------------------------------- forward
     @torch.no_grad()
@@ -278,7 +283,10 @@ class DualEncoderEngine:
         if any(d % (1 << (L - 1)) for d in (Z, Y, X)):
             raise NotImplementedError(f"spatial size {(Z, Y, X)} is not divisible by {1 << (L - 1)} (trilinear resize "
                                       "branch of UpBlock3D, reference unet.py:108-109, is not implemented)")
-        b = {"in": Blocked(n, (m.in_channels_per_modality + 15) // 16 * 16, Z, Y, X, sp, device)}
+        b = {}
+        for i in range(M):   # one input buffer per modality (zeroed once: gathers / packs only write the real channels' blocks)
+            b[f"in{i}"] = Blocked(n, (m.in_channels_per_modality + 15) // 16 * 16, Z, Y, X, sp, device)
+            b[f"in{i}"].t.zero_()
         for l in range(L):
             z, y, x = Z >> l, Y >> l, X >> l
             b[f"mid{l}"] = Blocked(n, f[l], z, y, x, sp, device)
@@ -293,26 +301,45 @@ class DualEncoderEngine:
         self._bufs[key] = b
         return b
 
+    def gather_windows(self, volume: Tensor, starts_dev: Tensor, n: int, roi) -> None:
+        """Sliding-window gather: modality i's channels of every window go to that modality's input buffer."""
+        m = self.module
+        cpm = m.in_channels_per_modality
+        b = self._buffers(n, roi[0], roi[1], roi[2], volume.device)
+        for i in range(m.num_modalities):
+            K.swi_gather(volume[i * cpm:(i + 1) * cpm], starts_dev, n, roi, b[f"in{i}"])
+
     @torch.no_grad()
     def forward(self, x: Tensor) -> Tensor:
         _lib.require_device()
         if not x.is_cuda:
             raise RuntimeError("mmseg_b200 engines run on CUDA tensors only (no CPU fallback)")
         m = self.module
-        f, L, M = m.features, len(m.features), m.num_modalities
         x = x.contiguous().float()
         n, cin, Z, Y, X = x.shape
         cpm = m.in_channels_per_modality
-        assert cin == M * cpm, f"expected {M * cpm} input channels, got {cin}"
-        P = self._pack()
+        assert cin == m.num_modalities * cpm, f"expected {m.num_modalities * cpm} input channels, got {cin}"
         b = self._buffers(n, Z, Y, X, x.device)
+        for i in range(m.num_modalities):   # modality i reads x[:, i*cpm:(i+1)*cpm] (dual_encoder.py:131-133)
+            K.pack_ncdhw(x[:, i * cpm:(i + 1) * cpm].contiguous(), b[f"in{i}"])
+        logits = torch.empty((n, m.out_channels, Z, Y, X), dtype=torch.float32, device=x.device)
+        return self.forward_blocked(n, Z, Y, X, logits)
+
+    @torch.no_grad()
+    def forward_blocked(self, n: int, Z: int, Y: int, X: int, logits: Tensor) -> Tensor:
+        """Runs the net on the per-modality input buffers; writes NCDHW fp32 logits [n, out_channels, Z, Y, X]."""
+        _lib.require_device()
+        m = self.module
+        f, L, M = m.features, len(m.features), m.num_modalities
+        cpm = m.in_channels_per_modality
+        P = self._pack()
+        b = self._buffers(n, Z, Y, X, logits.device)
         if self._runner is None:
-            self._runner = ConvRunner(self.split, x.device)
+            self._runner = ConvRunner(self.split, logits.device)
         r = self._runner
-        # encoders (dual_encoder.py:131-144): modality i reads x[:, i*cpm:(i+1)*cpm]
+        # encoders (dual_encoder.py:131-144)
         for i in range(M):
-            K.pack_ncdhw(x[:, i * cpm:(i + 1) * cpm].contiguous(), b["in"])
-            r.conv_norm_act(b["in"], [(0, cpm)], P[f"enc{i}.init.conv1"], b["mid0"])
+            r.conv_norm_act(b[f"in{i}"], [(0, cpm)], P[f"enc{i}.init.conv1"], b["mid0"])
             for l in range(L):
                 if l > 0:
                     r.conv_norm_act(b[f"pool{l}"], [(0, f[l - 1])], P[f"enc{i}.blocks.{l - 1}.conv1"], b[f"mid{l}"])
@@ -346,7 +373,6 @@ class DualEncoderEngine:
             r.conv_norm_act(b[f"cat{l}"], [(0, f[l]), (f[l], f[l])], P[f"decoder.{j}.conv1"], b[f"mid{l}"])
             r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[f"decoder.{j}.conv2"], b[f"dec{l}"])
             cur = b[f"dec{l}"]
-        logits = torch.empty((n, m.out_channels, Z, Y, X), dtype=torch.float32, device=x.device)
         r.conv_logits(cur, [(0, f[0])], P["out_conv"], logits)
         return logits
 

@@ -251,7 +251,9 @@ def instnorm_act_apply(raw: Tensor, raw_is_f32: bool, mean_rstd: Tensor, n_img: 
 
 def swi_gather(volume: Tensor, starts_dev: Tensor, n_win: int, roi: Tuple[int, int, int], dst: Blocked) -> None:
     Cc, VZ, VY, VX = volume.shape
-    cb = ((Cc + 15) // 16) * 2
+    # only the channel blocks that hold real channels are written: the zero padding up to a whole 16-channel K chunk
+    # is written once when the engine allocates (and zeroes) its input buffer
+    cb = (Cc + 7) // 8
     _call("mmseg_swi_gather", _ptr(volume), Cc, VZ, VY, VX, _ptr(starts_dev), n_win, roi[0], roi[1], roi[2],
                                _ptr(dst.t), dst.cbt, dst.lo_off, cb, _stream())
 

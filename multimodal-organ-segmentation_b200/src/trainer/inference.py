@@ -172,8 +172,7 @@ class SlidingWindowInferer:
         """gather -> forward -> blend for the n windows whose origins are in starts_dev[:n]."""
         eng = st["eng"]
         rz, ry, rx = self.roi
-        buf = eng.input_buffer(n, rz, ry, rx, volume.device)
-        K.swi_gather(volume, st["starts_dev"], n, self.roi, buf)
+        eng.gather_windows(volume, st["starts_dev"], n, self.roi)
         logits = st["logits"][:n]
         eng.forward_blocked(n, rz, ry, rx, logits)
         for j in range(n):

@@ -298,14 +298,21 @@ def swi_case(vol_shape=(48, 40, 36), roi=(32, 32, 32), mode="gaussian", net="une
              overlap=0.5, engine_batch=4):
     """Engine sliding-window inference vs the oracle restatement with the oracle model as predictor."""
     from mmseg_b200.src.models.backbones.unet import UNet3D
+    from mmseg_b200.src.models.backbones.dual_encoder import DualEncoder
     from mmseg_b200.src.trainer.inference import SlidingWindowInferer
-    from oracle.models import unet3d_forward
+    from oracle.models import unet3d_forward, dual_encoder_forward
     from oracle.sliding_window import sliding_window_inference as oswi
     torch.manual_seed(0)
-    m = UNet3D(in_channels=2, out_channels=8, features=list(features)).eval()
-    sd = {"backbone." + k: v.clone() for k, v in m.state_dict().items()}
+    if net == "dual":
+        m = DualEncoder(num_modalities=2, out_channels=8, features=list(features), fusion_type="attention").eval()
+        sd = {"backbone." + k: v.clone() for k, v in m.state_dict().items()}
+        predictor = lambda w: dual_encoder_forward(sd, w, "attention")
+    else:
+        m = UNet3D(in_channels=2, out_channels=8, features=list(features)).eval()
+        sd = {"backbone." + k: v.clone() for k, v in m.state_dict().items()}
+        predictor = lambda w: unet3d_forward(sd, w)
     vol = torch.randn(1, 2, *vol_shape)
-    want = oswi(vol, roi, 4, lambda w: unet3d_forward(sd, w), overlap=overlap, mode=mode)
+    want = oswi(vol, roi, 4, predictor, overlap=overlap, mode=mode)
     m = m.to(DEV).set_numeric_mode(nmode)
     inf = SlidingWindowInferer(m, roi, overlap, mode, engine_batch=engine_batch)
     got = inf(vol.to(DEV)).cpu()

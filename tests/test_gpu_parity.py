@@ -87,7 +87,7 @@ def test_swi_blend_finalize_exact():
 
 
 @pytest.mark.parametrize("kw", [dict(mode="gaussian"), dict(mode="constant"), dict(vol_shape=(33, 64, 40), overlap=0.25),
-                                dict(nmode="bf16")])
+                                dict(nmode="bf16"), dict(net="dual"), dict(vol_shape=(50, 41, 70), mode="gaussian")])
 def test_sliding_window_vs_oracle(kw):
     _c().swi_case(**kw)
 
