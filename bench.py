@@ -289,7 +289,7 @@ def run_ours(args):
         peak_src = "measured (MEASURED_PEAKS.json: bf16_tflops_sustained, hbm_gbs)"
     st = inf._state
     nb = st["nb"]
-    st["starts_dev"][:nb].copy_(st["starts_all"][:nb])
+    st["slots"][0]["starts_dev"][:nb].copy_(st["starts_all"][:nb])
     inf._run_batch(st, vol_dev, nb)
     torch.cuda.synchronize()
     K.PROFILE = []

@@ -125,6 +125,7 @@ class SlidingWindowInferer:
         self.overlap, self.mode, self.sigma_scale = overlap, mode, sigma_scale
         self.engine_batch = engine_batch
         self.use_graph = use_graph
+        self.n_slots = 2
         self._state = None
         self.launches_last = 0
 
@@ -157,27 +158,44 @@ class SlidingWindowInferer:
             # all window origins live on the device; each batch is a stream-ordered D2D copy into the fixed
             # `starts_dev` slot the (graph-captured) kernels read, so no host sync sits between batches
             "starts_all": torch.tensor(starts, dtype=torch.int32).to(device),
-            "starts_dev": torch.zeros((nb, 3), dtype=torch.int32, device=device),
-            "logits": torch.empty((nb, K_out, *self.roi), dtype=torch.float32, device=device),
             # weighted-logit accumulator and the count map share one allocation: acc[:K] = out, acc[K] = count,
             # so a rank's partial result travels as ONE tensor in the sharded exchange
             "acc": torch.empty((K_out + 1, VZ, VY, VX), dtype=torch.float32, device=device),
-            "graph": None, "vol_ptr": None, "launches_per_batch": 0,
         }
+        # TWO batch slots, each with its own engine buffers, window-origin slot, logits and CUDA stream: the forward of
+        # batch k+1 (tensor-bound convs + HBM-bound norm kernels) runs concurrently with the tail / blend of batch k, so
+        # the memory-bound kernels of one batch hide behind the tensor-bound kernels of the other.  Blends all run on the
+        # caller's stream in window order (deterministic), gated by per-slot events.
+        st["slots"] = []
+        for j in range(self.n_slots):
+            e = eng if j == 0 else type(eng)(eng.module, eng.mode)
+            st["slots"].append({
+                "eng": e, "stream": torch.cuda.Stream(device=device),
+                "starts_dev": torch.zeros((nb, 3), dtype=torch.int32, device=device),
+                "logits": torch.empty((nb, K_out, *self.roi), dtype=torch.float32, device=device),
+                "graph": None, "vol_ptr": None, "launches": 0,
+                "ev_fwd": torch.cuda.Event(), "ev_blend": None})
         st["out"], st["count"] = st["acc"][:K_out], st["acc"][K_out]
         self._state = st
         return st
 
-    def _run_batch(self, st, volume: Tensor, n: int) -> None:
-        """gather -> forward -> blend for the n windows whose origins are in starts_dev[:n]."""
-        eng = st["eng"]
+    def _forward_batch(self, st, slot, volume: Tensor, n: int) -> None:
+        """gather -> forward for the n windows whose origins are in the slot's starts_dev[:n] (current stream)."""
         rz, ry, rx = self.roi
-        eng.gather_windows(volume, st["starts_dev"], n, self.roi)
-        logits = st["logits"][:n]
-        eng.forward_blocked(n, rz, ry, rx, logits)
+        slot["eng"].gather_windows(volume, slot["starts_dev"], n, self.roi)
+        slot["eng"].forward_blocked(n, rz, ry, rx, slot["logits"][:n])
+
+    def _blend_batch(self, st, slot, n: int) -> None:
+        logits = slot["logits"]
         for j in range(n):
-            K.swi_blend(logits[j:j + 1], st["starts_dev"][j], 1, st["wz"], st["wy"], st["wx"], st["floor"], st["out"],
+            K.swi_blend(logits[j:j + 1], slot["starts_dev"][j], 1, st["wz"], st["wy"], st["wx"], st["floor"], st["out"],
                         st["count"], (-1, 0, 0, 0, 0, 0))
+
+    def _run_batch(self, st, volume: Tensor, n: int) -> None:
+        """One batch, eagerly, on the current stream with slot 0 (used by bench.py's per-kernel profile pass)."""
+        slot = st["slots"][0]
+        self._forward_batch(st, slot, volume, n)
+        self._blend_batch(st, slot, n)
 
     @torch.no_grad()
     def accumulate(self, volume: Tensor, lo: int = 0, hi: Optional[int] = None) -> None:
@@ -187,30 +205,43 @@ class SlidingWindowInferer:
         st = self._setup(volume.shape[0], volume.shape[1:], volume.device)
         starts = st["starts"]
         hi = len(starts) if hi is None else hi
+        main = torch.cuda.current_stream(volume.device)
         st["acc"].zero_()
         nb = st["nb"]
-        i = lo
+        for slot in st["slots"]:
+            slot["stream"].wait_stream(main)      # the volume (and anything else queued by the caller) is ready
+        i, k = lo, 0
         while i < hi:
             n = min(nb, hi - i)
-            st["starts_dev"][:n].copy_(st["starts_all"][i:i + n], non_blocking=True)
-            if self.use_graph and n == nb:
-                if st["graph"] is None or st["vol_ptr"] != volume.data_ptr():
-                    self._run_batch(st, volume, n)  # warm-up: allocates workspaces, packs weights
-                    torch.cuda.synchronize()
-                    g = torch.cuda.CUDAGraph()
-                    l0 = K.LAUNCHES[0]
-                    # capture records the launches without running them (the warm-up already did this batch)
-                    with torch.cuda.graph(g, stream=None):
-                        self._run_batch(st, volume, n)
-                    st["launches_per_batch"] = K.LAUNCHES[0] - l0
-                    K.LAUNCHES[0] = l0
-                    st["graph"], st["vol_ptr"] = g, volume.data_ptr()
+            slot = st["slots"][k % len(st["slots"])]
+            with torch.cuda.stream(slot["stream"]):
+                if slot["ev_blend"] is not None:   # the previous user of this slot's logits / origins has been blended
+                    slot["stream"].wait_event(slot["ev_blend"])
+                slot["starts_dev"][:n].copy_(st["starts_all"][i:i + n], non_blocking=True)
+                if self.use_graph and n == nb:
+                    if slot["graph"] is None or slot["vol_ptr"] != volume.data_ptr():
+                        self._forward_batch(st, slot, volume, n)  # warm-up: allocates workspaces, packs weights
+                        slot["stream"].synchronize()
+                        g = torch.cuda.CUDAGraph()
+                        l0 = K.LAUNCHES[0]
+                        with torch.cuda.graph(g, stream=slot["stream"]):
+                            self._forward_batch(st, slot, volume, n)
+                        slot["launches"] = K.LAUNCHES[0] - l0
+                        slot["graph"], slot["vol_ptr"] = g, volume.data_ptr()
+                        g.replay()
+                    else:
+                        slot["graph"].replay()
+                        K.LAUNCHES[0] += slot["launches"]
                 else:
-                    st["graph"].replay()
-                    K.LAUNCHES[0] += st["launches_per_batch"]
-            else:
-                self._run_batch(st, volume, n)
+                    self._forward_batch(st, slot, volume, n)
+                slot["ev_fwd"].record(slot["stream"])
+            main.wait_event(slot["ev_fwd"])
+            self._blend_batch(st, slot, n)
+            if slot["ev_blend"] is None:
+                slot["ev_blend"] = torch.cuda.Event()
+            slot["ev_blend"].record(main)
             i += n
+            k += 1
 
     @torch.no_grad()
     def finalize(self, normalize: bool = True, labels: bool = True, z0: int = 0, z1: Optional[int] = None):
