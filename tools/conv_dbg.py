@@ -9,20 +9,21 @@ cin, cout, S, n = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.
 torch.manual_seed(0)
 w = torch.randn(cout, cin, 3, 3, 3, device="cuda") * 0.05
 pw = K.pack_conv_weight(w, None, False, [cin], use_bias=False)
-src = Blocked(n, cin, S, S, S, False, "cuda"); src.t.normal_()
+src = Blocked(n, (cin + 15) // 16 * 16, S, S, S, False, "cuda"); src.t.normal_()
+flags = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 raw = torch.empty((n, cout // 8, S, S, S, 8), dtype=torch.bfloat16, device="cuda")
 a_cb = K.a_chunk_table(src, [0], [cin], False)
 tile = K.plan_conv(S, S, S, n, pw.n_kchunks, pw.n_out, 3, pw.NT)
 stats = torch.zeros(n * tile.tiles_per_img * cout * 2, device="cuda")
 for _ in range(3):
-    K.conv3d(src, pw, a_cb, raw, _lib.OUT_BLOCKED_BF16, stats=stats, dst_cbt=cout // 8, tile=tile)
+    K.conv3d(src, pw, a_cb, raw, _lib.OUT_BLOCKED_BF16, stats=stats, dst_cbt=cout // 8, tile=tile, flags=flags)
 torch.cuda.synchronize()
 ts = []
 for _ in range(5):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    K.conv3d(src, pw, a_cb, raw, _lib.OUT_BLOCKED_BF16, stats=stats, dst_cbt=cout // 8, tile=tile)
+    K.conv3d(src, pw, a_cb, raw, _lib.OUT_BLOCKED_BF16, stats=stats, dst_cbt=cout // 8, tile=tile, flags=flags)
     e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1) * 1e3)
 us = sorted(ts)[2]
-print(f"cin{cin} cout{cout} S{S} n{n} tile {tile.TX,tile.TY,tile.TZ,tile.NT,tile.stages}: {us:.0f} us  {2.0*n*S**3*cin*cout*27/us/1e6:.0f} TF/s")
+print(f"flags={flags} cin{cin} cout{cout} S{S} n{n} tile {tile.TX,tile.TY,tile.TZ,tile.NT,tile.stages}: {us:.0f} us  {2.0*n*S**3*cin*cout*27/us/1e6:.0f} TF/s")
