@@ -41,6 +41,7 @@ class GradBucketReducer:
         self._ready = [0] * len(self.buckets)
         self._works: list = []
         self._stream = None
+        self._producers: List[set] = [set() for _ in self.buckets]   # CUDA streams that packed into bucket i
         self.armed = False
 
     # ------------------------------------------------------------------ helpers
@@ -56,9 +57,13 @@ class GradBucketReducer:
         if flat.is_cuda:
             if self._stream is None:
                 self._stream = torch.cuda.Stream(device=flat.device)
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(flat.device))
-            self._stream.wait_event(ev)          # only this bucket's producers, not the rest of the backward
+            # only this bucket's producers (the backward's main stream and its wgrad side stream), not the rest of
+            # the backward
+            for st in self._producers[i] | {torch.cuda.current_stream(flat.device)}:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                self._stream.wait_event(ev)
+            self._producers[i] = set()
             with torch.cuda.stream(self._stream):
                 self._works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         else:
@@ -68,6 +73,7 @@ class GradBucketReducer:
     def arm(self) -> None:
         self.armed = True
         self._ready = [0] * len(self.buckets)
+        self._producers = [set() for _ in self.buckets]
         self._works = []
 
     @torch.no_grad()
@@ -79,6 +85,8 @@ class GradBucketReducer:
         dst.copy_(g.reshape(-1))
         if p.grad is not None:
             dst.add_(p.grad.reshape(-1).float())
+        if g.is_cuda:
+            self._producers[i].add(torch.cuda.current_stream(g.device))
         self._ready[i] += 1
         if self._ready[i] == len(self.buckets[i]):
             self._launch(i)

@@ -41,6 +41,11 @@ class TrainEngine:
         self.S: Dict[str, Tensor] = {}       # per-op saved tensors (raw conv outputs, mean/rstd) and workspaces
         self.tape: List[dict] = []
         self.grads: Dict[Tensor, Tensor] = {}
+        self._wstream = None
+        self._reducer = None
+        self._handed = set()
+        self._buf_busy: Dict[str, object] = {}
+        self._flip = 0
 
     # ---------------------------------------------------------------- buffers
     def _reset(self, n, Z, Y, X, device):
@@ -148,6 +153,32 @@ class TrainEngine:
         a_cb = K.a_chunk_table(dy, [0], [dy_channels], False)
         K.conv3d(dy, pw, a_cb, dst.t, _lib.OUT_BLOCKED_BF16, dst_cbt=dst.cbt, dst_cb_off=dst_c0 // 8)
 
+    def _wgrad_async(self, param, buf_key: str, *wargs, **wkw) -> None:
+        """Weight gradient on a SIDE stream: it only depends on the raw-output gradient just produced, so it overlaps
+        the dgrad / norm-backward kernels of the layers below (tensor-bound wgrad next to HBM-bound norm backward).
+        `buf_key` names the gradient workspace it reads; the next writer of that workspace waits for this wgrad."""
+        main = torch.cuda.current_stream(self.device)
+        if self._wstream is None:
+            self._wstream = torch.cuda.Stream(device=self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self._wstream.wait_event(ready)
+        with torch.cuda.stream(self._wstream):
+            g = K.conv3d_wgrad(*wargs, **wkw)
+            g.record_stream(main)
+            self.grads[param] = g
+            if self._reducer is not None and param.requires_grad:
+                self._reducer.grad_ready(param, g)       # packs + maybe launches the bucket all-reduce behind the wgrad
+                self._handed.add(param)
+            done = torch.cuda.Event()
+            done.record(self._wstream)
+        self._buf_busy[buf_key] = done
+
+    def _wait_buf(self, buf_key: str) -> None:
+        ev = self._buf_busy.pop(buf_key, None)
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+
     def _channel_sums(self, b: Blocked, c0: int, channels: int) -> Tensor:
         """[channels] fp32 sums over images and voxels (bias gradients)."""
         return (K.channel_mean(b, c0, channels) * float(b.nvox)).sum(0)
@@ -161,7 +192,10 @@ class TrainEngine:
         else:
             gA, gA_c0, scale = self.grad_of(dst), op["dst_c0"], 1.0
         gP = self.grad_of(op["pooled"]) if op["pooled"] is not None else None
-        draw_t = self.saved("ws.draw", (n * cout * Z * Y * X,), torch.bfloat16).view(n, cout // 8, Z, Y, X, 8)
+        self._flip ^= 1
+        dkey = f"ws.draw{self._flip}"            # two workspaces: the side-stream wgrad of the previous layer may still
+        self._wait_buf(dkey)                     # be reading the other one
+        draw_t = self.saved(dkey, (n * cout * Z * Y * X,), torch.bfloat16).view(n, cout // 8, Z, Y, X, 8)
         chan_scale, chan_bias = op["chan_scale"], None
         if op.get("gate_ref") is not None:   # encoder output feeding a CrossModalAttention gate (modality i)
             gate, i = op["gate_ref"]
@@ -171,7 +205,7 @@ class TrainEngine:
                            chan_scale, chan_bias)
         draw = _wrap(draw_t, n, cout, Z, Y, X)
         ks = conv.weight.shape[2]
-        self.grads[conv.weight] = K.conv3d_wgrad(src, op["segs"], draw_t, cout // 8, 0, cout, ks, conv.weight.shape)
+        self._wgrad_async(conv.weight, dkey, src, op["segs"], draw_t, cout // 8, 0, cout, ks, conv.weight.shape)
         if conv.bias is not None:  # cancelled exactly by the InstanceNorm mean subtraction
             self.grads[conv.bias] = torch.zeros_like(conv.bias, dtype=torch.float32)
         if op["need_dgrad"]:
@@ -186,10 +220,11 @@ class TrainEngine:
         cin, f = up.weight.shape[0], up.weight.shape[1]
         n, Z, Y, X = src.n_img, src.Z, src.Y, src.X
         gdst = self.grad_of(dst)
+        self._wait_buf("ws.dyu")
         dyu_t = self.saved("ws.dyu", (n * 8 * f * Z * Y * X,), torch.bfloat16).view(n, f, Z, Y, X, 8)  # 8f/8 = f blocks
         K.unshuffle_k2s2(gdst, 0, f, dyu_t)
         dyu = _wrap(dyu_t, n, 8 * f, Z, Y, X)
-        self.grads[up.weight] = K.conv3d_wgrad(src, [(0, cin)], dyu_t, f, 0, 8 * f, 1, up.weight.shape, transposed=True)
+        self._wgrad_async(up.weight, "ws.dyu", src, [(0, cin)], dyu_t, f, 0, 8 * f, 1, up.weight.shape, transposed=True)
         if up.bias is not None:
             self.grads[up.bias] = self._channel_sums(dyu, 0, 8 * f).view(8, f).sum(0)
         wd = up.weight.detach().float().reshape(cin, f, 8).permute(0, 2, 1).reshape(cin, 8 * f, 1, 1, 1).contiguous()
@@ -227,7 +262,9 @@ class TrainEngine:
 
     @torch.no_grad()
     def backward(self, dlogits: Tensor, reducer=None) -> Dict[Tensor, Tensor]:
-        handed = set()
+        self._reducer = reducer
+        handed = self._handed = set()
+        self._buf_busy = {}
         for op in reversed(self.tape):
             if reducer is not None:  # gradients produced by the previous op go out while this op's kernels are queued
                 for p, g in self.grads.items():
@@ -245,10 +282,13 @@ class TrainEngine:
                 self._bwd_convb(op)
             elif kind == "gate":
                 self._bwd_gate(op)
+        if self._wstream is not None:   # join the side stream: every weight gradient is complete on the caller's stream
+            torch.cuda.current_stream(self.device).wait_stream(self._wstream)
         if reducer is not None:
             for p, g in self.grads.items():
                 if p not in handed and p.requires_grad:
                     reducer.grad_ready(p, g)
+        self._reducer = None
         return self.grads
 
     # ---------------------------------------------------------------- model forwards
