@@ -16,6 +16,7 @@
 #include <cuda.h>
 
 #include "common.h"
+#include <type_traits>
 #include "ptx.cuh"
 
 namespace mmseg {
@@ -30,7 +31,8 @@ struct ConvKParams {
   uint32_t w_off, a_off;  // smem offsets (from the 128-aligned base)
   int out_mode, out_channels, dst_cbt, dst_cb_off, dst_lo_off;
   int desc_swap;
-  int w_stages;       // weight ring slots (2 for k=3: 27 taps per chunk; 8 for k=1: tiny chunks, latency-bound)
+  int w_stages;       // weight ring slots (2 for k=3: 27 taps per chunk; >= 8 for k=1: tiny chunks, latency-bound)
+  int w_resident;     // k=1 only: every K chunk's weights stay in shared memory for the CTA's lifetime (one load)
   int n_tiles;        // voxel tiles (all images) swept by the persistent CTAs of one N tile
   int acc_bufs;       // 1 or 2 accumulator sets in TMEM (2: the epilogue of tile i overlaps the MMAs of tile i+1)
   uint32_t buf_cols;  // TMEM columns between the two sets
@@ -43,6 +45,7 @@ struct ConvKParams {
   int16_t a_cb[MMSEG_MAX_KCHUNKS];
 };
 
+constexpr int kModeConvtHiLo = 100;   // epilogue-internal: MMSEG_OUT_CONVT_K2S2 with a lo plane (parity mode)
 constexpr int kMaxStages = 24;
 constexpr int kThreads = 192;
 constexpr int kMaxMT = 8;
@@ -110,7 +113,7 @@ __device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32
 // the C_out = 32 / 64 layers (an M=128, K=16 MMA costs >= ~51 clk whatever N is, measured).  All accumulators are
 // zeroed by the epilogue warps while the first TMA loads are in flight, so every MMA accumulates.
 template <int MT, int KS>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ ConvKParams p) {
   constexpr int KT = KS;  // taps per axis
   extern __shared__ uint8_t smem_raw[];
@@ -158,6 +161,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (elect_one()) {
       int stage = 0;
       uint32_t ph = 0, wc = 0, n_loaded = 0;
+      if (p.w_resident) {
+        const uint32_t wfull = smem_u32(&hdr->w_full[0]);
+        mbar_arrive_expect_tx(wfull, p.w_bytes * (uint32_t)p.n_kchunks);
+        for (int kc = 0; kc < p.n_kchunks; ++kc)
+          bulk_load_1d(w_smem + kc * p.w_bytes, p.W + ((size_t)nt * p.n_kchunks + kc) * p.w_bytes, p.w_bytes, wfull);
+      }
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         int t = tile;
         const int tx = t % p.tiles_x; t /= p.tiles_x;
@@ -166,11 +175,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int img = t / p.tiles_z;
         const int x0 = tx * p.TX, y0 = ty * p.TY, z0 = tz * p.TZ;
         for (int kc = 0; kc < p.n_kchunks; ++kc, ++wc) {
-          const uint32_t ws = wc % (uint32_t)p.w_stages, wph = (wc / (uint32_t)p.w_stages) & 1;
-          const uint32_t wfull = smem_u32(&hdr->w_full[ws]);
-          mbar_wait(smem_u32(&hdr->w_empty[ws]), wph ^ 1);
-          mbar_arrive_expect_tx(wfull, p.w_bytes);
-          bulk_load_1d(w_smem + ws * p.w_bytes, p.W + ((size_t)nt * p.n_kchunks + kc) * p.w_bytes, p.w_bytes, wfull);
+          if (!p.w_resident) {
+            const uint32_t ws = wc % (uint32_t)p.w_stages, wph = (wc / (uint32_t)p.w_stages) & 1;
+            const uint32_t wfull = smem_u32(&hdr->w_full[ws]);
+            mbar_wait(smem_u32(&hdr->w_empty[ws]), wph ^ 1);
+            mbar_arrive_expect_tx(wfull, p.w_bytes);
+            bulk_load_1d(w_smem + ws * p.w_bytes, p.W + ((size_t)nt * p.n_kchunks + kc) * p.w_bytes, p.w_bytes, wfull);
+          }
           const int cb = img * p.src_cbt + p.a_cb[kc];
           for (int pl = 0; pl < n_planes; ++pl) {
             const int z = z0 - p.halo + pl;
@@ -212,18 +223,70 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int stage = 0;
     uint32_t ph = 0, wc = 0, it = 0;
     const long long t_begin = clock64();
+    long long dbg_wait = 0, dbg_pre = 0, dbg_issue = 0, dbg_acc = 0, dbg_w = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int tz = (tile / (p.tiles_x * p.tiles_y)) % p.tiles_z;
       const int z0 = tz * p.TZ;
       const int tz_valid = min(p.TZ, p.Z - z0);
       const uint32_t as = p.acc_bufs == 2 ? (it & 1u) : 0u;
       const uint32_t aph = p.acc_bufs == 2 ? ((it >> 1) & 1u) : (it & 1u);
+      const long long ca = clock64();
       mbar_wait(smem_u32(&hdr->acc_empty[as]), aph);   // accumulator set drained and re-zeroed by the epilogue
       tc_fence_after();
+      dbg_acc += clock64() - ca;
       const uint32_t acc_base = tmem_base + as * p.buf_cols;
+      if (KS == 1 && p.w_resident) {
+        // k=1 with resident weights: the (K chunk, plane) items of the tile are consecutive ring stages and nothing
+        // else gates them, so they are issued in groups of up to 16 stages (one barrier round + one issue pause per
+        // group; with one group per K chunk of TZ <= 4 MMAs the ~400-cycle pause cost 3/4 of the tile time, measured)
+        if (it == 0) mbar_wait(smem_u32(&hdr->w_full[0]), 0);
+        constexpr int G1 = 16;
+        const int g1 = min(G1, p.stages);
+        const int total = p.n_kchunks * tz_valid;
+        const uint32_t idesc1 = make_idesc_bf16(128, NT);
+        int kc = 0, pl = 0;
+        for (int j0 = 0; j0 < total; j0 += g1) {
+          const int cnt = min(g1, total - j0);
+          if (lane < cnt) {
+            int si = stage + lane;
+            uint32_t pp = ph;
+            if (si >= p.stages) { si -= p.stages; pp ^= 1u; }
+            mbar_wait(smem_u32(&hdr->a_full[si]), pp);
+          }
+          __syncwarp();
+          tc_fence_after();
+          uint32_t d0[G1], at0[G1], bt0[G1], abar[G1];
+#pragma unroll
+          for (int h = 0; h < G1; ++h) {
+            int si = stage + h;
+            if (si >= p.stages) si -= p.stages;
+            d0[h] = acc_base + (uint32_t)pl * NT;
+            at0[h] = (((a_smem + si * p.stage_bytes) >> 4) & 0x3FFFu) | a_lbo;
+            bt0[h] = (((w_smem + (uint32_t)kc * p.w_bytes) >> 4) & 0x3FFFu) | b_lbo;
+            abar[h] = smem_u32(&hdr->a_empty[si]);
+            if (h < cnt && ++pl == tz_valid) { pl = 0; ++kc; }
+          }
+          if (leader) {
+#pragma unroll
+            for (int h = 0; h < G1; ++h) {
+              if (h < cnt) {
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                  umma_lohi(d0[h] + (uint32_t)m * m_cols, at0[h] + (uint32_t)m * 128u, a_hi, bt0[h], b_hi, idesc1);
+                umma_commit(abar[h]);
+              }
+            }
+          }
+          __syncwarp();
+          stage += cnt;
+          if (stage >= p.stages) { stage -= p.stages; ph ^= 1; }
+        }
+      } else
       for (int kc = 0; kc < p.n_kchunks; ++kc, ++wc) {
         const uint32_t ws = wc % (uint32_t)p.w_stages, wph = (wc / (uint32_t)p.w_stages) & 1;
+        const long long cw = clock64();
         mbar_wait(smem_u32(&hdr->w_full[ws]), wph);
+        dbg_w += clock64() - cw;
         const uint32_t b_base = (((w_smem + ws * p.w_bytes) >> 4) & 0x3FFFu) | b_lbo;
         // MEASURED (tools/micro/umma_bench.cu): a pause of the issuing lane between MMAs costs ~390 cycles + the pause
         // itself (8 back-to-back N=96 MMAs = 448 cycles; with a 100-cycle pause after them = 934), so barrier waits and
@@ -237,6 +300,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int pl_hi = min(n_planes, p.Z - z0 + p.halo);
         for (int g0 = pl_lo; g0 < pl_hi; g0 += gp) {
           const int cnt = min(gp, pl_hi - g0);
+          const long long c0 = clock64();
           if (lane < cnt) {
             int si = stage + lane;
             uint32_t pp = ph;
@@ -245,6 +309,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           __syncwarp();
           tc_fence_after();
+          const long long c1 = clock64();
           uint32_t idesc[GP], d0[GP], at0[GP], bt0[GP], nzv[GP], abar[GP];
 #pragma unroll
           for (int h = 0; h < GP; ++h) {
@@ -260,6 +325,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             bt0[h] = b_base + (uint32_t)(KT - 1 - dz_hi) * NT;   // first weight row of the dz range
             abar[h] = smem_u32(&hdr->a_empty[si]);
           }
+          const long long c2 = clock64();
           if (leader) {
 #pragma unroll
             for (int h = 0; h < GP; ++h) {
@@ -277,6 +343,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           __syncwarp();
+          const long long c3 = clock64();
+          dbg_wait += c1 - c0; dbg_pre += c2 - c1; dbg_issue += c3 - c2;
           stage += cnt;
           if (stage >= p.stages) { stage -= p.stages; ph ^= 1; }
         }
@@ -288,7 +356,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (p.dbg && leader) {
       long long* d = p.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8;
-      d[0] = clock64() - t_begin;
+      d[0] = clock64() - t_begin; d[1] = dbg_wait; d[2] = dbg_pre; d[3] = dbg_issue; d[4] = dbg_acc; d[7] = dbg_w;
     }
   } else {
     // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
@@ -304,6 +372,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int n_base = nt * p.NT;
     const bool want_stats = p.stats != nullptr;
+    // accumulator row L = m*128 + q*32 + lane is tile voxel (yy, xx) = (L / PX, L % PX): position for m = 0 and the step
+    // per M tile (no division inside the tile loop)
+    const int yy0 = (q * 32 + lane) / p.PX, xx0 = (q * 32 + lane) - yy0 * p.PX;
+    const int dy128 = 128 / p.PX, dx128 = 128 - dy128 * p.PX;
     const int n_cg = p.NT / 16;
     uint32_t it = 0;
     long long e_wait = 0;
@@ -324,133 +396,204 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(smem_u32(&hdr->acc_full[as]), aph);
       tc_fence_after();
       e_wait += clock64() - eq;
-      // per-tile, per-M-tile voxel position of this thread's accumulator row (one integer division per tile, not per
-      // column group: the ConvTranspose / logits / first-layer launches are epilogue-INSTRUCTION-bound, ncu)
-      int py[MT], px[MT];
-      bool ok[MT];
-#pragma unroll
-      for (int m = 0; m < MT; ++m) {
-        const int L = m * 128 + q * 32 + lane;
-        const int yy = L / p.PX;
-        const int xx = L - yy * p.PX;
-        py[m] = y0 + yy;
-        px[m] = x0 + xx;
-        ok[m] = (xx < p.TX) && (yy < p.TY) && (px[m] < p.X) && (py[m] < p.Y);
-      }
       const size_t plane = (size_t)p.Y * p.X;
       const size_t nvox = plane * p.Z;
-      for (int cg = 0; cg < ((p.dbg_flags & 4) ? 0 : n_cg); ++cg) {
-        const int n0 = n_base + cg * 16;
-        float bias_v[16];
+      // The column-group loop is instantiated per (output mode, statistics) and selected ONCE per tile: with the mode
+      // tested inside the chunk loop the k1 / ConvTranspose / first-layer launches were bound by the ~220 instructions
+      // per 16-column chunk of these 4 warps (ncu), not by TMEM or HBM.
+      auto epi = [&](auto mode_c, auto stats_c) {
+        constexpr int MODE = decltype(mode_c)::value;   // MMSEG_OUT_*; CONVT with a lo plane = kModeConvtHiLo
+        constexpr bool STATS = decltype(stats_c)::value;
+        constexpr bool F32 = MODE == MMSEG_OUT_BLOCKED_F32 || MODE == MMSEG_OUT_NCDHW_F32;
+        constexpr bool CONVT = MODE == MMSEG_OUT_CONVT_K2S2 || MODE == kModeConvtHiLo;
+        constexpr size_t ES = F32 ? 4 : 2;
+        const bool has_bias = p.bias != nullptr;
+        const size_t lo_bytes = (size_t)p.dst_lo_off * nvox * 8 * 2 * (CONVT ? 8 : 1);
+        for (int cg = 0; cg < ((p.dbg_flags & 4) ? 0 : n_cg); ++cg) {
+          const int n0 = n_base + cg * 16;
+          float bias_v[16];
+          if (has_bias) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) bias_v[i] = p.bias ? p.bias[n0 + i] : 0.f;
-        float s1[16], s2[16];
+            for (int i = 0; i < 16; ++i) bias_v[i] = p.bias[n0 + i];
+          }
+          float s1[16], s2[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-        // destination base of this column group (element offsets), hoisted out of the (zo, m) loops
-        size_t cbase = 0;
-        int ct_dz = 0, ct_dy = 0;
-        if (p.out_mode == MMSEG_OUT_CONVT_K2S2) {
-          const int CB = p.out_channels >> 3;
-          const int g = n0 >> 4;
-          const int tzy = g / CB, cb = g - tzy * CB;
-          ct_dz = tzy >> 1; ct_dy = tzy & 1;
-          cbase = (size_t)(img * p.dst_cbt + p.dst_cb_off + cb) * nvox * 8 * 8;   // output volume is 8x larger
-        } else if (p.out_mode == MMSEG_OUT_NCDHW_F32) {
-          cbase = ((size_t)img * p.out_channels + n0) * nvox;
-        } else {
-          cbase = (size_t)(img * p.dst_cbt + p.dst_cb_off + (n0 >> 3)) * nvox * 8;
-        }
-        const size_t lo_delta = (size_t)p.dst_lo_off * nvox * 8;
-        for (int zo = 0; zo < tz_valid; ++zo) {
-          const int z = z0 + zo;
-          const size_t zoff = (size_t)z * plane;
+          for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+          // destination of this column group at (z0, y = 0, x = 0) and the byte strides of a voxel step in z / y / x:
+          // everything mode-specific about addressing is hoisted out of the chunk loop
+          char* cg_base;
+          size_t zstride;
+          uint32_t ystride, xstride;
+          if constexpr (CONVT) {
+            const int CB = p.out_channels >> 3;
+            const int g = n0 >> 4;
+            const int tzy = g / CB, cb = g - tzy * CB;
+            const int ct_dz = tzy >> 1, ct_dy = tzy & 1;
+            const size_t cbase = (size_t)(img * p.dst_cbt + p.dst_cb_off + cb) * nvox * 8 * 8;   // output volume is 8x larger
+            const size_t oplane = (size_t)(2 * p.Y) * (2 * p.X);
+            zstride = 2 * oplane * 8 * ES;
+            ystride = (uint32_t)(2 * (2 * p.X) * 8 * ES);
+            xstride = (uint32_t)(2 * 8 * ES);
+            cg_base = reinterpret_cast<char*>(p.dst) +
+                      (cbase + ((size_t)(2 * z0 + ct_dz) * oplane + (size_t)ct_dy * (2 * p.X)) * 8) * ES;
+          } else if constexpr (MODE == MMSEG_OUT_NCDHW_F32) {
+            const size_t cbase = ((size_t)img * p.out_channels + n0) * nvox;
+            zstride = plane * ES;
+            ystride = (uint32_t)(p.X * ES);
+            xstride = (uint32_t)ES;
+            cg_base = reinterpret_cast<char*>(p.dst) + (cbase + (size_t)z0 * plane) * ES;
+          } else {
+            const size_t cbase = (size_t)(img * p.dst_cbt + p.dst_cb_off + (n0 >> 3)) * nvox * 8;
+            zstride = plane * 8 * ES;
+            ystride = (uint32_t)(p.X * 8 * ES);
+            xstride = (uint32_t)(8 * ES);
+            cg_base = reinterpret_cast<char*>(p.dst) + (cbase + (size_t)z0 * plane * 8) * ES;
+          }
+          const size_t half = nvox * 8 * ES;   // blocked layouts: the second 8-channel block of the 16 columns
+          // one (zo, m) accumulator chunk: bias, statistics, convert, store
+          auto consume = [&](const int zo, const bool okm, const uint32_t row_off, float* v) {
+            if (has_bias) {
 #pragma unroll
-          for (int m = 0; m < MT; ++m) {
-            float v[16];
-            const uint32_t taddr = acc_lane + (uint32_t)((m * p.TZ + zo) * p.NT + cg * 16);
-            tmem_ld16(taddr, v);
-            tmem_st16_zero(taddr);   // re-zero for the tile after next (every MMA accumulates)
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += bias_v[i];
-            if (ok[m]) {
-              if (want_stats) {
+              for (int i = 0; i < 16; ++i) v[i] += bias_v[i];
+            }
+            if (okm) {
+              if constexpr (STATS) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) { s1[i] += v[i]; s2[i] = fmaf(v[i], v[i], s2[i]); }
               }
-              const size_t vox = zoff + (size_t)py[m] * p.X + px[m];
-              if (p.out_mode == MMSEG_OUT_BLOCKED_BF16) {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst) + cbase + vox * 8;
+              char* o = cg_base + (size_t)zo * zstride + row_off;
+              if constexpr (MODE == MMSEG_OUT_BLOCKED_BF16) {
                 *reinterpret_cast<uint4*>(o) = pack8_bf16(v);
-                *reinterpret_cast<uint4*>(o + nvox * 8) = pack8_bf16(v + 8);
-              } else if (p.out_mode == MMSEG_OUT_BLOCKED_F32) {
-                float* o = reinterpret_cast<float*>(p.dst) + cbase + vox * 8;
+                *reinterpret_cast<uint4*>(o + half) = pack8_bf16(v + 8);
+              } else if constexpr (MODE == MMSEG_OUT_BLOCKED_F32) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                  float4* d = reinterpret_cast<float4*>(o + h * nvox * 8);
+                  float4* d = reinterpret_cast<float4*>(o + h * half);
                   d[0] = make_float4(v[8 * h + 0], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3]);
                   d[1] = make_float4(v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]);
                 }
-              } else if (p.out_mode == MMSEG_OUT_BLOCKED_BF16_HILO) {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst) + cbase + vox * 8;
+              } else if constexpr (MODE == MMSEG_OUT_BLOCKED_BF16_HILO) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                   uint4 hi, lo;
                   split8(v + 8 * h, hi, lo);
-                  *reinterpret_cast<uint4*>(o + h * nvox * 8) = hi;
-                  *reinterpret_cast<uint4*>(o + h * nvox * 8 + lo_delta) = lo;
+                  *reinterpret_cast<uint4*>(o + h * half) = hi;
+                  *reinterpret_cast<uint4*>(o + h * half + lo_bytes) = lo;
                 }
-              } else if (p.out_mode == MMSEG_OUT_CONVT_K2S2) {
+              } else if constexpr (MODE == MMSEG_OUT_CONVT_K2S2) {
                 // column n = (((dz*2 + dy)*CB + cb)*2 + dx)*8 + j: a thread's 16 columns are the SAME 8 output channels
                 // at the two x-adjacent output voxels -> one contiguous 32-byte store per thread, 1 KB per warp
-                const size_t ovox = ((size_t)(2 * z + ct_dz) * (2 * p.Y) + (size_t)(2 * py[m] + ct_dy)) * (2 * p.X) + 2 * px[m];
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst) + cbase + ovox * 8;
-                if (p.dst_lo_off > 0) {
+                *reinterpret_cast<uint4*>(o) = pack8_bf16(v);
+                *reinterpret_cast<uint4*>(o + 16) = pack8_bf16(v + 8);
+              } else if constexpr (MODE == kModeConvtHiLo) {
 #pragma unroll
-                  for (int h = 0; h < 2; ++h) {
-                    uint4 hi, l;
-                    split8(v + 8 * h, hi, l);
-                    *reinterpret_cast<uint4*>(o + 8 * h) = hi;
-                    *reinterpret_cast<uint4*>(o + 8 * h + lo_delta * 8) = l;
-                  }
-                } else {
-                  *reinterpret_cast<uint4*>(o) = pack8_bf16(v);
-                  *reinterpret_cast<uint4*>(o + 8) = pack8_bf16(v + 8);
+                for (int h = 0; h < 2; ++h) {
+                  uint4 hi, l;
+                  split8(v + 8 * h, hi, l);
+                  *reinterpret_cast<uint4*>(o + 16 * h) = hi;
+                  *reinterpret_cast<uint4*>(o + 16 * h + lo_bytes) = l;
                 }
               } else {  // MMSEG_OUT_NCDHW_F32
-                float* o = reinterpret_cast<float*>(p.dst) + cbase + vox;
+                float* of = reinterpret_cast<float*>(o);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                  if (n0 + i < p.out_channels) o[(size_t)i * nvox] = v[i];
+                  if (n0 + i < p.out_channels) of[(size_t)i * nvox] = v[i];
                 }
               }
             }
-          }
-        }
-        if (want_stats) {
-          // lanes -> one value per lane pair of arrays; 4 warps -> smem -> fixed-order sum -> global partial
+          };
+          // TMEM -> registers: two chunks (planes zo, zo+1 of the same M tile) per step, and the loads of the NEXT step
+          // are issued before this step's arithmetic and stores
+          auto chunk_addr = [&](const int zo, const int m) {
+            return acc_lane + (uint32_t)((m * p.TZ + zo) * p.NT + cg * 16);
+          };
+          uint32_t ra[16], rb[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < 16; ++i) rb[i] = 0u;
+          tmem_ld16_issue(chunk_addr(0, 0), ra);
+          if (tz_valid > 1) tmem_ld16_issue(chunk_addr(1, 0), rb);
+          for (int zo = 0; zo < tz_valid; zo += 2) {
+            const bool has_b = zo + 1 < tz_valid;
+            // the M-tile loop stays ROLLED (unrolled x MT x modes the epilogue no longer fits the instruction cache:
+            // stall_no_inst dominated the MT = 5 logits launch); the row position advances by 128 rows per M tile
+            int yy = yy0, xx = xx0;
+#pragma unroll 1
+            for (int m = 0; m < MT; ++m) {
+              const bool okm = (xx < p.TX) && (yy < p.TY) && (x0 + xx < p.X) && (y0 + yy < p.Y);
+              const uint32_t row_off = (uint32_t)(y0 + yy) * ystride + (uint32_t)(x0 + xx) * xstride;
+              xx += dx128; yy += dy128;
+              if (xx >= p.PX) { xx -= p.PX; ++yy; }
+              tmem_ld_wait16(ra);
+              tmem_ld_tie16(rb);
+              float va[16], vb[16];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
-              s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+              for (int i = 0; i < 16; ++i) { va[i] = __uint_as_float(ra[i]); vb[i] = __uint_as_float(rb[i]); }
+              if (m + 1 < MT) {
+                tmem_ld16_issue(chunk_addr(zo, m + 1), ra);
+                if (has_b) tmem_ld16_issue(chunk_addr(zo + 1, m + 1), rb);
+              } else if (zo + 2 < tz_valid) {
+                tmem_ld16_issue(chunk_addr(zo + 2, 0), ra);
+                if (zo + 3 < tz_valid) tmem_ld16_issue(chunk_addr(zo + 3, 0), rb);
+              }
+              // re-zero for the tile after next (every MMA accumulates); the loads of these columns have completed
+              tmem_st16_zero(chunk_addr(zo, m));
+              if (has_b) tmem_st16_zero(chunk_addr(zo + 1, m));
+              consume(zo, okm, row_off, va);
+              if (has_b) consume(zo + 1, okm, row_off, vb);
             }
           }
-          named_bar_sync(1, 128);  // previous column group's readers are done with hdr->red
-          if (lane == 0) {
+          if constexpr (STATS) {
+            // 32 per-thread sums (16 columns x {sum, sum of squares}) -> lane l holds the warp total of value l: a
+            // halving butterfly (31 shuffles) instead of 32 full reductions (160)
+            float r[32];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { hdr->red[ew][i] = s1[i]; hdr->red[ew][16 + i] = s2[i]; }
-          }
-          named_bar_sync(1, 128);
-          if (ew == 0) {
-            const float tot = hdr->red[0][lane] + hdr->red[1][lane] + hdr->red[2][lane] + hdr->red[3][lane];
-            const int ch = n0 + (lane & 15);
-            const int C = p.n_ntiles * p.NT;
-            float* dstp = p.stats + (((size_t)img * tiles_per_img + tile_in_img) * C + ch) * 2 + (lane >> 4);
-            *dstp = tot;
+            for (int i = 0; i < 16; ++i) { r[i] = s1[i]; r[16 + i] = s2[i]; }
+#pragma unroll
+            for (int off = 16, n = 16; off > 0; off >>= 1, n >>= 1) {
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < n; ++i) {
+                const float send = up ? r[i] : r[i + n];
+                const float keep = up ? r[i + n] : r[i];
+                r[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+            named_bar_sync(1, 128);  // previous column group's readers are done with hdr->red
+            hdr->red[ew][lane] = r[0];
+            named_bar_sync(1, 128);
+            if (ew == 0) {
+              const float tot = hdr->red[0][lane] + hdr->red[1][lane] + hdr->red[2][lane] + hdr->red[3][lane];
+              const int ch = n0 + (lane & 15);
+              const int C = p.n_ntiles * p.NT;
+              float* dstp = p.stats + (((size_t)img * tiles_per_img + tile_in_img) * C + ch) * 2 + (lane >> 4);
+              *dstp = tot;
+            }
           }
         }
+      };
+      using std::integral_constant;
+      using std::true_type;
+      using std::false_type;
+      switch (p.out_mode) {
+        case MMSEG_OUT_BLOCKED_BF16:
+          if (want_stats) epi(integral_constant<int, MMSEG_OUT_BLOCKED_BF16>{}, true_type{});
+          else epi(integral_constant<int, MMSEG_OUT_BLOCKED_BF16>{}, false_type{});
+          break;
+        case MMSEG_OUT_BLOCKED_F32:
+          if (want_stats) epi(integral_constant<int, MMSEG_OUT_BLOCKED_F32>{}, true_type{});
+          else epi(integral_constant<int, MMSEG_OUT_BLOCKED_F32>{}, false_type{});
+          break;
+        case MMSEG_OUT_BLOCKED_BF16_HILO:
+          if (want_stats) epi(integral_constant<int, MMSEG_OUT_BLOCKED_BF16_HILO>{}, true_type{});
+          else epi(integral_constant<int, MMSEG_OUT_BLOCKED_BF16_HILO>{}, false_type{});
+          break;
+        case MMSEG_OUT_CONVT_K2S2:
+          if (p.dst_lo_off > 0) epi(integral_constant<int, kModeConvtHiLo>{}, false_type{});
+          else epi(integral_constant<int, MMSEG_OUT_CONVT_K2S2>{}, false_type{});
+          break;
+        default:
+          epi(integral_constant<int, MMSEG_OUT_NCDHW_F32>{}, false_type{});
+          break;
       }
       // (planes zo >= tz_valid never receive MMAs and stay zero) hand the re-zeroed set back to the MMA warp
       tmem_wait_st();
@@ -544,7 +687,10 @@ static int plan_conv(const mmseg_conv_args* a, ConvPlan* out) {
   const uint32_t rows_needed = (uint32_t)(k.mt * 128 + 2 * k.halo * k.PX + 2 * k.halo);
   const uint32_t overflow = rows_needed * 16u > k.plane_bytes ? rows_needed * 16u - k.plane_bytes : 0u;
   k.w_off = kHeaderBytes;
-  k.w_stages = a->ksize == 1 ? 8 : 2;
+  // k=1: the whole [K x NT] weight panel of this CTA's column tile is a few KB -> keep it resident (one load per CTA,
+  // no per-chunk weight barrier, and the MMA warp can issue all (chunk, plane) items of a tile as one group)
+  k.w_resident = a->ksize == 1 && (uint32_t)a->n_kchunks * round_up(k.w_bytes, 128) <= 64u * 1024u;
+  k.w_stages = a->ksize == 1 ? (k.w_resident && a->n_kchunks > 8 ? a->n_kchunks : 8) : 2;
   k.a_off = k.w_off + k.w_stages * round_up(k.w_bytes, 128);
   uint32_t total = k.a_off + a->stages * k.stage_bytes + round_up(overflow, 128) + 128 /*align slack*/;
   // two CTAs share an SM only when both fit in TMEM: a CTA that needs more than 256 columns asks for more than half of

@@ -52,7 +52,15 @@ def tmem_cols(mt: int, TZ: int, NT: int) -> int:
     return tc
 
 
-def smem_bytes(ksize: int, TX: int, TY: int, NT: int, stages: int, TZ: int = 1) -> Optional[int]:
+def w_stages_for(ksize: int, NT: int, n_kchunks: int) -> int:
+    """Weight slots: 2 for k=3; k=1 keeps the whole [K x NT] panel resident when it fits 64 KB (mirrors plan_conv)."""
+    if ksize != 1:
+        return 2
+    resident = n_kchunks * _round_up(NT * 32, 128) <= 64 * 1024
+    return n_kchunks if (resident and n_kchunks > 8) else 8
+
+
+def smem_bytes(ksize: int, TX: int, TY: int, NT: int, stages: int, TZ: int = 1, n_kchunks: int = 1) -> Optional[int]:
     """Dynamic shared memory of one CTA, or None if the tiling is invalid (same arithmetic as plan_conv)."""
     h = ksize // 2
     PX, PY = TX + 2 * h, TY + 2 * h
@@ -70,7 +78,7 @@ def smem_bytes(ksize: int, TX: int, TY: int, NT: int, stages: int, TZ: int = 1) 
     stage = _round_up(a_tx, 128)
     rows_needed = mt * 128 + 2 * h * PX + 2 * h
     overflow = max(rows_needed * 16 - plane, 0)
-    w_stages = 8 if ksize == 1 else 2
+    w_stages = w_stages_for(ksize, NT, n_kchunks)
     total = HEADER_BYTES + w_stages * _round_up(w_bytes, 128) + stages * stage + _round_up(overflow, 128) + 128
     if tmem_cols(mt, TZ, NT) > 256 and total < 116 * 1024:
         total = 116 * 1024
@@ -110,7 +118,7 @@ def plan_conv(X: int, Y: int, Z: int, n_img: int, n_kchunks: int, n_out: int, ks
                 # of the activation bytes miss L2), so the bytes in flight — ring depth x stage size — bound the load
                 # rate (measured: 8 x 5.8 KB in flight = 20 GB/s per SM = load-bound).  Take the deepest ring that fits.
                 for st in (24, 20, 16, 12, 8, 6, 4, 3, 2):
-                    s_ = smem_bytes(ksize, TX, TY, NT, st, TZ)
+                    s_ = smem_bytes(ksize, TX, TY, NT, st, TZ, n_kchunks)
                     if s_ is not None:
                         sb, stages = s_, st
                         break

@@ -27,3 +27,7 @@ for _ in range(5):
     ts.append(e0.elapsed_time(e1) * 1e3)
 us = sorted(ts)[2]
 print(f"flags={flags} cin{cin} cout{cout} S{S} n{n} tile {tile.TX,tile.TY,tile.TZ,tile.NT,tile.stages}: {us:.0f} us  {2.0*n*S**3*cin*cout*27/us/1e6:.0f} TF/s")
+if flags & 2:   # per-CTA counters written over the stats buffer: [0] MMA warp total, [5] epilogue total, [6] epilogue waiting
+    torch.cuda.synchronize()
+    d = stats.view(torch.int64)[:148 * 8].view(148, 8).double().mean(0).tolist()
+    print(f"  clk: mma_total {d[0]:.0f} (a_full wait {d[1]:.0f}, descriptors {d[2]:.0f}, issue {d[3]:.0f}, acc_empty wait {d[4]:.0f}, w_full wait {d[7]:.0f})  epi_total {d[5]:.0f}  epi_wait_acc_full {d[6]:.0f}")
