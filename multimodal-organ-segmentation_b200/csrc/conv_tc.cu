@@ -127,7 +127,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
 
   const int nt = blockIdx.y;
-  const int n_planes = p.TZ + 2 * p.halo;
+  // k=3: one accumulator / one stage per z plane of the tile (+ halo planes).  k=1: the whole TX x TY x TZ tile is ONE
+  // stage (a 4-D TMA box) whose voxels are the flattened GEMM rows, so there is a single "plane" of MT M tiles
+  constexpr bool FLAT = KS == 1;
+  const int acc_z = FLAT ? 1 : p.TZ;
+  const int n_planes = acc_z + 2 * p.halo;
   const int tiles_per_img = p.tiles_x * p.tiles_y * p.tiles_z;
 
   if (threadIdx.x == 0) {
@@ -213,7 +217,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t b_hi = a_hi;
     const uint32_t a_lbo = (p.plane_bytes >> 4) << 16;          // K halves one plane apart
     const uint32_t b_lbo = ((brows * 16u) >> 4) << 16;
-    const uint32_t m_cols = (uint32_t)p.TZ * NT;                // TMEM columns between consecutive m tiles
+    const uint32_t m_cols = (uint32_t)acc_z * NT;                // TMEM columns between consecutive m tiles
     uint32_t a_tap[KT * KT], b_tap[KT * KT];
 #pragma unroll
     for (int i = 0; i < KT * KT; ++i) {
@@ -227,7 +231,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int tz = (tile / (p.tiles_x * p.tiles_y)) % p.tiles_z;
       const int z0 = tz * p.TZ;
-      const int tz_valid = min(p.TZ, p.Z - z0);
+      const int tz_valid = FLAT ? 1 : min(p.TZ, p.Z - z0);
       const uint32_t as = p.acc_bufs == 2 ? (it & 1u) : 0u;
       const uint32_t aph = p.acc_bufs == 2 ? ((it >> 1) & 1u) : (it & 1u);
       const long long ca = clock64();
@@ -374,8 +378,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool want_stats = p.stats != nullptr;
     // accumulator row L = m*128 + q*32 + lane is tile voxel (yy, xx) = (L / PX, L % PX): position for m = 0 and the step
     // per M tile (no division inside the tile loop)
-    const int yy0 = (q * 32 + lane) / p.PX, xx0 = (q * 32 + lane) - yy0 * p.PX;
-    const int dy128 = 128 / p.PX, dx128 = 128 - dy128 * p.PX;
+    // (k=1: rows are the flattened (zz, yy, xx) voxels of the TX x TY x TZ tile, PX = TX, PY = TY)
+    const int pxy = p.PX * p.PY;
+    const int L0 = q * 32 + lane;
+    const int zz0 = FLAT ? L0 / pxy : 0;
+    const int yy0 = (L0 - zz0 * pxy) / p.PX, xx0 = (L0 - zz0 * pxy) - yy0 * p.PX;
+    const int dz128 = FLAT ? 128 / pxy : 0;
+    const int dy128 = (128 - dz128 * pxy) / p.PX, dx128 = (128 - dz128 * pxy) - dy128 * p.PX;
     const int n_cg = p.NT / 16;
     uint32_t it = 0;
     long long e_wait = 0;
@@ -388,7 +397,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int img = t / p.tiles_z;
       const int tile_in_img = tile - img * tiles_per_img;
       const int x0 = tx * p.TX, y0 = ty * p.TY, z0 = tz * p.TZ;
-      const int tz_valid = min(p.TZ, p.Z - z0);
+      const int tz_valid = FLAT ? 1 : min(p.TZ, p.Z - z0);
       const uint32_t as = p.acc_bufs == 2 ? (it & 1u) : 0u;
       const uint32_t aph = p.acc_bufs == 2 ? ((it >> 1) & 1u) : (it & 1u);
       const uint32_t acc_lane = lane_base + as * p.buf_cols;
@@ -451,7 +460,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           const size_t half = nvox * 8 * ES;   // blocked layouts: the second 8-channel block of the 16 columns
           // one (zo, m) accumulator chunk: bias, statistics, convert, store
-          auto consume = [&](const int zo, const bool okm, const uint32_t row_off, float* v) {
+          auto consume = [&](const bool okm, const size_t off, float* v) {
             if (has_bias) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] += bias_v[i];
@@ -461,7 +470,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < 16; ++i) { s1[i] += v[i]; s2[i] = fmaf(v[i], v[i], s2[i]); }
               }
-              char* o = cg_base + (size_t)zo * zstride + row_off;
+              char* o = cg_base + off;
               if constexpr (MODE == MMSEG_OUT_BLOCKED_BF16) {
                 *reinterpret_cast<uint4*>(o) = pack8_bf16(v);
                 *reinterpret_cast<uint4*>(o + half) = pack8_bf16(v + 8);
@@ -505,41 +514,79 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // TMEM -> registers: two chunks (planes zo, zo+1 of the same M tile) per step, and the loads of the NEXT step
           // are issued before this step's arithmetic and stores
           auto chunk_addr = [&](const int zo, const int m) {
-            return acc_lane + (uint32_t)((m * p.TZ + zo) * p.NT + cg * 16);
+            return acc_lane + (uint32_t)((m * acc_z + zo) * p.NT + cg * 16);
           };
-          uint32_t ra[16], rb[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) rb[i] = 0u;
-          tmem_ld16_issue(chunk_addr(0, 0), ra);
-          if (tz_valid > 1) tmem_ld16_issue(chunk_addr(1, 0), rb);
-          for (int zo = 0; zo < tz_valid; zo += 2) {
-            const bool has_b = zo + 1 < tz_valid;
-            // the M-tile loop stays ROLLED (unrolled x MT x modes the epilogue no longer fits the instruction cache:
-            // stall_no_inst dominated the MT = 5 logits launch); the row position advances by 128 rows per M tile
-            int yy = yy0, xx = xx0;
-#pragma unroll 1
-            for (int m = 0; m < MT; ++m) {
-              const bool okm = (xx < p.TX) && (yy < p.TY) && (x0 + xx < p.X) && (y0 + yy < p.Y);
-              const uint32_t row_off = (uint32_t)(y0 + yy) * ystride + (uint32_t)(x0 + xx) * xstride;
-              xx += dx128; yy += dy128;
+          if constexpr (FLAT) {
+            // one chunk per M tile; the load of tile m+1 is in flight while tile m is converted and stored
+            uint32_t ra[16], rb[16];
+            int zz = zz0, yy = yy0, xx = xx0;
+            auto next_pos = [&](bool& okm, size_t& off) {
+              okm = (zz < p.TZ) && (z0 + zz < p.Z) && (y0 + yy < p.Y) && (x0 + xx < p.X);
+              off = (size_t)zz * zstride + (uint32_t)(y0 + yy) * ystride + (uint32_t)(x0 + xx) * xstride;
+              xx += dx128;
               if (xx >= p.PX) { xx -= p.PX; ++yy; }
+              yy += dy128;
+              if (yy >= p.PY) { yy -= p.PY; ++zz; }
+              zz += dz128;
+            };
+            tmem_ld16_issue(chunk_addr(0, 0), ra);
+#pragma unroll 1
+            for (int m = 0; m < MT; m += 2) {
+              bool okm;
+              size_t off;
+              float v[16];
+              next_pos(okm, off);
               tmem_ld_wait16(ra);
-              tmem_ld_tie16(rb);
-              float va[16], vb[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) { va[i] = __uint_as_float(ra[i]); vb[i] = __uint_as_float(rb[i]); }
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]);
+              if (m + 1 < MT) tmem_ld16_issue(chunk_addr(0, m + 1), rb);
+              tmem_st16_zero(chunk_addr(0, m));
+              consume(okm, off, v);
               if (m + 1 < MT) {
-                tmem_ld16_issue(chunk_addr(zo, m + 1), ra);
-                if (has_b) tmem_ld16_issue(chunk_addr(zo + 1, m + 1), rb);
-              } else if (zo + 2 < tz_valid) {
-                tmem_ld16_issue(chunk_addr(zo + 2, 0), ra);
-                if (zo + 3 < tz_valid) tmem_ld16_issue(chunk_addr(zo + 3, 0), rb);
+                next_pos(okm, off);
+                tmem_ld_wait16(rb);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]);
+                if (m + 2 < MT) tmem_ld16_issue(chunk_addr(0, m + 2), ra);
+                tmem_st16_zero(chunk_addr(0, m + 1));
+                consume(okm, off, v);
               }
-              // re-zero for the tile after next (every MMA accumulates); the loads of these columns have completed
-              tmem_st16_zero(chunk_addr(zo, m));
-              if (has_b) tmem_st16_zero(chunk_addr(zo + 1, m));
-              consume(zo, okm, row_off, va);
-              if (has_b) consume(zo + 1, okm, row_off, vb);
+            }
+          } else {
+            uint32_t ra[16], rb[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) rb[i] = 0u;
+            tmem_ld16_issue(chunk_addr(0, 0), ra);
+            if (tz_valid > 1) tmem_ld16_issue(chunk_addr(1, 0), rb);
+            for (int zo = 0; zo < tz_valid; zo += 2) {
+              const bool has_b = zo + 1 < tz_valid;
+              // the M-tile loop stays ROLLED (unrolled x MT x modes the epilogue no longer fits the instruction cache:
+              // stall_no_inst dominated the MT = 5 logits launch); the row position advances by 128 rows per M tile
+              int yy = yy0, xx = xx0;
+#pragma unroll 1
+              for (int m = 0; m < MT; ++m) {
+                const bool okm = (xx < p.TX) && (yy < p.TY) && (x0 + xx < p.X) && (y0 + yy < p.Y);
+                const uint32_t row_off = (uint32_t)(y0 + yy) * ystride + (uint32_t)(x0 + xx) * xstride;
+                xx += dx128; yy += dy128;
+                if (xx >= p.PX) { xx -= p.PX; ++yy; }
+                tmem_ld_wait16(ra);
+                tmem_ld_tie16(rb);
+                float va[16], vb[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { va[i] = __uint_as_float(ra[i]); vb[i] = __uint_as_float(rb[i]); }
+                if (m + 1 < MT) {
+                  tmem_ld16_issue(chunk_addr(zo, m + 1), ra);
+                  if (has_b) tmem_ld16_issue(chunk_addr(zo + 1, m + 1), rb);
+                } else if (zo + 2 < tz_valid) {
+                  tmem_ld16_issue(chunk_addr(zo + 2, 0), ra);
+                  if (zo + 3 < tz_valid) tmem_ld16_issue(chunk_addr(zo + 3, 0), rb);
+                }
+                // re-zero for the tile after next (every MMA accumulates); the loads of these columns have completed
+                tmem_st16_zero(chunk_addr(zo, m));
+                if (has_b) tmem_st16_zero(chunk_addr(zo + 1, m));
+                consume(okm, (size_t)zo * zstride + row_off, va);
+                if (has_b) consume(okm, (size_t)(zo + 1) * zstride + row_off, vb);
+              }
             }
           }
           if constexpr (STATS) {
@@ -664,9 +711,11 @@ static int plan_conv(const mmseg_conv_args* a, ConvPlan* out) {
   k.tiles_x = (a->X + a->TX - 1) / a->TX;
   k.tiles_y = (a->Y + a->TY - 1) / a->TY;
   k.tiles_z = (a->Z + a->TZ - 1) / a->TZ;
-  const int flat = (a->TY - 1) * k.PX + a->TX;
+  // k=3: rows of one padded plane up to the last needed voxel; k=1: every voxel of the TX x TY x TZ tile (one stage)
+  const int flat = a->ksize == 1 ? a->TX * a->TY * a->TZ : (a->TY - 1) * k.PX + a->TX;
   k.mt = (flat + 127) / 128;
-  const int n_acc = k.mt * a->TZ;
+  const int n_acc = a->ksize == 1 ? k.mt : k.mt * a->TZ;
+  if (a->ksize == 1 && a->TZ > 256) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: TZ=%d > 256 (TMA box)", a->TZ);
   if (k.mt > kMaxMT) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: %d M tiles per plane > %d", k.mt, kMaxMT);
   if (a->ksize == 3 && 3 * a->NT > 256) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: NT=%d > 80 with ksize 3 (folded MMA N = 3*NT <= 256)", a->NT);
   const int cols = n_acc * a->NT;
@@ -680,7 +729,7 @@ static int plan_conv(const mmseg_conv_args* a, ConvPlan* out) {
   k.NT = a->NT; k.n_ntiles = a->n_ntiles; k.n_kchunks = a->n_kchunks; k.src_cbt = a->src_cbt; k.stages = a->stages;
   const int taps = a->ksize * a->ksize * a->ksize;
   k.w_bytes = (uint32_t)taps * a->NT * 32u;
-  k.plane_bytes = (uint32_t)k.PX * k.PY * 16u;
+  k.plane_bytes = (uint32_t)k.PX * k.PY * 16u * (a->ksize == 1 ? (uint32_t)a->TZ : 1u);   // one K half of a stage
   if ((k.plane_bytes >> 4) > 0x3FFF) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: plane too large for LBO");
   k.a_tx_bytes = 2u * k.plane_bytes;
   k.stage_bytes = round_up(k.a_tx_bytes, 128);
@@ -744,7 +793,7 @@ extern "C" int mmseg_conv3d_fwd(const mmseg_conv_args* a, void* stream) {
   // activations viewed as 8-byte elements: dim0 = 2*X (one voxel's 8 bf16 channels = 2 elements)
   cuuint64_t dims[4] = {(cuuint64_t)2 * k.X, (cuuint64_t)k.Y, (cuuint64_t)k.Z, (cuuint64_t)k.n_img * k.src_cbt};
   cuuint64_t strides[3] = {(cuuint64_t)k.X * 16, (cuuint64_t)k.X * k.Y * 16, (cuuint64_t)k.X * k.Y * k.Z * 16};
-  cuuint32_t box[4] = {(cuuint32_t)(2 * k.PX), (cuuint32_t)k.PY, 1, 2};
+  cuuint32_t box[4] = {(cuuint32_t)(2 * k.PX), (cuuint32_t)k.PY, (cuuint32_t)(a->ksize == 1 ? k.TZ : 1), 2};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(a->src), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

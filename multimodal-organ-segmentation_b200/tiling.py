@@ -66,12 +66,14 @@ def smem_bytes(ksize: int, TX: int, TY: int, NT: int, stages: int, TZ: int = 1, 
     PX, PY = TX + 2 * h, TY + 2 * h
     if PX > 128 or PY > 256:
         return None
-    mt = _cdiv((TY - 1) * PX + TX, 128)
-    if mt > MAX_MT or mt * TZ * NT > TMEM_COLS or (ksize == 3 and 3 * NT > 256):
+    flat = ksize == 1                      # k=1: the whole TX x TY x TZ tile is one stage / one set of M tiles
+    mt = _cdiv(TX * TY * TZ, 128) if flat else _cdiv((TY - 1) * PX + TX, 128)
+    n_acc = mt if flat else mt * TZ
+    if mt > MAX_MT or n_acc * NT > TMEM_COLS or (ksize == 3 and 3 * NT > 256) or (flat and TZ > 256):
         return None
     taps = ksize ** 3
     w_bytes = taps * NT * 32
-    plane = PX * PY * 16
+    plane = PX * PY * 16 * (TZ if flat else 1)
     if (plane >> 4) > 0x3FFF:
         return None
     a_tx = 2 * plane
@@ -80,7 +82,7 @@ def smem_bytes(ksize: int, TX: int, TY: int, NT: int, stages: int, TZ: int = 1, 
     overflow = max(rows_needed * 16 - plane, 0)
     w_stages = w_stages_for(ksize, NT, n_kchunks)
     total = HEADER_BYTES + w_stages * _round_up(w_bytes, 128) + stages * stage + _round_up(overflow, 128) + 128
-    if tmem_cols(mt, TZ, NT) > 256 and total < 116 * 1024:
+    if tmem_cols(mt, 1 if flat else TZ, NT) > 256 and total < 116 * 1024:
         total = 116 * 1024
     if total > SMEM_LIMIT or w_bytes >= (1 << 20) or a_tx >= (1 << 20):
         return None
@@ -109,10 +111,17 @@ def plan_conv(X: int, Y: int, Z: int, n_img: int, n_kchunks: int, n_out: int, ks
         PX = TX + 2 * h
         for TY in range(1, Y + 1):
             mt = _cdiv((TY - 1) * PX + TX, 128)
+            if not h:
+                mt = _cdiv(TX * TY, 128)
             if mt > MAX_MT or mt * NT > TMEM_COLS:
                 break
-            for TZ in range(1, min(Z, TMEM_COLS // (mt * NT)) + 1):
-                tc = tmem_cols(mt, TZ, NT)
+            tz_max = min(Z, TMEM_COLS // (mt * NT)) if h else min(Z, 256, (MAX_MT * 128) // (TX * TY))
+            for TZ in range(1, tz_max + 1):
+                if not h:
+                    mt = _cdiv(TX * TY * TZ, 128)
+                    if mt * NT > TMEM_COLS:
+                        break
+                tc = tmem_cols(mt, TZ if h else 1, NT)
                 sb, stages = None, 0
                 # deep ring: one stage is a single small z-plane (a few KB) while a TMA round trip is ~1.5-2 us (a third
                 # of the activation bytes miss L2), so the bytes in flight — ring depth x stage size — bound the load
@@ -129,14 +138,14 @@ def plan_conv(X: int, Y: int, Z: int, n_img: int, n_kchunks: int, n_out: int, ks
                 if h:
                     per_tap = sum(_mma_cycles(NT * (min(2, pl) - max(0, pl - TZ + 1) + 1)) for pl in range(TZ + 2))
                     mma = n_kchunks * 9 * mt * (per_tap + 0.0)
-                else:
-                    mma = n_kchunks * TZ * mt * _mma_cycles(NT)
+                else:   # one tcgen05.commit (~45 clk) per stage = per K chunk, plus the TMA issue rate (~300 clk / stage)
+                    mma = n_kchunks * max(mt * _mma_cycles(NT) + 45.0, 300.0)
                 planes = TZ + 2 * h
                 load = n_kchunks * (planes * 2 * PX * (TY + 2 * h) * 16 + ksize ** 3 * NT * 32) / L2_BYTES_PER_CLK_SM
-                epi = TZ * mt * (NT // 16) * epi_cost + 500.0
+                epi = (TZ if h else 1) * mt * (NT // 16) * epi_cost + 500.0
                 # persistent CTAs (about one per SM in total): with two accumulator sets the epilogue of a tile hides
                 # behind the MMAs of the next one
-                double = 2 * mt * TZ * NT <= TMEM_COLS
+                double = 2 * mt * (TZ if h else 1) * NT <= TMEM_COLS
                 per_tile = max(mma, load, epi) + 300.0 if double else max(mma, load) + epi
                 ctas = max(1, min(n_tiles, NUM_SMS // n_ntiles))
                 est = _cdiv(n_tiles, ctas) * per_tile + 4000.0

@@ -111,11 +111,20 @@ int main() {
   cudaFuncSetAttribute(bench<0, -200>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(bench<0, -300>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(bench<0, -400>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int iters = 256;
   struct Named { const char* name; Exp e; } exps[] = {
       // how deep is the MMA queue?  the issuing thread spins D cycles after every 8 MMAs (8 x 56 = 448 cycles of work):
       // a deep queue hides the spin (56 cyc/MMA), a shallow one exposes it (56 + D/8)
       {"none N=96 back to back", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 0}},
+      // what does a tcgen05.commit between MMAs cost?  (k=1 convs used to commit after EVERY MMA)
+      {"none N=64 back to back", {0, 17248, 128, 1536, 128, 64, 2048 + 16, 0, 4, 0}},
+      {"none N=64 commit every 8 MMAs", {0, 17248, 128, 1536, 128, 64, 2048 + 16, 0, 4, 8}},
+      {"none N=64 commit every 4 MMAs", {0, 17248, 128, 1536, 128, 64, 2048 + 16, 0, 4, 4}},
+      {"none N=64 commit every 2 MMAs", {0, 17248, 128, 1536, 128, 64, 2048 + 16, 0, 4, 2}},
+      {"none N=64 commit every MMA", {0, 17248, 128, 1536, 128, 64, 2048 + 16, 0, 4, 1}},
       {"none N=96 spin 100 cycles every 8 MMAs", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 1100}},
       {"none N=96 spin 200 cycles every 8 MMAs", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 1200}},
       {"none N=96 spin 300 cycles every 8 MMAs", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 1300}},
@@ -125,6 +134,9 @@ int main() {
     switch (x.e.commit_every) {
       case 0: bench<0, 0><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
       case 8: bench<8, 0><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 4: bench<4, 0><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 2: bench<2, 0><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 1: bench<1, 0><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
       case 88: bench<8, 8><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
       case 108: bench<0, 8><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
       case 104: bench<0, 4><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
