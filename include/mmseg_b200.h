@@ -282,6 +282,11 @@ int mmseg_gate_mlp(const float* pooled, const float* w1, const float* b1, const 
 int mmseg_modality_combine(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_lo_off, int32_t M, int32_t cb,
                            int64_t voxels, const float* weights /* [n_img][M] or NULL */, float uniform_weight,
                            void* dst, int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, void* stream);
+/* out_conv / SegmentationHead k=1: nn.Conv3d(C, num_classes, 1) (unet.py:163,199; dual_encoder.py:118,164) on the CUDA
+ * cores at HBM speed: src blocked bf16 (channels cb_off*8 .. +cin, optional lo plane lo_off blocks away, parity mode),
+ * weight fp32 [cout][cin], bias fp32 [cout] or NULL, dst fp32 NCDHW [n_img][cout][voxels].  cin % 8 == 0, cout <= 16. */
+int mmseg_conv1x1_logits(const void* src, int32_t n_img, int32_t src_cbt, int32_t cb_off, int32_t lo_off, int32_t cin,
+                         int64_t voxels, const float* weight, const float* bias, int32_t cout, float* dst, void* stream);
 /* dst[b, c] = max over modalities (LateFusion fusion_method="max", src/models/fusion/late_fusion.py:62-64); bf16 mode. */
 int mmseg_modality_max(const void* src, int32_t n_img, int32_t src_cbt, int32_t M, int32_t cb, int64_t voxels, void* dst,
                        int32_t dst_cbt, int32_t dst_cb_off, void* stream);

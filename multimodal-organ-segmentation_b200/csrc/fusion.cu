@@ -221,9 +221,117 @@ static unsigned gx_for(size_t items, int rows) {
   return (unsigned)(g < 1 ? 1 : g);
 }
 
+// ------------------------------------------------------------------------------------------------ 1x1x1 logits conv
+// out_conv = nn.Conv3d(features[0], num_classes, 1) (unet.py:163, dual_encoder.py:118): K = 32, N = 8 is far too thin
+// for the tensor-core tile (N padded to 16, fp32 NCDHW scatter from 4 epilogue warps: 178 us per 8 windows) but it is
+// only 512 FLOP per voxel, so it runs on the CUDA cores at HBM speed: each thread owns 4 consecutive voxels, reads their
+// 8-channel blocks as 64 contiguous bytes, keeps COUT x 4 fp32 accumulators, and writes one float4 per class plane.
+// The weights sit in shared memory as [cin][COUT] so one LDS.128 feeds 16 FMAs.  fp32 accumulation of exact bf16 (or
+// hi + lo in parity mode) inputs with fp32 weights.
+template <int COUT>
+__global__ void __launch_bounds__(256) conv1x1_logits_kernel(const __nv_bfloat16* __restrict__ src, int src_cbt, int cb_off,
+                                                            int lo_off, int cin_blocks, size_t nvox,
+                                                            const float* __restrict__ weight, const float* __restrict__ bias,
+                                                            int cout, float* __restrict__ dst) {
+  extern __shared__ float wsm[];   // [cin][COUT], zero-padded classes
+  const int cin = cin_blocks * 8;
+  for (int i = threadIdx.x; i < cin * COUT; i += blockDim.x) {
+    const int ci = i / COUT, co = i - ci * COUT;
+    wsm[i] = co < cout ? weight[(size_t)co * cin + ci] : 0.f;
+  }
+  __syncthreads();
+  const int img = blockIdx.y;
+  const size_t v0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (v0 >= nvox) return;
+  const bool full = v0 + 4 <= nvox;
+  float acc[COUT][4];
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) {
+    const float b = (bias && co < cout) ? bias[co] : 0.f;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[co][v] = b;
+  }
+  for (int cb = 0; cb < cin_blocks; ++cb) {
+    const __nv_bfloat16* base = src + (((size_t)img * src_cbt + cb_off + cb) * nvox + v0) * 8;
+    float x[4][8];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      if (full || v0 + v < nvox) {
+        uint4 r = *reinterpret_cast<const uint4*>(base + v * 8);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          x[v][2 * j] = f.x; x[v][2 * j + 1] = f.y;
+        }
+        if (lo_off > 0) {
+          uint4 rl = *reinterpret_cast<const uint4*>(base + (size_t)lo_off * nvox * 8 + v * 8);
+          const __nv_bfloat162* hl = reinterpret_cast<const __nv_bfloat162*>(&rl);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(hl[j]);
+            x[v][2 * j] += f.x; x[v][2 * j + 1] += f.y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[v][j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4* wr = reinterpret_cast<const float4*>(wsm + (size_t)(cb * 8 + j) * COUT);
+#pragma unroll
+      for (int c4 = 0; c4 < COUT / 4; ++c4) {
+        const float4 w = wr[c4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          acc[4 * c4 + 0][v] = fmaf(w.x, x[v][j], acc[4 * c4 + 0][v]);
+          acc[4 * c4 + 1][v] = fmaf(w.y, x[v][j], acc[4 * c4 + 1][v]);
+          acc[4 * c4 + 2][v] = fmaf(w.z, x[v][j], acc[4 * c4 + 2][v]);
+          acc[4 * c4 + 3][v] = fmaf(w.w, x[v][j], acc[4 * c4 + 3][v]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) {
+    if (co < cout) {
+      float* o = dst + ((size_t)img * cout + co) * nvox + v0;
+      if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+        *reinterpret_cast<float4*>(o) = make_float4(acc[co][0], acc[co][1], acc[co][2], acc[co][3]);
+      } else {
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          if (v0 + v < nvox) o[v] = acc[co][v];
+      }
+    }
+  }
+}
+
 }  // namespace mmseg
 
 using namespace mmseg;
+
+extern "C" int mmseg_conv1x1_logits(const void* src, int32_t n_img, int32_t src_cbt, int32_t cb_off, int32_t lo_off,
+                                    int32_t cin, int64_t voxels, const float* weight, const float* bias, int32_t cout,
+                                    float* dst, void* stream) {
+  if (!src || !weight || !dst || n_img < 1 || voxels < 1) return fail(MMSEG_ERR_INVALID_ARG, "conv1x1_logits: bad arguments");
+  if (cin < 8 || (cin % 8) || cin > 256) return fail(MMSEG_ERR_UNSUPPORTED, "conv1x1_logits: cin=%d (multiple of 8, <= 256)", cin);
+  if (cout < 1 || cout > 16) return fail(MMSEG_ERR_UNSUPPORTED, "conv1x1_logits: cout=%d (1..16)", cout);
+  if (n_img > 65535) return fail(MMSEG_ERR_INVALID_ARG, "conv1x1_logits: n_img");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t nv = (size_t)voxels;
+  dim3 grid((unsigned)((nv + 1023) / 1024), (unsigned)n_img);
+  const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(src);
+  if (cout <= 4)
+    conv1x1_logits_kernel<4><<<grid, 256, (size_t)cin * 4 * sizeof(float), st>>>(s, src_cbt, cb_off, lo_off, cin / 8, nv, weight, bias, cout, dst);
+  else if (cout <= 8)
+    conv1x1_logits_kernel<8><<<grid, 256, (size_t)cin * 8 * sizeof(float), st>>>(s, src_cbt, cb_off, lo_off, cin / 8, nv, weight, bias, cout, dst);
+  else
+    conv1x1_logits_kernel<16><<<grid, 256, (size_t)cin * 16 * sizeof(float), st>>>(s, src_cbt, cb_off, lo_off, cin / 8, nv, weight, bias, cout, dst);
+  return check_launch("conv1x1_logits_kernel");
+}
 
 extern "C" int mmseg_channel_mean(const void* src, int32_t n_img, int32_t src_cbt, int32_t cb_off, int32_t lo_off,
                                   int32_t cb, int64_t voxels, float* partial, int32_t n_chunks, float* mean,

@@ -75,7 +75,13 @@ class ConvRunner:
                  dst_cbt=dst.cbt, dst_cb_off=dst_c0 // 8, dst_lo_off=dst.lo_off)
         self.launches += 1
 
-    def conv_logits(self, src: Blocked, segs, pw: PackedConv, out: Tensor) -> None:
+    def conv_logits(self, src: Blocked, segs, pw: PackedConv, out: Tensor, conv=None) -> None:
+        if conv is not None and len(segs) == 1 and segs[0][0] % 8 == 0 and segs[0][1] % 8 == 0 \
+                and conv.out_channels <= 16 and segs[0][1] <= 256:
+            # thin 1x1 (K = 32, N = 8): CUDA cores at HBM speed instead of a 16-column tensor-core tile
+            K.conv1x1_logits(src, segs[0][0], segs[0][1], conv.weight, conv.bias, out)
+            self.launches += 1
+            return
         a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], self.split)
         K.conv3d(src, pw, a_cb, out, _lib.OUT_NCDHW_F32)
         self.launches += 1
@@ -200,7 +206,7 @@ class UNet3DEngine:
             r.conv_norm_act(b[f"cat{l}"], [(0, f[l]), (f[l], f[l])], P[f"decoders.{j}.conv1"], b[f"mid{l}"])
             r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[f"decoders.{j}.conv2"], b[f"dec{l}"])
             cur = b[f"dec{l}"]
-        r.conv_logits(cur, [(0, f[0])], P["out_conv"], logits)
+        r.conv_logits(cur, [(0, f[0])], P["out_conv"], logits, m.out_conv)
         return logits
 
     @torch.no_grad()
@@ -373,7 +379,7 @@ class DualEncoderEngine:
             r.conv_norm_act(b[f"cat{l}"], [(0, f[l]), (f[l], f[l])], P[f"decoder.{j}.conv1"], b[f"mid{l}"])
             r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[f"decoder.{j}.conv2"], b[f"dec{l}"])
             cur = b[f"dec{l}"]
-        r.conv_logits(cur, [(0, f[0])], P["out_conv"], logits)
+        r.conv_logits(cur, [(0, f[0])], P["out_conv"], logits, m.out_conv)
         return logits
 
     def features_ncdhw(self, n, Z, Y, X):

@@ -502,6 +502,27 @@ def add_stats(a: Blocked, a_c0: int, b: Blocked, b_c0: int, channels: int):
     return y, partial, n_chunks
 
 
+def conv1x1_logits(src: Blocked, c0: int, cin: int, weight: Tensor, bias: Optional[Tensor], out: Tensor) -> None:
+    """nn.Conv3d(cin, classes, 1) -> fp32 NCDHW logits on the CUDA cores (HBM-bound; fp32 weights, hi + lo inputs in
+    parity mode).  weight: the module's [classes, cin, 1, 1, 1] parameter (read in place, no packed copy)."""
+    cout = weight.shape[0]
+    assert c0 % 8 == 0 and cin % 8 == 0 and cout <= 16 and weight.shape[1] == cin
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.shape[0] == src.n_img and out.shape[1] == cout
+    w = weight.detach().reshape(cout, cin)
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    b = None
+    if bias is not None:
+        b = bias.detach()
+        if b.dtype != torch.float32:
+            b = b.float()
+    if PROFILE is not None:
+        _INFO[0] = {"flops": 2.0 * src.n_img * src.nvox * cin * cout, "bytes": src.n_img * src.nvox * (cin * 2.0 + cout * 4.0),
+                    "layer": f"logits1x1 c{cin}->{cout} {src.Z}x{src.Y}x{src.X} img{src.n_img}"}
+    _call("mmseg_conv1x1_logits", _ptr(src.t), src.n_img, src.cbt, c0 // 8, src.lo_off if src.split else 0, cin, src.nvox,
+          _ptr(w), _ptr(b) if b is not None else None, cout, _ptr(out), _stream())
+
+
 def modality_max(src: Blocked, M: int, channels: int, dst: Blocked, dst_c0: int = 0) -> None:
     assert not src.split and not dst.split
     _call("mmseg_modality_max", _ptr(src.t), src.n_img, src.cbt, M, channels // 8, src.nvox, _ptr(dst.t), dst.cbt,

@@ -109,9 +109,12 @@ class TrainEngine:
 
     def conv_logits(self, name: str, src: Blocked, conv, logits: Tensor):
         cin = conv.weight.shape[1]
-        pw = K.pack_conv_weight(conv.weight, conv.bias, False, None)
-        a_cb = K.a_chunk_table(src, [0], [cin], False)
-        K.conv3d(src, pw, a_cb, logits, _lib.OUT_NCDHW_F32)
+        if cin % 8 == 0 and cin <= 256 and conv.out_channels <= 16:
+            K.conv1x1_logits(src, 0, cin, conv.weight, conv.bias, logits)
+        else:
+            pw = K.pack_conv_weight(conv.weight, conv.bias, False, None)
+            a_cb = K.a_chunk_table(src, [0], [cin], False)
+            K.conv3d(src, pw, a_cb, logits, _lib.OUT_NCDHW_F32)
         self.tape.append(dict(kind="logits", name=name, src=src, conv=conv))
 
     def conv_bias(self, name: str, src: Blocked, segs, conv, dst: Blocked, dst_c0: int):
