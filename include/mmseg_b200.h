@@ -68,6 +68,7 @@ int mmseg_device_ok(void);
  * stats_partial (optional): per-CTA per-channel (sum, sum of squares) of the fp32 accumulators over valid voxels —
  * the InstanceNorm3d statistics (unet.py:34-35) are produced by the conv epilogue, deterministically (no atomics).
  */
+#define MMSEG_CONV_ROLL_Z 16
 typedef struct {
   const void* src;       /* blocked bf16 [n_img*src_cbt][Z][Y][X][8]                                  */
   const void* weights;   /* packed bf16, see layout above                                             */
@@ -84,7 +85,10 @@ typedef struct {
   int32_t out_mode;
   int32_t out_channels;  /* real channels (masks N padding); for CONVT: channels per tap              */
   int32_t dst_cbt, dst_cb_off, dst_lo_off; /* blocked destinations: blocks per image, first block, lo-plane offset */
-  int32_t flags;         /* bit0: debug — swap LBO/SBO in the smem descriptors                        */
+  int32_t flags;         /* bit0: debug — swap LBO/SBO in the smem descriptors; MMSEG_CONV_ROLL_Z (16): run the
+                            rolling-accumulator kernel — TZ is then the z-SEGMENT length of a (TX x TY) column
+                            (needs ksize 3, NT = C_out = 32, one 128-row M tile per plane, blocked bf16 output, no
+                            bias, all K-chunk weights resident in shared memory; see conv_tc.cu)              */
   int16_t a_cb[MMSEG_MAX_KCHUNKS]; /* first channel block (of 2) in src for each K chunk              */
 } mmseg_conv_args;
 

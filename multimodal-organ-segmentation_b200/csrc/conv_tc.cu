@@ -34,6 +34,8 @@ struct ConvKParams {
   int w_stages;       // weight ring slots (2 for k=3: 27 taps per chunk; >= 8 for k=1: tiny chunks, latency-bound)
   int w_resident;     // k=1 only: every K chunk's weights stay in shared memory for the CTA's lifetime (one load)
   int n_tiles;        // voxel tiles (all images) swept by the persistent CTAs of one N tile
+  int roll;           // rolling-z kernel (conv3d_roll_kernel): TZ = z-segment length, tiles_z = segments per column
+  int R;              // rolling-z: TMEM ring slots (output planes in flight) = tmem_cols / NT
   int acc_bufs;       // 1 or 2 accumulator sets in TMEM (2: the epilogue of tile i overlaps the MMAs of tile i+1)
   uint32_t buf_cols;  // TMEM columns between the two sets
   long long* dbg;     // optional per-CTA cycle counters (flags bit1): MMA warp waits / epilogue waits
@@ -659,6 +661,336 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ rolling-z variant
+// For the full-resolution C_out = 32 layers (k=3, one 128-row M tile per plane, every K chunk's weights resident in
+// shared memory) the tile is a whole z SEGMENT of a (TX x TY) column, and the TMEM accumulators are a RING of
+// R = 512 / NT output planes: input plane q (outer loop; K chunks inner) adds its three z taps to ring slots
+// q-2 .. q with ONE N = 3*NT MMA per (dy, dx) tap, output plane q-2 is then complete and is handed to the epilogue
+// (z_full[slot]) while the MMAs run on, and the slot returns through z_empty[slot].  Versus the TZ = 8 tiles of
+// conv3d_tc_kernel this removes the four partial-N boundary planes of every tile (20 % of the MMA cycles: an N = 32
+// MMA costs the same ~51 cycles as an N = 96 one) and the per-tile accumulator hand-over.  A ring wrap splits one
+// plane's MMAs in two (1 plane in 16).  InstanceNorm partial sums are kept in registers over the whole segment.
+struct __align__(16) RollHeader {
+  uint64_t a_full[kMaxStages];
+  uint64_t a_empty[kMaxStages];
+  uint64_t z_full[16];
+  uint64_t z_empty[16];
+  uint64_t w_full;
+  uint32_t tmem_ptr;
+  uint32_t pad;
+  float red[4][64];
+};
+constexpr uint32_t kRollHeaderBytes = 2048;
+static_assert(sizeof(RollHeader) <= kRollHeaderBytes, "roll header too large");
+
+// warps: 0 TMA, 1 MMA, 2-9 epilogue (two warps per TMEM lane quarter, one 16-column group each: with four warps the
+// per-plane epilogue (~700 cycles) was slower than a plane's MMAs for C_in <= 32)
+constexpr int kRollThreads = 320;
+
+__global__ void __launch_bounds__(kRollThreads, 1)
+conv3d_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ ConvKParams p) {
+  constexpr int KT = 3;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  RollHeader* hdr = reinterpret_cast<RollHeader*>(smem);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t w_smem = smem_base + p.w_off;
+  const uint32_t a_smem = smem_base + p.a_off;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t R = 16;   // ring slots: 512 TMEM columns / NT (NT = 32, checked on the host); a power of two so
+                               // that the ring arithmetic of the issue loop is shifts and masks, not divisions
+  const int ZS = p.TZ;
+  const int items_per_img = p.tiles_x * p.tiles_y * p.tiles_z;
+  const int n_items = items_per_img * p.n_img;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&hdr->a_full[s]), 1);
+      mbar_init(smem_u32(&hdr->a_empty[s]), 1);
+    }
+    for (int s = 0; s < 16; ++s) {
+      mbar_init(smem_u32(&hdr->z_full[s]), 1);
+      mbar_init(smem_u32(&hdr->z_empty[s]), (kRollThreads - 64) / 32);   // one arrive per epilogue WARP (per plane: 256
+                                                                           // per-thread arrives would swamp the barrier unit)
+    }
+    mbar_init(smem_u32(&hdr->w_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmA);
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&hdr->tmem_ptr), p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer: weights once, then (item, plane, K chunk) stages =====================
+    if (elect_one()) {
+      const uint32_t wfull = smem_u32(&hdr->w_full);
+      mbar_arrive_expect_tx(wfull, p.w_bytes * (uint32_t)p.n_kchunks);
+      for (int kc = 0; kc < p.n_kchunks; ++kc)
+        bulk_load_1d(w_smem + kc * p.w_bytes, p.W + (size_t)kc * p.w_bytes, p.w_bytes, wfull);
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int t = item;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int zs = t % p.tiles_z;
+        const int img = t / p.tiles_z;
+        const int x0 = tx * p.TX, y0 = ty * p.TY, zs0 = zs * ZS;
+        const int zsv = min(ZS, p.Z - zs0);
+        for (int q = 0; q < zsv + 2; ++q) {
+          const int z = zs0 - 1 + q;
+          if (z < 0 || z >= p.Z) continue;
+          for (int kc = 0; kc < p.n_kchunks; ++kc) {
+            const uint32_t afull = smem_u32(&hdr->a_full[stage]);
+            mbar_wait(smem_u32(&hdr->a_empty[stage]), ph ^ 1);
+            mbar_arrive_expect_tx(afull, p.a_tx_bytes);
+            tma_load_4d(a_smem + stage * p.stage_bytes, &tmA, afull, 2 * (x0 - 1), y0 - 1, z, img * p.src_cbt + p.a_cb[kc]);
+            if (++stage == p.stages) { stage = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // A software-pipelined per-stage loop: the tensor pipe queues only ~2 MMAs behind the issuing thread (measured,
+    // tools/micro/umma_bench.cu: a pause of P cycles costs P - 110), so nothing longer than ~100 cycles may sit between
+    // two MMAs.  Hence the descriptors of stage s+1 are computed in the middle of stage s's nine MMAs, stage s+1's
+    // "full" barrier is probed there too, and there are no per-group barrier rounds at all.  ONE elected lane runs the
+    // whole loop (measured: the same loop run warp-uniformly with the MMAs under `if (leader)` is 35 % slower).
+    const bool leader = elect_one();
+    if (leader) {
+      const uint32_t NT = (uint32_t)p.NT;
+      const uint32_t brows = (uint32_t)KT * NT;
+      const uint32_t a_hi = (128u >> 4) | (1u << 14);
+      const uint32_t b_hi = a_hi;
+      const uint32_t a_lbo = (p.plane_bytes >> 4) << 16;
+      const uint32_t b_lbo = ((brows * 16u) >> 4) << 16;
+      uint32_t a_tap[KT * KT], b_tap[KT * KT];
+#pragma unroll
+      for (int i = 0; i < KT * KT; ++i) {
+        a_tap[i] = (uint32_t)((i / KT) * p.PX + (i % KT));
+        b_tap[i] = (uint32_t)i * 2u * brows;
+      }
+      const uint32_t a_stage0 = ((a_smem >> 4) & 0x3FFFu) | a_lbo;
+      const uint32_t a_stage_step = p.stage_bytes >> 4;
+      const uint32_t w_base0 = ((w_smem >> 4) & 0x3FFFu) | b_lbo;
+      const uint32_t w_step = p.w_bytes >> 4;
+      const uint32_t a_full0 = smem_u32(&hdr->a_full[0]), a_empty0 = smem_u32(&hdr->a_empty[0]);
+      const uint32_t z_full0 = smem_u32(&hdr->z_full[0]), z_empty0 = smem_u32(&hdr->z_empty[0]);
+      const int txy = p.tiles_x * p.tiles_y;
+
+      // ---- stage generator state: (item, plane q, K chunk kc), ring stage / phase, ring position gz
+      int item = blockIdx.x;
+      int zsv = 0, q = 0, q_last = -1, kc = 0;
+      uint32_t gz = 0, stage = 0, ph = 0;
+      bool more = item < n_items;
+      auto enter_item = [&]() {
+        const int zs = (item / txy) % p.tiles_z;
+        const int zs0 = zs * ZS;
+        zsv = min(ZS, p.Z - zs0);
+        q = zs0 == 0 ? 1 : 0;                                 // input planes inside the volume: q .. q_last
+        q_last = (zs0 + zsv >= p.Z) ? zsv : zsv + 1;
+        kc = 0;
+      };
+      if (more) enter_item();
+      // descriptor set of one stage
+      struct Stage { uint32_t at0, abar, afull, apar, bta, d0a, ida, btb, idb, zc0, zc1, zneed; };
+      auto gen = [&](Stage& d) {   // fills d for the current cursor and advances it; call only while `more`
+        const int dz_hi = min(KT - 1, q);
+        const int dz_lo = max(0, q - (zsv - 1));
+        const uint32_t n = (uint32_t)(dz_hi - dz_lo + 1);
+        const uint32_t g_lo = gz + (uint32_t)(q - dz_hi);
+        const uint32_t col = g_lo & (R - 1);
+        const uint32_t n1 = min(n, R - col);
+        d.at0 = a_stage0 + stage * a_stage_step;
+        d.abar = a_empty0 + stage * 8u;
+        d.afull = a_full0 + stage * 8u;
+        d.apar = ph;
+        const uint32_t bb = w_base0 + (uint32_t)kc * w_step + (uint32_t)(KT - 1 - dz_hi) * NT;
+        d.bta = bb;
+        d.d0a = tmem_base + col * NT;
+        d.ida = make_idesc_bf16(128, n1 * NT);
+        d.btb = bb + n1 * NT;
+        d.idb = n > n1 ? make_idesc_bf16(128, (n - n1) * NT) : 0u;
+        d.zneed = gz + (uint32_t)min(q, zsv - 1) + 1u;        // ring slots [.., zneed) must be acquired before this stage
+        d.zc0 = 0u; d.zc1 = 0u;
+        if (kc == p.n_kchunks - 1) {                          // last K chunk of plane q: output plane q-2 is complete
+          if (q >= 2) d.zc0 = z_full0 + ((gz + (uint32_t)(q - 2)) & (R - 1)) * 8u;
+          if (q == q_last && q_last == zsv)                   // top halo plane outside the volume: zsv-1 completes too
+            d.zc1 = z_full0 + ((gz + (uint32_t)(zsv - 1)) & (R - 1)) * 8u;
+        }
+        // advance
+        if (++stage == (uint32_t)p.stages) { stage = 0; ph ^= 1u; }
+        if (++kc == p.n_kchunks) {
+          kc = 0;
+          if (++q > q_last) {
+            gz += (uint32_t)zsv;
+            item += gridDim.x;
+            more = item < n_items;
+            if (more) enter_item();
+          }
+        }
+      };
+
+      mbar_wait(smem_u32(&hdr->w_full), 0);
+      uint32_t g_acq = 0;   // ring slots acquired so far (z_empty waited), a running count over all items
+      Stage cur, nxt;
+      bool have = more;
+      if (have) gen(cur);
+      bool cur_ready = false;
+      while (have) {
+        if (!cur_ready) mbar_wait(cur.afull, cur.apar);
+        while (g_acq < cur.zneed) {
+          mbar_wait(z_empty0 + (g_acq & (R - 1)) * 8u, (g_acq >> 4) & 1u);
+          ++g_acq;
+        }
+        tc_fence_after();
+        const bool have_next = more;
+        bool next_ready = false;
+#pragma unroll
+        for (int i = 0; i < KT * KT; ++i) {
+          umma_lohi(cur.d0a, cur.at0 + a_tap[i], a_hi, cur.bta + b_tap[i], b_hi, cur.ida);
+          // the descriptor arithmetic for stage s+1 and the probe of its "full" barrier sit between this stage's MMAs
+          // (each gap stays below the ~110 cycles the tensor pipe has queued)
+          if (i == 2 && have_next) gen(nxt);
+          if (i == 6 && have_next) next_ready = mbar_test_wait(nxt.afull, nxt.apar);
+        }
+        if (cur.idb) {
+#pragma unroll
+          for (int i = 0; i < KT * KT; ++i) umma_lohi(tmem_base, cur.at0 + a_tap[i], a_hi, cur.btb + b_tap[i], b_hi, cur.idb);
+        }
+        umma_commit(cur.abar);
+        if (cur.zc0) umma_commit(cur.zc0);
+        if (cur.zc1) umma_commit(cur.zc1);
+        cur = nxt;
+        cur_ready = next_ready;
+        have = have_next;
+      }
+    }
+  } else {
+    // ===================== epilogue (8 warps: TMEM lane quarter = warp & 3, column group = (warp - 2) / 4) ==========
+    const int qd = warp & 3;
+    const int ew = warp - 2;
+    const int cg = ew >> 2;          // 16-column group of this warp (NT = 32: two groups)
+    const int w4 = ew & 3;           // rank among the four warps of the group
+    const uint32_t lane_base = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)cg * 16u;
+    for (uint32_t c = 0; c < p.tmem_cols; c += 32) tmem_st16_zero(lane_base + c);
+    tmem_wait_st();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0)
+      for (int s = 0; s < (int)R; ++s) mbar_arrive(smem_u32(&hdr->z_empty[s]));
+
+    const bool want_stats = p.stats != nullptr;
+    const int L0 = qd * 32 + lane;
+    const int yy = L0 / p.PX, xx = L0 - yy * p.PX;
+    const size_t plane = (size_t)p.Y * p.X;
+    const size_t nvox = plane * p.Z;
+    uint32_t gz = 0;
+    long long e_wait = 0;
+    const long long e_begin = clock64();
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int t = item;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; t /= p.tiles_y;
+      const int zs = t % p.tiles_z;
+      const int img = t / p.tiles_z;
+      const int item_in_img = item - img * items_per_img;
+      const int x0 = tx * p.TX, y0 = ty * p.TY, zs0 = zs * ZS;
+      const int zsv = min(ZS, p.Z - zs0);
+      const bool ok = (xx < p.TX) && (yy < p.TY) && (x0 + xx < p.X) && (y0 + yy < p.Y);
+      __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(p.dst) +
+                           ((size_t)(img * p.dst_cbt + p.dst_cb_off + 2 * cg) * nvox + (size_t)zs0 * plane + (size_t)(y0 + yy) * p.X + (x0 + xx)) * 8;
+      float s1[16], s2[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+      int prev_slot = -1;
+      for (int zo = 0; zo < zsv; ++zo) {
+        const uint32_t g = gz + (uint32_t)zo;
+        const uint32_t slot = (g & (R - 1));
+        const long long eq = clock64();
+        mbar_wait(smem_u32(&hdr->z_full[slot]), (g >> 4) & 1u);
+        tc_fence_after();
+        e_wait += clock64() - eq;
+        const uint32_t taddr = lane_base + slot * (uint32_t)p.NT;
+        uint32_t ra[16];
+        tmem_ld16_issue(taddr, ra);
+        // the previous plane's re-zeroing store has long completed: hand its slot back now (keeps wait::st off the
+        // critical path of that plane)
+        if (prev_slot >= 0) {
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&hdr->z_empty[prev_slot]));
+        }
+        tmem_ld_wait16(ra);
+        float va[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) va[i] = __uint_as_float(ra[i]);
+        tmem_st16_zero(taddr);
+        prev_slot = (int)slot;
+        if (ok) {
+          if (want_stats) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { s1[i] += va[i]; s2[i] = fmaf(va[i], va[i], s2[i]); }
+          }
+          __nv_bfloat16* o = row + (size_t)zo * plane * 8;
+          *reinterpret_cast<uint4*>(o) = pack8_bf16(va);
+          *reinterpret_cast<uint4*>(o + nvox * 8) = pack8_bf16(va + 8);
+        }
+      }
+      if (prev_slot >= 0) {
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&hdr->z_empty[prev_slot]));
+      }
+      gz += (uint32_t)zsv;
+      if (want_stats) {
+        float r[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { r[i] = s1[i]; r[16 + i] = s2[i]; }
+#pragma unroll
+        for (int off = 16, n = 16; off > 0; off >>= 1, n >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            const float send = up ? r[i] : r[i + n];
+            const float keep = up ? r[i + n] : r[i];
+            r[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        hdr->red[w4][cg * 32 + lane] = r[0];
+        named_bar_sync(1, kRollThreads - 64);
+        if (w4 == 0) {   // one warp per column group: lane l<16 = sum of channel l, l>=16 = sum of squares
+          const float tot = hdr->red[0][cg * 32 + lane] + hdr->red[1][cg * 32 + lane] + hdr->red[2][cg * 32 + lane] +
+                            hdr->red[3][cg * 32 + lane];
+          const int ch = cg * 16 + (lane & 15);
+          float* dstp = p.stats + (((size_t)img * items_per_img + item_in_img) * p.NT + ch) * 2 + (lane >> 4);
+          *dstp = tot;
+        }
+        named_bar_sync(1, kRollThreads - 64);   // red is reused by the next item
+      }
+    }
+    if (p.dbg && warp == 2 && lane == 0) {
+      long long* d = p.dbg + (size_t)blockIdx.x * 8;
+      d[5] = clock64() - e_begin; d[6] = e_wait;
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -714,14 +1046,21 @@ static int plan_conv(const mmseg_conv_args* a, ConvPlan* out) {
   // k=3: rows of one padded plane up to the last needed voxel; k=1: every voxel of the TX x TY x TZ tile (one stage)
   const int flat = a->ksize == 1 ? a->TX * a->TY * a->TZ : (a->TY - 1) * k.PX + a->TX;
   k.mt = (flat + 127) / 128;
-  const int n_acc = a->ksize == 1 ? k.mt : k.mt * a->TZ;
+  k.roll = (a->flags & MMSEG_CONV_ROLL_Z) ? 1 : 0;
+  if (k.roll) {
+    if (a->ksize != 3 || a->out_mode != MMSEG_OUT_BLOCKED_BF16 || a->n_ntiles != 1 || a->NT != 32 || a->dst_lo_off != 0 || a->bias)
+      return fail(MMSEG_ERR_UNSUPPORTED, "conv3d: rolling-z needs ksize 3, NT = C_out = 32, blocked bf16 output, no bias");
+    if (k.mt != 1) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: rolling-z needs one M tile per plane (got %d)", k.mt);
+  }
+  const int n_acc = k.roll ? 512 / a->NT : (a->ksize == 1 ? k.mt : k.mt * a->TZ);
   if (a->ksize == 1 && a->TZ > 256) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: TZ=%d > 256 (TMA box)", a->TZ);
   if (k.mt > kMaxMT) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: %d M tiles per plane > %d", k.mt, kMaxMT);
   if (a->ksize == 3 && 3 * a->NT > 256) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: NT=%d > 80 with ksize 3 (folded MMA N = 3*NT <= 256)", a->NT);
   const int cols = n_acc * a->NT;
   if (cols > 512) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: %d TMEM columns > 512", cols);
   // two accumulator sets when they fit: the epilogue of one tile overlaps the MMAs of the next
-  k.acc_bufs = (2 * cols <= 512) ? 2 : 1;
+  k.acc_bufs = (k.roll || 2 * cols > 512) ? 1 : 2;
+  k.R = k.roll ? 16 : 0;
   k.buf_cols = (uint32_t)cols;
   uint32_t tc = 32;
   while ((int)tc < cols * k.acc_bufs) tc <<= 1;
@@ -740,6 +1079,11 @@ static int plan_conv(const mmseg_conv_args* a, ConvPlan* out) {
   // no per-chunk weight barrier, and the MMA warp can issue all (chunk, plane) items of a tile as one group)
   k.w_resident = a->ksize == 1 && (uint32_t)a->n_kchunks * round_up(k.w_bytes, 128) <= 64u * 1024u;
   k.w_stages = a->ksize == 1 ? (k.w_resident && a->n_kchunks > 8 ? a->n_kchunks : 8) : 2;
+  if (k.roll) {   // every K chunk's 27-tap weights resident
+    k.w_resident = 1;
+    k.w_stages = a->n_kchunks;
+    static_assert(kRollHeaderBytes == kHeaderBytes, "roll header shares the offset arithmetic");
+  }
   k.a_off = k.w_off + k.w_stages * round_up(k.w_bytes, 128);
   uint32_t total = k.a_off + a->stages * k.stage_bytes + round_up(overflow, 128) + 128 /*align slack*/;
   // two CTAs share an SM only when both fit in TMEM: a CTA that needs more than 256 columns asks for more than half of
@@ -814,12 +1158,23 @@ extern "C" int mmseg_conv3d_fwd(const mmseg_conv_args* a, void* stream) {
       }
     attr_set = true;
   }
-  // persistent CTAs: about one per SM in total, each sweeping its share of the voxel tiles of one N tile
   static int n_sms = 0;
   if (n_sms == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sms <= 0) n_sms = 148;
   }
+  if (k.roll) {
+    static bool roll_attr = false;
+    if (!roll_attr) {
+      cudaError_t e = cudaFuncSetAttribute(conv3d_roll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return fail(MMSEG_ERR_CUDA, "conv3d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      roll_attr = true;
+    }
+    const int n_ctas = k.n_tiles < n_sms ? k.n_tiles : n_sms;
+    conv3d_roll_kernel<<<n_ctas, kRollThreads, pl.smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tm, k);
+    return check_launch("conv3d_roll_kernel");
+  }
+  // persistent CTAs: about one per SM in total, each sweeping its share of the voxel tiles of one N tile
   int ctas = n_sms / k.n_ntiles;
   if (ctas < 1) ctas = 1;
   if (ctas > k.n_tiles) ctas = k.n_tiles;

@@ -49,6 +49,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (try_wait may suspend the thread for a hardware time slice; test_wait never does).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a pipeline bug must surface as a trapped kernel (CUDA error), never as a hung GPU.
 #ifndef MMSEG_WATCHDOG_NS
 #define MMSEG_WATCHDOG_NS 4000000000ull

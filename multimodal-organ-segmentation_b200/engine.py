@@ -53,7 +53,7 @@ class ConvRunner:
         cout = pw.n_out
         raw_f32 = self.split
         raw = self.ws.get("raw", n * cout * Z * Y * X, torch.float32 if raw_f32 else torch.bfloat16)
-        tile = K.plan_conv(X, Y, Z, n, pw.n_kchunks, pw.n_out, pw.ksize, pw.NT)
+        tile = K.plan_conv_norm((X, Y, Z), n, pw, raw_f32)
         stats = self.ws.get("stats", n * tile.tiles_per_img * cout * 2, torch.float32)
         mr = self.ws.get("mean_rstd", n * cout * 2, torch.float32)
         K.conv3d(src, pw, a_cb, raw, _lib.OUT_BLOCKED_F32 if raw_f32 else _lib.OUT_BLOCKED_BF16, stats=stats,

@@ -40,6 +40,7 @@ class ConvTile:
     smem_bytes: int
     tiles_per_img: int
     est_cycles: float
+    roll: bool = False       # rolling-z kernel: TZ is the z-segment length, tiles_per_img counts (x, y, z-segment) items
 
 
 def tmem_cols(mt: int, TZ: int, NT: int) -> int:
@@ -155,3 +156,57 @@ def plan_conv(X: int, Y: int, Z: int, n_img: int, n_kchunks: int, n_out: int, ks
     if best is None:
         raise ValueError(f"no valid conv tiling for X={X} Y={Y} Z={Z} n_out={n_out} ksize={ksize}")
     return best[1]
+
+
+ROLL_FLAG = 16               # MMSEG_CONV_ROLL_Z
+
+
+def roll_smem_bytes(TX: int, TY: int, NT: int, n_kchunks: int, stages: int) -> Optional[int]:
+    """Shared memory of conv3d_roll_kernel (all K-chunk weights resident), or None when the tiling is invalid."""
+    PX, PY = TX + 2, TY + 2
+    if PX > 128 or PY > 256 or _cdiv((TY - 1) * PX + TX, 128) != 1 or NT != 32:
+        return None
+    plane = PX * PY * 16
+    stage = _round_up(2 * plane, 128)
+    overflow = max((128 + 2 * PX + 2) * 16 - plane, 0)
+    total = HEADER_BYTES + n_kchunks * _round_up(27 * NT * 32, 128) + stages * stage + _round_up(overflow, 128) + 128
+    return total if total <= SMEM_LIMIT else None
+
+
+@lru_cache(maxsize=None)
+def plan_roll(X: int, Y: int, Z: int, n_img: int, n_kchunks: int, n_out: int) -> Optional[ConvTile]:
+    """Rolling-z plan for a k=3, C_out = 32 layer (None when not eligible).  Cost model: an N = 96 MMA is
+    shared-memory-bound at ~56 clk (measured), a partial-N boundary MMA ~51; one item = one z segment of a column."""
+    if n_out != 32:
+        return None
+    best = None
+    nx_min = 1
+    while _cdiv(X, nx_min) + 2 > 128:
+        nx_min += 1
+    for nx in range(nx_min, min(nx_min + 6, X) + 1):
+        TX = _cdiv(X, nx)
+        PX = TX + 2
+        TY = 0
+        while TY < Y and (TY * PX + TX) <= 128:   # largest TY with (TY-1)*PX + TX <= 128
+            TY += 1
+        if TY < 1:
+            continue
+        stages = 0
+        for st in (24, 20, 16, 12, 10, 8):
+            sb = roll_smem_bytes(TX, TY, 32, n_kchunks, st)
+            if sb is not None:
+                stages = st
+                break
+        if stages < max(8, 2 * n_kchunks):
+            continue
+        tx_n, ty_n = _cdiv(X, TX), _cdiv(Y, TY)
+        for nseg in range(1, max(1, Z // 8) + 1):
+            ZS = _cdiv(Z, nseg)
+            nseg_eff = _cdiv(Z, ZS)
+            items = tx_n * ty_n * nseg_eff * n_img
+            per_item = n_kchunks * 9 * ((ZS - 2) * 56.0 + 4 * 51.0) + ZS * 9 * 3.5 * n_kchunks + 1500.0
+            est = _cdiv(items, NUM_SMS) * per_item + 4000.0
+            cand = (est, -TX * TY)
+            if best is None or cand < best[0]:
+                best = (cand, ConvTile(TX, TY, ZS, 32, 1, stages, 1, sb, tx_n * ty_n * nseg_eff, est, True))
+    return None if best is None else best[1]

@@ -41,7 +41,7 @@ def _make_tile(pw, TX, TY, TZ, ks, stages=3):
     return ConvTile(TX, TY, TZ, pw.NT, pw.n_ntiles, stages, mt, 0, 0, 0.0)
 
 
-def conv_case(cin, cout, shape, n_img=1, tile=None, split=False, flags=0, ks=3, seed=0, name="conv"):
+def conv_case(cin, cout, shape, n_img=1, tile=None, split=False, flags=0, ks=3, seed=0, name="conv", roll=None):
     """raw conv output (blocked) + InstanceNorm partial statistics vs F.conv3d in fp64."""
     torch.manual_seed(seed)
     Z, Y, X = shape
@@ -54,6 +54,12 @@ def conv_case(cin, cout, shape, n_img=1, tile=None, split=False, flags=0, ks=3, 
     K.pack_ncdhw(x, src)
     a_cb = K.a_chunk_table(src, [0], [cin], split)
     t = plan_conv(X, Y, Z, n_img, pw.n_kchunks, pw.n_out, ks, pw.NT) if tile is None else _make_tile(pw, *tile, ks)
+    if roll is not None:   # rolling-z kernel: roll = "auto" (planner) or (TX, TY, z-segment length, stages)
+        from mmseg_b200.tiling import plan_roll
+        t = plan_roll(X, Y, Z, n_img, pw.n_kchunks, pw.n_out) if roll == "auto" else \
+            ConvTile(roll[0], roll[1], roll[2], 32, 1, roll[3], 1, 0, 0, 0.0, True)
+        assert t is not None and t.roll
+        name = f"{name}-roll{(t.TX, t.TY, t.TZ, t.stages)}"
     raw = torch.full((n_img, pw.n_out // 8, Z, Y, X, 8), float("nan"), device=DEV,
                      dtype=torch.float32 if split else torch.bfloat16)
     tiles_per_img = ((X + t.TX - 1) // t.TX) * ((Y + t.TY - 1) // t.TY) * ((Z + t.TZ - 1) // t.TZ)

@@ -38,6 +38,19 @@ def test_conv3d_tcgen05(args, kw):
 
 
 @pytest.mark.parametrize("args,kw", [
+    ((16, 32, (20, 12, 30)), dict(roll="auto")),
+    ((2, 32, (9, 11, 27)), dict(roll="auto", n_img=3)),
+    ((32, 32, (40, 7, 26)), dict(n_img=2, roll=(13, 4, 17, 8))),     # 3 segments (17, 17, 6), ring wraps, 2 K chunks
+    ((64, 32, (19, 6, 20)), dict(roll=(20, 5, 7, 12))),              # 4 K chunks, segments 7, 7, 5
+    ((16, 32, (1, 5, 8)), dict(roll=(8, 5, 4, 8))),                  # a single output plane
+    ((32, 32, (37, 5, 24)), dict(roll=(24, 5, 37, 10), n_img=2)),    # one long segment: 37 planes through a 16-slot ring
+])
+def test_conv3d_rolling_z(args, kw):
+    """conv3d_roll_kernel (TMEM ring of output planes) vs F.conv3d, raw output and InstanceNorm partial sums."""
+    _c().conv_case(*args, **kw)
+
+
+@pytest.mark.parametrize("args,kw", [
     ((16, 32, (8, 12, 16)), {}),
     ((2, 32, (8, 12, 16)), dict(split=True)),
     ((32, 64, (8, 8, 16)), dict(n_img=2, slope=0.2, split=True)),

@@ -13,7 +13,7 @@ src = Blocked(n, (cin + 15) // 16 * 16, S, S, S, False, "cuda"); src.t.normal_()
 flags = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 raw = torch.empty((n, cout // 8, S, S, S, 8), dtype=torch.bfloat16, device="cuda")
 a_cb = K.a_chunk_table(src, [0], [cin], False)
-tile = K.plan_conv(S, S, S, n, pw.n_kchunks, pw.n_out, 3, pw.NT)
+tile = K.plan_conv_norm((S, S, S), n, pw, False)
 stats = torch.zeros(n * tile.tiles_per_img * cout * 2, device="cuda")
 for _ in range(3):
     K.conv3d(src, pw, a_cb, raw, _lib.OUT_BLOCKED_BF16, stats=stats, dst_cbt=cout // 8, tile=tile, flags=flags)
@@ -26,8 +26,11 @@ for _ in range(5):
     e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1) * 1e3)
 us = sorted(ts)[2]
-print(f"flags={flags} cin{cin} cout{cout} S{S} n{n} tile {tile.TX,tile.TY,tile.TZ,tile.NT,tile.stages}: {us:.0f} us  {2.0*n*S**3*cin*cout*27/us/1e6:.0f} TF/s")
+print(("roll " if tile.roll else "") + f"flags={flags} cin{cin} cout{cout} S{S} n{n} tile {tile.TX,tile.TY,tile.TZ,tile.NT,tile.stages}: {us:.0f} us  {2.0*n*S**3*cin*cout*27/us/1e6:.0f} TF/s")
 if flags & 2:   # per-CTA counters written over the stats buffer: [0] MMA warp total, [5] epilogue total, [6] epilogue waiting
     torch.cuda.synchronize()
     d = stats.view(torch.int64)[:148 * 8].view(148, 8).double().mean(0).tolist()
+    if tile.roll:
+        print(f"  roll: mma_total {d[0]:.0f} clk, stages {d[3]:.0f} ({d[0] / max(d[3], 1):.0f} clk/stage), a_full not ready {d[1]:.0f}, "
+              f"z_empty not ready {d[2]:.0f}; epi_total {d[5]:.0f}, epi waiting z_full {d[6]:.0f}")
     print(f"  clk: mma_total {d[0]:.0f} (a_full wait {d[1]:.0f}, descriptors {d[2]:.0f}, issue {d[3]:.0f}, acc_empty wait {d[4]:.0f}, w_full wait {d[7]:.0f})  epi_total {d[5]:.0f}  epi_wait_acc_full {d[6]:.0f}")

@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(128, 1) bench(Exp e, int iters, long long* out
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(e.N >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t a0 = smem_u32(base), b0 = smem_u32(base) + 128 * 1024;
     uint32_t ph = 0;
+    uint32_t sink = threadIdx.x;
     for (int rep = 0; rep < 2; ++rep) {   // rep 0 = warm-up
       long long t0 = clock64();
       for (int i = 0; i < iters; ++i) {
@@ -76,6 +77,18 @@ __global__ void __launch_bounds__(128, 1) bench(Exp e, int iters, long long* out
           const uint32_t bb = e.a_stride == 1 ? b0 + (uint32_t)tap * e.k_adv : b0 + (uint32_t)(j & 3) * e.k_adv;
           umma(tm + (uint32_t)((j % e.n_acc) * e.N), mkdesc(aa, e.a_lbo, e.a_sbo, e.layout), mkdesc(bb, e.b_lbo, e.b_sbo, e.layout), idesc, 1u);
           if (CE > 0 && ((j + 1) % (CE > 0 ? CE : 1)) == 0) commit(smem_u32(&scratch_bar));
+          if (WE <= -3000) {                     // (-WE - 3000) dependent IMADs once per 16 MMAs: how far can the issuing
+                                                 // thread run ahead of the tensor pipe (queue depth)?
+            if (j == 15) {
+#pragma unroll
+              for (int k = 0; k < -WE - 3000; ++k) asm volatile("mad.lo.u32 %0, %0, 3, 1;" : "+r"(sink));
+            }
+          } else
+          if (WE <= -1000) {                     // (-WE - 1000) DEPENDENT integer ops after EVERY MMA (no clock reads:
+                                                 // CS2R serialises against the tensor pipe): how much issue slack is there?
+#pragma unroll
+            for (int k = 0; k < -WE - 1000; ++k) asm volatile("mad.lo.u32 %0, %0, 3, 1;" : "+r"(sink));
+          } else
           if (WE < 0 && ((j + 1) % 8) == 0) {   // spin -WE cycles in the issuing thread every 8 MMAs
             const long long ts = clock64();
             while (clock64() - ts < (long long)(-WE)) {}
@@ -90,7 +103,7 @@ __global__ void __launch_bounds__(128, 1) bench(Exp e, int iters, long long* out
       while (!mbar_try(smem_u32(&bar), ph)) {}
       ph ^= 1;
       long long t1 = clock64();
-      if (rep == 1) out[blockIdx.x] = t1 - t0;
+      if (rep == 1) out[blockIdx.x] = t1 - t0 + (sink == 0x12345u ? 1 : 0);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -114,6 +127,14 @@ int main() {
   cudaFuncSetAttribute(bench<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(bench<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(bench<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<0, -1010>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<0, -1020>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<0, -1030>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<0, -1040>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<0, -1060>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<0, -3050>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<0, -3100>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<0, -3200>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int iters = 256;
   struct Named { const char* name; Exp e; } exps[] = {
       // how deep is the MMA queue?  the issuing thread spins D cycles after every 8 MMAs (8 x 56 = 448 cycles of work):
@@ -125,6 +146,14 @@ int main() {
       {"none N=64 commit every 4 MMAs", {0, 17248, 128, 1536, 128, 64, 2048 + 16, 0, 4, 4}},
       {"none N=64 commit every 2 MMAs", {0, 17248, 128, 1536, 128, 64, 2048 + 16, 0, 4, 2}},
       {"none N=64 commit every MMA", {0, 17248, 128, 1536, 128, 64, 2048 + 16, 0, 4, 1}},
+      {"none N=96 10 dependent IMADs after every MMA", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 2010}},
+      {"none N=96 20 dependent IMADs after every MMA", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 2020}},
+      {"none N=96 30 dependent IMADs after every MMA", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 2030}},
+      {"none N=96 40 dependent IMADs after every MMA", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 2040}},
+      {"none N=96 60 dependent IMADs after every MMA", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 2060}},
+      {"none N=96 50 dependent IMADs (~200 clk) per 16 MMAs", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 4050}},
+      {"none N=96 100 dependent IMADs (~400 clk) per 16 MMAs", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 4100}},
+      {"none N=96 200 dependent IMADs (~800 clk) per 16 MMAs", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 4200}},
       {"none N=96 spin 100 cycles every 8 MMAs", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 1100}},
       {"none N=96 spin 200 cycles every 8 MMAs", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 1200}},
       {"none N=96 spin 300 cycles every 8 MMAs", {0, 17248, 128, 1536, 128, 96, 2048 + 16, 0, 5, 1300}},
@@ -141,6 +170,14 @@ int main() {
       case 108: bench<0, 8><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
       case 104: bench<0, 4><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
       case 116: bench<0, 16><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 2010: bench<0, -1010><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 2020: bench<0, -1020><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 2030: bench<0, -1030><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 2040: bench<0, -1040><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 2060: bench<0, -1060><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 4050: bench<0, -3050><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 4100: bench<0, -3100><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
+      case 4200: bench<0, -3200><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
       case 1100: bench<0, -100><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
       case 1200: bench<0, -200><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
       case 1300: bench<0, -300><<<148, 128, 200 * 1024>>>(x.e, iters, d); break;
