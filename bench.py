@@ -328,9 +328,9 @@ def run_ours(args):
     tj = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
     if os.path.exists(tj):
         traffic = json.load(open(tj)).get("dram_bytes_per_launch_avg")
-    roofline = {"bound": "tensor", "kernel": "conv3d_tc_kernel", "achieved": conv_tf, "peak": tf_peak, "unit": "TFLOP/s",
+    roofline = {"bound": "tensor", "kernel": "conv3d_tc_kernel + conv3d_roll_kernel", "achieved": conv_tf, "peak": tf_peak, "unit": "TFLOP/s",
                 "frac": conv_tf / tf_peak, "traffic": traffic,
-                "traffic_note": "average DRAM bytes per conv launch (ncu --set full, same 8-window forward; profiles/r01_final_ncu_conv_launches.csv)",
+                "traffic_note": "average DRAM bytes per conv launch (ncu --set full, same 8-window forward; profiles/r01_v5_ncu_conv_launches.csv)",
                 "peak_source": peak_src,
                 "launches": conv["n"] // 3, "avg_launch_ms": conv["ms"] / conv["n"],
                 "share_of_step": conv["ms"] / total_ms,

@@ -286,6 +286,10 @@ int mmseg_gate_mlp(const float* pooled, const float* w1, const float* b1, const 
 int mmseg_modality_combine(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_lo_off, int32_t M, int32_t cb,
                            int64_t voxels, const float* weights /* [n_img][M] or NULL */, float uniform_weight,
                            void* dst, int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, void* stream);
+/* F.interpolate(x, size=(Zo,Yo,Xo), mode="trilinear", align_corners=True) on fp32 [n_planes = N*C][Zi][Yi][Xi]:
+ * DeepSupervisionHead's resize of coarse-scale logits (src/models/heads/segmentation.py:108-113). */
+int mmseg_trilinear_resize(const float* src, int32_t n_planes, int32_t Zi, int32_t Yi, int32_t Xi, float* dst, int32_t Zo,
+                           int32_t Yo, int32_t Xo, void* stream);
 /* out_conv / SegmentationHead k=1: nn.Conv3d(C, num_classes, 1) (unet.py:163,199; dual_encoder.py:118,164) on the CUDA
  * cores at HBM speed: src blocked bf16 (channels cb_off*8 .. +cin, optional lo plane lo_off blocks away, parity mode),
  * weight fp32 [cout][cin], bias fp32 [cout] or NULL, dst fp32 NCDHW [n_img][cout][voxels].  cin % 8 == 0, cout <= 16. */

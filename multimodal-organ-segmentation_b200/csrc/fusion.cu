@@ -309,9 +309,47 @@ __global__ void __launch_bounds__(256) conv1x1_logits_kernel(const __nv_bfloat16
   }
 }
 
+// ------------------------------------------------------------------------------------------------ trilinear resize
+// F.interpolate(x, size, mode="trilinear", align_corners=True) on NCDHW fp32 (DeepSupervisionHead, segmentation.py:
+// 108-113; the logits of a coarse scale brought to the target size).  Same index arithmetic as ATen's
+// upsample_trilinear3d: src = dst * (in-1)/(out-1) in fp32, i0 = (int)src, lambda1 = src - i0, i1 = i0 + (i0 < in-1).
+__global__ void __launch_bounds__(256) trilinear_resize_kernel(const float* __restrict__ src, int Zi, int Yi, int Xi,
+                                                              float* __restrict__ dst, int Zo, int Yo, int Xo,
+                                                              float sz, float sy, float sx) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y % Yo, z = blockIdx.y / Yo;
+  const size_t nc = blockIdx.z;
+  if (x >= Xo) return;
+  const float fz = sz * z, fy = sy * y, fx = sx * x;
+  const int z0 = (int)fz, y0 = (int)fy, x0 = (int)fx;
+  const int zp = z0 < Zi - 1 ? 1 : 0, yp = y0 < Yi - 1 ? 1 : 0, xp = x0 < Xi - 1 ? 1 : 0;
+  const float z1l = fz - z0, y1l = fy - y0, x1l = fx - x0;
+  const float z0l = 1.f - z1l, y0l = 1.f - y1l, x0l = 1.f - x1l;
+  const float* p = src + ((nc * Zi + z0) * Yi + y0) * (size_t)Xi + x0;
+  const size_t sY = (size_t)Xi * yp, sZ = (size_t)Yi * Xi * zp;
+  const float v =
+      z0l * (y0l * (x0l * p[0] + x1l * p[xp]) + y1l * (x0l * p[sY] + x1l * p[sY + xp])) +
+      z1l * (y0l * (x0l * p[sZ] + x1l * p[sZ + xp]) + y1l * (x0l * p[sZ + sY] + x1l * p[sZ + sY + xp]));
+  dst[((nc * Zo + z) * Yo + y) * (size_t)Xo + x] = v;
+}
+
 }  // namespace mmseg
 
 using namespace mmseg;
+
+extern "C" int mmseg_trilinear_resize(const float* src, int32_t n_planes, int32_t Zi, int32_t Yi, int32_t Xi, float* dst,
+                                      int32_t Zo, int32_t Yo, int32_t Xo, void* stream) {
+  if (!src || !dst || n_planes < 1 || Zi < 1 || Yi < 1 || Xi < 1 || Zo < 1 || Yo < 1 || Xo < 1)
+    return fail(MMSEG_ERR_INVALID_ARG, "trilinear_resize: bad arguments");
+  if (n_planes > 65535 || (int64_t)Zo * Yo > 2147483647LL) return fail(MMSEG_ERR_INVALID_ARG, "trilinear_resize: grid too large");
+  const float sz = Zo > 1 ? (float)(Zi - 1) / (float)(Zo - 1) : 0.f;
+  const float sy = Yo > 1 ? (float)(Yi - 1) / (float)(Yo - 1) : 0.f;
+  const float sx = Xo > 1 ? (float)(Xi - 1) / (float)(Xo - 1) : 0.f;
+  const int bx = Xo >= 256 ? 256 : (Xo >= 128 ? 128 : (Xo >= 64 ? 64 : 32));
+  dim3 grid((unsigned)((Xo + bx - 1) / bx), (unsigned)(Zo * Yo), (unsigned)n_planes);
+  trilinear_resize_kernel<<<grid, bx, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, Zi, Yi, Xi, dst, Zo, Yo, Xo, sz, sy, sx);
+  return check_launch("trilinear_resize_kernel");
+}
 
 extern "C" int mmseg_conv1x1_logits(const void* src, int32_t n_img, int32_t src_cbt, int32_t cb_off, int32_t lo_off,
                                     int32_t cin, int64_t voxels, const float* weight, const float* bias, int32_t cout,

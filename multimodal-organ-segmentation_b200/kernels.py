@@ -518,6 +518,17 @@ def add_stats(a: Blocked, a_c0: int, b: Blocked, b_c0: int, channels: int):
     return y, partial, n_chunks
 
 
+def trilinear_resize(x: Tensor, size: Sequence[int]) -> Tensor:
+    """F.interpolate(x, size, mode='trilinear', align_corners=True) for NCDHW fp32 (DeepSupervisionHead)."""
+    assert x.dim() == 5 and x.dtype == torch.float32 and x.is_cuda
+    x = x.contiguous()
+    n, c, Zi, Yi, Xi = x.shape
+    Zo, Yo, Xo = (int(v) for v in size)
+    out = torch.empty((n, c, Zo, Yo, Xo), dtype=torch.float32, device=x.device)
+    _call("mmseg_trilinear_resize", _ptr(x), n * c, Zi, Yi, Xi, _ptr(out), Zo, Yo, Xo, _stream())
+    return out
+
+
 def conv1x1_logits(src: Blocked, c0: int, cin: int, weight: Tensor, bias: Optional[Tensor], out: Tensor) -> None:
     """nn.Conv3d(cin, classes, 1) -> fp32 NCDHW logits on the CUDA cores (HBM-bound; fp32 weights, hi + lo inputs in
     parity mode).  weight: the module's [classes, cin, 1, 1, 1] parameter (read in place, no packed copy)."""

@@ -120,7 +120,22 @@ def main():
     out["dice_metric"] = {"pred": [p1, p2], "target": [t1, t2],
                           "dice": float(r["dice"]), "dice_per_class": [float(v) for v in r["dice_per_class"]]}
 
+    # ---- DeepSupervisionHead (heads/segmentation.py:62-115): 3 scales, trilinear align_corners=True resize to the finest
+    from src.models.heads.segmentation import DeepSupervisionHead
+    torch.manual_seed(21)
+    ds = DeepSupervisionHead([16, 32, 64], 5).eval()
+    g2 = torch.Generator().manual_seed(22)
+    feats = [torch.randn(2, 16, 12, 10, 14, generator=g2), torch.randn(2, 32, 6, 5, 7, generator=g2),
+             torch.randn(2, 64, 3, 3, 4, generator=g2)]
+    with torch.no_grad():
+        outs = ds(feats, target_size=(12, 10, 14))
+    out["deep_supervision"] = {"state_dict": ds.state_dict(), "features": feats, "target_size": (12, 10, 14),
+                               "outputs": [o.clone() for o in outs]}
+
+    only = set(sys.argv[1:])      # python make_golden.py [name ...]: write only these fixtures (all are seeded)
     for k, v in out.items():
+        if only and k not in only:
+            continue
         torch.save(v, os.path.join(HERE, k + ".pt"))
         print(k, f"{os.path.getsize(os.path.join(HERE, k + '.pt')) / 1024:.0f} KiB")
 

@@ -162,6 +162,33 @@ def logits_case(cin, k, shape, n_img=2, split=False):
     return err
 
 
+def logits_cuda_core_case(cin, k, shape, n_img=2, split=False, c0=0):
+    """conv1x1_logits_kernel (CUDA cores, fp32 weights) vs F.conv3d in fp64; channels [c0, c0+cin) of a wider buffer."""
+    torch.manual_seed(11)
+    Z, Y, X = shape
+    ctot = c0 + cin
+    x = torch.randn(n_img, ctot, Z, Y, X, device=DEV)
+    w = torch.randn(k, cin, 1, 1, 1, device=DEV) * (1.0 / cin ** 0.5)     # fp32 weights are used as they are
+    b = torch.randn(k, device=DEV)
+    if not split:
+        x = _bf(x)
+    src = Blocked(n_img, (ctot + 15) // 16 * 16, Z, Y, X, split, DEV)
+    K.pack_ncdhw(x, src)
+    out = torch.full((n_img, k, Z, Y, X), float("nan"), device=DEV)
+    K.conv1x1_logits(src, c0, cin, w, b, out)
+    torch.cuda.synchronize()
+    ref = F.conv3d(x[:, c0:].double(), w.double(), b.double()).float()
+    tol = 2e-5 if split else 1e-5          # bf16 mode: the inputs ARE bf16 values, the arithmetic is fp32 -> tight either way
+    err = _report(f"logits cuda-core cin={cin} k={k} {shape} split={split} c0={c0}", out, ref, tol)
+    assert torch.isfinite(out).all()
+    assert err <= tol * max(1.0, ref.abs().max().item())
+    out2 = torch.empty_like(out)
+    K.conv1x1_logits(src, c0, cin, w, None, out2)
+    torch.cuda.synchronize()
+    assert (out2 + b.view(1, -1, 1, 1, 1) - out).abs().max().item() < 1e-5
+    return err
+
+
 def pack_roundtrip_case():
     torch.manual_seed(6)
     x = torch.randn(2, 5, 4, 6, 10, device=DEV)
@@ -626,6 +653,36 @@ def late_early_head_case():
         got = h.to(DEV)(x.to(DEV)).cpu()
     assert (got - ref).abs().max().item() < 2e-2
     print("[EarlyFusion / SegmentationHead] ok", flush=True)
+
+
+def trilinear_case(shape_in, shape_out, nc=(2, 3)):
+    """mmseg_trilinear_resize vs F.interpolate(mode='trilinear', align_corners=True) on the CPU."""
+    torch.manual_seed(12)
+    x = torch.randn(*nc, *shape_in)
+    ref = F.interpolate(x, size=shape_out, mode="trilinear", align_corners=True)
+    got = K.trilinear_resize(x.to(DEV), shape_out).cpu()
+    err = _report(f"trilinear {shape_in}->{shape_out}", got, ref, 2e-6)
+    assert got.shape == ref.shape and err <= 2e-6 * max(1.0, ref.abs().max().item())
+
+
+def deep_supervision_golden_case():
+    """DeepSupervisionHead vs the reference's own outputs (tests/golden/deep_supervision.pt)."""
+    from mmseg_b200.src.models.heads import DeepSupervisionHead
+    g = _gold("deep_supervision")
+    m = DeepSupervisionHead([16, 32, 64], 5).eval()
+    m.load_state_dict(g["state_dict"], strict=True)
+    m = m.to(DEV)
+    with torch.no_grad():
+        outs = m([f.to(DEV) for f in g["features"]], target_size=tuple(g["target_size"]))
+    assert len(outs) == len(g["outputs"])
+    for i, (o, r) in enumerate(zip(outs, g["outputs"])):
+        assert tuple(o.shape) == tuple(r.shape)
+        err = _report(f"deep supervision scale {i}", o.cpu(), r, 2e-2)      # inputs rounded to bf16 by the blocked pack
+        assert err <= 2e-2 * max(1.0, r.abs().max().item())
+    # without target_size nothing is resized
+    with torch.no_grad():
+        raw = m([f.to(DEV) for f in g["features"]])
+    assert [tuple(o.shape[2:]) for o in raw] == [tuple(f.shape[2:]) for f in g["features"]]
 
 
 def focal_tversky_golden_case():

@@ -69,6 +69,26 @@ def test_logits_1x1(split):
     _c().logits_case(32, 8, (6, 7, 20), split=split)
 
 
+@pytest.mark.parametrize("args,kw", [
+    ((32, 8, (6, 7, 20)), {}),
+    ((32, 8, (5, 3, 7)), dict(split=True)),              # 105 voxels: ragged 4-voxel groups
+    ((16, 3, (4, 5, 9)), dict(n_img=1)),                 # COUT template 4
+    ((64, 14, (3, 4, 10)), dict(split=True, c0=16)),     # COUT template 16, channel offset inside a wider buffer
+])
+def test_logits_1x1_cuda_cores(args, kw):
+    _c().logits_cuda_core_case(*args, **kw)
+
+
+@pytest.mark.parametrize("a,b", [((3, 4, 5), (6, 8, 10)), ((6, 5, 7), (12, 10, 14)), ((4, 4, 4), (4, 9, 1)),
+                                 ((1, 3, 300), (5, 2, 333))])
+def test_trilinear_resize_align_corners(a, b):
+    _c().trilinear_case(a, b)
+
+
+def test_deep_supervision_head_golden():
+    _c().deep_supervision_golden_case()
+
+
 def test_pack_unpack_roundtrip():
     _c().pack_roundtrip_case()
 
