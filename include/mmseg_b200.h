@@ -142,6 +142,7 @@ int mmseg_instnorm_finalize(const float* stats_partial, int32_t n_img, int32_t t
  * y = act((x - mean) * rstd) over a blocked tensor, act = ReLU (slope 0) / LeakyReLU(slope); writes bf16 (hi[, lo]).
  * Replaces nn.InstanceNorm3d apply + nn.ReLU (unet.py:45,55-59).  src_is_f32 selects the raw dtype.
  * pooled (optional): also writes MaxPool3d(2) (unet.py:73,77) of y into a second blocked buffer.
+ * The struct is zero-initialised by callers; the trailing fused-finalize fields default to "off".
  */
 typedef struct {
   const void* src;         /* raw conv output, blocked [n_img*cb][Z][Y][X][8] bf16 or fp32                 */
@@ -153,6 +154,13 @@ typedef struct {
   int32_t dst_cbt, dst_cb_off, dst_lo_off;
   int32_t pool_cbt, pool_cb_off, pool_lo_off;
   float slope;
+  /* fused statistics finalize (optional, replaces the mmseg_instnorm_finalize launch): when stats_partial is set,
+   * every block derives mean / rstd of its 8 channels from the conv epilogue's partials (fixed order, fp64) and
+   * mean_rstd is not read; mean_rstd_out (optional) receives the table for later consumers (backward). */
+  const float* stats_partial; /* [n_img][tiles_per_img][cb*8][2] or NULL                                   */
+  float* mean_rstd_out;       /* [n_img][cb*8][2] or NULL                                                  */
+  int32_t tiles_per_img;
+  float eps;
 } mmseg_norm_args;
 int mmseg_instnorm_act_apply(const mmseg_norm_args* args, void* stream);
 

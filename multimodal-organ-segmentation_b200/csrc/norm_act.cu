@@ -50,6 +50,11 @@ instnorm_finalize_kernel(const float* __restrict__ part, int n_img, int tiles, i
 struct NormK {
   const void* src;
   const float* mr;
+  const float* stats;   // optional: per-tile (sum, sum of squares) partials [n_img][tiles][C][2] -> finalized in the prologue
+  float* mr_out;        // optional: where block x == 0 of each row publishes the (mean, rstd) it derived
+  int tiles;
+  double inv_n;
+  float eps;
   __nv_bfloat16* dst;
   __nv_bfloat16* pooled;
   int n_img, cb, Z, Y, X;
@@ -100,18 +105,64 @@ __device__ __forceinline__ void store_act8(__nv_bfloat16* dst, size_t off, size_
   }
 }
 
+// mean / rstd of this block's 8 channels: read from the finalized table, or (stats != NULL) finalized HERE from the conv
+// epilogue's per-tile partials in a fixed order with fp64 accumulation — every block of a row derives bit-identical
+// values, and the 18 instnorm_finalize launches of a UNet3D forward (latency-bound, ~9 us each) disappear.  The partials
+// (<= 2 MB) are L2-resident; a block reads tiles x 64 B of them.
+__device__ __forceinline__ void block_mean_rstd(const NormK& k, int img, int c, float* mean, float* rstd) {
+  if (k.stats == nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 m = *reinterpret_cast<const float2*>(k.mr + ((size_t)img * k.cb * 8 + c * 8 + i) * 2);
+      mean[i] = m.x;
+      rstd[i] = m.y;
+    }
+    return;
+  }
+  __shared__ double sred[16][17];
+  __shared__ float smr[16];
+  const int C = k.cb * 8;
+  const int j = threadIdx.x & 15, r = threadIdx.x >> 4;   // value j = (channel i, {sum, sumsq}) x 16 row groups
+  const float* p = k.stats + ((size_t)img * k.tiles * C + (size_t)c * 8) * 2 + j;
+  double acc = 0.0;
+  int t = r;
+  for (; t + 7 * 16 < k.tiles; t += 8 * 16) {   // eight independent L2 loads in flight, summed in a fixed order
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (size_t)(t + u * 16) * C * 2);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += (double)v[u];
+  }
+  for (; t < k.tiles; t += 16) acc += (double)__ldg(p + (size_t)t * C * 2);
+  sred[r][j] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) { s1 += sred[g][2 * threadIdx.x]; s2 += sred[g][2 * threadIdx.x + 1]; }
+    const double m = s1 * k.inv_n;
+    double var = s2 * k.inv_n - m * m;
+    if (var < 0.0) var = 0.0;
+    const float mf = (float)m, rf = (float)(1.0 / sqrt(var + (double)k.eps));
+    smr[2 * threadIdx.x] = mf;
+    smr[2 * threadIdx.x + 1] = rf;
+    if (k.mr_out && blockIdx.x == 0) {
+      k.mr_out[((size_t)img * C + c * 8 + threadIdx.x) * 2] = mf;
+      k.mr_out[((size_t)img * C + c * 8 + threadIdx.x) * 2 + 1] = rf;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mean[i] = smr[2 * i]; rstd[i] = smr[2 * i + 1]; }
+}
+
 // grid: (chunks over voxels, n_img*cb).  One 8-channel vector per thread-iteration.
 template <bool F32>
 __global__ void __launch_bounds__(256) instnorm_apply_kernel(const NormK k) {
   const int blk = blockIdx.y;  // img*cb + c
   const int img = blk / k.cb, c = blk - img * k.cb;
   float mean[8], rstd[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float2 m = *reinterpret_cast<const float2*>(k.mr + ((size_t)img * k.cb * 8 + c * 8 + i) * 2);
-    mean[i] = m.x;
-    rstd[i] = m.y;
-  }
+  block_mean_rstd(k, img, c, mean, rstd);
   const size_t nvox = (size_t)k.Z * k.Y * k.X;
   const size_t src_base = (size_t)blk * nvox * 8;
   const size_t dst_base = (size_t)(img * k.dst_cbt + k.dst_cb_off + c) * nvox * 8;
@@ -146,12 +197,7 @@ __global__ void __launch_bounds__(256) instnorm_apply_pool_kernel(const NormK k)
   const int blk = blockIdx.y;
   const int img = blk / k.cb, c = blk - img * k.cb;
   float mean[8], rstd[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float2 m = *reinterpret_cast<const float2*>(k.mr + ((size_t)img * k.cb * 8 + c * 8 + i) * 2);
-    mean[i] = m.x;
-    rstd[i] = m.y;
-  }
+  block_mean_rstd(k, img, c, mean, rstd);
   const int Zh = k.Z / 2, Yh = k.Y / 2, Xh = k.X / 2;
   const size_t nvox = (size_t)k.Z * k.Y * k.X;
   const size_t ncell = (size_t)Zh * Yh * Xh;
@@ -257,11 +303,16 @@ extern "C" int mmseg_instnorm_finalize(const float* stats_partial, int32_t n_img
 }
 
 extern "C" int mmseg_instnorm_act_apply(const mmseg_norm_args* a, void* stream) {
-  if (!a || !a->src || !a->mean_rstd || !a->dst) return fail(MMSEG_ERR_INVALID_ARG, "instnorm_apply: null pointer");
+  if (!a || !a->src || !a->dst || (!a->mean_rstd && !a->stats_partial))
+    return fail(MMSEG_ERR_INVALID_ARG, "instnorm_apply: null pointer");
+  if (a->stats_partial && a->tiles_per_img < 1) return fail(MMSEG_ERR_INVALID_ARG, "instnorm_apply: tiles_per_img");
   if (a->n_img < 1 || a->cb < 1 || a->Z < 1 || a->Y < 1 || a->X < 1)
     return fail(MMSEG_ERR_INVALID_ARG, "instnorm_apply: bad extents");
   NormK k;
   k.src = a->src; k.mr = a->mean_rstd;
+  k.stats = a->stats_partial; k.mr_out = a->stats_partial ? a->mean_rstd_out : nullptr;
+  k.tiles = a->tiles_per_img; k.eps = a->eps;
+  k.inv_n = 1.0 / ((double)a->Z * a->Y * a->X);
   k.dst = reinterpret_cast<__nv_bfloat16*>(a->dst);
   k.pooled = reinterpret_cast<__nv_bfloat16*>(a->pooled);
   k.n_img = a->n_img; k.cb = a->cb; k.Z = a->Z; k.Y = a->Y; k.X = a->X;

@@ -55,12 +55,19 @@ class ConvRunner:
         raw = self.ws.get("raw", n * cout * Z * Y * X, torch.float32 if raw_f32 else torch.bfloat16)
         tile = K.plan_conv_norm((X, Y, Z), n, pw, raw_f32)
         stats = self.ws.get("stats", n * tile.tiles_per_img * cout * 2, torch.float32)
-        mr = self.ws.get("mean_rstd", n * cout * 2, torch.float32)
         K.conv3d(src, pw, a_cb, raw, _lib.OUT_BLOCKED_F32 if raw_f32 else _lib.OUT_BLOCKED_BF16, stats=stats,
                  dst_cbt=cout // 8, tile=tile)
-        K.instnorm_finalize(stats, n, tile.tiles_per_img, cout, Z * Y * X, mr)
-        K.instnorm_act_apply(raw, raw_f32, mr, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, pooled_c0)
-        self.launches += 3
+        if tile.tiles_per_img <= 256:
+            # InstanceNorm statistics finalized inside the apply kernel's prologue (no separate ~9 us launch); with more
+            # partial rows than this the per-block prologue (rows x 64 B from L2) costs more than the launch it saves
+            K.instnorm_act_apply(raw, raw_f32, None, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, pooled_c0,
+                                 stats=stats, tiles_per_img=tile.tiles_per_img)
+            self.launches += 2
+        else:
+            mr = self.ws.get("mean_rstd", n * cout * 2, torch.float32)
+            K.instnorm_finalize(stats, n, tile.tiles_per_img, cout, Z * Y * X, mr)
+            K.instnorm_act_apply(raw, raw_f32, mr, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, pooled_c0)
+            self.launches += 3
 
     def conv_transpose(self, src: Blocked, segs, pw: PackedConv, dst: Blocked, dst_c0: int = 0) -> None:
         a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], self.split)

@@ -245,11 +245,19 @@ def instnorm_finalize(stats: Tensor, n_img: int, tiles_per_img: int, channels: i
                                       _stream())
 
 
-def instnorm_act_apply(raw: Tensor, raw_is_f32: bool, mean_rstd: Tensor, n_img: int, channels: int,
+def instnorm_act_apply(raw: Tensor, raw_is_f32: bool, mean_rstd: Optional[Tensor], n_img: int, channels: int,
                        Z: int, Y: int, X: int, dst: Blocked, dst_c0: int = 0, slope: float = 0.0,
-                       pooled: Optional[Blocked] = None, pooled_c0: int = 0) -> None:
+                       pooled: Optional[Blocked] = None, pooled_c0: int = 0, *, stats: Optional[Tensor] = None,
+                       tiles_per_img: int = 0, eps: float = 1e-5, mean_rstd_out: Optional[Tensor] = None) -> None:
+    """stats (the conv epilogue's partials) given: the statistics are finalized inside the apply kernel and
+    mean_rstd is not read (no instnorm_finalize launch); mean_rstd_out optionally receives the table."""
     a = _lib.NormArgs()
-    a.src, a.mean_rstd, a.dst = raw.data_ptr(), mean_rstd.data_ptr(), dst.t.data_ptr()
+    a.src, a.dst = raw.data_ptr(), dst.t.data_ptr()
+    a.mean_rstd = mean_rstd.data_ptr() if mean_rstd is not None else None
+    if stats is not None:
+        assert stats.dtype == torch.float32 and stats.numel() >= n_img * tiles_per_img * channels * 2 and tiles_per_img >= 1
+        a.stats_partial, a.tiles_per_img, a.eps = stats.data_ptr(), tiles_per_img, eps
+        a.mean_rstd_out = mean_rstd_out.data_ptr() if mean_rstd_out is not None else None
     a.pooled = pooled.t.data_ptr() if pooled is not None else None
     a.n_img, a.cb, a.Z, a.Y, a.X = n_img, channels // 8, Z, Y, X
     a.src_is_f32 = 1 if raw_is_f32 else 0
