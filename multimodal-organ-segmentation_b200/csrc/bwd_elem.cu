@@ -56,7 +56,7 @@ __device__ __forceinline__ uint4 pkb8(const float* v) {
 }
 
 // Per-thread work item: one voxel (POOL = false) or one 2x2x2 cell (POOL = true).  Calls f(voxel_index, yhat[8], gprime[8]).
-template <bool POOL, typename F>
+template <bool POOL, int U, typename F>
 __device__ __forceinline__ void for_each_item(const NormBwdK& k, int img, int c, const float* mean, const float* rstd, F f) {
   const size_t nvox = (size_t)k.Z * k.Y * k.X;
   float cs[8];  // gA_scale x optional per-(image, channel) scale (Dropout3d: 0 or 1/(1-p))
@@ -68,32 +68,29 @@ __device__ __forceinline__ void for_each_item(const NormBwdK& k, int img, int c,
   const size_t xbase = (size_t)(img * k.cb + c) * nvox * 8;
   const size_t abase = (size_t)(img * k.gA_cbt + k.gA_cb_off + c) * nvox * 8;
   if (!POOL) {
-    // two voxels in flight per thread (all four 16-byte loads issued before any arithmetic): with one voxel per
-    // iteration the kernels ran at 40-58 % of HBM bandwidth; a 4-voxel unroll spilled (measured slower)
+    // U voxels in flight per thread (all 2U 16-byte loads issued before any arithmetic): with one voxel per iteration
+    // the kernels ran at 40-58 % of HBM bandwidth.  U = 4 for the read-only reduce, 2 for the apply (registers).
     const size_t step = (size_t)gridDim.x * blockDim.x;
     size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; v + step < nvox; v += 2 * step) {
-      uint4 rx0 = *reinterpret_cast<const uint4*>(k.x + xbase + v * 8);
-      uint4 rg0 = *reinterpret_cast<const uint4*>(k.gA + abase + v * 8);
-      uint4 rx1 = *reinterpret_cast<const uint4*>(k.x + xbase + (v + step) * 8);
-      uint4 rg1 = *reinterpret_cast<const uint4*>(k.gA + abase + (v + step) * 8);
-      float x[8], g[8];
-      unpk8(rx0, x);
-      unpk8(rg0, g);
+    for (; v + (U - 1) * step < nvox; v += U * step) {
+      uint4 rx[U], rg[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        x[i] = (x[i] - mean[i]) * rstd[i];
-        g[i] = (g[i] * cs[i] + cbias[i]) * (x[i] > 0.f ? 1.f : k.slope);
+      for (int u = 0; u < U; ++u) {
+        rx[u] = *reinterpret_cast<const uint4*>(k.x + xbase + (v + u * step) * 8);
+        rg[u] = *reinterpret_cast<const uint4*>(k.gA + abase + (v + u * step) * 8);
       }
-      f(v, x, g);
-      unpk8(rx1, x);
-      unpk8(rg1, g);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        x[i] = (x[i] - mean[i]) * rstd[i];
-        g[i] = (g[i] * cs[i] + cbias[i]) * (x[i] > 0.f ? 1.f : k.slope);
+      for (int u = 0; u < U; ++u) {
+        float x[8], g[8];
+        unpk8(rx[u], x);
+        unpk8(rg[u], g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          x[i] = (x[i] - mean[i]) * rstd[i];
+          g[i] = (g[i] * cs[i] + cbias[i]) * (x[i] > 0.f ? 1.f : k.slope);
+        }
+        f(v + u * step, x, g);
       }
-      f(v + step, x, g);
     }
     for (; v < nvox; v += step) {
       float x[8], g[8];
@@ -117,28 +114,31 @@ __device__ __forceinline__ void for_each_item(const NormBwdK& k, int img, int c,
       const int yh = (int)(r % Yh), zh = (int)(r / Yh);
       float gp[8];
       ldb8(k.gP + pbase + cell * 8, gp);
-      float yh8[8][8];
+      // pass 1: which of the 8 voxels holds each channel's maximum (3 bits per channel packed in one register).
+      // The normalised values are NOT kept (8 x 8 floats pushed the kernel to 198 / 251 registers = one block per SM
+      // and ~1.2 TB/s); pass 2 re-reads the 8 vectors, which are still in L1.
       float mx[8];
-      int arg[8];
+      uint32_t arg = 0u;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { mx[i] = -INFINITY; arg[i] = 0; }
+      for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
+      const size_t v000 = ((size_t)(2 * zh) * k.Y + (2 * yh)) * k.X + (2 * xh);
 #pragma unroll
       for (int d = 0; d < 8; ++d) {
-        const size_t v = ((size_t)(2 * zh + (d >> 2)) * k.Y + (2 * yh + ((d >> 1) & 1))) * k.X + (2 * xh + (d & 1));
+        const size_t v = v000 + ((size_t)(d >> 2) * k.Y + ((d >> 1) & 1)) * k.X + (d & 1);
         float x[8];
         ldb8(k.x + xbase + v * 8, x);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float y = (x[i] - mean[i]) * rstd[i];
-          yh8[d][i] = y;
           const float a = y > 0.f ? y : y * k.slope;
-          if (a > mx[i]) { mx[i] = a; arg[i] = d; }   // strict > keeps the first maximum in scan order
+          if (a > mx[i]) { mx[i] = a; arg = (arg & ~(7u << (3 * i))) | ((uint32_t)d << (3 * i)); }   // strict >: first maximum in scan order
         }
       }
-#pragma unroll
+#pragma unroll 2   // (fully unrolled the compiler hoists all 16 loads: 254 registers or spills)
       for (int d = 0; d < 8; ++d) {
-        const size_t v = ((size_t)(2 * zh + (d >> 2)) * k.Y + (2 * yh + ((d >> 1) & 1))) * k.X + (2 * xh + (d & 1));
-        float g[8];
+        const size_t v = v000 + ((size_t)(d >> 2) * k.Y + ((d >> 1) & 1)) * k.X + (d & 1);
+        float y[8], g[8];
+        ldb8(k.x + xbase + v * 8, y);
         if (k.gA) {
           ldb8(k.gA + abase + v * 8, g);
 #pragma unroll
@@ -149,10 +149,11 @@ __device__ __forceinline__ void for_each_item(const NormBwdK& k, int img, int c,
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          if (arg[i] == d) g[i] += gp[i];
-          g[i] *= (yh8[d][i] > 0.f ? 1.f : k.slope);
+          y[i] = (y[i] - mean[i]) * rstd[i];
+          if (((arg >> (3 * i)) & 7u) == (uint32_t)d) g[i] += gp[i];
+          g[i] *= (y[i] > 0.f ? 1.f : k.slope);
         }
-        f(v, yh8[d], g);
+        f(v, y, g);
       }
     }
   }
@@ -169,7 +170,7 @@ __device__ __forceinline__ void load_mr(const NormBwdK& k, int img, int c, float
 
 // grid (n_chunks, n_img*cb): partial[(blk*n_chunks + chunk)*16 + {i, 8+i}] = sum g', sum g'*y^
 template <bool POOL>
-__global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdK k) {
+__global__ void __launch_bounds__(256, 2) norm_bwd_reduce_kernel(const NormBwdK k) {
   const int blk = blockIdx.y;
   const int img = blk / k.cb, c = blk - img * k.cb;
   float mean[8], rstd[8];
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdK k) 
   float s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-  for_each_item<POOL>(k, img, c, mean, rstd, [&](size_t, const float* y, const float* g) {
+  for_each_item<POOL, 4>(k, img, c, mean, rstd, [&](size_t, const float* y, const float* g) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s1[i] += g[i]; s2[i] = fmaf(g[i], y[i], s2[i]); }
   });
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdK k) 
 
 // grid (any, n_img*cb): every block first re-reduces the n_chunks partials of its (img, cb) in a fixed order
 template <bool POOL>
-__global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdK k) {
+__global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(const NormBwdK k) {
   const int blk = blockIdx.y;
   const int img = blk / k.cb, c = blk - img * k.cb;
   __shared__ float m12[16];
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdK k) {
   for (int i = 0; i < 8; ++i) { m1[i] = m12[i]; m2[i] = m12[8 + i]; }
   const size_t nvox = (size_t)k.Z * k.Y * k.X;
   const size_t dbase = (size_t)(img * k.dx_cbt + k.dx_cb_off + c) * nvox * 8;
-  for_each_item<POOL>(k, img, c, mean, rstd, [&](size_t v, const float* y, const float* g) {
+  for_each_item<POOL, 2>(k, img, c, mean, rstd, [&](size_t v, const float* y, const float* g) {
     float d[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = rstd[i] * (g[i] - m1[i] - y[i] * m2[i]);

@@ -479,10 +479,10 @@ def instnorm_act_bwd(raw: Tensor, mean_rstd: Tensor, n_img: int, channels: int, 
     a.dx_cbt, a.dx_cb_off, a.n_chunks = channels // 8, 0, n_chunks
     a.gA_scale, a.slope = gA_scale, slope
     if PROFILE is not None:
-        _INFO[0] = {"bytes": n_img * channels * nvox * 4.0, "layer": f"bwd-reduce c{channels} {Z}x{Y}x{X}"}
+        _INFO[0] = {"bytes": n_img * channels * nvox * 4.0, "layer": f"bwd-reduce-c{channels}-{Z}-pool{int(gP is not None)}"}
     _call("mmseg_instnorm_act_bwd_reduce", C.byref(a), _stream())
     if PROFILE is not None:
-        _INFO[0] = {"bytes": n_img * channels * nvox * 6.0, "layer": f"bwd-apply c{channels} {Z}x{Y}x{X}"}
+        _INFO[0] = {"bytes": n_img * channels * nvox * 6.0, "layer": f"bwd-apply-c{channels}-{Z}-pool{int(gP is not None)}"}
     _call("mmseg_instnorm_act_bwd_apply", C.byref(a), _stream())
 
 

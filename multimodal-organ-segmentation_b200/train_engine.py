@@ -12,6 +12,8 @@ Reference semantics: autograd through UNet3D.forward (src/models/backbones/unet.
 """
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import os
+
 import torch
 
 from . import _lib
@@ -161,6 +163,13 @@ class TrainEngine:
         the dgrad / norm-backward kernels of the layers below (tensor-bound wgrad next to HBM-bound norm backward).
         `buf_key` names the gradient workspace it reads; the next writer of that workspace waits for this wgrad."""
         main = torch.cuda.current_stream(self.device)
+        if os.environ.get("MMSEG_WGRAD_SIDE_STREAM", "1") == "0":   # profiling: serialise, so per-kernel times are clean
+            g = K.conv3d_wgrad(*wargs, **wkw)
+            self.grads[param] = g
+            if self._reducer is not None and param.requires_grad:
+                self._reducer.grad_ready(param, g)
+                self._handed.add(param)
+            return
         if self._wstream is None:
             self._wstream = torch.cuda.Stream(device=self.device)
         ready = torch.cuda.Event()

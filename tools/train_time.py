@@ -46,11 +46,11 @@ prof, K.PROFILE = K.PROFILE, None
 agg = {}
 for name, info, a, b in prof:
     key = name if not info or "layer" not in info else name + ":" + (info["layer"] if "wgrad" in info["layer"] or "conv3d_fwd" in name else info["layer"].split(" ")[0])
-    d = agg.setdefault(key, [0.0, 0, 0.0])
+    d = agg.setdefault(key, [0.0, 0, 0.0, 0.0])
     d[0] += a.elapsed_time(b); d[1] += 1
-    if info: d[2] += info.get("flops", 0.0)
+    if info: d[2] += info.get("flops", 0.0); d[3] += info.get("bytes", 0.0) if "flops" not in info else 0.0
 tot = sum(d[0] for d in agg.values())
 print(f"kernel time inside C-ABI calls: {tot:.2f} ms")
 for k_, d in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-    tf = f"{d[2] / d[0] / 1e9:8.1f} TF/s" if d[2] else ""
+    tf = f"{d[2] / d[0] / 1e9:8.1f} TF/s" if d[2] else (f"{d[3] / d[0] / 1e6:8.0f} GB/s" if d[3] else "")
     print(f"  {k_:44s} {d[0]:8.3f} ms {100 * d[0] / tot:5.1f}%  n={d[1]:3d} {tf}")
