@@ -451,6 +451,9 @@ def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt
     if cm is None:  # cached: a host->device copy per call would also break CUDA-graph capture of the training step
         cm = _CI_MAPS[key] = torch.tensor(ci_map, dtype=torch.int32, device=x.t.device)
     cout = weight_shape[1] if transposed else weight_shape[0]
+    if PROFILE is not None:
+        _INFO[0] = {"bytes": 4.0 * partial.numel() + 4.0 * dw.numel(),
+                    "layer": f"reduce-k{ksize}-cin{cin}-n{cout_gemm}-part{n_part}-pairs{n_cig * n_cot}"}
     _call("mmseg_wgrad_reduce", _ptr(partial), n_part, ksize, cig // 8, ntc // 8, n_cot, cin, cout_gemm, cout,
           1 if transposed else 0, _ptr(cm), _ptr(dw), _stream())
     return dw
