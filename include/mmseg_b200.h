@@ -139,6 +139,16 @@ int mmseg_instnorm_finalize(const float* stats_partial, int32_t n_img, int32_t t
                             int64_t voxels, float eps, float* mean_rstd /* [n_img][channels][2] */, void* stream);
 
 /*
+ * GroupNorm(groups, channels) statistics (ConvBlock3D norm="group": nn.GroupNorm(8, C), unet.py:36-38) from the conv
+ * epilogue's partials (the conv must have added its bias): writes the apply kernel's table (mean_g, rstd_g * gamma_c)
+ * and shift = beta_c.  gamma / beta may be NULL (no affine).
+ */
+int mmseg_groupnorm_finalize(const float* stats_partial, int32_t n_img, int32_t tiles_per_img, int32_t channels,
+                             int32_t groups, int64_t voxels, float eps, const float* gamma, const float* beta,
+                             float* mean_rstd /* [n_img][channels][2] */, float* shift /* [n_img][channels] */,
+                             void* stream);
+
+/*
  * y = act((x - mean) * rstd) over a blocked tensor, act = ReLU (slope 0) / LeakyReLU(slope); writes bf16 (hi[, lo]).
  * Replaces nn.InstanceNorm3d apply + nn.ReLU (unet.py:45,55-59).  src_is_f32 selects the raw dtype.
  * pooled (optional): also writes MaxPool3d(2) (unet.py:73,77) of y into a second blocked buffer.
@@ -161,6 +171,9 @@ typedef struct {
   float* mean_rstd_out;       /* [n_img][cb*8][2] or NULL                                                  */
   int32_t tiles_per_img;
   float eps;
+  const float* shift;         /* [n_img][cb*8] or NULL: y = (x - mean) * rstd + shift before the activation — the
+                                 affine norms of ConvBlock3D (GroupNorm / BatchNorm, unet.py:30-38) fold gamma into
+                                 rstd and pass beta here; not combined with stats_partial                         */
 } mmseg_norm_args;
 int mmseg_instnorm_act_apply(const mmseg_norm_args* args, void* stream);
 

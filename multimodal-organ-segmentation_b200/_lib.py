@@ -67,6 +67,7 @@ class NormArgs(C.Structure):
         ("pool_cbt", C.c_int32), ("pool_cb_off", C.c_int32), ("pool_lo_off", C.c_int32),
         ("slope", C.c_float),
         ("stats_partial", C.c_void_p), ("mean_rstd_out", C.c_void_p), ("tiles_per_img", C.c_int32), ("eps", C.c_float),
+        ("shift", C.c_void_p),
     ]
 
 
@@ -107,6 +108,7 @@ SYMBOLS = {
     "mmseg_gate_mlp": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mmseg_modality_combine": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _f32, _vp, _i32, _i32, _i32, _vp]),
     "mmseg_modality_max": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i64, _vp, _i32, _i32, _vp]),
+    "mmseg_groupnorm_finalize": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i64, _f32, _vp, _vp, _vp, _vp, _vp]),
     "mmseg_trilinear_resize": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
     "mmseg_conv1x1_logits": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _i32, _vp, _vp]),
     "mmseg_maxpool3d_2": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),

@@ -46,10 +46,50 @@ instnorm_finalize_kernel(const float* __restrict__ part, int n_img, int tiles, i
   }
 }
 
+// GroupNorm(G, C) statistics (ConvBlock3D norm="group", unet.py:36-38): one warp per (image, group) sums the conv
+// epilogue's per-tile partials of the group's C/G channels in a fixed order (fp64) and writes, per channel, the table
+// the apply kernel consumes: (mean_g, rstd_g * gamma_c) and shift = beta_c, i.e. y = (x - mean_g) * rstd_g * gamma + beta.
+__global__ void __launch_bounds__(256)
+groupnorm_finalize_kernel(const float* __restrict__ part, int n_img, int tiles, int C, int G, double inv_n, float eps,
+                          const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ mean_rstd,
+                          float* __restrict__ shift) {
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (idx >= n_img * G) return;
+  const int img = idx / G, g = idx - img * G;
+  const int cpg = C / G;
+  const float* p = part + ((size_t)img * tiles * C + (size_t)g * cpg) * 2;
+  double s1 = 0.0, s2 = 0.0;
+  for (int t = lane; t < tiles; t += 32) {
+    const float* q = p + (size_t)t * C * 2;
+    for (int c = 0; c < cpg; ++c) {
+      s1 += (double)q[2 * c];
+      s2 += (double)q[2 * c + 1];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const double m = s1 * inv_n;
+  double var = s2 * inv_n - m * m;
+  if (var < 0.0) var = 0.0;
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  for (int c = lane; c < cpg; c += 32) {
+    const int ch = g * cpg + c;
+    const float ga = gamma ? gamma[ch] : 1.f;
+    mean_rstd[((size_t)img * C + ch) * 2] = (float)m;
+    mean_rstd[((size_t)img * C + ch) * 2 + 1] = (float)(rstd * (double)ga);
+    shift[(size_t)img * C + ch] = beta ? beta[ch] : 0.f;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- apply
 struct NormK {
   const void* src;
   const float* mr;
+  const float* shift;   // optional [n_img][C]: y = (x - mean) * rstd + shift (affine norms: GroupNorm / BatchNorm beta)
   const float* stats;   // optional: per-tile (sum, sum of squares) partials [n_img][tiles][C][2] -> finalized in the prologue
   float* mr_out;        // optional: where block x == 0 of each row publishes the (mean, rstd) it derived
   int tiles;
@@ -156,13 +196,19 @@ __device__ __forceinline__ void block_mean_rstd(const NormK& k, int img, int c, 
   for (int i = 0; i < 8; ++i) { mean[i] = smr[2 * i]; rstd[i] = smr[2 * i + 1]; }
 }
 
+__device__ __forceinline__ void block_shift(const NormK& k, int img, int c, float* sh) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sh[i] = k.shift ? k.shift[(size_t)img * k.cb * 8 + c * 8 + i] : 0.f;
+}
+
 // grid: (chunks over voxels, n_img*cb).  One 8-channel vector per thread-iteration.
 template <bool F32>
 __global__ void __launch_bounds__(256) instnorm_apply_kernel(const NormK k) {
   const int blk = blockIdx.y;  // img*cb + c
   const int img = blk / k.cb, c = blk - img * k.cb;
-  float mean[8], rstd[8];
+  float mean[8], rstd[8], sh[8];
   block_mean_rstd(k, img, c, mean, rstd);
+  block_shift(k, img, c, sh);
   const size_t nvox = (size_t)k.Z * k.Y * k.X;
   const size_t src_base = (size_t)blk * nvox * 8;
   const size_t dst_base = (size_t)(img * k.dst_cbt + k.dst_cb_off + c) * nvox * 8;
@@ -182,7 +228,7 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const NormK k) {
       if (v < nvox) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float y = (x[u][i] - mean[i]) * rstd[i];
+          const float y = (x[u][i] - mean[i]) * rstd[i] + sh[i];
           x[u][i] = y > 0.f ? y : y * k.slope;
         }
         store_act8(k.dst, dst_base + v * 8, lo_delta, x[u]);
@@ -196,8 +242,9 @@ template <bool F32>
 __global__ void __launch_bounds__(256) instnorm_apply_pool_kernel(const NormK k) {
   const int blk = blockIdx.y;
   const int img = blk / k.cb, c = blk - img * k.cb;
-  float mean[8], rstd[8];
+  float mean[8], rstd[8], sh[8];
   block_mean_rstd(k, img, c, mean, rstd);
+  block_shift(k, img, c, sh);
   const int Zh = k.Z / 2, Yh = k.Y / 2, Xh = k.X / 2;
   const size_t nvox = (size_t)k.Z * k.Y * k.X;
   const size_t ncell = (size_t)Zh * Yh * Xh;
@@ -226,7 +273,7 @@ __global__ void __launch_bounds__(256) instnorm_apply_pool_kernel(const NormK k)
           load8<F32>(k.src, src_base + v * 8, x);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float y = (x[i] - mean[i]) * rstd[i];
+            const float y = (x[i] - mean[i]) * rstd[i] + sh[i];
             x[i] = y > 0.f ? y : y * k.slope;
             mx[i] = fmaxf(mx[i], x[i]);
           }
@@ -302,6 +349,19 @@ extern "C" int mmseg_instnorm_finalize(const float* stats_partial, int32_t n_img
   return check_launch("instnorm_finalize_kernel");
 }
 
+extern "C" int mmseg_groupnorm_finalize(const float* stats_partial, int32_t n_img, int32_t tiles_per_img, int32_t channels,
+                                        int32_t groups, int64_t voxels, float eps, const float* gamma, const float* beta,
+                                        float* mean_rstd, float* shift, void* stream) {
+  if (!stats_partial || !mean_rstd || !shift || n_img < 1 || tiles_per_img < 1 || channels < 1 || groups < 1 || voxels < 1)
+    return fail(MMSEG_ERR_INVALID_ARG, "groupnorm_finalize: bad arguments");
+  if (channels % groups) return fail(MMSEG_ERR_INVALID_ARG, "groupnorm_finalize: channels %d not divisible by groups %d", channels, groups);
+  const int n = n_img * groups;
+  const double inv_n = 1.0 / ((double)voxels * (double)(channels / groups));
+  groupnorm_finalize_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      stats_partial, n_img, tiles_per_img, channels, groups, inv_n, eps, gamma, beta, mean_rstd, shift);
+  return check_launch("groupnorm_finalize_kernel");
+}
+
 extern "C" int mmseg_instnorm_act_apply(const mmseg_norm_args* a, void* stream) {
   if (!a || !a->src || !a->dst || (!a->mean_rstd && !a->stats_partial))
     return fail(MMSEG_ERR_INVALID_ARG, "instnorm_apply: null pointer");
@@ -310,6 +370,7 @@ extern "C" int mmseg_instnorm_act_apply(const mmseg_norm_args* a, void* stream) 
     return fail(MMSEG_ERR_INVALID_ARG, "instnorm_apply: bad extents");
   NormK k;
   k.src = a->src; k.mr = a->mean_rstd;
+  k.shift = a->shift;
   k.stats = a->stats_partial; k.mr_out = a->stats_partial ? a->mean_rstd_out : nullptr;
   k.tiles = a->tiles_per_img; k.eps = a->eps;
   k.inv_n = 1.0 / ((double)a->Z * a->Y * a->X);

@@ -36,6 +36,24 @@ class _Workspace:
         return t
 
 
+def norm_kind(norm) -> str:
+    """"instance" | "group" | "batch" | "none" for a ConvBlock3D norm module (reference unet.py:29-41)."""
+    if norm is None or isinstance(norm, torch.nn.InstanceNorm3d):
+        if norm is not None and (norm.affine or norm.track_running_stats):
+            raise NotImplementedError("InstanceNorm3d with affine / running statistics is never built by the reference")
+        return "instance"
+    if isinstance(norm, torch.nn.GroupNorm):
+        return "group"
+    if isinstance(norm, torch.nn.BatchNorm3d):
+        if norm.training or not norm.track_running_stats:
+            raise NotImplementedError("BatchNorm3d with batch statistics (train mode) is not built in the sm_100a path: "
+                                      "call model.eval() (inference uses the running statistics)")
+        return "batch"
+    if isinstance(norm, torch.nn.Identity):
+        return "none"
+    raise NotImplementedError(f"norm module {type(norm).__name__} has no sm_100a kernel")
+
+
 class ConvRunner:
     """conv (+ InstanceNorm statistics) -> finalize -> normalise/activate(/pool), on blocked buffers."""
 
@@ -44,20 +62,41 @@ class ConvRunner:
         self.device = device
         self.ws = _Workspace(device)
         self.launches = 0
+        self._tables: Dict[Tuple, Tuple] = {}
 
     # K segments: list of (first channel in src, real channels)
     def conv_norm_act(self, src: Blocked, segs: Sequence[Tuple[int, int]], pw: PackedConv, dst: Blocked, dst_c0: int = 0,
-                      pooled: Optional[Blocked] = None, pooled_c0: int = 0, slope: float = 0.0, tag: str = "") -> None:
+                      pooled: Optional[Blocked] = None, pooled_c0: int = 0, slope: float = 0.0, tag: str = "",
+                      norm=None) -> None:
+        """norm: the block's norm module (reference unet.py:29-41) — None / nn.InstanceNorm3d(affine=False): statistics
+        from the conv epilogue; nn.GroupNorm: group statistics from the same partials + affine; nn.BatchNorm3d in eval
+        mode: running statistics + affine (no statistics pass at all); nn.Identity: conv + bias + activation.  For the
+        last three `pw` must carry the conv bias (it is only cancelled by InstanceNorm)."""
         a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], self.split)
         n, Z, Y, X = src.n_img, src.Z, src.Y, src.X
         cout = pw.n_out
         raw_f32 = self.split
         raw = self.ws.get("raw", n * cout * Z * Y * X, torch.float32 if raw_f32 else torch.bfloat16)
         tile = K.plan_conv_norm((X, Y, Z), n, pw, raw_f32)
+        kind = norm_kind(norm)
+        out_mode = _lib.OUT_BLOCKED_F32 if raw_f32 else _lib.OUT_BLOCKED_BF16
+        if kind in ("batch", "none"):
+            K.conv3d(src, pw, a_cb, raw, out_mode, dst_cbt=cout // 8, tile=tile)
+            mr, shift = self._static_table(norm, kind, n, cout, raw.device)
+            K.instnorm_act_apply(raw, raw_f32, mr, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, pooled_c0, shift=shift)
+            self.launches += 2
+            return
         stats = self.ws.get("stats", n * tile.tiles_per_img * cout * 2, torch.float32)
-        K.conv3d(src, pw, a_cb, raw, _lib.OUT_BLOCKED_F32 if raw_f32 else _lib.OUT_BLOCKED_BF16, stats=stats,
-                 dst_cbt=cout // 8, tile=tile)
-        if tile.tiles_per_img <= 256:
+        K.conv3d(src, pw, a_cb, raw, out_mode, stats=stats, dst_cbt=cout // 8, tile=tile)
+        if kind == "group":
+            mr = self.ws.get("mean_rstd", n * cout * 2, torch.float32)
+            shift = self.ws.get("shift", n * cout, torch.float32)
+            ga = norm.weight.detach().float() if norm.weight is not None else None
+            be = norm.bias.detach().float() if norm.bias is not None else None
+            K.groupnorm_finalize(stats, n, tile.tiles_per_img, cout, norm.num_groups, Z * Y * X, ga, be, mr, shift, norm.eps)
+            K.instnorm_act_apply(raw, raw_f32, mr, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, pooled_c0, shift=shift)
+            self.launches += 3
+        elif tile.tiles_per_img <= 256:
             # InstanceNorm statistics finalized inside the apply kernel's prologue (no separate ~9 us launch); with more
             # partial rows than this the per-block prologue (rows x 64 B from L2) costs more than the launch it saves
             K.instnorm_act_apply(raw, raw_f32, None, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, pooled_c0,
@@ -68,6 +107,33 @@ class ConvRunner:
             K.instnorm_finalize(stats, n, tile.tiles_per_img, cout, Z * Y * X, mr)
             K.instnorm_act_apply(raw, raw_f32, mr, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, pooled_c0)
             self.launches += 3
+
+    def _static_table(self, norm, kind: str, n: int, cout: int, device):
+        """(mean, rstd) / shift tables of the norms that need no statistics of the current input: BatchNorm3d in eval mode
+        (running statistics; y = (x - rm) * gamma / sqrt(rv + eps) + beta) and Identity.  A few hundred floats of
+        parameter preparation, cached per parameter version like the packed weights."""
+        if kind == "none":
+            key, ver = ("none", n, cout), 0
+        else:
+            tens = [norm.running_mean, norm.running_var] + ([norm.weight, norm.bias] if norm.affine else [])
+            key, ver = (id(norm), n, cout), _param_version(tens)
+        hit = self._tables.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1], hit[2]
+        mr = torch.zeros((n, cout, 2), dtype=torch.float32, device=device)
+        shift = None
+        if kind == "none":
+            mr[:, :, 1] = 1.0
+        else:
+            c = norm.num_features
+            g = norm.weight.detach().float() if norm.affine else torch.ones(c, device=device)
+            mr[:, :c, 0] = norm.running_mean.detach().float()
+            mr[:, :c, 1] = g / torch.sqrt(norm.running_var.detach().float() + norm.eps)
+            shift = torch.zeros((n, cout), dtype=torch.float32, device=device)
+            if norm.affine:
+                shift[:, :c] = norm.bias.detach().float()
+        self._tables[key] = (ver, mr, shift)
+        return mr, shift
 
     def conv_transpose(self, src: Blocked, segs, pw: PackedConv, dst: Blocked, dst_c0: int = 0) -> None:
         a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], self.split)
@@ -126,10 +192,15 @@ class UNet3DEngine:
         sp = self.split
         P: Dict[str, PackedConv] = {}
 
+        self._norms: Dict[str, object] = {}
+
         def block(name: str, blk, segs1):
-            # bias of a conv that feeds InstanceNorm(affine=False) is cancelled exactly by the mean subtraction
-            P[name + ".conv1"] = K.pack_conv_weight(blk.conv1.weight, None, sp, segs1, use_bias=False)
-            P[name + ".conv2"] = K.pack_conv_weight(blk.conv2.weight, None, sp, None, use_bias=False)
+            # bias of a conv that feeds InstanceNorm(affine=False) is cancelled exactly by the mean subtraction; every
+            # other norm option (batch / group / none, model.backbone.norm) keeps it
+            inst = isinstance(blk.norm1, torch.nn.InstanceNorm3d)
+            P[name + ".conv1"] = K.pack_conv_weight(blk.conv1.weight, None if inst else blk.conv1.bias, sp, segs1, use_bias=not inst)
+            P[name + ".conv2"] = K.pack_conv_weight(blk.conv2.weight, None if inst else blk.conv2.bias, sp, None, use_bias=not inst)
+            self._norms[name + ".conv1"], self._norms[name + ".conv2"] = blk.norm1, blk.norm2
 
         block("init_conv", m.init_conv, [m.in_channels])
         for i, enc in enumerate(m.encoders):
@@ -186,32 +257,36 @@ class UNet3DEngine:
         f = m.features
         L = len(f)
         P = self._pack()
+        N = self._norms
         b = self._buffers(n, Z, Y, X, logits.device)
         if self._runner is None:
             self._runner = ConvRunner(self.split, logits.device)
         r = self._runner
         cin_p = (m.in_channels + 15) // 16 * 16
         # encoder (unet.py:181-187); each block's output lands in the skip half of its level's concat buffer
-        r.conv_norm_act(b["in"], [(0, m.in_channels)], P["init_conv.conv1"], b["mid0"])
+        r.conv_norm_act(b["in"], [(0, m.in_channels)], P["init_conv.conv1"], b["mid0"], norm=N["init_conv.conv1"])
         for l in range(L):
             last = l == L - 1
             if l > 0:
-                r.conv_norm_act(b[f"pool{l}"], [(0, f[l - 1])], P[f"encoders.{l - 1}.conv1"], b[f"mid{l}"])
+                r.conv_norm_act(b[f"pool{l}"], [(0, f[l - 1])], P[f"encoders.{l - 1}.conv1"], b[f"mid{l}"],
+                                norm=N[f"encoders.{l - 1}.conv1"])
                 name2 = f"encoders.{l - 1}.conv2"
             else:
                 name2 = "init_conv.conv2"
             if last:
-                r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[name2], b["bott"])
+                r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[name2], b["bott"], norm=N[name2])
             else:
                 r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[name2], b[f"cat{l}"], dst_c0=f[l],
-                                pooled=b[f"pool{l + 1}"])
+                                pooled=b[f"pool{l + 1}"], norm=N[name2])
         # decoder (unet.py:190-192): up -> cat([up, skip]) -> ConvBlock3D
         cur = b["bott"]
         for j in range(L - 1):
             l = L - 2 - j
             r.conv_transpose(cur, [(0, f[l + 1])], P[f"decoders.{j}.up"], b[f"cat{l}"], dst_c0=0)
-            r.conv_norm_act(b[f"cat{l}"], [(0, f[l]), (f[l], f[l])], P[f"decoders.{j}.conv1"], b[f"mid{l}"])
-            r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[f"decoders.{j}.conv2"], b[f"dec{l}"])
+            r.conv_norm_act(b[f"cat{l}"], [(0, f[l]), (f[l], f[l])], P[f"decoders.{j}.conv1"], b[f"mid{l}"],
+                            norm=N[f"decoders.{j}.conv1"])
+            r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[f"decoders.{j}.conv2"], b[f"dec{l}"],
+                            norm=N[f"decoders.{j}.conv2"])
             cur = b[f"dec{l}"]
         r.conv_logits(cur, [(0, f[0])], P["out_conv"], logits, m.out_conv)
         return logits

@@ -245,15 +245,27 @@ def instnorm_finalize(stats: Tensor, n_img: int, tiles_per_img: int, channels: i
                                       _stream())
 
 
+def groupnorm_finalize(stats: Tensor, n_img: int, tiles_per_img: int, channels: int, groups: int, voxels: int,
+                       gamma: Optional[Tensor], beta: Optional[Tensor], mean_rstd: Tensor, shift: Tensor,
+                       eps: float = 1e-5) -> None:
+    _call("mmseg_groupnorm_finalize", _ptr(stats), n_img, tiles_per_img, channels, groups, voxels, eps,
+          _ptr(gamma) if gamma is not None else None, _ptr(beta) if beta is not None else None, _ptr(mean_rstd),
+          _ptr(shift), _stream())
+
+
 def instnorm_act_apply(raw: Tensor, raw_is_f32: bool, mean_rstd: Optional[Tensor], n_img: int, channels: int,
                        Z: int, Y: int, X: int, dst: Blocked, dst_c0: int = 0, slope: float = 0.0,
                        pooled: Optional[Blocked] = None, pooled_c0: int = 0, *, stats: Optional[Tensor] = None,
-                       tiles_per_img: int = 0, eps: float = 1e-5, mean_rstd_out: Optional[Tensor] = None) -> None:
+                       tiles_per_img: int = 0, eps: float = 1e-5, mean_rstd_out: Optional[Tensor] = None,
+                       shift: Optional[Tensor] = None) -> None:
     """stats (the conv epilogue's partials) given: the statistics are finalized inside the apply kernel and
     mean_rstd is not read (no instnorm_finalize launch); mean_rstd_out optionally receives the table."""
     a = _lib.NormArgs()
     a.src, a.dst = raw.data_ptr(), dst.t.data_ptr()
     a.mean_rstd = mean_rstd.data_ptr() if mean_rstd is not None else None
+    if shift is not None:
+        assert stats is None and shift.dtype == torch.float32 and shift.numel() >= n_img * channels
+        a.shift = shift.data_ptr()
     if stats is not None:
         assert stats.dtype == torch.float32 and stats.numel() >= n_img * tiles_per_img * channels * 2 and tiles_per_img >= 1
         a.stats_partial, a.tiles_per_img, a.eps = stats.data_ptr(), tiles_per_img, eps

@@ -40,6 +40,10 @@ def _train_step_forward(model: nn.Module, kind: str, x: torch.Tensor) -> torch.T
     if x.requires_grad:
         raise NotImplementedError("gradients w.r.t. the input volume (first-layer dgrad) are not built: x.requires_grad "
                                   "must be False")
+    blk = getattr(model, "init_conv", None)
+    if blk is not None and getattr(blk, "norm_type", "instance") != "instance":
+        raise NotImplementedError(f"training with model.backbone.norm={blk.norm_type!r} is not built: the backward kernels "
+                                  "cover InstanceNorm3d (the reference's default); batch / group / no norm are inference-only")
     if model.numeric_mode != "bf16":
         raise NotImplementedError("the backward path runs in bf16 mode (north_star: bf16 training step); call "
                                   "set_numeric_mode('bf16') before training")
@@ -85,12 +89,12 @@ class ConvBlock3D(nn.Module):
         self._packed = None
 
     def kernel_supported(self) -> None:
-        if self.norm_type != "instance" or self.activation == "gelu" or self.conv1.kernel_size != (3, 3, 3) \
+        if self.activation == "gelu" or self.conv1.kernel_size != (3, 3, 3) \
                 or self.conv1.padding != (1, 1, 1) or self.out_channels % 16:
             raise NotImplementedError(
                 f"ConvBlock3D(norm={self.norm_type!r}, activation={self.activation!r}, k={self.conv1.kernel_size}, "
-                f"C_out={self.out_channels}) has no sm_100a kernel (covered: instance norm, relu/leaky_relu, k=3 p=1, "
-                "C_out % 16 == 0)")
+                f"C_out={self.out_channels}) has no sm_100a kernel (covered: instance / group / batch(eval) / no norm, "
+                "relu / leaky_relu, k=3 p=1, C_out % 16 == 0)")
 
     @property
     def slope(self) -> float:
@@ -104,18 +108,22 @@ class ConvBlock3D(nn.Module):
         with torch.no_grad():
             x = x.contiguous().float()
             n, c, Z, Y, X = x.shape
-            ver = (self.conv1.weight._version, self.conv2.weight._version, split)
+            inst = self.norm_type == "instance"   # only InstanceNorm cancels the conv bias
+            ver = (self.conv1.weight._version, self.conv2.weight._version, self.conv1.bias._version,
+                   self.conv2.bias._version, split)
             if self._packed is None or self._packed[0] != ver:
-                self._packed = (ver, K.pack_conv_weight(self.conv1.weight, None, split, [c], use_bias=False),
-                                K.pack_conv_weight(self.conv2.weight, None, split, None, use_bias=False))
+                self._packed = (ver, K.pack_conv_weight(self.conv1.weight, None if inst else self.conv1.bias, split, [c],
+                                                        use_bias=not inst),
+                                K.pack_conv_weight(self.conv2.weight, None if inst else self.conv2.bias, split, None,
+                                                   use_bias=not inst))
             if self._runner is None or self._runner.split != split:
                 self._runner = ConvRunner(split, x.device)
             src = Blocked(n, (c + 15) // 16 * 16, Z, Y, X, split, x.device)
             K.pack_ncdhw(x, src)
             mid = Blocked(n, self.out_channels, Z, Y, X, split, x.device)
             out = Blocked(n, self.out_channels, Z, Y, X, split, x.device)
-            self._runner.conv_norm_act(src, [(0, c)], self._packed[1], mid, slope=self.slope)
-            self._runner.conv_norm_act(mid, [(0, self.out_channels)], self._packed[2], out, slope=self.slope)
+            self._runner.conv_norm_act(src, [(0, c)], self._packed[1], mid, slope=self.slope, norm=self.norm1)
+            self._runner.conv_norm_act(mid, [(0, self.out_channels)], self._packed[2], out, slope=self.slope, norm=self.norm2)
             return out.to_ncdhw()
 
 
@@ -169,12 +177,16 @@ class UpBlock3D(nn.Module):
                 raise NotImplementedError("trilinear resize to the skip shape (reference unet.py:108-109) is not "
                                           "implemented; use spatial sizes divisible by 2**levels")
             half = c // 2
-            ver = (self.up.weight._version, self.conv.conv1.weight._version, self.conv.conv2.weight._version, split)
+            inst = self.conv.norm_type == "instance"   # only InstanceNorm cancels the conv bias
+            ver = (self.up.weight._version, self.conv.conv1.weight._version, self.conv.conv2.weight._version,
+                   self.conv.conv1.bias._version, self.conv.conv2.bias._version, split)
             if self._packed is None or self._packed[0] != ver:
                 self._packed = (ver,
                                 K.pack_conv_weight(self.up.weight, self.up.bias, split, None, transposed=True),
-                                K.pack_conv_weight(self.conv.conv1.weight, None, split, [half, skip.shape[1]], use_bias=False),
-                                K.pack_conv_weight(self.conv.conv2.weight, None, split, None, use_bias=False))
+                                K.pack_conv_weight(self.conv.conv1.weight, None if inst else self.conv.conv1.bias, split,
+                                                   [half, skip.shape[1]], use_bias=not inst),
+                                K.pack_conv_weight(self.conv.conv2.weight, None if inst else self.conv.conv2.bias, split,
+                                                   None, use_bias=not inst))
             if self._runner is None or self._runner.split != split:
                 self._runner = ConvRunner(split, x.device)
             r = self._runner
@@ -186,8 +198,9 @@ class UpBlock3D(nn.Module):
             co = self.conv.out_channels
             mid = Blocked(n, co, 2 * Z, 2 * Y, 2 * X, split, x.device)
             out = Blocked(n, co, 2 * Z, 2 * Y, 2 * X, split, x.device)
-            r.conv_norm_act(cat, [(0, half), (half, skip.shape[1])], self._packed[2], mid, slope=self.conv.slope)
-            r.conv_norm_act(mid, [(0, co)], self._packed[3], out, slope=self.conv.slope)
+            r.conv_norm_act(cat, [(0, half), (half, skip.shape[1])], self._packed[2], mid, slope=self.conv.slope,
+                            norm=self.conv.norm1)
+            r.conv_norm_act(mid, [(0, co)], self._packed[3], out, slope=self.conv.slope, norm=self.conv.norm2)
             return out.to_ncdhw()
 
 

@@ -28,32 +28,46 @@ def _act(x: Tensor, activation: str) -> Tensor:
     return F.relu(x)
 
 
-def conv_block3d(sd: SD, prefix: str, x: Tensor, activation: str = "relu") -> Tensor:
+def _norm3d(sd: SD, key: str, x: Tensor, norm: str) -> Tensor:
+    """norm1 / norm2 of ConvBlock3D — unet.py:29-41: InstanceNorm3d(affine=False) | BatchNorm3d (eval: running statistics)
+    | GroupNorm(8, C) | Identity.  All with eps = 1e-5 (PyTorch defaults)."""
+    dt = x.dtype
+    if norm == "instance":
+        return F.instance_norm(x, eps=1e-5)
+    if norm == "group":
+        return F.group_norm(x, 8, _p(sd, key + ".weight", dt), _p(sd, key + ".bias", dt), eps=1e-5)
+    if norm == "batch":
+        return F.batch_norm(x, _p(sd, key + ".running_mean", dt), _p(sd, key + ".running_var", dt),
+                            _p(sd, key + ".weight", dt), _p(sd, key + ".bias", dt), training=False, eps=1e-5)
+    return x
+
+
+def conv_block3d(sd: SD, prefix: str, x: Tensor, activation: str = "relu", norm: str = "instance") -> Tensor:
     """ConvBlock3D.forward — src/models/backbones/unet.py:53-60.
 
-    Conv3d(k3,p1,bias) -> InstanceNorm3d(affine=False, eps=1e-5) -> act, twice.
+    Conv3d(k3,p1,bias) -> norm (InstanceNorm3d(affine=False, eps=1e-5) by default) -> act, twice.
     """
     dt = x.dtype
     for i in (1, 2):
         x = F.conv3d(x, _p(sd, f"{prefix}.conv{i}.weight", dt), _p(sd, f"{prefix}.conv{i}.bias", dt), padding=1)
-        x = F.instance_norm(x, eps=1e-5)
+        x = _norm3d(sd, f"{prefix}.norm{i}", x, norm)
         x = _act(x, activation)
     return x
 
 
-def down_block3d(sd: SD, prefix: str, x: Tensor) -> Tensor:
+def down_block3d(sd: SD, prefix: str, x: Tensor, norm: str = "instance") -> Tensor:
     """DownBlock3D.forward — unet.py:76-79 (MaxPool3d(2) then ConvBlock3D)."""
-    return conv_block3d(sd, f"{prefix}.conv", F.max_pool3d(x, 2))
+    return conv_block3d(sd, f"{prefix}.conv", F.max_pool3d(x, 2), norm=norm)
 
 
-def up_block3d(sd: SD, prefix: str, x: Tensor, skip: Tensor) -> Tensor:
+def up_block3d(sd: SD, prefix: str, x: Tensor, skip: Tensor, norm: str = "instance") -> Tensor:
     """UpBlock3D.forward — unet.py:104-113 (ConvTranspose3d k2 s2, cat([up, skip]), ConvBlock3D)."""
     dt = x.dtype
     x = F.conv_transpose3d(x, _p(sd, f"{prefix}.up.weight", dt), _p(sd, f"{prefix}.up.bias", dt), stride=2)
     if x.shape != skip.shape:
         x = F.interpolate(x, size=skip.shape[2:], mode="trilinear", align_corners=True)
     x = torch.cat([x, skip], dim=1)
-    return conv_block3d(sd, f"{prefix}.conv", x)
+    return conv_block3d(sd, f"{prefix}.conv", x, norm=norm)
 
 
 def _num_levels(sd: SD, pattern: str) -> int:
@@ -63,19 +77,32 @@ def _num_levels(sd: SD, pattern: str) -> int:
     return n
 
 
+def _unet_norm_kind(sd: SD, prefix: str) -> str:
+    """model.backbone.norm as it shows in the state_dict: BatchNorm3d has running statistics, GroupNorm only an affine
+    pair, InstanceNorm3d(affine=False) / Identity nothing (those two are told apart by the caller: default instance)."""
+    if prefix + "init_conv.norm1.running_mean" in sd:
+        return "batch"
+    if prefix + "init_conv.norm1.weight" in sd:
+        return "group"
+    return "instance"
+
+
 def unet3d_forward(sd: SD, x: Tensor, prefix: str = "backbone.", dtype=torch.float32,
-                   return_features: bool = False):
-    """UNet3D.forward — src/models/backbones/unet.py:165-200 (dropout = identity / eval)."""
+                   return_features: bool = False, norm: str = None):
+    """UNet3D.forward — src/models/backbones/unet.py:165-200 (dropout = identity / eval).  norm: model.backbone.norm
+    ("instance" | "batch" | "group" | anything else = Identity); None = read it off the state_dict."""
     x = x.detach().to("cpu", dtype)
+    if norm is None:
+        norm = _unet_norm_kind(sd, prefix)
     n_enc = _num_levels(sd, prefix + "encoders.{}.conv.conv1.weight")
-    x = conv_block3d(sd, prefix + "init_conv", x)
+    x = conv_block3d(sd, prefix + "init_conv", x, norm=norm)
     feats = [x]
     for i in range(n_enc):
-        x = down_block3d(sd, f"{prefix}encoders.{i}", x)
+        x = down_block3d(sd, f"{prefix}encoders.{i}", x, norm=norm)
         feats.append(x)
     feats = feats[:-1]
     for j, skip in enumerate(reversed(feats)):
-        x = up_block3d(sd, f"{prefix}decoders.{j}", x, skip)
+        x = up_block3d(sd, f"{prefix}decoders.{j}", x, skip, norm=norm)
     x = F.conv3d(x, _p(sd, prefix + "out_conv.weight", dtype), _p(sd, prefix + "out_conv.bias", dtype))
     if return_features:
         return x, feats

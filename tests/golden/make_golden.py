@@ -132,6 +132,28 @@ def main():
     out["deep_supervision"] = {"state_dict": ds.state_dict(), "features": feats, "target_size": (12, 10, 14),
                                "outputs": [o.clone() for o in outs]}
 
+    # ---- UNet3D with model.backbone.norm = group / batch / none (unet.py:29-41,224): non-trivial affine parameters and,
+    # for batch, running statistics populated by two train-mode forwards before the eval-mode reference output
+    for norm in ("group", "batch", "none"):
+        torch.manual_seed(30)
+        cfgn = _cfg("unet", "early", ["CT", "PET"], [16, 32])
+        cfgn["model"]["backbone"]["norm"] = norm
+        mn = build_model(copy.deepcopy(cfgn))
+        gn = torch.Generator().manual_seed(31)
+        with torch.no_grad():
+            for prm_name, prm in mn.named_parameters():
+                if ".norm" in prm_name:      # gamma around 1, beta around 0 (defaults are exactly 1 / 0)
+                    prm.add_(0.3 * torch.randn(prm.shape, generator=gn))
+            if norm == "batch":
+                mn.train()
+                for _ in range(2):
+                    mn(torch.randn(2, 2, 16, 16, 16, generator=gn) * 1.5 + 0.3)
+        mn.eval()
+        xn = torch.randn(2, 2, 16, 16, 16, generator=gn)
+        with torch.no_grad():
+            yn = mn(xn)
+        out["unet_norm_" + norm] = {"config": cfgn, "state_dict": mn.state_dict(), "x": xn, "logits": yn}
+
     only = set(sys.argv[1:])      # python make_golden.py [name ...]: write only these fixtures (all are seeded)
     for k, v in out.items():
         if only and k not in only:

@@ -287,6 +287,34 @@ def unet_golden_case(mode="parity"):
         assert max_abs <= 2e-1 and rel_l2 <= 5e-2 and agree >= 0.95
 
 
+def unet_norm_golden_case(norm, mode="parity"):
+    """UNet3D with model.backbone.norm = group / batch / none vs the reference's own logits (tests/golden/unet_norm_*.pt)."""
+    import copy
+    from mmseg_b200.src.models.build import build_model
+    g = _gold("unet_norm_" + norm)
+    cfg = copy.deepcopy(g["config"])
+    cfg["hardware"]["device"] = "cuda"
+    m = build_model(cfg).eval()
+    m.load_state_dict(g["state_dict"], strict=True)
+    m.set_numeric_mode(mode)
+    with torch.no_grad():
+        got = m(g["x"].to(DEV))
+    max_abs, rel_l2, agree = _metrics(got.cpu(), g["logits"])
+    print(f"[unet norm={norm} mode={mode}] max_abs={max_abs:.3e} rel_l2={rel_l2:.3e} label_agree={agree * 100:.4f}%", flush=True)
+    if mode == "parity":
+        assert max_abs <= 2e-2 and rel_l2 <= 1e-3 and agree >= 0.999
+    else:
+        assert rel_l2 <= 5e-2 and agree >= 0.93
+    if norm == "batch":   # batch statistics (train mode) are not built: loud error, no fallback
+        m.train()
+        try:
+            with torch.no_grad():
+                m(g["x"].to(DEV))
+            raise AssertionError("train-mode BatchNorm3d must raise")
+        except NotImplementedError:
+            pass
+
+
 # ------------------------------------------------------------------------------------------------ DiceCE
 def dicece_case(B=2, C=8, shape=(12, 10, 14), weights=False, include_background=True, seed=0):
     from oracle import losses as OL

@@ -89,6 +89,12 @@ def test_deep_supervision_head_golden():
     _c().deep_supervision_golden_case()
 
 
+@pytest.mark.parametrize("norm,mode", [("group", "parity"), ("batch", "parity"), ("none", "parity"), ("group", "bf16"),
+                                       ("batch", "bf16")])
+def test_unet_norm_options_golden(norm, mode):
+    _c().unet_norm_golden_case(norm, mode)
+
+
 def test_pack_unpack_roundtrip():
     _c().pack_roundtrip_case()
 

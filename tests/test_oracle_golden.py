@@ -30,6 +30,16 @@ def test_unet_small_logits():
         assert abs(f.mean().item() - m) < 1e-5
 
 
+@pytest.mark.parametrize("norm", ["group", "batch", "none"])
+def test_unet_norm_options(norm):
+    """model.backbone.norm = group / batch (eval, running statistics) / anything else (Identity) — unet.py:29-41."""
+    g = load("unet_norm_" + norm)
+    y = OM.unet3d_forward(g["state_dict"], g["x"], norm=norm)
+    _close(y, g["logits"], atol=5e-5, rtol=1e-4)
+    if norm != "none":   # the kind is also recognisable from the state_dict alone
+        _close(OM.unet3d_forward(g["state_dict"], g["x"]), g["logits"], atol=5e-5, rtol=1e-4)
+
+
 def test_convblock_leaky_relu_option():
     g = load("convblock_leaky")
     sd = {"b." + k: v for k, v in g["state_dict"].items()}
