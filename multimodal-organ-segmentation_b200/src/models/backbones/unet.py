@@ -36,10 +36,8 @@ def _no_autograd(module: nn.Module, x: torch.Tensor) -> None:
 
 
 def _train_step_forward(model: nn.Module, kind: str, x: torch.Tensor) -> torch.Tensor:
-    """Forward that records the tape for the kernel backward (parameters get gradients; the input does not)."""
-    if x.requires_grad:
-        raise NotImplementedError("gradients w.r.t. the input volume (first-layer dgrad) are not built: x.requires_grad "
-                                  "must be False")
+    """Forward that records the tape for the kernel backward (parameters get gradients; so does the input volume when
+    x.requires_grad: the first layers' dgrad then runs as well)."""
     blk = getattr(model, "init_conv", None)
     if blk is not None and getattr(blk, "norm_type", "instance") != "instance":
         raise NotImplementedError(f"training with model.backbone.norm={blk.norm_type!r} is not built: the backward kernels "

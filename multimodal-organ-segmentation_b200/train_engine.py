@@ -222,7 +222,10 @@ class TrainEngine:
             self.grads[conv.bias] = torch.zeros_like(conv.bias, dtype=torch.float32)
         if op["need_dgrad"]:
             segs = op["segs"]
-            assert all(s[1] % 16 == 0 for s in segs) and all(segs[i][0] + segs[i][1] == segs[i + 1][0] for i in range(len(segs) - 1)), \
+            # (a single segment may have any channel count: the first layers' 1- or 2-channel input; the padded output
+            # channels of the dgrad conv are exact zeros)
+            assert (len(segs) == 1 and segs[0][0] % 8 == 0) or \
+                (all(s[1] % 16 == 0 for s in segs) and all(segs[i][0] + segs[i][1] == segs[i + 1][0] for i in range(len(segs) - 1))), \
                 "dgrad needs contiguous 16-channel-aligned input segments"
             wd = conv.weight.detach().float().flip(2, 3, 4).transpose(0, 1).contiguous()   # [cin, cout, k, k, k]
             self._dgrad(draw, cout, wd, self.grad_of(src), segs[0][0])
@@ -301,12 +304,19 @@ class TrainEngine:
                 if p not in handed and p.requires_grad:
                     reducer.grad_ready(p, g)
         self._reducer = None
+        self.x_grad = None
+        if getattr(self, "_input_grad", False):   # gradient w.r.t. the input volume, NCDHW fp32, modalities in channel order
+            parts = [self.grad_of(a).to_ncdhw(0, c) for a, c in self._inputs]
+            self.x_grad = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
         return self.grads
 
     # ---------------------------------------------------------------- model forwards
     @torch.no_grad()
-    def forward(self, x: Tensor, drop_scale: Optional[Tensor] = None) -> Tensor:
-        """x NCDHW fp32 (CUDA) -> logits NCDHW fp32; records the tape.  drop_scale [n, f0]: Dropout3d mask * 1/(1-p)."""
+    def forward(self, x: Tensor, drop_scale: Optional[Tensor] = None, input_grad: bool = False) -> Tensor:
+        """x NCDHW fp32 (CUDA) -> logits NCDHW fp32; records the tape.  drop_scale [n, f0]: Dropout3d mask * 1/(1-p).
+        input_grad: also run the first layers' dgrad in backward() (the gradient w.r.t. x: autograd's input gradient)."""
+        self._input_grad = bool(input_grad)
+        self._inputs: List[Tuple[Blocked, int]] = []      # (blocked input buffer, real channels) in channel order
         _lib.require_device()
         if not x.is_cuda:
             raise RuntimeError("mmseg_b200 engines run on CUDA tensors only (no CPU fallback)")
@@ -327,7 +337,9 @@ class TrainEngine:
             cin = m.in_channels
             a_in = A("in", (cin + 15) // 16 * 16, 0)
             K.pack_ncdhw(x, a_in)
-            self.conv_norm_act("init.c1", a_in, [(0, cin)], m.init_conv.conv1, A("e0.mid", f[0], 0), need_dgrad=False)
+            self._inputs.append((a_in, cin))
+            self.conv_norm_act("init.c1", a_in, [(0, cin)], m.init_conv.conv1, A("e0.mid", f[0], 0),
+                               need_dgrad=self._input_grad)
             for l in range(L):
                 blk = m.init_conv if l == 0 else m.encoders[l - 1].conv
                 if l > 0:
@@ -345,9 +357,10 @@ class TrainEngine:
             for i in range(M):
                 a_in = A(f"m{i}.in", (cpm + 15) // 16 * 16, 0)
                 K.pack_ncdhw(x[:, i * cpm:(i + 1) * cpm].contiguous(), a_in)
+                self._inputs.append((a_in, cpm))
                 enc = m.encoders[i]
                 self.conv_norm_act(f"m{i}.init.c1", a_in, [(0, cpm)], enc["init_conv"].conv1, A(f"m{i}.e0.mid", f[0], 0),
-                                   need_dgrad=False)
+                                   need_dgrad=self._input_grad)
                 for l in range(L):
                     blk = enc["init_conv"] if l == 0 else enc["blocks"][l - 1].conv
                     if l > 0:
@@ -404,7 +417,8 @@ class _ModelFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine: TrainEngine, x: Tensor, drop_scale: Optional[Tensor], *params: Tensor) -> Tensor:
         ctx.engine, ctx.params = engine, params
-        return engine.forward(x, drop_scale)
+        ctx.x_dtype = x.dtype
+        return engine.forward(x, drop_scale, input_grad=x.requires_grad)
 
     @staticmethod
     def backward(ctx, dlogits: Tensor):
@@ -415,7 +429,8 @@ class _ModelFunction(torch.autograd.Function):
             g = grads.get(p)
             # armed data-parallel step: the reducer owns the gradient (bucket -> all-reduce -> .grad in finish())
             out.append(None if (g is None or not p.requires_grad or red is not None) else g.to(p.dtype).view_as(p))
-        return (None, None, None, *out)
+        gx = ctx.engine.x_grad if ctx.needs_input_grad[1] else None
+        return (None, None if gx is None else gx.to(ctx.x_dtype), None, *out)
 
 
 def train_forward(engine: TrainEngine, x: Tensor, drop_scale: Optional[Tensor] = None) -> Tensor:

@@ -9,10 +9,11 @@ import torch
 import torch.nn.functional as F2
 
 
-def train_step(kind, sd, cfgkw, x, y, dtype=torch.float64, dice_weight=0.5, ce_weight=0.5):
-    """Oracle training step on the CPU: loss + parameter gradients by autograd over the oracle restatement."""
+def train_step(kind, sd, cfgkw, x, y, dtype=torch.float64, dice_weight=0.5, ce_weight=0.5, input_grad=False):
+    """Oracle training step on the CPU: loss + parameter gradients by autograd over the oracle restatement
+    (input_grad: the gradient w.r.t. x is returned under the key "__input__")."""
     params = {k: v.detach().to("cpu", dtype).requires_grad_(True) for k, v in sd.items()}
-    xx = x.detach().to("cpu", dtype)
+    xx = x.detach().to("cpu", dtype).requires_grad_(bool(input_grad))
     # the oracle forwards detach their parameters; re-state them here with autograd enabled
     def block(prefix, t):
         for i in (1, 2):
@@ -65,6 +66,9 @@ def train_step(kind, sd, cfgkw, x, y, dtype=torch.float64, dice_weight=0.5, ce_w
     I, U = (p * tt).flatten(2).sum(-1), p.flatten(2).sum(-1) + tt.flatten(2).sum(-1)
     loss = dice_weight * (1 - (2 * I + 1) / (U + 1)).mean() + ce_weight * F2.cross_entropy(logits, y.cpu().long())
     loss.backward()
-    return loss.item(), {k: v.grad for k, v in params.items()}, logits.detach()
+    grads = {k: v.grad for k, v in params.items()}
+    if input_grad:
+        grads["__input__"] = xx.grad
+    return loss.item(), grads, logits.detach()
 
 

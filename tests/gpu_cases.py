@@ -497,6 +497,40 @@ def train_step_case(kind="unet", features=(16, 32, 64), S=16, n_img=2, fusion="l
     assert worst < 0.25, worst
 
 
+def input_grad_case(kind="unet", features=(16, 32), S=16, n_img=2, fusion="add", M=2, seed=3):
+    """x.requires_grad: the first layers' dgrad returns d loss / d x (vs fp64 autograd over the oracle maths)."""
+    from oracle.train import train_step
+    from mmseg_b200.src.models.backbones.unet import UNet3D
+    from mmseg_b200.src.models.backbones.dual_encoder import DualEncoder
+    from mmseg_b200.src.trainer.losses import DiceCELoss
+    torch.manual_seed(seed)
+    if kind == "unet":
+        m, cin = UNet3D(in_channels=2, out_channels=8, features=list(features)), 2
+    else:
+        m, cin = DualEncoder(num_modalities=M, out_channels=8, features=list(features), fusion_type=fusion), M
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.randn(n_img, cin, S, S, S)
+    y = torch.randint(0, 8, (n_img, S, S, S))
+    ref_loss, ref_g, _ = train_step(kind, sd, dict(L=len(features), M=M, fusion=fusion), x, y, input_grad=True)
+    m = m.to(DEV).train()
+    xd = x.to(DEV).requires_grad_(True)
+    loss = DiceCELoss()(m(xd), y.to(DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert xd.grad is not None and xd.grad.shape == xd.shape and torch.isfinite(xd.grad).all()
+    g, r = xd.grad.detach().cpu().double(), ref_g["__input__"]
+    rel = ((g - r).norm() / r.norm()).item()
+    cos = (g.flatten() @ r.flatten() / (g.norm() * r.norm())).item()
+    print(f"[input grad {kind} {features}] |g|={r.norm().item():.3e} rel_l2={rel:.3e} cos={cos:.5f}", flush=True)
+    assert rel < 0.25 and cos > 0.97                                 # same bf16 floor as the parameter gradients
+    assert all(p.grad is not None for p in m.parameters())           # parameter gradients are still produced
+    # without requires_grad nothing changes: no input gradient, same loss
+    m.zero_grad()
+    loss2 = DiceCELoss()(m(x.to(DEV)), y.to(DEV))
+    loss2.backward()
+    assert abs(loss2.item() - loss.item()) < 1e-6
+
+
 def norm_bwd_case(channels=16, shape=(8, 12, 16), n_img=2, pool=True, slope=0.0, scale=1.0, seed=0):
     """InstanceNorm + act (+ MaxPool3d(2)) backward kernels vs fp64 autograd on the SAME bf16-rounded inputs."""
     torch.manual_seed(seed)

@@ -95,6 +95,11 @@ def test_unet_norm_options_golden(norm, mode):
     _c().unet_norm_golden_case(norm, mode)
 
 
+@pytest.mark.parametrize("kind", ["unet", "dual"])
+def test_input_gradient(kind):
+    _c().input_grad_case(kind)
+
+
 def test_pack_unpack_roundtrip():
     _c().pack_roundtrip_case()
 
