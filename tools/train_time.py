@@ -1,4 +1,5 @@
-"""Time the kernel training step: python tools/train_time.py [model unet|dual] [S] [B] [steps]"""
+"""Time the kernel training step: python tools/train_time.py [model unet|dual] [S] [B] [steps] [fusion] [n_modalities]
+BASELINE.json configs[1]: dual 128 2 3 cross_attention 2;  configs[4]: dual 128 4 3 attention 4 (and unet 128 4 3 early 4)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,15 +12,17 @@ kind = sys.argv[1] if len(sys.argv) > 1 else "dual"
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
-cfg = {"model": {"name": "dual_encoder" if kind == "dual" else "unet", "in_channels": 2, "out_channels": 8,
-                 "backbone": {"features": [32, 64, 128, 256, 512]}, "fusion": {"type": "cross_attention"},
+fusion = sys.argv[5] if len(sys.argv) > 5 else "cross_attention"
+M = int(sys.argv[6]) if len(sys.argv) > 6 else 2
+cfg = {"model": {"name": "dual_encoder" if kind == "dual" else "unet", "in_channels": M, "out_channels": 8,
+                 "backbone": {"features": [32, 64, 128, 256, 512]}, "fusion": {"type": fusion},
                  "head": {"dropout": 0.1}},
-       "data": {"modalities": ["CT", "PET"]}, "hardware": {"device": "cuda"}}
+       "data": {"modalities": ["CT", "PET", "MRI", "US"][:M]}, "hardware": {"device": "cuda"}}
 torch.manual_seed(0)
 m = build_model(cfg).train()
 opt = torch.optim.AdamW(m.parameters(), lr=1e-4, weight_decay=1e-5)
 crit = DiceCELoss()
-x = torch.randn(B, 2, S, S, S, device="cuda")
+x = torch.randn(B, M, S, S, S, device="cuda")
 y = torch.randint(0, 8, (B, S, S, S), device="cuda")
 def step():
     loss = crit(m(x), y)
