@@ -91,13 +91,19 @@ class TrainEngine:
         stats = self.saved("ws.stats", (n * tile.tiles_per_img * cout * 2,), torch.float32)
         mr = self.saved(name + ".mr", (n, cout, 2), torch.float32)
         K.conv3d(src, pw, a_cb, raw, _lib.OUT_BLOCKED_BF16, stats=stats, dst_cbt=cout // 8, tile=tile)
-        K.instnorm_finalize(stats, n, tile.tiles_per_img, cout, Z * Y * X, mr)
-        mr_apply = mr
-        if chan_scale is not None:  # Dropout3d: relu(y^) * s == relu(y^ * s) for s >= 0 -> fold s into rstd
-            mr_apply = self.saved(name + ".mr_drop", (n, cout, 2), torch.float32)
-            mr_apply.copy_(mr)
-            mr_apply[:, :, 1] *= chan_scale
-        K.instnorm_act_apply(raw, False, mr_apply, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, 0)
+        if chan_scale is None and tile.tiles_per_img <= 256:
+            # statistics finalized in the apply kernel's prologue; the (mean, rstd) table the backward needs is written
+            # by the first block of every (image, channel-block) row
+            K.instnorm_act_apply(raw, False, None, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, 0,
+                                 stats=stats, tiles_per_img=tile.tiles_per_img, mean_rstd_out=mr)
+        else:
+            K.instnorm_finalize(stats, n, tile.tiles_per_img, cout, Z * Y * X, mr)
+            mr_apply = mr
+            if chan_scale is not None:  # Dropout3d: relu(y^) * s == relu(y^ * s) for s >= 0 -> fold s into rstd
+                mr_apply = self.saved(name + ".mr_drop", (n, cout, 2), torch.float32)
+                mr_apply.copy_(mr)
+                mr_apply[:, :, 1] *= chan_scale
+            K.instnorm_act_apply(raw, False, mr_apply, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, 0)
         self.tape.append(dict(kind="cna", name=name, src=src, segs=list(segs), conv=conv, dst=dst, dst_c0=dst_c0,
                               pooled=pooled, slope=slope, raw=raw, mr=mr, gspec=gspec, need_dgrad=need_dgrad,
                               chan_scale=chan_scale, gate_ref=gate_ref))
