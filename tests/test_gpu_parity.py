@@ -100,6 +100,10 @@ def test_input_gradient(kind):
     _c().input_grad_case(kind)
 
 
+def test_trainer_train_validate_resume_predict(tmp_path):
+    _c().trainer_end_to_end_case(tmp_path)
+
+
 def test_pack_unpack_roundtrip():
     _c().pack_roundtrip_case()
 
