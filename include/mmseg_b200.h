@@ -174,6 +174,7 @@ typedef struct {
   const float* shift;         /* [n_img][cb*8] or NULL: y = (x - mean) * rstd + shift before the activation — the
                                  affine norms of ConvBlock3D (GroupNorm / BatchNorm, unet.py:30-38) fold gamma into
                                  rstd and pass beta here; not combined with stats_partial                         */
+  int32_t act;                /* 0: ReLU / LeakyReLU(slope); 1: exact GELU (ConvBlock3D activation="gelu", unet.py:47-48) */
 } mmseg_norm_args;
 int mmseg_instnorm_act_apply(const mmseg_norm_args* args, void* stream);
 

@@ -67,7 +67,7 @@ class NormArgs(C.Structure):
         ("pool_cbt", C.c_int32), ("pool_cb_off", C.c_int32), ("pool_lo_off", C.c_int32),
         ("slope", C.c_float),
         ("stats_partial", C.c_void_p), ("mean_rstd_out", C.c_void_p), ("tiles_per_img", C.c_int32), ("eps", C.c_float),
-        ("shift", C.c_void_p),
+        ("shift", C.c_void_p), ("act", C.c_int32),
     ]
 
 

@@ -101,6 +101,7 @@ struct NormK {
   int dst_cbt, dst_cb_off, dst_lo_off;
   int pool_cbt, pool_cb_off, pool_lo_off;
   float slope;
+  int act;              // 0: ReLU / LeakyReLU(slope); 1: exact GELU (nn.GELU(), ConvBlock3D activation="gelu", unet.py:47-48)
 };
 
 template <bool F32>
@@ -196,6 +197,11 @@ __device__ __forceinline__ void block_mean_rstd(const NormK& k, int img, int c, 
   for (int i = 0; i < 8; ++i) { mean[i] = smr[2 * i]; rstd[i] = smr[2 * i + 1]; }
 }
 
+__device__ __forceinline__ float act_fn(float y, float slope, int act) {
+  if (act == 1) return 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));
+  return y > 0.f ? y : y * slope;
+}
+
 __device__ __forceinline__ void block_shift(const NormK& k, int img, int c, float* sh) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) sh[i] = k.shift ? k.shift[(size_t)img * k.cb * 8 + c * 8 + i] : 0.f;
@@ -229,7 +235,7 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const NormK k) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float y = (x[u][i] - mean[i]) * rstd[i] + sh[i];
-          x[u][i] = y > 0.f ? y : y * k.slope;
+          x[u][i] = act_fn(y, k.slope, k.act);
         }
         store_act8(k.dst, dst_base + v * 8, lo_delta, x[u]);
       }
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(256) instnorm_apply_pool_kernel(const NormK k)
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float y = (x[i] - mean[i]) * rstd[i] + sh[i];
-            x[i] = y > 0.f ? y : y * k.slope;
+            x[i] = act_fn(y, k.slope, k.act);
             mx[i] = fmaxf(mx[i], x[i]);
           }
           store_act8(k.dst, dst_base + v * 8, lo_delta, x);
@@ -380,6 +386,8 @@ extern "C" int mmseg_instnorm_act_apply(const mmseg_norm_args* a, void* stream) 
   k.dst_cbt = a->dst_cbt; k.dst_cb_off = a->dst_cb_off; k.dst_lo_off = a->dst_lo_off;
   k.pool_cbt = a->pool_cbt; k.pool_cb_off = a->pool_cb_off; k.pool_lo_off = a->pool_lo_off;
   k.slope = a->slope;
+  k.act = a->act;
+  if (k.act != 0 && k.act != 1) return fail(MMSEG_ERR_INVALID_ARG, "instnorm_apply: act=%d (0 relu/leaky_relu, 1 gelu)", k.act);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int rows = a->n_img * a->cb;
   if (a->pooled) {

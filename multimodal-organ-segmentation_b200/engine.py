@@ -67,7 +67,7 @@ class ConvRunner:
     # K segments: list of (first channel in src, real channels)
     def conv_norm_act(self, src: Blocked, segs: Sequence[Tuple[int, int]], pw: PackedConv, dst: Blocked, dst_c0: int = 0,
                       pooled: Optional[Blocked] = None, pooled_c0: int = 0, slope: float = 0.0, tag: str = "",
-                      norm=None) -> None:
+                      norm=None, gelu: bool = False) -> None:
         """norm: the block's norm module (reference unet.py:29-41) — None / nn.InstanceNorm3d(affine=False): statistics
         from the conv epilogue; nn.GroupNorm: group statistics from the same partials + affine; nn.BatchNorm3d in eval
         mode: running statistics + affine (no statistics pass at all); nn.Identity: conv + bias + activation.  For the
@@ -83,7 +83,7 @@ class ConvRunner:
         if kind in ("batch", "none"):
             K.conv3d(src, pw, a_cb, raw, out_mode, dst_cbt=cout // 8, tile=tile)
             mr, shift = self._static_table(norm, kind, n, cout, raw.device)
-            K.instnorm_act_apply(raw, raw_f32, mr, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, pooled_c0, shift=shift)
+            K.instnorm_act_apply(raw, raw_f32, mr, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, pooled_c0, shift=shift, gelu=gelu)
             self.launches += 2
             return
         stats = self.ws.get("stats", n * tile.tiles_per_img * cout * 2, torch.float32)
@@ -94,18 +94,18 @@ class ConvRunner:
             ga = norm.weight.detach().float() if norm.weight is not None else None
             be = norm.bias.detach().float() if norm.bias is not None else None
             K.groupnorm_finalize(stats, n, tile.tiles_per_img, cout, norm.num_groups, Z * Y * X, ga, be, mr, shift, norm.eps)
-            K.instnorm_act_apply(raw, raw_f32, mr, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, pooled_c0, shift=shift)
+            K.instnorm_act_apply(raw, raw_f32, mr, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, pooled_c0, shift=shift, gelu=gelu)
             self.launches += 3
         elif tile.tiles_per_img <= 256:
             # InstanceNorm statistics finalized inside the apply kernel's prologue (no separate ~9 us launch); with more
             # partial rows than this the per-block prologue (rows x 64 B from L2) costs more than the launch it saves
             K.instnorm_act_apply(raw, raw_f32, None, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, pooled_c0,
-                                 stats=stats, tiles_per_img=tile.tiles_per_img)
+                                 stats=stats, tiles_per_img=tile.tiles_per_img, gelu=gelu)
             self.launches += 2
         else:
             mr = self.ws.get("mean_rstd", n * cout * 2, torch.float32)
             K.instnorm_finalize(stats, n, tile.tiles_per_img, cout, Z * Y * X, mr)
-            K.instnorm_act_apply(raw, raw_f32, mr, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, pooled_c0)
+            K.instnorm_act_apply(raw, raw_f32, mr, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, pooled_c0, gelu=gelu)
             self.launches += 3
 
     def _static_table(self, norm, kind: str, n: int, cout: int, device):

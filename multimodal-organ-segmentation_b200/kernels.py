@@ -257,11 +257,12 @@ def instnorm_act_apply(raw: Tensor, raw_is_f32: bool, mean_rstd: Optional[Tensor
                        Z: int, Y: int, X: int, dst: Blocked, dst_c0: int = 0, slope: float = 0.0,
                        pooled: Optional[Blocked] = None, pooled_c0: int = 0, *, stats: Optional[Tensor] = None,
                        tiles_per_img: int = 0, eps: float = 1e-5, mean_rstd_out: Optional[Tensor] = None,
-                       shift: Optional[Tensor] = None) -> None:
+                       shift: Optional[Tensor] = None, gelu: bool = False) -> None:
     """stats (the conv epilogue's partials) given: the statistics are finalized inside the apply kernel and
     mean_rstd is not read (no instnorm_finalize launch); mean_rstd_out optionally receives the table."""
     a = _lib.NormArgs()
     a.src, a.dst = raw.data_ptr(), dst.t.data_ptr()
+    a.act = 1 if gelu else 0
     a.mean_rstd = mean_rstd.data_ptr() if mean_rstd is not None else None
     if shift is not None:
         assert stats is None and shift.dtype == torch.float32 and shift.numel() >= n_img * channels

@@ -39,6 +39,8 @@ def _train_step_forward(model: nn.Module, kind: str, x: torch.Tensor) -> torch.T
     """Forward that records the tape for the kernel backward (parameters get gradients; so does the input volume when
     x.requires_grad: the first layers' dgrad then runs as well)."""
     blk = getattr(model, "init_conv", None)
+    if blk is not None and getattr(blk, "activation", "relu") == "gelu":
+        raise NotImplementedError("training with activation='gelu' is not built (the backward kernels cover ReLU / LeakyReLU)")
     if blk is not None and getattr(blk, "norm_type", "instance") != "instance":
         raise NotImplementedError(f"training with model.backbone.norm={blk.norm_type!r} is not built: the backward kernels "
                                   "cover InstanceNorm3d (the reference's default); batch / group / no norm are inference-only")
@@ -87,12 +89,11 @@ class ConvBlock3D(nn.Module):
         self._packed = None
 
     def kernel_supported(self) -> None:
-        if self.activation == "gelu" or self.conv1.kernel_size != (3, 3, 3) \
-                or self.conv1.padding != (1, 1, 1) or self.out_channels % 16:
+        if self.conv1.kernel_size != (3, 3, 3) or self.conv1.padding != (1, 1, 1) or self.out_channels % 16:
             raise NotImplementedError(
                 f"ConvBlock3D(norm={self.norm_type!r}, activation={self.activation!r}, k={self.conv1.kernel_size}, "
                 f"C_out={self.out_channels}) has no sm_100a kernel (covered: instance / group / batch(eval) / no norm, "
-                "relu / leaky_relu, k=3 p=1, C_out % 16 == 0)")
+                "relu / leaky_relu / gelu, k=3 p=1, C_out % 16 == 0)")
 
     @property
     def slope(self) -> float:
@@ -120,8 +121,10 @@ class ConvBlock3D(nn.Module):
             K.pack_ncdhw(x, src)
             mid = Blocked(n, self.out_channels, Z, Y, X, split, x.device)
             out = Blocked(n, self.out_channels, Z, Y, X, split, x.device)
-            self._runner.conv_norm_act(src, [(0, c)], self._packed[1], mid, slope=self.slope, norm=self.norm1)
-            self._runner.conv_norm_act(mid, [(0, self.out_channels)], self._packed[2], out, slope=self.slope, norm=self.norm2)
+            gelu = self.activation == "gelu"
+            self._runner.conv_norm_act(src, [(0, c)], self._packed[1], mid, slope=self.slope, norm=self.norm1, gelu=gelu)
+            self._runner.conv_norm_act(mid, [(0, self.out_channels)], self._packed[2], out, slope=self.slope,
+                                       norm=self.norm2, gelu=gelu)
             return out.to_ncdhw()
 
 

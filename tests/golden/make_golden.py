@@ -154,6 +154,15 @@ def main():
             yn = mn(xn)
         out["unet_norm_" + norm] = {"config": cfgn, "state_dict": mn.state_dict(), "x": xn, "logits": yn}
 
+    # ---- ConvBlock3D(activation="gelu") with group norm (unet.py:36-38,47-48): options only reachable by direct construction
+    torch.manual_seed(40)
+    blkg = ConvBlock3D(16, 32, norm="group", activation="gelu").eval()
+    gg = torch.Generator().manual_seed(41)
+    xg = torch.randn(2, 16, 8, 10, 12, generator=gg)
+    with torch.no_grad():
+        yg = blkg(xg)
+    out["convblock_gelu_group"] = {"state_dict": blkg.state_dict(), "x": xg, "y": yg}
+
     only = set(sys.argv[1:])      # python make_golden.py [name ...]: write only these fixtures (all are seeded)
     for k, v in out.items():
         if only and k not in only:

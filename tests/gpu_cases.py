@@ -802,6 +802,21 @@ def trainer_end_to_end_case(tmp_dir):
     assert agree >= 0.995
 
 
+def convblock_gelu_group_golden_case(mode="parity"):
+    """ConvBlock3D(norm="group", activation="gelu") module vs the reference's own output."""
+    from mmseg_b200.src.models.backbones.unet import ConvBlock3D
+    g = _gold("convblock_gelu_group")
+    blk = ConvBlock3D(16, 32, norm="group", activation="gelu").eval()
+    blk.load_state_dict(g["state_dict"], strict=True)
+    blk = blk.to(DEV)
+    blk.numeric_mode = mode
+    with torch.no_grad():
+        got = blk(g["x"].to(DEV)).cpu()
+    tol = 2e-3 if mode == "parity" else 8e-2
+    err = _report(f"ConvBlock3D gelu+group mode={mode}", got, g["y"], tol)
+    assert err <= tol
+
+
 def focal_tversky_golden_case():
     """Focal / Tversky loss kernels (value + gradient) vs the reference's own outputs (tests/golden/losses.pt)."""
     from mmseg_b200.src.trainer.losses import FocalLoss, TverskyLoss, get_loss

@@ -104,6 +104,11 @@ def test_trainer_train_validate_resume_predict(tmp_path):
     _c().trainer_end_to_end_case(tmp_path)
 
 
+@pytest.mark.parametrize("mode", ["parity", "bf16"])
+def test_convblock_gelu_group_golden(mode):
+    _c().convblock_gelu_group_golden_case(mode)
+
+
 def test_pack_unpack_roundtrip():
     _c().pack_roundtrip_case()
 

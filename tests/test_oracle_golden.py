@@ -40,6 +40,12 @@ def test_unet_norm_options(norm):
         _close(OM.unet3d_forward(g["state_dict"], g["x"]), g["logits"], atol=5e-5, rtol=1e-4)
 
 
+def test_convblock_gelu_group_option():
+    g = load("convblock_gelu_group")
+    sd = {"b." + k: v for k, v in g["state_dict"].items()}
+    _close(OM.conv_block3d(sd, "b", g["x"], activation="gelu", norm="group"), g["y"], atol=5e-5, rtol=1e-4)
+
+
 def test_convblock_leaky_relu_option():
     g = load("convblock_leaky")
     sd = {"b." + k: v for k, v in g["state_dict"].items()}
