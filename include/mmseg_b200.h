@@ -215,6 +215,12 @@ int mmseg_unshuffle_k2s2(const void* src, int32_t n_img, int32_t src_cbt, int32_
 int mmseg_pack_ncdhw(const float* src, void* dst, int32_t n_img, int32_t C, int32_t Z, int32_t Y, int32_t X,
                      int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, int32_t cb, void* stream);
 /* blocked bf16 (hi[, lo]) -> NCDHW fp32 (feature taps for return_features / hooks). */
+/* mmseg_pack_ncdhw with SUVGuidedAttention's element-wise steps folded in (fusion/attention_fusion.py:283-292):
+ * pre_sigmoid: x <- sigmoid((x - pre_sub) * pre_mul) (soft SUV mask); gate_logits [n_img][voxels] fp32 or NULL:
+ * x <- x * (1 + sigmoid(gate)) (CT features modulated by the spatial attention). */
+int mmseg_pack_ncdhw_ex(const float* src, void* dst, int32_t n_img, int32_t C, int32_t Z, int32_t Y, int32_t X,
+                        int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, int32_t cb, int32_t pre_sigmoid,
+                        float pre_sub, float pre_mul, const float* gate_logits, void* stream);
 int mmseg_unpack_ncdhw(const void* src, float* dst, int32_t n_img, int32_t C, int32_t Z, int32_t Y, int32_t X,
                        int32_t src_cbt, int32_t src_cb_off, int32_t src_lo_off, void* stream);
 

@@ -308,6 +308,32 @@ pack_ncdhw_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst
   }
 }
 
+// pack with the two element-wise steps of SUVGuidedAttention (fusion/attention_fusion.py:283-292) folded in:
+//   pre:  x <- sigmoid((x - pre_sub) * pre_mul)          (the soft SUV mask of the 1-channel PET image), and / or
+//   gate: x <- x * (1 + sigmoid(gate[img][voxel]))        (CT features modulated by the spatial attention LOGITS)
+__global__ void __launch_bounds__(256)
+pack_ncdhw_ex_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n_img, int C, size_t nvox,
+                     int dst_cbt, int dst_cb_off, int dst_lo_off, int cb, int pre, float pre_sub, float pre_mul,
+                     const float* __restrict__ gate) {
+  const int blk = blockIdx.y;  // img*cb + c
+  const int img = blk / cb, c = blk - img * cb;
+  const size_t dst_base = (size_t)(img * dst_cbt + dst_cb_off + c) * nvox * 8;
+  const size_t lo_delta = (size_t)dst_lo_off * nvox * 8;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
+    float g = 1.f;
+    if (gate) g = 1.f + 1.f / (1.f + expf(-gate[(size_t)img * nvox + v]));
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ch = c * 8 + i;
+      float t = ch < C ? src[((size_t)img * C + ch) * nvox + v] : 0.f;
+      if (pre && ch < C) t = 1.f / (1.f + expf(-(t - pre_sub) * pre_mul));
+      x[i] = t * g;
+    }
+    store_act8(dst, dst_base + v * 8, lo_delta, x);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 unpack_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int n_img, int C, size_t nvox,
                     int src_cbt, int src_cb_off, int src_lo_off) {
@@ -415,6 +441,19 @@ extern "C" int mmseg_pack_ncdhw(const float* src, void* dst, int32_t n_img, int3
   pack_ncdhw_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       src, reinterpret_cast<__nv_bfloat16*>(dst), n_img, C, nvox, dst_cbt, dst_cb_off, dst_lo_off, cb);
   return check_launch("pack_ncdhw_kernel");
+}
+
+extern "C" int mmseg_pack_ncdhw_ex(const float* src, void* dst, int32_t n_img, int32_t C, int32_t Z, int32_t Y, int32_t X,
+                                   int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, int32_t cb, int32_t pre_sigmoid,
+                                   float pre_sub, float pre_mul, const float* gate_logits, void* stream) {
+  if (!src || !dst || n_img < 1 || C < 1 || cb * 8 < C) return fail(MMSEG_ERR_INVALID_ARG, "pack_ncdhw_ex: bad arguments");
+  const size_t nvox = (size_t)Z * Y * X;
+  const int rows = n_img * cb;
+  dim3 grid(grid_x_for(nvox, rows), rows);
+  pack_ncdhw_ex_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), n_img, C, nvox, dst_cbt, dst_cb_off, dst_lo_off, cb, pre_sigmoid ? 1 : 0,
+      pre_sub, pre_mul, gate_logits);
+  return check_launch("pack_ncdhw_ex_kernel");
 }
 
 extern "C" int mmseg_unpack_ncdhw(const void* src, float* dst, int32_t n_img, int32_t C, int32_t Z, int32_t Y,

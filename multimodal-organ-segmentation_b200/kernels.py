@@ -286,6 +286,21 @@ def instnorm_act_apply(raw: Tensor, raw_is_f32: bool, mean_rstd: Optional[Tensor
     _call("mmseg_instnorm_act_apply", C.byref(a), _stream())
 
 
+def pack_ncdhw_ex(x: Tensor, dst: Blocked, c0: int = 0, pre_sigmoid: Optional[Tuple[float, float]] = None,
+                  gate_logits: Optional[Tensor] = None) -> None:
+    """pack_ncdhw with x <- sigmoid((x - a) * b) (pre_sigmoid = (a, b)) and / or x <- x * (1 + sigmoid(gate)) folded in
+    (gate_logits [n_img, 1, Z, Y, X] fp32): the element-wise steps of SUVGuidedAttention."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    n, Cc, Z, Y, X = x.shape
+    cb = (Cc + 15) // 16 * 2
+    a, b = pre_sigmoid if pre_sigmoid is not None else (0.0, 1.0)
+    if gate_logits is not None:
+        assert gate_logits.dtype == torch.float32 and gate_logits.is_contiguous() and gate_logits.numel() == n * Z * Y * X
+    _call("mmseg_pack_ncdhw_ex", _ptr(x), _ptr(dst.t), n, Cc, Z, Y, X, dst.cbt, c0 // 8, dst.lo_off, cb,
+          1 if pre_sigmoid is not None else 0, float(a), float(b), _ptr(gate_logits) if gate_logits is not None else None,
+          _stream())
+
+
 def swi_gather(volume: Tensor, starts_dev: Tensor, n_win: int, roi: Tuple[int, int, int], dst: Blocked) -> None:
     Cc, VZ, VY, VX = volume.shape
     # only the channel blocks that hold real channels are written: the zero padding up to a whole 16-channel K chunk

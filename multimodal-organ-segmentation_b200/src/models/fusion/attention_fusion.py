@@ -180,3 +180,65 @@ class BidirectionalCrossAttention(nn.Module):
             out = Blocked(B, C, Z, Y, X, False, dev)
             self._runner.conv_norm_act(cat, [(0, C), (C, C)], pw, out)
             return out.to_ncdhw()
+
+
+class SUVGuidedAttention(nn.Module):
+    """reference attention_fusion.py:219-295: high-SUV regions of the PET image gate the CT features.
+
+    Same constructor / parameters / state_dict (threshold buffer or parameter, spatial_attn.{0,2}, feature_mod.0).  The
+    arithmetic: trilinear resize (kernel), soft mask folded into the blocked pack, the two 3x3x3 convs on the tcgen05
+    kernel (bias + ReLU through the norm-less apply; 1-channel logits as NCDHW fp32), the sigmoid gate CT * (1 + a) folded
+    into the pack of the CT features, Conv3d(C, C, 1) + InstanceNorm3d (no activation) through the conv / norm kernels."""
+
+    def __init__(self, in_channels: int, suv_threshold: float = 2.5, learnable_threshold: bool = False):
+        super().__init__()
+        self.in_channels = in_channels
+        if learnable_threshold:
+            self.threshold = nn.Parameter(torch.tensor(suv_threshold))
+        else:
+            self.register_buffer("threshold", torch.tensor(suv_threshold))
+        self.spatial_attn = nn.Sequential(
+            nn.Conv3d(1, 16, kernel_size=3, padding=1),
+            nn.ReLU(inplace=True),
+            nn.Conv3d(16, 1, kernel_size=3, padding=1),
+            nn.Sigmoid(),
+        )
+        self.feature_mod = nn.Sequential(
+            nn.Conv3d(in_channels, in_channels, kernel_size=1),
+            nn.InstanceNorm3d(in_channels),
+        )
+        self.out_channels = in_channels
+        self._runner = None
+
+    def forward(self, ct_features: torch.Tensor, pet_suv: torch.Tensor) -> torch.Tensor:
+        _require_cuda(ct_features)
+        _no_autograd(self, ct_features)
+        if self.in_channels % 16:
+            raise NotImplementedError("SUVGuidedAttention kernels need channels % 16 == 0")
+        with torch.no_grad():
+            dev = ct_features.device
+            ct = ct_features.contiguous().float()
+            pet = pet_suv.contiguous().float()
+            B, C, Z, Y, X = ct.shape
+            if tuple(pet.shape[2:]) != (Z, Y, X):
+                pet = K.trilinear_resize(pet, (Z, Y, X))
+            if self._runner is None:
+                self._runner = ConvRunner(False, dev)
+            r = self._runner
+            # soft SUV mask, packed straight into the first conv's (padded) input
+            m = Blocked(B, 16, Z, Y, X, False, dev)
+            K.pack_ncdhw_ex(pet, m, pre_sigmoid=(float(self.threshold), 2.0))
+            c1, c2 = self.spatial_attn[0], self.spatial_attn[2]
+            h = Blocked(B, 16, Z, Y, X, False, dev)
+            r.conv_norm_act(m, [(0, 1)], K.pack_conv_weight(c1.weight, c1.bias, False, [1]), h, norm=nn.Identity())
+            gate = torch.empty((B, 1, Z, Y, X), dtype=torch.float32, device=dev)       # attention LOGITS (pre-sigmoid)
+            pw2 = K.pack_conv_weight(c2.weight, c2.bias, False, [16])
+            K.conv3d(h, pw2, K.a_chunk_table(h, [0], [16], False), gate, _lib.OUT_NCDHW_F32)
+            # CT * (1 + sigmoid(logits)) folded into the pack of the CT features
+            att = Blocked(B, C, Z, Y, X, False, dev)
+            K.pack_ncdhw_ex(ct, att, gate_logits=gate)
+            fm = self.feature_mod[0]
+            out = Blocked(B, C, Z, Y, X, False, dev)
+            # Conv3d(C, C, 1) + InstanceNorm3d without activation: LeakyReLU with slope 1 is the identity
+            r.conv_norm_act(att, [(0, C)], K.pack_conv_weight(fm.weight, None, False, [C], use_bias=False), out, slope=1.0)
+            return out.to_ncdhw()

@@ -185,6 +185,22 @@ def bidirectional_cross_attention(sd: SD, f1: Tensor, f2: Tensor, num_heads: int
     return F.relu(F.instance_norm(y, eps=1e-5))
 
 
+def suv_guided_attention(sd: SD, ct_features: Tensor, pet_suv: Tensor, prefix: str = "", dtype=torch.float32) -> Tensor:
+    """SUVGuidedAttention.forward — fusion/attention_fusion.py:266-295: resize PET to the CT feature grid, soft SUV mask
+    sigmoid((suv - threshold) * 2), spatial attention Conv3d(1,16,3)+ReLU+Conv3d(16,1,3)+Sigmoid, CT * (1 + attention),
+    Conv3d(C,C,1) + InstanceNorm3d."""
+    ct = ct_features.detach().to("cpu", dtype)
+    pet = pet_suv.detach().to("cpu", dtype)
+    if pet.shape[2:] != ct.shape[2:]:
+        pet = F.interpolate(pet, size=ct.shape[2:], mode="trilinear", align_corners=True)
+    mask = torch.sigmoid((pet - _p(sd, prefix + "threshold", dtype)) * 2)
+    a = F.relu(F.conv3d(mask, _p(sd, prefix + "spatial_attn.0.weight", dtype), _p(sd, prefix + "spatial_attn.0.bias", dtype), padding=1))
+    a = torch.sigmoid(F.conv3d(a, _p(sd, prefix + "spatial_attn.2.weight", dtype), _p(sd, prefix + "spatial_attn.2.bias", dtype), padding=1))
+    y = ct * (1 + a)
+    y = F.conv3d(y, _p(sd, prefix + "feature_mod.0.weight", dtype), _p(sd, prefix + "feature_mod.0.bias", dtype))
+    return F.instance_norm(y, eps=1e-5)
+
+
 def attention_fusion(sd: SD, feats: Sequence[Tensor], prefix: str = "", dtype=torch.float32) -> Tensor:
     """AttentionFusion.forward — attention_fusion.py:48-74 (same maths as CrossModalAttention)."""
     feats = [f.detach().to("cpu", dtype) for f in feats]

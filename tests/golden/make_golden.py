@@ -163,6 +163,20 @@ def main():
         yg = blkg(xg)
     out["convblock_gelu_group"] = {"state_dict": blkg.state_dict(), "x": xg, "y": yg}
 
+    # ---- SUVGuidedAttention (attention_fusion.py:219-295), PET given at half resolution (exercises the trilinear resize)
+    from src.models.fusion.attention_fusion import SUVGuidedAttention
+    torch.manual_seed(50)
+    suv = SUVGuidedAttention(32, suv_threshold=1.2).eval()
+    gs = torch.Generator().manual_seed(51)
+    ctf = torch.randn(2, 32, 8, 10, 12, generator=gs)
+    pets = torch.rand(2, 1, 4, 5, 6, generator=gs) * 4.0
+    with torch.no_grad():
+        ys = suv(ctf, pets)
+        ys_same = suv(ctf, torch.rand(2, 1, 8, 10, 12, generator=torch.Generator().manual_seed(52)) * 4.0)
+    out["suv_guided_attention"] = {"state_dict": suv.state_dict(), "ct": ctf, "pet": pets, "y": ys,
+                                   "pet_same": torch.rand(2, 1, 8, 10, 12, generator=torch.Generator().manual_seed(52)) * 4.0,
+                                   "y_same": ys_same}
+
     only = set(sys.argv[1:])      # python make_golden.py [name ...]: write only these fixtures (all are seeded)
     for k, v in out.items():
         if only and k not in only:

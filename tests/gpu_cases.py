@@ -817,6 +817,21 @@ def convblock_gelu_group_golden_case(mode="parity"):
     assert err <= tol
 
 
+def suv_guided_attention_golden_case():
+    """SUVGuidedAttention module vs the reference's own outputs (PET at half and at full resolution)."""
+    from mmseg_b200.src.models.fusion.attention_fusion import SUVGuidedAttention
+    g = _gold("suv_guided_attention")
+    m = SUVGuidedAttention(32, suv_threshold=1.2).eval()
+    m.load_state_dict(g["state_dict"], strict=True)
+    m = m.to(DEV)
+    with torch.no_grad():
+        for pet, want, tag in ((g["pet"], g["y"], "half-res PET"), (g["pet_same"], g["y_same"], "full-res PET")):
+            got = m(g["ct"].to(DEV), pet.to(DEV)).cpu()
+            rel = ((got - want).norm() / want.norm()).item()
+            err = _report(f"SUVGuidedAttention {tag} (rel_l2 {rel:.2e})", got, want, 8e-2)
+            assert err <= 8e-2 and rel <= 2e-2          # bf16 path: the output is an InstanceNorm (unit variance)
+
+
 def focal_tversky_golden_case():
     """Focal / Tversky loss kernels (value + gradient) vs the reference's own outputs (tests/golden/losses.pt)."""
     from mmseg_b200.src.trainer.losses import FocalLoss, TverskyLoss, get_loss

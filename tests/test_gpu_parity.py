@@ -109,6 +109,10 @@ def test_convblock_gelu_group_golden(mode):
     _c().convblock_gelu_group_golden_case(mode)
 
 
+def test_suv_guided_attention_golden():
+    _c().suv_guided_attention_golden_case()
+
+
 def test_pack_unpack_roundtrip():
     _c().pack_roundtrip_case()
 

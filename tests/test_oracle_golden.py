@@ -40,6 +40,12 @@ def test_unet_norm_options(norm):
         _close(OM.unet3d_forward(g["state_dict"], g["x"]), g["logits"], atol=5e-5, rtol=1e-4)
 
 
+def test_suv_guided_attention():
+    g = load("suv_guided_attention")
+    _close(OM.suv_guided_attention(g["state_dict"], g["ct"], g["pet"]), g["y"], atol=5e-5, rtol=1e-4)
+    _close(OM.suv_guided_attention(g["state_dict"], g["ct"], g["pet_same"]), g["y_same"], atol=5e-5, rtol=1e-4)
+
+
 def test_convblock_gelu_group_option():
     g = load("convblock_gelu_group")
     sd = {"b." + k: v for k, v in g["state_dict"].items()}
