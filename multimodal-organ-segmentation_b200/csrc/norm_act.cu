@@ -208,13 +208,15 @@ __device__ __forceinline__ void block_shift(const NormK& k, int img, int c, floa
 }
 
 // grid: (chunks over voxels, n_img*cb).  One 8-channel vector per thread-iteration.
-template <bool F32>
-__global__ void __launch_bounds__(256) instnorm_apply_kernel(const NormK k) {
+// EXT = additive shift and / or GELU (the affine norms / gelu option): kept out of the default instantiation, whose
+// register count decides how many loads are in flight (80 -> 93 registers cost a resident block per SM)
+template <bool F32, bool EXT>
+__global__ void __launch_bounds__(256, 3) instnorm_apply_kernel(const NormK k) {
   const int blk = blockIdx.y;  // img*cb + c
   const int img = blk / k.cb, c = blk - img * k.cb;
   float mean[8], rstd[8], sh[8];
   block_mean_rstd(k, img, c, mean, rstd);
-  block_shift(k, img, c, sh);
+  if constexpr (EXT) block_shift(k, img, c, sh);
   const size_t nvox = (size_t)k.Z * k.Y * k.X;
   const size_t src_base = (size_t)blk * nvox * 8;
   const size_t dst_base = (size_t)(img * k.dst_cbt + k.dst_cb_off + c) * nvox * 8;
@@ -234,8 +236,12 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const NormK k) {
       if (v < nvox) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float y = (x[u][i] - mean[i]) * rstd[i] + sh[i];
-          x[u][i] = act_fn(y, k.slope, k.act);
+          if constexpr (EXT) {
+            x[u][i] = act_fn((x[u][i] - mean[i]) * rstd[i] + sh[i], k.slope, k.act);
+          } else {
+            const float y = (x[u][i] - mean[i]) * rstd[i];
+            x[u][i] = y > 0.f ? y : y * k.slope;
+          }
         }
         store_act8(k.dst, dst_base + v * 8, lo_delta, x[u]);
       }
@@ -244,13 +250,13 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const NormK k) {
 }
 
 // Variant that also emits MaxPool3d(2): one 2x2x2 cell per thread-iteration (Z, Y, X even).
-template <bool F32>
+template <bool F32, bool EXT>
 __global__ void __launch_bounds__(256) instnorm_apply_pool_kernel(const NormK k) {
   const int blk = blockIdx.y;
   const int img = blk / k.cb, c = blk - img * k.cb;
   float mean[8], rstd[8], sh[8];
   block_mean_rstd(k, img, c, mean, rstd);
-  block_shift(k, img, c, sh);
+  if constexpr (EXT) block_shift(k, img, c, sh);
   const int Zh = k.Z / 2, Yh = k.Y / 2, Xh = k.X / 2;
   const size_t nvox = (size_t)k.Z * k.Y * k.X;
   const size_t ncell = (size_t)Zh * Yh * Xh;
@@ -279,8 +285,12 @@ __global__ void __launch_bounds__(256) instnorm_apply_pool_kernel(const NormK k)
           load8<F32>(k.src, src_base + v * 8, x);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float y = (x[i] - mean[i]) * rstd[i] + sh[i];
-            x[i] = act_fn(y, k.slope, k.act);
+            if constexpr (EXT) {
+              x[i] = act_fn((x[i] - mean[i]) * rstd[i] + sh[i], k.slope, k.act);
+            } else {
+              const float y = (x[i] - mean[i]) * rstd[i];
+              x[i] = y > 0.f ? y : y * k.slope;
+            }
             mx[i] = fmaxf(mx[i], x[i]);
           }
           store_act8(k.dst, dst_base + v * 8, lo_delta, x);
@@ -416,17 +426,28 @@ extern "C" int mmseg_instnorm_act_apply(const mmseg_norm_args* a, void* stream) 
   if (k.act != 0 && k.act != 1) return fail(MMSEG_ERR_INVALID_ARG, "instnorm_apply: act=%d (0 relu/leaky_relu, 1 gelu)", k.act);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int rows = a->n_img * a->cb;
+  const bool ext = k.shift != nullptr || k.act != 0;
   if (a->pooled) {
     if ((a->Z | a->Y | a->X) & 1) return fail(MMSEG_ERR_UNSUPPORTED, "instnorm_apply: fused MaxPool3d(2) needs even extents");
     const size_t ncell = (size_t)(a->Z / 2) * (a->Y / 2) * (a->X / 2);
     dim3 grid(grid_x_for(ncell, rows), rows);
-    if (a->src_is_f32) instnorm_apply_pool_kernel<true><<<grid, 256, 0, st>>>(k);
-    else instnorm_apply_pool_kernel<false><<<grid, 256, 0, st>>>(k);
+    if (ext) {
+      if (a->src_is_f32) instnorm_apply_pool_kernel<true, true><<<grid, 256, 0, st>>>(k);
+      else instnorm_apply_pool_kernel<false, true><<<grid, 256, 0, st>>>(k);
+    } else {
+      if (a->src_is_f32) instnorm_apply_pool_kernel<true, false><<<grid, 256, 0, st>>>(k);
+      else instnorm_apply_pool_kernel<false, false><<<grid, 256, 0, st>>>(k);
+    }
   } else {
     const size_t nvox = (size_t)a->Z * a->Y * a->X;
     dim3 grid(grid_x_for(nvox, rows), rows);
-    if (a->src_is_f32) instnorm_apply_kernel<true><<<grid, 256, 0, st>>>(k);
-    else instnorm_apply_kernel<false><<<grid, 256, 0, st>>>(k);
+    if (ext) {
+      if (a->src_is_f32) instnorm_apply_kernel<true, true><<<grid, 256, 0, st>>>(k);
+      else instnorm_apply_kernel<false, true><<<grid, 256, 0, st>>>(k);
+    } else {
+      if (a->src_is_f32) instnorm_apply_kernel<true, false><<<grid, 256, 0, st>>>(k);
+      else instnorm_apply_kernel<false, false><<<grid, 256, 0, st>>>(k);
+    }
   }
   return check_launch("instnorm_apply_kernel");
 }
