@@ -86,23 +86,24 @@ groupnorm_finalize_kernel(const float* __restrict__ part, int n_img, int tiles, 
 }
 
 // ---------------------------------------------------------------------------------------------- apply
-struct NormK {
+struct NormK {   // kept at exactly 128 bytes: one more field and the default apply kernel goes from 80 to 88 registers
   const void* src;
   const float* mr;
-  const float* shift;   // optional [n_img][C]: y = (x - mean) * rstd + shift (affine norms: GroupNorm / BatchNorm beta)
   const float* stats;   // optional: per-tile (sum, sum of squares) partials [n_img][tiles][C][2] -> finalized in the prologue
   float* mr_out;        // optional: where block x == 0 of each row publishes the (mean, rstd) it derived
-  int tiles;
-  double inv_n;
-  float eps;
   __nv_bfloat16* dst;
   __nv_bfloat16* pooled;
+  const float* shift;   // optional [n_img][C]: y = (x - mean) * rstd + shift (affine norms: GroupNorm / BatchNorm beta)
+  double inv_n;
+  int tiles;
   int n_img, cb, Z, Y, X;
   int dst_cbt, dst_cb_off, dst_lo_off;
   int pool_cbt, pool_cb_off, pool_lo_off;
+  float eps;
   float slope;
   int act;              // 0: ReLU / LeakyReLU(slope); 1: exact GELU (nn.GELU(), ConvBlock3D activation="gelu", unet.py:47-48)
 };
+static_assert(sizeof(NormK) <= 128, "NormK must stay within 128 bytes (register allocation of the apply kernels)");
 
 template <bool F32>
 __device__ __forceinline__ void load8(const void* base, size_t elem_off, float* v) {
@@ -211,7 +212,7 @@ __device__ __forceinline__ void block_shift(const NormK& k, int img, int c, floa
 // EXT = additive shift and / or GELU (the affine norms / gelu option): kept out of the default instantiation, whose
 // register count decides how many loads are in flight (80 -> 93 registers cost a resident block per SM)
 template <bool F32, bool EXT>
-__global__ void __launch_bounds__(256, 3) instnorm_apply_kernel(const NormK k) {
+__global__ void __launch_bounds__(256) instnorm_apply_kernel(const NormK k) {
   const int blk = blockIdx.y;  // img*cb + c
   const int img = blk / k.cb, c = blk - img * k.cb;
   float mean[8], rstd[8], sh[8];

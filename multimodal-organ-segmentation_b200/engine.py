@@ -96,9 +96,10 @@ class ConvRunner:
             K.groupnorm_finalize(stats, n, tile.tiles_per_img, cout, norm.num_groups, Z * Y * X, ga, be, mr, shift, norm.eps)
             K.instnorm_act_apply(raw, raw_f32, mr, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, pooled_c0, shift=shift, gelu=gelu)
             self.launches += 3
-        elif tile.tiles_per_img <= 256:
-            # InstanceNorm statistics finalized inside the apply kernel's prologue (no separate ~9 us launch); with more
-            # partial rows than this the per-block prologue (rows x 64 B from L2) costs more than the launch it saves
+        elif tile.tiles_per_img <= 64:
+            # InstanceNorm statistics finalized inside the apply kernel's prologue (no separate ~9 us launch) for the deep,
+            # latency-bound levels; with more partial rows the per-block prologue (rows x 64 B from L2) shows up in the
+            # HBM-bound apply kernels of the 96^3 / 48^3 levels (measured: 5.2 -> 4.5 TB/s), so those keep the launch
             K.instnorm_act_apply(raw, raw_f32, None, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, pooled_c0,
                                  stats=stats, tiles_per_img=tile.tiles_per_img, gelu=gelu)
             self.launches += 2

@@ -91,7 +91,7 @@ class TrainEngine:
         stats = self.saved("ws.stats", (n * tile.tiles_per_img * cout * 2,), torch.float32)
         mr = self.saved(name + ".mr", (n, cout, 2), torch.float32)
         K.conv3d(src, pw, a_cb, raw, _lib.OUT_BLOCKED_BF16, stats=stats, dst_cbt=cout // 8, tile=tile)
-        if chan_scale is None and tile.tiles_per_img <= 256:
+        if chan_scale is None and tile.tiles_per_img <= 64:
             # statistics finalized in the apply kernel's prologue; the (mean, rstd) table the backward needs is written
             # by the first block of every (image, channel-block) row
             K.instnorm_act_apply(raw, False, None, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, 0,
