@@ -32,7 +32,7 @@ OVERLAP = 0.5
 MODE = "gaussian"
 FEATURES = [32, 64, 128, 256, 512]
 GF_PER_WINDOW = 403.2          # UNet3D(2->8) forward at 96^3, conv-type layers, 2*MACs
-CROP = (192, 192, 144)         # exactly 18 windows: the bounded CPU sample / parity sample
+CROP = (192, 192, 240)         # exactly 36 windows (3 x 3 x 4): the bounded CPU sample (~14 s) / parity sample
 
 
 def log(*a):
@@ -347,8 +347,8 @@ def run_ours(args):
         vol_cpu = vol_host.clone()
         t, n_win, ref_logits = cpu_sample(sd_o, vol_cpu, CROP, threads)
         cpu_baseline = {"value": full_volume_equiv(t, n_win), "unit": "voxels/s", "cores": threads, "kind": "port",
-                        "sample": f"{n_win} of the 600 windows (192x192x144 crop of the same volume, {t:.1f} s), "
-                                  "extrapolated x600/18; oracle = CPU fp32 restatement of the reference"}
+                        "sample": f"{n_win} of the 600 windows ({CROP[0]}x{CROP[1]}x{CROP[2]} crop of the same volume, "
+                                  f"{t:.1f} s), extrapolated x600/{n_win}; oracle = CPU fp32 restatement of the reference"}
         ref_lab = ref_logits.argmax(1)[0]
         parity = {}
         crop_dev = vol_dev[:, :CROP[0], :CROP[1], :CROP[2]].contiguous()
