@@ -69,6 +69,7 @@ int mmseg_device_ok(void);
  * the InstanceNorm3d statistics (unet.py:34-35) are produced by the conv epilogue, deterministically (no atomics).
  */
 #define MMSEG_CONV_ROLL_Z 16
+#define MMSEG_CONV_ROLL_KPAIR 32   /* rolling-z: one TMA stage = two adjacent K chunks (4 channel blocks) */
 typedef struct {
   const void* src;       /* blocked bf16 [n_img*src_cbt][Z][Y][X][8]                                  */
   const void* weights;   /* packed bf16, see layout above                                             */

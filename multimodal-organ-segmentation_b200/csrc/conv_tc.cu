@@ -35,6 +35,7 @@ struct ConvKParams {
   int w_resident;     // k=1 only: every K chunk's weights stay in shared memory for the CTA's lifetime (one load)
   int n_tiles;        // voxel tiles (all images) swept by the persistent CTAs of one N tile
   int roll;           // rolling-z kernel (conv3d_roll_kernel): TZ = z-segment length, tiles_z = segments per column
+  int kpb;            // rolling-z: K chunks per TMA stage (2: one 4-block box per plane step, half the stage operations)
   int R;              // rolling-z: TMEM ring slots (output planes in flight) = tmem_cols / NT
   int acc_bufs;       // 1 or 2 accumulator sets in TMEM (2: the epilogue of tile i overlaps the MMAs of tile i+1)
   uint32_t buf_cols;  // TMEM columns between the two sets
@@ -747,7 +748,7 @@ conv3d_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int q = 0; q < zsv + 2; ++q) {
           const int z = zs0 - 1 + q;
           if (z < 0 || z >= p.Z) continue;
-          for (int kc = 0; kc < p.n_kchunks; ++kc) {
+          for (int kc = 0; kc < p.n_kchunks; kc += p.kpb) {   // one box = kpb K chunks = 2*kpb consecutive channel blocks
             const uint32_t afull = smem_u32(&hdr->a_full[stage]);
             mbar_wait(smem_u32(&hdr->a_empty[stage]), ph ^ 1);
             mbar_arrive_expect_tx(afull, p.a_tx_bytes);
@@ -781,7 +782,10 @@ conv3d_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint32_t a_stage0 = ((a_smem >> 4) & 0x3FFFu) | a_lbo;
       const uint32_t a_stage_step = p.stage_bytes >> 4;
       const uint32_t w_base0 = ((w_smem >> 4) & 0x3FFFu) | b_lbo;
-      const uint32_t w_step = p.w_bytes >> 4;
+      const uint32_t w_step = p.w_bytes >> 4;                  // one K chunk of weights
+      const uint32_t a_chunk = 2u * (p.plane_bytes >> 4);      // one K chunk (two channel blocks) inside a stage
+      const int kpb = p.kpb;
+      const int n_st = p.n_kchunks / kpb;                      // stages per input plane
       const uint32_t a_full0 = smem_u32(&hdr->a_full[0]), a_empty0 = smem_u32(&hdr->a_empty[0]);
       const uint32_t z_full0 = smem_u32(&hdr->z_full[0]), z_empty0 = smem_u32(&hdr->z_empty[0]);
       const int txy = p.tiles_x * p.tiles_y;
@@ -813,7 +817,7 @@ conv3d_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         d.abar = a_empty0 + stage * 8u;
         d.afull = a_full0 + stage * 8u;
         d.apar = ph;
-        const uint32_t bb = w_base0 + (uint32_t)kc * w_step + (uint32_t)(KT - 1 - dz_hi) * NT;
+        const uint32_t bb = w_base0 + (uint32_t)(kc * kpb) * w_step + (uint32_t)(KT - 1 - dz_hi) * NT;
         d.bta = bb;
         d.d0a = tmem_base + col * NT;
         d.ida = make_idesc_bf16(128, n1 * NT);
@@ -821,14 +825,14 @@ conv3d_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         d.idb = n > n1 ? make_idesc_bf16(128, (n - n1) * NT) : 0u;
         d.zneed = gz + (uint32_t)min(q, zsv - 1) + 1u;        // ring slots [.., zneed) must be acquired before this stage
         d.zc0 = 0u; d.zc1 = 0u;
-        if (kc == p.n_kchunks - 1) {                          // last K chunk of plane q: output plane q-2 is complete
+        if (kc == n_st - 1) {                                 // last stage of plane q: output plane q-2 is complete
           if (q >= 2) d.zc0 = z_full0 + ((gz + (uint32_t)(q - 2)) & (R - 1)) * 8u;
           if (q == q_last && q_last == zsv)                   // top halo plane outside the volume: zsv-1 completes too
             d.zc1 = z_full0 + ((gz + (uint32_t)(zsv - 1)) & (R - 1)) * 8u;
         }
         // advance
         if (++stage == (uint32_t)p.stages) { stage = 0; ph ^= 1u; }
-        if (++kc == p.n_kchunks) {
+        if (++kc == n_st) {
           kc = 0;
           if (++q > q_last) {
             gz += (uint32_t)zsv;
@@ -865,6 +869,15 @@ conv3d_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (cur.idb) {
 #pragma unroll
           for (int i = 0; i < KT * KT; ++i) umma_lohi(tmem_base, cur.at0 + a_tap[i], a_hi, cur.btb + b_tap[i], b_hi, cur.idb);
+        }
+        if (kpb == 2) {   // second K chunk of the stage: channel blocks 2, 3 of the box, next chunk of weights
+          const uint32_t a1 = cur.at0 + a_chunk, b1 = cur.bta + w_step, b1b = cur.btb + w_step;
+#pragma unroll
+          for (int i = 0; i < KT * KT; ++i) umma_lohi(cur.d0a, a1 + a_tap[i], a_hi, b1 + b_tap[i], b_hi, cur.ida);
+          if (cur.idb) {
+#pragma unroll
+            for (int i = 0; i < KT * KT; ++i) umma_lohi(tmem_base, a1 + a_tap[i], a_hi, b1b + b_tap[i], b_hi, cur.idb);
+          }
         }
         umma_commit(cur.abar);
         if (cur.zc0) umma_commit(cur.zc0);
@@ -1070,7 +1083,14 @@ static int plan_conv(const mmseg_conv_args* a, ConvPlan* out) {
   k.w_bytes = (uint32_t)taps * a->NT * 32u;
   k.plane_bytes = (uint32_t)k.PX * k.PY * 16u * (a->ksize == 1 ? (uint32_t)a->TZ : 1u);   // one K half of a stage
   if ((k.plane_bytes >> 4) > 0x3FFF) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: plane too large for LBO");
-  k.a_tx_bytes = 2u * k.plane_bytes;
+  k.kpb = 1;
+  if (k.roll && (a->flags & MMSEG_CONV_ROLL_KPAIR)) {
+    if (a->n_kchunks % 2) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: paired K chunks need an even chunk count");
+    for (int i = 0; i + 1 < a->n_kchunks; i += 2)
+      if (a->a_cb[i + 1] != a->a_cb[i] + 2) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: paired K chunks must be adjacent channel blocks");
+    k.kpb = 2;
+  }
+  k.a_tx_bytes = 2u * k.plane_bytes * (uint32_t)k.kpb;
   k.stage_bytes = round_up(k.a_tx_bytes, 128);
   const uint32_t rows_needed = (uint32_t)(k.mt * 128 + 2 * k.halo * k.PX + 2 * k.halo);
   const uint32_t overflow = rows_needed * 16u > k.plane_bytes ? rows_needed * 16u - k.plane_bytes : 0u;
@@ -1137,7 +1157,7 @@ extern "C" int mmseg_conv3d_fwd(const mmseg_conv_args* a, void* stream) {
   // activations viewed as 8-byte elements: dim0 = 2*X (one voxel's 8 bf16 channels = 2 elements)
   cuuint64_t dims[4] = {(cuuint64_t)2 * k.X, (cuuint64_t)k.Y, (cuuint64_t)k.Z, (cuuint64_t)k.n_img * k.src_cbt};
   cuuint64_t strides[3] = {(cuuint64_t)k.X * 16, (cuuint64_t)k.X * k.Y * 16, (cuuint64_t)k.X * k.Y * k.Z * 16};
-  cuuint32_t box[4] = {(cuuint32_t)(2 * k.PX), (cuuint32_t)k.PY, (cuuint32_t)(a->ksize == 1 ? k.TZ : 1), 2};
+  cuuint32_t box[4] = {(cuuint32_t)(2 * k.PX), (cuuint32_t)k.PY, (cuuint32_t)(a->ksize == 1 ? k.TZ : 1), (cuuint32_t)(2 * k.kpb)};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(a->src), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

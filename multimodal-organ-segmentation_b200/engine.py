@@ -77,7 +77,7 @@ class ConvRunner:
         cout = pw.n_out
         raw_f32 = self.split
         raw = self.ws.get("raw", n * cout * Z * Y * X, torch.float32 if raw_f32 else torch.bfloat16)
-        tile = K.plan_conv_norm((X, Y, Z), n, pw, raw_f32)
+        tile = K.plan_conv_norm((X, Y, Z), n, pw, raw_f32, a_cb)
         kind = norm_kind(norm)
         out_mode = _lib.OUT_BLOCKED_F32 if raw_f32 else _lib.OUT_BLOCKED_BF16
         if kind in ("batch", "none"):

@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import lib, check
 import os
 
-from .tiling import plan_conv, plan_roll, ConvTile, ROLL_FLAG
+from .tiling import plan_conv, plan_roll, ConvTile, ROLL_FLAG, ROLL_KPAIR_FLAG
 
 Tensor = torch.Tensor
 
@@ -190,7 +190,7 @@ def a_chunk_table(src: Blocked, seg_c0: Sequence[int], seg_channels: Sequence[in
     return hi + lo + hi
 
 
-def plan_conv_norm(src_dims, n_img: int, pw: "PackedConv", raw_f32: bool) -> ConvTile:
+def plan_conv_norm(src_dims, n_img: int, pw: "PackedConv", raw_f32: bool, a_cb: Optional[Sequence[int]] = None) -> ConvTile:
     """Tile plan of a conv whose output goes to InstanceNorm (raw blocked output + statistics): the rolling-z kernel
     for the k=3, C_out = 32 bf16 layers whose weights fit in shared memory, else the classic tile kernel."""
     X, Y, Z = src_dims
@@ -198,7 +198,14 @@ def plan_conv_norm(src_dims, n_img: int, pw: "PackedConv", raw_f32: bool) -> Con
     # per plane, the issue loop's per-plane work is not amortised): 0.227 vs 0.220 ms -> rolling-z from two K chunks up
     if (pw.ksize == 3 and pw.n_out == 32 and pw.NT == 32 and pw.bias is None and not raw_f32 and pw.n_kchunks >= 2
             and os.environ.get("MMSEG_NO_ROLL", "0") != "1"):
-        t = plan_roll(X, Y, Z, n_img, pw.n_kchunks, pw.n_out)
+        # two adjacent K chunks per TMA stage when the channel blocks allow it (half the stage operations of the issue lane)
+        kpb = 1
+        if a_cb is not None and pw.n_kchunks % 2 == 0 and os.environ.get("MMSEG_ROLL_KPAIR", "1") == "1" \
+                and all(a_cb[i + 1] == a_cb[i] + 2 for i in range(0, pw.n_kchunks, 2)):
+            kpb = 2
+        t = plan_roll(X, Y, Z, n_img, pw.n_kchunks, pw.n_out, kpb)
+        if t is None and kpb == 2:
+            t = plan_roll(X, Y, Z, n_img, pw.n_kchunks, pw.n_out, 1)
         if t is not None:
             return t
     return plan_conv(X, Y, Z, n_img, pw.n_kchunks, pw.n_out, pw.ksize, pw.NT)
@@ -222,7 +229,7 @@ def conv3d(src: Blocked, pw: PackedConv, a_cb: Sequence[int], dst: Tensor, out_m
     a.TX, a.TY, a.TZ, a.stages = tile.TX, tile.TY, tile.TZ, tile.stages
     a.out_mode, a.out_channels = out_mode, pw.out_channels
     a.dst_cbt, a.dst_cb_off, a.dst_lo_off = dst_cbt, dst_cb_off, dst_lo_off
-    a.flags = flags | (ROLL_FLAG if tile.roll else 0)
+    a.flags = flags | (ROLL_FLAG if tile.roll else 0) | (ROLL_KPAIR_FLAG if (tile.roll and tile.kpb == 2) else 0)
     for i, v in enumerate(a_cb):
         a.a_cb[i] = v
     if stats is not None:

@@ -41,6 +41,7 @@ class ConvTile:
     tiles_per_img: int
     est_cycles: float
     roll: bool = False       # rolling-z kernel: TZ is the z-segment length, tiles_per_img counts (x, y, z-segment) items
+    kpb: int = 1             # rolling-z: K chunks per TMA stage (2 = paired, needs adjacent channel blocks)
 
 
 def tmem_cols(mt: int, TZ: int, NT: int) -> int:
@@ -159,22 +160,23 @@ def plan_conv(X: int, Y: int, Z: int, n_img: int, n_kchunks: int, n_out: int, ks
 
 
 ROLL_FLAG = 16               # MMSEG_CONV_ROLL_Z
+ROLL_KPAIR_FLAG = 32         # MMSEG_CONV_ROLL_KPAIR
 
 
-def roll_smem_bytes(TX: int, TY: int, NT: int, n_kchunks: int, stages: int) -> Optional[int]:
+def roll_smem_bytes(TX: int, TY: int, NT: int, n_kchunks: int, stages: int, kpb: int = 1) -> Optional[int]:
     """Shared memory of conv3d_roll_kernel (all K-chunk weights resident), or None when the tiling is invalid."""
     PX, PY = TX + 2, TY + 2
     if PX > 128 or PY > 256 or _cdiv((TY - 1) * PX + TX, 128) != 1 or NT != 32:
         return None
     plane = PX * PY * 16
-    stage = _round_up(2 * plane, 128)
+    stage = _round_up(2 * plane * kpb, 128)
     overflow = max((128 + 2 * PX + 2) * 16 - plane, 0)
     total = HEADER_BYTES + n_kchunks * _round_up(27 * NT * 32, 128) + stages * stage + _round_up(overflow, 128) + 128
     return total if total <= SMEM_LIMIT else None
 
 
 @lru_cache(maxsize=None)
-def plan_roll(X: int, Y: int, Z: int, n_img: int, n_kchunks: int, n_out: int) -> Optional[ConvTile]:
+def plan_roll(X: int, Y: int, Z: int, n_img: int, n_kchunks: int, n_out: int, kpb: int = 1) -> Optional[ConvTile]:
     """Rolling-z plan for a k=3, C_out = 32 layer (None when not eligible).  Cost model: an N = 96 MMA is
     shared-memory-bound at ~56 clk (measured), a partial-N boundary MMA ~51; one item = one z segment of a column."""
     if n_out != 32:
@@ -192,12 +194,12 @@ def plan_roll(X: int, Y: int, Z: int, n_img: int, n_kchunks: int, n_out: int) ->
         if TY < 1:
             continue
         stages = 0
-        for st in (24, 20, 16, 12, 10, 8):
-            sb = roll_smem_bytes(TX, TY, 32, n_kchunks, st)
+        for st in (24, 20, 16, 12, 10, 8, 6, 5, 4):
+            sb = roll_smem_bytes(TX, TY, 32, n_kchunks, st, kpb)
             if sb is not None:
                 stages = st
                 break
-        if stages < max(8, 2 * n_kchunks):
+        if stages * kpb < max(8, 2 * n_kchunks):
             continue
         tx_n, ty_n = _cdiv(X, TX), _cdiv(Y, TY)
         for nseg in range(1, max(1, Z // 8) + 1):
@@ -208,5 +210,5 @@ def plan_roll(X: int, Y: int, Z: int, n_img: int, n_kchunks: int, n_out: int) ->
             est = _cdiv(items, NUM_SMS) * per_item + 4000.0
             cand = (est, -TX * TY)
             if best is None or cand < best[0]:
-                best = (cand, ConvTile(TX, TY, ZS, 32, 1, stages, 1, sb, tx_n * ty_n * nseg_eff, est, True))
+                best = (cand, ConvTile(TX, TY, ZS, 32, 1, stages, 1, sb, tx_n * ty_n * nseg_eff, est, True, kpb))
     return None if best is None else best[1]

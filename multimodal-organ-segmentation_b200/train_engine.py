@@ -86,7 +86,7 @@ class TrainEngine:
         cout = conv.weight.shape[0]
         pw = K.pack_conv_weight(conv.weight, None, False, [s[1] for s in segs], use_bias=False)
         a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], False)
-        tile = K.plan_conv_norm((X, Y, Z), n, pw, False)
+        tile = K.plan_conv_norm((X, Y, Z), n, pw, False, a_cb)
         raw = self.saved(name + ".raw", (n, cout // 8, Z, Y, X, 8), torch.bfloat16)
         stats = self.saved("ws.stats", (n * tile.tiles_per_img * cout * 2,), torch.float32)
         mr = self.saved(name + ".mr", (n, cout, 2), torch.float32)

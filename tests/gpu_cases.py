@@ -57,9 +57,9 @@ def conv_case(cin, cout, shape, n_img=1, tile=None, split=False, flags=0, ks=3, 
     if roll is not None:   # rolling-z kernel: roll = "auto" (planner) or (TX, TY, z-segment length, stages)
         from mmseg_b200.tiling import plan_roll
         t = plan_roll(X, Y, Z, n_img, pw.n_kchunks, pw.n_out) if roll == "auto" else \
-            ConvTile(roll[0], roll[1], roll[2], 32, 1, roll[3], 1, 0, 0, 0.0, True)
+            ConvTile(roll[0], roll[1], roll[2], 32, 1, roll[3], 1, 0, 0, 0.0, True, roll[4] if len(roll) > 4 else 1)
         assert t is not None and t.roll
-        name = f"{name}-roll{(t.TX, t.TY, t.TZ, t.stages)}"
+        name = f"{name}-roll{(t.TX, t.TY, t.TZ, t.stages, t.kpb)}"
     raw = torch.full((n_img, pw.n_out // 8, Z, Y, X, 8), float("nan"), device=DEV,
                      dtype=torch.float32 if split else torch.bfloat16)
     tiles_per_img = ((X + t.TX - 1) // t.TX) * ((Y + t.TY - 1) // t.TY) * ((Z + t.TZ - 1) // t.TZ)

@@ -44,6 +44,8 @@ def test_conv3d_tcgen05(args, kw):
     ((64, 32, (19, 6, 20)), dict(roll=(20, 5, 7, 12))),              # 4 K chunks, segments 7, 7, 5
     ((16, 32, (1, 5, 8)), dict(roll=(8, 5, 4, 8))),                  # a single output plane
     ((32, 32, (37, 5, 24)), dict(roll=(24, 5, 37, 10), n_img=2)),    # one long segment: 37 planes through a 16-slot ring
+    ((32, 32, (40, 7, 26)), dict(n_img=2, roll=(13, 4, 17, 6, 2))),  # two K chunks per TMA stage (4-block box)
+    ((64, 32, (19, 6, 20)), dict(roll=(20, 5, 7, 5, 2))),            # 4 K chunks = 2 paired stages per plane, 5-stage ring
 ])
 def test_conv3d_rolling_z(args, kw):
     """conv3d_roll_kernel (TMEM ring of output planes) vs F.conv3d, raw output and InstanceNorm partial sums."""

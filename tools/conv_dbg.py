@@ -13,7 +13,7 @@ src = Blocked(n, (cin + 15) // 16 * 16, S, S, S, False, "cuda"); src.t.normal_()
 flags = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 raw = torch.empty((n, cout // 8, S, S, S, 8), dtype=torch.bfloat16, device="cuda")
 a_cb = K.a_chunk_table(src, [0], [cin], False)
-tile = K.plan_conv_norm((S, S, S), n, pw, False)
+tile = K.plan_conv_norm((S, S, S), n, pw, False, a_cb)
 stats = torch.zeros(n * tile.tiles_per_img * cout * 2, device="cuda")
 for _ in range(3):
     K.conv3d(src, pw, a_cb, raw, _lib.OUT_BLOCKED_BF16, stats=stats, dst_cbt=cout // 8, tile=tile, flags=flags)
