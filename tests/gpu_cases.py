@@ -832,6 +832,28 @@ def suv_guided_attention_golden_case():
             assert err <= 8e-2 and rel <= 2e-2          # bf16 path: the output is an InstanceNorm (unit variance)
 
 
+def predict_volume_case():
+    """predict_volume (pinned host volume -> slab-wise upload overlapping the first windows -> labels in host memory)
+    gives exactly the labels of the resident path, for a volume with several upload slabs and a ragged last one."""
+    from mmseg_b200.src.models.backbones.unet import UNet3D
+    from mmseg_b200.src.trainer.inference import SlidingWindowInferer, predict_volume
+    torch.manual_seed(2)
+    m = UNet3D(in_channels=2, out_channels=5, features=[16, 32]).eval().to(DEV)
+    roi = (16, 16, 16)
+    vol = torch.randn(2, 150, 20, 24).pin_memory()            # 150 planes -> slabs of 19 planes, last one ragged
+    want = SlidingWindowInferer(m, roi, 0.5, "gaussian", engine_batch=4)(vol.to(DEV)[None], return_labels=True).cpu()
+    got = predict_volume(m, vol, roi, 0.5, "gaussian", engine_batch=4)
+    assert got.dtype == torch.uint8 and tuple(got.shape) == (150, 20, 24)
+    assert torch.equal(got, want), (got != want).sum().item()
+    out = torch.empty((150, 20, 24), dtype=torch.uint8).pin_memory()
+    vol2 = (vol * 0.5 + 0.1).pin_memory()
+    got2 = predict_volume(m, vol2, roi, 0.5, "gaussian", engine_batch=4, out_host=out)    # cached engine, caller's buffer
+    assert got2.data_ptr() == out.data_ptr()
+    want2 = SlidingWindowInferer(m, roi, 0.5, "gaussian", engine_batch=4)(vol2.to(DEV)[None], return_labels=True).cpu()
+    assert torch.equal(got2, want2)
+    print("[predict_volume] labels identical to the resident path (2 volumes)", flush=True)
+
+
 def focal_tversky_golden_case():
     """Focal / Tversky loss kernels (value + gradient) vs the reference's own outputs (tests/golden/losses.pt)."""
     from mmseg_b200.src.trainer.losses import FocalLoss, TverskyLoss, get_loss
