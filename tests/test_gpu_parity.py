@@ -115,6 +115,10 @@ def test_suv_guided_attention_golden():
     _c().suv_guided_attention_golden_case()
 
 
+def test_full_size_volume_properties():
+    _c().full_volume_properties_case()
+
+
 def test_predict_volume_host_to_host():
     _c().predict_volume_case()
 
