@@ -904,6 +904,37 @@ def full_volume_properties_case():
     assert int(lab8.max()) <= 7 and lab8.dtype == torch.uint8 and tuple(lab8.shape) == VOL
 
 
+def full_train_step_properties_case():
+    """BASELINE.json configs[1] at FULL size (DualEncoder CT+PET, features 32-512, 128^3, batch 2): properties instead of a
+    CPU oracle run (minutes) — the backward is deterministic (no float atomics: two runs give bit-identical gradients) and
+    linear in the loss gradient (scaling the loss by 2, a power of two, scales every gradient by exactly 2)."""
+    from mmseg_b200.src.models.backbones.dual_encoder import DualEncoder
+    from mmseg_b200.src.trainer.losses import DiceCELoss
+    torch.manual_seed(0)
+    m = DualEncoder(num_modalities=2, out_channels=8, features=[32, 64, 128, 256, 512], fusion_type="cross_attention").to(DEV).train()
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn((2, 2, 128, 128, 128), device=DEV, generator=g)
+    y = torch.randint(0, 8, (2, 128, 128, 128), device=DEV, generator=g)
+    crit = DiceCELoss()
+    def grads(scale):
+        m.zero_grad(set_to_none=True)
+        loss = crit(m(x), y)
+        (loss * scale).backward()
+        torch.cuda.synchronize()
+        return loss.item(), [p.grad.detach().clone() for p in m.parameters()]
+    l1, g1 = grads(1.0)
+    l2, g2 = grads(1.0)
+    l3, g3 = grads(2.0)
+    assert l1 == l2 == l3 and abs(l1 - 2.0794) < 0.7        # ~ ln 8 + dice term at random init
+    n_bad = sum(int(not torch.equal(a, b)) for a, b in zip(g1, g2))
+    n_lin = sum(int(not torch.equal(2 * a, c)) for a, c in zip(g1, g3))
+    tot = sum(float(a.double().abs().sum()) for a in g1)
+    print(f"[full train step] loss {l1:.5f}, {len(g1)} gradient tensors, |g|_1 = {tot:.4e}: "
+          f"{n_bad} differ between runs, {n_lin} break exact 2x linearity", flush=True)
+    assert all(torch.isfinite(a).all() for a in g1) and tot > 0
+    assert n_bad == 0 and n_lin == 0
+
+
 def focal_tversky_golden_case():
     """Focal / Tversky loss kernels (value + gradient) vs the reference's own outputs (tests/golden/losses.pt)."""
     from mmseg_b200.src.trainer.losses import FocalLoss, TverskyLoss, get_loss

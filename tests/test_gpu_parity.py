@@ -119,6 +119,10 @@ def test_full_size_volume_properties():
     _c().full_volume_properties_case()
 
 
+def test_full_size_train_step_properties():
+    _c().full_train_step_properties_case()
+
+
 def test_predict_volume_host_to_host():
     _c().predict_volume_case()
 
