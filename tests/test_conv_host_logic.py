@@ -102,3 +102,34 @@ def test_planner_matches_library_limits():
         got = _lib.lib.mmseg_conv3d_smem_bytes(C.byref(a))
         assert got == t.smem_bytes, (X, ks, nout, got, t, _lib.last_error())
         assert _lib.lib.mmseg_conv3d_tiles_per_img(C.byref(a)) == t.tiles_per_img
+
+
+def test_rolling_z_plans_match_library():
+    """plan_roll (rolling-z kernel: z segments, resident weights, optional paired K chunks) must be accepted by the C-side
+    plan with the same shared-memory size, and its items must cover the volume."""
+    import ctypes as C
+    from mmseg_b200 import _lib
+    from mmseg_b200.tiling import plan_roll, ROLL_FLAG, ROLL_KPAIR_FLAG
+    for (X, Y, Z, n, kc, kpb) in [(96, 96, 96, 8, 1, 1), (96, 96, 96, 8, 2, 1), (96, 96, 96, 8, 2, 2), (96, 96, 96, 8, 4, 2),
+                                  (128, 128, 128, 2, 4, 2), (128, 128, 128, 2, 2, 2), (48, 40, 36, 2, 1, 1), (20, 12, 30, 1, 2, 2)]:
+        t = plan_roll(X, Y, Z, n, kc, 32, kpb)
+        assert t is not None and t.roll and t.kpb == kpb and t.mt == 1 and t.NT == 32 and t.n_ntiles == 1
+        assert (t.TY - 1) * (t.TX + 2) + t.TX <= 128
+        assert t.tiles_per_img == -(-X // t.TX) * -(-Y // t.TY) * -(-Z // t.TZ)
+        a = _lib.ConvArgs()
+        a.n_img, a.Z, a.Y, a.X = n, Z, Y, X
+        a.src_cbt, a.ksize, a.n_kchunks = 2 * kc, 3, kc
+        a.NT, a.n_ntiles, a.TX, a.TY, a.TZ, a.stages = 32, 1, t.TX, t.TY, t.TZ, t.stages
+        a.out_mode, a.out_channels = 0, 32
+        a.flags = ROLL_FLAG | (ROLL_KPAIR_FLAG if kpb == 2 else 0)
+        for i in range(kc):
+            a.a_cb[i] = 2 * i
+        got = _lib.lib.mmseg_conv3d_smem_bytes(C.byref(a))
+        assert got == t.smem_bytes, (X, kc, kpb, got, t, _lib.last_error())
+        assert _lib.lib.mmseg_conv3d_tiles_per_img(C.byref(a)) == t.tiles_per_img
+    # not eligible: C_out != 32; rejected by the library: paired chunks that are not adjacent channel blocks
+    assert plan_roll(96, 96, 96, 8, 2, 64) is None
+    a.n_kchunks, a.flags = 2, ROLL_FLAG | ROLL_KPAIR_FLAG
+    a.a_cb[0], a.a_cb[1] = 0, 4
+    a.src_cbt = 8
+    assert _lib.lib.mmseg_conv3d_smem_bytes(C.byref(a)) < 0 and "adjacent" in _lib.last_error()
