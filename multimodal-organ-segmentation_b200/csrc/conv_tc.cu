@@ -1,7 +1,7 @@
 // Conv3d forward (k=3 pad 1, k=1, and ConvTranspose3d k2 s2 as a 1x1 GEMM + pixel shuffle) as a tcgen05 / TMEM
 // implicit GEMM for sm_100a.  See include/mmseg_b200.h for the contract and DESIGN.md for the derivation.
 //
-// One CTA owns an output tile of TZ x TY x TX voxels x NT channels.
+// conv3d_tc_kernel<MT, KS> (tile kernel): one persistent CTA sweeps output tiles of TZ x TY x TX voxels x NT channels.
 //   * activations live in HBM as [cb][Z][Y][X][8] bf16 ("blocked"); a TMA box (2 channel blocks x PY x PX voxels,
 //     zero-filled outside the volume = the conv's zero padding) lands in shared memory as two contiguous planes of
 //     16-byte voxel rows, which IS the SWIZZLE_NONE K-major UMMA operand layout (row pitch 16 B, LBO = plane size).
@@ -9,10 +9,15 @@
 //     moves, nothing is re-loaded.  128-row M tiles run over the flattened (y, x) plane; rows that fall in the halo
 //     columns are computed and discarded (2/PX of the rows).
 //   * K loop = 16-channel chunks (outer) x input z-planes (ring of `stages` smem slots) x (dy, dx) taps; the TZ*mt
-//     accumulators (NT fp32 columns each, <= 512 columns) stay resident in TMEM for the whole loop.  The dz taps are
-//     folded into the MMA N dimension: one MMA adds an input plane to up to three adjacent output-plane accumulators.
-//   * warp 0: TMA producer, warp 1: MMA issuer (one elected lane each), warps 2-5: epilogue (TMEM -> registers ->
-//     HBM, plus per-channel sum / sum-of-squares partials for InstanceNorm).
+//     accumulators (NT fp32 columns each, <= 512 columns, two sets when they fit) stay resident in TMEM for the whole
+//     loop.  The dz taps are folded into the MMA N dimension: one MMA adds an input plane to up to three adjacent
+//     output-plane accumulators.
+//   * k = 1 (ConvTranspose GEMM, 1x1 projections): the whole TX x TY x TZ tile is ONE stage (4-D box) whose voxels are the
+//     flattened GEMM rows, the [K x NT] weight panel is resident, stages are issued in groups of up to 16.
+//   * warp 0: TMA producer, warp 1: MMA issuer (one elected lane issues), warps 2-5: epilogue (TMEM -> registers ->
+//     HBM, plus per-channel sum / sum-of-squares partials for InstanceNorm), instantiated per output mode.
+// conv3d_roll_kernel (rolling-z, further down): the full-resolution C_out = 32 layers — z segments of a column, a TMEM
+//     ring of 16 output planes, all weights resident, per-plane hand-over to 8 epilogue warps.
 #include <cuda.h>
 
 #include "common.h"
