@@ -239,6 +239,15 @@ int mmseg_unpack_ncdhw(const void* src, float* dst, int32_t n_img, int32_t C, in
 int mmseg_swi_gather(const float* volume, int32_t C, int32_t VZ, int32_t VY, int32_t VX, const int32_t* starts_dev,
                      int32_t n_win, int32_t RZ, int32_t RY, int32_t RX, void* dst, int32_t dst_cbt, int32_t dst_lo_off,
                      int32_t cb, void* stream);
+/* out_conv (1x1x1, C -> K <= 8 classes, unet.py:163,199) fused into the blend of ONE window: the logits of window
+ * `window` of the blocked feature batch are computed in registers and blended into out / count (same arithmetic and order
+ * as mmseg_conv1x1_logits + mmseg_swi_blend in window mode, bit-identical accumulators) — the logits tensor is never
+ * materialised.  RX, VX and the window's x origin must be multiples of 4. */
+int mmseg_swi_logits_blend(const void* feat, int32_t src_cbt, int32_t cb_off, int32_t lo_off, int32_t cin, int32_t window,
+                           const float* weight /* [K][cin] fp32 */, const float* bias, int32_t K,
+                           const int32_t* starts_dev /* this window's origin */, int32_t RZ, int32_t RY, int32_t RX,
+                           const float* wz, const float* wy, const float* wx, float w_floor, float* out, float* count,
+                           int32_t VZ, int32_t VY, int32_t VX, void* stream);
 int mmseg_swi_blend(const float* win_logits /* [n_win][K][RZ][RY][RX] */, const int32_t* starts_dev, int32_t n_win,
                     int32_t K, int32_t RZ, int32_t RY, int32_t RX, const float* wz, const float* wy, const float* wx,
                     float w_floor, float* out /* [K][VZ][VY][VX] */, float* count /* [VZ][VY][VX] */, int32_t VZ,

@@ -108,6 +108,8 @@ SYMBOLS = {
     "mmseg_gate_mlp": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mmseg_modality_combine": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _f32, _vp, _i32, _i32, _i32, _vp]),
     "mmseg_modality_max": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i64, _vp, _i32, _i32, _vp]),
+    "mmseg_swi_logits_blend": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp,
+                                         _vp, _f32, _vp, _vp, _i32, _i32, _i32, _vp]),
     "mmseg_pack_ncdhw_ex": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp]),
     "mmseg_groupnorm_finalize": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i64, _f32, _vp, _vp, _vp, _vp, _vp]),
     "mmseg_trilinear_resize": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),

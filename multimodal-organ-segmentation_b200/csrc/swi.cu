@@ -154,6 +154,109 @@ swi_blend_window_kernel(const float* __restrict__ logits, const int* __restrict_
   }
 }
 
+// out_conv fused into the blend: logits = W x features + b are computed in registers from the window's last feature map
+// (blocked bf16, optional lo plane) and blended straight into the volume accumulator — the NCDHW logits tensor is never
+// written or read (28 + 28 MB per 96^3 window).  Same arithmetic, in the same order, as conv1x1_logits_kernel followed
+// by swi_blend_window_kernel (fp32 FMAs over the channels in index order, then seg * w and out + seg as separate
+// roundings), so the accumulator is bit-identical to the two-kernel path.  One thread = 4 consecutive x voxels of a
+// window row (float4 accumulator accesses); needs RX, VX and every window's x origin to be multiples of 4.
+template <int KP>   // classes padded to a multiple of 4 (<= 8)
+__global__ void __launch_bounds__(128)
+swi_logits_blend_kernel(const __nv_bfloat16* __restrict__ feat, int src_cbt, int cb_off, int lo_off, int cin_blocks, int win,
+                        const float* __restrict__ weight, const float* __restrict__ bias, int K,
+                        const int* __restrict__ starts, int RZ, int RY, int RX, const float* __restrict__ wz,
+                        const float* __restrict__ wy, const float* __restrict__ wx, float w_floor, float* __restrict__ out,
+                        float* __restrict__ count, int VZ, int VY, int VX) {
+  extern __shared__ float wsm[];   // [cin][KP], zero-padded classes
+  const int cin = cin_blocks * 8;
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < cin * KP; i += blockDim.x * blockDim.y) {
+    const int ci = i / KP, co = i - ci * KP;
+    wsm[i] = co < K ? weight[(size_t)co * cin + ci] : 0.f;
+  }
+  __syncthreads();
+  const int row = blockIdx.y * blockDim.y + threadIdx.y;
+  if (row >= RZ * RY) return;
+  const int lz = row / RY, ly = row - lz * RY;
+  const int z = starts[0] + lz, y = starts[1] + ly;
+  const int sx = starts[2];
+  if (z < 0 || z >= VZ || y < 0 || y >= VY) return;
+  const size_t nvox_v = (size_t)VZ * VY * VX;
+  const size_t nvox_r = (size_t)RZ * RY * RX;
+  const float wzy = __fmul_rn(wz[lz], wy[ly]);
+  const size_t row_v = ((size_t)z * VY + y) * VX;
+  const size_t row_r = ((size_t)lz * RY + ly) * RX;
+  for (int lx = 4 * (blockIdx.x * blockDim.x + threadIdx.x); lx < RX; lx += 4 * gridDim.x * blockDim.x) {
+    float acc[KP][4];
+#pragma unroll
+    for (int co = 0; co < KP; ++co) {
+      const float b = (bias && co < K) ? bias[co] : 0.f;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[co][v] = b;
+    }
+    for (int cb = 0; cb < cin_blocks; ++cb) {
+      const __nv_bfloat16* base = feat + (((size_t)win * src_cbt + cb_off + cb) * nvox_r + row_r + lx) * 8;
+      float x[4][8];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const uint4 r = *reinterpret_cast<const uint4*>(base + v * 8);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          x[v][2 * j] = f.x; x[v][2 * j + 1] = f.y;
+        }
+        if (lo_off > 0) {
+          const uint4 rl = *reinterpret_cast<const uint4*>(base + (size_t)lo_off * nvox_r * 8 + v * 8);
+          const __nv_bfloat162* hl = reinterpret_cast<const __nv_bfloat162*>(&rl);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(hl[j]);
+            x[v][2 * j] += f.x; x[v][2 * j + 1] += f.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4* wr = reinterpret_cast<const float4*>(wsm + (size_t)(cb * 8 + j) * KP);
+#pragma unroll
+        for (int c4 = 0; c4 < KP / 4; ++c4) {
+          const float4 w = wr[c4];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            acc[4 * c4 + 0][v] = fmaf(w.x, x[v][j], acc[4 * c4 + 0][v]);
+            acc[4 * c4 + 1][v] = fmaf(w.y, x[v][j], acc[4 * c4 + 1][v]);
+            acc[4 * c4 + 2][v] = fmaf(w.z, x[v][j], acc[4 * c4 + 2][v]);
+            acc[4 * c4 + 3][v] = fmaf(w.w, x[v][j], acc[4 * c4 + 3][v]);
+          }
+        }
+      }
+    }
+    const float4 w4 = *reinterpret_cast<const float4*>(wx + lx);
+    const float w[4] = {fmaxf(__fmul_rn(wzy, w4.x), w_floor), fmaxf(__fmul_rn(wzy, w4.y), w_floor),
+                        fmaxf(__fmul_rn(wzy, w4.z), w_floor), fmaxf(__fmul_rn(wzy, w4.w), w_floor)};
+    const size_t vox = row_v + sx + lx;
+    float4 a4[KP];
+#pragma unroll
+    for (int c = 0; c < KP; ++c)
+      if (c < K) a4[c] = *reinterpret_cast<const float4*>(out + (size_t)c * nvox_v + vox);
+#pragma unroll
+    for (int c = 0; c < KP; ++c) {
+      if (c < K) {
+        float4 a = a4[c];
+        a.x = __fadd_rn(a.x, __fmul_rn(acc[c][0], w[0]));
+        a.y = __fadd_rn(a.y, __fmul_rn(acc[c][1], w[1]));
+        a.z = __fadd_rn(a.z, __fmul_rn(acc[c][2], w[2]));
+        a.w = __fadd_rn(a.w, __fmul_rn(acc[c][3], w[3]));
+        *reinterpret_cast<float4*>(out + (size_t)c * nvox_v + vox) = a;
+      }
+    }
+    float4* cp = reinterpret_cast<float4*>(count + vox);
+    float4 cv = *cp;
+    cv.x = __fadd_rn(cv.x, w[0]); cv.y = __fadd_rn(cv.y, w[1]); cv.z = __fadd_rn(cv.z, w[2]); cv.w = __fadd_rn(cv.w, w[3]);
+    *cp = cv;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 swi_finalize_kernel(float* __restrict__ out, const float* __restrict__ count, int K, size_t nvox, int normalize,
                     uint8_t* __restrict__ labels) {
@@ -214,6 +317,33 @@ extern "C" int mmseg_swi_blend(const float* win_logits, const int32_t* starts_de
       win_logits, starts_dev, n_win, K, RZ, RY, RX, wz, wy, wx, w_floor, out, count, VZ, VY, VX, bz0, by0, bx0, bx1,
       by1 - by0);
   return check_launch("swi_blend_kernel");
+}
+
+extern "C" int mmseg_swi_logits_blend(const void* feat, int32_t src_cbt, int32_t cb_off, int32_t lo_off, int32_t cin,
+                                      int32_t window, const float* weight, const float* bias, int32_t K,
+                                      const int32_t* starts_dev, int32_t RZ, int32_t RY, int32_t RX, const float* wz,
+                                      const float* wy, const float* wx, float w_floor, float* out, float* count,
+                                      int32_t VZ, int32_t VY, int32_t VX, void* stream) {
+  if (!feat || !weight || !starts_dev || !wz || !wy || !wx || !out || !count || window < 0)
+    return fail(MMSEG_ERR_INVALID_ARG, "swi_logits_blend: bad arguments");
+  if (K < 1 || K > 8 || cin < 8 || (cin % 8) || cin > 128)
+    return fail(MMSEG_ERR_UNSUPPORTED, "swi_logits_blend: K=%d (1..8), cin=%d (multiple of 8, <= 128)", K, cin);
+  if ((RX & 3) || (VX & 3) || RX / 4 > 128 || (int64_t)RZ * RY > 65535 * 8)
+    return fail(MMSEG_ERR_UNSUPPORTED, "swi_logits_blend: RX and VX must be multiples of 4 (RX <= 512)");
+  const int bx = RX / 4;
+  const int by = bx >= 128 ? 1 : 128 / bx;
+  dim3 block(bx, by), grid(1, (RZ * RY + by - 1) / by);
+  const __nv_bfloat16* f = reinterpret_cast<const __nv_bfloat16*>(feat);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (K <= 4)
+    swi_logits_blend_kernel<4><<<grid, block, (size_t)cin * 4 * sizeof(float), st>>>(
+        f, src_cbt, cb_off, lo_off, cin / 8, window, weight, bias, K, starts_dev, RZ, RY, RX, wz, wy, wx, w_floor, out, count,
+        VZ, VY, VX);
+  else
+    swi_logits_blend_kernel<8><<<grid, block, (size_t)cin * 8 * sizeof(float), st>>>(
+        f, src_cbt, cb_off, lo_off, cin / 8, window, weight, bias, K, starts_dev, RZ, RY, RX, wz, wy, wx, w_floor, out, count,
+        VZ, VY, VX);
+  return check_launch("swi_logits_blend_kernel");
 }
 
 extern "C" int mmseg_swi_finalize(float* out, const float* count, int32_t K, int64_t voxels,

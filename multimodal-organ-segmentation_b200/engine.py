@@ -251,7 +251,7 @@ class UNet3DEngine:
 
     # ---------------------------------------------------------------- forward
     @torch.no_grad()
-    def forward_blocked(self, n: int, Z: int, Y: int, X: int, logits: Tensor) -> Tensor:
+    def forward_blocked(self, n: int, Z: int, Y: int, X: int, logits: Optional[Tensor], device=None):
         """Runs the net on the engine's input buffer; writes NCDHW fp32 logits [n, out_channels, Z, Y, X]."""
         _lib.require_device()
         m = self.module
@@ -259,9 +259,10 @@ class UNet3DEngine:
         L = len(f)
         P = self._pack()
         N = self._norms
-        b = self._buffers(n, Z, Y, X, logits.device)
+        device = logits.device if logits is not None else device
+        b = self._buffers(n, Z, Y, X, device)
         if self._runner is None:
-            self._runner = ConvRunner(self.split, logits.device)
+            self._runner = ConvRunner(self.split, device)
         r = self._runner
         cin_p = (m.in_channels + 15) // 16 * 16
         # encoder (unet.py:181-187); each block's output lands in the skip half of its level's concat buffer
@@ -289,6 +290,8 @@ class UNet3DEngine:
             r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[f"decoders.{j}.conv2"], b[f"dec{l}"],
                             norm=N[f"decoders.{j}.conv2"])
             cur = b[f"dec{l}"]
+        if logits is None:   # features only: the caller fuses out_conv into its consumer (sliding-window blend)
+            return cur
         r.conv_logits(cur, [(0, f[0])], P["out_conv"], logits, m.out_conv)
         return logits
 
@@ -415,16 +418,17 @@ class DualEncoderEngine:
         return self.forward_blocked(n, Z, Y, X, logits)
 
     @torch.no_grad()
-    def forward_blocked(self, n: int, Z: int, Y: int, X: int, logits: Tensor) -> Tensor:
+    def forward_blocked(self, n: int, Z: int, Y: int, X: int, logits: Optional[Tensor], device=None):
         """Runs the net on the per-modality input buffers; writes NCDHW fp32 logits [n, out_channels, Z, Y, X]."""
         _lib.require_device()
         m = self.module
         f, L, M = m.features, len(m.features), m.num_modalities
         cpm = m.in_channels_per_modality
         P = self._pack()
-        b = self._buffers(n, Z, Y, X, logits.device)
+        device = logits.device if logits is not None else device
+        b = self._buffers(n, Z, Y, X, device)
         if self._runner is None:
-            self._runner = ConvRunner(self.split, logits.device)
+            self._runner = ConvRunner(self.split, device)
         r = self._runner
         # encoders (dual_encoder.py:131-144)
         for i in range(M):
@@ -462,6 +466,8 @@ class DualEncoderEngine:
             r.conv_norm_act(b[f"cat{l}"], [(0, f[l]), (f[l], f[l])], P[f"decoder.{j}.conv1"], b[f"mid{l}"])
             r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[f"decoder.{j}.conv2"], b[f"dec{l}"])
             cur = b[f"dec{l}"]
+        if logits is None:   # features only: the caller fuses out_conv into its consumer (sliding-window blend)
+            return cur
         r.conv_logits(cur, [(0, f[0])], P["out_conv"], logits, m.out_conv)
         return logits
 

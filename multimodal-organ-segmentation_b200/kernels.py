@@ -325,6 +325,20 @@ def swi_blend(win_logits: Tensor, starts_dev: Tensor, n_win: int, wz: Tensor, wy
                               w_floor, _ptr(out), _ptr(count), VZ, VY, VX, *box, _stream())
 
 
+def swi_logits_blend(feat: Blocked, c0: int, cin: int, window: int, weight: Tensor, bias: Optional[Tensor],
+                     start_dev: Tensor, wz: Tensor, wy: Tensor, wx: Tensor, w_floor: float, out: Tensor, count: Tensor) -> None:
+    """out_conv + blend of window `window` of the blocked feature batch `feat` in one kernel (no logits tensor)."""
+    Kc, VZ, VY, VX = out.shape
+    assert weight.shape[0] == Kc and weight.shape[1] == cin and c0 % 8 == 0
+    w = weight.detach().reshape(Kc, cin)
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    b = bias.detach().float() if bias is not None else None
+    _call("mmseg_swi_logits_blend", _ptr(feat.t), feat.cbt, c0 // 8, feat.lo_off if feat.split else 0, cin, window, _ptr(w),
+          _ptr(b) if b is not None else None, Kc, _ptr(start_dev), feat.Z, feat.Y, feat.X, _ptr(wz), _ptr(wy), _ptr(wx),
+          w_floor, _ptr(out), _ptr(count), VZ, VY, VX, _stream())
+
+
 def swi_finalize(out: Tensor, count: Tensor, normalize_in_place: bool, labels: Optional[Tensor]) -> None:
     K = out.shape[0]
     vox = count.numel()

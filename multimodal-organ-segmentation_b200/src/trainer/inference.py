@@ -16,6 +16,8 @@ fall into the axis-0 slab it owns, finalises that slab and the uint8 labels are 
 import math
 from typing import Callable, List, Optional, Sequence, Tuple
 
+import os
+
 import torch
 
 from ... import kernels as K
@@ -176,6 +178,13 @@ class SlidingWindowInferer:
                 "graph": None, "vol_ptr": None, "launches": 0,
                 "ev_fwd": torch.cuda.Event(), "ev_blend": None})
         st["out"], st["count"] = st["acc"][:K_out], st["acc"][K_out]
+        # out_conv fused into the blend (no logits tensor) when the 1x1 head and the window geometry allow it
+        oc = getattr(eng.module, "out_conv", None)
+        f0 = eng.module.features[0]
+        st["fused_head"] = bool(
+            os.environ.get("MMSEG_SWI_FUSED_HEAD", "1") == "1" and oc is not None and tuple(oc.kernel_size) == (1, 1, 1)
+            and K_out <= 8 and f0 % 8 == 0 and f0 <= 128 and self.roi[2] % 4 == 0 and VX % 4 == 0
+            and self.roi[2] // 4 <= 128 and all(s_[2] % 4 == 0 for s_ in starts))
         self._state = st
         return st
 
@@ -183,9 +192,20 @@ class SlidingWindowInferer:
         """gather -> forward for the n windows whose origins are in the slot's starts_dev[:n] (current stream)."""
         rz, ry, rx = self.roi
         slot["eng"].gather_windows(volume, slot["starts_dev"], n, self.roi)
-        slot["eng"].forward_blocked(n, rz, ry, rx, slot["logits"][:n])
+        if st["fused_head"]:
+            # features only; the buffer is persistent per batch size (graph replays of full batches keep reading it)
+            slot.setdefault("feat", {})[n] = slot["eng"].forward_blocked(n, rz, ry, rx, None, device=volume.device)
+        else:
+            slot["eng"].forward_blocked(n, rz, ry, rx, slot["logits"][:n])
 
     def _blend_batch(self, st, slot, n: int) -> None:
+        if st["fused_head"]:
+            oc = slot["eng"].module.out_conv
+            feat = slot["feat"][n]
+            for j in range(n):
+                K.swi_logits_blend(feat, 0, oc.in_channels, j, oc.weight, oc.bias, slot["starts_dev"][j], st["wz"],
+                                   st["wy"], st["wx"], st["floor"], st["out"], st["count"])
+            return
         logits = slot["logits"]
         for j in range(n):
             K.swi_blend(logits[j:j + 1], slot["starts_dev"][j], 1, st["wz"], st["wy"], st["wx"], st["floor"], st["out"],

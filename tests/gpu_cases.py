@@ -832,6 +832,32 @@ def suv_guided_attention_golden_case():
             assert err <= 8e-2 and rel <= 2e-2          # bf16 path: the output is an InstanceNorm (unit variance)
 
 
+def fused_head_case():
+    """out_conv fused into the blend (swi_logits_blend) gives bit-identical accumulators and labels to the two-kernel path
+    (conv1x1_logits + blend), in both numeric modes; falls back when a window origin is not a multiple of 4."""
+    import os
+    from mmseg_b200.src.models.backbones.unet import UNet3D
+    from mmseg_b200.src.trainer.inference import SlidingWindowInferer
+    torch.manual_seed(4)
+    m = UNet3D(in_channels=2, out_channels=6, features=[16, 32]).eval().to(DEV)
+    vol = torch.randn(1, 2, 40, 36, 56, device=DEV)
+    for mode in ("bf16", "parity"):
+        m.set_numeric_mode(mode)
+        res = {}
+        for fused in ("1", "0"):
+            os.environ["MMSEG_SWI_FUSED_HEAD"] = fused
+            inf = SlidingWindowInferer(m, (16, 16, 16), 0.5, "gaussian", engine_batch=4)
+            out = inf(vol).clone()
+            assert inf._state["fused_head"] == (fused == "1")
+            res[fused] = (out, inf._state["count"].clone())
+        assert torch.equal(res["1"][0], res["0"][0]) and torch.equal(res["1"][1], res["0"][1]), mode
+    os.environ["MMSEG_SWI_FUSED_HEAD"] = "1"
+    odd = SlidingWindowInferer(m, (16, 16, 16), 0.5, "gaussian", engine_batch=4)
+    odd(torch.randn(1, 2, 40, 36, 54, device=DEV))        # VX = 54: not a multiple of 4 -> two-kernel path
+    assert odd._state["fused_head"] is False
+    print("[fused head] accumulators bit-identical to the two-kernel path (bf16 + parity), fallback ok", flush=True)
+
+
 def predict_volume_case():
     """predict_volume (pinned host volume -> slab-wise upload overlapping the first windows -> labels in host memory)
     gives exactly the labels of the resident path, for a volume with several upload slabs and a ragged last one."""

@@ -123,6 +123,10 @@ def test_full_size_train_step_properties():
     _c().full_train_step_properties_case()
 
 
+def test_sliding_window_fused_head_bit_identical():
+    _c().fused_head_case()
+
+
 def test_predict_volume_host_to_host():
     _c().predict_volume_case()
 
