@@ -329,14 +329,14 @@ def run_ours(args):
     if os.path.exists(tj):
         traffic = json.load(open(tj)).get("dram_bytes_per_launch_avg")
     roofline = {"bound": "tensor", "kernel": "conv3d_tc_kernel + conv3d_roll_kernel", "achieved": conv_tf, "peak": tf_peak, "unit": "TFLOP/s",
-                "frac": conv_tf / tf_peak, "traffic": traffic,
+                "frac": conv_tf / tf_peak, "frac_of_nominal_2250": conv_tf / 2250.0, "traffic": traffic,
                 "traffic_note": "average DRAM bytes per conv launch (ncu --set full, same 8-window forward; profiles/r01_v5_ncu_conv_launches.csv)",
                 "peak_source": peak_src,
                 "launches": conv["n"] // 3, "avg_launch_ms": conv["ms"] / conv["n"],
                 "share_of_step": conv["ms"] / total_ms,
                 "note": "algorithmic conv FLOPs of one %d-window batch / sum of conv launch durations" % nb}
     roofline_norm = {"bound": "hbm", "kernel": "instnorm_apply(_pool)_kernel", "achieved": norm_gbs, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": norm_gbs / hbm_peak, "traffic": None,
+                     "unit": "GB/s", "frac": norm_gbs / hbm_peak, "frac_of_nominal_8000": norm_gbs / 8000.0, "traffic": None,
                      "share_of_step": norm["ms"] / total_ms, "avg_launch_ms": norm["ms"] / norm["n"]}
     step_tf = n_windows * GF_PER_WINDOW / 1e3 / (ms_step * 1e-3) / world
     # ---- CPU baseline + parity on the bounded sample (rank 0, N=1 only)
