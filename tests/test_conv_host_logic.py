@@ -133,3 +133,41 @@ def test_rolling_z_plans_match_library():
     a.a_cb[0], a.a_cb[1] = 0, 4
     a.src_cbt = 8
     assert _lib.lib.mmseg_conv3d_smem_bytes(C.byref(a)) < 0 and "adjacent" in _lib.last_error()
+
+
+def test_norm_option_tables_host_logic():
+    """engine.norm_kind / ConvRunner._static_table: the (mean, rstd) + shift tables handed to the apply kernel reproduce
+    BatchNorm3d in eval mode (running statistics + affine) and Identity; train-mode BatchNorm is refused loudly."""
+    import pytest
+    import torch
+    import torch.nn.functional as F
+    from mmseg_b200.engine import ConvRunner, norm_kind
+    assert norm_kind(None) == "instance" and norm_kind(torch.nn.InstanceNorm3d(8)) == "instance"
+    assert norm_kind(torch.nn.GroupNorm(8, 16)) == "group" and norm_kind(torch.nn.Identity()) == "none"
+    bn = torch.nn.BatchNorm3d(16)
+    with pytest.raises(NotImplementedError):
+        norm_kind(bn)                                   # training mode: batch statistics are not built
+    with pytest.raises(NotImplementedError):
+        norm_kind(torch.nn.LayerNorm(4))
+    bn.eval()
+    assert norm_kind(bn) == "batch"
+    torch.manual_seed(0)
+    with torch.no_grad():
+        bn.running_mean.normal_()
+        bn.running_var.uniform_(0.5, 2.0)
+        bn.weight.normal_(1.0, 0.3)
+        bn.bias.normal_(0.0, 0.3)
+    r = ConvRunner(False, torch.device("cpu"))
+    mr, shift = r._static_table(bn, "batch", 2, 16, torch.device("cpu"))
+    x = torch.randn(2, 16, 3, 4, 5)
+    got = (x - mr[:, :, 0].view(2, 16, 1, 1, 1)) * mr[:, :, 1].view(2, 16, 1, 1, 1) + shift.view(2, 16, 1, 1, 1)
+    want = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, training=False, eps=bn.eps)
+    assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)
+    mr2, shift2 = r._static_table(bn, "batch", 2, 16, torch.device("cpu"))
+    assert mr2 is mr                                    # cached until a parameter / buffer changes
+    with torch.no_grad():
+        bn.bias.add_(1.0)
+    mr3, shift3 = r._static_table(bn, "batch", 2, 16, torch.device("cpu"))
+    assert torch.allclose(shift3, shift + 1.0)
+    mrn, shn = r._static_table(torch.nn.Identity(), "none", 3, 8, torch.device("cpu"))
+    assert shn is None and bool((mrn[:, :, 0] == 0).all()) and bool((mrn[:, :, 1] == 1).all())
