@@ -173,6 +173,8 @@ def test_sliding_window_vs_oracle(kw):
     ((32, 32, (9, 12, 20)), dict(n_img=2)),                       # ragged tiles, several images
     ((16, 32, (8, 8, 8)), {}),
     ((2, 32, (6, 10, 24)), {}),                                   # first layer (2 real input channels)
+    ((1, 32, (5, 9, 41)), dict(n_img=2)),                         # DualEncoder first layer, ragged x / y tiles
+    ((2, 64, (3, 6, 70)), {}),                                    # 64 output channels: two passes of 8 warps
     ((64, 64, (8, 8, 8)), {}),
     ((64, 32, (6, 16, 16)), dict(segs=[(0, 32), (32, 32)])),      # concat input [up | skip]
     ((32, 8, (6, 7, 20)), dict(ks=1)),                            # out_conv
