@@ -164,10 +164,11 @@ class SlidingWindowInferer:
             # so a rank's partial result travels as ONE tensor in the sharded exchange
             "acc": torch.empty((K_out + 1, VZ, VY, VX), dtype=torch.float32, device=device),
         }
-        # TWO batch slots, each with its own engine buffers, window-origin slot, logits and CUDA stream: the forward of
-        # batch k+1 (tensor-bound convs + HBM-bound norm kernels) runs concurrently with the tail / blend of batch k, so
-        # the memory-bound kernels of one batch hide behind the tensor-bound kernels of the other.  Blends all run on the
-        # caller's stream in window order (deterministic), gated by per-slot events.
+        # n_slots (default 3, MMSEG_SWI_SLOTS) batch slots, each with its own engine buffers, window-origin slot, logits
+        # and CUDA stream: the forward of batch k+1 (tensor-bound convs + HBM-bound norm kernels) runs concurrently with
+        # the tail / blend of batch k, so the memory-bound kernels of one batch hide behind the tensor-bound kernels of
+        # another (measured: 2, 3 and 4 slots are within 0.5 %).  Blends all run on the caller's stream in window order
+        # (deterministic), gated by per-slot events.
         st["slots"] = []
         for j in range(self.n_slots):
             e = eng if j == 0 else type(eng)(eng.module, eng.mode)
