@@ -1,5 +1,8 @@
-"""Mirror of reference src/models/backbones/__init__.py (SwinUNETR is scope row N2: not built)."""
-from .unet import UNet3D
-from .dual_encoder import DualEncoder
+"""Backbones with sm_100a kernels behind the reference's class names (UNet3D, DualEncoder).  SwinUNETR — a thin wrapper
+over MONAI in the reference — is scope row N2 and not built."""
+from . import dual_encoder as _de, unet as _unet
 
-__all__ = ["UNet3D", "DualEncoder"]
+UNet3D = _unet.UNet3D
+DualEncoder = _de.DualEncoder
+
+__all__ = ("UNet3D", "DualEncoder")

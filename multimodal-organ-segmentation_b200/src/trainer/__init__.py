@@ -1,6 +1,10 @@
-"""Mirror of reference src/trainer/__init__.py:5-7."""
-from .trainer import Trainer
-from .losses import get_loss
-from .metrics import get_metrics
+"""Public names of the training package of the sm_100a path — the three the reference's main.py imports
+(`Trainer`, `get_loss`, `get_metrics`; reference src/trainer/__init__.py:5-7) plus the host-to-host inference helpers."""
+from . import losses as _losses, metrics as _metrics, trainer as _trainer
+from .inference import SlidingWindowInferer, predict_volume, sliding_window_inference
 
-__all__ = ["Trainer", "get_loss", "get_metrics"]
+Trainer = _trainer.Trainer
+get_loss = _losses.get_loss
+get_metrics = _metrics.get_metrics
+
+__all__ = ("Trainer", "get_loss", "get_metrics", "SlidingWindowInferer", "predict_volume", "sliding_window_inference")

@@ -67,75 +67,71 @@ class Trainer:
                            f"cuda available: {torch.cuda.is_available()}); there is no CPU fallback")
 
     def _setup_optimizer(self) -> torch.optim.Optimizer:
-        opt_config = self.config["training"]["optimizer"]
-        opt_name = opt_config["name"].lower()
+        """training.optimizer.{name, lr, weight_decay[, betas | momentum]} -> torch optimizer (reference trainer.py:100-124).
+        AdamW is created capturable when hardware.cuda_graph asks for whole-step graph capture."""
+        oc = self.config["training"]["optimizer"]
+        common = dict(lr=oc["lr"], weight_decay=oc.get("weight_decay", 0))
         params = self.model.parameters()
-        lr = opt_config["lr"]
-        weight_decay = opt_config.get("weight_decay", 0)
-        if opt_name == "adam":
-            return torch.optim.Adam(params, lr=lr, weight_decay=weight_decay)
-        elif opt_name == "adamw":
-            betas = tuple(opt_config.get("betas", [0.9, 0.999]))
-            return torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, betas=betas,
-                                     capturable=bool(self.config["hardware"].get("cuda_graph", False)))
-        elif opt_name == "sgd":
-            return torch.optim.SGD(params, lr=lr, momentum=opt_config.get("momentum", 0.9), weight_decay=weight_decay)
-        return torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay)
+        kind = oc["name"].lower()
+        if kind == "adam":
+            return torch.optim.Adam(params, **common)
+        if kind == "sgd":
+            return torch.optim.SGD(params, momentum=oc.get("momentum", 0.9), **common)
+        extra = {}
+        if kind == "adamw":
+            extra = dict(betas=tuple(oc.get("betas", [0.9, 0.999])),
+                         capturable=bool(self.config["hardware"].get("cuda_graph", False)))
+        return torch.optim.AdamW(params, **common, **extra)     # also the reference's fall-through for unknown names
 
     def _setup_scheduler(self):
-        sched_config = self.config["training"].get("scheduler", {})
-        sched_name = sched_config.get("name", "cosine").lower()
-        if sched_name == "cosine":
-            warmup = sched_config.get("warmup_epochs", 0)
-            return torch.optim.lr_scheduler.CosineAnnealingLR(self.optimizer, T_max=self.epochs - warmup,
-                                                              eta_min=sched_config.get("min_lr", 1e-6))
-        elif sched_name == "step":
-            return torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=sched_config.get("step_size", 30),
-                                                   gamma=sched_config.get("gamma", 0.1))
-        elif sched_name == "plateau":
-            return torch.optim.lr_scheduler.ReduceLROnPlateau(self.optimizer, mode="max",
-                                                              patience=sched_config.get("patience", 10),
-                                                              factor=sched_config.get("factor", 0.1))
+        """training.scheduler.name: cosine (default) | step | plateau | anything else = none (reference trainer.py:126-164)."""
+        sc = self.config["training"].get("scheduler", {})
+        kind = sc.get("name", "cosine").lower()
+        S = torch.optim.lr_scheduler
+        if kind == "cosine":
+            return S.CosineAnnealingLR(self.optimizer, T_max=self.epochs - sc.get("warmup_epochs", 0),
+                                       eta_min=sc.get("min_lr", 1e-6))
+        if kind == "step":
+            return S.StepLR(self.optimizer, step_size=sc.get("step_size", 30), gamma=sc.get("gamma", 0.1))
+        if kind == "plateau":
+            return S.ReduceLROnPlateau(self.optimizer, mode="max", patience=sc.get("patience", 10),
+                                       factor=sc.get("factor", 0.1))
         return None
 
     def _resume(self, checkpoint_path: str) -> None:
-        checkpoint = load_checkpoint(self.model, checkpoint_path)
-        if "optimizer_state_dict" in checkpoint:
-            self.optimizer.load_state_dict(checkpoint["optimizer_state_dict"])
-        if "epoch" in checkpoint:
-            self.current_epoch = checkpoint["epoch"]
-        if "best_metric" in checkpoint:
-            self.best_metric = checkpoint["best_metric"]
+        ck = load_checkpoint(self.model, checkpoint_path)
+        if "optimizer_state_dict" in ck:
+            self.optimizer.load_state_dict(ck["optimizer_state_dict"])
+        self.current_epoch = ck.get("epoch", self.current_epoch)
+        self.best_metric = ck.get("best_metric", self.best_metric)
         if self.logger:
             self.logger.info(f"Resumed from epoch {self.current_epoch}")
 
     # ------------------------------------------------------------------ reference trainer.py:166-220
     def train(self) -> Dict[str, Any]:
-        early_stop_config = self.config["training"].get("early_stopping", {})
-        patience = early_stop_config.get("patience", 30)
-        no_improve_count = 0
+        """Epoch loop: train, validate, step the scheduler, write checkpoints, early stopping on the validation Dice."""
+        stop_cfg = self.config["training"].get("early_stopping", {})
+        patience, stale = stop_cfg.get("patience", 30), 0
         for epoch in range(self.current_epoch, self.epochs):
             self.current_epoch = epoch
             train_loss = self._train_epoch()
-            self.history["train_loss"].append(train_loss)
             val_loss, val_metrics = self._validate()
-            self.history["val_loss"].append(val_loss)
-            self.history["val_dice"].append(val_metrics.get("dice", 0))
+            dice = val_metrics.get("dice", 0)
+            for key, value in (("train_loss", train_loss), ("val_loss", val_loss), ("val_dice", dice)):
+                self.history[key].append(value)
             if self.logger:
                 self.logger.info(f"Epoch [{epoch+1}/{self.epochs}] Train Loss: {train_loss:.4f} "
-                                 f"Val Loss: {val_loss:.4f} Val Dice: {val_metrics.get('dice', 0):.4f}")
-            if self.scheduler is not None:
-                if isinstance(self.scheduler, torch.optim.lr_scheduler.ReduceLROnPlateau):
-                    self.scheduler.step(val_metrics.get("dice", 0))
-                else:
-                    self.scheduler.step()
-            self._save_checkpoints(val_metrics)
-            if val_metrics.get("dice", 0) > self.best_metric:
-                self.best_metric = val_metrics.get("dice", 0)
-                no_improve_count = 0
+                                 f"Val Loss: {val_loss:.4f} Val Dice: {dice:.4f}")
+            if isinstance(self.scheduler, torch.optim.lr_scheduler.ReduceLROnPlateau):
+                self.scheduler.step(dice)
+            elif self.scheduler is not None:
+                self.scheduler.step()
+            self._save_checkpoints(val_metrics)      # (written before best_metric is updated, as in the reference)
+            if dice > self.best_metric:
+                self.best_metric, stale = dice, 0
             else:
-                no_improve_count += 1
-            if early_stop_config.get("enabled", False) and no_improve_count >= patience:
+                stale += 1
+            if stop_cfg.get("enabled", False) and stale >= patience:
                 if self.logger:
                     self.logger.info(f"Early stopping at epoch {epoch+1}")
                 break
@@ -263,16 +259,20 @@ class Trainer:
                                         predictor=self.model, overlap=sw["overlap"], mode=sw.get("mode", "constant"))
 
     def _save_checkpoints(self, metrics: Dict[str, float]) -> None:
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_rank() != 0:
+        """last.pth / best.pth / epoch_N.pth under <output_dir>/<name> (reference trainer.py:397-433); rank 0 only."""
+        dist = torch.distributed
+        if dist.is_available() and dist.is_initialized() and dist.get_rank() != 0:
             return
-        ckpt_config = self.config["training"].get("checkpoint", {})
-        if ckpt_config.get("save_last", True):
-            save_checkpoint(self.model, self.optimizer, self.current_epoch, str(self.output_dir / "last.pth"),
-                            best_metric=self.best_metric, history=self.history)
-        if ckpt_config.get("save_best", True) and metrics.get("dice", 0) >= self.best_metric:
-            save_checkpoint(self.model, self.optimizer, self.current_epoch, str(self.output_dir / "best.pth"),
-                            best_metric=metrics.get("dice", 0), history=self.history)
-        save_every = ckpt_config.get("save_every", 0)
-        if save_every > 0 and (self.current_epoch + 1) % save_every == 0:
-            save_checkpoint(self.model, self.optimizer, self.current_epoch,
-                            str(self.output_dir / f"epoch_{self.current_epoch+1}.pth"), best_metric=self.best_metric)
+        cc = self.config["training"].get("checkpoint", {})
+        dice = metrics.get("dice", 0)
+
+        def write(name: str, **extra) -> None:
+            save_checkpoint(self.model, self.optimizer, self.current_epoch, str(self.output_dir / name), **extra)
+
+        if cc.get("save_last", True):
+            write("last.pth", best_metric=self.best_metric, history=self.history)
+        if cc.get("save_best", True) and dice >= self.best_metric:
+            write("best.pth", best_metric=dice, history=self.history)
+        every = cc.get("save_every", 0)
+        if every > 0 and (self.current_epoch + 1) % every == 0:
+            write(f"epoch_{self.current_epoch+1}.pth", best_metric=self.best_metric)
