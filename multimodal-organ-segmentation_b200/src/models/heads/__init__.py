@@ -1,4 +1,8 @@
-"""Mirror of reference src/models/heads/__init__.py (DetectionHead is out of scope: never instantiated)."""
-from .segmentation import SegmentationHead, DeepSupervisionHead
+"""Task heads with sm_100a kernels: SegmentationHead and DeepSupervisionHead.  (The reference's DetectionHead is never
+instantiated by any of its builders and lies outside the hot path — SURVEY.md §2.1.)"""
+from . import segmentation as _seg
 
-__all__ = ["SegmentationHead", "DeepSupervisionHead"]
+SegmentationHead = _seg.SegmentationHead
+DeepSupervisionHead = _seg.DeepSupervisionHead
+
+__all__ = ("SegmentationHead", "DeepSupervisionHead")
