@@ -78,3 +78,45 @@ def to_blocked(x, cbt=None):
     xp = torch.zeros((n, cp, Z, Y, X), dtype=x.dtype)
     xp[:, :c] = x
     return xp.reshape(n, cp // 8, 8, Z, Y, X).permute(0, 1, 3, 4, 5, 2).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ rolling-z schedule
+def roll_schedule(Z, ZS, n_kchunks, kpb=1, R=16, n_items_xy=1):
+    """The stage stream conv3d_roll_kernel's MMA lane generates for one (x, y) column of a volume of depth Z cut into
+    z segments of length ZS (conv_tc.cu, `gen()`): a list of dicts, one per TMA stage, with
+      item, q (input plane index inside the segment, z = zs0 - 1 + q), kc (first K chunk of the stage), chunks,
+      mma = [(ring slot of the first output plane, number of output planes, first dz), ...]  (1 entry, 2 at a ring wrap),
+      acquire = global output-plane indices whose ring slot must be free before the stage (z_empty waits),
+      complete = global output-plane indices signalled complete after the stage (z_full commits).
+    Pure integer logic restated from the kernel so that the `not gpu` tests can check its invariants."""
+    assert n_kchunks % kpb == 0
+    n_st = n_kchunks // kpb
+    stages, gz, g_acq = [], 0, 0
+    n_seg = -(-Z // ZS)
+    for item in range(n_seg * n_items_xy):
+        zs0 = (item % n_seg) * ZS
+        zsv = min(ZS, Z - zs0)
+        q_first = 1 if zs0 == 0 else 0
+        q_last = zsv if zs0 + zsv >= Z else zsv + 1
+        for q in range(q_first, q_last + 1):
+            dz_hi = min(2, q)
+            dz_lo = max(0, q - (zsv - 1))
+            n = dz_hi - dz_lo + 1
+            g_lo = gz + (q - dz_hi)
+            col = g_lo % R
+            n1 = min(n, R - col)
+            mma = [(col, n1, dz_hi)] + ([(0, n - n1, dz_hi - n1)] if n > n1 else [])
+            zneed = gz + min(q, zsv - 1) + 1
+            for kc in range(n_st):
+                acquire = list(range(g_acq, zneed)) if g_acq < zneed else []
+                g_acq = max(g_acq, zneed)
+                complete = []
+                if kc == n_st - 1:
+                    if q >= 2:
+                        complete.append(gz + q - 2)
+                    if q == q_last and q_last == zsv:
+                        complete.append(gz + zsv - 1)
+                stages.append(dict(item=item, q=q, z=zs0 - 1 + q, kc=kc * kpb, chunks=kpb, mma=mma, acquire=acquire,
+                                   complete=complete, gz=gz, zsv=zsv, zs0=zs0))
+        gz += zsv
+    return stages

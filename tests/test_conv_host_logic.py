@@ -171,3 +171,47 @@ def test_norm_option_tables_host_logic():
     assert torch.allclose(shift3, shift + 1.0)
     mrn, shn = r._static_table(torch.nn.Identity(), "none", 3, 8, torch.device("cpu"))
     assert shn is None and bool((mrn[:, :, 0] == 0).all()) and bool((mrn[:, :, 1] == 1).all())
+
+
+def test_rolling_z_schedule_invariants():
+    """The stage stream of the rolling-z kernel (restated in tests/emulate.py): every output plane receives exactly the
+    taps dz of its (up to three) in-volume input planes from every K chunk, is acquired before its first MMA, is signalled
+    complete exactly once and only after its last contribution, and a ring slot is never reused before it completed."""
+    from tests.emulate import roll_schedule
+    R = 16
+    for (Z, ZS, kc_n, kpb) in [(96, 32, 2, 1), (96, 32, 4, 2), (96, 48, 1, 1), (40, 17, 2, 2), (37, 37, 2, 1), (1, 4, 1, 1),
+                               (5, 2, 4, 2), (128, 32, 4, 2), (19, 7, 4, 2)]:
+        st = roll_schedule(Z, ZS, kc_n, kpb, R, n_items_xy=3)
+        n_seg = -(-Z // ZS)
+        contrib, acquired, completed = {}, set(), {}
+        for i, s in enumerate(st):
+            assert 0 <= s["z"] < Z                                   # only in-volume input planes are loaded
+            for g in s["acquire"]:
+                assert g not in acquired
+                acquired.add(g)
+                assert g < R or (g - R) in completed, (g, "slot reused before its previous plane completed")
+            zo_first = None
+            for (col, n, dz_first) in s["mma"]:
+                assert 1 <= n <= 3 and col + n <= R                  # one MMA never wraps the ring
+                for j in range(n):
+                    dz = dz_first - j                                # weight rows are dz-descending
+                    zo = s["q"] - dz                                 # output plane inside the segment
+                    assert 0 <= zo < s["zsv"] and 0 <= dz <= 2
+                    g = s["gz"] + zo
+                    assert g % R == col + j and g in acquired and g not in completed
+                    for c in range(s["kc"], s["kc"] + s["chunks"]):
+                        key = (g, dz, c)
+                        assert key not in contrib
+                        contrib[key] = i
+                    zo_first = zo if zo_first is None else zo_first
+            for g in s["complete"]:
+                assert g not in completed
+                completed[g] = i
+        total_planes = 3 * Z                                         # three columns of the same depth
+        assert sorted(completed) == list(range(total_planes)) and acquired == set(range(total_planes))
+        for g in range(total_planes):
+            z = g % Z                                                # global plane -> volume z (segments tile the depth)
+            want = {(g, dz, c) for dz in range(3) for c in range(kc_n) if 0 <= z + dz - 1 < Z}
+            got = {k for k in contrib if k[0] == g}
+            assert got == want, (Z, ZS, g, sorted(want - got), sorted(got - want))
+            assert max(contrib[k] for k in got) <= completed[g]       # complete only after the last contribution
