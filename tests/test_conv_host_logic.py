@@ -215,3 +215,30 @@ def test_rolling_z_schedule_invariants():
             got = {k for k in contrib if k[0] == g}
             assert got == want, (Z, ZS, g, sorted(want - got), sorted(got - want))
             assert max(contrib[k] for k in got) <= completed[g]       # complete only after the last contribution
+
+
+def test_epilogue_incremental_row_mapping():
+    """The conv epilogue advances its voxel position by 128 accumulator rows per M tile without dividing (conv_tc.cu:
+    xx += dx128, carry into yy, yy += dy128, carry into zz for the flat k=1 tiles): the carries are exact for every plane
+    shape the planner can produce."""
+    for PX in range(1, 129):
+        for PY in (1, 2, 3, 4, 5, 7, 8, 11, 16, 31, 64):
+            pxy = PX * PY
+            dz128 = 128 // pxy
+            r = 128 - dz128 * pxy
+            dy128, dx128 = r // PX, r % PX
+            for L0 in (0, 1, 31, 32, 63, 95, 96, 127):
+                zz = L0 // pxy
+                yy, xx = (L0 - zz * pxy) // PX, (L0 - zz * pxy) % PX
+                for m in range(8):
+                    L = m * 128 + L0
+                    assert (zz, yy, xx) == (L // pxy, (L % pxy) // PX, (L % pxy) % PX), (PX, PY, L)
+                    xx += dx128
+                    if xx >= PX:
+                        xx -= PX
+                        yy += 1
+                    yy += dy128
+                    if yy >= PY:
+                        yy -= PY
+                        zz += 1
+                    zz += dz128
