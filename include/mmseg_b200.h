@@ -14,7 +14,9 @@
  *  - spatial axes are named (Z, Y, X) = tensor dims (2, 3, 4) of the reference's [B, C, H, W, D]; X is stride-1.
  *
  * Device data layouts
- *  - "blocked" activations: [n_img * cbt][Z][Y][X][8] bf16 — channels in blocks of 8 (16 bytes per voxel per block);
+ *  - "blocked" activations: [n_img * cbt][Z][Y][X][8] bf16 (or fp16: MMSEG_FMT_FP16 / MMSEG_CONV_FP16, the "fp16"
+ *    numeric modes; every comment below that says bf16 means "the 16-bit element format") — channels in blocks of 8
+ *    (16 bytes per voxel per block);
  *    cbt = channel blocks per image held by the buffer (a buffer may hold a concat of several producers, and, in the
  *    3-pass "parity" numeric mode, a bf16 hi plane followed by a bf16 lo plane of the same channels).
  *  - raw conv output before InstanceNorm: same blocked shape, bf16 (fast mode) or fp32 (parity mode).
@@ -29,7 +31,11 @@
 extern "C" {
 #endif
 
-#define MMSEG_ABI_VERSION 1
+#define MMSEG_ABI_VERSION 2
+/* 16-bit element format of blocked activations / packed weights (`fmt` arguments): the tensor cores run kind::f16 on
+ * either at the same rate; fp16 carries an 11-bit significand (bf16: 8) at a narrower exponent range. */
+#define MMSEG_FMT_BF16 0
+#define MMSEG_FMT_FP16 1
 #define MMSEG_MAX_KCHUNKS 256
 #define MMSEG_MAX_WGRAD_GROUPS 64
 
@@ -70,6 +76,7 @@ int mmseg_device_ok(void);
  */
 #define MMSEG_CONV_ROLL_Z 16
 #define MMSEG_CONV_ROLL_KPAIR 32   /* rolling-z: one TMA stage = two adjacent K chunks (4 channel blocks) */
+#define MMSEG_CONV_FP16 64         /* activations, weights and 16-bit outputs are fp16 instead of bf16 (MMSEG_FMT_FP16) */
 typedef struct {
   const void* src;       /* blocked bf16 [n_img*src_cbt][Z][Y][X][8]                                  */
   const void* weights;   /* packed bf16, see layout above                                             */
@@ -176,6 +183,7 @@ typedef struct {
                                  affine norms of ConvBlock3D (GroupNorm / BatchNorm, unet.py:30-38) fold gamma into
                                  rstd and pass beta here; not combined with stats_partial                         */
   int32_t act;                /* 0: ReLU / LeakyReLU(slope); 1: exact GELU (ConvBlock3D activation="gelu", unet.py:47-48) */
+  int32_t elem_fmt;           /* MMSEG_FMT_*: element type of the 16-bit tensors (src when !src_is_f32, dst, pooled) */
 } mmseg_norm_args;
 int mmseg_instnorm_act_apply(const mmseg_norm_args* args, void* stream);
 
@@ -214,16 +222,16 @@ int mmseg_unshuffle_k2s2(const void* src, int32_t n_img, int32_t src_cbt, int32_
 
 /* NCDHW fp32 [n_img][C][Z][Y][X] -> blocked bf16 (hi[, lo]) with channels zero-padded to cb*8.  Module boundary. */
 int mmseg_pack_ncdhw(const float* src, void* dst, int32_t n_img, int32_t C, int32_t Z, int32_t Y, int32_t X,
-                     int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, int32_t cb, void* stream);
+                     int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, int32_t cb, int32_t fmt, void* stream);
 /* blocked bf16 (hi[, lo]) -> NCDHW fp32 (feature taps for return_features / hooks). */
 /* mmseg_pack_ncdhw with SUVGuidedAttention's element-wise steps folded in (fusion/attention_fusion.py:283-292):
  * pre_sigmoid: x <- sigmoid((x - pre_sub) * pre_mul) (soft SUV mask); gate_logits [n_img][voxels] fp32 or NULL:
  * x <- x * (1 + sigmoid(gate)) (CT features modulated by the spatial attention). */
 int mmseg_pack_ncdhw_ex(const float* src, void* dst, int32_t n_img, int32_t C, int32_t Z, int32_t Y, int32_t X,
                         int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, int32_t cb, int32_t pre_sigmoid,
-                        float pre_sub, float pre_mul, const float* gate_logits, void* stream);
+                        float pre_sub, float pre_mul, const float* gate_logits, int32_t fmt, void* stream);
 int mmseg_unpack_ncdhw(const void* src, float* dst, int32_t n_img, int32_t C, int32_t Z, int32_t Y, int32_t X,
-                       int32_t src_cbt, int32_t src_cb_off, int32_t src_lo_off, void* stream);
+                       int32_t src_cbt, int32_t src_cb_off, int32_t src_lo_off, int32_t fmt, void* stream);
 
 /*
  * Sliding-window inference pieces (monai.inferers.sliding_window_inference as called at
@@ -238,7 +246,7 @@ int mmseg_unpack_ncdhw(const void* src, float* dst, int32_t n_img, int32_t C, in
  */
 int mmseg_swi_gather(const float* volume, int32_t C, int32_t VZ, int32_t VY, int32_t VX, const int32_t* starts_dev,
                      int32_t n_win, int32_t RZ, int32_t RY, int32_t RX, void* dst, int32_t dst_cbt, int32_t dst_lo_off,
-                     int32_t cb, void* stream);
+                     int32_t cb, int32_t fmt, void* stream);
 /* out_conv (1x1x1, C -> K <= 8 classes, unet.py:163,199) fused into the blend of ONE window: the logits of window
  * `window` of the blocked feature batch are computed in registers and blended into out / count (same arithmetic and order
  * as mmseg_conv1x1_logits + mmseg_swi_blend in window mode, bit-identical accumulators) — the logits tensor is never
@@ -247,14 +255,22 @@ int mmseg_swi_logits_blend(const void* feat, int32_t src_cbt, int32_t cb_off, in
                            const float* weight /* [K][cin] fp32 */, const float* bias, int32_t K,
                            const int32_t* starts_dev /* this window's origin */, int32_t RZ, int32_t RY, int32_t RX,
                            const float* wz, const float* wy, const float* wx, float w_floor, float* out, float* count,
-                           int32_t VZ, int32_t VY, int32_t VX, void* stream);
+                           int32_t VZ, int32_t VY, int32_t VX, int32_t fmt, void* stream);
 int mmseg_swi_blend(const float* win_logits /* [n_win][K][RZ][RY][RX] */, const int32_t* starts_dev, int32_t n_win,
                     int32_t K, int32_t RZ, int32_t RY, int32_t RX, const float* wz, const float* wy, const float* wx,
                     float w_floor, float* out /* [K][VZ][VY][VX] */, float* count /* [VZ][VY][VX] */, int32_t VZ,
                     int32_t VY, int32_t VX, int32_t bz0, int32_t bz1, int32_t by0, int32_t by1, int32_t bx0,
                     int32_t bx1, void* stream);
-int mmseg_swi_finalize(float* out, const float* count, int32_t K, int64_t voxels, int32_t normalize_in_place,
-                       uint8_t* labels /* or NULL */, void* stream);
+/* finalize: `out` / `count` / `labels` address the first voxel of the range; class plane c of `out` starts
+ * c * plane_stride elements further, so an axis-0 slab of the [K][VZ][VY][VX] accumulator is finalized in place
+ * (whole volume: plane_stride == voxels). */
+int mmseg_swi_finalize(float* out, const float* count, int32_t K, int64_t voxels, int64_t plane_stride,
+                       int32_t normalize_in_place, uint8_t* labels /* or NULL */, void* stream);
+/* acc[p][i] += part[p][i], p < planes, i < n (plane strides in elements): the one add of the sharded (multi-GPU) path —
+ * the owner of an axis-0 slab adds, in rank order, the partial sums (K weighted-logit planes + the count map) another
+ * rank accumulated over that slab.  No reference counterpart: the reference has no distributed path. */
+int mmseg_swi_add_partial(float* acc, int64_t acc_plane_stride, const float* part, int64_t part_plane_stride,
+                          int32_t planes, int64_t n, void* stream);
 
 /*
  * DiceCE forward in one pass over the logits (src/trainer/losses.py:216-228, DiceLoss :39-80, CrossEntropyLoss).
@@ -318,12 +334,12 @@ int mmseg_confusion_hist(const void* pred, int32_t pred_is_u8, const int64_t* ta
  */
 int mmseg_channel_mean(const void* src, int32_t n_img, int32_t src_cbt, int32_t cb_off, int32_t lo_off, int32_t cb,
                        int64_t voxels, float* partial /* [n_img*cb][n_chunks][8] */, int32_t n_chunks,
-                       float* mean /* [n_img][cb*8] */, void* stream);
+                       float* mean /* [n_img][cb*8] */, int32_t fmt, void* stream);
 int mmseg_gate_mlp(const float* pooled, const float* w1, const float* b1, const float* w2, const float* b2,
                    int32_t n_img, int32_t MC, int32_t H, int32_t M, float* weights /* [n_img][M] */, void* stream);
 int mmseg_modality_combine(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_lo_off, int32_t M, int32_t cb,
                            int64_t voxels, const float* weights /* [n_img][M] or NULL */, float uniform_weight,
-                           void* dst, int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, void* stream);
+                           void* dst, int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, int32_t fmt, void* stream);
 /* F.interpolate(x, size=(Zo,Yo,Xo), mode="trilinear", align_corners=True) on fp32 [n_planes = N*C][Zi][Yi][Xi]:
  * DeepSupervisionHead's resize of coarse-scale logits (src/models/heads/segmentation.py:108-113). */
 int mmseg_trilinear_resize(const float* src, int32_t n_planes, int32_t Zi, int32_t Yi, int32_t Xi, float* dst, int32_t Zo,
@@ -332,13 +348,14 @@ int mmseg_trilinear_resize(const float* src, int32_t n_planes, int32_t Zi, int32
  * cores at HBM speed: src blocked bf16 (channels cb_off*8 .. +cin, optional lo plane lo_off blocks away, parity mode),
  * weight fp32 [cout][cin], bias fp32 [cout] or NULL, dst fp32 NCDHW [n_img][cout][voxels].  cin % 8 == 0, cout <= 16. */
 int mmseg_conv1x1_logits(const void* src, int32_t n_img, int32_t src_cbt, int32_t cb_off, int32_t lo_off, int32_t cin,
-                         int64_t voxels, const float* weight, const float* bias, int32_t cout, float* dst, void* stream);
+                         int64_t voxels, const float* weight, const float* bias, int32_t cout, float* dst, int32_t fmt,
+                         void* stream);
 /* dst[b, c] = max over modalities (LateFusion fusion_method="max", src/models/fusion/late_fusion.py:62-64); bf16 mode. */
 int mmseg_modality_max(const void* src, int32_t n_img, int32_t src_cbt, int32_t M, int32_t cb, int64_t voxels, void* dst,
                        int32_t dst_cbt, int32_t dst_cb_off, void* stream);
 int mmseg_maxpool3d_2(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_cb_off, int32_t src_lo_off,
                       int32_t cb, int32_t Z, int32_t Y, int32_t X, void* dst, int32_t dst_cbt, int32_t dst_cb_off,
-                      int32_t dst_lo_off, void* stream);
+                      int32_t dst_lo_off, int32_t fmt, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,10 @@ OUT_BLOCKED_BF16_HILO = 2
 OUT_CONVT_K2S2 = 3
 OUT_NCDHW_F32 = 4
 
+FMT_BF16 = 0
+FMT_FP16 = 1
+CONV_FP16_FLAG = 64   # MMSEG_CONV_FP16
+
 
 class ConvArgs(C.Structure):
     _fields_ = [
@@ -67,7 +71,7 @@ class NormArgs(C.Structure):
         ("pool_cbt", C.c_int32), ("pool_cb_off", C.c_int32), ("pool_lo_off", C.c_int32),
         ("slope", C.c_float),
         ("stats_partial", C.c_void_p), ("mean_rstd_out", C.c_void_p), ("tiles_per_img", C.c_int32), ("eps", C.c_float),
-        ("shift", C.c_void_p), ("act", C.c_int32),
+        ("shift", C.c_void_p), ("act", C.c_int32), ("elem_fmt", C.c_int32),
     ]
 
 
@@ -89,12 +93,13 @@ SYMBOLS = {
     "mmseg_instnorm_act_bwd_apply": (C.c_int, [C.POINTER(NormBwdArgs), _vp]),
     "mmseg_modality_dot": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _vp]),
     "mmseg_unshuffle_k2s2": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
-    "mmseg_pack_ncdhw": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "mmseg_unpack_ncdhw": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "mmseg_swi_gather": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
+    "mmseg_pack_ncdhw": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "mmseg_unpack_ncdhw": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "mmseg_swi_gather": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "mmseg_swi_blend": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _vp,
                                   _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "mmseg_swi_finalize": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp]),
+    "mmseg_swi_finalize": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i32, _vp, _vp]),
+    "mmseg_swi_add_partial": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i64, _vp]),
     "mmseg_dicece_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _f32, _f32, _f32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "mmseg_dicece_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _f32, _f32, _f32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mmseg_tversky_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _f32, _f32, _f32, _vp, _i32, _vp, _vp, _vp]),
@@ -104,17 +109,17 @@ SYMBOLS = {
                                             _f32, _vp]),
     "mmseg_add_stats": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _i32, _vp]),
     "mmseg_confusion_hist": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _vp]),
-    "mmseg_channel_mean": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _vp]),
+    "mmseg_channel_mean": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _i32, _vp]),
     "mmseg_gate_mlp": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
-    "mmseg_modality_combine": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _f32, _vp, _i32, _i32, _i32, _vp]),
+    "mmseg_modality_combine": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _f32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "mmseg_modality_max": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i64, _vp, _i32, _i32, _vp]),
     "mmseg_swi_logits_blend": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp,
-                                         _vp, _f32, _vp, _vp, _i32, _i32, _i32, _vp]),
-    "mmseg_pack_ncdhw_ex": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp]),
+                                         _vp, _f32, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "mmseg_pack_ncdhw_ex": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _i32, _vp]),
     "mmseg_groupnorm_finalize": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i64, _f32, _vp, _vp, _vp, _vp, _vp]),
     "mmseg_trilinear_resize": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
-    "mmseg_conv1x1_logits": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _i32, _vp, _vp]),
-    "mmseg_maxpool3d_2": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
+    "mmseg_conv1x1_logits": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _i32, _vp, _i32, _vp]),
+    "mmseg_maxpool3d_2": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
 }
 
 if not os.path.exists(LIB_PATH):

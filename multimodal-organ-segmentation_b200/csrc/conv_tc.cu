@@ -36,6 +36,7 @@ struct ConvKParams {
   uint32_t w_off, a_off;  // smem offsets (from the 128-aligned base)
   int out_mode, out_channels, dst_cbt, dst_cb_off, dst_lo_off;
   int desc_swap;
+  int fp16;           // 16-bit element format of activations / weights / 16-bit outputs: 0 bf16, 1 fp16 (MMSEG_CONV_FP16)
   int w_stages;       // weight ring slots (2 for k=3: 27 taps per chunk; >= 8 for k=1: tiny chunks, latency-bound)
   int w_resident;     // k=1 only: every K chunk's weights stay in shared memory for the CTA's lifetime (one load)
   int n_tiles;        // voxel tiles (all images) swept by the persistent CTAs of one N tile
@@ -76,30 +77,6 @@ __device__ __forceinline__ size_t blocked_off(int blk, int Z, int Y, int X, int 
   return ((((size_t)blk * Z + z) * Y + y) * X + x) * 8;
 }
 
-__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
-  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
-  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]);
-  __nv_bfloat162 d = __floats2bfloat162_rn(v[6], v[7]);
-  uint4 r;
-  r.x = *reinterpret_cast<uint32_t*>(&a);
-  r.y = *reinterpret_cast<uint32_t*>(&b);
-  r.z = *reinterpret_cast<uint32_t*>(&c);
-  r.w = *reinterpret_cast<uint32_t*>(&d);
-  return r;
-}
-__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
-  float h[8], l[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    __nv_bfloat16 bh = __float2bfloat16_rn(v[i]);
-    h[i] = __bfloat162float(bh);
-    l[i] = v[i] - h[i];
-  }
-  hi = pack8_bf16(h);
-  lo = pack8_bf16(l);
-}
-
 // UMMA with the two descriptor words passed separately: only the low word (start address) changes per MMA.
 __device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                           uint32_t idesc) {
@@ -113,14 +90,15 @@ __device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32
       : "memory");
 }
 
-// MT = 128-row M tiles per output plane, KS = filter size (3: padding 1, taps along z folded into the MMA N dimension).
+// MT = 128-row M tiles per output plane, KS = filter size (3: padding 1, taps along z folded into the MMA N dimension),
+// FP16 = 16-bit element format of operands and 16-bit outputs (false: bf16, true: fp16 — same MMA rate, 11-bit significand).
 //
 // Accumulator (m, zo) lives at TMEM column (m*TZ + zo)*NT, so the accumulators of consecutive output planes are
 // adjacent: ONE MMA of N = nz*NT columns adds input plane `pl`'s contribution for the filter taps dz = dz_hi..dz_lo to the
 // nz output planes zo = pl-dz_hi .. pl-dz_lo (the weight rows are stored dz-descending).  This triples the MMA N for
 // the C_out = 32 / 64 layers (an M=128, K=16 MMA costs >= ~51 clk whatever N is, measured).  All accumulators are
 // zeroed by the epilogue warps while the first TMA loads are in flight, so every MMA accumulates.
-template <int MT, int KS>
+template <int MT, int KS, bool FP16>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ ConvKParams p) {
   constexpr int KT = KS;  // taps per axis
@@ -219,6 +197,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // the critical resource of this kernel (measured: every extra dependent instruction per plane shows up 1:1 in the
     // kernel time), hence the per-tap offsets are precomputed and only two adds per MMA remain.
     const bool leader = elect_one();
+    constexpr bool fp16 = FP16;
     const uint32_t NT = (uint32_t)p.NT;
     const uint32_t brows = (uint32_t)KT * NT;                   // weight rows per (tap9, k half): dz-descending x NT
     const uint32_t a_hi = (128u >> 4) | (1u << 14);             // SBO = 128 B, descriptor version 1
@@ -255,7 +234,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         constexpr int G1 = 16;
         const int g1 = min(G1, p.stages);
         const int total = p.n_kchunks * tz_valid;
-        const uint32_t idesc1 = make_idesc_bf16(128, NT);
+        const uint32_t idesc1 = make_idesc_16(128, NT, fp16);
         int kc = 0, pl = 0;
         for (int j0 = 0; j0 < total; j0 += g1) {
           const int cnt = min(g1, total - j0);
@@ -331,7 +310,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int dz_hi = min(KT - 1, q);
             const int dz_lo = max(0, q - tz_valid + 1);
             nzv[h] = (uint32_t)max(dz_hi - dz_lo + 1, 0);
-            idesc[h] = make_idesc_bf16(128, nzv[h] * NT);
+            idesc[h] = make_idesc_16(128, nzv[h] * NT, fp16);
             d0[h] = acc_base + (uint32_t)(q - dz_hi) * NT;
             at0[h] = (((a_smem + si * p.stage_bytes) >> 4) & 0x3FFFu) | a_lbo;
             bt0[h] = b_base + (uint32_t)(KT - 1 - dz_hi) * NT;   // first weight row of the dz range
@@ -480,8 +459,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
               char* o = cg_base + off;
               if constexpr (MODE == MMSEG_OUT_BLOCKED_BF16) {
-                *reinterpret_cast<uint4*>(o) = pack8_bf16(v);
-                *reinterpret_cast<uint4*>(o + half) = pack8_bf16(v + 8);
+                *reinterpret_cast<uint4*>(o) = cvt8_from_f32(v, FP16);
+                *reinterpret_cast<uint4*>(o + half) = cvt8_from_f32(v + 8, FP16);
               } else if constexpr (MODE == MMSEG_OUT_BLOCKED_F32) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -493,20 +472,20 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                   uint4 hi, lo;
-                  split8(v + 8 * h, hi, lo);
+                  split8_from_f32(v + 8 * h, hi, lo, FP16);
                   *reinterpret_cast<uint4*>(o + h * half) = hi;
                   *reinterpret_cast<uint4*>(o + h * half + lo_bytes) = lo;
                 }
               } else if constexpr (MODE == MMSEG_OUT_CONVT_K2S2) {
                 // column n = (((dz*2 + dy)*CB + cb)*2 + dx)*8 + j: a thread's 16 columns are the SAME 8 output channels
                 // at the two x-adjacent output voxels -> one contiguous 32-byte store per thread, 1 KB per warp
-                *reinterpret_cast<uint4*>(o) = pack8_bf16(v);
-                *reinterpret_cast<uint4*>(o + 16) = pack8_bf16(v + 8);
+                *reinterpret_cast<uint4*>(o) = cvt8_from_f32(v, FP16);
+                *reinterpret_cast<uint4*>(o + 16) = cvt8_from_f32(v + 8, FP16);
               } else if constexpr (MODE == kModeConvtHiLo) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                   uint4 hi, l;
-                  split8(v + 8 * h, hi, l);
+                  split8_from_f32(v + 8 * h, hi, l, FP16);
                   *reinterpret_cast<uint4*>(o + 16 * h) = hi;
                   *reinterpret_cast<uint4*>(o + 16 * h + lo_bytes) = l;
                 }
@@ -693,6 +672,7 @@ static_assert(sizeof(RollHeader) <= kRollHeaderBytes, "roll header too large");
 // per-plane epilogue (~700 cycles) was slower than a plane's MMAs for C_in <= 32)
 constexpr int kRollThreads = 320;
 
+template <bool FP16>
 __global__ void __launch_bounds__(kRollThreads, 1)
 conv3d_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ ConvKParams p) {
   constexpr int KT = 3;
@@ -704,6 +684,7 @@ conv3d_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t a_smem = smem_base + p.a_off;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr bool fp16 = FP16;
   constexpr uint32_t R = 16;   // ring slots: 512 TMEM columns / NT (NT = 32, checked on the host); a power of two so
                                // that the ring arithmetic of the issue loop is shifts and masks, not divisions
   const int ZS = p.TZ;
@@ -825,9 +806,9 @@ conv3d_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const uint32_t bb = w_base0 + (uint32_t)(kc * kpb) * w_step + (uint32_t)(KT - 1 - dz_hi) * NT;
         d.bta = bb;
         d.d0a = tmem_base + col * NT;
-        d.ida = make_idesc_bf16(128, n1 * NT);
+        d.ida = make_idesc_16(128, n1 * NT, fp16);
         d.btb = bb + n1 * NT;
-        d.idb = n > n1 ? make_idesc_bf16(128, (n - n1) * NT) : 0u;
+        d.idb = n > n1 ? make_idesc_16(128, (n - n1) * NT, fp16) : 0u;
         d.zneed = gz + (uint32_t)min(q, zsv - 1) + 1u;        // ring slots [.., zneed) must be acquired before this stage
         d.zc0 = 0u; d.zc1 = 0u;
         if (kc == n_st - 1) {                                 // last stage of plane q: output plane q-2 is complete
@@ -960,8 +941,8 @@ conv3d_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (int i = 0; i < 16; ++i) { s1[i] += va[i]; s2[i] = fmaf(va[i], va[i], s2[i]); }
           }
           __nv_bfloat16* o = row + (size_t)zo * plane * 8;
-          *reinterpret_cast<uint4*>(o) = pack8_bf16(va);
-          *reinterpret_cast<uint4*>(o + nvox * 8) = pack8_bf16(va + 8);
+          *reinterpret_cast<uint4*>(o) = cvt8_from_f32(va, fp16);
+          *reinterpret_cast<uint4*>(o + nvox * 8) = cvt8_from_f32(va + 8, fp16);
         }
       }
       if (prev_slot >= 0) {
@@ -1120,6 +1101,7 @@ static int plan_conv(const mmseg_conv_args* a, ConvPlan* out) {
   k.out_mode = a->out_mode; k.out_channels = a->out_channels;
   k.dst_cbt = a->dst_cbt; k.dst_cb_off = a->dst_cb_off; k.dst_lo_off = a->dst_lo_off;
   k.desc_swap = a->flags & 1;
+  k.fp16 = (a->flags & MMSEG_CONV_FP16) ? 1 : 0;
   k.dbg_flags = a->flags;
   k.dbg = (a->flags & 2) ? reinterpret_cast<long long*>(a->stats_partial) : nullptr;  // debug: counters replace stats
   k.n_tiles = k.tiles_x * k.tiles_y * k.tiles_z * a->n_img;
@@ -1169,18 +1151,18 @@ extern "C" int mmseg_conv3d_fwd(const mmseg_conv_args* a, void* stream) {
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(MMSEG_ERR_CUDA, "conv3d: cuTensorMapEncodeTiled failed (%d)", (int)cr);
   typedef void (*KernelFn)(const CUtensorMap, const ConvKParams);
-  static const KernelFn table[2][kMaxMT] = {
-      {conv3d_tc_kernel<1, 1>, conv3d_tc_kernel<2, 1>, conv3d_tc_kernel<3, 1>, conv3d_tc_kernel<4, 1>,
-       conv3d_tc_kernel<5, 1>, conv3d_tc_kernel<6, 1>, conv3d_tc_kernel<7, 1>, conv3d_tc_kernel<8, 1>},
-      {conv3d_tc_kernel<1, 3>, conv3d_tc_kernel<2, 3>, conv3d_tc_kernel<3, 3>, conv3d_tc_kernel<4, 3>,
-       conv3d_tc_kernel<5, 3>, conv3d_tc_kernel<6, 3>, conv3d_tc_kernel<7, 3>, conv3d_tc_kernel<8, 3>}};
+#define MMSEG_ROW(KS, F) {conv3d_tc_kernel<1, KS, F>, conv3d_tc_kernel<2, KS, F>, conv3d_tc_kernel<3, KS, F>, conv3d_tc_kernel<4, KS, F>, \
+                          conv3d_tc_kernel<5, KS, F>, conv3d_tc_kernel<6, KS, F>, conv3d_tc_kernel<7, KS, F>, conv3d_tc_kernel<8, KS, F>}
+  static const KernelFn table[2][2][kMaxMT] = {{MMSEG_ROW(1, false), MMSEG_ROW(3, false)}, {MMSEG_ROW(1, true), MMSEG_ROW(3, true)}};
+#undef MMSEG_ROW
   static bool attr_set = false;
   if (!attr_set) {
-    for (int i = 0; i < 2; ++i)
-      for (int j = 0; j < kMaxMT; ++j) {
-        cudaError_t e = cudaFuncSetAttribute(table[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return fail(MMSEG_ERR_CUDA, "conv3d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      }
+    for (int f = 0; f < 2; ++f)
+      for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < kMaxMT; ++j) {
+          cudaError_t e = cudaFuncSetAttribute(table[f][i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+          if (e != cudaSuccess) return fail(MMSEG_ERR_CUDA, "conv3d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        }
     attr_set = true;
   }
   static int n_sms = 0;
@@ -1191,12 +1173,14 @@ extern "C" int mmseg_conv3d_fwd(const mmseg_conv_args* a, void* stream) {
   if (k.roll) {
     static bool roll_attr = false;
     if (!roll_attr) {
-      cudaError_t e = cudaFuncSetAttribute(conv3d_roll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaError_t e = cudaFuncSetAttribute(conv3d_roll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3d_roll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return fail(MMSEG_ERR_CUDA, "conv3d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       roll_attr = true;
     }
     const int n_ctas = k.n_tiles < n_sms ? k.n_tiles : n_sms;
-    conv3d_roll_kernel<<<n_ctas, kRollThreads, pl.smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tm, k);
+    if (k.fp16) conv3d_roll_kernel<true><<<n_ctas, kRollThreads, pl.smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tm, k);
+    else conv3d_roll_kernel<false><<<n_ctas, kRollThreads, pl.smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tm, k);
     return check_launch("conv3d_roll_kernel");
   }
   // persistent CTAs: about one per SM in total, each sweeping its share of the voxel tiles of one N tile
@@ -1204,6 +1188,6 @@ extern "C" int mmseg_conv3d_fwd(const mmseg_conv_args* a, void* stream) {
   if (ctas < 1) ctas = 1;
   if (ctas > k.n_tiles) ctas = k.n_tiles;
   dim3 grid((unsigned)ctas, (unsigned)k.n_ntiles);
-  table[a->ksize == 3 ? 1 : 0][k.mt - 1]<<<grid, kThreads, pl.smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tm, k);
+  table[k.fp16][a->ksize == 3 ? 1 : 0][k.mt - 1]<<<grid, kThreads, pl.smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tm, k);
   return check_launch("conv3d_tc_kernel");
 }

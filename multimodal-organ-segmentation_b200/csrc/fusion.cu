@@ -8,43 +8,15 @@ namespace mmseg {
 
 int num_sms();
 
-__device__ __forceinline__ void ld8_bf16(const __nv_bfloat16* p, float* v) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 f = __bfloat1622float2(h[i]);
-    v[2 * i] = f.x;
-    v[2 * i + 1] = f.y;
-  }
-}
-__device__ __forceinline__ uint4 pk8(const float* v) {
-  uint4 r;
-  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
-  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
-  r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
-  r.z = *reinterpret_cast<uint32_t*>(&c); r.w = *reinterpret_cast<uint32_t*>(&d);
-  return r;
-}
-__device__ __forceinline__ void st8_act(__nv_bfloat16* dst, size_t off, size_t lo_delta, const float* y) {
-  if (lo_delta == 0) {
-    *reinterpret_cast<uint4*>(dst + off) = pk8(y);
-  } else {
-    float h[8], l[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      h[i] = __bfloat162float(__float2bfloat16_rn(y[i]));
-      l[i] = y[i] - h[i];
-    }
-    *reinterpret_cast<uint4*>(dst + off) = pk8(h);
-    *reinterpret_cast<uint4*>(dst + off + lo_delta) = pk8(l);
-  }
+// 16-byte (8-channel) vector accessors in the blocked buffer's element format (bf16 / fp16), 2-byte element offsets
+__device__ __forceinline__ void ld8_e(const uint16_t* p, float* v, bool fp16) {
+  cvt8_to_f32(*reinterpret_cast<const uint4*>(p), v, fp16);
 }
 
 // grid (n_chunks, n_img*cb): per-chunk partial sums of 8 channels -> partial[(blk*n_chunks + chunk)*8 + i]
 __global__ void __launch_bounds__(256)
-channel_sum_partial_kernel(const __nv_bfloat16* __restrict__ src, int src_cbt, int cb_off, int lo_off, int cb,
-                           size_t nvox, float* __restrict__ partial) {
+channel_sum_partial_kernel(const uint16_t* __restrict__ src, int src_cbt, int cb_off, int lo_off, int cb,
+                           size_t nvox, float* __restrict__ partial, bool fp16) {
   const int blk = blockIdx.y;
   const int img = blk / cb, c = blk - img * cb;
   const size_t base = (size_t)(img * src_cbt + cb_off + c) * nvox * 8;
@@ -54,10 +26,10 @@ channel_sum_partial_kernel(const __nv_bfloat16* __restrict__ src, int src_cbt, i
   for (int i = 0; i < 8; ++i) s[i] = 0.f;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
     float x[8];
-    ld8_bf16(src + base + v * 8, x);
+    ld8_e(src + base + v * 8, x, fp16);
     if (lo_delta) {
       float l[8];
-      ld8_bf16(src + base + lo_delta + v * 8, l);
+      ld8_e(src + base + lo_delta + v * 8, l, fp16);
 #pragma unroll
       for (int i = 0; i < 8; ++i) x[i] += l[i];
     }
@@ -126,9 +98,9 @@ __global__ void gate_mlp_kernel(const float* __restrict__ pooled, const float* _
 
 // dst[b, c] = sum_m w[b, m] * src[b, m*cb + c]; grid (chunks, n_img*cb)
 __global__ void __launch_bounds__(256)
-modality_combine_kernel(const __nv_bfloat16* __restrict__ src, int src_cbt, int src_lo_off, int M, int cb, size_t nvox,
-                        const float* __restrict__ weights, float uniform_w, __nv_bfloat16* __restrict__ dst,
-                        int dst_cbt, int dst_cb_off, int dst_lo_off) {
+modality_combine_kernel(const uint16_t* __restrict__ src, int src_cbt, int src_lo_off, int M, int cb, size_t nvox,
+                        const float* __restrict__ weights, float uniform_w, uint16_t* __restrict__ dst,
+                        int dst_cbt, int dst_cb_off, int dst_lo_off, bool fp16) {
   const int blk = blockIdx.y;
   const int img = blk / cb, c = blk - img * cb;
   const size_t src_lo = (size_t)src_lo_off * nvox * 8;
@@ -142,24 +114,24 @@ modality_combine_kernel(const __nv_bfloat16* __restrict__ src, int src_cbt, int 
       const float w = weights ? weights[(size_t)img * M + m] : uniform_w;
       const size_t base = (size_t)(img * src_cbt + m * cb + c) * nvox * 8 + v * 8;
       float x[8];
-      ld8_bf16(src + base, x);
+      ld8_e(src + base, x, fp16);
       if (src_lo) {
         float l[8];
-        ld8_bf16(src + base + src_lo, l);
+        ld8_e(src + base + src_lo, l, fp16);
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] += l[i];
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, x[i], acc[i]);
     }
-    st8_act(dst, dst_base + v * 8, dst_lo, acc);
+    store8_act(dst, dst_base + v * 8, dst_lo, acc, fp16);
   }
 }
 
 // dst[b, c] = max_m src[b, m*cb + c]  (LateFusion 'max', src/models/fusion/late_fusion.py:62-64); grid (chunks, n_img*cb)
 __global__ void __launch_bounds__(256)
-modality_max_kernel(const __nv_bfloat16* __restrict__ src, int src_cbt, int M, int cb, size_t nvox,
-                    __nv_bfloat16* __restrict__ dst, int dst_cbt, int dst_cb_off) {
+modality_max_kernel(const uint16_t* __restrict__ src, int src_cbt, int M, int cb, size_t nvox,
+                    uint16_t* __restrict__ dst, int dst_cbt, int dst_cb_off) {
   const int blk = blockIdx.y;
   const int img = blk / cb, c = blk - img * cb;
   const size_t dst_base = (size_t)(img * dst_cbt + dst_cb_off + c) * nvox * 8;
@@ -169,18 +141,18 @@ modality_max_kernel(const __nv_bfloat16* __restrict__ src, int src_cbt, int M, i
     for (int i = 0; i < 8; ++i) acc[i] = -INFINITY;
     for (int m = 0; m < M; ++m) {
       float x[8];
-      ld8_bf16(src + (size_t)(img * src_cbt + m * cb + c) * nvox * 8 + v * 8, x);
+      ld8_e(src + (size_t)(img * src_cbt + m * cb + c) * nvox * 8 + v * 8, x, false);
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], x[i]);
     }
-    st8_act(dst, dst_base + v * 8, 0, acc);
+    store8_act(dst, dst_base + v * 8, 0, acc, false);
   }
 }
 
 // MaxPool3d(2) on a blocked tensor (stand-alone DownBlock3D use); grid (chunks, n_img*cb)
 __global__ void __launch_bounds__(256)
-maxpool2_kernel(const __nv_bfloat16* __restrict__ src, int src_cbt, int src_cb_off, int src_lo_off, int cb, int Z, int Y,
-                int X, __nv_bfloat16* __restrict__ dst, int dst_cbt, int dst_cb_off, int dst_lo_off) {
+maxpool2_kernel(const uint16_t* __restrict__ src, int src_cbt, int src_cb_off, int src_lo_off, int cb, int Z, int Y,
+                int X, uint16_t* __restrict__ dst, int dst_cbt, int dst_cb_off, int dst_lo_off, bool fp16) {
   const int blk = blockIdx.y;
   const int img = blk / cb, c = blk - img * cb;
   const int Zh = Z / 2, Yh = Y / 2, Xh = X / 2;
@@ -200,17 +172,17 @@ maxpool2_kernel(const __nv_bfloat16* __restrict__ src, int src_cbt, int src_cb_o
     for (int d = 0; d < 8; ++d) {
       const size_t v = ((size_t)(2 * zh + (d >> 2)) * Y + (2 * yh + ((d >> 1) & 1))) * X + (2 * xh + (d & 1));
       float x[8];
-      ld8_bf16(src + sbase + v * 8, x);
+      ld8_e(src + sbase + v * 8, x, fp16);
       if (slo) {
         float l[8];
-        ld8_bf16(src + sbase + slo + v * 8, l);
+        ld8_e(src + sbase + slo + v * 8, l, fp16);
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] += l[i];
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], x[i]);
     }
-    st8_act(dst, dbase + cell * 8, dlo, mx);
+    store8_act(dst, dbase + cell * 8, dlo, mx, fp16);
   }
 }
 
@@ -229,10 +201,10 @@ static unsigned gx_for(size_t items, int rows) {
 // The weights sit in shared memory as [cin][COUT] so one LDS.128 feeds 16 FMAs.  fp32 accumulation of exact bf16 (or
 // hi + lo in parity mode) inputs with fp32 weights.
 template <int COUT>
-__global__ void __launch_bounds__(256) conv1x1_logits_kernel(const __nv_bfloat16* __restrict__ src, int src_cbt, int cb_off,
+__global__ void __launch_bounds__(256) conv1x1_logits_kernel(const uint16_t* __restrict__ src, int src_cbt, int cb_off,
                                                             int lo_off, int cin_blocks, size_t nvox,
                                                             const float* __restrict__ weight, const float* __restrict__ bias,
-                                                            int cout, float* __restrict__ dst) {
+                                                            int cout, float* __restrict__ dst, bool fp16) {
   extern __shared__ float wsm[];   // [cin][COUT], zero-padded classes
   const int cin = cin_blocks * 8;
   for (int i = threadIdx.x; i < cin * COUT; i += blockDim.x) {
@@ -252,26 +224,17 @@ __global__ void __launch_bounds__(256) conv1x1_logits_kernel(const __nv_bfloat16
     for (int v = 0; v < 4; ++v) acc[co][v] = b;
   }
   for (int cb = 0; cb < cin_blocks; ++cb) {
-    const __nv_bfloat16* base = src + (((size_t)img * src_cbt + cb_off + cb) * nvox + v0) * 8;
+    const uint16_t* base = src + (((size_t)img * src_cbt + cb_off + cb) * nvox + v0) * 8;
     float x[4][8];
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
       if (full || v0 + v < nvox) {
-        uint4 r = *reinterpret_cast<const uint4*>(base + v * 8);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(h[j]);
-          x[v][2 * j] = f.x; x[v][2 * j + 1] = f.y;
-        }
+        ld8_e(base + v * 8, x[v], fp16);
         if (lo_off > 0) {
-          uint4 rl = *reinterpret_cast<const uint4*>(base + (size_t)lo_off * nvox * 8 + v * 8);
-          const __nv_bfloat162* hl = reinterpret_cast<const __nv_bfloat162*>(&rl);
+          float l[8];
+          ld8_e(base + (size_t)lo_off * nvox * 8 + v * 8, l, fp16);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __bfloat1622float2(hl[j]);
-            x[v][2 * j] += f.x; x[v][2 * j + 1] += f.y;
-          }
+          for (int j = 0; j < 8; ++j) x[v][j] += l[j];
         }
       } else {
 #pragma unroll
@@ -353,33 +316,36 @@ extern "C" int mmseg_trilinear_resize(const float* src, int32_t n_planes, int32_
 
 extern "C" int mmseg_conv1x1_logits(const void* src, int32_t n_img, int32_t src_cbt, int32_t cb_off, int32_t lo_off,
                                     int32_t cin, int64_t voxels, const float* weight, const float* bias, int32_t cout,
-                                    float* dst, void* stream) {
-  if (!src || !weight || !dst || n_img < 1 || voxels < 1) return fail(MMSEG_ERR_INVALID_ARG, "conv1x1_logits: bad arguments");
+                                    float* dst, int32_t fmt, void* stream) {
+  if (!src || !weight || !dst || n_img < 1 || voxels < 1 || (fmt != MMSEG_FMT_BF16 && fmt != MMSEG_FMT_FP16))
+    return fail(MMSEG_ERR_INVALID_ARG, "conv1x1_logits: bad arguments");
   if (cin < 8 || (cin % 8) || cin > 256) return fail(MMSEG_ERR_UNSUPPORTED, "conv1x1_logits: cin=%d (multiple of 8, <= 256)", cin);
   if (cout < 1 || cout > 16) return fail(MMSEG_ERR_UNSUPPORTED, "conv1x1_logits: cout=%d (1..16)", cout);
   if (n_img > 65535) return fail(MMSEG_ERR_INVALID_ARG, "conv1x1_logits: n_img");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t nv = (size_t)voxels;
   dim3 grid((unsigned)((nv + 1023) / 1024), (unsigned)n_img);
-  const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(src);
+  const uint16_t* s = reinterpret_cast<const uint16_t*>(src);
+  const bool fp16 = fmt == MMSEG_FMT_FP16;
   if (cout <= 4)
-    conv1x1_logits_kernel<4><<<grid, 256, (size_t)cin * 4 * sizeof(float), st>>>(s, src_cbt, cb_off, lo_off, cin / 8, nv, weight, bias, cout, dst);
+    conv1x1_logits_kernel<4><<<grid, 256, (size_t)cin * 4 * sizeof(float), st>>>(s, src_cbt, cb_off, lo_off, cin / 8, nv, weight, bias, cout, dst, fp16);
   else if (cout <= 8)
-    conv1x1_logits_kernel<8><<<grid, 256, (size_t)cin * 8 * sizeof(float), st>>>(s, src_cbt, cb_off, lo_off, cin / 8, nv, weight, bias, cout, dst);
+    conv1x1_logits_kernel<8><<<grid, 256, (size_t)cin * 8 * sizeof(float), st>>>(s, src_cbt, cb_off, lo_off, cin / 8, nv, weight, bias, cout, dst, fp16);
   else
-    conv1x1_logits_kernel<16><<<grid, 256, (size_t)cin * 16 * sizeof(float), st>>>(s, src_cbt, cb_off, lo_off, cin / 8, nv, weight, bias, cout, dst);
+    conv1x1_logits_kernel<16><<<grid, 256, (size_t)cin * 16 * sizeof(float), st>>>(s, src_cbt, cb_off, lo_off, cin / 8, nv, weight, bias, cout, dst, fp16);
   return check_launch("conv1x1_logits_kernel");
 }
 
 extern "C" int mmseg_channel_mean(const void* src, int32_t n_img, int32_t src_cbt, int32_t cb_off, int32_t lo_off,
                                   int32_t cb, int64_t voxels, float* partial, int32_t n_chunks, float* mean,
-                                  void* stream) {
-  if (!src || !partial || !mean || n_img < 1 || cb < 1 || voxels < 1 || n_chunks < 1)
+                                  int32_t fmt, void* stream) {
+  if (!src || !partial || !mean || n_img < 1 || cb < 1 || voxels < 1 || n_chunks < 1 ||
+      (fmt != MMSEG_FMT_BF16 && fmt != MMSEG_FMT_FP16))
     return fail(MMSEG_ERR_INVALID_ARG, "channel_mean: bad arguments");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(n_chunks, n_img * cb);
-  channel_sum_partial_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), src_cbt, cb_off,
-                                                   lo_off, cb, (size_t)voxels, partial);
+  channel_sum_partial_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(src), src_cbt, cb_off, lo_off, cb,
+                                                   (size_t)voxels, partial, fmt == MMSEG_FMT_FP16);
   int rc = check_launch("channel_sum_partial_kernel");
   if (rc) return rc;
   const int n = n_img * cb * 8;
@@ -399,14 +365,14 @@ extern "C" int mmseg_gate_mlp(const float* pooled, const float* w1, const float*
 
 extern "C" int mmseg_modality_combine(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_lo_off, int32_t M,
                                       int32_t cb, int64_t voxels, const float* weights, float uniform_weight, void* dst,
-                                      int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, void* stream) {
-  if (!src || !dst || n_img < 1 || M < 1 || cb < 1 || voxels < 1)
+                                      int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, int32_t fmt, void* stream) {
+  if (!src || !dst || n_img < 1 || M < 1 || cb < 1 || voxels < 1 || (fmt != MMSEG_FMT_BF16 && fmt != MMSEG_FMT_FP16))
     return fail(MMSEG_ERR_INVALID_ARG, "modality_combine: bad arguments");
   const int rows = n_img * cb;
   dim3 grid(gx_for((size_t)voxels, rows), rows);
   modality_combine_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(src), src_cbt, src_lo_off, M, cb, (size_t)voxels, weights, uniform_weight,
-      reinterpret_cast<__nv_bfloat16*>(dst), dst_cbt, dst_cb_off, dst_lo_off);
+      reinterpret_cast<const uint16_t*>(src), src_cbt, src_lo_off, M, cb, (size_t)voxels, weights, uniform_weight,
+      reinterpret_cast<uint16_t*>(dst), dst_cbt, dst_cb_off, dst_lo_off, fmt == MMSEG_FMT_FP16);
   return check_launch("modality_combine_kernel");
 }
 
@@ -417,21 +383,21 @@ extern "C" int mmseg_modality_max(const void* src, int32_t n_img, int32_t src_cb
   const int rows = n_img * cb;
   dim3 grid(gx_for((size_t)voxels, rows), rows);
   modality_max_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(src), src_cbt, M, cb, (size_t)voxels,
-      reinterpret_cast<__nv_bfloat16*>(dst), dst_cbt, dst_cb_off);
+      reinterpret_cast<const uint16_t*>(src), src_cbt, M, cb, (size_t)voxels,
+      reinterpret_cast<uint16_t*>(dst), dst_cbt, dst_cb_off);
   return check_launch("modality_max_kernel");
 }
 
 extern "C" int mmseg_maxpool3d_2(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_cb_off,
                                  int32_t src_lo_off, int32_t cb, int32_t Z, int32_t Y, int32_t X, void* dst,
-                                 int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, void* stream) {
-  if (!src || !dst || n_img < 1 || cb < 1 || Z < 2 || Y < 2 || X < 2)
+                                 int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, int32_t fmt, void* stream) {
+  if (!src || !dst || n_img < 1 || cb < 1 || Z < 2 || Y < 2 || X < 2 || (fmt != MMSEG_FMT_BF16 && fmt != MMSEG_FMT_FP16))
     return fail(MMSEG_ERR_INVALID_ARG, "maxpool3d_2: bad arguments");
   const size_t ncell = (size_t)(Z / 2) * (Y / 2) * (X / 2);
   const int rows = n_img * cb;
   dim3 grid(gx_for(ncell, rows), rows);
   maxpool2_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(src), src_cbt, src_cb_off, src_lo_off, cb, Z, Y, X,
-      reinterpret_cast<__nv_bfloat16*>(dst), dst_cbt, dst_cb_off, dst_lo_off);
+      reinterpret_cast<const uint16_t*>(src), src_cbt, src_cb_off, src_lo_off, cb, Z, Y, X,
+      reinterpret_cast<uint16_t*>(dst), dst_cbt, dst_cb_off, dst_lo_off, fmt == MMSEG_FMT_FP16);
   return check_launch("maxpool2_kernel");
 }

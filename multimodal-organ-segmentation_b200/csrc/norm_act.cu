@@ -91,8 +91,8 @@ struct NormK {   // kept at exactly 128 bytes: one more field and the default ap
   const float* mr;
   const float* stats;   // optional: per-tile (sum, sum of squares) partials [n_img][tiles][C][2] -> finalized in the prologue
   float* mr_out;        // optional: where block x == 0 of each row publishes the (mean, rstd) it derived
-  __nv_bfloat16* dst;
-  __nv_bfloat16* pooled;
+  void* dst;
+  void* pooled;
   const float* shift;   // optional [n_img][C]: y = (x - mean) * rstd + shift (affine norms: GroupNorm / BatchNorm beta)
   double inv_n;
   int tiles;
@@ -105,45 +105,14 @@ struct NormK {   // kept at exactly 128 bytes: one more field and the default ap
 };
 static_assert(sizeof(NormK) <= 128, "NormK must stay within 128 bytes (register allocation of the apply kernels)");
 
-template <bool F32>
+template <bool F32, bool FP16>
 __device__ __forceinline__ void load8(const void* base, size_t elem_off, float* v) {
   if (F32) {
     const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off);
     const float4 a = p[0], b = p[1];
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   } else {
-    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __bfloat1622float2(h[i]);
-      v[2 * i] = f.x;
-      v[2 * i + 1] = f.y;
-    }
-  }
-}
-
-__device__ __forceinline__ uint4 pack8(const float* v) {
-  uint4 r;
-  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
-  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
-  r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
-  r.z = *reinterpret_cast<uint32_t*>(&c); r.w = *reinterpret_cast<uint32_t*>(&d);
-  return r;
-}
-
-__device__ __forceinline__ void store_act8(__nv_bfloat16* dst, size_t off, size_t lo_delta, const float* y) {
-  if (lo_delta == 0) {
-    *reinterpret_cast<uint4*>(dst + off) = pack8(y);
-  } else {
-    float h[8], l[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      h[i] = __bfloat162float(__float2bfloat16_rn(y[i]));
-      l[i] = y[i] - h[i];
-    }
-    *reinterpret_cast<uint4*>(dst + off) = pack8(h);
-    *reinterpret_cast<uint4*>(dst + off + lo_delta) = pack8(l);
+    load8_act(base, elem_off, v, FP16);
   }
 }
 
@@ -211,7 +180,7 @@ __device__ __forceinline__ void block_shift(const NormK& k, int img, int c, floa
 // grid: (chunks over voxels, n_img*cb).  One 8-channel vector per thread-iteration.
 // EXT = additive shift and / or GELU (the affine norms / gelu option): kept out of the default instantiation, whose
 // register count decides how many loads are in flight (80 -> 93 registers cost a resident block per SM)
-template <bool F32, bool EXT>
+template <bool F32, bool EXT, bool FP16>
 __global__ void __launch_bounds__(256) instnorm_apply_kernel(const NormK k) {
   const int blk = blockIdx.y;  // img*cb + c
   const int img = blk / k.cb, c = blk - img * k.cb;
@@ -229,7 +198,7 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const NormK k) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const size_t v = v0 + u * stride;
-      if (v < nvox) load8<F32>(k.src, src_base + v * 8, x[u]);
+      if (v < nvox) load8<F32, FP16>(k.src, src_base + v * 8, x[u]);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -244,14 +213,14 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const NormK k) {
             x[u][i] = y > 0.f ? y : y * k.slope;
           }
         }
-        store_act8(k.dst, dst_base + v * 8, lo_delta, x[u]);
+        store8_act(k.dst, dst_base + v * 8, lo_delta, x[u], FP16);
       }
     }
   }
 }
 
 // Variant that also emits MaxPool3d(2): one 2x2x2 cell per thread-iteration (Z, Y, X even).
-template <bool F32, bool EXT>
+template <bool F32, bool EXT, bool FP16>
 __global__ void __launch_bounds__(256) instnorm_apply_pool_kernel(const NormK k) {
   const int blk = blockIdx.y;
   const int img = blk / k.cb, c = blk - img * k.cb;
@@ -283,7 +252,7 @@ __global__ void __launch_bounds__(256) instnorm_apply_pool_kernel(const NormK k)
         for (int dx = 0; dx < 2; ++dx) {
           const size_t v = ((size_t)(2 * zh + dz) * k.Y + (2 * yh + dy)) * k.X + (2 * xh + dx);
           float x[8];
-          load8<F32>(k.src, src_base + v * 8, x);
+          load8<F32, FP16>(k.src, src_base + v * 8, x);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if constexpr (EXT) {
@@ -294,16 +263,16 @@ __global__ void __launch_bounds__(256) instnorm_apply_pool_kernel(const NormK k)
             }
             mx[i] = fmaxf(mx[i], x[i]);
           }
-          store_act8(k.dst, dst_base + v * 8, lo_delta, x);
+          store8_act(k.dst, dst_base + v * 8, lo_delta, x, FP16);
         }
-    store_act8(k.pooled, pool_base + cell * 8, pool_lo, mx);
+    store8_act(k.pooled, pool_base + cell * 8, pool_lo, mx, FP16);
   }
 }
 
 // ---------------------------------------------------------------------------------------------- layout converters
 __global__ void __launch_bounds__(256)
-pack_ncdhw_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n_img, int C, size_t nvox,
-                  int dst_cbt, int dst_cb_off, int dst_lo_off, int cb) {
+pack_ncdhw_kernel(const float* __restrict__ src, void* __restrict__ dst, int n_img, int C, size_t nvox,
+                  int dst_cbt, int dst_cb_off, int dst_lo_off, int cb, int fp16) {
   const int blk = blockIdx.y;  // img*cb + c
   const int img = blk / cb, c = blk - img * cb;
   const size_t dst_base = (size_t)(img * dst_cbt + dst_cb_off + c) * nvox * 8;
@@ -315,7 +284,7 @@ pack_ncdhw_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst
       const int ch = c * 8 + i;
       x[i] = ch < C ? src[((size_t)img * C + ch) * nvox + v] : 0.f;
     }
-    store_act8(dst, dst_base + v * 8, lo_delta, x);
+    store8_act(dst, dst_base + v * 8, lo_delta, x, fp16 != 0);
   }
 }
 
@@ -323,9 +292,9 @@ pack_ncdhw_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst
 //   pre:  x <- sigmoid((x - pre_sub) * pre_mul)          (the soft SUV mask of the 1-channel PET image), and / or
 //   gate: x <- x * (1 + sigmoid(gate[img][voxel]))        (CT features modulated by the spatial attention LOGITS)
 __global__ void __launch_bounds__(256)
-pack_ncdhw_ex_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n_img, int C, size_t nvox,
+pack_ncdhw_ex_kernel(const float* __restrict__ src, void* __restrict__ dst, int n_img, int C, size_t nvox,
                      int dst_cbt, int dst_cb_off, int dst_lo_off, int cb, int pre, float pre_sub, float pre_mul,
-                     const float* __restrict__ gate) {
+                     const float* __restrict__ gate, int fp16) {
   const int blk = blockIdx.y;  // img*cb + c
   const int img = blk / cb, c = blk - img * cb;
   const size_t dst_base = (size_t)(img * dst_cbt + dst_cb_off + c) * nvox * 8;
@@ -341,13 +310,13 @@ pack_ncdhw_ex_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ 
       if (pre && ch < C) t = 1.f / (1.f + expf(-(t - pre_sub) * pre_mul));
       x[i] = t * g;
     }
-    store_act8(dst, dst_base + v * 8, lo_delta, x);
+    store8_act(dst, dst_base + v * 8, lo_delta, x, fp16 != 0);
   }
 }
 
 __global__ void __launch_bounds__(256)
-unpack_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int n_img, int C, size_t nvox,
-                    int src_cbt, int src_cb_off, int src_lo_off) {
+unpack_ncdhw_kernel(const void* __restrict__ src, float* __restrict__ dst, int n_img, int C, size_t nvox,
+                    int src_cbt, int src_cb_off, int src_lo_off, int fp16) {
   const int cbn = (C + 7) / 8;
   const int blk = blockIdx.y;
   const int img = blk / cbn, c = blk - img * cbn;
@@ -355,10 +324,10 @@ unpack_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ d
   const size_t lo_delta = (size_t)src_lo_off * nvox * 8;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
     float x[8];
-    load8<false>(src, src_base + v * 8, x);
+    load8_act(src, src_base + v * 8, x, fp16 != 0);
     if (lo_delta) {
       float l[8];
-      load8<false>(src, src_base + lo_delta + v * 8, l);
+      load8_act(src, src_base + lo_delta + v * 8, l, fp16 != 0);
 #pragma unroll
       for (int i = 0; i < 8; ++i) x[i] += l[i];
     }
@@ -417,74 +386,82 @@ extern "C" int mmseg_instnorm_act_apply(const mmseg_norm_args* a, void* stream) 
   k.stats = a->stats_partial; k.mr_out = a->stats_partial ? a->mean_rstd_out : nullptr;
   k.tiles = a->tiles_per_img; k.eps = a->eps;
   k.inv_n = 1.0 / ((double)a->Z * a->Y * a->X);
-  k.dst = reinterpret_cast<__nv_bfloat16*>(a->dst);
-  k.pooled = reinterpret_cast<__nv_bfloat16*>(a->pooled);
+  k.dst = a->dst;
+  k.pooled = a->pooled;
   k.n_img = a->n_img; k.cb = a->cb; k.Z = a->Z; k.Y = a->Y; k.X = a->X;
   k.dst_cbt = a->dst_cbt; k.dst_cb_off = a->dst_cb_off; k.dst_lo_off = a->dst_lo_off;
   k.pool_cbt = a->pool_cbt; k.pool_cb_off = a->pool_cb_off; k.pool_lo_off = a->pool_lo_off;
   k.slope = a->slope;
   k.act = a->act;
   if (k.act != 0 && k.act != 1) return fail(MMSEG_ERR_INVALID_ARG, "instnorm_apply: act=%d (0 relu/leaky_relu, 1 gelu)", k.act);
+  if (a->elem_fmt != MMSEG_FMT_BF16 && a->elem_fmt != MMSEG_FMT_FP16)
+    return fail(MMSEG_ERR_INVALID_ARG, "instnorm_apply: elem_fmt=%d", a->elem_fmt);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int rows = a->n_img * a->cb;
   const bool ext = k.shift != nullptr || k.act != 0;
+  const bool f32 = a->src_is_f32 != 0, fp16 = a->elem_fmt == MMSEG_FMT_FP16;
+  // instantiation index: (raw fp32, affine shift / gelu, fp16 elements)
+  const int inst = (f32 ? 4 : 0) | (ext ? 2 : 0) | (fp16 ? 1 : 0);
+  typedef void (*ApplyFn)(const NormK);
   if (a->pooled) {
     if ((a->Z | a->Y | a->X) & 1) return fail(MMSEG_ERR_UNSUPPORTED, "instnorm_apply: fused MaxPool3d(2) needs even extents");
+    static const ApplyFn pool_fns[8] = {
+        instnorm_apply_pool_kernel<false, false, false>, instnorm_apply_pool_kernel<false, false, true>,
+        instnorm_apply_pool_kernel<false, true, false>,  instnorm_apply_pool_kernel<false, true, true>,
+        instnorm_apply_pool_kernel<true, false, false>,  instnorm_apply_pool_kernel<true, false, true>,
+        instnorm_apply_pool_kernel<true, true, false>,   instnorm_apply_pool_kernel<true, true, true>};
     const size_t ncell = (size_t)(a->Z / 2) * (a->Y / 2) * (a->X / 2);
     dim3 grid(grid_x_for(ncell, rows), rows);
-    if (ext) {
-      if (a->src_is_f32) instnorm_apply_pool_kernel<true, true><<<grid, 256, 0, st>>>(k);
-      else instnorm_apply_pool_kernel<false, true><<<grid, 256, 0, st>>>(k);
-    } else {
-      if (a->src_is_f32) instnorm_apply_pool_kernel<true, false><<<grid, 256, 0, st>>>(k);
-      else instnorm_apply_pool_kernel<false, false><<<grid, 256, 0, st>>>(k);
-    }
+    pool_fns[inst]<<<grid, 256, 0, st>>>(k);
   } else {
+    static const ApplyFn fns[8] = {
+        instnorm_apply_kernel<false, false, false>, instnorm_apply_kernel<false, false, true>,
+        instnorm_apply_kernel<false, true, false>,  instnorm_apply_kernel<false, true, true>,
+        instnorm_apply_kernel<true, false, false>,  instnorm_apply_kernel<true, false, true>,
+        instnorm_apply_kernel<true, true, false>,   instnorm_apply_kernel<true, true, true>};
     const size_t nvox = (size_t)a->Z * a->Y * a->X;
     dim3 grid(grid_x_for(nvox, rows), rows);
-    if (ext) {
-      if (a->src_is_f32) instnorm_apply_kernel<true, true><<<grid, 256, 0, st>>>(k);
-      else instnorm_apply_kernel<false, true><<<grid, 256, 0, st>>>(k);
-    } else {
-      if (a->src_is_f32) instnorm_apply_kernel<true, false><<<grid, 256, 0, st>>>(k);
-      else instnorm_apply_kernel<false, false><<<grid, 256, 0, st>>>(k);
-    }
+    fns[inst]<<<grid, 256, 0, st>>>(k);
   }
   return check_launch("instnorm_apply_kernel");
 }
 
 extern "C" int mmseg_pack_ncdhw(const float* src, void* dst, int32_t n_img, int32_t C, int32_t Z, int32_t Y,
                                 int32_t X, int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, int32_t cb,
-                                void* stream) {
-  if (!src || !dst || n_img < 1 || C < 1 || cb * 8 < C) return fail(MMSEG_ERR_INVALID_ARG, "pack_ncdhw: bad arguments");
+                                int32_t fmt, void* stream) {
+  if (!src || !dst || n_img < 1 || C < 1 || cb * 8 < C || (fmt != MMSEG_FMT_BF16 && fmt != MMSEG_FMT_FP16))
+    return fail(MMSEG_ERR_INVALID_ARG, "pack_ncdhw: bad arguments");
   const size_t nvox = (size_t)Z * Y * X;
   const int rows = n_img * cb;
   dim3 grid(grid_x_for(nvox, rows), rows);
   pack_ncdhw_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      src, reinterpret_cast<__nv_bfloat16*>(dst), n_img, C, nvox, dst_cbt, dst_cb_off, dst_lo_off, cb);
+      src, dst, n_img, C, nvox, dst_cbt, dst_cb_off, dst_lo_off, cb, fmt);
   return check_launch("pack_ncdhw_kernel");
 }
 
 extern "C" int mmseg_pack_ncdhw_ex(const float* src, void* dst, int32_t n_img, int32_t C, int32_t Z, int32_t Y, int32_t X,
                                    int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, int32_t cb, int32_t pre_sigmoid,
-                                   float pre_sub, float pre_mul, const float* gate_logits, void* stream) {
-  if (!src || !dst || n_img < 1 || C < 1 || cb * 8 < C) return fail(MMSEG_ERR_INVALID_ARG, "pack_ncdhw_ex: bad arguments");
+                                   float pre_sub, float pre_mul, const float* gate_logits, int32_t fmt, void* stream) {
+  if (!src || !dst || n_img < 1 || C < 1 || cb * 8 < C || (fmt != MMSEG_FMT_BF16 && fmt != MMSEG_FMT_FP16))
+    return fail(MMSEG_ERR_INVALID_ARG, "pack_ncdhw_ex: bad arguments");
   const size_t nvox = (size_t)Z * Y * X;
   const int rows = n_img * cb;
   dim3 grid(grid_x_for(nvox, rows), rows);
   pack_ncdhw_ex_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      src, reinterpret_cast<__nv_bfloat16*>(dst), n_img, C, nvox, dst_cbt, dst_cb_off, dst_lo_off, cb, pre_sigmoid ? 1 : 0,
-      pre_sub, pre_mul, gate_logits);
+      src, dst, n_img, C, nvox, dst_cbt, dst_cb_off, dst_lo_off, cb, pre_sigmoid ? 1 : 0, pre_sub, pre_mul, gate_logits,
+      fmt);
   return check_launch("pack_ncdhw_ex_kernel");
 }
 
 extern "C" int mmseg_unpack_ncdhw(const void* src, float* dst, int32_t n_img, int32_t C, int32_t Z, int32_t Y,
-                                  int32_t X, int32_t src_cbt, int32_t src_cb_off, int32_t src_lo_off, void* stream) {
-  if (!src || !dst || n_img < 1 || C < 1) return fail(MMSEG_ERR_INVALID_ARG, "unpack_ncdhw: bad arguments");
+                                  int32_t X, int32_t src_cbt, int32_t src_cb_off, int32_t src_lo_off, int32_t fmt,
+                                  void* stream) {
+  if (!src || !dst || n_img < 1 || C < 1 || (fmt != MMSEG_FMT_BF16 && fmt != MMSEG_FMT_FP16))
+    return fail(MMSEG_ERR_INVALID_ARG, "unpack_ncdhw: bad arguments");
   const size_t nvox = (size_t)Z * Y * X;
   const int rows = n_img * ((C + 7) / 8);
   dim3 grid(grid_x_for(nvox, rows), rows);
   unpack_ncdhw_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(src), dst, n_img, C, nvox, src_cbt, src_cb_off, src_lo_off);
+      src, dst, n_img, C, nvox, src_cbt, src_cb_off, src_lo_off, fmt);
   return check_launch("unpack_ncdhw_kernel");
 }

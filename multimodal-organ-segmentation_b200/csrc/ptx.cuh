@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace mmseg {
@@ -137,6 +138,78 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 // Instruction descriptor: kind::f16, A=B=bf16, D=f32, both operands K-major, M=128, N=n.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+// Same with the 16-bit operand format chosen at run time: a/b format field 1 = bf16, 0 = fp16 (MMSEG_FMT_*).
+__host__ __device__ constexpr uint32_t make_idesc_16(uint32_t m, uint32_t n, bool fp16) {
+  return (1u << 4) | (fp16 ? 0u : ((1u << 7) | (1u << 10))) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- 16-bit element format of the blocked layout
+// Eight channels of one voxel = one 16-byte vector; the element type is bf16 (MMSEG_FMT_BF16) or fp16 (MMSEG_FMT_FP16).
+// `fp16` is warp-uniform everywhere, so the branch costs one uniform predicate.
+__device__ __forceinline__ void cvt8_to_f32(const uint4& u, float* v, bool fp16) {
+  if (fp16) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  } else {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ uint4 cvt8_from_f32(const float* v, bool fp16) {
+  uint4 r;
+  uint32_t* o = reinterpret_cast<uint32_t*>(&r);
+  if (fp16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      o[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      o[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+  }
+  return r;
+}
+// v ~= hi + lo, both in the element format (the split numeric modes)
+__device__ __forceinline__ void split8_from_f32(const float* v, uint4& hi, uint4& lo, bool fp16) {
+  float h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = fp16 ? __half2float(__float2half_rn(v[i])) : __bfloat162float(__float2bfloat16_rn(v[i]));
+    l[i] = v[i] - h[i];
+  }
+  hi = cvt8_from_f32(h, fp16);
+  lo = cvt8_from_f32(l, fp16);
+}
+// store 8 activations as hi (and lo when lo_delta != 0); dst is addressed in 2-byte elements
+__device__ __forceinline__ void store8_act(void* dst, size_t off, size_t lo_delta, const float* y, bool fp16) {
+  uint16_t* d = reinterpret_cast<uint16_t*>(dst);
+  if (lo_delta == 0) {
+    *reinterpret_cast<uint4*>(d + off) = cvt8_from_f32(y, fp16);
+  } else {
+    uint4 hi, lo;
+    split8_from_f32(y, hi, lo, fp16);
+    *reinterpret_cast<uint4*>(d + off) = hi;
+    *reinterpret_cast<uint4*>(d + off + lo_delta) = lo;
+  }
+}
+__device__ __forceinline__ void load8_act(const void* src, size_t off, float* v, bool fp16) {
+  const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(src) + off);
+  cvt8_to_f32(u, v, fp16);
 }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {

@@ -8,19 +8,10 @@ namespace mmseg {
 
 int num_sms();
 
-__device__ __forceinline__ uint4 pack8s(const float* v) {
-  uint4 r;
-  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
-  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
-  r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
-  r.z = *reinterpret_cast<uint32_t*>(&c); r.w = *reinterpret_cast<uint32_t*>(&d);
-  return r;
-}
-
 // grid: (x-chunks, RZ*RY rows, n_win*cb)
 __global__ void __launch_bounds__(128)
 swi_gather_kernel(const float* __restrict__ vol, int C, int VZ, int VY, int VX, const int* __restrict__ starts,
-                  int RZ, int RY, int RX, __nv_bfloat16* __restrict__ dst, int dst_cbt, int dst_lo_off, int cb) {
+                  int RZ, int RY, int RX, void* __restrict__ dst, int dst_cbt, int dst_lo_off, int cb, int fp16) {
   const int wc = blockIdx.z;
   const int win = wc / cb, c = wc - win * cb;
   const int row = blockIdx.y;
@@ -42,18 +33,7 @@ swi_gather_kernel(const float* __restrict__ vol, int C, int VZ, int VY, int VX, 
                  ? vol[(size_t)ch * nvox_v + ((size_t)gz * VY + gy) * VX + gx]
                  : 0.f;
     }
-    if (lo_delta == 0) {
-      *reinterpret_cast<uint4*>(dst + dst_base + (size_t)lx * 8) = pack8s(v);
-    } else {
-      float h[8], l[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        h[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
-        l[i] = v[i] - h[i];
-      }
-      *reinterpret_cast<uint4*>(dst + dst_base + (size_t)lx * 8) = pack8s(h);
-      *reinterpret_cast<uint4*>(dst + dst_base + lo_delta + (size_t)lx * 8) = pack8s(l);
-    }
+    store8_act(dst, dst_base + (size_t)lx * 8, lo_delta, v, fp16 != 0);
   }
 }
 
@@ -162,11 +142,11 @@ swi_blend_window_kernel(const float* __restrict__ logits, const int* __restrict_
 // window row (float4 accumulator accesses); needs RX, VX and every window's x origin to be multiples of 4.
 template <int KP>   // classes padded to a multiple of 4 (<= 8)
 __global__ void __launch_bounds__(128)
-swi_logits_blend_kernel(const __nv_bfloat16* __restrict__ feat, int src_cbt, int cb_off, int lo_off, int cin_blocks, int win,
+swi_logits_blend_kernel(const uint16_t* __restrict__ feat, int src_cbt, int cb_off, int lo_off, int cin_blocks, int win,
                         const float* __restrict__ weight, const float* __restrict__ bias, int K,
                         const int* __restrict__ starts, int RZ, int RY, int RX, const float* __restrict__ wz,
                         const float* __restrict__ wy, const float* __restrict__ wx, float w_floor, float* __restrict__ out,
-                        float* __restrict__ count, int VZ, int VY, int VX) {
+                        float* __restrict__ count, int VZ, int VY, int VX, int fp16) {
   extern __shared__ float wsm[];   // [cin][KP], zero-padded classes
   const int cin = cin_blocks * 8;
   for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < cin * KP; i += blockDim.x * blockDim.y) {
@@ -194,25 +174,16 @@ swi_logits_blend_kernel(const __nv_bfloat16* __restrict__ feat, int src_cbt, int
       for (int v = 0; v < 4; ++v) acc[co][v] = b;
     }
     for (int cb = 0; cb < cin_blocks; ++cb) {
-      const __nv_bfloat16* base = feat + (((size_t)win * src_cbt + cb_off + cb) * nvox_r + row_r + lx) * 8;
+      const uint16_t* base = feat + (((size_t)win * src_cbt + cb_off + cb) * nvox_r + row_r + lx) * 8;
       float x[4][8];
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        const uint4 r = *reinterpret_cast<const uint4*>(base + v * 8);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(h[j]);
-          x[v][2 * j] = f.x; x[v][2 * j + 1] = f.y;
-        }
+        cvt8_to_f32(*reinterpret_cast<const uint4*>(base + v * 8), x[v], fp16 != 0);
         if (lo_off > 0) {
-          const uint4 rl = *reinterpret_cast<const uint4*>(base + (size_t)lo_off * nvox_r * 8 + v * 8);
-          const __nv_bfloat162* hl = reinterpret_cast<const __nv_bfloat162*>(&rl);
+          float l[8];
+          cvt8_to_f32(*reinterpret_cast<const uint4*>(base + (size_t)lo_off * nvox_r * 8 + v * 8), l, fp16 != 0);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __bfloat1622float2(hl[j]);
-            x[v][2 * j] += f.x; x[v][2 * j + 1] += f.y;
-          }
+          for (int j = 0; j < 8; ++j) x[v][j] += l[j];
         }
       }
 #pragma unroll
@@ -257,19 +228,43 @@ swi_logits_blend_kernel(const __nv_bfloat16* __restrict__ feat, int src_cbt, int
   }
 }
 
+// `out` addresses the first voxel of the range in class plane 0; plane c starts `plane` elements further (a z-slab of the
+// [K][VZ][VY][VX] accumulator is finalized in place: nvox = slab voxels, plane = VZ*VY*VX).
 __global__ void __launch_bounds__(256)
-swi_finalize_kernel(float* __restrict__ out, const float* __restrict__ count, int K, size_t nvox, int normalize,
-                    uint8_t* __restrict__ labels) {
+swi_finalize_kernel(float* __restrict__ out, const float* __restrict__ count, int K, size_t nvox, size_t plane,
+                    int normalize, uint8_t* __restrict__ labels) {
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
     const float cnt = count[v];
     float best = -INFINITY;
     int arg = 0;
     for (int c = 0; c < K; ++c) {
-      const float q = __fdiv_rn(out[(size_t)c * nvox + v], cnt);
-      if (normalize) out[(size_t)c * nvox + v] = q;
+      const float q = __fdiv_rn(out[(size_t)c * plane + v], cnt);
+      if (normalize) out[(size_t)c * plane + v] = q;
       if (q > best) { best = q; arg = c; }
     }
     if (labels) labels[v] = (uint8_t)arg;
+  }
+}
+
+// acc[p][i] += part[p][i] for p < planes, i < n (plane strides in elements): the owner's rank-ordered add of another
+// rank's partial sums in the sharded exchange.  float4 when both ranges are 16-byte aligned.
+__global__ void __launch_bounds__(256)
+swi_add_partial_kernel(float* __restrict__ acc, size_t acc_plane, const float* __restrict__ part, size_t part_plane,
+                       size_t n, int vec) {
+  float* a = acc + (size_t)blockIdx.y * acc_plane;
+  const float* b = part + (size_t)blockIdx.y * part_plane;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (vec) {
+    const size_t n4 = n >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      float4 x = reinterpret_cast<float4*>(a)[i];
+      const float4 y = reinterpret_cast<const float4*>(b)[i];
+      x.x = __fadd_rn(x.x, y.x); x.y = __fadd_rn(x.y, y.y); x.z = __fadd_rn(x.z, y.z); x.w = __fadd_rn(x.w, y.w);
+      reinterpret_cast<float4*>(a)[i] = x;
+    }
+    for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] = __fadd_rn(a[i], b[i]);
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] = __fadd_rn(a[i], b[i]);
   }
 }
 
@@ -279,12 +274,13 @@ using namespace mmseg;
 
 extern "C" int mmseg_swi_gather(const float* volume, int32_t C, int32_t VZ, int32_t VY, int32_t VX,
                                 const int32_t* starts_dev, int32_t n_win, int32_t RZ, int32_t RY, int32_t RX,
-                                void* dst, int32_t dst_cbt, int32_t dst_lo_off, int32_t cb, void* stream) {
-  if (!volume || !starts_dev || !dst || n_win < 1 || C < 1 || cb * 8 < C || RZ * RY > 65535 || n_win * cb > 65535)
+                                void* dst, int32_t dst_cbt, int32_t dst_lo_off, int32_t cb, int32_t fmt, void* stream) {
+  if (!volume || !starts_dev || !dst || n_win < 1 || C < 1 || cb * 8 < C || RZ * RY > 65535 || n_win * cb > 65535 ||
+      (fmt != MMSEG_FMT_BF16 && fmt != MMSEG_FMT_FP16))
     return fail(MMSEG_ERR_INVALID_ARG, "swi_gather: bad arguments");
   dim3 grid((RX + 127) / 128, RZ * RY, n_win * cb);
   swi_gather_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      volume, C, VZ, VY, VX, starts_dev, RZ, RY, RX, reinterpret_cast<__nv_bfloat16*>(dst), dst_cbt, dst_lo_off, cb);
+      volume, C, VZ, VY, VX, starts_dev, RZ, RY, RX, dst, dst_cbt, dst_lo_off, cb, fmt);
   return check_launch("swi_gather_kernel");
 }
 
@@ -323,7 +319,8 @@ extern "C" int mmseg_swi_logits_blend(const void* feat, int32_t src_cbt, int32_t
                                       int32_t window, const float* weight, const float* bias, int32_t K,
                                       const int32_t* starts_dev, int32_t RZ, int32_t RY, int32_t RX, const float* wz,
                                       const float* wy, const float* wx, float w_floor, float* out, float* count,
-                                      int32_t VZ, int32_t VY, int32_t VX, void* stream) {
+                                      int32_t VZ, int32_t VY, int32_t VX, int32_t fmt, void* stream) {
+  if (fmt != MMSEG_FMT_BF16 && fmt != MMSEG_FMT_FP16) return fail(MMSEG_ERR_INVALID_ARG, "swi_logits_blend: fmt");
   if (!feat || !weight || !starts_dev || !wz || !wy || !wx || !out || !count || window < 0)
     return fail(MMSEG_ERR_INVALID_ARG, "swi_logits_blend: bad arguments");
   if (K < 1 || K > 8 || cin < 8 || (cin % 8) || cin > 128)
@@ -333,26 +330,43 @@ extern "C" int mmseg_swi_logits_blend(const void* feat, int32_t src_cbt, int32_t
   const int bx = RX / 4;
   const int by = bx >= 128 ? 1 : 128 / bx;
   dim3 block(bx, by), grid(1, (RZ * RY + by - 1) / by);
-  const __nv_bfloat16* f = reinterpret_cast<const __nv_bfloat16*>(feat);
+  const uint16_t* f = reinterpret_cast<const uint16_t*>(feat);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (K <= 4)
     swi_logits_blend_kernel<4><<<grid, block, (size_t)cin * 4 * sizeof(float), st>>>(
         f, src_cbt, cb_off, lo_off, cin / 8, window, weight, bias, K, starts_dev, RZ, RY, RX, wz, wy, wx, w_floor, out, count,
-        VZ, VY, VX);
+        VZ, VY, VX, fmt);
   else
     swi_logits_blend_kernel<8><<<grid, block, (size_t)cin * 8 * sizeof(float), st>>>(
         f, src_cbt, cb_off, lo_off, cin / 8, window, weight, bias, K, starts_dev, RZ, RY, RX, wz, wy, wx, w_floor, out, count,
-        VZ, VY, VX);
+        VZ, VY, VX, fmt);
   return check_launch("swi_logits_blend_kernel");
 }
 
-extern "C" int mmseg_swi_finalize(float* out, const float* count, int32_t K, int64_t voxels,
+extern "C" int mmseg_swi_finalize(float* out, const float* count, int32_t K, int64_t voxels, int64_t plane_stride,
                                   int32_t normalize_in_place, uint8_t* labels, void* stream) {
-  if (!out || !count || K < 1 || voxels < 1) return fail(MMSEG_ERR_INVALID_ARG, "swi_finalize: bad arguments");
+  if (!out || !count || K < 1 || voxels < 1 || plane_stride < voxels)
+    return fail(MMSEG_ERR_INVALID_ARG, "swi_finalize: bad arguments");
   int64_t blocks = (voxels + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   swi_finalize_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      out, count, K, (size_t)voxels, normalize_in_place, labels);
+      out, count, K, (size_t)voxels, (size_t)plane_stride, normalize_in_place, labels);
   return check_launch("swi_finalize_kernel");
+}
+
+extern "C" int mmseg_swi_add_partial(float* acc, int64_t acc_plane_stride, const float* part, int64_t part_plane_stride,
+                                     int32_t planes, int64_t n, void* stream) {
+  if (!acc || !part || planes < 1 || planes > 65535 || n < 1 || acc_plane_stride < n || part_plane_stride < n)
+    return fail(MMSEG_ERR_INVALID_ARG, "swi_add_partial: bad arguments");
+  const int vec = ((reinterpret_cast<uintptr_t>(acc) | reinterpret_cast<uintptr_t>(part)) & 15) == 0 &&
+                  (acc_plane_stride & 3) == 0 && (part_plane_stride & 3) == 0;
+  int64_t blocks = ((vec ? n / 4 : n) + 255) / 256;
+  const int64_t cap = ((int64_t)num_sms() * 16 + planes - 1) / planes;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  dim3 grid((unsigned)blocks, (unsigned)planes);
+  swi_add_partial_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      acc, (size_t)acc_plane_stride, part, (size_t)part_plane_stride, (size_t)n, vec);
+  return check_launch("swi_add_partial_kernel");
 }

@@ -4,8 +4,9 @@ An engine owns (a) kernel-layout copies of the module's weights (derived caches,
 and (b) the activation workspaces for one (n_img, Z, Y, X) problem size.  It issues only C-ABI kernel launches on
 the current stream, so a whole forward can be captured in a CUDA graph.
 
-Numeric modes
+Numeric modes (numerics.py — the parity ladder bf16 / fp16 / fp16w2 / fp16a2 / parity = bf16x3 / fp16x3)
   * "bf16"   — bf16 operands, fp32 accumulate (north_star's throughput mode); raw conv outputs stored bf16.
+  * "fp16"   — the same single pass with fp16 operands and storage (11-bit significand, same MMA rate).
   * "parity" — 3-pass split-bf16 (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, fp32 accumulate), activations stored as
                bf16 hi+lo pairs and raw conv outputs as fp32: ~2^-16 relative operand error, which is what the
                stated logit/label tolerances need.
@@ -17,6 +18,7 @@ import torch
 from . import _lib
 from . import kernels as K
 from .kernels import Blocked, PackedConv
+from .numerics import mode as numeric_mode
 
 Tensor = torch.Tensor
 
@@ -57,8 +59,10 @@ def norm_kind(norm) -> str:
 class ConvRunner:
     """conv (+ InstanceNorm statistics) -> finalize -> normalise/activate(/pool), on blocked buffers."""
 
-    def __init__(self, split: bool, device):
-        self.split = split
+    def __init__(self, split, device):
+        """split: NumericMode / mode name, or the legacy bool (False = bf16, True = parity)."""
+        self.nm = numeric_mode(split)
+        self.split = self.nm      # what Blocked / pack_conv_weight / a_chunk_table take
         self.device = device
         self.ws = _Workspace(device)
         self.launches = 0
@@ -72,11 +76,11 @@ class ConvRunner:
         from the conv epilogue; nn.GroupNorm: group statistics from the same partials + affine; nn.BatchNorm3d in eval
         mode: running statistics + affine (no statistics pass at all); nn.Identity: conv + bias + activation.  For the
         last three `pw` must carry the conv bias (it is only cancelled by InstanceNorm)."""
-        a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], self.split)
+        a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], pw.nm or self.split)
         n, Z, Y, X = src.n_img, src.Z, src.Y, src.X
         cout = pw.n_out
-        raw_f32 = self.split
-        raw = self.ws.get("raw", n * cout * Z * Y * X, torch.float32 if raw_f32 else torch.bfloat16)
+        raw_f32 = self.nm.raw_f32
+        raw = self.ws.get("raw", n * cout * Z * Y * X, torch.float32 if raw_f32 else self.nm.dtype)
         tile = K.plan_conv_norm((X, Y, Z), n, pw, raw_f32, a_cb)
         kind = norm_kind(norm)
         out_mode = _lib.OUT_BLOCKED_F32 if raw_f32 else _lib.OUT_BLOCKED_BF16
@@ -137,15 +141,15 @@ class ConvRunner:
         return mr, shift
 
     def conv_transpose(self, src: Blocked, segs, pw: PackedConv, dst: Blocked, dst_c0: int = 0) -> None:
-        a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], self.split)
+        a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], pw.nm or self.split)
         K.conv3d(src, pw, a_cb, dst.t, _lib.OUT_CONVT_K2S2, dst_cbt=dst.cbt, dst_cb_off=dst_c0 // 8,
                  dst_lo_off=dst.lo_off)
         self.launches += 1
 
     def conv_act(self, src: Blocked, segs, pw: PackedConv, dst: Blocked, dst_c0: int = 0) -> None:
         """conv + bias straight to an activation buffer (no norm): 1x1 fusion projections."""
-        a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], self.split)
-        K.conv3d(src, pw, a_cb, dst.t, _lib.OUT_BLOCKED_BF16_HILO if self.split else _lib.OUT_BLOCKED_BF16,
+        a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], pw.nm or self.split)
+        K.conv3d(src, pw, a_cb, dst.t, _lib.OUT_BLOCKED_BF16_HILO if self.nm.a_split else _lib.OUT_BLOCKED_BF16,
                  dst_cbt=dst.cbt, dst_cb_off=dst_c0 // 8, dst_lo_off=dst.lo_off)
         self.launches += 1
 
@@ -156,13 +160,19 @@ class ConvRunner:
             K.conv1x1_logits(src, segs[0][0], segs[0][1], conv.weight, conv.bias, out)
             self.launches += 1
             return
-        a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], self.split)
+        a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], pw.nm or self.split)
         K.conv3d(src, pw, a_cb, out, _lib.OUT_NCDHW_F32)
         self.launches += 1
 
 
 def _param_version(params: Sequence[Tensor]) -> Tuple:
     return tuple((p.data_ptr(), p._version) for p in params)
+
+
+def module_version(module) -> Tuple:
+    """Version stamp of everything a captured forward bakes in: parameters and norm buffers (BatchNorm running
+    statistics).  In-place updates (optimizer.step, load_state_dict) bump `_version`; re-assignment changes data_ptr."""
+    return _param_version(list(module.parameters()) + list(module.buffers()))
 
 
 class UNet3DEngine:
@@ -172,11 +182,14 @@ class UNet3DEngine:
     parameters are read.  Dropout is applied by the caller (it is the identity in eval / p=0).
     """
 
-    def __init__(self, module, mode: str = "bf16"):
-        assert mode in ("bf16", "parity")
+    def __init__(self, module, mode: str = "bf16", weights_from: Optional["UNet3DEngine"] = None):
+        """weights_from: another engine of the same module and mode whose packed weights this one reads (the extra
+        batch slots of the sliding-window inferer: one kernel-layout copy of the weights, not one per slot)."""
+        self.nm = numeric_mode(mode)
         self.module = module
         self.mode = mode
-        self.split = mode == "parity"
+        self.split = self.nm      # what Blocked / pack_conv_weight / a_chunk_table take
+        self._weights_from = weights_from
         self._packed: Optional[Dict[str, PackedConv]] = None
         self._packed_version = None
         self._bufs: Dict[Tuple, Dict[str, object]] = {}
@@ -184,33 +197,38 @@ class UNet3DEngine:
 
     # ---------------------------------------------------------------- weights
     def _pack(self) -> Dict[str, PackedConv]:
+        if self._weights_from is not None:
+            P = self._weights_from._pack()
+            self._norms = self._weights_from._norms
+            return P
         m = self.module
         params = list(m.parameters())
         ver = _param_version(params)
         if self._packed is not None and ver == self._packed_version:
             return self._packed
         f = m.features
-        sp = self.split
+        nm = self.nm
         P: Dict[str, PackedConv] = {}
 
         self._norms: Dict[str, object] = {}
 
-        def block(name: str, blk, segs1):
+        def block(name: str, blk, segs1, level: int):
             # bias of a conv that feeds InstanceNorm(affine=False) is cancelled exactly by the mean subtraction; every
             # other norm option (batch / group / none, model.backbone.norm) keeps it
             inst = isinstance(blk.norm1, torch.nn.InstanceNorm3d)
+            sp = nm.for_layer(level)      # mixed modes split the weights only on the cheap (deep) levels
             P[name + ".conv1"] = K.pack_conv_weight(blk.conv1.weight, None if inst else blk.conv1.bias, sp, segs1, use_bias=not inst)
             P[name + ".conv2"] = K.pack_conv_weight(blk.conv2.weight, None if inst else blk.conv2.bias, sp, None, use_bias=not inst)
             self._norms[name + ".conv1"], self._norms[name + ".conv2"] = blk.norm1, blk.norm2
 
-        block("init_conv", m.init_conv, [m.in_channels])
+        block("init_conv", m.init_conv, [m.in_channels], 0)
         for i, enc in enumerate(m.encoders):
-            block(f"encoders.{i}", enc.conv, [f[i]])
+            block(f"encoders.{i}", enc.conv, [f[i]], i + 1)
         for j, dec in enumerate(m.decoders):
             lvl = len(f) - 2 - j
-            P[f"decoders.{j}.up"] = K.pack_conv_weight(dec.up.weight, dec.up.bias, sp, None, transposed=True)
-            block(f"decoders.{j}", dec.conv, [f[lvl], f[lvl]])
-        P["out_conv"] = K.pack_conv_weight(m.out_conv.weight, m.out_conv.bias, sp, None)
+            P[f"decoders.{j}.up"] = K.pack_conv_weight(dec.up.weight, dec.up.bias, nm.for_layer(lvl + 1, True), None, transposed=True)
+            block(f"decoders.{j}", dec.conv, [f[lvl], f[lvl]], lvl)
+        P["out_conv"] = K.pack_conv_weight(m.out_conv.weight, m.out_conv.bias, nm.for_layer(0), None)
         self._packed, self._packed_version = P, ver
         return P
 
@@ -327,11 +345,12 @@ class DualEncoderEngine:
     The fused feature lands directly in the skip half of that level's decoder concat buffer.
     """
 
-    def __init__(self, module, mode: str = "bf16"):
-        assert mode in ("bf16", "parity")
+    def __init__(self, module, mode: str = "bf16", weights_from: Optional["DualEncoderEngine"] = None):
+        self.nm = numeric_mode(mode)
         self.module = module
         self.mode = mode
-        self.split = mode == "parity"
+        self.split = self.nm      # what Blocked / pack_conv_weight / a_chunk_table take
+        self._weights_from = weights_from
         self._packed = None
         self._packed_version = None
         self._bufs: Dict[Tuple, Dict[str, object]] = {}
@@ -339,29 +358,32 @@ class DualEncoderEngine:
         self.last_gate_weights: List[Tensor] = []
 
     def _pack(self) -> Dict[str, PackedConv]:
+        if self._weights_from is not None:
+            return self._weights_from._pack()
         m = self.module
         ver = _param_version(list(m.parameters()))
         if self._packed is not None and ver == self._packed_version:
             return self._packed
-        f, sp, M = m.features, self.split, m.num_modalities
+        f, nm, M = m.features, self.nm, m.num_modalities
         P: Dict[str, PackedConv] = {}
 
-        def block(name, blk, segs1):
+        def block(name, blk, segs1, level):
+            sp = nm.for_layer(level)
             P[name + ".conv1"] = K.pack_conv_weight(blk.conv1.weight, None, sp, segs1, use_bias=False)
             P[name + ".conv2"] = K.pack_conv_weight(blk.conv2.weight, None, sp, None, use_bias=False)
 
         for i, enc in enumerate(m.encoders):
-            block(f"enc{i}.init", enc["init_conv"], [m.in_channels_per_modality])
+            block(f"enc{i}.init", enc["init_conv"], [m.in_channels_per_modality], 0)
             for l, blk in enumerate(enc["blocks"]):
-                block(f"enc{i}.blocks.{l}", blk.conv, [f[l]])
+                block(f"enc{i}.blocks.{l}", blk.conv, [f[l]], l + 1)
         if m.fusion_type == "concat":
             for l, proj in enumerate(m.fusion_proj):
-                P[f"fusion_proj.{l}"] = K.pack_conv_weight(proj.weight, proj.bias, sp, [f[l]] * M)
+                P[f"fusion_proj.{l}"] = K.pack_conv_weight(proj.weight, proj.bias, nm.for_layer(l, True), [f[l]] * M)
         for j, dec in enumerate(m.decoder):
             lvl = len(f) - 2 - j
-            P[f"decoder.{j}.up"] = K.pack_conv_weight(dec.up.weight, dec.up.bias, sp, None, transposed=True)
-            block(f"decoder.{j}", dec.conv, [f[lvl], f[lvl]])
-        P["out_conv"] = K.pack_conv_weight(m.out_conv.weight, m.out_conv.bias, sp, None)
+            P[f"decoder.{j}.up"] = K.pack_conv_weight(dec.up.weight, dec.up.bias, nm.for_layer(lvl + 1, True), None, transposed=True)
+            block(f"decoder.{j}", dec.conv, [f[lvl], f[lvl]], lvl)
+        P["out_conv"] = K.pack_conv_weight(m.out_conv.weight, m.out_conv.bias, nm.for_layer(0), None)
         self._packed, self._packed_version = P, ver
         return P
 

@@ -14,6 +14,7 @@ from ._lib import lib, check
 import os
 
 from .tiling import plan_conv, plan_roll, ConvTile, ROLL_FLAG, ROLL_KPAIR_FLAG
+from .numerics import NumericMode, mode as numeric_mode
 
 Tensor = torch.Tensor
 
@@ -56,14 +57,18 @@ class Blocked:
     (blocks [0, cb)) followed by a lo plane (blocks [cb, 2cb)), i.e. lo_off == cb.
     """
 
-    def __init__(self, n_img: int, channels: int, Z: int, Y: int, X: int, split: bool, device):
+    def __init__(self, n_img: int, channels: int, Z: int, Y: int, X: int, split, device):
+        """split: a NumericMode / mode name (numerics.py), or the legacy bool (False = bf16, True = parity)."""
         assert channels % 8 == 0
+        nm = numeric_mode(split)
         self.n_img, self.channels, self.Z, self.Y, self.X = n_img, channels, Z, Y, X
         self.cb = channels // 8
-        self.split = split
-        self.cbt = self.cb * (2 if split else 1)
-        self.lo_off = self.cb if split else 0
-        self.t = torch.empty((n_img, self.cbt, Z, Y, X, 8), dtype=torch.bfloat16, device=device)
+        self.nm = nm
+        self.fmt = nm.fmt                      # element format of the 16-bit storage (MMSEG_FMT_*)
+        self.split = nm.a_split                # hi + lo planes
+        self.cbt = self.cb * (2 if self.split else 1)
+        self.lo_off = self.cb if self.split else 0
+        self.t = torch.empty((n_img, self.cbt, Z, Y, X, 8), dtype=nm.dtype, device=device)
 
     @property
     def nvox(self) -> int:
@@ -75,7 +80,7 @@ class Blocked:
         assert c0 % 8 == 0
         out = torch.empty((self.n_img, channels, self.Z, self.Y, self.X), dtype=torch.float32, device=self.t.device)
         _call("mmseg_unpack_ncdhw", _ptr(self.t), _ptr(out), self.n_img, channels, self.Z, self.Y, self.X,
-                                     self.cbt, c0 // 8, self.lo_off, _stream())
+                                     self.cbt, c0 // 8, self.lo_off, self.fmt, _stream())
         return out
 
 
@@ -85,7 +90,7 @@ def pack_ncdhw(x: Tensor, dst: Blocked, c0: int = 0) -> None:
     n, Cc, Z, Y, X = x.shape
     cb = ((Cc + 15) // 16) * 2
     assert (n, Z, Y, X) == (dst.n_img, dst.Z, dst.Y, dst.X) and c0 % 8 == 0 and c0 // 8 + cb <= dst.cb
-    _call("mmseg_pack_ncdhw", _ptr(x), _ptr(dst.t), n, Cc, Z, Y, X, dst.cbt, c0 // 8, dst.lo_off, cb, _stream())
+    _call("mmseg_pack_ncdhw", _ptr(x), _ptr(dst.t), n, Cc, Z, Y, X, dst.cbt, c0 // 8, dst.lo_off, cb, dst.fmt, _stream())
 
 
 # --------------------------------------------------------------------------------------------- weight packing
@@ -100,9 +105,10 @@ class PackedConv:
     out_channels: int         # real output channels (per tap for convT)
     NT: int
     n_ntiles: int
-    n_kchunks: int            # including the 3x of split mode
-    split: bool
+    n_kchunks: int            # including the extra passes of the split modes
+    split: bool               # any operand split (more than one pass)
     is_convt: bool = False
+    nm: Optional[NumericMode] = None
 
 
 def _pack_gemm_weight(wmat: Tensor, NT: int) -> Tensor:
@@ -130,8 +136,11 @@ def pack_conv_weight(weight: Tensor, bias: Optional[Tensor], split: bool, seg_ch
 
     seg_channels: real channels of each input segment (concat order); each segment is zero-padded to a multiple
     of 16 channels so that a 16-channel K chunk never straddles two producers.
-    Split mode appends K chunks: [W_hi | W_hi | W_lo] to be paired with activations [A_hi | A_lo | A_hi].
+    Split modes append K chunks (numerics.py): a+w split [W_hi | W_hi | W_lo] pairs with [A_hi | A_lo | A_hi];
+    w split only [W_hi | W_lo] with [A | A]; a split only [W | W] with [A_hi | A_lo].
     """
+    nm = numeric_mode(split)
+    dt = nm.dtype
     w = weight.detach().float()
     if transposed:  # [Cin, Cout, 2,2,2] -> GEMM columns n = (((dz*2+dy)*CB + cb)*2 + dx)*8 + j  (co = cb*8 + j)
         cin, cout = w.shape[0], w.shape[1]
@@ -162,32 +171,37 @@ def pack_conv_weight(weight: Tensor, bias: Optional[Tensor], split: bool, seg_ch
     NT = min(n_out, nt_cap)
     while n_out % NT:
         NT -= 16
-    if split:
-        hi = wp.to(torch.bfloat16)
-        lo = (wp - hi.float()).to(torch.bfloat16)
-        packed = torch.cat([_pack_gemm_weight(hi.float(), NT).to(torch.bfloat16)] * 2 +
-                           [_pack_gemm_weight(lo.float(), NT).to(torch.bfloat16)], dim=1).contiguous()
-    else:
-        packed = _pack_gemm_weight(wp, NT).to(torch.bfloat16).contiguous()
+    hi = wp.to(dt)
+    p_hi = _pack_gemm_weight(hi.float(), NT).to(dt)
+    parts_w = [p_hi] * (2 if nm.a_split else 1)
+    if nm.w_split:
+        lo = (wp - hi.float()).to(dt)
+        parts_w.append(_pack_gemm_weight(lo.float(), NT).to(dt))
+    packed = (torch.cat(parts_w, dim=1) if len(parts_w) > 1 else p_hi).contiguous()
     bias_p = None
     if use_bias and b is not None:
         bias_p = torch.zeros(n_out, dtype=torch.float32, device=w.device)
         bias_p[:n_real] = b
-    return PackedConv(packed, bias_p, ksize, cin, n_out, out_channels, NT, n_out // NT, packed.shape[1], split,
-                      transposed)
+    return PackedConv(packed, bias_p, ksize, cin, n_out, out_channels, NT, n_out // NT, packed.shape[1], nm.passes > 1,
+                      transposed, nm)
 
 
-def a_chunk_table(src: Blocked, seg_c0: Sequence[int], seg_channels: Sequence[int], split: bool) -> List[int]:
+def a_chunk_table(src: Blocked, seg_c0: Sequence[int], seg_channels: Sequence[int], split) -> List[int]:
     """First channel block of every K chunk, in the order pack_conv_weight laid the chunks out."""
+    nm = numeric_mode(split)
     hi = []
     for c0, s in zip(seg_c0, seg_channels):
         assert c0 % 16 == 0
         for j in range((s + 15) // 16):
             hi.append(c0 // 8 + 2 * j)
-    if not split:
-        return hi
-    lo = [b + src.lo_off for b in hi]
-    return hi + lo + hi
+    assert getattr(src, "split", nm.a_split) == nm.a_split and getattr(src, "fmt", nm.fmt) == nm.fmt, \
+        "activation buffer and numeric mode disagree"
+    out = list(hi)
+    if nm.a_split:
+        out += [b + src.lo_off for b in hi]      # A_lo * W_hi
+    if nm.w_split:
+        out += hi                                 # A_hi * W_lo
+    return out
 
 
 def plan_conv_norm(src_dims, n_img: int, pw: "PackedConv", raw_f32: bool, a_cb: Optional[Sequence[int]] = None) -> ConvTile:
@@ -229,7 +243,9 @@ def conv3d(src: Blocked, pw: PackedConv, a_cb: Sequence[int], dst: Tensor, out_m
     a.TX, a.TY, a.TZ, a.stages = tile.TX, tile.TY, tile.TZ, tile.stages
     a.out_mode, a.out_channels = out_mode, pw.out_channels
     a.dst_cbt, a.dst_cb_off, a.dst_lo_off = dst_cbt, dst_cb_off, dst_lo_off
-    a.flags = flags | (ROLL_FLAG if tile.roll else 0) | (ROLL_KPAIR_FLAG if (tile.roll and tile.kpb == 2) else 0)
+    assert pw.w.dtype == src.t.dtype, "weights and activations must share the 16-bit element format"
+    a.flags = flags | (ROLL_FLAG if tile.roll else 0) | (ROLL_KPAIR_FLAG if (tile.roll and tile.kpb == 2) else 0) \
+        | (_lib.CONV_FP16_FLAG if src.fmt == _lib.FMT_FP16 else 0)
     for i, v in enumerate(a_cb):
         a.a_cb[i] = v
     if stats is not None:
@@ -285,6 +301,7 @@ def instnorm_act_apply(raw: Tensor, raw_is_f32: bool, mean_rstd: Optional[Tensor
     if pooled is not None:
         a.pool_cbt, a.pool_cb_off, a.pool_lo_off = pooled.cbt, pooled_c0 // 8, pooled.lo_off
     a.slope = slope
+    a.elem_fmt = dst.fmt
     if PROFILE is not None:
         nel = n_img * channels * Z * Y * X
         out_b = 2 * (2 if dst.split else 1)
@@ -305,7 +322,7 @@ def pack_ncdhw_ex(x: Tensor, dst: Blocked, c0: int = 0, pre_sigmoid: Optional[Tu
         assert gate_logits.dtype == torch.float32 and gate_logits.is_contiguous() and gate_logits.numel() == n * Z * Y * X
     _call("mmseg_pack_ncdhw_ex", _ptr(x), _ptr(dst.t), n, Cc, Z, Y, X, dst.cbt, c0 // 8, dst.lo_off, cb,
           1 if pre_sigmoid is not None else 0, float(a), float(b), _ptr(gate_logits) if gate_logits is not None else None,
-          _stream())
+          dst.fmt, _stream())
 
 
 def swi_gather(volume: Tensor, starts_dev: Tensor, n_win: int, roi: Tuple[int, int, int], dst: Blocked) -> None:
@@ -314,7 +331,7 @@ def swi_gather(volume: Tensor, starts_dev: Tensor, n_win: int, roi: Tuple[int, i
     # is written once when the engine allocates (and zeroes) its input buffer
     cb = (Cc + 7) // 8
     _call("mmseg_swi_gather", _ptr(volume), Cc, VZ, VY, VX, _ptr(starts_dev), n_win, roi[0], roi[1], roi[2],
-                               _ptr(dst.t), dst.cbt, dst.lo_off, cb, _stream())
+                               _ptr(dst.t), dst.cbt, dst.lo_off, cb, dst.fmt, _stream())
 
 
 def swi_blend(win_logits: Tensor, starts_dev: Tensor, n_win: int, wz: Tensor, wy: Tensor, wx: Tensor, w_floor: float,
@@ -336,14 +353,31 @@ def swi_logits_blend(feat: Blocked, c0: int, cin: int, window: int, weight: Tens
     b = bias.detach().float() if bias is not None else None
     _call("mmseg_swi_logits_blend", _ptr(feat.t), feat.cbt, c0 // 8, feat.lo_off if feat.split else 0, cin, window, _ptr(w),
           _ptr(b) if b is not None else None, Kc, _ptr(start_dev), feat.Z, feat.Y, feat.X, _ptr(wz), _ptr(wy), _ptr(wx),
-          w_floor, _ptr(out), _ptr(count), VZ, VY, VX, _stream())
+          w_floor, _ptr(out), _ptr(count), VZ, VY, VX, feat.fmt, _stream())
 
 
-def swi_finalize(out: Tensor, count: Tensor, normalize_in_place: bool, labels: Optional[Tensor]) -> None:
-    K = out.shape[0]
-    vox = count.numel()
-    _call("mmseg_swi_finalize", _ptr(out), _ptr(count), K, vox, 1 if normalize_in_place else 0, _ptr(labels),
-                                 _stream())
+def swi_finalize(out: Tensor, count: Tensor, normalize_in_place: bool, labels: Optional[Tensor], z0: int = 0,
+                 z1: Optional[int] = None) -> None:
+    """out [K, VZ, VY, VX] / count [VZ, VY, VX] (contiguous); finalizes the axis-0 slab [z0, z1) in place.
+    labels (optional): uint8 [z1 - z0, VY, VX]."""
+    K, VZ, VY, VX = out.shape
+    z1 = VZ if z1 is None else z1
+    assert out.is_contiguous() and count.is_contiguous() and 0 <= z0 < z1 <= VZ
+    plane, row = VZ * VY * VX, VY * VX
+    if labels is not None:
+        assert labels.is_contiguous() and labels.numel() == (z1 - z0) * row and labels.dtype == torch.uint8
+    _call("mmseg_swi_finalize", C.c_void_p(out.data_ptr() + 4 * z0 * row), C.c_void_p(count.data_ptr() + 4 * z0 * row), K,
+          (z1 - z0) * row, plane, 1 if normalize_in_place else 0, _ptr(labels), _stream())
+
+
+def swi_add_partial(acc: Tensor, z0: int, z1: int, part: Tensor) -> None:
+    """acc[:, z0:z1] += part — acc [P, VZ, VY, VX] contiguous fp32, part [P, z1 - z0, VY, VX] contiguous fp32."""
+    P, VZ, VY, VX = acc.shape
+    row = VY * VX
+    assert acc.is_contiguous() and part.is_contiguous() and tuple(part.shape) == (P, z1 - z0, VY, VX)
+    assert acc.dtype == part.dtype == torch.float32
+    _call("mmseg_swi_add_partial", C.c_void_p(acc.data_ptr() + 4 * z0 * row), VZ * row, _ptr(part), (z1 - z0) * row, P,
+          (z1 - z0) * row, _stream())
 
 
 def dicece_fwd(logits: Tensor, target: Tensor, dice_weight: float, ce_weight: float, smooth: float = 1.0,
@@ -384,7 +418,7 @@ def channel_mean(src: Blocked, c0: int, channels: int) -> Tensor:
     partial = torch.empty((src.n_img * cb, n_chunks, 8), dtype=torch.float32, device=src.t.device)
     mean = torch.empty((src.n_img, channels), dtype=torch.float32, device=src.t.device)
     _call("mmseg_channel_mean", _ptr(src.t), src.n_img, src.cbt, c0 // 8, src.lo_off, cb, src.nvox, _ptr(partial),
-                                 n_chunks, _ptr(mean), _stream())
+                                 n_chunks, _ptr(mean), src.fmt, _stream())
     return mean
 
 
@@ -402,13 +436,13 @@ def modality_combine(src: Blocked, M: int, channels: int, dst: Blocked, dst_c0: 
                      uniform_weight: float = 1.0) -> None:
     _call("mmseg_modality_combine", _ptr(src.t), src.n_img, src.cbt, src.lo_off, M, channels // 8, src.nvox,
                                      _ptr(weights), uniform_weight, _ptr(dst.t), dst.cbt, dst_c0 // 8, dst.lo_off,
-                                     _stream())
+                                     dst.fmt, _stream())
 
 
 def maxpool3d_2(src: Blocked, dst: Blocked, channels: Optional[int] = None, src_c0: int = 0, dst_c0: int = 0) -> None:
     channels = src.channels if channels is None else channels
     _call("mmseg_maxpool3d_2", _ptr(src.t), src.n_img, src.cbt, src_c0 // 8, src.lo_off, channels // 8, src.Z, src.Y,
-                                src.X, _ptr(dst.t), dst.cbt, dst_c0 // 8, dst.lo_off, _stream())
+                                src.X, _ptr(dst.t), dst.cbt, dst_c0 // 8, dst.lo_off, dst.fmt, _stream())
 
 
 # --------------------------------------------------------------------------------------------- weight gradient
@@ -460,7 +494,7 @@ def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt
     """dW (fp32, PyTorch weight layout `weight_shape`) of a conv whose input is `x` (channel segments `segs` in concat
     order) and whose raw-output gradient is `dy` (blocked bf16, `dy_cbt` channel blocks per image, first block dy_cb0)."""
     _lib.require_device()
-    assert not x.split, "the backward path runs in bf16 mode"
+    assert not x.split and x.fmt == _lib.FMT_BF16, "the backward path runs in bf16 mode"
     seg_ch = [s[1] for s in segs]
     seg_pad = [(s + 15) // 16 * 16 for s in seg_ch]
     cin = sum(seg_ch)
@@ -559,7 +593,8 @@ def cross_attention(q: Blocked, q_c0: int, kv: Blocked, k_c0: int, v_c0: int, ou
                     head_dim: int, scale: float) -> None:
     """out[:, head h] = softmax(Q_h K_h^T * scale) V_h over all voxels; head_dim is the (padded) per-head channel count."""
     _lib.require_device()
-    assert not (q.split or kv.split or out.split), "the attention kernel runs in bf16 mode"
+    assert not (q.split or kv.split or out.split) and q.fmt == kv.fmt == out.fmt == _lib.FMT_BF16, \
+        "the attention kernel runs in bf16 mode"
     assert q.nvox == kv.nvox == out.nvox and q.n_img == kv.n_img == out.n_img
     if PROFILE is not None:
         _INFO[0] = {"flops": 4.0 * q.n_img * heads * q.nvox * q.nvox * head_dim,
@@ -607,11 +642,11 @@ def conv1x1_logits(src: Blocked, c0: int, cin: int, weight: Tensor, bias: Option
         _INFO[0] = {"flops": 2.0 * src.n_img * src.nvox * cin * cout, "bytes": src.n_img * src.nvox * (cin * 2.0 + cout * 4.0),
                     "layer": f"logits1x1 c{cin}->{cout} {src.Z}x{src.Y}x{src.X} img{src.n_img}"}
     _call("mmseg_conv1x1_logits", _ptr(src.t), src.n_img, src.cbt, c0 // 8, src.lo_off if src.split else 0, cin, src.nvox,
-          _ptr(w), _ptr(b) if b is not None else None, cout, _ptr(out), _stream())
+          _ptr(w), _ptr(b) if b is not None else None, cout, _ptr(out), src.fmt, _stream())
 
 
 def modality_max(src: Blocked, M: int, channels: int, dst: Blocked, dst_c0: int = 0) -> None:
-    assert not src.split and not dst.split
+    assert not src.split and not dst.split and src.fmt == dst.fmt == _lib.FMT_BF16
     _call("mmseg_modality_max", _ptr(src.t), src.n_img, src.cbt, M, channels // 8, src.nvox, _ptr(dst.t), dst.cbt,
           dst_c0 // 8, _stream())
 

@@ -14,6 +14,7 @@ from .unet import (ConvBlock3D, DownBlock3D, UpBlock3D, _require_cuda, _no_autog
 from ....engine import DualEncoderEngine
 from .... import kernels as K
 from ....kernels import Blocked
+from ....numerics import mode as numeric_mode
 
 
 class CrossModalAttention(nn.Module):
@@ -40,7 +41,7 @@ class CrossModalAttention(nn.Module):
         B, M, C, H, W, D = x.shape
         if C % 16:
             raise NotImplementedError("CrossModalAttention kernels need channels % 16 == 0")
-        split = self.numeric_mode == "parity"
+        split = numeric_mode(self.numeric_mode)
         with torch.no_grad():
             st = Blocked(B, M * C, H, W, D, split, x.device)
             K.pack_ncdhw(x.reshape(B, M * C, H, W, D).contiguous().float(), st)
@@ -94,8 +95,7 @@ class DualEncoder(nn.Module):
         return decoder
 
     def set_numeric_mode(self, mode: str) -> "DualEncoder":
-        assert mode in ("bf16", "parity")
-        self.numeric_mode = mode
+        self.numeric_mode = numeric_mode(mode).name
         return self
 
     def engine(self) -> DualEncoderEngine:

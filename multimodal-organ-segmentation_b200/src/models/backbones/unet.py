@@ -14,6 +14,7 @@ from ....train_engine import TrainEngine, train_forward
 from .... import kernels as K
 from .... import _lib
 from ....kernels import Blocked
+from ....numerics import MODES, mode as numeric_mode
 
 _DEFAULT_MODE = "bf16"
 
@@ -103,7 +104,7 @@ class ConvBlock3D(nn.Module):
         _require_cuda(x)
         _no_autograd(self, x)
         self.kernel_supported()
-        split = self.numeric_mode == "parity"
+        split = numeric_mode(self.numeric_mode)
         with torch.no_grad():
             x = x.contiguous().float()
             n, c, Z, Y, X = x.shape
@@ -169,7 +170,7 @@ class UpBlock3D(nn.Module):
             raise NotImplementedError("UpBlock3D(mode != 'transpose') is never selected by the reference's builders "
                                       "(unet.py:149) and has no sm_100a kernel")
         self.conv.kernel_supported()
-        split = self.numeric_mode == "parity"
+        split = numeric_mode(self.numeric_mode)
         with torch.no_grad():
             x = x.contiguous().float()
             skip = skip.contiguous().float()
@@ -227,9 +228,9 @@ class UNet3D(nn.Module):
         self._engines: Dict[str, UNet3DEngine] = {}
 
     def set_numeric_mode(self, mode: str) -> "UNet3D":
-        """'bf16' (throughput) or 'parity' (3-pass split-bf16; meets the stated logit / label tolerances)."""
-        assert mode in ("bf16", "parity")
-        self.numeric_mode = mode
+        """'bf16' (throughput), 'parity' (3-pass split-bf16; meets the stated logit / label tolerances) or another rung
+        of the ladder in numerics.py ('fp16', 'fp16w2', 'fp16a2', 'fp16x3')."""
+        self.numeric_mode = numeric_mode(mode).name
         return self
 
     def engine(self) -> UNet3DEngine:

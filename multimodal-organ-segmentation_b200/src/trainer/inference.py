@@ -116,19 +116,40 @@ def touched_range(starts: Sequence[Tuple[int, ...]], lo: int, hi: int, roi0: int
     return min(s), max(s) + roi0
 
 
+def pick_engine_batch(n_windows: int, preferred: int = 8, lo: int = 6, hi: int = 16) -> int:
+    """Windows per engine batch: the divisor of `n_windows` in [lo, hi] closest to `preferred` (every batch is then a
+    full, graph-replayed batch — e.g. 75 windows per rank at 8 GPUs run as 5 x 15 instead of 9 x 8 + 3), else
+    `preferred` (the shorter tail batch gets its own captured graph)."""
+    if n_windows <= preferred:
+        return max(1, n_windows)
+    divs = [d for d in range(lo, hi + 1) if n_windows % d == 0]
+    if not divs:
+        return preferred
+    return min(divs, key=lambda d: (abs(d - preferred), -d))
+
+
 # ------------------------------------------------------------------------------------------ the inferer
 class SlidingWindowInferer:
-    """Stateful sliding-window engine for one (volume shape, roi, overlap, mode)."""
+    """Stateful sliding-window engine of one model for one (roi, overlap, blend mode).
+
+    Persistent across calls and volume shapes: the batch slots (engine, stream, window-origin slot, activation buffers —
+    they depend on the roi, not on the volume).  Per volume shape: the window list and the accumulator.  CUDA graphs of
+    a batch (gather + forward) are cached per (slot, batch size, volume buffer) and dropped whenever the model's
+    parameters or norm buffers change (engine.module_version), so predict -> train / load_state_dict -> predict never
+    replays a forward that reads stale packed weights."""
 
     def __init__(self, model, roi_size=(96, 96, 96), overlap: float = 0.5, mode: str = "constant",
-                 sigma_scale: float = 0.125, engine_batch: int = 8, use_graph: bool = True):
+                 sigma_scale: float = 0.125, engine_batch: Optional[int] = None, use_graph: bool = True):
         self.model = model
         self.roi = tuple(int(r) for r in roi_size)
         self.overlap, self.mode, self.sigma_scale = overlap, mode, sigma_scale
-        self.engine_batch = engine_batch
+        self.engine_batch = engine_batch          # None: chosen per call from the number of windows (pick_engine_batch)
         self.use_graph = use_graph
-        self.n_slots = int(__import__("os").environ.get("MMSEG_SWI_SLOTS", "3"))   # 2 -> 383 ms, 3 -> 378 ms per volume
+        self.n_slots = int(os.environ.get("MMSEG_SWI_SLOTS", "3"))   # 2 -> 383 ms, 3 -> 378 ms per volume
         self._state = None
+        self._slots = None
+        self._slots_key = None
+        self._weights_version = None
         self.launches_last = 0
 
     # -- helpers
@@ -143,49 +164,82 @@ class SlidingWindowInferer:
             v = self._dev_vol = torch.zeros(tuple(shape), dtype=torch.float32, device=device)
         return v
 
-    def _setup(self, C: int, vol_shape, device):
-        key = (C, tuple(vol_shape), str(device), self._backbone().numeric_mode)
+    def _get_slots(self, device):
+        """Batch slots, kept for the life of the inferer (per device and numeric mode): each has its own engine buffers,
+        window-origin slot and CUDA stream, and all share slot 0's packed weights.  The forward of batch k+1
+        (tensor-bound convs + HBM-bound norm kernels) runs concurrently with the tail / blend of batch k (measured:
+        2, 3 and 4 slots are within 0.5 %).  Blends all run on the caller's stream in window order (deterministic)."""
+        bb = self._backbone()
+        key = (str(device), bb.numeric_mode)
+        if self._slots is not None and self._slots_key == key:
+            return self._slots
+        eng = bb.engine()
+        slots = []
+        for j in range(self.n_slots):
+            e = eng if j == 0 else type(eng)(eng.module, eng.mode, weights_from=eng)
+            slots.append({"eng": e, "stream": torch.cuda.Stream(device=device), "starts_dev": None, "logits": None,
+                          "graphs": {}, "launches": {}, "feat": {}, "ev_fwd": torch.cuda.Event(), "ev_blend": None})
+        self._slots, self._slots_key = slots, key
+        return slots
+
+    def _check_weights(self) -> None:
+        """Drop every captured graph when a parameter / norm buffer changed since capture (a replay would
+        read the previous — possibly freed — packed weights)."""
+        from ...engine import module_version
+        ver = module_version(self._backbone())
+        if ver != self._weights_version:
+            if self._slots is not None:
+                for slot in self._slots:
+                    slot["graphs"].clear()
+                    slot["launches"].clear()
+            self._weights_version = ver
+
+    def _setup(self, C: int, vol_shape, device, n_local: Optional[int] = None):
+        bb = self._backbone()
+        slots = self._get_slots(device)
+        starts_n = None
+        nb_req = self.engine_batch
+        key = (C, tuple(vol_shape), str(device), bb.numeric_mode, nb_req, n_local)
         if self._state is not None and self._state["key"] == key:
             return self._state
-        bb = self._backbone()
-        eng = bb.engine()
         K_out = bb.out_channels
         VZ, VY, VX = vol_shape
         starts = window_starts(vol_shape, self.roi, self.overlap)
         tabs, floor = importance_tables(self.roi, self.mode, self.sigma_scale)
-        nb = min(self.engine_batch, len(starts))
+        n_mine = len(starts) if n_local is None else n_local
+        nb = pick_engine_batch(n_mine) if nb_req is None else min(nb_req, max(1, n_mine))
+        prev = self._state
+        acc = None
+        if prev is not None and tuple(prev["acc"].shape) == (K_out + 1, VZ, VY, VX) and prev["acc"].device == device:
+            acc = prev["acc"]
         st = {
-            "key": key, "eng": eng, "starts": starts, "nb": nb, "K": K_out,
+            "key": key, "eng": slots[0]["eng"], "starts": starts, "nb": nb, "K": K_out, "slots": slots,
             "wz": tabs[0].to(device), "wy": tabs[1].to(device), "wx": tabs[2].to(device), "floor": floor,
             # all window origins live on the device; each batch is a stream-ordered D2D copy into the fixed
             # `starts_dev` slot the (graph-captured) kernels read, so no host sync sits between batches
             "starts_all": torch.tensor(starts, dtype=torch.int32).to(device),
             # weighted-logit accumulator and the count map share one allocation: acc[:K] = out, acc[K] = count,
             # so a rank's partial result travels as ONE tensor in the sharded exchange
-            "acc": torch.empty((K_out + 1, VZ, VY, VX), dtype=torch.float32, device=device),
+            "acc": acc if acc is not None else torch.empty((K_out + 1, VZ, VY, VX), dtype=torch.float32, device=device),
         }
-        # n_slots (default 3, MMSEG_SWI_SLOTS) batch slots, each with its own engine buffers, window-origin slot, logits
-        # and CUDA stream: the forward of batch k+1 (tensor-bound convs + HBM-bound norm kernels) runs concurrently with
-        # the tail / blend of batch k, so the memory-bound kernels of one batch hide behind the tensor-bound kernels of
-        # another (measured: 2, 3 and 4 slots are within 0.5 %).  Blends all run on the caller's stream in window order
-        # (deterministic), gated by per-slot events.
-        st["slots"] = []
-        for j in range(self.n_slots):
-            e = eng if j == 0 else type(eng)(eng.module, eng.mode)
-            st["slots"].append({
-                "eng": e, "stream": torch.cuda.Stream(device=device),
-                "starts_dev": torch.zeros((nb, 3), dtype=torch.int32, device=device),
-                "logits": torch.empty((nb, K_out, *self.roi), dtype=torch.float32, device=device),
-                "graph": None, "vol_ptr": None, "launches": 0,
-                "ev_fwd": torch.cuda.Event(), "ev_blend": None})
+        for slot in slots:
+            if slot["starts_dev"] is None or slot["starts_dev"].shape[0] < nb:
+                slot["starts_dev"] = torch.zeros((nb, 3), dtype=torch.int32, device=device)
+                slot["graphs"].clear()      # the graphs baked the old origin slot's address in
+                slot["launches"].clear()
         st["out"], st["count"] = st["acc"][:K_out], st["acc"][K_out]
         # out_conv fused into the blend (no logits tensor) when the 1x1 head and the window geometry allow it
+        eng = slots[0]["eng"]
         oc = getattr(eng.module, "out_conv", None)
         f0 = eng.module.features[0]
         st["fused_head"] = bool(
             os.environ.get("MMSEG_SWI_FUSED_HEAD", "1") == "1" and oc is not None and tuple(oc.kernel_size) == (1, 1, 1)
             and K_out <= 8 and f0 % 8 == 0 and f0 <= 128 and self.roi[2] % 4 == 0 and VX % 4 == 0
             and self.roi[2] // 4 <= 128 and all(s_[2] % 4 == 0 for s_ in starts))
+        if not st["fused_head"]:
+            for slot in slots:
+                if slot["logits"] is None or slot["logits"].shape[0] < nb or slot["logits"].shape[1] != K_out:
+                    slot["logits"] = torch.empty((nb, K_out, *self.roi), dtype=torch.float32, device=device)
         self._state = st
         return st
 
@@ -195,7 +249,7 @@ class SlidingWindowInferer:
         slot["eng"].gather_windows(volume, slot["starts_dev"], n, self.roi)
         if st["fused_head"]:
             # features only; the buffer is persistent per batch size (graph replays of full batches keep reading it)
-            slot.setdefault("feat", {})[n] = slot["eng"].forward_blocked(n, rz, ry, rx, None, device=volume.device)
+            slot["feat"][n] = slot["eng"].forward_blocked(n, rz, ry, rx, None, device=volume.device)
         else:
             slot["eng"].forward_blocked(n, rz, ry, rx, slot["logits"][:n])
 
@@ -226,7 +280,10 @@ class SlidingWindowInferer:
         that covers its windows instead of for the whole volume."""
         _lib.require_device()
         assert volume.dim() == 4 and volume.is_cuda and volume.dtype == torch.float32 and volume.is_contiguous()
-        st = self._setup(volume.shape[0], volume.shape[1:], volume.device)
+        n_total = len(window_starts(volume.shape[1:], self.roi, self.overlap)) if (hi is not None or lo) else None
+        n_local = None if n_total is None else (n_total if hi is None else hi) - lo
+        st = self._setup(volume.shape[0], volume.shape[1:], volume.device, n_local)
+        self._check_weights()
         starts = st["starts"]
         hi = len(starts) if hi is None else hi
         main = torch.cuda.current_stream(volume.device)
@@ -236,6 +293,7 @@ class SlidingWindowInferer:
             slot["stream"].wait_stream(main)      # the volume (and anything else queued by the caller) is ready
         i, k = lo, 0
         ri = 0
+        vkey = (volume.data_ptr(), tuple(volume.shape))
         while i < hi:
             n = min(nb, hi - i)
             slot = st["slots"][k % len(st["slots"])]
@@ -248,20 +306,24 @@ class SlidingWindowInferer:
                 if slot["ev_blend"] is not None:   # the previous user of this slot's logits / origins has been blended
                     slot["stream"].wait_event(slot["ev_blend"])
                 slot["starts_dev"][:n].copy_(st["starts_all"][i:i + n], non_blocking=True)
-                if self.use_graph and n == nb:
-                    if slot["graph"] is None or slot["vol_ptr"] != volume.data_ptr():
+                if self.use_graph:
+                    gkey = (n, vkey, st["fused_head"])
+                    g = slot["graphs"].get(gkey)
+                    if g is None:
                         self._forward_batch(st, slot, volume, n)  # warm-up: allocates workspaces, packs weights
                         slot["stream"].synchronize()
                         g = torch.cuda.CUDAGraph()
                         l0 = K.LAUNCHES[0]
                         with torch.cuda.graph(g, stream=slot["stream"]):
                             self._forward_batch(st, slot, volume, n)
-                        slot["launches"] = K.LAUNCHES[0] - l0
-                        slot["graph"], slot["vol_ptr"] = g, volume.data_ptr()
+                        slot["launches"][gkey] = K.LAUNCHES[0] - l0
+                        if len(slot["graphs"]) >= 8:      # bounded: volumes of many shapes do not pile up graphs
+                            slot["graphs"].pop(next(iter(slot["graphs"])))
+                        slot["graphs"][gkey] = g
                         g.replay()
                     else:
-                        slot["graph"].replay()
-                        K.LAUNCHES[0] += slot["launches"]
+                        g.replay()
+                        K.LAUNCHES[0] += slot["launches"][gkey]
                 else:
                     self._forward_batch(st, slot, volume, n)
                 slot["ev_fwd"].record(slot["stream"])
@@ -275,57 +337,57 @@ class SlidingWindowInferer:
 
     @torch.no_grad()
     def finalize(self, normalize: bool = True, labels: bool = True, z0: int = 0, z1: Optional[int] = None):
-        """out /= count (in place) and / or argmax -> uint8 over the axis-0 slab [z0, z1)."""
+        """out /= count (in place) and / or argmax -> uint8 over the axis-0 slab [z0, z1), in place (the kernel takes
+        the class-plane stride, so a slab needs no packed copy)."""
         st = self._state
-        VZ = st["out"].shape[1]
+        VZ, VY, VX = st["out"].shape[1:]
         z1 = VZ if z1 is None else z1
         lab = None
         if z1 > z0:
-            if z0 == 0 and z1 == VZ:
-                out_v, cnt_v = st["out"], st["count"]
-            else:
-                # a z-slab of [K, VZ, VY, VX] is not contiguous across K: finalize works on a packed copy
-                out_v = st["out"][:, z0:z1].contiguous()
-                cnt_v = st["count"][z0:z1].contiguous()
-            lab = torch.empty(cnt_v.shape, dtype=torch.uint8, device=cnt_v.device) if labels else None
-            K.swi_finalize(out_v, cnt_v, normalize, lab)
-            if normalize and out_v is not st["out"]:
-                st["out"][:, z0:z1].copy_(out_v)
+            lab = torch.empty((z1 - z0, VY, VX), dtype=torch.uint8, device=st["acc"].device) if labels else None
+            K.swi_finalize(st["out"], st["count"], normalize, lab, z0, z1)
         return (st["out"] if normalize else None), lab
 
     @torch.no_grad()
     def __call__(self, inputs: Tensor, return_labels: bool = False):
-        """inputs [1, C, H, W, D] -> logits [1, K, H, W, D] (input dtype fp32) or uint8 labels [H, W, D]."""
+        """inputs [1, C, H, W, D] -> logits [1, K, H, W, D] (input dtype fp32) or uint8 labels [H, W, D].
+        The logits are a VIEW of the inferer's persistent accumulator (overwritten by the next call): internal
+        callers only — the public `sliding_window_inference` returns a fresh tensor."""
         assert inputs.dim() == 5 and inputs.shape[0] == 1, "engine path takes one volume at a time (trainer.py:357)"
         vol = inputs[0].contiguous().float()
         self.accumulate(vol)
         out, lab = self.finalize(normalize=not return_labels, labels=return_labels)
         return lab if return_labels else out.unsqueeze(0)
 
-
     # ------------------------------------------------------------------ multi-GPU: window chunks + one exchange
     @torch.no_grad()
-    def run_sharded(self, volume: Tensor, group=None, want: str = "labels", ready=None):
+    def run_sharded(self, volume: Tensor, group=None, want: str = "all", ready=None):
         """One volume over all ranks of `group`: rank r evaluates its contiguous chunk of the ordered window list,
         then ONE exchange moves every partial (weighted logits + count, K+1 channels) that falls into another rank's
-        axis-0 slab to that owner, which adds them in rank order (deterministic), finalises its slab, and the uint8
-        labels are all-gathered.  `volume` must hold valid data at least over this rank's input range
-        (see `input_range`).  Returns uint8 labels [VZ, VY, VX] on every rank."""
+        axis-0 slab to that owner, which adds them in rank order (deterministic) and finalises its slab in place.
+        `volume` must hold valid data at least over this rank's input range (see `input_range`).
+        want: "all"   — uint8 labels [VZ, VY, VX] on every rank (all-gather of the slabs);
+              "rank0" — the full label map on rank 0 only (gather; other ranks return None);
+              "slab"  — (labels of this rank's own slab, (z0, z1)) and no label collective at all."""
         import torch.distributed as dist
         world = dist.get_world_size(group)
         rank = dist.get_rank(group)
-        st = self._setup(volume.shape[0], volume.shape[1:], volume.device)
-        starts = st["starts"]
+        starts = window_starts(volume.shape[1:], self.roi, self.overlap)
         lo, hi = shard_windows(len(starts), world, rank)
         self.accumulate(volume, lo, hi, ready=ready)
-        if world == 1:
-            return self.finalize(normalize=False, labels=True)[1]
+        st = self._state
         VZ = st["acc"].shape[1]
+        if world == 1:
+            lab = self.finalize(normalize=False, labels=True)[1]
+            return (lab, (0, VZ)) if want == "slab" else lab
         plan = exchange_plan(starts, self.roi[0], VZ, world)
-        exchange_partials(st["acc"], plan, rank, world, group)
+        exchange_partials(st["acc"], plan, rank, world, group, cache=st.setdefault("xchg", {}))
         z0, z1 = plan["slabs"][rank]
         _, lab = self.finalize(normalize=False, labels=True, z0=z0, z1=z1)
-        return gather_label_slabs(lab, plan["slabs"], st["acc"].shape[1:], rank, world, group, volume.device)
+        if want == "slab":
+            return lab, (z0, z1)
+        return gather_label_slabs(lab, plan["slabs"], st["acc"].shape[1:], rank, world, group, volume.device,
+                                  dst=0 if want == "rank0" else None)
 
     def input_range(self, vol_shape, world: int, rank: int) -> Tuple[int, int]:
         """Axis-0 range of the input volume that rank's window chunk reads."""
@@ -349,39 +411,70 @@ def exchange_plan(starts, roi0: int, size0: int, world: int):
     return {"slabs": slabs, "touched": touched, "sends": sends}
 
 
-def exchange_partials(acc: Tensor, plan, rank: int, world: int, group=None) -> None:
+def exchange_partials(acc: Tensor, plan, rank: int, world: int, group=None, cache: Optional[dict] = None) -> None:
     """The single data-path exchange of sharded inference: point-to-point sends of overlap regions to their owner
-    (NCCL over NVLink on GPUs, gloo in the CPU tests), then a rank-ordered add on the owner."""
+    (NCCL over NVLink on GPUs, gloo in the CPU tests), then a rank-ordered add on the owner.
+
+    No staging copies: plane p of the range acc[p, z0:z1] is contiguous, so it is sent as is (one P2P op per plane,
+    all batched into one group call); the receive buffers persist in `cache`; the add is one strided kernel per sender
+    on CUDA (kernels.swi_add_partial) — in rank order, so the sums are deterministic."""
     import torch.distributed as dist
     sends = plan["sends"]
-    ops, recv_bufs, send_bufs = [], {}, []
+    P = acc.shape[0]
+    peer = (lambda r: r) if group is None else (lambda r: dist.get_global_rank(group, r))
+    ops, recv_bufs = [], {}
     for src in range(world):
         rng = sends[src][rank]
         if rng is not None:
-            buf = torch.empty((acc.shape[0], rng[1] - rng[0], *acc.shape[2:]), dtype=acc.dtype, device=acc.device)
+            shape = (P, rng[1] - rng[0], *acc.shape[2:])
+            buf = cache.get(("recv", src, shape)) if cache is not None else None
+            if buf is None:
+                buf = torch.empty(shape, dtype=acc.dtype, device=acc.device)
+                if cache is not None:
+                    cache[("recv", src, shape)] = buf
             recv_bufs[src] = (rng, buf)
-            ops.append(dist.P2POp(dist.irecv, buf, src if group is None else dist.get_global_rank(group, src), group))
+            for p in range(P):
+                ops.append(dist.P2POp(dist.irecv, buf[p], peer(src), group))
     for dst in range(world):
         rng = sends[rank][dst]
         if rng is not None:
-            buf = acc[:, rng[0]:rng[1]].contiguous()
-            send_bufs.append(buf)
-            ops.append(dist.P2POp(dist.isend, buf, dst if group is None else dist.get_global_rank(group, dst), group))
+            for p in range(P):
+                ops.append(dist.P2POp(dist.isend, acc[p, rng[0]:rng[1]], peer(dst), group))
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
     for src in sorted(recv_bufs):  # fixed (rank) order -> deterministic sums
         (z0, z1), buf = recv_bufs[src]
-        acc[:, z0:z1] += buf
+        if acc.is_cuda:
+            K.swi_add_partial(acc, z0, z1, buf)
+        else:   # CPU (gloo) tests of the exchange logic
+            acc[:, z0:z1] += buf
 
 
-def gather_label_slabs(lab: Optional[Tensor], slabs, vol_shape, rank: int, world: int, group, device) -> Tensor:
-    """all-gather of the per-rank uint8 label slabs (padded to the largest slab) into the full label volume."""
+def gather_label_slabs(lab: Optional[Tensor], slabs, vol_shape, rank: int, world: int, group, device,
+                       dst: Optional[int] = None) -> Optional[Tensor]:
+    """The per-rank uint8 label slabs -> the full label volume: on every rank (dst None: all-gather, slabs padded to
+    the largest) or on rank `dst` only (point-to-point sends of exactly the slab bytes; other ranks return None)."""
     import torch.distributed as dist
     VZ, VY, VX = vol_shape
-    zmax = max(z1 - z0 for z0, z1 in slabs)
-    mine = torch.zeros((zmax, VY, VX), dtype=torch.uint8, device=device)
     z0, z1 = slabs[rank]
+    if dst is not None:
+        peer = (lambda r: r) if group is None else (lambda r: dist.get_global_rank(group, r))
+        if rank != dst:
+            if z1 > z0:
+                for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, lab, peer(dst), group)]):
+                    w.wait()
+            return None
+        full = torch.empty((VZ, VY, VX), dtype=torch.uint8, device=device)
+        ops = [dist.P2POp(dist.irecv, full[a:b], peer(r), group) for r, (a, b) in enumerate(slabs) if r != dst and b > a]
+        if z1 > z0:
+            full[z0:z1].copy_(lab)
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return full
+    zmax = max(b - a for a, b in slabs)
+    mine = torch.zeros((zmax, VY, VX), dtype=torch.uint8, device=device)
     if z1 > z0:
         mine[:z1 - z0] = lab
     flat = torch.empty((world * zmax, VY, VX), dtype=torch.uint8, device=device)
@@ -394,26 +487,41 @@ def gather_label_slabs(lab: Optional[Tensor], slabs, vol_shape, rank: int, world
     return full
 
 
+def get_inferer(model, roi_size, overlap: float, mode: str, sigma_scale: float = 0.125,
+                engine_batch: Optional[int] = None) -> SlidingWindowInferer:
+    """The model's cached inferer for these settings.  The cache lives ON the model object (a plain attribute, not a
+    registered submodule), so it is collected with the model and never pins another model's buffers; at most four
+    settings are kept per model."""
+    cache = model.__dict__.setdefault("_mmseg_inferers", {})
+    key = (tuple(int(r) for r in roi_size), float(overlap), mode, float(sigma_scale), engine_batch)
+    inf = cache.get(key)
+    if inf is None:
+        if len(cache) >= 4:
+            cache.pop(next(iter(cache)))
+        inf = cache[key] = SlidingWindowInferer(model, roi_size, overlap, mode, sigma_scale, engine_batch=engine_batch)
+    return inf
+
+
 @torch.no_grad()
 def predict_volume(model, image_host: Tensor, roi_size=(96, 96, 96), overlap: float = 0.5, mode: str = "constant",
-                   engine_batch: int = 8, group=None, out_host: Optional[Tensor] = None) -> Tensor:
+                   engine_batch: Optional[int] = None, group=None, out_host: Optional[Tensor] = None,
+                   gather: str = "all") -> Optional[Tensor]:
     """Host-to-host inference of one volume — the arithmetic of Trainer.predict (reference trainer.py:357-367):
     image [C, H, W, D] fp32 in (pinned) host memory -> uint8 label map [H, W, D] in host memory.
 
     Every step is stream-ordered: H2D copy of the input range this rank needs, sliding-window accumulation, the
     sharded exchange when torch.distributed is initialised with more than one rank, finalize + argmax, D2H of labels.
-    """
+    gather (multi-rank only): "all" — every rank returns the full label map (all-gather + a full D2H per rank);
+    "rank0" — rank 0 returns the full map, the others None (one gather, one D2H: the cheap way to a complete result);
+    "slab" — every rank returns only its own axis-0 slab, copied into out_host[z0:z1] (no label collective)."""
     import torch.distributed as dist
     dev = next(model.parameters()).device
     if dev.type != "cuda":
         raise RuntimeError("predict_volume needs the model on a CUDA device (no CPU fallback)")
     assert image_host.dim() == 4 and image_host.dtype == torch.float32 and not image_host.is_cuda
-    key = (id(model), tuple(roi_size), overlap, mode, engine_batch)
-    inf = _INFERERS.get(key)
-    if inf is None:
-        inf = _INFERERS[key] = SlidingWindowInferer(model, roi_size, overlap, mode, engine_batch=engine_batch)
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
+    inf = get_inferer(model, roi_size, overlap, mode, engine_batch=engine_batch)
     vol = inf.device_volume(image_host.shape, dev)
     z0, z1 = inf.input_range(image_host.shape[1:], world, rank)
     # slab-wise upload on a copy stream: contiguous per-channel slabs (plain async H2D copies, no host staging), one
@@ -433,15 +541,26 @@ def predict_volume(model, image_host: Tensor, roi_size=(96, 96, 96), overlap: fl
             ev = torch.cuda.Event()
             ev.record(cs)
             ready.append((ze, ev))
+    VZ, VY, VX = image_host.shape[1:]
     if world > 1:
-        lab = inf.run_sharded(vol, group, ready=ready)
+        res = inf.run_sharded(vol, group, want=gather, ready=ready)
     else:
         inf.accumulate(vol, ready=ready)
-        lab = inf.finalize(normalize=False, labels=True)[1]
+        res = inf.finalize(normalize=False, labels=True)[1]
+        if gather == "slab":
+            res = (res, (0, VZ))
     main.wait_stream(cs)
+    if res is None:                       # gather == "rank0" on another rank
+        torch.cuda.current_stream().synchronize()
+        return None
     if out_host is None:
-        out_host = torch.empty(lab.shape, dtype=torch.uint8, pin_memory=True)
-    out_host.copy_(lab, non_blocking=True)
+        out_host = torch.empty((VZ, VY, VX), dtype=torch.uint8, pin_memory=True)
+    if gather == "slab":
+        lab, (a, b) = res
+        if b > a:
+            out_host[a:b].copy_(lab, non_blocking=True)
+    else:
+        out_host.copy_(res, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return out_host
 
@@ -458,16 +577,13 @@ def _pad_to_roi(inputs: Tensor, roi: Sequence[int], cval: float):
     return torch.nn.functional.pad(inputs, pad, mode="constant", value=cval), pad
 
 
-_INFERERS = {}
-
-
 def sliding_window_inference(inputs: Tensor, roi_size, sw_batch_size: int, predictor: Callable, overlap: float = 0.25,
                              mode: str = "constant", sigma_scale: float = 0.125, padding_mode: str = "constant",
                              cval: float = 0.0, **kwargs) -> Tensor:
     """Signature-compatible with monai.inferers.sliding_window_inference as called by the reference.
 
     `sw_batch_size` is accepted for compatibility; the engine picks its own batch (the result is independent of it).
-    """
+    Returns a FRESH tensor like MONAI does (the inferer's accumulator is reused by the next call)."""
     if not inputs.is_cuda:
         raise RuntimeError("mmseg_b200 sliding_window_inference runs on CUDA tensors only (no CPU fallback)")
     if padding_mode != "constant":
@@ -478,13 +594,8 @@ def sliding_window_inference(inputs: Tensor, roi_size, sw_batch_size: int, predi
     roi = [int(r) if r and r > 0 else int(s) for r, s in zip(roi_size, inputs.shape[2:])]
     orig = inputs.shape[2:]
     inputs, pad = _pad_to_roi(inputs.float(), roi, cval)
-    key = (id(predictor), tuple(roi), overlap, mode, sigma_scale)
-    inf = _INFERERS.get(key)
-    if inf is None:
-        inf = _INFERERS[key] = SlidingWindowInferer(predictor, roi, overlap, mode, sigma_scale)
-    outs = []
-    for b in range(inputs.shape[0]):
-        outs.append(inf(inputs[b:b + 1]).clone() if inputs.shape[0] > 1 else inf(inputs[b:b + 1]))
+    inf = get_inferer(predictor, roi, overlap, mode, sigma_scale)
+    outs = [inf(inputs[b:b + 1]).clone() for b in range(inputs.shape[0])]
     out = torch.cat(outs) if len(outs) > 1 else outs[0]
     if pad is not None:
         nsp = len(orig)
@@ -492,5 +603,5 @@ def sliding_window_inference(inputs: Tensor, roi_size, sw_batch_size: int, predi
         for k in range(nsp):
             before = pad[2 * (nsp - 1 - k)]
             crop.append(slice(before, before + orig[k]))
-        out = out[tuple(crop)]
+        out = out[tuple(crop)].contiguous()
     return out

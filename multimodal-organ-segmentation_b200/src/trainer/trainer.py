@@ -4,8 +4,10 @@
 Differences that are deliberate (documented in DESIGN.md):
   * mixed precision: the kernels compute in bf16 with fp32 accumulation, so `hardware.mixed_precision` needs neither
     autocast nor a GradScaler (reference: fp16 autocast + GradScaler, trainer.py:74-75,237-248);
-  * sliding-window inference honours `inference.sliding_window.mode` (the reference never passes it to MONAI, so its
-    YAML value "gaussian" is dead config and MONAI's default "constant" applies; set the key to "constant" for that);
+  * sliding-window blending follows the reference's BEHAVIOUR, not its dead config: the reference never passes
+    `inference.sliding_window.mode` to MONAI (trainer.py:386-392), so MONAI's default "constant" applies whatever the
+    YAML says — and so it does here.  Gaussian blending is opt-in through the new key
+    `inference.sliding_window.blend_mode: gaussian`;
   * data-parallel training: when torch.distributed is initialised, gradients are averaged with a bucketed all-reduce
     that overlaps the backward kernels (parallel.GradBucketReducer); the reference has no distributed path.
 """
@@ -16,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from ..models.build import load_checkpoint, save_checkpoint
-from .inference import sliding_window_inference
+from .inference import predict_volume, sliding_window_inference
 from .losses import get_loss
 from .metrics import DiceMetric, get_metrics
 from ...parallel import GradBucketReducer
@@ -246,17 +248,33 @@ class Trainer:
                 pred = self.predict_array(np.stack(images, axis=0))
                 nib.save(nib.Nifti1Image(pred, affine), str(output_path / f"{case_id}_pred.nii.gz"))
 
+    def _blend_mode(self) -> str:
+        """MONAI's default ("constant") unless the explicit key of this path asks for gaussian; the reference's own
+        `mode` key is never read, exactly as in the reference (trainer.py:386-392)."""
+        return self.config["inference"]["sliding_window"].get("blend_mode", "constant")
+
     def predict_array(self, image):
-        """[C, H, W, D] float32 numpy volume -> uint8 label map [H, W, D] (trainer.py:357-367 without the file I/O)."""
-        t = torch.from_numpy(image).unsqueeze(0).to(self.device)
-        output = self._sliding_window_inference(t)
-        return torch.argmax(output, dim=1).squeeze(0).to(torch.uint8).cpu().numpy()
+        """[C, H, W, D] float32 numpy volume -> uint8 label map [H, W, D] (trainer.py:357-367 without the file I/O).
+        Runs the fused path (inference.predict_volume): slab-wise upload, windows, ÷count + argmax fused in the finalize
+        kernel, uint8 labels back — the fp32 logits volume (2.5 GB at 512x512x300) is never materialised."""
+        import numpy as np
+        sw = self.config["inference"]["sliding_window"]
+        roi = tuple(int(r) for r in sw["roi_size"])
+        t = torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32))
+        if any(d < r for d, r in zip(t.shape[1:], roi)):
+            # smaller than the roi on some axis: MONAI pads symmetrically and crops (rare, tiny volumes)
+            output = self._sliding_window_inference(t.unsqueeze(0).to(self.device))
+            return torch.argmax(output, dim=1).squeeze(0).to(torch.uint8).cpu().numpy()
+        self.model.eval()
+        return predict_volume(self.model, t, roi, sw["overlap"], self._blend_mode()).numpy()
 
     def _sliding_window_inference(self, image: torch.Tensor) -> torch.Tensor:
+        """Full fp32 logits [1, K, H, W, D] like the reference's helper (trainer.py:370-395); predict() itself goes
+        through predict_array, which never builds them."""
         sw = self.config["inference"]["sliding_window"]
         return sliding_window_inference(image, roi_size=tuple(sw["roi_size"]),
                                         sw_batch_size=self.config["inference"].get("batch_size", 4),
-                                        predictor=self.model, overlap=sw["overlap"], mode=sw.get("mode", "constant"))
+                                        predictor=self.model, overlap=sw["overlap"], mode=self._blend_mode())
 
     def _save_checkpoints(self, metrics: Dict[str, float]) -> None:
         """last.pth / best.pth / epoch_N.pth under <output_dir>/<name> (reference trainer.py:397-433); rank 0 only."""

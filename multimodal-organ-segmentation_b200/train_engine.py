@@ -29,6 +29,7 @@ def _wrap(t: Tensor, n: int, channels: int, Z: int, Y: int, X: int) -> Blocked:
     b.n_img, b.channels, b.Z, b.Y, b.X = n, channels, Z, Y, X
     b.cb = b.cbt = channels // 8
     b.split, b.lo_off = False, 0
+    b.fmt, b.nm = _lib.FMT_BF16, None
     b.t = t
     return b
 

@@ -202,6 +202,20 @@ def pack_roundtrip_case():
         assert b.to_ncdhw(8, 8).abs().max().item() == 0.0
 
 
+# north_star gates: logits 2e-2 max-abs / 1e-3 relative L2, labels >= 99.9 % — asserted for every mode whose operands
+# carry >= 16 significant bits (parity = bf16x3, fp16x3).
+GATES = (2e-2, 1e-3, 0.999)
+# The single- and two-pass rungs of the ladder do NOT meet the gates on random-init nets (B200, 36-window bench crop:
+# bf16 7.7e-2 / 2.5e-2 / 97.9 %); what their tests assert is only that the result is finite and inside the noise class
+# of the operand format — sanity bounds, not parity claims.  bench.py reports the real figures per mode.
+NOISE_CLASS = {"bf16": (2e-1, 5e-2, 0.95), "fp16": (3e-2, 8e-3, 0.985), "fp16w2": (3e-2, 8e-3, 0.985),
+               "fp16a2": (3e-2, 8e-3, 0.985)}
+
+
+def mode_bounds(mode):
+    return GATES if mode in ("parity", "bf16x3", "fp16x3") else NOISE_CLASS[mode]
+
+
 def _metrics(got, ref):
     d = (got - ref).double()
     max_abs = d.abs().max().item()
@@ -226,7 +240,7 @@ def unet_case(features=(16, 32, 64), S=32, n_img=1, mode="parity", in_ch=2, seed
     print(f"[unet {features} S={S} n={n_img} mode={mode}] max_abs={max_abs:.3e} rel_l2={rel_l2:.3e} "
           f"label_agree={agree * 100:.4f}%", flush=True)
     if tol is None:
-        tol = (2e-2, 1e-3, 0.999) if mode == "parity" else (2e-1, 5e-2, 0.95)
+        tol = mode_bounds(mode)
     assert torch.isfinite(got).all()
     assert max_abs <= tol[0] and rel_l2 <= tol[1] and agree >= tol[2], (max_abs, rel_l2, agree)
     return max_abs, rel_l2, agree
@@ -382,10 +396,8 @@ def swi_case(vol_shape=(48, 40, 36), roi=(32, 32, 32), mode="gaussian", net="une
     agree_lab = (lab.long() == want.argmax(1)[0]).double().mean().item()
     print(f"[swi {vol_shape} roi={roi} {mode} {nmode}] max_abs={max_abs:.3e} rel_l2={rel_l2:.3e} "
           f"label_agree={agree * 100:.4f}% uint8_labels={agree_lab * 100:.4f}%", flush=True)
-    if nmode == "parity":
-        assert max_abs <= 2e-2 and rel_l2 <= 1e-3 and agree >= 0.999 and agree_lab >= 0.999
-    else:
-        assert rel_l2 <= 5e-2 and agree >= 0.95
+    b = mode_bounds(nmode)
+    assert max_abs <= b[0] and rel_l2 <= b[1] and agree >= b[2] and agree_lab >= b[2], (max_abs, rel_l2, agree, agree_lab)
 
 
 def swi_constant_predictor_case():
@@ -793,13 +805,65 @@ def trainer_end_to_end_case(tmp_dir):
     # predict_array: [C, H, W, D] numpy volume -> uint8 labels through the sliding-window engine
     vol = (torch.randn(2, 24, 20, 28, generator=g)).numpy().astype(np.float32)
     tr.model.set_numeric_mode("parity") if hasattr(tr.model, "set_numeric_mode") else None
-    pred = tr.predict_array(vol)
-    assert pred.shape == (24, 20, 28) and pred.dtype == np.uint8
     sd = {k: v.detach().cpu() for k, v in tr.model.state_dict().items()}
-    want = oswi(torch.from_numpy(vol)[None], (16, 16, 16), 2, lambda w: unet3d_forward(sd, w), overlap=0.5, mode="gaussian")
-    agree = (torch.from_numpy(pred.astype(np.int64)) == want.argmax(1)[0]).double().mean().item()
-    print(f"[trainer] losses {hist['train_loss']} val dice {hist['val_dice']} predict label agreement {agree * 100:.3f}%", flush=True)
-    assert agree >= 0.995
+    # the YAML key `mode` is dead config in the reference (never passed to MONAI, trainer.py:386-392): constant blending
+    # applies; gaussian is this path's explicit opt-in key `blend_mode`
+    for blend in ("constant", "gaussian"):
+        if blend == "gaussian":
+            cfg["inference"]["sliding_window"]["blend_mode"] = "gaussian"
+        pred = tr.predict_array(vol)
+        assert pred.shape == (24, 20, 28) and pred.dtype == np.uint8
+        want = oswi(torch.from_numpy(vol)[None], (16, 16, 16), 2, lambda w: unet3d_forward(sd, w), overlap=0.5, mode=blend)
+        agree = (torch.from_numpy(pred.astype(np.int64)) == want.argmax(1)[0]).double().mean().item()
+        print(f"[trainer] losses {hist['train_loss']} val dice {hist['val_dice']} predict ({blend}) label agreement "
+              f"{agree * 100:.3f}%", flush=True)
+        assert agree >= 0.995
+    # a volume smaller than the roi on one axis takes the padded route (MONAI pads symmetrically and crops)
+    small = vol[:, :12]
+    pred_s = tr.predict_array(small)
+    want_s = oswi(torch.from_numpy(small)[None], (16, 16, 16), 2, lambda w: unet3d_forward(sd, w), overlap=0.5, mode="gaussian")
+    assert pred_s.shape == (12, 20, 28)
+    assert (torch.from_numpy(pred_s.astype(np.int64)) == want_s.argmax(1)[0]).double().mean().item() >= 0.995
+
+
+def swi_weight_update_case():
+    """Captured sliding-window graphs must not outlive the weights they baked in: infer, change the
+    parameters IN PLACE (what optimizer.step / load_state_dict do), infer again with the same inferer and volume buffer,
+    and compare with a fresh model that was built with the new weights.  Also: the public API returns a fresh tensor
+    (a second call must not overwrite the first result)."""
+    from mmseg_b200.src.models.backbones.unet import UNet3D
+    from mmseg_b200.src.trainer.inference import predict_volume, sliding_window_inference
+    torch.manual_seed(0)
+    m = UNet3D(2, 4, [16, 32]).to(DEV).eval()
+    g = torch.Generator().manual_seed(11)
+    vol = torch.randn(2, 40, 32, 48, generator=g).pin_memory()
+    roi = (16, 16, 16)
+    lab1 = predict_volume(m, vol, roi, 0.5, "gaussian", engine_batch=4).clone()
+    lab1b = predict_volume(m, vol, roi, 0.5, "gaussian", engine_batch=4).clone()     # replay of the captured graphs
+    assert torch.equal(lab1, lab1b)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(torch.randn(p.shape, generator=torch.Generator().manual_seed(p.numel())).to(DEV) * p.abs().mean())
+    lab2 = predict_volume(m, vol, roi, 0.5, "gaussian", engine_batch=4).clone()
+    fresh = UNet3D(2, 4, [16, 32]).to(DEV).eval()
+    fresh.load_state_dict(m.state_dict())
+    lab3 = predict_volume(fresh, vol, roi, 0.5, "gaussian", engine_batch=4)
+    changed = (lab2 != lab1).double().mean().item()
+    assert torch.equal(lab2, lab3), "stale captured weights after an in-place parameter update"
+    assert changed > 0.05, f"the perturbation should change the labels (changed {changed:.3f})"
+    # load_state_dict (copy_ into the same storage) is caught the same way
+    m.load_state_dict({k: v.clone() for k, v in UNet3D(2, 4, [16, 32]).state_dict().items()})
+    fresh.load_state_dict(m.state_dict())
+    assert torch.equal(predict_volume(m, vol, roi, 0.5, "gaussian", engine_batch=4),
+                       predict_volume(fresh, vol, roi, 0.5, "gaussian", engine_batch=4))
+    # public API: fresh output tensors
+    x = vol.to(DEV)[None]
+    o1 = sliding_window_inference(x, roi, 4, m, overlap=0.5, mode="gaussian")
+    keep = o1.clone()
+    o2 = sliding_window_inference(x * 0.5, roi, 4, m, overlap=0.5, mode="gaussian")
+    assert o1.data_ptr() != o2.data_ptr() and torch.equal(o1, keep)
+    print(f"[swi weight update] graphs recaptured after in-place updates ({changed * 100:.1f}% labels changed); "
+          "public API returns fresh tensors", flush=True)
 
 
 def convblock_gelu_group_golden_case(mode="parity"):

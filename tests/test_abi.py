@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 
 def test_version_and_error_channel():
-    assert _lib.lib.mmseg_version() == 1
+    assert _lib.lib.mmseg_version() == 2
     # a rejected call returns a negative status and sets the thread-local message; nothing is launched
     a = _lib.ConvArgs()
     a.ksize = 5

@@ -131,14 +131,23 @@ def test_predict_volume_host_to_host():
     _c().predict_volume_case()
 
 
+def test_sliding_window_graphs_follow_weight_updates():
+    _c().swi_weight_update_case()
+
+
 def test_pack_unpack_roundtrip():
     _c().pack_roundtrip_case()
 
 
 @pytest.mark.parametrize("features,S,n,mode", [((16, 32, 64), 32, 1, "parity"), ((16, 32, 64), 32, 2, "bf16"),
+                                                ((16, 32, 64), 32, 2, "fp16"), ((16, 32, 64), 32, 1, "fp16w2"),
+                                                ((16, 32, 64), 32, 1, "fp16a2"), ((16, 32, 64), 32, 2, "fp16x3"),
                                                 ((32, 64, 128, 256, 512), 96, 1, "parity"),
+                                                ((32, 64, 128, 256, 512), 96, 1, "fp16"),
                                                 ((32, 64, 128, 256, 512), 96, 1, "bf16")])
 def test_unet3d_vs_oracle(features, S, n, mode):
+    """Every rung of the numeric-mode ladder (numerics.py): the >= 16-bit modes against the north_star gates, the
+    faster rungs against the noise class of their operand format (gpu_cases.NOISE_CLASS)."""
     _c().unet_case(features, S, n, mode)
 
 
@@ -162,7 +171,8 @@ def test_swi_blend_finalize_exact():
 
 
 @pytest.mark.parametrize("kw", [dict(mode="gaussian"), dict(mode="constant"), dict(vol_shape=(33, 64, 40), overlap=0.25),
-                                dict(nmode="bf16"), dict(net="dual"), dict(vol_shape=(50, 41, 70), mode="gaussian")])
+                                dict(nmode="bf16"), dict(nmode="fp16"), dict(net="dual"), dict(net="dual", nmode="fp16"),
+                                dict(vol_shape=(50, 41, 70), mode="gaussian")])
 def test_sliding_window_vs_oracle(kw):
     _c().swi_case(**kw)
 
