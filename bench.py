@@ -104,7 +104,7 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------------ CPU legs
 REF_CROP = (192, 192, 144)     # exactly 18 windows (3 x 3 x 2): one step of the reference arm (>= 18)
-HEADLINE_DEFAULT = "parity"    # fastest mode that met all four north_star gates on B200 (see `ladder` in the bench line)
+HEADLINE_DEFAULT = "fp16m"     # fastest mode that met all four north_star gates on B200 (see `parity` in the bench line)
 
 
 def plain_unet_state_dict(features=FEATURES, cin=2, cout=8):
@@ -310,9 +310,6 @@ def run_ours(args):
             log(f"[ladder] {mode}: " + json.dumps(ladder[mode]))
         del crop_dev
         torch.cuda.empty_cache()
-        if args.mode == "auto":
-            passing = [m for m in LADDER if ladder[m]["passes_gates"]]
-            headline = passing[0] if passing else HEADLINE_DEFAULT   # LADDER is ordered fastest first
 
     # ---- throughput of every rung at N=1 (short), then the headline mode with the requested steps
     def measure_mode(mode, steps, warmup, with_e2e):
@@ -343,8 +340,6 @@ def run_ours(args):
 
     if world == 1 and not args.no_ladder:
         for mode in LADDER:
-            if mode == headline:
-                continue
             r = measure_mode(mode, 2, 1, with_e2e=True)
             ladder.setdefault(mode, {"dtype": MODES[mode].bench_dtype, "mma_passes": MODES[mode].passes})
             ladder[mode].update({"ms_per_step": r["ms_per_step"], "value": r["value"],
@@ -354,6 +349,10 @@ def run_ours(args):
             del r
             model.__dict__.pop("_mmseg_inferers", None)
             torch.cuda.empty_cache()
+        if args.mode == "auto" and ladder and all("passes_gates" in v for v in ladder.values()):
+            passing = [m for m in LADDER if ladder[m]["passes_gates"]]
+            if passing:   # the headline rule: the fastest (measured) mode among those that meet every gate
+                headline = min(passing, key=lambda m: ladder[m]["ms_per_step"])
 
     sampler = ClockSampler(local)
     sampler.start()

@@ -79,8 +79,8 @@ class ConvRunner:
         a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], pw.nm or self.split)
         n, Z, Y, X = src.n_img, src.Z, src.Y, src.X
         cout = pw.n_out
-        raw_f32 = self.nm.raw_f32
-        raw = self.ws.get("raw", n * cout * Z * Y * X, torch.float32 if raw_f32 else self.nm.dtype)
+        raw_f32 = (pw.nm or self.nm).raw_f32    # per layer in the mixed modes
+        raw = self.ws.get("raw32" if raw_f32 else "raw16", n * cout * Z * Y * X, torch.float32 if raw_f32 else self.nm.dtype)
         tile = K.plan_conv_norm((X, Y, Z), n, pw, raw_f32, a_cb)
         kind = norm_kind(norm)
         out_mode = _lib.OUT_BLOCKED_F32 if raw_f32 else _lib.OUT_BLOCKED_BF16
@@ -149,7 +149,7 @@ class ConvRunner:
     def conv_act(self, src: Blocked, segs, pw: PackedConv, dst: Blocked, dst_c0: int = 0) -> None:
         """conv + bias straight to an activation buffer (no norm): 1x1 fusion projections."""
         a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], pw.nm or self.split)
-        K.conv3d(src, pw, a_cb, dst.t, _lib.OUT_BLOCKED_BF16_HILO if self.nm.a_split else _lib.OUT_BLOCKED_BF16,
+        K.conv3d(src, pw, a_cb, dst.t, _lib.OUT_BLOCKED_BF16_HILO if dst.split else _lib.OUT_BLOCKED_BF16,
                  dst_cbt=dst.cbt, dst_cb_off=dst_c0 // 8, dst_lo_off=dst.lo_off)
         self.launches += 1
 
@@ -212,23 +212,30 @@ class UNet3DEngine:
 
         self._norms: Dict[str, object] = {}
 
-        def block(name: str, blk, segs1, level: int):
+        L = len(f)
+        bsplit = lambda buf: nm.buffer(buf).a_split     # is that activation buffer stored hi + lo?
+
+        def block(name: str, blk, segs1, tag: str, src1: str, src2: str):
             # bias of a conv that feeds InstanceNorm(affine=False) is cancelled exactly by the mean subtraction; every
             # other norm option (batch / group / none, model.backbone.norm) keeps it
             inst = isinstance(blk.norm1, torch.nn.InstanceNorm3d)
-            sp = nm.for_layer(level)      # mixed modes split the weights only on the cheap (deep) levels
-            P[name + ".conv1"] = K.pack_conv_weight(blk.conv1.weight, None if inst else blk.conv1.bias, sp, segs1, use_bias=not inst)
-            P[name + ".conv2"] = K.pack_conv_weight(blk.conv2.weight, None if inst else blk.conv2.bias, sp, None, use_bias=not inst)
+            # mixed modes: the layer's passes follow its input buffer (activation split) and its tag (weight split)
+            P[name + ".conv1"] = K.pack_conv_weight(blk.conv1.weight, None if inst else blk.conv1.bias,
+                                                    nm.layer(tag + ".1", bsplit(src1)), segs1, use_bias=not inst)
+            P[name + ".conv2"] = K.pack_conv_weight(blk.conv2.weight, None if inst else blk.conv2.bias,
+                                                    nm.layer(tag + ".2", bsplit(src2)), None, use_bias=not inst)
             self._norms[name + ".conv1"], self._norms[name + ".conv2"] = blk.norm1, blk.norm2
 
-        block("init_conv", m.init_conv, [m.in_channels], 0)
+        block("init_conv", m.init_conv, [m.in_channels], "enc0", "in", "mid0")
         for i, enc in enumerate(m.encoders):
-            block(f"encoders.{i}", enc.conv, [f[i]], i + 1)
+            block(f"encoders.{i}", enc.conv, [f[i]], f"enc{i + 1}", f"pool{i + 1}", f"mid{i + 1}")
         for j, dec in enumerate(m.decoders):
-            lvl = len(f) - 2 - j
-            P[f"decoders.{j}.up"] = K.pack_conv_weight(dec.up.weight, dec.up.bias, nm.for_layer(lvl + 1, True), None, transposed=True)
-            block(f"decoders.{j}", dec.conv, [f[lvl], f[lvl]], lvl)
-        P["out_conv"] = K.pack_conv_weight(m.out_conv.weight, m.out_conv.bias, nm.for_layer(0), None)
+            lvl = L - 2 - j
+            up_src = "bott" if j == 0 else f"dec{lvl + 1}"
+            P[f"decoders.{j}.up"] = K.pack_conv_weight(dec.up.weight, dec.up.bias, nm.layer("up", bsplit(up_src)), None,
+                                                       transposed=True)
+            block(f"decoders.{j}", dec.conv, [f[lvl], f[lvl]], f"dec{lvl}", f"cat{lvl}", f"mid{lvl}")
+        P["out_conv"] = K.pack_conv_weight(m.out_conv.weight, m.out_conv.bias, nm.layer("up", bsplit("dec0")), None)
         self._packed, self._packed_version = P, ver
         return P
 
@@ -244,19 +251,19 @@ class UNet3DEngine:
             raise NotImplementedError(
                 f"spatial size {(Z, Y, X)} is not divisible by {1 << (L - 1)}: the trilinear resize branch of "
                 "UpBlock3D (reference unet.py:108-109) is not implemented in the sm_100a path")
-        sp = self.split
-        b = {"in": Blocked(n, (self.module.in_channels + 15) // 16 * 16, Z, Y, X, sp, device)}
+        sp = self.nm.buffer          # per-buffer storage mode (hi-only vs hi + lo; mixed modes differ per buffer)
+        b = {"in": Blocked(n, (self.module.in_channels + 15) // 16 * 16, Z, Y, X, sp("in"), device)}
         b["in"].t.zero_()   # the sliding-window gather writes only the blocks with real channels
         for l in range(L):
             z, y, x = Z >> l, Y >> l, X >> l
-            b[f"mid{l}"] = Blocked(n, f[l], z, y, x, sp, device)            # ConvBlock3D conv1 output
+            b[f"mid{l}"] = Blocked(n, f[l], z, y, x, sp(f"mid{l}"), device)            # ConvBlock3D conv1 output
             if l < L - 1:
-                b[f"cat{l}"] = Blocked(n, 2 * f[l], z, y, x, sp, device)     # [up | skip]
-                b[f"dec{l}"] = Blocked(n, f[l], z, y, x, sp, device)         # decoder block output
+                b[f"cat{l}"] = Blocked(n, 2 * f[l], z, y, x, sp(f"cat{l}"), device)     # [up | skip]
+                b[f"dec{l}"] = Blocked(n, f[l], z, y, x, sp(f"dec{l}"), device)         # decoder block output
             else:
-                b[f"bott"] = Blocked(n, f[l], z, y, x, sp, device)
+                b[f"bott"] = Blocked(n, f[l], z, y, x, sp("bott"), device)
             if l > 0:
-                b[f"pool{l}"] = Blocked(n, f[l - 1], z, y, x, sp, device)    # MaxPool3d(2) of level l-1
+                b[f"pool{l}"] = Blocked(n, f[l - 1], z, y, x, sp(f"pool{l}"), device)    # MaxPool3d(2) of level l-1
         self._bufs[key] = b
         return b
 
@@ -367,23 +374,26 @@ class DualEncoderEngine:
         f, nm, M = m.features, self.nm, m.num_modalities
         P: Dict[str, PackedConv] = {}
 
-        def block(name, blk, segs1, level):
-            sp = nm.for_layer(level)
-            P[name + ".conv1"] = K.pack_conv_weight(blk.conv1.weight, None, sp, segs1, use_bias=False)
-            P[name + ".conv2"] = K.pack_conv_weight(blk.conv2.weight, None, sp, None, use_bias=False)
+        L = len(f)
+        bsplit = lambda buf: nm.buffer(buf).a_split
+
+        def block(name, blk, segs1, tag, src1, src2):
+            P[name + ".conv1"] = K.pack_conv_weight(blk.conv1.weight, None, nm.layer(tag + ".1", bsplit(src1)), segs1, use_bias=False)
+            P[name + ".conv2"] = K.pack_conv_weight(blk.conv2.weight, None, nm.layer(tag + ".2", bsplit(src2)), None, use_bias=False)
 
         for i, enc in enumerate(m.encoders):
-            block(f"enc{i}.init", enc["init_conv"], [m.in_channels_per_modality], 0)
+            block(f"enc{i}.init", enc["init_conv"], [m.in_channels_per_modality], "enc0", "in", "mid0")
             for l, blk in enumerate(enc["blocks"]):
-                block(f"enc{i}.blocks.{l}", blk.conv, [f[l]], l + 1)
+                block(f"enc{i}.blocks.{l}", blk.conv, [f[l]], f"enc{l + 1}", f"pool{l + 1}", f"mid{l + 1}")
         if m.fusion_type == "concat":
             for l, proj in enumerate(m.fusion_proj):
-                P[f"fusion_proj.{l}"] = K.pack_conv_weight(proj.weight, proj.bias, nm.for_layer(l, True), [f[l]] * M)
+                P[f"fusion_proj.{l}"] = K.pack_conv_weight(proj.weight, proj.bias, nm.layer("up", bsplit(f"stack{l}")), [f[l]] * M)
         for j, dec in enumerate(m.decoder):
-            lvl = len(f) - 2 - j
-            P[f"decoder.{j}.up"] = K.pack_conv_weight(dec.up.weight, dec.up.bias, nm.for_layer(lvl + 1, True), None, transposed=True)
-            block(f"decoder.{j}", dec.conv, [f[lvl], f[lvl]], lvl)
-        P["out_conv"] = K.pack_conv_weight(m.out_conv.weight, m.out_conv.bias, nm.for_layer(0), None)
+            lvl = L - 2 - j
+            up_src = "bott" if j == 0 else f"dec{lvl + 1}"
+            P[f"decoder.{j}.up"] = K.pack_conv_weight(dec.up.weight, dec.up.bias, nm.layer("up", bsplit(up_src)), None, transposed=True)
+            block(f"decoder.{j}", dec.conv, [f[lvl], f[lvl]], f"dec{lvl}", f"cat{lvl}", f"mid{lvl}")
+        P["out_conv"] = K.pack_conv_weight(m.out_conv.weight, m.out_conv.bias, nm.layer("up", bsplit("dec0")), None)
         self._packed, self._packed_version = P, ver
         return P
 
@@ -393,25 +403,25 @@ class DualEncoderEngine:
         if b is not None:
             return b
         m = self.module
-        f, L, M, sp = m.features, len(m.features), m.num_modalities, self.split
+        f, L, M, sp = m.features, len(m.features), m.num_modalities, self.nm.buffer
         if any(d % (1 << (L - 1)) for d in (Z, Y, X)):
             raise NotImplementedError(f"spatial size {(Z, Y, X)} is not divisible by {1 << (L - 1)} (trilinear resize "
                                       "branch of UpBlock3D, reference unet.py:108-109, is not implemented)")
         b = {}
         for i in range(M):   # one input buffer per modality (zeroed once: gathers / packs only write the real channels' blocks)
-            b[f"in{i}"] = Blocked(n, (m.in_channels_per_modality + 15) // 16 * 16, Z, Y, X, sp, device)
+            b[f"in{i}"] = Blocked(n, (m.in_channels_per_modality + 15) // 16 * 16, Z, Y, X, sp("in"), device)
             b[f"in{i}"].t.zero_()
         for l in range(L):
             z, y, x = Z >> l, Y >> l, X >> l
-            b[f"mid{l}"] = Blocked(n, f[l], z, y, x, sp, device)
-            b[f"stack{l}"] = Blocked(n, M * f[l], z, y, x, sp, device)       # every modality's level-l output
+            b[f"mid{l}"] = Blocked(n, f[l], z, y, x, sp(f"mid{l}"), device)
+            b[f"stack{l}"] = Blocked(n, M * f[l], z, y, x, sp(f"stack{l}"), device)       # every modality's level-l output
             if l < L - 1:
-                b[f"cat{l}"] = Blocked(n, 2 * f[l], z, y, x, sp, device)     # [up | fused skip]
-                b[f"dec{l}"] = Blocked(n, f[l], z, y, x, sp, device)
+                b[f"cat{l}"] = Blocked(n, 2 * f[l], z, y, x, sp(f"cat{l}"), device)     # [up | fused skip]
+                b[f"dec{l}"] = Blocked(n, f[l], z, y, x, sp(f"dec{l}"), device)
             else:
-                b["bott"] = Blocked(n, f[l], z, y, x, sp, device)
+                b["bott"] = Blocked(n, f[l], z, y, x, sp("bott"), device)
             if l > 0:
-                b[f"pool{l}"] = Blocked(n, f[l - 1], z, y, x, sp, device)
+                b[f"pool{l}"] = Blocked(n, f[l - 1], z, y, x, sp(f"pool{l}"), device)
         self._bufs[key] = b
         return b
 

@@ -14,9 +14,11 @@ from ....train_engine import TrainEngine, train_forward
 from .... import kernels as K
 from .... import _lib
 from ....kernels import Blocked
-from ....numerics import MODES, mode as numeric_mode
+from ....numerics import DEFAULT_INFERENCE_MODE, MODES, mode as numeric_mode
 
-_DEFAULT_MODE = "bf16"
+# numeric mode of the INFERENCE path (numerics.py): the fastest rung of the ladder that meets north_star's gates.  The
+# training path (TrainEngine) always computes in bf16 (north_star: bf16 training step), whatever this says.
+_DEFAULT_MODE = DEFAULT_INFERENCE_MODE
 
 
 def _require_cuda(x: torch.Tensor) -> None:
@@ -45,9 +47,6 @@ def _train_step_forward(model: nn.Module, kind: str, x: torch.Tensor) -> torch.T
     if blk is not None and getattr(blk, "norm_type", "instance") != "instance":
         raise NotImplementedError(f"training with model.backbone.norm={blk.norm_type!r} is not built: the backward kernels "
                                   "cover InstanceNorm3d (the reference's default); batch / group / no norm are inference-only")
-    if model.numeric_mode != "bf16":
-        raise NotImplementedError("the backward path runs in bf16 mode (north_star: bf16 training step); call "
-                                  "set_numeric_mode('bf16') before training")
     eng = model.__dict__.get("_train_engine")
     if eng is None:
         eng = model.__dict__["_train_engine"] = TrainEngine(model, kind)
@@ -228,8 +227,9 @@ class UNet3D(nn.Module):
         self._engines: Dict[str, UNet3DEngine] = {}
 
     def set_numeric_mode(self, mode: str) -> "UNet3D":
-        """'bf16' (throughput), 'parity' (3-pass split-bf16; meets the stated logit / label tolerances) or another rung
-        of the ladder in numerics.py ('fp16', 'fp16w2', 'fp16a2', 'fp16x3')."""
+        """Inference numeric mode, a rung of the ladder in numerics.py: 'fp16m' (default: fastest mode that meets the
+        stated logit / label tolerances), 'bf16' / 'fp16' (single pass, fastest), 'parity' (3-pass split-bf16, ~5e-5),
+        'fp16w2', 'fp16a2', 'fp16x3'.  Training always runs the bf16 kernels."""
         self.numeric_mode = numeric_mode(mode).name
         return self
 

@@ -142,7 +142,9 @@ def test_pack_unpack_roundtrip():
 @pytest.mark.parametrize("features,S,n,mode", [((16, 32, 64), 32, 1, "parity"), ((16, 32, 64), 32, 2, "bf16"),
                                                 ((16, 32, 64), 32, 2, "fp16"), ((16, 32, 64), 32, 1, "fp16w2"),
                                                 ((16, 32, 64), 32, 1, "fp16a2"), ((16, 32, 64), 32, 2, "fp16x3"),
+                                                ((16, 32, 64), 32, 2, "fp16m"),
                                                 ((32, 64, 128, 256, 512), 96, 1, "parity"),
+                                                ((32, 64, 128, 256, 512), 96, 1, "fp16m"),
                                                 ((32, 64, 128, 256, 512), 96, 1, "fp16"),
                                                 ((32, 64, 128, 256, 512), 96, 1, "bf16")])
 def test_unet3d_vs_oracle(features, S, n, mode):
@@ -171,7 +173,8 @@ def test_swi_blend_finalize_exact():
 
 
 @pytest.mark.parametrize("kw", [dict(mode="gaussian"), dict(mode="constant"), dict(vol_shape=(33, 64, 40), overlap=0.25),
-                                dict(nmode="bf16"), dict(nmode="fp16"), dict(net="dual"), dict(net="dual", nmode="fp16"),
+                                dict(nmode="bf16"), dict(nmode="fp16"), dict(nmode="fp16m"), dict(net="dual"),
+                                dict(net="dual", nmode="fp16"), dict(net="dual", nmode="fp16m"),
                                 dict(vol_shape=(50, 41, 70), mode="gaussian")])
 def test_sliding_window_vs_oracle(kw):
     _c().swi_case(**kw)

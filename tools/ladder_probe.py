@@ -1,6 +1,8 @@
-"""Parity / throughput probe of mixed numeric modes: python tools/ladder_probe.py [levels ...]
-For every w_split_min_level L (weights split on ConvTranspose + levels >= L; activations split everywhere) prints the
-four north_star gate metrics on the 36-window bench crop and the full-volume time.  CPU reference = bench.cpu_predictor."""
+"""Parity / throughput probe of mixed numeric modes: python tools/ladder_probe.py [policy ...]
+policy = "A:<bufs>/W:<tags>/R:<tags>" ('+'-joined; "*" = all, "" = none): activation buffers stored hi + lo (in, mid0,
+cat0, dec0, pool1, ... bott), conv tags whose weights are split (enc0, enc0.1, dec0, up, ...), conv tags whose raw
+output stays fp32.  Prints the four north_star gate metrics on the 36-window bench crop and the full-volume time.
+CPU reference = bench.cpu_predictor."""
 import json
 import os
 import sys
@@ -14,7 +16,7 @@ from mmseg_b200.numerics import MODES, NumericMode
 from mmseg_b200.src.models.build import build_model
 from mmseg_b200.src.trainer.inference import SlidingWindowInferer
 
-levels = [int(a) for a in sys.argv[1:]] or [1, 2, 3, 4, 5]
+policies = sys.argv[1:] or ["A:*/W:enc0/R:*"]
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 model = build_model(bench.model_config("cuda")).eval()
@@ -26,9 +28,15 @@ print(f"cpu {kind}: {t:.1f} s for {n_win} windows", flush=True)
 crop_dev = vol_host[:, :bench.CROP[0], :bench.CROP[1], :bench.CROP[2]].contiguous().to(dev)
 vol_dev = vol_host.to(dev)
 names = []
-for L in levels:
-    name = f"fp16m_L{L}"
-    MODES[name] = NumericMode(name, _lib.FMT_FP16, True, False, True, L)
+def _set(spec):
+    return None if spec == "*" else frozenset(t for t in spec.split("+") if t)
+
+
+for pol in policies:
+    parts = dict(p.split(":", 1) for p in pol.split("/"))
+    A, W, R = _set(parts.get("A", "*")), _set(parts.get("W", "")), _set(parts.get("R", "*"))
+    name = f"fp16m[{pol}]"
+    MODES[name] = NumericMode(name, _lib.FMT_FP16, A is None, W is None, R is None, A, W, R)
     names.append(name)
 extra = os.environ.get("PROBE_EXTRA", "fp16a2,parity").split(",")
 for name in names + [e for e in extra if e]:
