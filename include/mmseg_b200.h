@@ -95,8 +95,9 @@ typedef struct {
   int32_t dst_cbt, dst_cb_off, dst_lo_off; /* blocked destinations: blocks per image, first block, lo-plane offset */
   int32_t flags;         /* bit0: debug — swap LBO/SBO in the smem descriptors; MMSEG_CONV_ROLL_Z (16): run the
                             rolling-accumulator kernel — TZ is then the z-SEGMENT length of a (TX x TY) column
-                            (needs ksize 3, NT = C_out = 32, one 128-row M tile per plane, blocked bf16 output, no
-                            bias, all K-chunk weights resident in shared memory; see conv_tc.cu)              */
+                            (needs ksize 3, NT = C_out = 32, one 128-row M tile per plane, blocked 16-bit or fp32
+                            raw output, no bias, all K-chunk weights resident in shared memory; see conv_tc.cu);
+                            MMSEG_CONV_FP16 (64): fp16 instead of bf16 elements                               */
   int16_t a_cb[MMSEG_MAX_KCHUNKS]; /* first channel block (of 2) in src for each K chunk              */
 } mmseg_conv_args;
 

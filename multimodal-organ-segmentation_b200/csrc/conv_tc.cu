@@ -672,7 +672,9 @@ static_assert(sizeof(RollHeader) <= kRollHeaderBytes, "roll header too large");
 // per-plane epilogue (~700 cycles) was slower than a plane's MMAs for C_in <= 32)
 constexpr int kRollThreads = 320;
 
-template <bool FP16>
+// F32OUT: raw output blocked fp32 (MMSEG_OUT_BLOCKED_F32: the modes that keep the InstanceNorm input in fp32) instead of
+// the 16-bit element format.
+template <bool FP16, bool F32OUT>
 __global__ void __launch_bounds__(kRollThreads, 1)
 conv3d_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ ConvKParams p) {
   constexpr int KT = 3;
@@ -905,8 +907,9 @@ conv3d_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int x0 = tx * p.TX, y0 = ty * p.TY, zs0 = zs * ZS;
       const int zsv = min(ZS, p.Z - zs0);
       const bool ok = (xx < p.TX) && (yy < p.TY) && (x0 + xx < p.X) && (y0 + yy < p.Y);
-      __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(p.dst) +
-                           ((size_t)(img * p.dst_cbt + p.dst_cb_off + 2 * cg) * nvox + (size_t)zs0 * plane + (size_t)(y0 + yy) * p.X + (x0 + xx)) * 8;
+      constexpr size_t ES = F32OUT ? 4 : 2;
+      char* row = reinterpret_cast<char*>(p.dst) +
+                  ((size_t)(img * p.dst_cbt + p.dst_cb_off + 2 * cg) * nvox + (size_t)zs0 * plane + (size_t)(y0 + yy) * p.X + (x0 + xx)) * 8 * ES;
       float s1[16], s2[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
@@ -940,9 +943,18 @@ conv3d_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
             for (int i = 0; i < 16; ++i) { s1[i] += va[i]; s2[i] = fmaf(va[i], va[i], s2[i]); }
           }
-          __nv_bfloat16* o = row + (size_t)zo * plane * 8;
-          *reinterpret_cast<uint4*>(o) = cvt8_from_f32(va, fp16);
-          *reinterpret_cast<uint4*>(o + nvox * 8) = cvt8_from_f32(va + 8, fp16);
+          char* o = row + (size_t)zo * plane * 8 * ES;
+          if constexpr (F32OUT) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float4* d = reinterpret_cast<float4*>(o + (size_t)h * nvox * 8 * ES);
+              d[0] = make_float4(va[8 * h + 0], va[8 * h + 1], va[8 * h + 2], va[8 * h + 3]);
+              d[1] = make_float4(va[8 * h + 4], va[8 * h + 5], va[8 * h + 6], va[8 * h + 7]);
+            }
+          } else {
+            *reinterpret_cast<uint4*>(o) = cvt8_from_f32(va, fp16);
+            *reinterpret_cast<uint4*>(o + nvox * 8 * ES) = cvt8_from_f32(va + 8, fp16);
+          }
         }
       }
       if (prev_slot >= 0) {
@@ -1047,8 +1059,9 @@ static int plan_conv(const mmseg_conv_args* a, ConvPlan* out) {
   k.mt = (flat + 127) / 128;
   k.roll = (a->flags & MMSEG_CONV_ROLL_Z) ? 1 : 0;
   if (k.roll) {
-    if (a->ksize != 3 || a->out_mode != MMSEG_OUT_BLOCKED_BF16 || a->n_ntiles != 1 || a->NT != 32 || a->dst_lo_off != 0 || a->bias)
-      return fail(MMSEG_ERR_UNSUPPORTED, "conv3d: rolling-z needs ksize 3, NT = C_out = 32, blocked bf16 output, no bias");
+    if (a->ksize != 3 || (a->out_mode != MMSEG_OUT_BLOCKED_BF16 && a->out_mode != MMSEG_OUT_BLOCKED_F32) || a->n_ntiles != 1 ||
+        a->NT != 32 || a->dst_lo_off != 0 || a->bias)
+      return fail(MMSEG_ERR_UNSUPPORTED, "conv3d: rolling-z needs ksize 3, NT = C_out = 32, blocked 16-bit or fp32 raw output, no bias");
     if (k.mt != 1) return fail(MMSEG_ERR_INVALID_ARG, "conv3d: rolling-z needs one M tile per plane (got %d)", k.mt);
   }
   const int n_acc = k.roll ? 512 / a->NT : (a->ksize == 1 ? k.mt : k.mt * a->TZ);
@@ -1171,16 +1184,19 @@ extern "C" int mmseg_conv3d_fwd(const mmseg_conv_args* a, void* stream) {
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sms <= 0) n_sms = 148;
   }
   if (k.roll) {
+    typedef void (*RollFn)(const CUtensorMap, const ConvKParams);
+    static const RollFn roll_fns[2][2] = {{conv3d_roll_kernel<false, false>, conv3d_roll_kernel<false, true>},
+                                          {conv3d_roll_kernel<true, false>, conv3d_roll_kernel<true, true>}};
     static bool roll_attr = false;
     if (!roll_attr) {
-      cudaError_t e = cudaFuncSetAttribute(conv3d_roll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3d_roll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) return fail(MMSEG_ERR_CUDA, "conv3d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      for (int i = 0; i < 4; ++i) {
+        cudaError_t e = cudaFuncSetAttribute(roll_fns[i >> 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return fail(MMSEG_ERR_CUDA, "conv3d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      }
       roll_attr = true;
     }
     const int n_ctas = k.n_tiles < n_sms ? k.n_tiles : n_sms;
-    if (k.fp16) conv3d_roll_kernel<true><<<n_ctas, kRollThreads, pl.smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tm, k);
-    else conv3d_roll_kernel<false><<<n_ctas, kRollThreads, pl.smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tm, k);
+    roll_fns[k.fp16][a->out_mode == MMSEG_OUT_BLOCKED_F32 ? 1 : 0]<<<n_ctas, kRollThreads, pl.smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tm, k);
     return check_launch("conv3d_roll_kernel");
   }
   // persistent CTAs: about one per SM in total, each sweeping its share of the voxel tiles of one N tile

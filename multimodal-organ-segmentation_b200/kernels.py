@@ -210,7 +210,7 @@ def plan_conv_norm(src_dims, n_img: int, pw: "PackedConv", raw_f32: bool, a_cb: 
     X, Y, Z = src_dims
     # measured on B200 (96^3 x 8 windows): C_in 64: 0.639 vs 0.704 ms, C_in 32: 0.364 vs 0.371 ms, C_in <= 16 (one K chunk
     # per plane, the issue loop's per-plane work is not amortised): 0.227 vs 0.220 ms -> rolling-z from two K chunks up
-    if (pw.ksize == 3 and pw.n_out == 32 and pw.NT == 32 and pw.bias is None and not raw_f32 and pw.n_kchunks >= 2
+    if (pw.ksize == 3 and pw.n_out == 32 and pw.NT == 32 and pw.bias is None and pw.n_kchunks >= 2
             and os.environ.get("MMSEG_NO_ROLL", "0") != "1"):
         # two adjacent K chunks per TMA stage when the channel blocks allow it (half the stage operations of the issue lane)
         kpb = 1

@@ -41,14 +41,22 @@ def _make_tile(pw, TX, TY, TZ, ks, stages=3):
     return ConvTile(TX, TY, TZ, pw.NT, pw.n_ntiles, stages, mt, 0, 0, 0.0)
 
 
-def conv_case(cin, cout, shape, n_img=1, tile=None, split=False, flags=0, ks=3, seed=0, name="conv", roll=None):
-    """raw conv output (blocked) + InstanceNorm partial statistics vs F.conv3d in fp64."""
+def conv_case(cin, cout, shape, n_img=1, tile=None, split=False, flags=0, ks=3, seed=0, name="conv", roll=None,
+              raw_f32=None):
+    """raw conv output (blocked) + InstanceNorm partial statistics vs F.conv3d in fp64.
+    split: False (bf16) / True (parity) / a numeric-mode name of numerics.py; operands that the mode does NOT split are
+    pre-rounded to its element format, so the only error left is the output rounding (none with fp32 raw output)."""
+    from mmseg_b200.numerics import mode as numeric_mode
+    nm = numeric_mode(split)
     torch.manual_seed(seed)
     Z, Y, X = shape
     x = torch.randn(n_img, cin, Z, Y, X, device=DEV)
     w = torch.randn(cout, cin, ks, ks, ks, device=DEV) * (1.0 / (cin * ks ** 3) ** 0.5)
-    if not split:
-        x, w = _bf(x), _bf(w)
+    if not nm.a_split:
+        x = x.to(nm.dtype).float()
+    if not nm.w_split:
+        w = w.to(nm.dtype).float()
+    rawf = nm.raw_f32 if raw_f32 is None else raw_f32
     pw = K.pack_conv_weight(w, None, split, [cin], use_bias=False)
     src = Blocked(n_img, (cin + 15) // 16 * 16, Z, Y, X, split, DEV)
     K.pack_ncdhw(x, src)
@@ -61,16 +69,16 @@ def conv_case(cin, cout, shape, n_img=1, tile=None, split=False, flags=0, ks=3, 
         assert t is not None and t.roll
         name = f"{name}-roll{(t.TX, t.TY, t.TZ, t.stages, t.kpb)}"
     raw = torch.full((n_img, pw.n_out // 8, Z, Y, X, 8), float("nan"), device=DEV,
-                     dtype=torch.float32 if split else torch.bfloat16)
+                     dtype=torch.float32 if rawf else nm.dtype)
     tiles_per_img = ((X + t.TX - 1) // t.TX) * ((Y + t.TY - 1) // t.TY) * ((Z + t.TZ - 1) // t.TZ)
     stats = torch.zeros((n_img, tiles_per_img, pw.n_out, 2), device=DEV)
-    K.conv3d(src, pw, a_cb, raw, _lib.OUT_BLOCKED_F32 if split else _lib.OUT_BLOCKED_BF16, stats=stats,
+    K.conv3d(src, pw, a_cb, raw, _lib.OUT_BLOCKED_F32 if rawf else _lib.OUT_BLOCKED_BF16, stats=stats,
              dst_cbt=pw.n_out // 8, tile=t, flags=flags)
     torch.cuda.synchronize()
     got = raw.float().permute(0, 1, 5, 2, 3, 4).reshape(n_img, pw.n_out, Z, Y, X)[:, :cout]
     ref = _ref_conv(x, w, pad=ks // 2)
-    tol = 3e-5 if split else 2e-2
-    err = _report(f"{name} cin={cin} cout={cout} {shape} n={n_img} tile={tile} split={split} flags={flags}", got, ref, tol)
+    tol = 3e-5 if rawf else (2e-2 if nm.dtype == torch.bfloat16 else 2.5e-3)
+    err = _report(f"{name} cin={cin} cout={cout} {shape} n={n_img} tile={tile} mode={nm.name} raw_f32={rawf} flags={flags}", got, ref, tol)
     assert torch.isfinite(got).all(), "non-finite output (unwritten voxels?)"
     assert err <= tol * max(1.0, ref.abs().max().item())
     # statistics: sum and sum of squares over voxels per (img, channel)

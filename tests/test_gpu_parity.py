@@ -32,6 +32,12 @@ def _c():
     ((64, 32, (8, 16, 48)), dict(split=True)),
     ((32, 16, (5, 6, 20)), dict(ks=1)),
     ((256, 512, (3, 3, 3)), {}),
+    ((32, 32, (6, 8, 20)), dict(split="fp16")),                   # fp16 operands, fp16 raw output
+    ((32, 64, (5, 11, 50)), dict(split="fp16", raw_f32=True, tile=(25, 5, 2))),
+    ((64, 32, (8, 16, 48)), dict(split="fp16a2")),                # [A_hi | A_lo] x [W | W]
+    ((32, 32, (6, 8, 20)), dict(split="fp16w2")),                 # [A | A] x [W_hi | W_lo]
+    ((2, 32, (6, 10, 24)), dict(split="fp16x3")),
+    ((32, 16, (5, 6, 20)), dict(ks=1, split="fp16x3")),
 ])
 def test_conv3d_tcgen05(args, kw):
     _c().conv_case(*args, **kw)
@@ -46,6 +52,9 @@ def test_conv3d_tcgen05(args, kw):
     ((32, 32, (37, 5, 24)), dict(roll=(24, 5, 37, 10), n_img=2)),    # one long segment: 37 planes through a 16-slot ring
     ((32, 32, (40, 7, 26)), dict(n_img=2, roll=(13, 4, 17, 6, 2))),  # two K chunks per TMA stage (4-block box)
     ((64, 32, (19, 6, 20)), dict(roll=(20, 5, 7, 5, 2))),            # 4 K chunks = 2 paired stages per plane, 5-stage ring
+    ((32, 32, (40, 7, 26)), dict(n_img=2, roll=(13, 4, 17, 8), raw_f32=True)),              # fp32 raw output (bf16 operands)
+    ((64, 32, (19, 6, 20)), dict(roll=(20, 5, 7, 5, 2), split="fp16", raw_f32=True)),        # fp16 operands, fp32 raw output
+    ((32, 32, (20, 12, 30)), dict(roll="auto", split="fp16")),                               # fp16 operands and output
 ])
 def test_conv3d_rolling_z(args, kw):
     """conv3d_roll_kernel (TMEM ring of output planes) vs F.conv3d, raw output and InstanceNorm partial sums."""
