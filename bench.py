@@ -380,7 +380,9 @@ def run_ours(args):
     agreement_vs_n1 = None
     if world > 1 and not args.no_selfcheck:
         if rank == 0:
-            solo = SlidingWindowInferer(model, ROI, OVERLAP, MODE, engine_batch=8)
+            # same engine batch as the sharded run: a window's logits depend on the batch size only through the tile plan
+            # (summation order of the InstanceNorm statistics), so what is left is the order of the overlap adds
+            solo = SlidingWindowInferer(model, ROI, OVERLAP, MODE, engine_batch=inf._state["nb"])
             lab1 = solo(inf._dev_vol.unsqueeze(0), return_labels=True)
             agreement_vs_n1 = (lab1 == labels).double().mean().item()
             log(f"[selfcheck] sharded x{world} labels vs single-GPU labels: {agreement_vs_n1 * 100:.5f}% identical")

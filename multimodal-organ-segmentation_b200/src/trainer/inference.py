@@ -116,7 +116,7 @@ def touched_range(starts: Sequence[Tuple[int, ...]], lo: int, hi: int, roi0: int
     return min(s), max(s) + roi0
 
 
-def pick_engine_batch(n_windows: int, preferred: int = 8, lo: int = 6, hi: int = 16) -> int:
+def pick_engine_batch(n_windows: int, preferred: int = 12, lo: int = 6, hi: int = 16) -> int:
     """Windows per engine batch: the divisor of `n_windows` in [lo, hi] closest to `preferred` (every batch is then a
     full, graph-replayed batch — e.g. 75 windows per rank at 8 GPUs run as 5 x 15 instead of 9 x 8 + 3), else
     `preferred` (the shorter tail batch gets its own captured graph)."""
