@@ -134,11 +134,13 @@ typedef struct {
 } mmseg_wgrad_args;
 int mmseg_conv3d_wgrad(const mmseg_wgrad_args* args, void* stream);
 int64_t mmseg_conv3d_wgrad_smem_bytes(const mmseg_wgrad_args* args);
-/* ci_map[ci] = group*CIG + index inside the group for weight input channel ci.  transposed: ConvTranspose3d(k2,s2)
- * layout [Cin][Cout][2][2][2] from the GEMM columns n = tap8*Cout + co (Cout_gemm = 8*Cout). */
+/* ci_of_pos[group*CIG + index inside the group] = weight input channel held by that accumulator row, or -1 for a padded
+ * row (CIG = cig_blocks*8; n_cig groups).  dst must be zero-initialised only where no accumulator row maps (never: every
+ * real (co, ci, tap) is written exactly once).  transposed: ConvTranspose3d(k2,s2) layout [Cin][Cout][2][2][2] from the
+ * GEMM columns n = tap8*Cout + co (Cout_gemm = 8*Cout). */
 int mmseg_wgrad_reduce(const float* partial, int32_t n_part, int32_t ksize, int32_t cig_blocks, int32_t cot_blocks,
-                       int32_t n_cot, int32_t Cin, int32_t Cout_gemm, int32_t Cout, int32_t transposed,
-                       const int32_t* ci_map, float* dst, void* stream);
+                       int32_t n_cig, int32_t n_cot, int32_t Cin, int32_t Cout_gemm, int32_t Cout, int32_t transposed,
+                       const int32_t* ci_of_pos, float* dst, void* stream);
 
 /*
  * InstanceNorm3d(affine=False, eps) statistics: reduce the conv epilogue's per-CTA partials in a fixed order (fp64)
@@ -357,6 +359,44 @@ int mmseg_modality_max(const void* src, int32_t n_img, int32_t src_cbt, int32_t 
 int mmseg_maxpool3d_2(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_cb_off, int32_t src_lo_off,
                       int32_t cb, int32_t Z, int32_t Y, int32_t X, void* dst, int32_t dst_cbt, int32_t dst_cb_off,
                       int32_t dst_lo_off, int32_t fmt, void* stream);
+
+/*
+ * Trainer step glue — the kernels either side of forward / backward.
+ *
+ * mmseg_weights_repack: fp32 PyTorch-layout parameter (nn.Conv3d [Cout][Cin][k][k][k], nn.ConvTranspose3d
+ * [Cin][Cout][2][2][2]) -> the packed 16-bit GEMM operand of mmseg_conv3d_fwd, in one launch: the forward form, the
+ * spatially flipped + channel-transposed form the dgrad launch needs (autograd's convolution_backward input gradient,
+ * reached from src/trainer/trainer.py:243), the ConvTranspose GEMM forms and the hi / lo splits of the split numeric
+ * modes.  It replaces the per-step flip / permute / cat / copy chains.  The caller supplies two int32 device tables:
+ *   n_off[n_out]   element offset of GEMM column n in the source, -1 = zero-padding column
+ *   k_off[n_kc*16] element offset of GEMM K index (16 per chunk) in the source, -1 = zero padding
+ * element = w[n_off[n] + k_off[k] + tap] * scale (tap mirrored when flip).  dst layout as consumed by conv_tc.cu:
+ * [n_out/NT][n_kc_total][9 | 1][2][3*NT | NT][8], n_kc_total = n_kc * (hi_copies + has_lo).
+ */
+int mmseg_weights_repack(const float* w, const int32_t* n_off, const int32_t* k_off, void* dst, int32_t n_out, int32_t NT,
+                         int32_t n_kc, int32_t n_kc_total, int32_t ksize, int32_t flip, int32_t hi_copies, int32_t has_lo,
+                         int32_t fmt, float scale, void* stream);
+/* dst[i] = idx[i] >= 0 ? src[idx[i]] : 0 — conv bias padded / expanded to the GEMM columns (ConvTranspose: x8 taps). */
+int mmseg_gather_f32(const float* src, const int32_t* idx, float* dst, int32_t n, void* stream);
+
+/*
+ * torch.optim.AdamW.step() (reference src/trainer/trainer.py:115-117, stepped at :245-248) over a whole list of fp32
+ * tensors in one launch: decoupled weight decay, bias correction, optional zeroing of the gradients (optimizer.zero_grad).
+ * tensors: device array of mmseg_adamw_tensor; chunks: device array of (tensor index, chunk index) pairs, one per CTA,
+ * 8192 elements per chunk; step: device fp32 counter (incremented); hyper: device fp32[6] =
+ * {lr, beta1, beta2, eps, weight_decay, grad_scale} (grad_scale multiplies every gradient, e.g. 1/world after a summing
+ * all-reduce).  Graph-capturable: no host-side state.
+ */
+typedef struct {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int64_t n;
+} mmseg_adamw_tensor;
+#define MMSEG_ADAMW_CHUNK 8192
+int mmseg_adamw_multi(const void* tensors, const int32_t* chunks, int32_t n_chunks, float* step, const float* hyper,
+                      int32_t zero_grad, void* stream);
 
 #ifdef __cplusplus
 }

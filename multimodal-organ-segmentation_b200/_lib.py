@@ -51,6 +51,13 @@ class WgradArgs(C.Structure):
     ]
 
 
+class AdamwTensor(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int64)]
+
+
+ADAMW_CHUNK = 8192
+
+
 class NormBwdArgs(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("mean_rstd", C.c_void_p), ("gA", C.c_void_p), ("gP", C.c_void_p),
@@ -86,7 +93,7 @@ SYMBOLS = {
     "mmseg_conv3d_tiles_per_img": (_i32, [C.POINTER(ConvArgs)]),
     "mmseg_conv3d_wgrad": (C.c_int, [C.POINTER(WgradArgs), _vp]),
     "mmseg_conv3d_wgrad_smem_bytes": (_i64, [C.POINTER(WgradArgs)]),
-    "mmseg_wgrad_reduce": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "mmseg_wgrad_reduce": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "mmseg_instnorm_finalize": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _f32, _vp, _vp]),
     "mmseg_instnorm_act_apply": (C.c_int, [C.POINTER(NormArgs), _vp]),
     "mmseg_instnorm_act_bwd_reduce": (C.c_int, [C.POINTER(NormBwdArgs), _vp]),
@@ -119,6 +126,9 @@ SYMBOLS = {
     "mmseg_groupnorm_finalize": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i64, _f32, _vp, _vp, _vp, _vp, _vp]),
     "mmseg_trilinear_resize": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
     "mmseg_conv1x1_logits": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _i32, _vp, _i32, _vp]),
+    "mmseg_weights_repack": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "mmseg_gather_f32": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
+    "mmseg_adamw_multi": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _vp]),
     "mmseg_maxpool3d_2": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
 }
 

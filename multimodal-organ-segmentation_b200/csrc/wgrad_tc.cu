@@ -220,29 +220,56 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
 }
 
-// dW[...] = sum over the persistent CTAs' partials, fixed order.  One thread per weight element.
+// dW[...] = sum over the persistent CTAs' partials in a fixed order (deterministic split-K), written straight into the
+// PyTorch-layout fp32 gradient.
 //   mode 0 (Conv3d):          dst[(co*Cin + ci)*taps + tap],            tap = (dz*KT + dy)*KT + dx
 //   mode 1 (ConvTranspose3d): GEMM column n = tap8*Cout + co,            dst[(ci*Cout + co)*8 + tap8]
-__global__ void __launch_bounds__(256)
+// The partials are read in THEIR memory order: a warp owns 32 consecutive fp32 columns of one partial row (128-byte
+// coalesced loads), the block's 8 warps each sum a slice k = w, w + 8, ... of the n_part partials (independent loads in
+// flight), and the slices are combined in warp order through shared memory — every element sees the same association
+// whatever the grid.  (The first version had one thread per weight element walking all partials with a 128*ncols
+// stride: 175-500 GB/s, 1.05 ms of a 20 ms training step.)
+constexpr int kRedSlices = 8;
+__global__ void __launch_bounds__(32 * kRedSlices)
 wgrad_reduce_kernel(const float* __restrict__ partial, int n_part, int ncols, int n_cot, int NTc, int CIG, int KT,
-                    int Cin, int Cout_gemm, int Cout, int mode, const int* __restrict__ ci_map, float* __restrict__ dst) {
-  const int taps = KT * KT * KT;
-  const long long total = (long long)Cout_gemm * Cin * taps;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int tap = (int)(idx % taps);
-  const long long r = idx / taps;
-  const int ci = (int)(r % Cin);
-  const int n = (int)(r / Cin);  // GEMM column (co, or tap8*Cout + co)
-  const int dz = tap / (KT * KT), dy = (tap / KT) % KT, dx = tap % KT;
-  const int cm = ci_map[ci];
-  const int cig = cm / CIG, cil = cm - cig * CIG;
-  const int cot = n / NTc, col_l = n - cot * NTc;
-  const int lane = dx * CIG + cil;
-  const int col = dy * (KT * NTc) + (KT - 1 - dz) * NTc + col_l;
-  const float* p = partial + (((size_t)(cig * n_cot + cot) * n_part) * 128 + lane) * ncols + col;
+                    int Cin, int Cout_gemm, int Cout, int mode, const int* __restrict__ ci_of_pos,
+                    float* __restrict__ dst) {
+  __shared__ double sm[kRedSlices][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int cols_blocks = (ncols + 31) / 32;
+  int b = blockIdx.x;
+  const int cblk = b % cols_blocks; b /= cols_blocks;
+  const int row = b % 128;                       // accumulator row = (dx, ci inside the group)
+  const int pair = b / 128;                      // (input-channel group, output-channel group)
+  const int col = cblk * 32 + lane;
+  const int dx = row / CIG, cil = row - dx * CIG;
+  const int cig = pair / n_cot, cot = pair - cig * n_cot;
+  const int ci = (dx < KT) ? ci_of_pos[cig * CIG + cil] : -1;   // rows >= KT*CIG multiplied garbage: never stored
   double s = 0.0;
-  for (int k = 0; k < n_part; ++k) s += (double)p[(size_t)k * 128 * ncols];
+  if (col < ncols && ci >= 0) {
+    const float* p = partial + (((size_t)pair * n_part) * 128 + row) * ncols + col;
+    const size_t kstride = (size_t)128 * ncols;
+    int k = slice;
+    for (; k + 3 * kRedSlices < n_part; k += 4 * kRedSlices) {
+      const float v0 = p[(size_t)k * kstride], v1 = p[(size_t)(k + kRedSlices) * kstride];
+      const float v2 = p[(size_t)(k + 2 * kRedSlices) * kstride], v3 = p[(size_t)(k + 3 * kRedSlices) * kstride];
+      s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
+    }
+    for (; k < n_part; k += kRedSlices) s += (double)p[(size_t)k * kstride];
+  }
+  sm[slice][lane] = s;
+  __syncthreads();
+  if (slice != 0 || col >= ncols || ci < 0) return;
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < kRedSlices; ++w) t += sm[w][lane];
+  const int dy = col / (KT * NTc), r2 = col - dy * (KT * NTc);
+  const int dzr = r2 / NTc, col_l = r2 - dzr * NTc;
+  const int dz = KT - 1 - dzr;
+  const int n = cot * NTc + col_l;                // GEMM column (co, or tap8*Cout + co)
+  if (n >= Cout_gemm) return;
+  const int taps = KT * KT * KT;
+  const int tap = (dz * KT + dy) * KT + dx;
   size_t o;
   if (mode == 0) {
     o = ((size_t)n * Cin + ci) * taps + tap;
@@ -250,7 +277,7 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int n_part, int ncols, in
     const int tap8 = n / Cout, co = n - tap8 * Cout;
     o = ((size_t)ci * Cout + co) * 8 + tap8;
   }
-  dst[o] = (float)s;
+  dst[o] = (float)t;
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -381,15 +408,16 @@ extern "C" int mmseg_conv3d_wgrad(const mmseg_wgrad_args* a, void* stream) {
 }
 
 extern "C" int mmseg_wgrad_reduce(const float* partial, int32_t n_part, int32_t ksize, int32_t cig_blocks,
-                                  int32_t cot_blocks, int32_t n_cot, int32_t Cin, int32_t Cout_gemm, int32_t Cout,
-                                  int32_t transposed, const int32_t* ci_map, float* dst, void* stream) {
-  if (!partial || !ci_map || !dst || n_part < 1 || Cin < 1 || Cout_gemm < 1)
+                                  int32_t cot_blocks, int32_t n_cig, int32_t n_cot, int32_t Cin, int32_t Cout_gemm,
+                                  int32_t Cout, int32_t transposed, const int32_t* ci_of_pos, float* dst, void* stream) {
+  if (!partial || !ci_of_pos || !dst || n_part < 1 || Cin < 1 || Cout_gemm < 1 || n_cig < 1 || n_cot < 1)
     return fail(MMSEG_ERR_INVALID_ARG, "wgrad_reduce: bad arguments");
   const int KT = ksize;
   const int ncols = KT * KT * cot_blocks * 8;
-  const long long total = (long long)Cout_gemm * Cin * KT * KT * KT;
-  wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  const long long blocks = (long long)n_cig * n_cot * 128 * ((ncols + 31) / 32);
+  if (blocks > 2147483647LL) return fail(MMSEG_ERR_INVALID_ARG, "wgrad_reduce: grid too large");
+  wgrad_reduce_kernel<<<(unsigned)blocks, 32 * kRedSlices, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       partial, n_part, ncols, n_cot, cot_blocks * 8, cig_blocks * 8, KT, Cin, Cout_gemm, Cout, transposed ? 1 : 0,
-      ci_map, dst);
+      ci_of_pos, dst);
   return check_launch("wgrad_reduce_kernel");
 }

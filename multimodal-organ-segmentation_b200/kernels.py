@@ -186,6 +186,141 @@ def pack_conv_weight(weight: Tensor, bias: Optional[Tensor], split: bool, seg_ch
                       transposed, nm)
 
 
+class PackPlan:
+    """Kernel-side weight packing (mmseg_weights_repack): a persistent packed buffer plus the two int32 gather tables that
+    describe where every GEMM element lives in the fp32 PyTorch-layout parameter.  `run()` re-derives the packed operand
+    from the LIVE parameter with one launch (plus one tiny launch for a bias) — no ATen flip / permute / cat / copy, no
+    allocation, graph-capturable, and the packed buffer keeps its address (captured graphs stay valid across updates).
+
+    Forms (constructors below): `forward` (what pack_conv_weight builds, incl. concat segments, ConvTranspose and the hi / lo
+    splits), `dgrad` (flipped taps, channels transposed), `convt_dgrad`, `k1_dgrad`.  pack_conv_weight remains the ATen
+    restatement the tests compare this kernel against bit for bit."""
+
+    def __init__(self, weight: Tensor, n_off: Sequence[int], k_off: Sequence[int], ksize: int, flip: bool, nm,
+                 nt_cap: int, out_channels: int, cin: int, is_convt: bool = False, bias: Optional[Tensor] = None,
+                 bias_idx: Optional[Sequence[int]] = None):
+        nm = numeric_mode(nm)
+        dev = weight.device
+        assert weight.dtype == torch.float32 and weight.is_contiguous(), "parameters are fp32 contiguous"
+        self.weight, self.bias_src, self.nm = weight, bias, nm
+        n_out = len(n_off)
+        assert n_out % 16 == 0 and len(k_off) % 16 == 0
+        NT = min(n_out, nt_cap)
+        while n_out % NT:
+            NT -= 16
+        self.n_kc = len(k_off) // 16
+        self.hi_copies = 2 if nm.a_split else 1
+        self.has_lo = bool(nm.w_split)
+        n_kc_total = self.n_kc * (self.hi_copies + int(self.has_lo))
+        taps2d, rows = (9, 3 * NT) if ksize == 3 else (1, NT)
+        self.n_off = torch.tensor(list(n_off), dtype=torch.int32, device=dev)
+        self.k_off = torch.tensor(list(k_off), dtype=torch.int32, device=dev)
+        w = torch.empty((n_out // NT, n_kc_total, taps2d, 2, rows, 8), dtype=nm.dtype, device=dev)
+        bias_p = None
+        self.bias_idx = None
+        if bias is not None:
+            assert bias_idx is not None and len(bias_idx) == n_out and bias.dtype == torch.float32
+            self.bias_idx = torch.tensor(list(bias_idx), dtype=torch.int32, device=dev)
+            bias_p = torch.empty(n_out, dtype=torch.float32, device=dev)
+        self.ksize, self.flip = ksize, bool(flip)
+        self.pc = PackedConv(w, bias_p, ksize, cin, n_out, out_channels, NT, n_out // NT, n_kc_total, nm.passes > 1,
+                             is_convt, nm)
+        self.version = None
+
+    def run(self) -> PackedConv:
+        pc = self.pc
+        _call("mmseg_weights_repack", _ptr(self.weight), _ptr(self.n_off), _ptr(self.k_off), _ptr(pc.w), pc.n_out, pc.NT,
+              self.n_kc, pc.n_kchunks, self.ksize, 1 if self.flip else 0, self.hi_copies, 1 if self.has_lo else 0,
+              self.nm.fmt, 1.0, _stream())
+        if pc.bias is not None:
+            _call("mmseg_gather_f32", _ptr(self.bias_src), _ptr(self.bias_idx), _ptr(pc.bias), pc.n_out, _stream())
+        return pc
+
+    def fresh(self) -> PackedConv:
+        """run() only when the parameter changed since the last call (inference: weights are usually static)."""
+        ver = (self.weight.data_ptr(), self.weight._version,
+               None if self.bias_src is None else (self.bias_src.data_ptr(), self.bias_src._version))
+        if ver != self.version:
+            self.run()
+            self.version = ver
+        return self.pc
+
+    # ---- constructors (same arguments as pack_conv_weight where they overlap)
+    @staticmethod
+    def _k_table(seg, elem_off):
+        """K positions of concat segments (each padded to a whole 16-channel chunk) -> source offsets."""
+        k_off, c = [], 0
+        for s_ in seg:
+            sp = (s_ + 15) // 16 * 16
+            k_off += [elem_off(c + i) for i in range(s_)] + [-1] * (sp - s_)
+            c += s_
+        return k_off
+
+    @classmethod
+    def forward(cls, weight: Tensor, bias: Optional[Tensor], split, seg_channels: Optional[Sequence[int]] = None,
+                use_bias: bool = True, nt_cap: int = 64, transposed: bool = False) -> "PackPlan":
+        w = weight.detach()
+        b = bias.detach() if (use_bias and bias is not None) else None
+        if transposed:   # nn.ConvTranspose3d [Cin, Cout, 2,2,2]: column n = (((dz*2+dy)*CB + cb)*2 + dx)*8 + j
+            cin, cout = w.shape[0], w.shape[1]
+            assert tuple(w.shape[2:]) == (2, 2, 2) and cout % 16 == 0
+            cbn = cout // 8
+            n_off, bias_idx = [], []
+            for zy in range(4):
+                for cb in range(cbn):
+                    for dx in range(2):
+                        for j in range(8):
+                            co = cb * 8 + j
+                            n_off.append(co * 8 + zy * 2 + dx)
+                            bias_idx.append(co)
+            seg = list(seg_channels) if seg_channels is not None else [cin]
+            k_off = cls._k_table(seg, lambda ci: ci * cout * 8)
+            return cls(w, n_off, k_off, 1, False, split, nt_cap, cout, cin, True, b, bias_idx if b is not None else None)
+        cout, cin, ksize = w.shape[0], w.shape[1], w.shape[2]
+        assert ksize in (1, 3) and tuple(w.shape[2:]) == (ksize,) * 3
+        taps = ksize ** 3
+        n_pad = (cout + 15) // 16 * 16
+        n_off = [n * cin * taps for n in range(cout)] + [-1] * (n_pad - cout)
+        bias_idx = list(range(cout)) + [-1] * (n_pad - cout)
+        seg = list(seg_channels) if seg_channels is not None else [cin]
+        assert sum(seg) == cin
+        k_off = cls._k_table(seg, lambda ci: ci * taps)
+        return cls(w, n_off, k_off, ksize, False, split, nt_cap, cout, cin, False, b, bias_idx if b is not None else None)
+
+    @classmethod
+    def dgrad(cls, weight: Tensor, nt_cap: int = 64) -> "PackPlan":
+        """The conv whose forward IS the input gradient of nn.Conv3d(k, padding k//2): weight.flip(2,3,4).transpose(0,1),
+        i.e. GEMM column = input channel, K = output channel, taps mirrored."""
+        w = weight.detach()
+        cout, cin, ksize = w.shape[0], w.shape[1], w.shape[2]
+        taps = ksize ** 3
+        n_pad = (cin + 15) // 16 * 16
+        n_off = [ci * taps for ci in range(cin)] + [-1] * (n_pad - cin)
+        k_off = cls._k_table([cout], lambda co: co * cin * taps)
+        return cls(w, n_off, k_off, ksize, True, False, nt_cap, cin, cout)
+
+    @classmethod
+    def convt_dgrad(cls, weight: Tensor, nt_cap: int = 64) -> "PackPlan":
+        """Input gradient of ConvTranspose3d(k2,s2) through its k=1 GEMM view: column = input channel ci, K index =
+        tap8*Cout + co (the channel order mmseg_unshuffle_k2s2 produces)."""
+        w = weight.detach()
+        cin, f = w.shape[0], w.shape[1]
+        n_pad = (cin + 15) // 16 * 16
+        n_off = [ci * f * 8 for ci in range(cin)] + [-1] * (n_pad - cin)
+        k_off = cls._k_table([8 * f], lambda k: (k % f) * 8 + k // f)
+        return cls(w, n_off, k_off, 1, False, False, nt_cap, cin, 8 * f)
+
+    @classmethod
+    def k1_dgrad(cls, weight: Tensor, nt_cap: int = 64) -> "PackPlan":
+        """Input gradient of a 1x1x1 conv [Cout, Cin, 1,1,1]: column = ci, K = co."""
+        w = weight.detach()
+        cout, cin = w.shape[0], w.shape[1]
+        n_pad = (cin + 15) // 16 * 16
+        n_off = list(range(cin)) + [-1] * (n_pad - cin)
+        k_off = cls._k_table([cout], lambda co: co * cin)
+        return cls(w, n_off, k_off, 1, False, False, nt_cap, cin, cout)
+
+
 def a_chunk_table(src: Blocked, seg_c0: Sequence[int], seg_channels: Sequence[int], split) -> List[int]:
     """First channel block of every K chunk, in the order pack_conv_weight laid the chunks out."""
     nm = numeric_mode(split)
@@ -529,15 +664,18 @@ def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt
                     "tile": (TX, TY, TZ, ntc, cig), "ctas": n_part * n_cig * n_cot}
     _call("mmseg_conv3d_wgrad", C.byref(a), _stream())
     dw = torch.empty(tuple(weight_shape), dtype=torch.float32, device=x.t.device)
-    key = (tuple(ci_map), str(x.t.device))
+    key = (tuple(ci_map), n_cig * cig, str(x.t.device))
     cm = _CI_MAPS.get(key)
     if cm is None:  # cached: a host->device copy per call would also break CUDA-graph capture of the training step
-        cm = _CI_MAPS[key] = torch.tensor(ci_map, dtype=torch.int32, device=x.t.device)
+        inv = [-1] * (n_cig * cig)            # accumulator row position -> weight input channel (-1: padding row)
+        for ci_, pos in enumerate(ci_map):
+            inv[pos] = ci_
+        cm = _CI_MAPS[key] = torch.tensor(inv, dtype=torch.int32, device=x.t.device)
     cout = weight_shape[1] if transposed else weight_shape[0]
     if PROFILE is not None:
         _INFO[0] = {"bytes": 4.0 * partial.numel() + 4.0 * dw.numel(),
                     "layer": f"reduce-k{ksize}-cin{cin}-n{cout_gemm}-part{n_part}-pairs{n_cig * n_cot}"}
-    _call("mmseg_wgrad_reduce", _ptr(partial), n_part, ksize, cig // 8, ntc // 8, n_cot, cin, cout_gemm, cout,
+    _call("mmseg_wgrad_reduce", _ptr(partial), n_part, ksize, cig // 8, ntc // 8, n_cig, n_cot, cin, cout_gemm, cout,
           1 if transposed else 0, _ptr(cm), _ptr(dw), _stream())
     return dw
 

@@ -22,6 +22,7 @@ from .inference import predict_volume, sliding_window_inference
 from .losses import get_loss
 from .metrics import DiceMetric, get_metrics
 from ...parallel import GradBucketReducer
+from ...optim import FusedAdamW
 
 
 def _progress(it, desc=""):
@@ -69,8 +70,10 @@ class Trainer:
                            f"cuda available: {torch.cuda.is_available()}); there is no CPU fallback")
 
     def _setup_optimizer(self) -> torch.optim.Optimizer:
-        """training.optimizer.{name, lr, weight_decay[, betas | momentum]} -> torch optimizer (reference trainer.py:100-124).
-        AdamW is created capturable when hardware.cuda_graph asks for whole-step graph capture."""
+        """training.optimizer.{name, lr, weight_decay[, betas | momentum]} -> optimizer (reference trainer.py:100-124).
+        AdamW (the reference's default and its fall-through for unknown names) is the fused multi-tensor kernel
+        (optim.FusedAdamW: one launch per step, device-side step counter and hyper-parameters, so it is graph-capturable and
+        keeps torch.optim.AdamW's update rule and state_dict layout); Adam / SGD stay torch's."""
         oc = self.config["training"]["optimizer"]
         common = dict(lr=oc["lr"], weight_decay=oc.get("weight_decay", 0))
         params = self.model.parameters()
@@ -79,11 +82,7 @@ class Trainer:
             return torch.optim.Adam(params, **common)
         if kind == "sgd":
             return torch.optim.SGD(params, momentum=oc.get("momentum", 0.9), **common)
-        extra = {}
-        if kind == "adamw":
-            extra = dict(betas=tuple(oc.get("betas", [0.9, 0.999])),
-                         capturable=bool(self.config["hardware"].get("cuda_graph", False)))
-        return torch.optim.AdamW(params, **common, **extra)     # also the reference's fall-through for unknown names
+        return FusedAdamW(params, betas=tuple(oc.get("betas", [0.9, 0.999])), **common)
 
     def _setup_scheduler(self):
         """training.scheduler.name: cosine (default) | step | plateau | anything else = none (reference trainer.py:126-164)."""
@@ -157,7 +156,7 @@ class Trainer:
             self.reducer.finish()
         if step_optimizer:
             self.optimizer.step()
-            self.optimizer.zero_grad()
+            self.optimizer.zero_grad()      # set_to_none: the next backward hands over fresh gradient tensors
         return loss.detach()
 
     def graphed_train_step(self, images: torch.Tensor, labels: torch.Tensor):
@@ -178,10 +177,16 @@ class Trainer:
         with torch.cuda.graph(graph):
             static_loss = self.train_step(static_x, static_y)
 
+        params = [p for p in self.model.parameters() if p.requires_grad]
+
         def replay(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
             static_x.copy_(x, non_blocking=True)
             static_y.copy_(y, non_blocking=True)
+            if isinstance(self.optimizer, FusedAdamW):
+                self.optimizer.sync_hyper()     # a scheduler may have changed lr since the capture
             graph.replay()
+            # the replayed optimizer kernel rewrote the parameters: packed-weight caches / inference graphs key on this
+            torch.autograd.graph.increment_version(params)
             return static_loss
         return replay
 

@@ -49,6 +49,16 @@ class TrainEngine:
         self._handed = set()
         self._buf_busy: Dict[str, object] = {}
         self._flip = 0
+        self._plans: Dict[Tuple, K.PackPlan] = {}
+
+    def _packed(self, param: Tensor, variant: str, make) -> K.PackedConv:
+        """Kernel-layout operand of `param` in form `variant`, re-derived from the live parameter by ONE repack launch
+        (kernels.PackPlan / mmseg_weights_repack): the tables and the packed buffer are built once per parameter."""
+        key = (id(param), variant)
+        plan = self._plans.get(key)
+        if plan is None or plan.weight.data_ptr() != param.data_ptr():
+            plan = self._plans[key] = make()
+        return plan.run()
 
     # ---------------------------------------------------------------- buffers
     def _reset(self, n, Z, Y, X, device):
@@ -85,7 +95,8 @@ class TrainEngine:
                       chan_scale: Optional[Tensor] = None, gate_ref=None):
         n, Z, Y, X = src.n_img, src.Z, src.Y, src.X
         cout = conv.weight.shape[0]
-        pw = K.pack_conv_weight(conv.weight, None, False, [s[1] for s in segs], use_bias=False)
+        seg_ch = tuple(s[1] for s in segs)
+        pw = self._packed(conv.weight, ("fwd", seg_ch), lambda: K.PackPlan.forward(conv.weight, None, False, seg_ch, use_bias=False))
         a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], False)
         tile = K.plan_conv_norm((X, Y, Z), n, pw, False, a_cb)
         raw = self.saved(name + ".raw", (n, cout // 8, Z, Y, X, 8), torch.bfloat16)
@@ -111,7 +122,7 @@ class TrainEngine:
 
     def conv_transpose(self, name: str, src: Blocked, up, dst: Blocked):
         cin = up.weight.shape[0]
-        pw = K.pack_conv_weight(up.weight, up.bias, False, None, transposed=True)
+        pw = self._packed(up.weight, "convt", lambda: K.PackPlan.forward(up.weight, up.bias, False, None, transposed=True))
         a_cb = K.a_chunk_table(src, [0], [cin], False)
         K.conv3d(src, pw, a_cb, dst.t, _lib.OUT_CONVT_K2S2, dst_cbt=dst.cbt, dst_cb_off=0, dst_lo_off=0)
         self.tape.append(dict(kind="convt", name=name, src=src, up=up, dst=dst))
@@ -128,7 +139,8 @@ class TrainEngine:
 
     def conv_bias(self, name: str, src: Blocked, segs, conv, dst: Blocked, dst_c0: int):
         """1x1 conv + bias straight into an activation buffer (DualEncoder 'concat' fusion_proj)."""
-        pw = K.pack_conv_weight(conv.weight, conv.bias, False, [s[1] for s in segs])
+        seg_ch = tuple(s[1] for s in segs)
+        pw = self._packed(conv.weight, ("fwdb", seg_ch), lambda: K.PackPlan.forward(conv.weight, conv.bias, False, seg_ch))
         a_cb = K.a_chunk_table(src, [s[0] for s in segs], [s[1] for s in segs], False)
         K.conv3d(src, pw, a_cb, dst.t, _lib.OUT_BLOCKED_BF16, dst_cbt=dst.cbt, dst_cb_off=dst_c0 // 8)
         self.tape.append(dict(kind="convb", name=name, src=src, segs=list(segs), conv=conv, dst=dst, dst_c0=dst_c0))
@@ -159,10 +171,10 @@ class TrainEngine:
             self.grads[p] = gp
 
     # ---------------------------------------------------------------- backward ops
-    def _dgrad(self, dy: Blocked, dy_channels: int, w_as_conv: Tensor, dst: Blocked, dst_c0: int):
-        """dst[:, dst_c0 : dst_c0 + Cout'] = conv(dy, w_as_conv) with the forward tcgen05 kernel."""
-        pw = K.pack_conv_weight(w_as_conv, None, False, [dy_channels], use_bias=False)
-        a_cb = K.a_chunk_table(dy, [0], [dy_channels], False)
+    def _dgrad(self, dy: Blocked, dy_channels: int, pw: K.PackedConv, dst: Blocked, dst_c0: int, dy_c0: int = 0):
+        """dst[:, dst_c0 : dst_c0 + Cout'] = conv(dy[:, dy_c0 : dy_c0 + dy_channels], pw) with the forward tcgen05 kernel
+        (pw = the dgrad-form operand: flipped taps, channels transposed)."""
+        a_cb = K.a_chunk_table(dy, [dy_c0], [dy_channels], False)
         K.conv3d(dy, pw, a_cb, dst.t, _lib.OUT_BLOCKED_BF16, dst_cbt=dst.cbt, dst_cb_off=dst_c0 // 8)
 
     def _wgrad_async(self, param, buf_key: str, *wargs, **wkw) -> None:
@@ -234,8 +246,8 @@ class TrainEngine:
             assert (len(segs) == 1 and segs[0][0] % 8 == 0) or \
                 (all(s[1] % 16 == 0 for s in segs) and all(segs[i][0] + segs[i][1] == segs[i + 1][0] for i in range(len(segs) - 1))), \
                 "dgrad needs contiguous 16-channel-aligned input segments"
-            wd = conv.weight.detach().float().flip(2, 3, 4).transpose(0, 1).contiguous()   # [cin, cout, k, k, k]
-            self._dgrad(draw, cout, wd, self.grad_of(src), segs[0][0])
+            pwd = self._packed(conv.weight, "dgrad", lambda: K.PackPlan.dgrad(conv.weight))   # flipped, [cin, cout, k, k, k]
+            self._dgrad(draw, cout, pwd, self.grad_of(src), segs[0][0])
 
     def _bwd_convt(self, op):
         src, dst, up = op["src"], op["dst"], op["up"]
@@ -249,8 +261,8 @@ class TrainEngine:
         self._wgrad_async(up.weight, "ws.dyu", src, [(0, cin)], dyu_t, f, 0, 8 * f, 1, up.weight.shape, transposed=True)
         if up.bias is not None:
             self.grads[up.bias] = self._channel_sums(dyu, 0, 8 * f).view(8, f).sum(0)
-        wd = up.weight.detach().float().reshape(cin, f, 8).permute(0, 2, 1).reshape(cin, 8 * f, 1, 1, 1).contiguous()
-        self._dgrad(dyu, 8 * f, wd, self.grad_of(src), 0)
+        pwd = self._packed(up.weight, "convt_dgrad", lambda: K.PackPlan.convt_dgrad(up.weight))
+        self._dgrad(dyu, 8 * f, pwd, self.grad_of(src), 0)
 
     def _bwd_logits(self, op, dlogits: Tensor):
         src, conv = op["src"], op["conv"]
@@ -262,11 +274,8 @@ class TrainEngine:
         self.grads[conv.weight] = K.conv3d_wgrad(src, [(0, cin)], dl.t, dl.cbt, 0, k, 1, conv.weight.shape)
         if conv.bias is not None:
             self.grads[conv.bias] = self._channel_sums(dl, 0, kp)[:k]
-        wd = conv.weight.detach().float().reshape(k, cin).t().reshape(cin, k, 1, 1, 1).contiguous()
-        pw = K.pack_conv_weight(wd, None, False, [k], use_bias=False)
-        a_cb = K.a_chunk_table(dl, [0], [k], False)
-        g = self.grad_of(src)
-        K.conv3d(dl, pw, a_cb, g.t, _lib.OUT_BLOCKED_BF16, dst_cbt=g.cbt, dst_cb_off=0)
+        pwd = self._packed(conv.weight, "k1_dgrad", lambda: K.PackPlan.k1_dgrad(conv.weight))
+        self._dgrad(dl, k, pwd, self.grad_of(src), 0)
 
     def _bwd_convb(self, op):
         src, dst, conv, c0 = op["src"], op["dst"], op["conv"], op["dst_c0"]
@@ -276,11 +285,8 @@ class TrainEngine:
         if conv.bias is not None:
             self.grads[conv.bias] = self._channel_sums(g, c0, cout)
         # dgrad reads the gradient region in place: view it as a blocked tensor through the K-chunk table
-        wd = conv.weight.detach().float().reshape(cout, cin).t().reshape(cin, cout, 1, 1, 1).contiguous()
-        pw = K.pack_conv_weight(wd, None, False, [cout], use_bias=False)
-        a_cb = K.a_chunk_table(g, [c0], [cout], False)
-        gs = self.grad_of(src)
-        K.conv3d(g, pw, a_cb, gs.t, _lib.OUT_BLOCKED_BF16, dst_cbt=gs.cbt, dst_cb_off=op["segs"][0][0] // 8)
+        pwd = self._packed(conv.weight, "k1_dgrad", lambda: K.PackPlan.k1_dgrad(conv.weight))
+        self._dgrad(g, cout, pwd, self.grad_of(src), op["segs"][0][0], dy_c0=c0)
 
     @torch.no_grad()
     def backward(self, dlogits: Tensor, reducer=None) -> Dict[Tensor, Tensor]:

@@ -1052,3 +1052,106 @@ def focal_tversky_golden_case():
     want = focal_loss(g["logits"], g["target"], alpha=w, gamma=1.5).item()
     got = FocalLoss(alpha=w, gamma=1.5)(lg, tg).item()
     assert abs(got - want) < 1e-5 * max(1.0, abs(want)), (got, want)
+
+
+# ------------------------------------------------------------------------------------------------ N1: trainer step glue
+def weights_repack_case():
+    """mmseg_weights_repack (kernels.PackPlan) against the ATen restatement pack_conv_weight, bit for bit, in every form
+    the engines use: forward (plain / concat segments / first layer / 1x1 with bias / ConvTranspose with bias), the hi / lo
+    split modes in bf16 and fp16, and the dgrad forms against the flip / transpose / permute chains they replace."""
+    torch.manual_seed(0)
+    g = lambda *sh: torch.randn(*sh, device=DEV) * 0.1
+    cases = []
+    for mode in (False, "parity", "fp16", "fp16w2", "fp16a2", "fp16x3"):
+        cases += [("fwd", g(32, 32, 3, 3, 3), None, mode, None, False),
+                  ("fwd-cat", g(64, 96, 3, 3, 3), None, mode, [40, 56], False),      # segments padded to 48 and 64
+                  ("fwd-first", g(32, 2, 3, 3, 3), None, mode, [2], False),
+                  ("fwd-k1-bias", g(24, 64, 1, 1, 1), g(24), mode, None, False),   # 24 columns padded to 32
+                  ("convt", g(64, 32, 2, 2, 2), g(32), mode, None, True)]
+    for name, w, b, mode, seg, tr in cases:
+        want = K.pack_conv_weight(w, b, mode, seg, use_bias=b is not None, transposed=tr)
+        plan = K.PackPlan.forward(w, b, mode, seg, use_bias=b is not None, transposed=tr)
+        got = plan.run()
+        assert got.w.shape == want.w.shape and got.w.dtype == want.w.dtype, (name, mode, got.w.shape, want.w.shape)
+        assert torch.equal(got.w.view(torch.int16), want.w.view(torch.int16)), (name, mode)
+        assert (got.NT, got.n_ntiles, got.n_kchunks, got.n_out, got.out_channels, got.cin, got.ksize) == \
+               (want.NT, want.n_ntiles, want.n_kchunks, want.n_out, want.out_channels, want.cin, want.ksize), (name, mode)
+        if b is not None:
+            assert torch.equal(got.bias, want.bias), (name, mode)
+    # the packed buffer follows the LIVE parameter: an in-place update + run() == a fresh pack
+    w = g(32, 32, 3, 3, 3)
+    plan = K.PackPlan.forward(w, None, False, None, use_bias=False)
+    first = plan.run().w.clone()
+    w.mul_(1.5)
+    again = plan.run().w
+    assert plan.pc.w.data_ptr() == again.data_ptr() and not torch.equal(first, again)
+    assert torch.equal(again.view(torch.int16), K.pack_conv_weight(w, None, False, None, use_bias=False).w.view(torch.int16))
+    # dgrad forms vs the ATen chains of round 1
+    w = g(48, 32, 3, 3, 3)
+    wd = w.flip(2, 3, 4).transpose(0, 1).contiguous()
+    want = K.pack_conv_weight(wd, None, False, [48], use_bias=False)
+    assert torch.equal(K.PackPlan.dgrad(w).run().w.view(torch.int16), want.w.view(torch.int16))
+    up = g(64, 32, 2, 2, 2)
+    wd = up.reshape(64, 32, 8).permute(0, 2, 1).reshape(64, 256, 1, 1, 1).contiguous()
+    want = K.pack_conv_weight(wd, None, False, [256], use_bias=False)
+    assert torch.equal(K.PackPlan.convt_dgrad(up).run().w.view(torch.int16), want.w.view(torch.int16))
+    oc = g(8, 32, 1, 1, 1)
+    wd = oc.reshape(8, 32).t().reshape(32, 8, 1, 1, 1).contiguous()
+    want = K.pack_conv_weight(wd, None, False, [8], use_bias=False)
+    assert torch.equal(K.PackPlan.k1_dgrad(oc).run().w.view(torch.int16), want.w.view(torch.int16))
+    print(f"[weights_repack] {len(cases)} forward forms + 3 dgrad forms bit-identical to the ATen packing", flush=True)
+
+
+def fused_adamw_case():
+    """optim.FusedAdamW (mmseg_adamw_multi) vs torch.optim.AdamW over several steps with a changing learning rate, odd
+    tensor sizes, a parameter without gradient, state_dict round trip into torch's optimizer and back."""
+    from mmseg_b200.optim import FusedAdamW
+    torch.manual_seed(1)
+    shapes = [(32, 2, 3, 3, 3), (32,), (64, 32, 3, 3, 3), (7,), (8, 32, 1, 1, 1), (100003,), (3,)]
+    pa = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    kw = dict(lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-2)
+    oa, ob = FusedAdamW(pa, **kw), torch.optim.AdamW(pb, **kw)
+    for it in range(6):
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            if i == len(pa) - 1 and it < 2:
+                continue                                   # a parameter that receives no gradient at first
+            gr = torch.randn(a.shape, device=DEV) * (1.0 + it)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        if it == 3:
+            for o in (oa, ob):
+                o.param_groups[0]["lr"] = 1e-3             # a scheduler step
+        v0 = pa[0]._version
+        oa.step()
+        ob.step()
+        assert pa[0]._version > v0, "the in-place update must bump the parameter version"
+        oa.zero_grad()
+        ob.zero_grad()
+    worst = 0.0
+    for a, b in zip(pa, pb):
+        worst = max(worst, ((a - b).abs().max() / b.abs().max().clamp_min(1e-6)).item())
+    sa, sb = oa.state_dict(), ob.state_dict()
+    for k in sb["state"]:
+        for name in ("exp_avg", "exp_avg_sq"):
+            d = (sa["state"][k][name] - sb["state"][k][name]).abs().max().item()
+            worst = max(worst, d / sb["state"][k][name].abs().max().clamp_min(1e-12).item())
+        assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"])
+    print(f"[fused adamw] 6 steps, 7 tensors: worst relative difference vs torch.optim.AdamW {worst:.2e}", flush=True)
+    assert worst < 2e-5
+    # state_dict interchange: ours -> torch -> one more step on both
+    oc = torch.optim.AdamW(pb, **kw)
+    oc.load_state_dict(sa)
+    od = FusedAdamW(pa, **kw)
+    od.load_state_dict(sb)
+    for a, b in zip(pa, pb):
+        gr = torch.randn(a.shape, device=DEV)
+        a.grad, b.grad = gr.clone(), gr.clone()
+    od.step()
+    oc.step()
+    worst2 = max(((a - b).abs().max() / b.abs().max().clamp_min(1e-6)).item() for a, b in zip(pa, pb))
+    assert worst2 < 4e-5, worst2
+    # zero_grad fused into the step
+    for a in pa:
+        a.grad = torch.ones_like(a)
+    od.step(zero_grad=True)
+    assert all(float(a.grad.abs().max()) == 0.0 for a in pa)

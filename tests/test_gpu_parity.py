@@ -260,3 +260,12 @@ def test_late_early_fusion_and_head():
 
 def test_focal_tversky_golden():
     _c().focal_tversky_golden_case()
+
+
+# ------------------------------------------------------------------------------------------------ N1: trainer step glue
+def test_weights_repack_matches_aten_packing():
+    _c().weights_repack_case()
+
+
+def test_fused_adamw_matches_torch():
+    _c().fused_adamw_case()
