@@ -382,8 +382,8 @@ int mmseg_gather_f32(const float* src, const int32_t* idx, float* dst, int32_t n
 /*
  * torch.optim.AdamW.step() (reference src/trainer/trainer.py:115-117, stepped at :245-248) over a whole list of fp32
  * tensors in one launch: decoupled weight decay, bias correction, optional zeroing of the gradients (optimizer.zero_grad).
- * tensors: device array of mmseg_adamw_tensor; chunks: device array of (tensor index, chunk index) pairs, one per CTA,
- * 8192 elements per chunk; step: device fp32 counter (incremented); hyper: device fp32[6] =
+ * tensors: device array of n_tensors mmseg_adamw_tensor (each with its own device fp32 step counter, incremented by the
+ * call); chunks: device array of (tensor index, chunk index) pairs, one per CTA, 8192 elements per chunk; hyper: device fp32[6] =
  * {lr, beta1, beta2, eps, weight_decay, grad_scale} (grad_scale multiplies every gradient, e.g. 1/world after a summing
  * all-reduce).  Graph-capturable: no host-side state.
  */
@@ -392,10 +392,11 @@ typedef struct {
   const float* g;
   float* m;
   float* v;
+  float* step;
   int64_t n;
 } mmseg_adamw_tensor;
 #define MMSEG_ADAMW_CHUNK 8192
-int mmseg_adamw_multi(const void* tensors, const int32_t* chunks, int32_t n_chunks, float* step, const float* hyper,
+int mmseg_adamw_multi(const void* tensors, int32_t n_tensors, const int32_t* chunks, int32_t n_chunks, const float* hyper,
                       int32_t zero_grad, void* stream);
 
 #ifdef __cplusplus

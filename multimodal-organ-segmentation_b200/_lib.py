@@ -52,7 +52,8 @@ class WgradArgs(C.Structure):
 
 
 class AdamwTensor(C.Structure):
-    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int64)]
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("step", C.c_void_p),
+                ("n", C.c_int64)]
 
 
 ADAMW_CHUNK = 8192
@@ -128,7 +129,7 @@ SYMBOLS = {
     "mmseg_conv1x1_logits": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _i32, _vp, _i32, _vp]),
     "mmseg_weights_repack": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
     "mmseg_gather_f32": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
-    "mmseg_adamw_multi": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _vp]),
+    "mmseg_adamw_multi": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp]),
     "mmseg_maxpool3d_2": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
 }
 

@@ -77,8 +77,8 @@ __global__ void gather_f32_kernel(const float* __restrict__ src, const int* __re
 // torch.optim.AdamW semantics (decoupled decay, no amsgrad, maximize = false):
 //   p <- p * (1 - lr * wd);  m <- b1 m + (1 - b1) g;  v <- b2 v + (1 - b2) g^2;
 //   p <- p - (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
-// `step` is a DEVICE counter (fp32; a 1-thread kernel increments it stream-ordered behind the update) and the
-// hyper-parameters are a device array {lr, beta1, beta2, eps, weight_decay, grad_scale}, so the whole optimizer step
+// Every tensor has its own DEVICE step counter (fp32; a small kernel increments them stream-ordered behind the update)
+// and the hyper-parameters are a device array {lr, beta1, beta2, eps, weight_decay, grad_scale}, so the whole optimizer step
 // can sit in a captured CUDA graph and still follow a learning-rate schedule.  One launch covers every tensor of the list: chunk c of the
 // launch = (tensor, offset) from the caller-built chunk table.
 struct AdamwTensor {
@@ -86,22 +86,23 @@ struct AdamwTensor {
   const float* g;
   float* m;
   float* v;
+  float* step;     // this tensor's own device-side step counter (fp32 scalar), like torch.optim.AdamW(capturable=True)
   long long n;
 };
 constexpr int kAdamChunk = 8192;   // elements per block
 
 __global__ void __launch_bounds__(256)
 adamw_multi_kernel(const AdamwTensor* __restrict__ tensors, const int2* __restrict__ chunks, int n_chunks,
-                   const float* __restrict__ step_io, const float* __restrict__ hyper, int zero_grad) {
+                   const float* __restrict__ hyper, int zero_grad) {
   // hyper-parameters live on the device (lr changes under a scheduler; a captured graph must see the new value)
   const float lr = hyper[0], beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3], wd = hyper[4], grad_scale = hyper[5];
-  const float step = step_io[0] + 1.f;
+  const int2 ch = chunks[blockIdx.x];
+  const AdamwTensor t = tensors[ch.x];
+  const float step = t.step[0] + 1.f;
   const float bc1 = 1.f - powf(beta1, step);
   const float bc2 = 1.f - powf(beta2, step);
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
-  const int2 ch = chunks[blockIdx.x];
-  const AdamwTensor t = tensors[ch.x];
   const long long base = (long long)ch.y * kAdamChunk;
   const long long end = base + kAdamChunk < t.n ? base + kAdamChunk : t.n;
   const float decay = 1.f - lr * wd;
@@ -140,7 +141,10 @@ adamw_multi_kernel(const AdamwTensor* __restrict__ tensors, const int2* __restri
   }
 }
 
-__global__ void adamw_step_inc_kernel(float* step_io) { step_io[0] += 1.f; }
+__global__ void adamw_step_inc_kernel(const AdamwTensor* __restrict__ tensors, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tensors[i].step[0] += 1.f;
+}
 
 }  // namespace mmseg
 
@@ -172,16 +176,18 @@ extern "C" int mmseg_gather_f32(const float* src, const int32_t* idx, float* dst
   return check_launch("gather_f32_kernel");
 }
 
-extern "C" int mmseg_adamw_multi(const void* tensors, const int32_t* chunks, int32_t n_chunks, float* step,
+extern "C" int mmseg_adamw_multi(const void* tensors, int32_t n_tensors, const int32_t* chunks, int32_t n_chunks,
                                  const float* hyper, int32_t zero_grad, void* stream) {
-  if (!tensors || !chunks || !step || !hyper || n_chunks < 1) return fail(MMSEG_ERR_INVALID_ARG, "adamw_multi: bad arguments");
-  static_assert(sizeof(AdamwTensor) == 40, "mmseg_adamw_tensor layout");
+  if (!tensors || !chunks || !hyper || n_chunks < 1 || n_tensors < 1)
+    return fail(MMSEG_ERR_INVALID_ARG, "adamw_multi: bad arguments");
+  static_assert(sizeof(AdamwTensor) == sizeof(mmseg_adamw_tensor), "mmseg_adamw_tensor layout");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   adamw_multi_kernel<<<(unsigned)n_chunks, 256, 0, st>>>(reinterpret_cast<const AdamwTensor*>(tensors),
-                                                        reinterpret_cast<const int2*>(chunks), n_chunks, step, hyper,
+                                                        reinterpret_cast<const int2*>(chunks), n_chunks, hyper,
                                                         zero_grad ? 1 : 0);
   int rc = check_launch("adamw_multi_kernel");
   if (rc) return rc;
-  adamw_step_inc_kernel<<<1, 1, 0, st>>>(step);   // stream-ordered behind every block's read of the counter
+  // the counters advance stream-ordered behind every block's read of them
+  adamw_step_inc_kernel<<<(n_tensors + 255) / 256, 256, 0, st>>>(reinterpret_cast<const AdamwTensor*>(tensors), n_tensors);
   return check_launch("adamw_step_inc_kernel");
 }

@@ -229,40 +229,50 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 // flight), and the slices are combined in warp order through shared memory — every element sees the same association
 // whatever the grid.  (The first version had one thread per weight element walking all partials with a 128*ncols
 // stride: 175-500 GB/s, 1.05 ms of a 20 ms training step.)
-constexpr int kRedSlices = 8;
-__global__ void __launch_bounds__(32 * kRedSlices)
+// S slices x R rows per block (S * R = 8 warps): S = 8 when there are many partials, 1 when a single CTA produced the
+// partial (the deep layers: pure layout change).  Only the 3*CIG valid accumulator rows get blocks.
+template <int S>
+__global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, int n_part, int ncols, int n_cot, int NTc, int CIG, int KT,
                     int Cin, int Cout_gemm, int Cout, int mode, const int* __restrict__ ci_of_pos,
                     float* __restrict__ dst) {
-  __shared__ double sm[kRedSlices][32];
-  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  constexpr int R = 8 / S;
+  __shared__ double sm[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slice = warp % S, rl = warp / S;
+  const int valid_rows = KT * CIG;
+  const int row_blocks = (valid_rows + R - 1) / R;
   const int cols_blocks = (ncols + 31) / 32;
   int b = blockIdx.x;
   const int cblk = b % cols_blocks; b /= cols_blocks;
-  const int row = b % 128;                       // accumulator row = (dx, ci inside the group)
-  const int pair = b / 128;                      // (input-channel group, output-channel group)
+  const int rblk = b % row_blocks;
+  const int pair = b / row_blocks;                // (input-channel group, output-channel group)
+  const int row = rblk * R + rl;                  // accumulator row = (dx, ci inside the group)
   const int col = cblk * 32 + lane;
   const int dx = row / CIG, cil = row - dx * CIG;
   const int cig = pair / n_cot, cot = pair - cig * n_cot;
-  const int ci = (dx < KT) ? ci_of_pos[cig * CIG + cil] : -1;   // rows >= KT*CIG multiplied garbage: never stored
+  const int ci = (row < valid_rows) ? ci_of_pos[cig * CIG + cil] : -1;
   double s = 0.0;
   if (col < ncols && ci >= 0) {
     const float* p = partial + (((size_t)pair * n_part) * 128 + row) * ncols + col;
     const size_t kstride = (size_t)128 * ncols;
     int k = slice;
-    for (; k + 3 * kRedSlices < n_part; k += 4 * kRedSlices) {
-      const float v0 = p[(size_t)k * kstride], v1 = p[(size_t)(k + kRedSlices) * kstride];
-      const float v2 = p[(size_t)(k + 2 * kRedSlices) * kstride], v3 = p[(size_t)(k + 3 * kRedSlices) * kstride];
+    for (; k + 3 * S < n_part; k += 4 * S) {
+      const float v0 = p[(size_t)k * kstride], v1 = p[(size_t)(k + S) * kstride];
+      const float v2 = p[(size_t)(k + 2 * S) * kstride], v3 = p[(size_t)(k + 3 * S) * kstride];
       s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
     }
-    for (; k < n_part; k += kRedSlices) s += (double)p[(size_t)k * kstride];
+    for (; k < n_part; k += S) s += (double)p[(size_t)k * kstride];
   }
-  sm[slice][lane] = s;
-  __syncthreads();
-  if (slice != 0 || col >= ncols || ci < 0) return;
-  double t = 0.0;
+  if (S > 1) {
+    sm[warp][lane] = s;
+    __syncthreads();
+    if (slice != 0) return;
+    s = 0.0;
 #pragma unroll
-  for (int w = 0; w < kRedSlices; ++w) t += sm[w][lane];
+    for (int w = 0; w < S; ++w) s += sm[rl * S + w][lane];
+  }
+  if (col >= ncols || ci < 0) return;
   const int dy = col / (KT * NTc), r2 = col - dy * (KT * NTc);
   const int dzr = r2 / NTc, col_l = r2 - dzr * NTc;
   const int dz = KT - 1 - dzr;
@@ -277,7 +287,7 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int n_part, int ncols, in
     const int tap8 = n / Cout, co = n - tap8 * Cout;
     o = ((size_t)ci * Cout + co) * 8 + tap8;
   }
-  dst[o] = (float)t;
+  dst[o] = (float)s;
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -414,10 +424,19 @@ extern "C" int mmseg_wgrad_reduce(const float* partial, int32_t n_part, int32_t 
     return fail(MMSEG_ERR_INVALID_ARG, "wgrad_reduce: bad arguments");
   const int KT = ksize;
   const int ncols = KT * KT * cot_blocks * 8;
-  const long long blocks = (long long)n_cig * n_cot * 128 * ((ncols + 31) / 32);
+  const int S = n_part >= 16 ? 8 : (n_part >= 4 ? 4 : (n_part >= 2 ? 2 : 1));
+  const int R = 8 / S;
+  const int valid_rows = KT * cig_blocks * 8;
+  const long long blocks = (long long)n_cig * n_cot * ((valid_rows + R - 1) / R) * ((ncols + 31) / 32);
   if (blocks > 2147483647LL) return fail(MMSEG_ERR_INVALID_ARG, "wgrad_reduce: grid too large");
-  wgrad_reduce_kernel<<<(unsigned)blocks, 32 * kRedSlices, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      partial, n_part, ncols, n_cot, cot_blocks * 8, cig_blocks * 8, KT, Cin, Cout_gemm, Cout, transposed ? 1 : 0,
-      ci_of_pos, dst);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define MMSEG_RED(SV)                                                                                                  \
+  wgrad_reduce_kernel<SV><<<(unsigned)blocks, 256, 0, st>>>(partial, n_part, ncols, n_cot, cot_blocks * 8, cig_blocks * 8, \
+                                                            KT, Cin, Cout_gemm, Cout, transposed ? 1 : 0, ci_of_pos, dst)
+  if (S == 8) MMSEG_RED(8);
+  else if (S == 4) MMSEG_RED(4);
+  else if (S == 2) MMSEG_RED(2);
+  else MMSEG_RED(1);
+#undef MMSEG_RED
   return check_launch("wgrad_reduce_kernel");
 }

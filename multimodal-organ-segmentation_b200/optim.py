@@ -22,13 +22,16 @@ class FusedAdamW(torch.optim.Optimizer):
             raise ValueError("invalid AdamW hyper-parameter")
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         self._plans: Dict[int, dict] = {}          # per param group: device tables, keyed by the gradient addresses
-        self._hyper_host: Dict[int, list] = {}
+        self._hyper: Dict[int, dict] = {}          # per param group: device hyper-parameter array + the values it holds
+        self._captured: List[dict] = []
         self.grad_scale = 1.0
 
     # ------------------------------------------------------------------ state
     def _init_state(self, p: torch.Tensor) -> dict:
         st = self.state[p]
         if len(st) == 0:
+            # like torch.optim.AdamW(capturable=True): a device-side fp32 step counter PER parameter (a parameter that
+            # receives no gradient in some step does not advance)
             st["step"] = torch.zeros((), dtype=torch.float32, device=p.device)
             st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
             st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
@@ -43,36 +46,35 @@ class FusedAdamW(torch.optim.Optimizer):
                 raise RuntimeError("FusedAdamW updates contiguous fp32 CUDA parameters (there is no CPU fallback)")
             if p.grad.dtype != torch.float32 or not p.grad.is_contiguous():
                 p.grad = p.grad.float().contiguous()
-        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in params)
+        states = [self._init_state(p) for p in params]
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), st["step"].data_ptr()) for p, st in zip(params, states))
         capturing = torch.cuda.is_current_stream_capturing()
         plan = self._plans.get(gi)
         if plan is not None and plan["key"] == key and plan["capturing"] == capturing:
             return plan
         dev = params[0].device
-        states = [self._init_state(p) for p in params]
-        # ONE device step counter per group: every parameter's `step` is a view of it (they advance together)
-        shared = plan["step"] if plan is not None else None
-        if shared is None or any(st["step"].data_ptr() != shared.data_ptr() for st in states):
-            # first build, or load_state_dict replaced the per-parameter counters (equal values): unify them
-            shared = torch.full((1,), float(states[0]["step"]), dtype=torch.float32, device=dev)
-            for st in states:
-                st["step"] = shared.view(())
-        step = shared
         tens = (_lib.AdamwTensor * len(params))()
         chunks: List[int] = []
         for i, (p, st) in enumerate(zip(params, states)):
+            if st["step"].dtype != torch.float32 or st["step"].device != dev:   # e.g. a checkpoint written on the CPU
+                st["step"] = st["step"].to(dev, torch.float32)
             tens[i].p, tens[i].g = p.data_ptr(), p.grad.data_ptr()
-            tens[i].m, tens[i].v, tens[i].n = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()
+            tens[i].m, tens[i].v, tens[i].step = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), st["step"].data_ptr()
+            tens[i].n = p.numel()
             for c in range((p.numel() + _lib.ADAMW_CHUNK - 1) // _lib.ADAMW_CHUNK):
                 chunks += [i, c]
-        raw = bytes(tens)
-        # pinned staging: the host->device copies of the tables are stream-ordered (and capturable)
-        t_host = torch.frombuffer(bytearray(raw), dtype=torch.uint8).pin_memory()
+        # pinned staging: the host->device copies of the tables are stream-ordered (and capturable); a capture gets its
+        # own staging buffers so that a later eager step cannot change what a replay uploads
+        t_host = torch.frombuffer(bytearray(bytes(tens)), dtype=torch.uint8).pin_memory()
         c_host = torch.tensor(chunks, dtype=torch.int32).pin_memory()
-        plan = {"key": key, "capturing": capturing, "n_chunks": len(chunks) // 2, "step": step,
+        hyper = self._hyper.get(gi)
+        if hyper is None:
+            hyper = self._hyper[gi] = {"dev": torch.zeros(6, dtype=torch.float32, device=dev), "vals": None}
+        plan = {"key": key, "capturing": capturing, "n_chunks": len(chunks) // 2, "n_tensors": len(params),
                 "tensors": t_host.to(dev, non_blocking=True), "chunks": c_host.to(dev, non_blocking=True),
-                "hyper": torch.zeros(6, dtype=torch.float32, device=dev), "hyper_vals": None,
                 "_keep": (t_host, c_host)}
+        if capturing:
+            self._captured.append(plan)     # the graph replays these uploads: keep the staging buffers alive
         self._plans[gi] = plan
         return plan
 
@@ -84,16 +86,16 @@ class FusedAdamW(torch.optim.Optimizer):
         """Push the groups' current hyper-parameters (lr under a scheduler, grad_scale) to the device arrays the kernel
         reads.  Called by step(); call it yourself before replaying a captured graph after the values changed."""
         for gi, group in enumerate(self.param_groups):
-            plan = self._plans.get(gi)
-            if plan is None:
+            hyper = self._hyper.get(gi)
+            if hyper is None:
                 continue
             vals = (float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]),
                     float(group["weight_decay"]), float(self.grad_scale))
-            if vals != plan["hyper_vals"]:
+            if vals != hyper["vals"]:
                 if torch.cuda.is_current_stream_capturing():
                     raise RuntimeError("hyper-parameters changed inside a CUDA-graph capture; call sync_hyper() before")
-                plan["hyper"].copy_(torch.tensor(vals, dtype=torch.float32))
-                plan["hyper_vals"] = vals
+                hyper["dev"].copy_(torch.tensor(vals, dtype=torch.float32))
+                hyper["vals"] = vals
 
     # ------------------------------------------------------------------ step
     @torch.no_grad()
@@ -110,8 +112,8 @@ class FusedAdamW(torch.optim.Optimizer):
             if plan is None:
                 continue
             self.sync_hyper()
-            K._call("mmseg_adamw_multi", C.c_void_p(plan["tensors"].data_ptr()), C.c_void_p(plan["chunks"].data_ptr()),
-                    plan["n_chunks"], C.c_void_p(plan["step"].data_ptr()), C.c_void_p(plan["hyper"].data_ptr()),
+            K._call("mmseg_adamw_multi", C.c_void_p(plan["tensors"].data_ptr()), plan["n_tensors"],
+                    C.c_void_p(plan["chunks"].data_ptr()), plan["n_chunks"], C.c_void_p(self._hyper[gi]["dev"].data_ptr()),
                     1 if zero_grad else 0, K._stream())
             # parameters changed in place behind autograd's back: bump the version counters that the packed-weight
             # caches and the captured inference graphs key on
