@@ -498,6 +498,13 @@ def run_ours(args):
 
     train_res = secondary_train("train")
     train5_res = secondary_train("train5")
+    attn_res = None
+    if world == 1 and not args.no_train:
+        try:
+            attn_res = attention_measure(dev)
+        except Exception as e:   # never allowed to break the headline line
+            torch.cuda.synchronize()
+            attn_res = {"error": f"{type(e).__name__}: {e}"}
 
     cfg = workload_config(args, world)
     cfg["numeric_mode"] = headline
@@ -516,7 +523,7 @@ def run_ours(args):
                          "(max-abs <= 2e-2, rel-L2 <= 1e-3, labels >= 99.9 %, Dice within 1e-3 of the reference)",
         "parity": ladder or None, "gates": GATE_LIMITS,
         "label_agreement_vs_n1": agreement_vs_n1,
-        "train": train_res, "train5": train5_res,
+        "train": train_res, "train5": train5_res, "attention": attn_res,
     }
     emit(line)
     if world > 1:
@@ -677,6 +684,65 @@ def train_measure(steps, warmup, world, rank, dev, use_graph=True, cpu=False, wh
     return res
 
 
+# ------------------------------------------------------------------------------------------------ attention leg
+# (C, spatial side, CPU seconds of the reference module at B = 2 from BASELINE.md §2, 8 vCPU)
+ATTN_SHAPES = [(512, 8, 1.30), (256, 16, 0.37), (128, 24, 4.56), (128, 32, None)]
+
+
+def attention_measure(dev, steps=10, warmup=3):
+    """CrossAttentionFusion forward (reference src/models/fusion/attention_fusion.py:120-164) at B = 2, 4 heads: the fused
+    tcgen05 attention core (softmax(Q K^T / sqrt(hd)) V without the N x N matrix) and the whole module (q / kv / out
+    projections on the conv kernel, residual + InstanceNorm).  TFLOP/s against the algorithmic 4*B*N^2*C of the core."""
+    import mmseg_b200  # noqa: F401
+    from mmseg_b200 import kernels as K
+    from mmseg_b200.kernels import Blocked
+    from mmseg_b200.src.models.fusion.attention_fusion import CrossAttentionFusion
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    tf_peak = json.load(open(pk))["bf16_tflops_sustained"] if os.path.exists(pk) else 1400.0
+    out = []
+    B = 2
+    for C, S, cpu_s in ATTN_SHAPES:
+        torch.manual_seed(0)
+        m = CrossAttentionFusion(C, num_heads=4).to(dev).eval()
+        g = torch.Generator(device=dev).manual_seed(1)
+        q_in, kv_in, dst = (Blocked(B, C, S, S, S, False, dev) for _ in range(3))
+        K.pack_ncdhw(torch.randn((B, C, S, S, S), device=dev, generator=g), q_in)
+        K.pack_ncdhw(torch.randn((B, C, S, S, S), device=dev, generator=g), kv_in)
+        with torch.no_grad():
+            for _ in range(warmup):
+                m.forward_blocked(q_in, kv_in, dst)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                m.forward_blocked(q_in, kv_in, dst)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_module = e0.elapsed_time(e1) / steps
+            K.PROFILE = []
+            for _ in range(steps):
+                m.forward_blocked(q_in, kv_in, dst)
+            torch.cuda.synchronize()
+            prof, K.PROFILE = K.PROFILE, None
+        core = [a.elapsed_time(b) for name, _, a, b in prof if name == "mmseg_cross_attention_fwd"]
+        ms_core = sum(core) / len(core)
+        N = S ** 3
+        flops = 4.0 * B * N * N * C
+        proj = 8.0 * B * N * C * C
+        row = {"C": C, "tokens": N, "batch": B, "heads": 4, "head_dim": C // 4, "core_ms": ms_core,
+               "core_tflops": flops / (ms_core * 1e-3) / 1e12, "core_frac_of_tensor_peak": flops / (ms_core * 1e-3) / 1e12 / tf_peak,
+               "module_ms": ms_module, "module_tflops": (flops + proj) / (ms_module * 1e-3) / 1e12,
+               "reference_cpu_s_8vcpu": cpu_s, "speedup_vs_reference_cpu": (cpu_s / (ms_module * 1e-3)) if cpu_s else None}
+        out.append(row)
+        log(f"[attention] C={C} N={N}: core {ms_core:.3f} ms = {row['core_tflops']:.0f} TFLOP/s "
+            f"({100 * row['core_frac_of_tensor_peak']:.0f}% of sustained peak), module {ms_module:.3f} ms"
+            + (f", reference CPU {cpu_s:.2f} s" if cpu_s else ""))
+        del m, q_in, kv_in, dst
+        torch.cuda.empty_cache()
+    return {"metric": "CrossAttentionFusion forward (B=2, 4 heads), algorithmic 4*B*N^2*C", "peak_tflops": tf_peak, "shapes": out}
+
+
 def run_train(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -731,7 +797,7 @@ def main():
     ap.add_argument("--no-ladder", action="store_true", help="skip the throughput of the non-headline numeric modes")
     ap.add_argument("--no-selfcheck", action="store_true", help="N>1: skip the sharded-vs-single-GPU label comparison")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline / parity sample")
-    ap.add_argument("--workload", default="inference", choices=["inference", "train", "train5"],
+    ap.add_argument("--workload", default="inference", choices=["inference", "train", "train5", "attention"],
                     help="inference = headline sliding-window voxels/s (default); train = DualEncoder CT+PET 128^3 B=2 "
                          "samples/s (configs[1]); train5 = 4-modality attention-gate DualEncoder 128^3 B=4 (configs[4])")
     ap.add_argument("--no-graph", action="store_true", help="train workload: do not capture the step in a CUDA graph")
@@ -741,6 +807,9 @@ def main():
         run_reference(args)
     elif args.workload in ("train", "train5"):
         run_train(args)
+    elif args.workload == "attention":
+        torch.cuda.set_device(0)
+        emit(attention_measure(torch.device("cuda", 0)))
     else:
         run_ours(args)
 

@@ -3,8 +3,8 @@ copy travels to the GPU box like a built .so) — the reference arm of bench.py 
 reference's own `build_model` / `forward` instead of the oracle port.
 
 The reference has no setup.py / pyproject.toml (nothing for `pip install --target baseline/_ref` to build), so the
-install is a plain copy of the packages the path needs: src/__init__.py, src/models/** and src/trainer/** (stock files,
-byte for byte).  Nothing under baseline/_ref is ever committed, imported by the product, or edited.
+install is a plain copy of the packages the path needs: src/__init__.py, src/models/**, src/trainer/** and — for the
+drop-in test of the CLI — main.py, src/utils/**, src/data/**, configs/default.yaml (stock files, byte for byte).  Nothing under baseline/_ref is ever committed, imported by the product, or edited.
 
 TEST / BENCH INFRASTRUCTURE ONLY: tests/, __graft_entry__ and bench.py's cpu legs may import it; the product never does.
 """
@@ -15,7 +15,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
 DST = os.path.join(ROOT, "baseline", "_ref")
-PARTS = ["src/__init__.py", "src/models", "src/trainer"]
+# the hot-path packages + the CLI and its host-side helpers (tests/test_dropin_main.py drives the reference's own
+# main.py with src.models / src.trainer shadowed by this repo's mirror)
+PARTS = ["src/__init__.py", "src/models", "src/trainer", "src/utils", "src/data", "main.py", "configs/default.yaml"]
 
 
 def install(force: bool = False) -> bool:

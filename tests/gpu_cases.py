@@ -1155,3 +1155,64 @@ def fused_adamw_case():
         a.grad = torch.ones_like(a)
     od.step(zero_grad=True)
     assert all(float(a.grad.abs().max()) == 0.0 for a in pa)
+
+
+# ------------------------------------------------------------------------------------------------ the reference CLI
+def reference_cli_inference_case(tmp_dir):
+    """`python main.py --mode inference` of the REFERENCE (its own main.py / src.utils from baseline/_ref, unmodified)
+    running on this repo's drop-in `src.models` / `src.trainer`: parse_args -> default.yaml -> merge -> run_inference ->
+    build_model -> load_state_dict(checkpoint) -> Trainer.predict -> sliding window on the B200 -> label files.  The labels
+    are compared with the CPU oracle (reference arithmetic: constant blending, because the reference never forwards its
+    YAML `mode` key to MONAI)."""
+    import os
+    import numpy as np
+    from tests import dropin
+    from oracle.models import unet3d_forward
+    from oracle.sliding_window import sliding_window_inference as oswi
+    if not dropin.available():
+        import pytest
+        pytest.skip("baseline/_ref (reference CLI) not installed")
+    refmain, restore = dropin.load_reference_main()
+    try:
+        inp, out = tmp_dir / "input", tmp_dir / "pred"
+        (inp / "ct").mkdir(parents=True)
+        (inp / "pet").mkdir(parents=True)
+        g = torch.Generator().manual_seed(21)
+        vols = {}
+        for case, shape in (("case_a", (40, 48, 36)), ("case_b", (33, 32, 50))):
+            ct = torch.rand(shape, generator=g).numpy().astype(np.float32)
+            pet = (torch.rand(shape, generator=g) ** 3).numpy().astype(np.float32)
+            dropin.write_volume(inp / "ct" / f"{case}.nii.gz", ct)
+            dropin.write_volume(inp / "pet" / f"{case}.nii.gz", pet)
+            vols[case] = np.stack([ct, pet])
+        ck = tmp_dir / "model.pth"
+        argv = ["main.py", "--mode", "inference", "--model", "unet", "--fusion", "early", "--checkpoint", str(ck), "--input",
+                str(inp), "--output", str(out), "--output-dir", str(tmp_dir), "--device", "cuda", "--modalities", "CT", "PET"]
+        import sys
+        old = sys.argv
+        sys.argv = argv
+        try:
+            args = refmain.parse_args()
+        finally:
+            sys.argv = old
+        config = refmain.load_config(os.path.join(dropin.REF, "configs", "default.yaml"))
+        config = refmain.merge_config_with_args(config, args)
+        config["model"]["backbone"]["features"] = [16, 32, 64]          # a small net and roi keep the CPU oracle fast
+        config["inference"]["sliding_window"]["roi_size"] = [32, 32, 32]
+        from src.models import build_model                              # resolves to the drop-in factory
+        torch.manual_seed(3)
+        ref_model = build_model(config)
+        sd = {k: v.detach().cpu().clone() for k, v in ref_model.state_dict().items()}
+        torch.save({"epoch": 0, "model_state_dict": sd}, ck)
+        logger = refmain.get_logger("dropin")
+        refmain.run_inference(config, logger)
+        for case, vol in vols.items():
+            pred = dropin.read_volume(out / f"{case}_pred.nii.gz")
+            assert pred.shape == vol.shape[1:] and pred.dtype == np.uint8
+            want = oswi(torch.from_numpy(vol)[None], (32, 32, 32), 4, lambda w: unet3d_forward(sd, w), overlap=0.5,
+                        mode="constant").argmax(1)[0]
+            agree = (torch.from_numpy(pred.astype(np.int64)) == want).double().mean().item()
+            print(f"[reference CLI] {case} {vol.shape[1:]}: labels vs CPU oracle {agree * 100:.3f}%", flush=True)
+            assert agree >= 0.995, agree
+    finally:
+        restore()

@@ -269,3 +269,8 @@ def test_weights_repack_matches_aten_packing():
 
 def test_fused_adamw_matches_torch():
     _c().fused_adamw_case()
+
+
+def test_reference_cli_inference_on_dropin(tmp_path):
+    """The reference's own main.py --mode inference, end to end on the drop-in packages (tests/dropin.py)."""
+    _c().reference_cli_inference_case(tmp_path)
