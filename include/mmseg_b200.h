@@ -312,6 +312,18 @@ int mmseg_focal(const float* logits, const int64_t* target, int32_t B, int32_t C
  */
 int mmseg_cross_attention_fwd(const void* q, int32_t q_cbt, int32_t q_cb0, const void* kv, int32_t kv_cbt,
                               int32_t k_cb0, int32_t v_cb0, void* out, int32_t o_cbt, int32_t o_cb0, int32_t n_img,
+                              int32_t heads, int32_t head_dim, int64_t n_tok, float scale,
+                              float* lse /* optional [n_img][heads][n_tok]: saved for the backward */, void* stream);
+/*
+ * Backward of the fused attention (autograd through attention_fusion.py:144-155 in the reference), flash style by
+ * recomputation, deterministic: dsum = rowsum(dO o O) (workspace [n_img][heads][n_tok]), then one kernel per 128-key
+ * tile writes dK / dV and one per 128-query tile writes dQ (all blocked bf16 token tensors, same head layout as the
+ * forward; dK and dV live in one tensor `dkv` like K and V do).  lse: the forward's log-sum-exp output.
+ */
+int mmseg_cross_attention_bwd(const void* q, int32_t q_cbt, int32_t q_cb0, const void* kv, int32_t kv_cbt, int32_t k_cb0,
+                              int32_t v_cb0, const void* out, int32_t o_cbt, int32_t o_cb0, const void* d_out,
+                              int32_t do_cbt, int32_t do_cb0, const float* lse, float* dsum, void* dq, int32_t dq_cbt,
+                              int32_t dq_cb0, void* dkv, int32_t dkv_cbt, int32_t dk_cb0, int32_t dv_cb0, int32_t n_img,
                               int32_t heads, int32_t head_dim, int64_t n_tok, float scale, void* stream);
 /* y (fp32 blocked [n_img*cb][voxels][8]) = a + b (blocked bf16) and per-chunk (sum, sum of squares) partials
  * [n_img][n_chunks][cb*8][2] for mmseg_instnorm_finalize. */
@@ -359,6 +371,20 @@ int mmseg_modality_max(const void* src, int32_t n_img, int32_t src_cbt, int32_t 
 int mmseg_maxpool3d_2(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_cb_off, int32_t src_lo_off,
                       int32_t cb, int32_t Z, int32_t Y, int32_t X, void* dst, int32_t dst_cbt, int32_t dst_cb_off,
                       int32_t dst_lo_off, int32_t fmt, void* stream);
+
+/*
+ * Inference-edge preprocessing on the device: ModalitySpecificNormalize of the reference's data pipeline
+ * (src/data/transforms.py:362-404) on a [C][voxels] fp32 volume that is already in HBM.
+ *  channel_stats: per channel (max, mean, population std) -> stats[C][3]; deterministic two-stage reduction;
+ *                 partial = workspace of C * n_blocks * 3 doubles.
+ *  modality_normalize: kind[c] 0 copy | 1 CT window clip(v, a, b) -> (v - a) / (b - a) (transforms.py:380-387) |
+ *                 2 PET v / max when max > 0 (:389-394) | 3 z-score (v - mean) / (std + 1e-8) (MRI / US, :396-401).
+ * Resize(order=1) (transforms.py:215-250, scipy.ndimage.zoom) is mmseg_trilinear_resize (aligned corners).
+ */
+int mmseg_channel_stats(const float* vol, int32_t C, int64_t voxels, void* partial, int32_t n_blocks, float* stats,
+                        void* stream);
+int mmseg_modality_normalize(const float* src, float* dst, int32_t C, int64_t voxels, const int32_t* kind, const float* a,
+                             const float* b, const float* stats, void* stream);
 
 /*
  * Trainer step glue — the kernels either side of forward / backward.

@@ -114,7 +114,9 @@ SYMBOLS = {
     "mmseg_tversky_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
     "mmseg_focal": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _vp, _f32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "mmseg_cross_attention_fwd": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i64,
-                                            _f32, _vp]),
+                                            _f32, _vp, _vp]),
+    "mmseg_cross_attention_bwd": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _vp,
+                                            _vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i64, _f32, _vp]),
     "mmseg_add_stats": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _i32, _vp]),
     "mmseg_confusion_hist": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _vp]),
     "mmseg_channel_mean": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _i32, _vp]),
@@ -127,6 +129,8 @@ SYMBOLS = {
     "mmseg_groupnorm_finalize": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i64, _f32, _vp, _vp, _vp, _vp, _vp]),
     "mmseg_trilinear_resize": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
     "mmseg_conv1x1_logits": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _i32, _vp, _i32, _vp]),
+    "mmseg_channel_stats": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _vp, _vp]),
+    "mmseg_modality_normalize": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "mmseg_weights_repack": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
     "mmseg_gather_f32": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "mmseg_adamw_multi": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp]),

@@ -28,7 +28,7 @@ def _ptr(t: Optional[Tensor]) -> C.c_void_p:
 
 
 # kernels launched by each C-ABI entry point (bench.py reports the count as `gpu_launches`)
-KERNELS_PER_CALL = {"mmseg_dicece_fwd": 2, "mmseg_channel_mean": 2, "mmseg_modality_dot": 2, "mmseg_tversky_fwd": 2}
+KERNELS_PER_CALL = {"mmseg_cross_attention_bwd": 3, "mmseg_adamw_multi": 2, "mmseg_channel_stats": 2, "mmseg_dicece_fwd": 2, "mmseg_channel_mean": 2, "mmseg_modality_dot": 2, "mmseg_tversky_fwd": 2}
 LAUNCHES = [0]
 # when a list, every C-ABI call is bracketed by CUDA events on the current stream: (name, info, ev0, ev1)
 PROFILE: Optional[list] = None
@@ -728,17 +728,36 @@ def confusion_hist(pred: Tensor, target: Tensor, num_classes: int, counts: Tenso
 
 # --------------------------------------------------------------------------------------------- token cross attention
 def cross_attention(q: Blocked, q_c0: int, kv: Blocked, k_c0: int, v_c0: int, out: Blocked, o_c0: int, heads: int,
-                    head_dim: int, scale: float) -> None:
-    """out[:, head h] = softmax(Q_h K_h^T * scale) V_h over all voxels; head_dim is the (padded) per-head channel count."""
+                    head_dim: int, scale: float, lse: Optional[Tensor] = None) -> None:
+    """out[:, head h] = softmax(Q_h K_h^T * scale) V_h over all voxels; head_dim is the (padded) per-head channel count.
+    lse (optional fp32 [n_img, heads, n_tok]): log-sum-exp rows, saved for cross_attention_bwd."""
     _lib.require_device()
     assert not (q.split or kv.split or out.split) and q.fmt == kv.fmt == out.fmt == _lib.FMT_BF16, \
         "the attention kernel runs in bf16 mode"
     assert q.nvox == kv.nvox == out.nvox and q.n_img == kv.n_img == out.n_img
+    if lse is not None:
+        assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == q.n_img * heads * q.nvox
     if PROFILE is not None:
         _INFO[0] = {"flops": 4.0 * q.n_img * heads * q.nvox * q.nvox * head_dim,
                     "layer": f"attn h{heads} hd{head_dim} N{q.nvox} img{q.n_img}"}
     _call("mmseg_cross_attention_fwd", _ptr(q.t), q.cbt, q_c0 // 8, _ptr(kv.t), kv.cbt, k_c0 // 8, v_c0 // 8, _ptr(out.t),
-          out.cbt, o_c0 // 8, q.n_img, heads, head_dim, q.nvox, scale, _stream())
+          out.cbt, o_c0 // 8, q.n_img, heads, head_dim, q.nvox, scale, _ptr(lse), _stream())
+
+
+def cross_attention_bwd(q: Blocked, q_c0: int, kv: Blocked, k_c0: int, v_c0: int, out: Blocked, o_c0: int, d_out: Blocked,
+                        do_c0: int, lse: Tensor, dq: Blocked, dq_c0: int, dkv: Blocked, dk_c0: int, dv_c0: int, heads: int,
+                        head_dim: int, scale: float) -> None:
+    """dQ, dK, dV of cross_attention (blocked bf16, same head layout), by recomputation from q / kv / out / lse."""
+    _lib.require_device()
+    for b in (q, kv, out, d_out, dq, dkv):
+        assert not b.split and b.fmt == _lib.FMT_BF16 and b.nvox == q.nvox and b.n_img == q.n_img
+    dsum = torch.empty((q.n_img, heads, q.nvox), dtype=torch.float32, device=q.t.device)
+    if PROFILE is not None:
+        _INFO[0] = {"flops": 14.0 * q.n_img * heads * q.nvox * q.nvox * head_dim,
+                    "layer": f"attn-bwd h{heads} hd{head_dim} N{q.nvox} img{q.n_img}"}
+    _call("mmseg_cross_attention_bwd", _ptr(q.t), q.cbt, q_c0 // 8, _ptr(kv.t), kv.cbt, k_c0 // 8, v_c0 // 8, _ptr(out.t),
+          out.cbt, o_c0 // 8, _ptr(d_out.t), d_out.cbt, do_c0 // 8, _ptr(lse), _ptr(dsum), _ptr(dq.t), dq.cbt, dq_c0 // 8,
+          _ptr(dkv.t), dkv.cbt, dk_c0 // 8, dv_c0 // 8, q.n_img, heads, head_dim, q.nvox, scale, _stream())
 
 
 def add_stats(a: Blocked, a_c0: int, b: Blocked, b_c0: int, channels: int):

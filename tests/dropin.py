@@ -31,7 +31,8 @@ def _stub_nibabel():
     def load(path):
         with open(path, "rb") as f:
             blob = np.load(f, allow_pickle=False)
-        return Nifti1Image(blob["data"], blob["affine"])
+            data, affine = np.array(blob["data"]), np.array(blob["affine"])
+        return Nifti1Image(data, affine)
 
     def save(img, path):
         with open(path, "wb") as f:
@@ -50,7 +51,7 @@ def write_volume(path, data, affine=None):
 
 def read_volume(path):
     with open(path, "rb") as f:
-        return np.load(f, allow_pickle=False)["data"]
+        return np.array(np.load(f, allow_pickle=False)["data"])
 
 
 def load_reference_main():

@@ -1216,3 +1216,90 @@ def reference_cli_inference_case(tmp_dir):
             assert agree >= 0.995, agree
     finally:
         restore()
+
+
+# ------------------------------------------------------------------------------------------------ N3: inference edge
+def device_transforms_case():
+    """Device ModalitySpecificNormalize / Resize vs the numpy / scipy arithmetic of the reference's transforms
+    (src/data/transforms.py:362-404, 215-250; restated inline — and, where baseline/_ref is installed, against the
+    reference classes themselves)."""
+    import numpy as np
+    from scipy.ndimage import zoom
+    from mmseg_b200.src.data import ModalitySpecificNormalize, Resize
+    cfg = {"data": {"modalities": ["CT", "PET", "MRI", "US"],
+                    "preprocessing": {"ct": {"window_center": -100, "window_width": 700}, "pet": {"normalize": True},
+                                      "mri": {"normalize": True}, "us": {"normalize": False}}}}
+    g = np.random.default_rng(0)
+    img = np.stack([g.normal(-100, 400, (37, 40, 52)), np.exp(g.normal(0, 1, (37, 40, 52))),
+                    g.normal(3, 2, (37, 40, 52)), g.normal(0, 1, (37, 40, 52))]).astype(np.float32)
+    want = img.copy()
+    lo, hi = -100 - 350.0, -100 + 350.0
+    want[0] = (np.clip(want[0], lo, hi) - lo) / (hi - lo)
+    want[1] = want[1] / want[1].max()
+    want[2] = (want[2] - want[2].mean()) / (want[2].std() + 1e-8)
+    got = ModalitySpecificNormalize(cfg)({"image": torch.from_numpy(img).to(DEV)})["image"].cpu().numpy()
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[3], want[3])
+    assert np.abs(got[2] - want[2]).max() < 2e-5        # numpy sums in fp32 (pairwise), the kernel in fp64
+    try:
+        from tests import dropin
+        if dropin.available():
+            refmain, restore = dropin.load_reference_main()
+            try:
+                from src.data.transforms import ModalitySpecificNormalize as RefNorm
+                ref = RefNorm(cfg)({"image": img.copy()})["image"]
+                assert np.abs(got - ref).max() < 2e-5
+            finally:
+                restore()
+    except ImportError:
+        pass
+    small = img[:2, :20, :24, :28]
+    r = Resize((31, 16, 40))({"image": torch.from_numpy(small.copy()).to(DEV)})["image"].cpu().numpy()
+    wr = np.stack([zoom(small[c], (31 / 20, 16 / 24, 40 / 28), order=1) for c in range(2)])
+    assert r.shape == wr.shape == (2, 31, 16, 40)
+    err = np.abs(r - wr).max() / np.abs(wr).max()
+    print(f"[device transforms] normalize exact (z-score 2e-5), resize vs scipy.zoom(order=1) rel err {err:.2e}", flush=True)
+    assert err < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ attention backward
+def attention_core_bwd_case(heads=4, hd=32, n_tok=300, n_img=2, seed=0):
+    """mmseg_cross_attention_fwd (+ LSE) / _bwd on blocked token tensors vs fp64 autograd of softmax(Q K^T / sqrt(hd)) V on
+    the same bf16-rounded inputs: the only differences are the bf16 roundings of P / dS / the outputs."""
+    torch.manual_seed(seed)
+    C = heads * hd
+    shape = (1, 1, n_tok)
+
+    def blocked(t):                      # [n, C, N] fp32 -> Blocked tokens
+        b = Blocked(n_img, C, *shape, False, DEV)
+        K.pack_ncdhw(t.reshape(n_img, C, *shape).contiguous(), b)
+        return b
+
+    q, k, v, do = (_bf(torch.randn(n_img, C, n_tok, device=DEV)) for _ in range(4))
+    kvb = Blocked(n_img, 2 * C, *shape, False, DEV)
+    K.pack_ncdhw(torch.cat([k, v], 1).reshape(n_img, 2 * C, *shape).contiguous(), kvb)
+    qb, dob = blocked(q), blocked(do)
+    ob = Blocked(n_img, C, *shape, False, DEV)
+    lse = torch.empty((n_img, heads, n_tok), dtype=torch.float32, device=DEV)
+    scale = float(hd) ** -0.5
+    K.cross_attention(qb, 0, kvb, 0, C, ob, 0, heads, hd, scale, lse=lse)
+    dqb = Blocked(n_img, C, *shape, False, DEV)
+    dkvb = Blocked(n_img, 2 * C, *shape, False, DEV)
+    K.cross_attention_bwd(qb, 0, kvb, 0, C, ob, 0, dob, 0, lse, dqb, 0, dkvb, 0, C, heads, hd, scale)
+    torch.cuda.synchronize()
+    # fp64 reference
+    q64, k64, v64 = (t.double().reshape(n_img, heads, hd, n_tok).requires_grad_(True) for t in (q, k, v))
+    s_ = torch.einsum("bhdn,bhdm->bhnm", q64, k64) * scale
+    a_ = torch.softmax(s_, dim=-1)
+    o_ = torch.einsum("bhnm,bhdm->bhdn", a_, v64)
+    o_.backward(do.double().reshape(n_img, heads, hd, n_tok))
+    want_lse = torch.logsumexp(s_.detach(), dim=-1) * 1.4426950408889634      # log2 domain
+    got_o = ob.to_ncdhw().reshape(n_img, heads, hd, n_tok).double()
+    errs = {"out": ((got_o - o_.detach()).norm() / o_.detach().norm()).item(),
+            "lse": (lse.double() - want_lse).abs().max().item()}
+    got_dq = dqb.to_ncdhw().reshape(n_img, heads, hd, n_tok).double()
+    dkv = dkvb.to_ncdhw().reshape(n_img, 2, heads, hd, n_tok).double()
+    for name, got, want in (("dq", got_dq, q64.grad), ("dk", dkv[:, 0], k64.grad), ("dv", dkv[:, 1], v64.grad)):
+        errs[name] = ((got - want).norm() / want.norm()).item()
+    print(f"[attention bwd h={heads} hd={hd} N={n_tok} n={n_img}] " + " ".join(f"{k_}={v_:.2e}" for k_, v_ in errs.items()), flush=True)
+    assert errs["out"] < 1e-2 and errs["lse"] < 1e-3
+    assert errs["dq"] < 1.5e-2 and errs["dk"] < 1.5e-2 and errs["dv"] < 1e-2, errs

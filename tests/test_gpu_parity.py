@@ -274,3 +274,14 @@ def test_fused_adamw_matches_torch():
 def test_reference_cli_inference_on_dropin(tmp_path):
     """The reference's own main.py --mode inference, end to end on the drop-in packages (tests/dropin.py)."""
     _c().reference_cli_inference_case(tmp_path)
+
+
+def test_device_transforms_match_reference_numpy():
+    _c().device_transforms_case()
+
+
+@pytest.mark.parametrize("kw", [dict(hd=32, n_tok=300), dict(hd=16, n_tok=128, heads=2), dict(hd=64, n_tok=513, n_img=1),
+                                dict(hd=128, n_tok=260, heads=2, n_img=1), dict(hd=32, n_tok=1000, heads=1)])
+def test_cross_attention_core_backward(kw):
+    """dQ / dK / dV of the fused attention kernel vs fp64 autograd (ragged token counts, every head dim)."""
+    _c().attention_core_bwd_case(**kw)
