@@ -12,7 +12,6 @@
 //               P as bf16 into the K-major operand layout, rescale the fp32 output row kept in registers and add O_t.
 // S and O_t live in TMEM (128 + hd columns).
 #include <cuda.h>
-#include <stdlib.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -256,9 +255,7 @@ struct AttnBwdParams {
   const float* dsum;    // [n_img][heads][n_tok]  D = rowsum(dO o O)
   __nv_bfloat16* dq;
   __nv_bfloat16* dkv;
-  volatile int* dbg;    // optional progress markers in mapped host memory (MMSEG_ATTN_DBG_PTR), CTA (0,0,0) only
 };
-#define ATTN_MARK(i, v) do { if (p.dbg) { const int cta_ = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x; if (cta_ < 24) { p.dbg[cta_ * 32 + (i)] = (v); __threadfence_system(); } } } while (0)
 
 struct __align__(16) ABSmemHeader {
   uint64_t res_full, ring_full[2], ring_empty[2], sp_full, pds_full, pds_free, acc_full;
@@ -361,11 +358,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tma_load_2d(res_a, &tmQ, smem_u32(&hdr->res_full), 2 * t0, qcb);
         tma_load_2d(res_b, &tmDO, smem_u32(&hdr->res_full), 2 * t0, docb);
       }
-      ATTN_MARK(0, 1);
       for (int t = 0; t < n_it; ++t) {
         const uint32_t s = t % STAGES, ph = (t / STAGES) & 1;
         mbar_wait(smem_u32(&hdr->ring_empty[s]), ph ^ 1);
-        ATTN_MARK(1, t + 1);
         const uint32_t full = smem_u32(&hdr->ring_full[s]);
         mbar_arrive_expect_tx(full, 2 * kTileBytes);
         if (MODE == 0) {
@@ -383,13 +378,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t lbo_k = (kPlane >> 4) << 16;                     //          LBO = one plane (K halves)
       const uint32_t hi_mn = ((kPlane >> 4) & 0x3FFFu) | (1u << 14);  // MN-major: SBO = plane (next 8 MN elements)
       const uint32_t lbo_mn = (128u >> 4) << 16;                      //           LBO = 8 K rows
-      ATTN_MARK(8, 1);
       mbar_wait(smem_u32(&hdr->res_full), 0);
-      ATTN_MARK(8, 2);
       for (int t = 0; t < n_it; ++t) {
         const uint32_t s = t % STAGES, ph = (t / STAGES) & 1;
         mbar_wait(smem_u32(&hdr->ring_full[s]), ph);
-        ATTN_MARK(9, t + 1);
         tc_fence_after();
         const uint32_t q_t = MODE == 0 ? ring_a + s * kTileBytes : res_a;
         const uint32_t do_t = MODE == 0 ? ring_b + s * kTileBytes : res_b;
@@ -410,9 +402,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           umma_acc(tmem_dp, a, hi_k, b, hi_k, idesc_kk(128), j > 0 ? 1u : 0u);
         }
         umma_commit(smem_u32(&hdr->sp_full));
-        ATTN_MARK(10, t + 1);
         mbar_wait(smem_u32(&hdr->pds_full), t & 1);     // P / dS of this pair in shared memory
-        ATTN_MARK(11, t + 1);
         tc_fence_after();
         if (MODE == 0) {
           // dV += P^T dO, dK += dS^T Q: contraction over the 128 queries; A = P / dS read MN-major (rows = keys)
@@ -439,7 +429,6 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         umma_commit(smem_u32(&hdr->ring_empty[s]));
         umma_commit(smem_u32(&hdr->pds_free));
-        ATTN_MARK(12, t + 1);
       }
       umma_commit(smem_u32(&hdr->acc_full));
     }
@@ -454,12 +443,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const bool qok = qtok < p.n_tok;
       const float lse = qok ? p.lse[stat_base + qtok] : 0.f;
       const float dsum = qok ? p.dsum[stat_base + qtok] : 0.f;
-      if (threadIdx.x == 64) ATTN_MARK(16, t + 1);
       mbar_wait(smem_u32(&hdr->sp_full), t & 1);
-      if (threadIdx.x == 64) ATTN_MARK(17, t + 1);
       tc_fence_after();
       mbar_wait(smem_u32(&hdr->pds_free), (t & 1) ^ 1);   // the MMAs that read the previous P / dS have completed
-      if (threadIdx.x == 64) ATTN_MARK(18, t + 1);
 #pragma unroll
       for (int c = 0; c < kTile / 16; ++c) {
         float sv[16], dv[16];
@@ -483,12 +469,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
       mbar_arrive(smem_u32(&hdr->pds_full));
-      if (threadIdx.x == 64) ATTN_MARK(19, t + 1);
     }
     // epilogue: accumulator rows = this CTA's keys (MODE 0) / queries (MODE 1)
-    if (threadIdx.x == 64) ATTN_MARK(20, 1);
     mbar_wait(smem_u32(&hdr->acc_full), 0);
-    if (threadIdx.x == 64) ATTN_MARK(20, 2);
     tc_fence_after();
     const int tok = t0 + row;
     const bool tok_ok = tok < p.n_tok;
@@ -511,15 +494,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     } else {
       store(tmem_acc0, p.dq, img * p.dq_cbt + p.dq_cb0 + head * (HD / 8));
     }
-    if (threadIdx.x == 64) ATTN_MARK(21, 1);
   }
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) ATTN_MARK(22, 1);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(hdr->tmem_ptr, 512);
-    if (lane == 0) ATTN_MARK(23, 1);
   }
 }
 
@@ -686,9 +666,7 @@ extern "C" int mmseg_cross_attention_bwd(const void* q, int32_t q_cbt, int32_t q
   if (!rc) rc = make_tok_map(enc, &tdo, d_out, (int)n_tok, n_img * do_cbt, head_dim);
   if (rc) return fail(MMSEG_ERR_CUDA, "cross_attention_bwd: cuTensorMapEncodeTiled failed (%d)", rc);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const char* dbg_env = getenv("MMSEG_ATTN_BWD_STAGE");   // debugging aid: bit0 rowdot, bit1 dK/dV kernel, bit2 dQ kernel
-  const int dbg_stage = dbg_env ? atoi(dbg_env) : 7;
-  if (dbg_stage & 1) {
+  {
     dim3 g((unsigned)((n_tok + 255) / 256), (unsigned)heads, (unsigned)n_img);
     attention_rowdot_kernel<<<g, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(out), o_cbt, o_cb0,
                                                reinterpret_cast<const __nv_bfloat16*>(d_out), do_cbt, do_cb0, heads, head_dim,
@@ -703,8 +681,6 @@ extern "C" int mmseg_cross_attention_bwd(const void* q, int32_t q_cbt, int32_t q
   p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
   p.lse = lse; p.dsum = dsum;
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.dkv = reinterpret_cast<__nv_bfloat16*>(dkv);
-  const char* dbg_ptr = getenv("MMSEG_ATTN_DBG_PTR");
-  p.dbg = dbg_ptr ? reinterpret_cast<volatile int*>(strtoull(dbg_ptr, nullptr, 10)) : nullptr;
   const uint32_t tile_bytes = (uint32_t)(head_dim / 8) * kTile * 16;
   const int stages = head_dim <= 64 ? 2 : 1;
   uint32_t smem = 128 + 128 + (2 + 2 * stages) * tile_bytes + 2 * 16 * kTile * 16 + 128;
@@ -721,10 +697,10 @@ extern "C" int mmseg_cross_attention_bwd(const void* q, int32_t q_cbt, int32_t q
       if (e != cudaSuccess) return fail(MMSEG_ERR_CUDA, "cross_attention_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); \
       set = true;                                                                                                    \
     }                                                                                                                \
-    if (dbg_stage & 2) attention_bwd_kernel<HD, 0><<<grid, kAThreads, smem, st>>>(tq, tk, tv, tdo, p);               \
+    attention_bwd_kernel<HD, 0><<<grid, kAThreads, smem, st>>>(tq, tk, tv, tdo, p);               \
     rc = check_launch("attention_bwd_kernel<dkv>");                                                                  \
     if (rc) return rc;                                                                                               \
-    if (dbg_stage & 4) attention_bwd_kernel<HD, 1><<<grid, kAThreads, smem, st>>>(tq, tk, tv, tdo, p);               \
+    attention_bwd_kernel<HD, 1><<<grid, kAThreads, smem, st>>>(tq, tk, tv, tdo, p);               \
   }
   switch (head_dim) {
     case 16: MMSEG_ATTN_BWD(16); break;

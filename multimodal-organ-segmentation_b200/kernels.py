@@ -684,8 +684,9 @@ def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt
 def instnorm_act_bwd(raw: Tensor, mean_rstd: Tensor, n_img: int, channels: int, Z: int, Y: int, X: int,
                      gA: Optional[Blocked], gA_c0: int, gA_scale: float, gP: Optional[Blocked], gP_c0: int,
                      dx: Tensor, slope: float = 0.0, chan_scale: Optional[Tensor] = None,
-                     chan_bias: Optional[Tensor] = None) -> None:
-    """dx (blocked bf16 [n_img, channels/8, Z, Y, X, 8]) = gradient of the raw conv output; see mmseg_norm_bwd_args."""
+                     chan_bias: Optional[Tensor] = None, dx_cbt: Optional[int] = None, dx_cb_off: int = 0) -> None:
+    """dx (blocked bf16 [n_img, channels/8, Z, Y, X, 8]) = gradient of the raw conv output; see mmseg_norm_bwd_args.
+    dx_cbt / dx_cb_off: dx is a channel-block range of a wider blocked buffer (dx_cbt blocks per image)."""
     a = _lib.NormBwdArgs()
     nvox = Z * Y * X
     n_chunks = max(1, min(64, (nvox + 8191) // 8192))
@@ -700,7 +701,7 @@ def instnorm_act_bwd(raw: Tensor, mean_rstd: Tensor, n_img: int, channels: int, 
         a.gA_cbt, a.gA_cb_off = gA.cbt, gA_c0 // 8
     if gP is not None:
         a.gP_cbt, a.gP_cb_off = gP.cbt, gP_c0 // 8
-    a.dx_cbt, a.dx_cb_off, a.n_chunks = channels // 8, 0, n_chunks
+    a.dx_cbt, a.dx_cb_off, a.n_chunks = (channels // 8 if dx_cbt is None else dx_cbt), dx_cb_off, n_chunks
     a.gA_scale, a.slope = gA_scale, slope
     if PROFILE is not None:
         _INFO[0] = {"bytes": n_img * channels * nvox * 4.0, "layer": f"bwd-reduce-c{channels}-{Z}-pool{int(gP is not None)}"}

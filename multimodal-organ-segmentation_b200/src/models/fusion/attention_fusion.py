@@ -1,17 +1,18 @@
 """Attention-based fusion — drop-in mirror of the reference's src/models/fusion/attention_fusion.py
 (AttentionFusion, CrossAttentionFusion, BidirectionalCrossAttention; same constructors, parameter names, forward
-signatures).  Forward-only in the sm_100a kernels (bf16 operands, fp32 accumulation / softmax):
+signatures), in the sm_100a kernels (bf16 operands, fp32 accumulation / softmax):
   * q/k/v/out 1x1 projections  -> tcgen05 implicit-GEMM conv kernel (k and v as ONE conv over the key/value features);
   * softmax(QK^T)V              -> fused flash-style tcgen05 attention kernel (csrc/attention.cu), no N x N matrix;
   * InstanceNorm3d(q + out)     -> add + statistics kernel, finalize, normalise (no activation).
-SUVGuidedAttention (never instantiated by the reference, needs a sigmoid gate kernel) is not built.
+CrossAttentionFusion also TRAINS through the kernels (_CrossAttentionFunction: norm backward, projection dgrad / wgrad,
+flash-style attention backward by recomputation); the other modules of this file are forward-only.
 """
-from typing import List
+from typing import List, Optional
 
 import torch
 import torch.nn as nn
 
-from ..backbones.unet import _require_cuda, _no_autograd
+from ..backbones.unet import _require_cuda, _no_autograd, _wants_grad
 from .... import kernels as K
 from .... import _lib
 from ....engine import ConvRunner
@@ -103,8 +104,10 @@ class CrossAttentionFusion(nn.Module):
         self.__dict__["_pack_cache"] = (ver, packs)
         return packs
 
-    def forward_blocked(self, q_in: Blocked, kv_in: Blocked, dst: Blocked, dst_c0: int = 0) -> None:
-        """q_in / kv_in: blocked bf16 features (C channels at block 0); writes InstanceNorm(q + attention) into dst."""
+    def forward_blocked(self, q_in: Blocked, kv_in: Blocked, dst: Blocked, dst_c0: int = 0, save: Optional[dict] = None) -> None:
+        """q_in / kv_in: blocked bf16 features (C channels at block 0); writes InstanceNorm(q + attention) into dst.
+        save (training): receives what backward_blocked needs (projections, attention output, log-sum-exp rows, the
+        pre-norm sum as bf16 and its statistics)."""
         if self.training and self.dropout.p > 0:
             raise NotImplementedError("attention dropout (p > 0, train mode) is not built in the fused kernel")
         C, h, hd = self.in_channels, self.num_heads, self.head_dim
@@ -119,21 +122,105 @@ class CrossAttentionFusion(nn.Module):
         kvb = Blocked(n, 2 * h * hdp, Z, Y, X, False, dev)
         ab = Blocked(n, h * hdp, Z, Y, X, False, dev)
         ob = Blocked(n, C, Z, Y, X, False, dev)
+        lse = torch.empty((n, h, Z * Y * X), dtype=torch.float32, device=dev) if save is not None else None
         r.conv_act(q_in, [(0, C)], P["q"], qb)
         r.conv_act(kv_in, [(0, C)], P["kv"], kvb)
-        K.cross_attention(qb, 0, kvb, 0, h * hdp, ab, 0, h, hdp, float(hd) ** -0.5)
+        K.cross_attention(qb, 0, kvb, 0, h * hdp, ab, 0, h, hdp, float(hd) ** -0.5, lse=lse)
         r.conv_act(ab, [(0, h * hdp)], P["o"], ob)
         y, partial, n_chunks = K.add_stats(q_in, 0, ob, 0, C)
         mr = torch.empty((n, C, 2), dtype=torch.float32, device=dev)
         K.instnorm_finalize(partial, n, n_chunks, C, Z * Y * X, mr, eps=self.norm.eps)
         K.instnorm_act_apply(y, True, mr, n, C, Z, Y, X, dst, dst_c0, slope=1.0)   # slope 1 = no activation
+        if save is not None:
+            # the norm backward reads the pre-norm tensor in bf16: an identity pass (mean 0, rstd 1, slope 1) converts it
+            ybf = Blocked(n, C, Z, Y, X, False, dev)
+            ident = torch.zeros((n, C, 2), dtype=torch.float32, device=dev)
+            ident[:, :, 1] = 1.0
+            K.instnorm_act_apply(y, True, ident, n, C, Z, Y, X, ybf, 0, slope=1.0)
+            save.update(q_in=q_in, kv_in=kv_in, qb=qb, kvb=kvb, ab=ab, lse=lse, ybf=ybf, mr=mr, hdp=hdp)
+
+    def backward_blocked(self, saved: dict, g_out: Blocked):
+        """Backward of forward_blocked in the sm_100a kernels (autograd through attention_fusion.py:138-162 in the
+        reference): InstanceNorm backward, out_proj dgrad / wgrad, the flash-style attention backward, q / k / v projection
+        dgrad / wgrad, and the residual.  g_out: gradient w.r.t. the module output (blocked bf16, C channels).
+        Returns (d_query_features, d_key_value_features) as Blocked and {parameter: fp32 gradient}."""
+        from ....train_engine import _wrap
+        C, h, hd = self.in_channels, self.num_heads, self.head_dim
+        hdp = saved["hdp"]
+        q_in, kv_in, qb, kvb, ab = saved["q_in"], saved["kv_in"], saved["qb"], saved["kvb"], saved["ab"]
+        n, Z, Y, X = q_in.n_img, q_in.Z, q_in.Y, q_in.X
+        dev = q_in.t.device
+        nvox = Z * Y * X
+        HP = h * hdp
+        chan_sums = lambda b, c0, ch: (K.channel_mean(b, c0, ch) * float(nvox)).sum(0)
+        # d(q + out_proj(attn)) through the InstanceNorm (no activation: slope 1); lands in channels [0, C) of `stack`, whose
+        # channels [C, 2C) receive the q_proj input gradient: d_query = their sum (the residual)
+        stack = Blocked(n, 2 * C, Z, Y, X, False, dev)
+        K.instnorm_act_bwd(saved["ybf"].t, saved["mr"], n, C, Z, Y, X, g_out, 0, 1.0, None, 0, stack.t, slope=1.0,
+                           dx_cbt=stack.cbt, dx_cb_off=0)
+        grads = {}
+        W = self._bwd_weights()
+        # out_proj
+        dwo = K.conv3d_wgrad(ab, [(0, HP)], stack.t, stack.cbt, 0, C, 1, (C, HP, 1, 1, 1))
+        grads[self.out_proj.weight] = dwo.view(C, h, hdp)[:, :, :hd].reshape(C, C, 1, 1, 1)
+        grads[self.out_proj.bias] = chan_sums(stack, 0, C)
+        d_ab = Blocked(n, HP, Z, Y, X, False, dev)
+        K.conv3d(stack, W["o"], K.a_chunk_table(stack, [0], [C], False), d_ab.t, _lib.OUT_BLOCKED_BF16, dst_cbt=d_ab.cbt)
+        # attention core
+        dqb = Blocked(n, HP, Z, Y, X, False, dev)
+        dkvb = Blocked(n, 2 * HP, Z, Y, X, False, dev)
+        K.cross_attention_bwd(qb, 0, kvb, 0, HP, ab, 0, d_ab, 0, saved["lse"], dqb, 0, dkvb, 0, HP, h, hdp, float(hd) ** -0.5)
+        # q projection
+        dwq = K.conv3d_wgrad(q_in, [(0, C)], dqb.t, dqb.cbt, 0, HP, 1, (HP, C, 1, 1, 1))
+        grads[self.q_proj.weight] = dwq.view(h, hdp, C)[:, :hd].reshape(C, C, 1, 1, 1)
+        grads[self.q_proj.bias] = chan_sums(dqb, 0, HP).view(h, hdp)[:, :hd].reshape(C)
+        K.conv3d(dqb, W["q"], K.a_chunk_table(dqb, [0], [HP], False), stack.t, _lib.OUT_BLOCKED_BF16, dst_cbt=stack.cbt,
+                 dst_cb_off=C // 8)
+        d_q = Blocked(n, C, Z, Y, X, False, dev)
+        K.modality_combine(stack, 2, C, d_q, 0, None, 1.0)
+        # k / v projections (one stacked conv, like the forward)
+        dwkv = K.conv3d_wgrad(kv_in, [(0, C)], dkvb.t, dkvb.cbt, 0, 2 * HP, 1, (2 * HP, C, 1, 1, 1))
+        bkv = chan_sums(dkvb, 0, 2 * HP)
+        grads[self.k_proj.weight] = dwkv[:HP].view(h, hdp, C)[:, :hd].reshape(C, C, 1, 1, 1)
+        grads[self.v_proj.weight] = dwkv[HP:].view(h, hdp, C)[:, :hd].reshape(C, C, 1, 1, 1)
+        grads[self.k_proj.bias] = bkv[:HP].view(h, hdp)[:, :hd].reshape(C)
+        grads[self.v_proj.bias] = bkv[HP:].view(h, hdp)[:, :hd].reshape(C)
+        d_kv = Blocked(n, C, Z, Y, X, False, dev)
+        K.conv3d(dkvb, W["kv"], K.a_chunk_table(dkvb, [0], [2 * HP], False), d_kv.t, _lib.OUT_BLOCKED_BF16, dst_cbt=d_kv.cbt)
+        return d_q, d_kv, grads
+
+    def _bwd_weights(self):
+        """dgrad-form operands of the three projections (column = input channel, K = output channel in the padded head
+        layout), packed by the repack kernel from the same padded matrices the forward uses."""
+        C, h, hd = self.in_channels, self.num_heads, self.head_dim
+        ver = tuple(p._version for p in self.parameters())
+        c = self.__dict__.get("_bwd_cache")
+        if c is not None and c[0] == ver:
+            return c[1]
+        hdp = max(16, (hd + 15) // 16 * 16)
+        r2 = lambda conv: conv.weight.detach().float().reshape(C, C)
+        wq, _ = _pad_heads_out(r2(self.q_proj), self.q_proj.bias, h, hd, hdp)
+        wk, _ = _pad_heads_out(r2(self.k_proj), self.k_proj.bias, h, hd, hdp)
+        wv, _ = _pad_heads_out(r2(self.v_proj), self.v_proj.bias, h, hd, hdp)
+        wkv = torch.cat([wk, wv])
+        wo = torch.zeros((C, h * hdp), dtype=torch.float32, device=wq.device)
+        wo.view(C, h, hdp)[:, :, :hd] = r2(self.out_proj).view(C, h, hd)
+        f5 = lambda w: w.reshape(w.shape[0], w.shape[1], 1, 1, 1).contiguous()
+        keep = {"q": f5(wq), "kv": f5(wkv), "o": f5(wo)}
+        packs = {k_: K.PackPlan.k1_dgrad(v_).run() for k_, v_ in keep.items()}
+        packs["_keep"] = keep
+        self.__dict__["_bwd_cache"] = (ver, packs)
+        return packs
 
     def forward(self, query_features: torch.Tensor, key_value_features: torch.Tensor) -> torch.Tensor:
         _require_cuda(query_features)
-        _no_autograd(self, query_features)
         B, C, Z, Y, X = query_features.shape
         if C % 16:
             raise NotImplementedError("CrossAttentionFusion kernels need channels % 16 == 0")
+        if _wants_grad(self, query_features) or (torch.is_grad_enabled() and key_value_features.requires_grad):
+            params = [self.q_proj.weight, self.q_proj.bias, self.k_proj.weight, self.k_proj.bias, self.v_proj.weight,
+                      self.v_proj.bias, self.out_proj.weight, self.out_proj.bias]
+            return _CrossAttentionFunction.apply(self, query_features, key_value_features, *params)
         with torch.no_grad():
             dev = query_features.device
             q_in = Blocked(B, C, Z, Y, X, False, dev)
@@ -143,6 +230,39 @@ class CrossAttentionFusion(nn.Module):
             dst = Blocked(B, C, Z, Y, X, False, dev)
             self.forward_blocked(q_in, kv_in, dst)
             return dst.to_ncdhw()
+
+
+class _CrossAttentionFunction(torch.autograd.Function):
+    """CrossAttentionFusion.forward with the whole backward in the sm_100a kernels (bf16 operands, fp32 accumulation)."""
+
+    @staticmethod
+    def forward(ctx, module, q_feat, kv_feat, *params):
+        dev = q_feat.device
+        B, C, Z, Y, X = q_feat.shape
+        with torch.no_grad():
+            q_in = Blocked(B, C, Z, Y, X, False, dev)
+            kv_in = Blocked(B, C, Z, Y, X, False, dev)
+            K.pack_ncdhw(q_feat.detach().contiguous().float(), q_in)
+            K.pack_ncdhw(kv_feat.detach().contiguous().float(), kv_in)
+            dst = Blocked(B, C, Z, Y, X, False, dev)
+            saved = {}
+            module.forward_blocked(q_in, kv_in, dst, save=saved)
+        ctx.module, ctx.saved, ctx.params = module, saved, params
+        ctx.dtypes = (q_feat.dtype, kv_feat.dtype)
+        return dst.to_ncdhw()
+
+    @staticmethod
+    def backward(ctx, g):
+        m, saved = ctx.module, ctx.saved
+        q_in = saved["q_in"]
+        with torch.no_grad():
+            g_out = Blocked(q_in.n_img, m.in_channels, q_in.Z, q_in.Y, q_in.X, False, g.device)
+            K.pack_ncdhw(g.contiguous().float(), g_out)
+            d_q, d_kv, grads = m.backward_blocked(saved, g_out)
+            gq = d_q.to_ncdhw().to(ctx.dtypes[0]) if ctx.needs_input_grad[1] else None
+            gkv = d_kv.to_ncdhw().to(ctx.dtypes[1]) if ctx.needs_input_grad[2] else None
+            gp = [grads[p].to(p.dtype).view_as(p) if (p.requires_grad and p in grads) else None for p in ctx.params]
+        return (None, gq, gkv, *gp)
 
 
 class BidirectionalCrossAttention(nn.Module):

@@ -285,3 +285,9 @@ def test_device_transforms_match_reference_numpy():
 def test_cross_attention_core_backward(kw):
     """dQ / dK / dV of the fused attention kernel vs fp64 autograd (ragged token counts, every head dim)."""
     _c().attention_core_bwd_case(**kw)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(C=32, heads=4, shape=(4, 6, 5), n_img=1), dict(C=128, heads=4, shape=(8, 8, 8))])
+def test_cross_attention_fusion_trains_through_the_kernels(kw):
+    """Module-level gradient parity (inputs + all projections) vs fp64 autograd of the oracle maths."""
+    _c().cross_attention_module_grad_case(**kw)
