@@ -139,11 +139,13 @@ class CrossAttentionFusion(nn.Module):
             K.instnorm_act_apply(y, True, ident, n, C, Z, Y, X, ybf, 0, slope=1.0)
             save.update(q_in=q_in, kv_in=kv_in, qb=qb, kvb=kvb, ab=ab, lse=lse, ybf=ybf, mr=mr, hdp=hdp)
 
-    def backward_blocked(self, saved: dict, g_out: Blocked):
+    def backward_blocked(self, saved: dict, g_out: Blocked, g_c0: int = 0, dq_dst: Optional[Blocked] = None, dq_c0: int = 0,
+                         dkv_dst: Optional[Blocked] = None, dkv_c0: int = 0):
         """Backward of forward_blocked in the sm_100a kernels (autograd through attention_fusion.py:138-162 in the
         reference): InstanceNorm backward, out_proj dgrad / wgrad, the flash-style attention backward, q / k / v projection
-        dgrad / wgrad, and the residual.  g_out: gradient w.r.t. the module output (blocked bf16, C channels).
-        Returns (d_query_features, d_key_value_features) as Blocked and {parameter: fp32 gradient}."""
+        dgrad / wgrad, and the residual.  g_out: gradient w.r.t. the module output (blocked bf16, C channels from channel
+        g_c0).  Returns (d_query_features, d_key_value_features) as Blocked — written into dq_dst / dkv_dst at the given
+        channel offsets when supplied — and {parameter: fp32 gradient}."""
         from ....train_engine import _wrap
         C, h, hd = self.in_channels, self.num_heads, self.head_dim
         hdp = saved["hdp"]
@@ -156,7 +158,7 @@ class CrossAttentionFusion(nn.Module):
         # d(q + out_proj(attn)) through the InstanceNorm (no activation: slope 1); lands in channels [0, C) of `stack`, whose
         # channels [C, 2C) receive the q_proj input gradient: d_query = their sum (the residual)
         stack = Blocked(n, 2 * C, Z, Y, X, False, dev)
-        K.instnorm_act_bwd(saved["ybf"].t, saved["mr"], n, C, Z, Y, X, g_out, 0, 1.0, None, 0, stack.t, slope=1.0,
+        K.instnorm_act_bwd(saved["ybf"].t, saved["mr"], n, C, Z, Y, X, g_out, g_c0, 1.0, None, 0, stack.t, slope=1.0,
                            dx_cbt=stack.cbt, dx_cb_off=0)
         grads = {}
         W = self._bwd_weights()
@@ -176,8 +178,8 @@ class CrossAttentionFusion(nn.Module):
         grads[self.q_proj.bias] = chan_sums(dqb, 0, HP).view(h, hdp)[:, :hd].reshape(C)
         K.conv3d(dqb, W["q"], K.a_chunk_table(dqb, [0], [HP], False), stack.t, _lib.OUT_BLOCKED_BF16, dst_cbt=stack.cbt,
                  dst_cb_off=C // 8)
-        d_q = Blocked(n, C, Z, Y, X, False, dev)
-        K.modality_combine(stack, 2, C, d_q, 0, None, 1.0)
+        d_q = dq_dst if dq_dst is not None else Blocked(n, C, Z, Y, X, False, dev)
+        K.modality_combine(stack, 2, C, d_q, dq_c0, None, 1.0)
         # k / v projections (one stacked conv, like the forward)
         dwkv = K.conv3d_wgrad(kv_in, [(0, C)], dkvb.t, dkvb.cbt, 0, 2 * HP, 1, (2 * HP, C, 1, 1, 1))
         bkv = chan_sums(dkvb, 0, 2 * HP)
@@ -185,8 +187,9 @@ class CrossAttentionFusion(nn.Module):
         grads[self.v_proj.weight] = dwkv[HP:].view(h, hdp, C)[:, :hd].reshape(C, C, 1, 1, 1)
         grads[self.k_proj.bias] = bkv[:HP].view(h, hdp)[:, :hd].reshape(C)
         grads[self.v_proj.bias] = bkv[HP:].view(h, hdp)[:, :hd].reshape(C)
-        d_kv = Blocked(n, C, Z, Y, X, False, dev)
-        K.conv3d(dkvb, W["kv"], K.a_chunk_table(dkvb, [0], [2 * HP], False), d_kv.t, _lib.OUT_BLOCKED_BF16, dst_cbt=d_kv.cbt)
+        d_kv = dkv_dst if dkv_dst is not None else Blocked(n, C, Z, Y, X, False, dev)
+        K.conv3d(dkvb, W["kv"], K.a_chunk_table(dkvb, [0], [2 * HP], False), d_kv.t, _lib.OUT_BLOCKED_BF16, dst_cbt=d_kv.cbt,
+                 dst_cb_off=dkv_c0 // 8)
         return d_q, d_kv, grads
 
     def _bwd_weights(self):
@@ -282,8 +285,10 @@ class BidirectionalCrossAttention(nn.Module):
 
     def forward(self, features_1: torch.Tensor, features_2: torch.Tensor) -> torch.Tensor:
         _require_cuda(features_1)
-        _no_autograd(self, features_1)
         B, C, Z, Y, X = features_1.shape
+        if _wants_grad(self, features_1) or (torch.is_grad_enabled() and features_2.requires_grad):
+            params = [p for p in self.parameters()]
+            return _BidirectionalFunction.apply(self, features_1, features_2, *params)
         with torch.no_grad():
             dev = features_1.device
             f1 = Blocked(B, C, Z, Y, X, False, dev)
@@ -300,6 +305,73 @@ class BidirectionalCrossAttention(nn.Module):
             out = Blocked(B, C, Z, Y, X, False, dev)
             self._runner.conv_norm_act(cat, [(0, C), (C, C)], pw, out)
             return out.to_ncdhw()
+
+
+class _BidirectionalFunction(torch.autograd.Function):
+    """BidirectionalCrossAttention.forward (reference attention_fusion.py:193-216) with the backward in the kernels: the two
+    CrossAttentionFusion backwards, the 1x1 fusion conv's dgrad / wgrad and the InstanceNorm + ReLU backward."""
+
+    @staticmethod
+    def forward(ctx, module, f1_t, f2_t, *params):
+        dev = f1_t.device
+        B, C, Z, Y, X = f1_t.shape
+        with torch.no_grad():
+            f1 = Blocked(B, C, Z, Y, X, False, dev)
+            f2 = Blocked(B, C, Z, Y, X, False, dev)
+            K.pack_ncdhw(f1_t.detach().contiguous().float(), f1)
+            K.pack_ncdhw(f2_t.detach().contiguous().float(), f2)
+            cat = Blocked(B, 2 * C, Z, Y, X, False, dev)
+            s1, s2 = {}, {}
+            module.cross_attn_1to2.forward_blocked(f1, f2, cat, 0, save=s1)
+            module.cross_attn_2to1.forward_blocked(f2, f1, cat, C, save=s2)
+            conv = module.fusion[0]
+            pw = K.PackPlan.forward(conv.weight, None, False, [C, C], use_bias=False).run()   # bias cancelled by the norm
+            a_cb = K.a_chunk_table(cat, [0, C], [C, C], False)
+            tile = K.plan_conv_norm((X, Y, Z), B, pw, False, a_cb)
+            raw = torch.empty((B, C // 8, Z, Y, X, 8), dtype=torch.bfloat16, device=dev)
+            stats = torch.empty(B * tile.tiles_per_img * C * 2, dtype=torch.float32, device=dev)
+            mr = torch.empty((B, C, 2), dtype=torch.float32, device=dev)
+            K.conv3d(cat, pw, a_cb, raw, _lib.OUT_BLOCKED_BF16, stats=stats, dst_cbt=C // 8, tile=tile)
+            K.instnorm_finalize(stats, B, tile.tiles_per_img, C, Z * Y * X, mr, eps=module.fusion[1].eps)
+            out = Blocked(B, C, Z, Y, X, False, dev)
+            K.instnorm_act_apply(raw, False, mr, B, C, Z, Y, X, out, 0, 0.0)
+        ctx.module, ctx.saved, ctx.params = module, (s1, s2, cat, raw, mr), params
+        ctx.dtypes = (f1_t.dtype, f2_t.dtype)
+        return out.to_ncdhw()
+
+    @staticmethod
+    def backward(ctx, g):
+        m = ctx.module
+        s1, s2, cat, raw, mr = ctx.saved
+        B, C, Z, Y, X = cat.n_img, m.out_channels, cat.Z, cat.Y, cat.X
+        dev = g.device
+        conv = m.fusion[0]
+        with torch.no_grad():
+            g_out = Blocked(B, C, Z, Y, X, False, dev)
+            K.pack_ncdhw(g.contiguous().float(), g_out)
+            draw = Blocked(B, C, Z, Y, X, False, dev)
+            K.instnorm_act_bwd(raw, mr, B, C, Z, Y, X, g_out, 0, 1.0, None, 0, draw.t, slope=0.0)
+            grads = {conv.weight: K.conv3d_wgrad(cat, [(0, C), (C, C)], draw.t, draw.cbt, 0, C, 1, conv.weight.shape)}
+            if conv.bias is not None:
+                grads[conv.bias] = torch.zeros_like(conv.bias, dtype=torch.float32)    # cancelled by the InstanceNorm
+            d_cat = Blocked(B, 2 * C, Z, Y, X, False, dev)
+            pwd = K.PackPlan.k1_dgrad(conv.weight.detach()).run()
+            K.conv3d(draw, pwd, K.a_chunk_table(draw, [0], [C], False), d_cat.t, _lib.OUT_BLOCKED_BF16, dst_cbt=d_cat.cbt)
+            # d f1 = dq(1->2) + dkv(2->1);  d f2 = dkv(1->2) + dq(2->1): each pair lands side by side, then one add
+            sum1 = Blocked(B, 2 * C, Z, Y, X, False, dev)
+            sum2 = Blocked(B, 2 * C, Z, Y, X, False, dev)
+            _, _, g1 = m.cross_attn_1to2.backward_blocked(s1, d_cat, 0, dq_dst=sum1, dq_c0=0, dkv_dst=sum2, dkv_c0=0)
+            _, _, g2 = m.cross_attn_2to1.backward_blocked(s2, d_cat, C, dq_dst=sum2, dq_c0=C, dkv_dst=sum1, dkv_c0=C)
+            grads.update(g1)
+            grads.update(g2)
+            d1 = Blocked(B, C, Z, Y, X, False, dev)
+            d2 = Blocked(B, C, Z, Y, X, False, dev)
+            K.modality_combine(sum1, 2, C, d1, 0, None, 1.0)
+            K.modality_combine(sum2, 2, C, d2, 0, None, 1.0)
+            gf1 = d1.to_ncdhw().to(ctx.dtypes[0]) if ctx.needs_input_grad[1] else None
+            gf2 = d2.to_ncdhw().to(ctx.dtypes[1]) if ctx.needs_input_grad[2] else None
+            gp = [grads[p].to(p.dtype).view_as(p) if (p.requires_grad and p in grads) else None for p in ctx.params]
+        return (None, gf1, gf2, *gp)
 
 
 class SUVGuidedAttention(nn.Module):

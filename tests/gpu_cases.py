@@ -1346,3 +1346,39 @@ def cross_attention_module_grad_case(C=64, heads=4, shape=(6, 8, 8), n_img=2, se
     assert errs["out"] < 2e-2
     worst = max(v for k, v in errs.items() if k != "out")
     assert worst < 6e-2, errs          # bf16 operands end to end (the reference under bf16 autocast sits at the same level)
+
+
+def bidirectional_attention_grad_case(C=32, heads=4, shape=(4, 6, 6), n_img=2, seed=1):
+    """BidirectionalCrossAttention trained through the kernels vs fp64 autograd of the oracle maths."""
+    from mmseg_b200.src.models.fusion import BidirectionalCrossAttention
+    torch.manual_seed(seed)
+    m = BidirectionalCrossAttention(C, heads)
+    P = {k: v.detach().clone().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    f1, f2, r = (torch.randn(n_img, C, *shape) for _ in range(3))
+    a64, b64 = f1.double().requires_grad_(True), f2.double().requires_grad_(True)
+    hd = C // heads
+
+    def ca(prefix, q, kv):
+        proj = lambda name, t: F.conv3d(t, P[f"{prefix}.{name}.weight"], P[f"{prefix}.{name}.bias"])
+        Q = proj("q_proj", q).reshape(n_img, heads, hd, -1)
+        Kk = proj("k_proj", kv).reshape(n_img, heads, hd, -1)
+        V = proj("v_proj", kv).reshape(n_img, heads, hd, -1)
+        att = torch.softmax(torch.einsum("bhdn,bhdm->bhnm", Q, Kk) * (hd ** -0.5), dim=-1)
+        return F.instance_norm(q + proj("out_proj", torch.einsum("bhnm,bhdm->bhdn", att, V).reshape(q.shape)), eps=1e-5)
+
+    y = F.relu(F.instance_norm(F.conv3d(torch.cat([ca("cross_attn_1to2", a64, b64), ca("cross_attn_2to1", b64, a64)], 1),
+                                        P["fusion.0.weight"], P["fusion.0.bias"]), eps=1e-5))
+    (y * r.double()).sum().backward()
+    m = m.to(DEV).train()
+    d1, d2 = f1.to(DEV).requires_grad_(True), f2.to(DEV).requires_grad_(True)
+    out = m(d1, d2)
+    (out * r.to(DEV)).sum().backward()
+    rel = lambda a, b, fl=1e-30: ((a.double().cpu() - b).norm() / max(b.norm().item(), fl)).item()
+    errs = {"out": rel(out.detach(), y.detach()), "df1": rel(d1.grad, a64.grad), "df2": rel(d2.grad, b64.grad)}
+    for name, p in m.named_parameters():
+        fl = P[name.replace(".bias", ".weight")].grad.norm().item() if name.endswith(".bias") else 1e-30
+        errs[name] = rel(p.grad, P[name].grad, fl)
+    worst = max(v for k, v in errs.items() if k != "out")
+    print(f"[BidirectionalCrossAttention grads C={C}] out={errs['out']:.1e} df1={errs['df1']:.1e} df2={errs['df2']:.1e} "
+          f"worst parameter {max(v for k, v in errs.items() if '.' in k):.1e}", flush=True)
+    assert errs["out"] < 4e-2 and worst < 1e-1, errs

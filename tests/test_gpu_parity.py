@@ -291,3 +291,7 @@ def test_cross_attention_core_backward(kw):
 def test_cross_attention_fusion_trains_through_the_kernels(kw):
     """Module-level gradient parity (inputs + all projections) vs fp64 autograd of the oracle maths."""
     _c().cross_attention_module_grad_case(**kw)
+
+
+def test_bidirectional_cross_attention_trains_through_the_kernels():
+    _c().bidirectional_attention_grad_case()
