@@ -111,9 +111,7 @@ int32_t mmseg_conv3d_tiles_per_img(const mmseg_conv_args* args);
  * src/models/backbones/unet.py:26-27,54,57,163 and, through the k=1 GEMM view, nn.ConvTranspose3d(k2,s2) at unet.py:95;
  * the reference reaches it via loss.backward(), src/trainer/trainer.py:243).
  *   dW[co, ci, tap] = sum over images and voxels of dY[vox, co] * X[vox + tap, ci]
- * tcgen05 GEMM with the voxels as the contraction dimension, both operands MN-major straight from the blocked layout
- * (X is loaded once per plane: the dy taps are M groups of one MMA, the dx tap a start-address offset, the dz taps the N
- * dimension).
+ * tcgen05 GEMM with the voxels as the contraction dimension, both operands MN-major straight from the blocked layout.
  * grid = n_part persistent CTAs x (n_cig * n_cot) channel-group pairs; every CTA sweeps its share of the voxel tiles
  * with the accumulators resident in TMEM and writes ONE fp32 partial; mmseg_wgrad_reduce sums the partials in a fixed
  * order (deterministic split-K) into the PyTorch-layout gradient.  dgrad needs no entry point of its own: it is
@@ -122,11 +120,11 @@ int32_t mmseg_conv3d_tiles_per_img(const mmseg_conv_args* args);
 typedef struct {
   const void* x;        /* conv input, blocked bf16 [n_img*x_cbt][Z][Y][X][8]                                 */
   const void* dy;       /* gradient of the raw conv output, blocked bf16 [n_img*y_cbt][Z][Y][X][8]            */
-  float* partial;       /* workspace [n_cig*n_cot][n_part][128 = (dy, ci)][ksize^2 * cot_blocks*8 = (dx, dz, co)] fp32 */
+  float* partial;       /* workspace [n_cig*n_cot][n_part][128][ksize^2 * cot_blocks*8] fp32                  */
   int32_t n_img, Z, Y, X;
   int32_t ksize;        /* 3 (padding 1) or 1                                                                 */
-  int32_t TX, TY, TZ;   /* voxel tile per sweep step; TX % 16 == 0, TX + ksize - 1 <= 128                     */
-  int32_t cig_blocks;   /* input-channel blocks (of 8) per group: a divisor of 16 with 16/cig_blocks >= ksize */
+  int32_t TX, TY, TZ;   /* voxel tile per sweep step; TX*TY % 16 == 0, TX <= 128                              */
+  int32_t cig_blocks;   /* input-channel blocks (of 8) per group; ksize*cig_blocks <= 16                      */
   int32_t cot_blocks;   /* output-channel blocks per group (even); ksize*cot_blocks*8 <= 256                  */
   int32_t n_cig, n_cot; /* number of input / output channel groups                                            */
   int32_t x_cbt, y_cbt; /* channel blocks per image in x / dy                                                 */

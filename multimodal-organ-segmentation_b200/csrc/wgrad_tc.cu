@@ -3,20 +3,15 @@
 //
 // Both operands are read MN-major straight from the blocked activation layout ([cb][Z][Y][X][8] bf16): a voxel row is
 // 16 bytes = 8 channels, 8 consecutive voxel rows form one SWIZZLE_NONE core matrix (K direction, LBO = 128 B) and the
-// next 8-channel group (MN direction) is SBO further — no transposition anywhere.
+// next channel block (MN direction) is one smem plane further (SBO = plane bytes) — no transposition anywhere.
+//   A (M = 128 rows) = X halo tile, loaded three times by TMA with x shifted by dx = -1, 0, +1 (rows of TX voxels, no x
+//       halo, so A and B share the row pitch): M index = (dx, ci) -> 3*CIG valid rows (the rest multiply garbage and
+//       are never stored).  The dy tap is a start-address offset of dy*TX rows.
 //   B (N columns) = dY tile; the dz taps are folded into N: the planes z-1, z, z+1 of dY sit in consecutive ring slots,
 //       so one MMA of N = 3*NTc columns pairs X plane p with dY planes p+1, p, p-1  (dz = 0, 1, 2).
-//   A (M = 128 rows) = X halo tile, loaded ONCE per plane by a TMA box whose dimensions are ordered (x, channel block,
-//       y): in shared memory the channel blocks of one y row are adjacent, [y][cb][x + halo][8], so the 16 MN groups of
-//       an MMA = (row offset r, cb) are an affine walk (SBO = one padded row): for cig = 32 channels the M rows are
-//       (r = 0..3, ci) — the dy taps r = 0, 1, 2 come out of ONE MMA (r = 3 multiplies garbage into accumulator rows that
-//       are never stored) and the dx tap is a start-address offset of dx voxels (K chunks are 16 consecutive x of one row,
-//       so A and B need not share a row pitch).  D[dx] (TMEM, fp32) = [(dy, ci)] x [(dz-descending, co)].
-//       (Round 1 loaded three x-shifted copies of every X plane to fold dx into M: 3x the L2 -> shared-memory traffic,
-//       15 TB/s at the tensor-pipe rate — the kernel ran at 600 TFLOP/s, L2-bound, with room for only two ring slots.)
-//   k = 1 (KT = 1): M = channel blocks of one row only, no halo.
-//   A PERSISTENT CTA sweeps many voxel tiles with D resident in TMEM, then writes one partial; mmseg_wgrad_reduce sums
-//   the partials in a fixed order (deterministic split-K, no atomics) straight into the PyTorch-layout fp32 gradient.
+//   D[dy] (TMEM, fp32) = [(dx, ci)] x [(dz-descending, co)], kept resident while a PERSISTENT CTA sweeps many voxel
+//       tiles; each CTA then writes one partial and mmseg_wgrad_reduce sums the partials in a fixed order
+//       (deterministic split-K, no atomics) straight into the PyTorch-layout fp32 gradient.
 #include <cuda.h>
 
 #include "common.h"
@@ -30,10 +25,7 @@ struct WgradKParams {
   int tiles_x, tiles_y, tiles_z, n_tiles;
   int cig_blocks, cot_blocks, n_cig, n_cot;
   int x_cbt, y_cbt, y_cb0;
-  int rx, ry;                      // ring depths (X planes / dY planes)
-  uint32_t xrow_bytes;             // one (y, cb) row of the X tile: (TX + 2H) voxels * 16 B  = the A operand's SBO
-  uint32_t yplane_bytes, xslot_bytes, yslot_bytes, x_off, y_off;
-  uint32_t xslot_stride;           // xslot_bytes rounded up to 128 B (TMA destinations are 128-byte aligned)
+  uint32_t xplane_bytes, yplane_bytes, xslot_bytes, yslot_bytes, x_off, y_off;
   uint32_t tmem_cols;
   int ncols;
   float* partial;
@@ -41,16 +33,16 @@ struct WgradKParams {
 };
 
 constexpr int kWThreads = 192;
-constexpr int kMaxRX = 8;  // X-plane ring slots (upper bound; the plan picks what fits)
-constexpr int kMaxRY = 8;  // dY-plane ring slots (three live + in flight)
+constexpr int kRX = 2;  // X-plane ring slots
+constexpr int kRY = 4;  // dY-plane ring slots (three live + one in flight)
 
 struct __align__(16) WSmemHeader {
-  uint64_t x_full[kMaxRX], x_empty[kMaxRX];
-  uint64_t y_full[kMaxRY], y_empty[kMaxRY];
+  uint64_t x_full[kRX], x_empty[kRX];
+  uint64_t y_full[kRY], y_empty[kRY];
   uint64_t acc_full, acc_zero;
   uint32_t tmem_ptr;
 };
-constexpr uint32_t kWHeaderBytes = 512;
+constexpr uint32_t kWHeaderBytes = 256;
 static_assert(sizeof(WSmemHeader) <= kWHeaderBytes, "header too large");
 
 // idesc: bf16 x bf16 -> f32, A and B both MN-major, M = 128
@@ -85,11 +77,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int pair = blockIdx.y;
   const int cig = pair / p.n_cot, cot = pair - cig * p.n_cot;
   const int NTc = p.cot_blocks * 8;
-  const uint32_t RX = (uint32_t)p.rx, RY = (uint32_t)p.ry;
+  const int PY = p.TY + 2 * H;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kMaxRX; ++s) { mbar_init(smem_u32(&hdr->x_full[s]), 1); mbar_init(smem_u32(&hdr->x_empty[s]), 1); }
-    for (int s = 0; s < kMaxRY; ++s) { mbar_init(smem_u32(&hdr->y_full[s]), 1); mbar_init(smem_u32(&hdr->y_empty[s]), 1); }
+    for (int s = 0; s < kRX; ++s) { mbar_init(smem_u32(&hdr->x_full[s]), 1); mbar_init(smem_u32(&hdr->x_empty[s]), 1); }
+    for (int s = 0; s < kRY; ++s) { mbar_init(smem_u32(&hdr->y_full[s]), 1); mbar_init(smem_u32(&hdr->y_empty[s]), 1); }
     mbar_init(smem_u32(&hdr->acc_full), 1);
     mbar_init(smem_u32(&hdr->acc_zero), 128);
     fence_mbar_init();
@@ -100,6 +92,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_ptr;
+  const uint32_t x_bytes = (uint32_t)KT * p.cig_blocks * p.xplane_bytes;   // bytes landing per X plane (KT dx copies)
+  const uint32_t x_dx_bytes = (uint32_t)p.cig_blocks * p.xplane_bytes;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -117,20 +111,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int ycb = img * p.y_cbt + p.y_cb0 + cot * p.cot_blocks;
         for (int i = 0; i < tzv + 2 * H; ++i) {
           if (i < tzv) {  // dY plane z0 + i
-            const uint32_t s = yc % RY, ph = (yc / RY) & 1;
+            const uint32_t s = yc % kRY, ph = (yc / kRY) & 1;
             mbar_wait(smem_u32(&hdr->y_empty[s]), ph ^ 1);
             const uint32_t full = smem_u32(&hdr->y_full[s]);
             mbar_arrive_expect_tx(full, p.yslot_bytes);
             tma_load_4d(y_smem + s * p.yslot_bytes, &tmY, full, 2 * x0, y0, z0 + i, ycb);
             ++yc;
           }
-          const int pz = z0 - H + i;  // X plane: ONE box, dimensions (x, channel block, y, z)
+          const int pz = z0 - H + i;  // X plane
           if (pz >= 0 && pz < p.Z) {
-            const uint32_t s = xc % RX, ph = (xc / RX) & 1;
+            const uint32_t s = xc % kRX, ph = (xc / kRX) & 1;
             mbar_wait(smem_u32(&hdr->x_empty[s]), ph ^ 1);
             const uint32_t full = smem_u32(&hdr->x_full[s]);
-            mbar_arrive_expect_tx(full, p.xslot_bytes);
-            tma_load_4d(x_smem + s * p.xslot_stride, &tmX, full, 2 * (x0 - H), xcb, y0 - H, pz);
+            mbar_arrive_expect_tx(full, x_bytes);
+#pragma unroll
+            for (int dx = 0; dx < KT; ++dx)
+              tma_load_4d(x_smem + s * p.xslot_bytes + dx * x_dx_bytes, &tmX, full, 2 * (x0 - H + dx), y0 - H, pz, xcb);
             ++xc;
           }
         }
@@ -139,11 +135,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
-      const uint32_t a_hi = ((p.xrow_bytes >> 4) & 0x3FFFu) | (1u << 14);    // SBO = MN-group stride = one (y, cb) row
-      const uint32_t b_hi = ((p.yplane_bytes >> 4) & 0x3FFFu) | (1u << 14);  // SBO = one dY channel-block plane
+      const uint32_t a_hi = ((p.xplane_bytes >> 4) & 0x3FFFu) | (1u << 14);  // SBO = MN-group stride = one X plane
+      const uint32_t b_hi = ((p.yplane_bytes >> 4) & 0x3FFFu) | (1u << 14);
       const uint32_t lbo = (128u >> 4) << 16;                                  // K-group stride = 8 voxel rows
-      const int xchunks = p.TX >> 4;                                           // 16-voxel K chunks per tile row
-      const uint32_t arow = (uint32_t)p.cig_blocks * (p.xrow_bytes >> 4);      // one y row of the X tile, in 16-B units
+      const int nchunks = (p.TX * p.TY) >> 4;
       uint32_t xc = 0, yc = 0, yw = 0;  // yc: first dY plane counter of this tile; yw: dY planes waited so far
       mbar_wait(smem_u32(&hdr->acc_zero), 0);
       tc_fence_after();
@@ -158,34 +153,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             const int za = max(pz - H, z0), zb = min(pz + H, z0 + tzv - 1);
             // dY planes up to zb must have landed
             while ((int)(yw - yc) <= zb - z0) {
-              mbar_wait(smem_u32(&hdr->y_full[yw % RY]), (yw / RY) & 1);
+              mbar_wait(smem_u32(&hdr->y_full[yw % kRY]), (yw / kRY) & 1);
               ++yw;
             }
-            const uint32_t sx = xc % RX;
-            mbar_wait(smem_u32(&hdr->x_full[sx]), (xc / RX) & 1);
+            const uint32_t sx = xc % kRX;
+            mbar_wait(smem_u32(&hdr->x_full[sx]), (xc / kRX) & 1);
             tc_fence_after();
             if (za <= zb) {
-              const uint32_t ya = (yc + (uint32_t)(za - z0)) % RY;       // ring slot of plane za
+              const uint32_t ya = (yc + (uint32_t)(za - z0)) % kRY;      // ring slot of plane za
               const int n_pl = zb - za + 1;
-              const int n_first = min(n_pl, (int)RY - (int)ya);           // planes before the ring wraps
+              const int n_first = min(n_pl, kRY - (int)ya);              // planes before the ring wraps
               const uint32_t col0 = (uint32_t)(za - (pz - H)) * NTc;      // dz-descending column block of plane za
-              const uint32_t a_base = (((x_smem + sx * p.xslot_stride) >> 4) & 0x3FFFu) | lbo;
+              const uint32_t a_base = (((x_smem + sx * p.xslot_bytes) >> 4) & 0x3FFFu) | lbo;
               const uint32_t b1 = (((y_smem + ya * p.yslot_bytes) >> 4) & 0x3FFFu) | lbo;
               const uint32_t b2 = ((y_smem >> 4) & 0x3FFFu) | lbo;        // slot 0 after the wrap
               const uint32_t id1 = make_idesc_mn((uint32_t)(n_first * NTc));
               const uint32_t id2 = make_idesc_mn((uint32_t)((n_pl - n_first) * NTc));
-              for (int y = 0; y < p.TY; ++y) {
-                const uint32_t ay = a_base + (uint32_t)y * arow;                 // rows y .. y+3 (dy taps) of the halo tile
-                const uint32_t by = (uint32_t)(y * p.TX);                         // dY row y (no halo)
-                for (int kc = 0; kc < xchunks; ++kc) {
-                  const uint32_t bo = by + (uint32_t)(kc * 16);
+              for (int kc = 0; kc < nchunks; ++kc) {
 #pragma unroll
-                  for (int dx = 0; dx < KT; ++dx) {
-                    const uint32_t a = ay + (uint32_t)(kc * 16 + dx);            // x halo: tap dx starts dx voxels in
-                    const uint32_t d = tmem_base + (uint32_t)(dx * KT * NTc) + col0;
-                    umma_mn(d, a, a_hi, b1 + bo, b_hi, id1);
-                    if (n_first < n_pl) umma_mn(d + (uint32_t)(n_first * NTc), a, a_hi, b2 + bo, b_hi, id2);
-                  }
+                for (int dy = 0; dy < KT; ++dy) {
+                  const uint32_t a = a_base + (uint32_t)(dy * p.TX + kc * 16);
+                  const uint32_t d = tmem_base + (uint32_t)(dy * KT * NTc) + col0;
+                  umma_mn(d, a, a_hi, b1 + (uint32_t)(kc * 16), b_hi, id1);
+                  if (n_first < n_pl) umma_mn(d + (uint32_t)(n_first * NTc), a, a_hi, b2 + (uint32_t)(kc * 16), b_hi, id2);
                 }
               }
             }
@@ -194,7 +184,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           }
           // dY plane pz - H is not needed by any later X plane
           const int zr = pz - H;
-          if (zr >= z0 && zr < z0 + tzv) umma_commit(smem_u32(&hdr->y_empty[(yc + (uint32_t)(zr - z0)) % RY]));
+          if (zr >= z0 && zr < z0 + tzv) umma_commit(smem_u32(&hdr->y_empty[(yc + (uint32_t)(zr - z0)) % kRY]));
         }
         yc += (uint32_t)tzv;
       }
@@ -257,9 +247,9 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int n_part, int ncols, in
   const int cblk = b % cols_blocks; b /= cols_blocks;
   const int rblk = b % row_blocks;
   const int pair = b / row_blocks;                // (input-channel group, output-channel group)
-  const int row = rblk * R + rl;                  // accumulator row = (dy, ci inside the group)
+  const int row = rblk * R + rl;                  // accumulator row = (dx, ci inside the group)
   const int col = cblk * 32 + lane;
-  const int dy = row / CIG, cil = row - dy * CIG;
+  const int dx = row / CIG, cil = row - dx * CIG;
   const int cig = pair / n_cot, cot = pair - cig * n_cot;
   const int ci = (row < valid_rows) ? ci_of_pos[cig * CIG + cil] : -1;
   double s = 0.0;
@@ -283,7 +273,7 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int n_part, int ncols, in
     for (int w = 0; w < S; ++w) s += sm[rl * S + w][lane];
   }
   if (col >= ncols || ci < 0) return;
-  const int dx = col / (KT * NTc), r2 = col - dx * (KT * NTc);   // accumulator D[dx]
+  const int dy = col / (KT * NTc), r2 = col - dy * (KT * NTc);
   const int dzr = r2 / NTc, col_l = r2 - dzr * NTc;
   const int dz = KT - 1 - dzr;
   const int n = cot * NTc + col_l;                // GEMM column (co, or tap8*Cout + co)
@@ -331,12 +321,11 @@ static int plan_wgrad(const mmseg_wgrad_args* a, WgradPlan* out) {
   if (!a) return fail(MMSEG_ERR_INVALID_ARG, "wgrad: null args");
   if (a->ksize != 1 && a->ksize != 3) return fail(MMSEG_ERR_UNSUPPORTED, "wgrad: ksize %d (only 1, 3)", a->ksize);
   if (a->n_img < 1 || a->X < 1 || a->Y < 1 || a->Z < 1) return fail(MMSEG_ERR_INVALID_ARG, "wgrad: bad extents");
-  if (a->TX < 16 || a->TY < 1 || a->TZ < 1 || (a->TX & 15))
-    return fail(MMSEG_ERR_INVALID_ARG, "wgrad: TX=%d must be a positive multiple of 16 (K chunks are 16 voxels of one row)", a->TX);
+  if (a->TX < 1 || a->TY < 1 || a->TZ < 1 || ((a->TX * a->TY) & 15))
+    return fail(MMSEG_ERR_INVALID_ARG, "wgrad: TX*TY=%d must be a positive multiple of 16", a->TX * a->TY);
+  if (a->TX > 128) return fail(MMSEG_ERR_INVALID_ARG, "wgrad: TX > 128 (TMA box limit)");
   const int KT = a->ksize, H = KT / 2;
-  if (a->TX + 2 * H > 128) return fail(MMSEG_ERR_INVALID_ARG, "wgrad: TX + halo > 128 (TMA box limit)");
-  if (a->cig_blocks < 1 || a->cig_blocks > 16 || (16 % a->cig_blocks) || 16 / a->cig_blocks < KT)
-    return fail(MMSEG_ERR_INVALID_ARG, "wgrad: %d ci blocks: need a divisor of 16 with 16/blocks >= ksize (dy taps are M groups)", a->cig_blocks);
+  if (a->cig_blocks < 1 || KT * a->cig_blocks > 16) return fail(MMSEG_ERR_INVALID_ARG, "wgrad: %d ci blocks x %d dx copies > 16 M groups", a->cig_blocks, KT);
   if (a->cot_blocks & 1) return fail(MMSEG_ERR_INVALID_ARG, "wgrad: cot_blocks must be even (MMA N is a multiple of 16)");
   if (a->cot_blocks < 1 || KT * a->cot_blocks * 8 > 256) return fail(MMSEG_ERR_INVALID_ARG, "wgrad: folded N = %d > 256", KT * a->cot_blocks * 8);
   if (a->n_cig < 1 || a->n_cig > MMSEG_MAX_WGRAD_GROUPS || a->n_cot < 1) return fail(MMSEG_ERR_INVALID_ARG, "wgrad: group counts");
@@ -350,33 +339,22 @@ static int plan_wgrad(const mmseg_wgrad_args* a, WgradPlan* out) {
   k.cig_blocks = a->cig_blocks; k.cot_blocks = a->cot_blocks; k.n_cig = a->n_cig; k.n_cot = a->n_cot;
   k.x_cbt = a->x_cbt; k.y_cbt = a->y_cbt; k.y_cb0 = a->y_cb0;
   const int PY = a->TY + 2 * H;
-  if (PY > 256) return fail(MMSEG_ERR_INVALID_ARG, "wgrad: TY too large");
-  k.xrow_bytes = (uint32_t)(a->TX + 2 * H) * 16u;
+  k.xplane_bytes = (uint32_t)PY * a->TX * 16u;
   k.yplane_bytes = (uint32_t)a->TY * a->TX * 16u;
-  if ((k.yplane_bytes >> 4) > 0x3FFF) return fail(MMSEG_ERR_INVALID_ARG, "wgrad: dY plane too large for SBO");
-  k.xslot_bytes = (uint32_t)PY * a->cig_blocks * k.xrow_bytes;
-  k.xslot_stride = rup(k.xslot_bytes, 128);
+  if ((k.xplane_bytes >> 4) > 0x3FFF) return fail(MMSEG_ERR_INVALID_ARG, "wgrad: X plane too large for SBO");
+  k.xslot_bytes = (uint32_t)KT * a->cig_blocks * k.xplane_bytes;
   k.yslot_bytes = (uint32_t)a->cot_blocks * k.yplane_bytes;
   k.ncols = KT * KT * a->cot_blocks * 8;
   if (k.ncols > 512) return fail(MMSEG_ERR_INVALID_ARG, "wgrad: %d TMEM columns > 512", k.ncols);
   uint32_t tc = 32;
   while ((int)tc < k.ncols) tc <<= 1;
   k.tmem_cols = tc;
-  // ring depths: as many X planes as fit next to KT + 2 dY planes (KT live + two in flight), at most 8 / 8
-  const uint32_t budget = 227u * 1024u - kWHeaderBytes - 256u;
-  // an MMA reads 16 MN groups = 16 / cig_blocks tile rows from its start row: keep the reach of the last slot inside
-  // the allocation (rows past the tile multiply garbage into accumulator rows that are never stored)
-  const uint32_t reach = (uint32_t)(16 / a->cig_blocks) * a->cig_blocks * k.xrow_bytes;
-  int ry = KT + 2, rx = 2;
-  if ((uint64_t)rx * k.xslot_stride + (uint64_t)ry * k.yslot_bytes + reach > budget)
-    return fail(MMSEG_ERR_INVALID_ARG, "wgrad: tile %dx%d needs more than 227 KB of shared memory", a->TX, a->TY);
-  while (rx < kMaxRX && (uint64_t)(rx + 1) * k.xslot_stride + (uint64_t)ry * k.yslot_bytes + reach <= budget) ++rx;
-  while (ry < kMaxRY && (uint64_t)rx * k.xslot_stride + (uint64_t)(ry + 1) * k.yslot_bytes + reach <= budget) ++ry;
-  k.rx = rx; k.ry = ry;
   k.x_off = kWHeaderBytes;
-  k.y_off = k.x_off + (uint32_t)rx * k.xslot_stride;
-  uint32_t total = k.y_off + (uint32_t)ry * k.yslot_bytes;
-  if (k.x_off + (uint32_t)rx * k.xslot_stride + reach > total) total = k.x_off + (uint32_t)rx * k.xslot_stride + reach;
+  k.y_off = k.x_off + kRX * k.xslot_bytes;
+  // A reads 16 MN groups from the start of a slot (+ the dy/kc row offset): keep that inside the allocation
+  const uint32_t a_reach = (kRX - 1) * k.xslot_bytes + 15u * k.xplane_bytes + (uint32_t)(2 * H * a->TX + a->TX * a->TY) * 16u;
+  uint32_t total = k.y_off + kRY * k.yslot_bytes;
+  if (k.x_off + a_reach > total) total = k.x_off + a_reach;
   total = rup(total, 128) + 128;
   if (total < 116u * 1024u) total = 116u * 1024u;  // one CTA per SM (each allocates up to all 512 TMEM columns)
   if (total > 227u * 1024u) return fail(MMSEG_ERR_INVALID_ARG, "wgrad: %u bytes of shared memory > 227 KB", total);
@@ -411,16 +389,14 @@ extern "C" int mmseg_conv3d_wgrad(const mmseg_wgrad_args* a, void* stream) {
   const WgradKParams& k = pl.k;
   const int H = pl.KT / 2;
   CUtensorMap tmx, tmy;
+  cuuint64_t strides[3] = {(cuuint64_t)k.X * 16, (cuuint64_t)k.X * k.Y * 16, (cuuint64_t)k.X * k.Y * k.Z * 16};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  // X: dimensions ordered (x, channel block, y, z) so that a box lands in shared memory as [y][cb][x + halo][8]
-  cuuint64_t dimsx[4] = {(cuuint64_t)2 * k.X, (cuuint64_t)k.n_img * k.x_cbt, (cuuint64_t)k.Y, (cuuint64_t)k.Z};
-  cuuint64_t stridesx[3] = {(cuuint64_t)k.X * k.Y * k.Z * 16, (cuuint64_t)k.X * 16, (cuuint64_t)k.X * k.Y * 16};
-  cuuint32_t boxx[4] = {(cuuint32_t)(2 * (k.TX + 2 * H)), (cuuint32_t)k.cig_blocks, (cuuint32_t)(k.TY + 2 * H), 1};
-  CUresult cr = enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(a->x), dimsx, stridesx, boxx, estr,
+  cuuint64_t dimsx[4] = {(cuuint64_t)2 * k.X, (cuuint64_t)k.Y, (cuuint64_t)k.Z, (cuuint64_t)k.n_img * k.x_cbt};
+  cuuint32_t boxx[4] = {(cuuint32_t)(2 * k.TX), (cuuint32_t)(k.TY + 2 * H), 1, (cuuint32_t)k.cig_blocks};
+  CUresult cr = enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(a->x), dimsx, strides, boxx, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(MMSEG_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(X) failed (%d)", (int)cr);
-  cuuint64_t strides[3] = {(cuuint64_t)k.X * 16, (cuuint64_t)k.X * k.Y * 16, (cuuint64_t)k.X * k.Y * k.Z * 16};
   cuuint64_t dimsy[4] = {(cuuint64_t)2 * k.X, (cuuint64_t)k.Y, (cuuint64_t)k.Z, (cuuint64_t)k.n_img * k.y_cbt};
   cuuint32_t boxy[4] = {(cuuint32_t)(2 * k.TX), (cuuint32_t)k.TY, 1, (cuuint32_t)k.cot_blocks};
   cr = enc(&tmy, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(a->dy), dimsy, strides, boxy, estr,

@@ -590,39 +590,34 @@ def _largest_divisor(cands, values):
 
 @lru_cache(maxsize=None)
 def _plan_wgrad_tile(X: int, Y: int, Z: int, ksize: int, cig_blocks: int, cot_blocks: int) -> Tuple[int, int, int]:
-    """(TX, TY, TZ) accepted by the library.  TX is a multiple of 16 (a K chunk = 16 voxels of one row) with
-    TX + ksize - 1 <= 128 (TMA box); among the tiles that leave room for at least three X-plane ring slots (the loads
-    of two planes in flight behind the one being multiplied) the one with the least padding, then the most voxels per
-    plane step (<= 512: one step is already ~2,700 tensor-pipe cycles)."""
-    H = ksize // 2
-    budget = 227 * 1024 - 512 - 256
+    """(TX, TY, TZ) accepted by the library: largest K rows per plane (TX*TY, multiple of 16) that fits shared memory."""
     best = None
-    for TX in range(16, 113, 16):
-        if TX - 16 >= X:
-            break
-        for TY in (8, 6, 5, 4, 3, 2, 1):
-            if TY > max(Y, 1) and TY != 1:
-                continue
-            xrow = (TX + 2 * H) * 16
-            xslot = -(-(TY + 2 * H) * cig_blocks * xrow // 128) * 128
-            yslot = cot_blocks * TY * TX * 16
-            reach = (16 // cig_blocks) * cig_blocks * xrow
-            rx = (budget - (ksize + 2) * yslot - reach) // xslot
-            if rx < 2:
+    for nx in range(1, X + 1):
+        TX = (X + nx - 1) // nx
+        if TX > 128:
+            continue
+        for TY in range(min(Y, 32), 0, -1):
+            if (TX * TY) % 16:
                 continue
             a = _lib.WgradArgs()
             a.n_img, a.Z, a.Y, a.X, a.ksize = 1, Z, Y, X, ksize
             a.TX, a.TY, a.TZ = TX, TY, min(Z, 8)
             a.cig_blocks, a.cot_blocks, a.n_cig, a.n_cot = cig_blocks, cot_blocks, 1, 1
             a.x_cbt, a.y_cbt, a.y_cb0, a.n_part = cig_blocks, cot_blocks, 0, 1
-            if lib.mmseg_conv3d_wgrad_smem_bytes(C.byref(a)) <= 0:
-                continue
-            waste = (-(-X // TX) * TX) * (-(-Y // TY) * TY) / float(X * Y)
-            score = (min(rx, 3), -round(waste, 3), min(TX * TY, 512), TX)
-            if best is None or score > best[0]:
-                best = (score, (TX, TY, min(Z, 8)))
+            if lib.mmseg_conv3d_wgrad_smem_bytes(C.byref(a)) > 0:
+                rows = TX * TY
+                waste = ((X + TX - 1) // TX * TX) * ((Y + TY - 1) // TY * TY) / float(X * Y)
+                score = (min(rows, 512) / waste, -nx)
+                if best is None or score > best[0]:
+                    best = (score, (TX, TY, min(Z, 8)))
+                break
+        if best is not None and nx >= 4:
+            break
     if best is None:
-        raise RuntimeError(f"no wgrad tile for X={X} Y={Y} ksize={ksize} cig_blocks={cig_blocks} cot_blocks={cot_blocks}")
+        # rows must be a multiple of 16: pad the tile beyond the volume (TMA zero-fills, so the sum is unchanged)
+        TX = min(X, 16) if X >= 16 else 16
+        TY = max(1, 16 // TX) if TX * max(1, 16 // TX) % 16 == 0 else 16
+        best = (None, (TX, TY, min(Z, 8)))
     return best[1]
 
 
