@@ -34,7 +34,10 @@ dicece_partial_kernel(const float* __restrict__ logits, const long long* __restr
       se += e;
     }
     const float inv = 1.f / se;
-    const float w = cw ? cw[t] : 1.f;
+    // a label outside [0, C) (ignore values such as -100 / 255) selects no class: no one-hot term and zero CE weight
+    // (the reference raises in F.one_hot; here it must at least never index class_weights out of bounds)
+    const bool tv = t >= 0 && t < C;
+    const float w = tv ? (cw ? cw[t] : 1.f) : 0.f;
     nll += w * (logf(se) - zt);
     wsum += w;
 #pragma unroll
@@ -156,7 +159,7 @@ dicece_bwd_kernel(const float* __restrict__ logits, const long long* __restrict_
       const float g = gB[c] + (c == t ? gA[c] : 0.f);
       dot = fmaf(g, z[c], dot);
     }
-    const float wce = ce_w * (cw ? cw[t] : 1.f) / wtot;
+    const float wce = (t >= 0 && t < C) ? ce_w * (cw ? cw[t] : 1.f) / wtot : 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const float g = gB[c] + (c == t ? gA[c] : 0.f);
@@ -258,7 +261,7 @@ focal_kernel(const float* __restrict__ logits, const long long* __restrict__ tar
     float se = 0.f, zt = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) { if (c == t) zt = z[c] - mx; z[c] = expf(z[c] - mx); se += z[c]; }
-    const float w = cw ? cw[t] : 1.f;
+    const float w = (t >= 0 && t < C) ? (cw ? cw[t] : 1.f) : 0.f;   // out-of-range label: ignored (never read out of bounds)
     const float ce = w * (logf(se) - zt);     // = -w log p_t
     const float pt = expf(-ce);
     const float om = 1.f - pt;

@@ -38,10 +38,14 @@ class _DiceCEFunction(torch.autograd.Function):
 class DiceLoss(nn.Module):
     """reference losses.py:12-80."""
 
-    def __init__(self, smooth: float = 1.0, reduction: str = "mean", include_background: bool = True):
+    def __init__(self, smooth: float = 1.0, reduction: str = "mean", softmax: bool = True, include_background: bool = True):
         super().__init__()
+        if not softmax:
+            raise NotImplementedError("DiceLoss(softmax=False) (predictions that are already probabilities) has no "
+                                      "sm_100a kernel: the one-pass kernel applies the softmax itself")
         self.smooth = smooth
         self.reduction = reduction
+        self.softmax = softmax
         self.include_background = include_background
 
     def forward(self, pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
