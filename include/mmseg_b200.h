@@ -425,6 +425,52 @@ typedef struct {
 int mmseg_adamw_multi(const void* tensors, int32_t n_tensors, const int32_t* chunks, int32_t n_chunks, const float* hyper,
                       int32_t zero_grad, void* stream);
 
+/*
+ * SwinUNETR (BASELINE.json configs[3]).  The reference's SwinUNETR (src/models/backbones/swin_unetr.py:20-200) builds
+ * monai.networks.nets.SwinUNETR in its ctor (:80-96) and forward is self.model(x) (:117); these entry points replace
+ * the non-convolution ATen ops MONAI issues under that call.  Linear layers (qkv / proj / mlp / patch-merging
+ * reduction) are 1x1x1 GEMMs through mmseg_conv3d_fwd; tokens stay in the blocked layout, residual stream fp32.
+ */
+/* swinViT.patch_embed: nn.Conv3d(Cin, F, kernel 2, stride 2) + bias.  x NCDHW fp32 [n][Cin][2Z][2Y][2X] ->
+ * xs blocked fp32 [n * F/8][Z][Y][X][8]. */
+int mmseg_swin_patch_embed(const float* x, const float* w /* [F][Cin][2][2][2] */, const float* b /* [F] or NULL */, float* xs,
+                           int32_t n_img, int32_t Cin, int32_t F, int32_t Z, int32_t Y, int32_t X, void* stream);
+/* Residual add + token LayerNorm over channels (SwinTransformerBlock: x = shortcut + attn(...), norm2(x); x = x + mlp,
+ * next block's norm1(x); SwinTransformer.proj_out: F.layer_norm without affine):
+ *   xs += add (when add != NULL);  dst = LN(xs) * gamma + beta (when dst != NULL; gamma / beta NULL = no affine).
+ * xs / add blocked fp32 [n * cb][voxels][8]; dst blocked 16-bit (elem_fmt) at channel block dst_cb_off of dst_cbt. */
+int mmseg_swin_layernorm(float* xs, const float* add, const float* gamma, const float* beta, void* dst, int32_t n_img,
+                         int32_t cb, int64_t voxels, int32_t dst_cbt, int32_t dst_cb_off, float eps, int32_t elem_fmt,
+                         void* stream);
+/* PatchMerging (MONAI "merging", 3-D legacy gather order) + LayerNorm(8C) with affine: xs blocked fp32 [n*cb][Z][Y][X][8] ->
+ * dst blocked 16-bit [n * 8cb][Z/2][Y/2][X/2][8] (channel = octant * C + c); the Linear(8C -> 2C) follows as a GEMM. */
+int mmseg_swin_merge_ln(const float* xs, const float* gamma, const float* beta, void* dst, int32_t n_img, int32_t cb, int32_t Z,
+                        int32_t Y, int32_t X, float eps, int32_t elem_fmt, void* stream);
+/* WindowAttention inside SwinTransformerBlock.forward_part1: zero padding to a multiple of the window, cyclic shift,
+ * window partition, softmax(q k^T * scale + relative_position_bias [+ shift mask]) v, window reverse, un-shift, crop —
+ * all as addressing inside one kernel (mma.sync m16n8k16 tensor-core tiles, head_dim 16, online softmax). */
+typedef struct {
+  const void* qkv;        /* blocked 16-bit [n_img * qkv_cbt][D][H][W][8]: channels [q | k | v], each heads x 16          */
+  void* out;              /* blocked 16-bit [n_img * out_cbt][D][H][W][8]: attention output before proj                   */
+  const float* table;     /* relative_position_bias_table [(2w0-1)(2w1-1)(2w2-1)][heads] fp32                             */
+  const float* qkv_bias;  /* [3 * heads * 16] fp32 or NULL: q / k / v of a zero-padded token                              */
+  int32_t n_img, D, H, W;
+  int32_t window[3];      /* configured window (7, 7, 7); an axis not longer than it shrinks the window, cancels the shift */
+  int32_t shift[3];       /* cyclic shift of this block (0 or window / 2)                                                 */
+  int32_t heads, head_dim;
+  int32_t qkv_cbt, out_cbt, out_cb_off;
+  float scale;            /* head_dim^-0.5                                                                                 */
+  int32_t elem_fmt;
+} mmseg_swin_attn_args;
+int mmseg_swin_window_attention(const mmseg_swin_attn_args* args, void* stream);
+/* UnetResBlock tail (MONAI dynunet_block.UnetResBlock, the block of every SwinUNETR encoder / decoder stage):
+ *   y = LeakyReLU(slope)( IN(a) + r' ),  r' = IN(r) with r_mean_rstd (1x1x1 residual conv) or r itself (NULL).
+ * a: raw conv output blocked [n*cb] (fp32 or 16-bit); r: blocked at channel block r_cb_off of r_cbt. */
+int mmseg_instnorm_residual_act(const void* a, int32_t a_is_f32, const float* a_mean_rstd, const void* r, int32_t r_is_f32,
+                                const float* r_mean_rstd, int32_t r_cbt, int32_t r_cb_off, void* dst, int32_t dst_cbt,
+                                int32_t dst_cb_off, int32_t n_img, int32_t cb, int64_t voxels, float slope, int32_t elem_fmt,
+                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

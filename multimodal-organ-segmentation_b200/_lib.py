@@ -83,6 +83,17 @@ class NormArgs(C.Structure):
     ]
 
 
+class SwinAttnArgs(C.Structure):
+    _fields_ = [
+        ("qkv", C.c_void_p), ("out", C.c_void_p), ("table", C.c_void_p), ("qkv_bias", C.c_void_p),
+        ("n_img", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("window", C.c_int32 * 3), ("shift", C.c_int32 * 3),
+        ("heads", C.c_int32), ("head_dim", C.c_int32),
+        ("qkv_cbt", C.c_int32), ("out_cbt", C.c_int32), ("out_cb_off", C.c_int32),
+        ("scale", C.c_float), ("elem_fmt", C.c_int32),
+    ]
+
+
 # every symbol include/mmseg_b200.h declares: name -> (restype, argtypes)
 _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 SYMBOLS = {
@@ -134,6 +145,12 @@ SYMBOLS = {
     "mmseg_weights_repack": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
     "mmseg_gather_f32": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "mmseg_adamw_multi": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp]),
+    "mmseg_swin_patch_embed": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "mmseg_swin_layernorm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _i32, _f32, _i32, _vp]),
+    "mmseg_swin_merge_ln": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
+    "mmseg_swin_window_attention": (C.c_int, [C.POINTER(SwinAttnArgs), _vp]),
+    "mmseg_instnorm_residual_act": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i64,
+                                              _f32, _i32, _vp]),
     "mmseg_maxpool3d_2": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
 }
 

@@ -861,3 +861,70 @@ def focal(logits: Tensor, target: Tensor, class_weights: Optional[Tensor], gamma
     _call("mmseg_focal", _ptr(logits), _ptr(target), B, Cc, N, _ptr(class_weights), gamma, _ptr(partial), n_blocks,
           _ptr(result), None, None, _stream())
     return result
+
+
+# --------------------------------------------------------------------------------------------- SwinUNETR pieces (swin.cu)
+def swin_patch_embed(x: Tensor, weight: Tensor, bias: Optional[Tensor], xs: Tensor) -> None:
+    """Conv3d(Cin, F, k2, s2): NCDHW fp32 -> blocked fp32 tokens xs [n, F/8, Z, Y, X, 8]."""
+    n, cin, Z2, Y2, X2 = x.shape
+    F = weight.shape[0]
+    assert x.dtype == torch.float32 and x.is_contiguous() and weight.dtype == torch.float32 and weight.is_contiguous()
+    assert tuple(weight.shape[1:]) == (cin, 2, 2, 2) and not ((Z2 | Y2 | X2) & 1)
+    assert xs.dtype == torch.float32 and xs.numel() == n * F * (Z2 // 2) * (Y2 // 2) * (X2 // 2)
+    _call("mmseg_swin_patch_embed", _ptr(x), _ptr(weight), _ptr(bias), _ptr(xs), n, cin, F, Z2 // 2, Y2 // 2, X2 // 2, _stream())
+
+
+def swin_layernorm(xs: Tensor, n_img: int, channels: int, voxels: int, dst: Optional[Blocked], dst_c0: int = 0,
+                   add: Optional[Tensor] = None, gamma: Optional[Tensor] = None, beta: Optional[Tensor] = None,
+                   eps: float = 1e-5) -> None:
+    """xs += add; dst = LayerNorm over channels (optional affine).  xs / add: blocked fp32 [n, C/8, voxels, 8]."""
+    assert xs.dtype == torch.float32 and xs.numel() == n_img * channels * voxels and channels % 8 == 0
+    assert add is None or (add.dtype == torch.float32 and add.numel() >= xs.numel())
+    fmt = dst.fmt if dst is not None else _lib.FMT_BF16
+    if dst is not None:
+        assert not dst.split and dst.nvox == voxels and dst.n_img == n_img and dst_c0 % 8 == 0
+    _call("mmseg_swin_layernorm", _ptr(xs), _ptr(add), _ptr(gamma), _ptr(beta), _ptr(dst.t) if dst is not None else None,
+          n_img, channels // 8, voxels, dst.cbt if dst is not None else 0, dst_c0 // 8, eps, fmt, _stream())
+
+
+def swin_merge_ln(xs: Tensor, n_img: int, channels: int, Z: int, Y: int, X: int, gamma: Tensor, beta: Tensor, dst: Blocked,
+                  eps: float = 1e-5) -> None:
+    assert xs.dtype == torch.float32 and xs.numel() == n_img * channels * Z * Y * X
+    assert dst.channels == 8 * channels and (dst.Z, dst.Y, dst.X) == (Z // 2, Y // 2, X // 2) and not dst.split
+    _call("mmseg_swin_merge_ln", _ptr(xs), _ptr(gamma), _ptr(beta), _ptr(dst.t), n_img, channels // 8, Z, Y, X, eps, dst.fmt,
+          _stream())
+
+
+def swin_window_attention(qkv: Blocked, out: Blocked, table: Tensor, qkv_bias: Optional[Tensor], heads: int,
+                          window: Sequence[int], shift: Sequence[int], out_c0: int = 0) -> None:
+    """softmax(q k^T / 4 + relative-position bias [+ shift mask]) v per (window, head); qkv channels = [q | k | v]."""
+    C_ = heads * 16
+    assert qkv.channels == 3 * C_ and not qkv.split and not out.split and qkv.fmt == out.fmt
+    assert table.dtype == torch.float32 and table.is_contiguous() and table.shape[1] == heads
+    a = _lib.SwinAttnArgs()
+    a.qkv, a.out, a.table = qkv.t.data_ptr(), out.t.data_ptr(), table.data_ptr()
+    a.qkv_bias = qkv_bias.data_ptr() if qkv_bias is not None else None
+    a.n_img, a.D, a.H, a.W = qkv.n_img, qkv.Z, qkv.Y, qkv.X
+    for i in range(3):
+        a.window[i], a.shift[i] = int(window[i]), int(shift[i])
+    a.heads, a.head_dim = heads, 16
+    a.qkv_cbt, a.out_cbt, a.out_cb_off = qkv.cbt, out.cbt, out_c0 // 8
+    a.scale, a.elem_fmt = 0.25, qkv.fmt
+    if PROFILE is not None:
+        _INFO[0] = {"flops": 4.0 * qkv.n_img * qkv.nvox * min(343, qkv.nvox) * C_,
+                    "layer": f"winattn c{C_} {qkv.Z}x{qkv.Y}x{qkv.X} img{qkv.n_img} shift{int(shift[0])}"}
+    _call("mmseg_swin_window_attention", C.byref(a), _stream())
+
+
+def instnorm_residual_act(a: Tensor, a_is_f32: bool, a_mr: Tensor, r: Tensor, r_is_f32: bool, r_mr: Optional[Tensor],
+                          r_cbt: int, r_c0: int, dst: Blocked, dst_c0: int, n_img: int, channels: int, voxels: int,
+                          slope: float) -> None:
+    """y = LeakyReLU(IN(a) + (IN(r) if r_mr is not None else r)) -> dst (UnetResBlock tail)."""
+    assert not dst.split and dst.nvox == voxels
+    if PROFILE is not None:
+        nel = n_img * channels * voxels
+        _INFO[0] = {"bytes": nel * ((4 if a_is_f32 else 2) + (4 if r_is_f32 else 2) + 2),
+                    "layer": f"resnorm c{channels} vox{voxels} img{n_img}"}
+    _call("mmseg_instnorm_residual_act", _ptr(a), 1 if a_is_f32 else 0, _ptr(a_mr), _ptr(r), 1 if r_is_f32 else 0,
+          _ptr(r_mr), r_cbt, r_c0 // 8, _ptr(dst.t), dst.cbt, dst_c0 // 8, n_img, channels // 8, voxels, slope, dst.fmt,
+          _stream())

@@ -10,20 +10,15 @@ import torch
 import torch.nn as nn
 
 from .backbones.dual_encoder import DualEncoder, build_dual_encoder  # noqa: F401  (re-exported like the reference)
+from .backbones.swin_unetr import SwinUNETR, build_swin_unetr        # noqa: F401
 from .backbones.unet import UNet3D, build_unet3d                      # noqa: F401
 
 Config = Dict[str, Any]
 
 
-def _swin_unetr_unavailable(config: Config) -> nn.Module:
-    # The reference (build.py:17, backbones/swin_unetr.py:71-96) only wraps monai.networks.nets.SwinUNETR; MONAI is not a
-    # dependency of this path and the arithmetic has no pinned oracle here.
-    raise NotImplementedError("swin_unetr is scope row N2 (MONAI SwinUNETR restatement): not part of this build")
-
-
 # name -> builder(config); the keys are the reference's MODEL_REGISTRY keys (build.py:16-21)
 MODEL_REGISTRY: Dict[str, Callable[[Config], nn.Module]] = {
-    "swin_unetr": _swin_unetr_unavailable,
+    "swin_unetr": build_swin_unetr,
     "unet": build_unet3d,
     "unet3d": build_unet3d,
     "dual_encoder": build_dual_encoder,
