@@ -506,6 +506,14 @@ def run_ours(args):
             torch.cuda.synchronize()
             attn_res = {"error": f"{type(e).__name__}: {e}"}
 
+    swin_res = None
+    if world == 1 and not args.no_train:
+        try:
+            swin_res = swin_measure(dev, cpu=not args.no_cpu)
+        except Exception as e:   # never allowed to break the headline line
+            torch.cuda.synchronize()
+            swin_res = {"error": f"{type(e).__name__}: {e}"}
+
     cfg = workload_config(args, world)
     cfg["numeric_mode"] = headline
     cfg["engine_batch"] = inf._state["nb"] if inf._state is not None else (args.engine_batch or "auto")
@@ -523,7 +531,7 @@ def run_ours(args):
                          "(max-abs <= 2e-2, rel-L2 <= 1e-3, labels >= 99.9 %, Dice within 1e-3 of the reference)",
         "parity": ladder or None, "gates": GATE_LIMITS,
         "label_agreement_vs_n1": agreement_vs_n1,
-        "train": train_res, "train5": train5_res, "attention": attn_res,
+        "train": train_res, "train5": train5_res, "attention": attn_res, "swin": swin_res,
     }
     emit(line)
     if world > 1:
@@ -743,6 +751,73 @@ def attention_measure(dev, steps=10, warmup=3):
     return {"metric": "CrossAttentionFusion forward (B=2, 4 heads), algorithmic 4*B*N^2*C", "peak_tflops": tf_peak, "shapes": out}
 
 
+def swin_measure(dev, steps=5, warmup=3, cpu=True):
+    """SwinUNETR feature_size 48, 2-channel 96^3 patches (BASELINE.json configs[3]), FORWARD through the drop-in module
+    (the backward of this model is not built): ms per batch, patches/s, algorithmic TFLOP/s (convs + linear layers +
+    window attention), the per-kernel split of one eager forward, and parity against the CPU oracle restatement
+    (PARITY UNPINNED: MONAI is absent, see oracle/swin_unetr.py) whose run time is the CPU baseline."""
+    import mmseg_b200  # noqa: F401
+    from mmseg_b200 import kernels as K
+    from mmseg_b200.src.models.backbones.swin_unetr import SwinUNETR
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    tf_peak = json.load(open(pk))["bf16_tflops_sustained"] if os.path.exists(pk) else 1400.0
+    torch.manual_seed(0)
+    m = SwinUNETR(in_channels=2, out_channels=8, feature_size=48).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.to(dev)
+    res = {"metric": "SwinUNETR-48 forward patches/s (2-channel 96^3, fp16 operands / fp32 accumulate)",
+           "config": "BASELINE.json configs[3] (forward only: the backward of SwinUNETR is not built)", "peak_tflops": tf_peak,
+           "batches": []}
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for B in (1, 4):
+        x = torch.randn((B, 2, 96, 96, 96), generator=g).to(dev)
+        with torch.no_grad():
+            for _ in range(warmup):
+                out = m(x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                out = m(x)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            K.PROFILE = []
+            out = m(x)
+            torch.cuda.synchronize()
+            prof, K.PROFILE = K.PROFILE, None
+        kms, flops = {}, 0.0
+        for name, info, a, b in prof:
+            kms[name] = kms.get(name, 0.0) + a.elapsed_time(b)
+            if info and "flops" in info:
+                flops += info["flops"]
+        row = {"batch": B, "ms": ms, "patches_per_s": B / (ms * 1e-3), "voxels_per_s": B * 96 ** 3 / (ms * 1e-3),
+               "gflop_per_patch": flops / B / 1e9, "tflops": flops / (ms * 1e-3) / 1e12,
+               "frac_of_tensor_peak": flops / (ms * 1e-3) / 1e12 / tf_peak, "launches": len(prof),
+               "kernel_ms": {k: round(v, 3) for k, v in sorted(kms.items(), key=lambda kv: -kv[1])}}
+        res["batches"].append(row)
+        log(f"[swin] B={B}: {ms:.2f} ms -> {row['patches_per_s']:.1f} patches/s, {row['tflops']:.0f} TFLOP/s "
+            f"({100 * row['frac_of_tensor_peak']:.0f}% of sustained peak), {len(prof)} launches; top: "
+            + ", ".join(f"{k[6:]} {v:.2f}" for k, v in list(row["kernel_ms"].items())[:6]))
+        if B == 1 and cpu:
+            from oracle.swin_unetr import swin_unetr_forward
+            torch.set_num_threads(max(1, os.cpu_count() or 1))
+            t0 = time.time()
+            ref = swin_unetr_forward(sd, x.cpu())
+            cpu_s = time.time() - t0
+            d = out.cpu() - ref
+            res["parity_vs_oracle"] = {"max_abs": d.abs().max().item(), "rel_l2": (d.norm() / ref.norm()).item(),
+                                       "label_agreement": (out.cpu().argmax(1) == ref.argmax(1)).double().mean().item(),
+                                       "oracle": "oracle/swin_unetr.py (CPU fp32 restatement of MONAI SwinUNETR, PARITY UNPINNED)"}
+            res["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
+                                   "sample": f"one 96^3 forward through the oracle ({cpu_s:.1f} s)"}
+            log(f"[swin] vs oracle: {res['parity_vs_oracle']}; CPU forward {cpu_s:.1f} s")
+        del x, out
+    del m
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_train(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -797,7 +872,7 @@ def main():
     ap.add_argument("--no-ladder", action="store_true", help="skip the throughput of the non-headline numeric modes")
     ap.add_argument("--no-selfcheck", action="store_true", help="N>1: skip the sharded-vs-single-GPU label comparison")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline / parity sample")
-    ap.add_argument("--workload", default="inference", choices=["inference", "train", "train5", "attention"],
+    ap.add_argument("--workload", default="inference", choices=["inference", "train", "train5", "attention", "swin"],
                     help="inference = headline sliding-window voxels/s (default); train = DualEncoder CT+PET 128^3 B=2 "
                          "samples/s (configs[1]); train5 = 4-modality attention-gate DualEncoder 128^3 B=4 (configs[4])")
     ap.add_argument("--no-graph", action="store_true", help="train workload: do not capture the step in a CUDA graph")
@@ -810,6 +885,9 @@ def main():
     elif args.workload == "attention":
         torch.cuda.set_device(0)
         emit(attention_measure(torch.device("cuda", 0)))
+    elif args.workload == "swin":
+        torch.cuda.set_device(0)
+        emit(swin_measure(torch.device("cuda", 0), steps=args.steps, warmup=args.warmup, cpu=not args.no_cpu))
     else:
         run_ours(args)
 

@@ -223,7 +223,10 @@ int mmseg_modality_dot(const void* x, int32_t x_cbt, const void* g, int32_t g_cb
 int mmseg_unshuffle_k2s2(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_cb_off, int32_t cb, int32_t Z,
                          int32_t Y, int32_t X, void* dst, void* stream);
 
-/* NCDHW fp32 [n_img][C][Z][Y][X] -> blocked bf16 (hi[, lo]) with channels zero-padded to cb*8.  Module boundary. */
+/* NCDHW fp32 [n_img][C][Z][Y][X] -> blocked bf16 (hi[, lo]) with channels zero-padded to cb*8.  Module boundary.  * dst_lo_off < 0 ("packed split"): instead of separate hi / lo planes the destination receives the VIRTUAL channels
+ * [hi(C) | lo(C) | hi(C)] (3C <= 8*cb), so that A_hi*W_hi + A_lo*W_hi + A_hi*W_lo of a thin first layer is ONE K chunk
+ * against the weights [W_hi | W_hi | W_lo]; mmseg_swi_gather takes the same convention.
+ */
 int mmseg_pack_ncdhw(const float* src, void* dst, int32_t n_img, int32_t C, int32_t Z, int32_t Y, int32_t X,
                      int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, int32_t cb, int32_t fmt, void* stream);
 /* blocked bf16 (hi[, lo]) -> NCDHW fp32 (feature taps for return_features / hooks). */

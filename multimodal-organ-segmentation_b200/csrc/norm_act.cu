@@ -276,9 +276,21 @@ pack_ncdhw_kernel(const float* __restrict__ src, void* __restrict__ dst, int n_i
   const int blk = blockIdx.y;  // img*cb + c
   const int img = blk / cb, c = blk - img * cb;
   const size_t dst_base = (size_t)(img * dst_cbt + dst_cb_off + c) * nvox * 8;
-  const size_t lo_delta = (size_t)dst_lo_off * nvox * 8;
+  const size_t lo_delta = dst_lo_off > 0 ? (size_t)dst_lo_off * nvox * 8 : 0;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
     float x[8];
+    if (dst_lo_off < 0) {   // packed split: virtual channels [hi(C) | lo(C) | hi(C)] in one 16-channel K chunk (see swi_gather_kernel)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int vc = c * 8 + i;
+        const int part = vc / C, ch = vc - part * C;
+        const float t = part < 3 ? src[((size_t)img * C + ch) * nvox + v] : 0.f;
+        const float hi = fp16 ? __half2float(__float2half_rn(t)) : __bfloat162float(__float2bfloat16_rn(t));
+        x[i] = part == 1 ? t - hi : hi;
+      }
+      store8_act(dst, dst_base + v * 8, 0, x, fp16 != 0);
+      continue;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int ch = c * 8 + i;
@@ -429,7 +441,8 @@ extern "C" int mmseg_instnorm_act_apply(const mmseg_norm_args* a, void* stream) 
 extern "C" int mmseg_pack_ncdhw(const float* src, void* dst, int32_t n_img, int32_t C, int32_t Z, int32_t Y,
                                 int32_t X, int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, int32_t cb,
                                 int32_t fmt, void* stream) {
-  if (!src || !dst || n_img < 1 || C < 1 || cb * 8 < C || (fmt != MMSEG_FMT_BF16 && fmt != MMSEG_FMT_FP16))
+  if (!src || !dst || n_img < 1 || C < 1 || cb * 8 < (dst_lo_off < 0 ? 3 * C : C) ||
+      (fmt != MMSEG_FMT_BF16 && fmt != MMSEG_FMT_FP16))
     return fail(MMSEG_ERR_INVALID_ARG, "pack_ncdhw: bad arguments");
   const size_t nvox = (size_t)Z * Y * X;
   const int rows = n_img * cb;

@@ -22,10 +22,26 @@ swi_gather_kernel(const float* __restrict__ vol, int C, int VZ, int VY, int VX, 
   const size_t nvox_v = (size_t)VZ * VY * VX;
   const size_t nvox_r = (size_t)RZ * RY * RX;
   const size_t dst_base = ((size_t)(win * dst_cbt + c) * nvox_r + ((size_t)lz * RY + ly) * RX) * 8;
-  const size_t lo_delta = (size_t)dst_lo_off * nvox_r * 8;
+  const size_t lo_delta = dst_lo_off > 0 ? (size_t)dst_lo_off * nvox_r * 8 : 0;
   for (int lx = blockIdx.x * blockDim.x + threadIdx.x; lx < RX; lx += gridDim.x * blockDim.x) {
     const int gx = sx + lx;
     float v[8];
+    if (dst_lo_off < 0) {
+      // packed split (numeric modes that keep the INPUT hi + lo AND split the first conv's weights): the three operand
+      // passes A_hi*W_hi + A_lo*W_hi + A_hi*W_lo of a C <= 5 channel input fit ONE 16-channel K chunk as the virtual
+      // channels [hi(C) | lo(C) | hi(C)] against the weights [W_hi | W_hi | W_lo] (engine.py)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int vc = c * 8 + i;
+        const int part = vc / C, ch = vc - part * C;
+        float x = 0.f;
+        if (row_in && gx >= 0 && gx < VX && part < 3) x = vol[(size_t)ch * nvox_v + ((size_t)gz * VY + gy) * VX + gx];
+        const float hi = fp16 ? __half2float(__float2half_rn(x)) : __bfloat162float(__float2bfloat16_rn(x));
+        v[i] = part == 1 ? x - hi : hi;
+      }
+      store8_act(dst, dst_base + (size_t)lx * 8, 0, v, fp16 != 0);
+      continue;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int ch = c * 8 + i;
@@ -275,7 +291,7 @@ using namespace mmseg;
 extern "C" int mmseg_swi_gather(const float* volume, int32_t C, int32_t VZ, int32_t VY, int32_t VX,
                                 const int32_t* starts_dev, int32_t n_win, int32_t RZ, int32_t RY, int32_t RX,
                                 void* dst, int32_t dst_cbt, int32_t dst_lo_off, int32_t cb, int32_t fmt, void* stream) {
-  if (!volume || !starts_dev || !dst || n_win < 1 || C < 1 || cb * 8 < C || RZ * RY > 65535 || n_win * cb > 65535 ||
+  if (!volume || !starts_dev || !dst || n_win < 1 || C < 1 || cb * 8 < (dst_lo_off < 0 ? 3 * C : C) || RZ * RY > 65535 || n_win * cb > 65535 ||
       (fmt != MMSEG_FMT_BF16 && fmt != MMSEG_FMT_FP16))
     return fail(MMSEG_ERR_INVALID_ARG, "swi_gather: bad arguments");
   dim3 grid((RX + 127) / 128, RZ * RY, n_win * cb);

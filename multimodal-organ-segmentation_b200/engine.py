@@ -11,6 +11,7 @@ Numeric modes (numerics.py — the parity ladder bf16 / fp16 / fp16w2 / fp16a2 /
                bf16 hi+lo pairs and raw conv outputs as fp32: ~2^-16 relative operand error, which is what the
                stated logit/label tolerances need.
 """
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -227,6 +228,16 @@ class UNet3DEngine:
             self._norms[name + ".conv1"], self._norms[name + ".conv2"] = blk.norm1, blk.norm2
 
         block("init_conv", m.init_conv, [m.in_channels], "enc0", "in", "mid0")
+        if self.in_packed:
+            # hi + lo input AND split first-conv weights with a thin input: the three operand passes become ONE K chunk —
+            # virtual input channels [hi | lo | hi] (written by pack_ncdhw / swi_gather) against [W_hi | W_hi | W_lo]
+            blk = m.init_conv
+            inst = isinstance(blk.norm1, torch.nn.InstanceNorm3d)
+            w = blk.conv1.weight.detach().float()
+            w_hi = w.to(nm.dtype).float()
+            wv = torch.cat([w_hi, w_hi, w - w_hi], dim=1)
+            P["init_conv.conv1"] = K.pack_conv_weight(wv, None if inst else blk.conv1.bias, self._in_packed_mode(),
+                                                      [3 * m.in_channels], use_bias=not inst)
         for i, enc in enumerate(m.encoders):
             block(f"encoders.{i}", enc.conv, [f[i]], f"enc{i + 1}", f"pool{i + 1}", f"mid{i + 1}")
         for j, dec in enumerate(m.decoders):
@@ -238,6 +249,17 @@ class UNet3DEngine:
         P["out_conv"] = K.pack_conv_weight(m.out_conv.weight, m.out_conv.bias, nm.layer("up", bsplit("dec0")), None)
         self._packed, self._packed_version = P, ver
         return P
+
+    @property
+    def in_packed(self) -> bool:
+        """First layer with the split passes packed into one K chunk (kernels.Blocked.packed_split)."""
+        nm, m = self.nm, self.module
+        return (nm.buffer("in").a_split and nm.layer("enc0.1", True).w_split and 3 * m.in_channels <= 16
+                and os.environ.get("MMSEG_IN_PACKED", "1") == "1")
+
+    def _in_packed_mode(self):
+        from .numerics import _resolved
+        return _resolved(self.nm, False, False, self.nm.layer("enc0.1", True).raw_f32)
 
     # ---------------------------------------------------------------- buffers
     def _buffers(self, n: int, Z: int, Y: int, X: int, device) -> Dict[str, object]:
@@ -253,6 +275,9 @@ class UNet3DEngine:
                 "UpBlock3D (reference unet.py:108-109) is not implemented in the sm_100a path")
         sp = self.nm.buffer          # per-buffer storage mode (hi-only vs hi + lo; mixed modes differ per buffer)
         b = {"in": Blocked(n, (self.module.in_channels + 15) // 16 * 16, Z, Y, X, sp("in"), device)}
+        if self.in_packed:
+            b["in"] = Blocked(n, 16, Z, Y, X, self._in_packed_mode(), device)
+            b["in"].packed_split = True
         b["in"].t.zero_()   # the sliding-window gather writes only the blocks with real channels
         for l in range(L):
             z, y, x = Z >> l, Y >> l, X >> l
@@ -291,7 +316,8 @@ class UNet3DEngine:
         r = self._runner
         cin_p = (m.in_channels + 15) // 16 * 16
         # encoder (unet.py:181-187); each block's output lands in the skip half of its level's concat buffer
-        r.conv_norm_act(b["in"], [(0, m.in_channels)], P["init_conv.conv1"], b["mid0"], norm=N["init_conv.conv1"])
+        r.conv_norm_act(b["in"], [(0, (3 if self.in_packed else 1) * m.in_channels)], P["init_conv.conv1"], b["mid0"],
+                        norm=N["init_conv.conv1"])
         for l in range(L):
             last = l == L - 1
             if l > 0:

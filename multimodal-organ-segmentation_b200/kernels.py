@@ -69,6 +69,9 @@ class Blocked:
         self.cbt = self.cb * (2 if self.split else 1)
         self.lo_off = self.cb if self.split else 0
         self.t = torch.empty((n_img, self.cbt, Z, Y, X, 8), dtype=nm.dtype, device=device)
+        # "packed split" input buffer: the producers (pack_ncdhw / swi_gather) write the virtual channels
+        # [hi(C) | lo(C) | hi(C)] into this (non-split) buffer instead of hi / lo planes — see engine.py
+        self.packed_split = False
 
     @property
     def nvox(self) -> int:
@@ -90,7 +93,11 @@ def pack_ncdhw(x: Tensor, dst: Blocked, c0: int = 0) -> None:
     n, Cc, Z, Y, X = x.shape
     cb = ((Cc + 15) // 16) * 2
     assert (n, Z, Y, X) == (dst.n_img, dst.Z, dst.Y, dst.X) and c0 % 8 == 0 and c0 // 8 + cb <= dst.cb
-    _call("mmseg_pack_ncdhw", _ptr(x), _ptr(dst.t), n, Cc, Z, Y, X, dst.cbt, c0 // 8, dst.lo_off, cb, dst.fmt, _stream())
+    lo_off = dst.lo_off
+    if dst.packed_split:
+        assert 3 * Cc <= 8 * cb and not dst.split and c0 == 0
+        lo_off = -1
+    _call("mmseg_pack_ncdhw", _ptr(x), _ptr(dst.t), n, Cc, Z, Y, X, dst.cbt, c0 // 8, lo_off, cb, dst.fmt, _stream())
 
 
 # --------------------------------------------------------------------------------------------- weight packing
@@ -465,8 +472,11 @@ def swi_gather(volume: Tensor, starts_dev: Tensor, n_win: int, roi: Tuple[int, i
     # only the channel blocks that hold real channels are written: the zero padding up to a whole 16-channel K chunk
     # is written once when the engine allocates (and zeroes) its input buffer
     cb = (Cc + 7) // 8
+    lo_off = dst.lo_off
+    if dst.packed_split:
+        cb, lo_off = (3 * Cc + 7) // 8, -1
     _call("mmseg_swi_gather", _ptr(volume), Cc, VZ, VY, VX, _ptr(starts_dev), n_win, roi[0], roi[1], roi[2],
-                               _ptr(dst.t), dst.cbt, dst.lo_off, cb, dst.fmt, _stream())
+                               _ptr(dst.t), dst.cbt, lo_off, cb, dst.fmt, _stream())
 
 
 def swi_blend(win_logits: Tensor, starts_dev: Tensor, n_win: int, wz: Tensor, wy: Tensor, wx: Tensor, w_floor: float,

@@ -224,6 +224,9 @@ def mode_bounds(mode):
     return GATES if mode in ("parity", "bf16x3", "fp16x3", "fp16m") else NOISE_CLASS[mode]
 
 
+NOISE_CLASS["fp16i"] = (2e-2, 3e-3, 0.995)   # thin margins by construction; bench.py measures the gates on the crop
+
+
 def _metrics(got, ref):
     d = (got - ref).double()
     max_abs = d.abs().max().item()
@@ -252,6 +255,31 @@ def unet_case(features=(16, 32, 64), S=32, n_img=1, mode="parity", in_ch=2, seed
     assert torch.isfinite(got).all()
     assert max_abs <= tol[0] and rel_l2 <= tol[1] and agree >= tol[2], (max_abs, rel_l2, agree)
     return max_abs, rel_l2, agree
+
+
+def in_packed_case(features=(16, 32, 64), S=32, mode="fp16m", in_ch=2):
+    """The first layer with its three split passes packed into one K chunk (virtual channels [hi | lo | hi] x
+    [W_hi | W_hi | W_lo]) gives the logits of the three-chunk form (same products, another fp32 summation order)."""
+    import os
+    from mmseg_b200.src.models.backbones.unet import UNet3D
+    torch.manual_seed(3)
+    m = UNet3D(in_channels=in_ch, out_channels=8, features=list(features)).eval().to(DEV)
+    x = torch.randn(2, in_ch, S, S, S, device=DEV) * 3 + 1
+    outs = {}
+    for flag in ("0", "1"):
+        os.environ["MMSEG_IN_PACKED"] = flag
+        m._engines.clear()
+        m.set_numeric_mode(mode)
+        eng = m.engine()
+        assert eng.in_packed == (flag == "1"), (flag, eng.in_packed)
+        with torch.no_grad():
+            outs[flag] = m(x).clone()
+    os.environ.pop("MMSEG_IN_PACKED", None)
+    d = (outs["0"] - outs["1"]).abs().max().item()
+    print(f"[in_packed {mode} cin{in_ch}] max|packed - three chunks| = {d:.2e} (logit scale {outs['0'].abs().max().item():.2f})")
+    # identical products, but every later activation is re-rounded to 16 bits, so a 1e-7 change of the summation order moves
+    # roundings: in the mixed modes the two forms differ by the mode's own noise (~1e-3), in the 3-pass modes by ~1e-5
+    assert d < (2e-4 if mode in ("parity", "fp16x3") else 5e-3)
 
 
 def unet_time_case(n_img=1, S=96, mode="bf16", iters=5):

@@ -61,6 +61,11 @@ def test_conv3d_rolling_z(args, kw):
     _c().conv_case(*args, **kw)
 
 
+@pytest.mark.parametrize("mode,in_ch", [("fp16m", 2), ("parity", 2), ("fp16i", 4), ("fp16x3", 1)])
+def test_first_layer_packed_split(mode, in_ch):
+    _c().in_packed_case(mode=mode, in_ch=in_ch)
+
+
 @pytest.mark.parametrize("args,kw", [
     ((16, 32, (8, 12, 16)), {}),
     ((2, 32, (8, 12, 16)), dict(split=True)),
@@ -151,7 +156,7 @@ def test_pack_unpack_roundtrip():
 @pytest.mark.parametrize("features,S,n,mode", [((16, 32, 64), 32, 1, "parity"), ((16, 32, 64), 32, 2, "bf16"),
                                                 ((16, 32, 64), 32, 2, "fp16"), ((16, 32, 64), 32, 1, "fp16w2"),
                                                 ((16, 32, 64), 32, 1, "fp16a2"), ((16, 32, 64), 32, 2, "fp16x3"),
-                                                ((16, 32, 64), 32, 2, "fp16m"),
+                                                ((16, 32, 64), 32, 2, "fp16m"), ((16, 32, 64), 32, 2, "fp16i"),
                                                 ((32, 64, 128, 256, 512), 96, 1, "parity"),
                                                 ((32, 64, 128, 256, 512), 96, 1, "fp16m"),
                                                 ((32, 64, 128, 256, 512), 96, 1, "fp16"),
