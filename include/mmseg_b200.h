@@ -253,6 +253,10 @@ int mmseg_unpack_ncdhw(const void* src, float* dst, int32_t n_img, int32_t C, in
 int mmseg_swi_gather(const float* volume, int32_t C, int32_t VZ, int32_t VY, int32_t VX, const int32_t* starts_dev,
                      int32_t n_win, int32_t RZ, int32_t RY, int32_t RX, void* dst, int32_t dst_cbt, int32_t dst_lo_off,
                      int32_t cb, int32_t fmt, void* stream);
+/* The same windows as a plain fp32 batch dst [n_win][C][RZ][RY][RX] (zero outside the volume): the image input of
+ * SwinUNETR's patch embedding under monai.inferers.sliding_window_inference (trainer.py:381-392). */
+int mmseg_swi_gather_ncdhw(const float* volume, int32_t C, int32_t VZ, int32_t VY, int32_t VX, const int32_t* starts_dev,
+                           int32_t n_win, int32_t RZ, int32_t RY, int32_t RX, float* dst, void* stream);
 /* out_conv (1x1x1, C -> K <= 8 classes, unet.py:163,199) fused into the blend of ONE window: the logits of window
  * `window` of the blocked feature batch are computed in registers and blended into out / count (same arithmetic and order
  * as mmseg_conv1x1_logits + mmseg_swi_blend in window mode, bit-identical accumulators) — the logits tensor is never

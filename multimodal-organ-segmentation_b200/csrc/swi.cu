@@ -53,6 +53,25 @@ swi_gather_kernel(const float* __restrict__ vol, int C, int VZ, int VY, int VX, 
   }
 }
 
+// Windows as a plain NCDHW fp32 batch (zero outside the volume): the input of SwinUNETR's strided patch embedding, which
+// reads the image itself rather than the 16-bit blocked copy.
+__global__ void __launch_bounds__(128)
+swi_gather_ncdhw_kernel(const float* __restrict__ vol, int C, int VZ, int VY, int VX, const int* __restrict__ starts,
+                        int RZ, int RY, int RX, float* __restrict__ dst) {
+  const int wc = blockIdx.z;
+  const int win = wc / C, ch = wc - win * C;
+  const int row = blockIdx.y;
+  const int lz = row / RY, ly = row - lz * RY;
+  const int gz = starts[win * 3 + 0] + lz, gy = starts[win * 3 + 1] + ly, sx = starts[win * 3 + 2];
+  const bool row_in = (gz >= 0) && (gz < VZ) && (gy >= 0) && (gy < VY);
+  const float* src = vol + (size_t)ch * VZ * VY * VX + ((size_t)gz * VY + gy) * VX;
+  float* d = dst + ((size_t)wc * RZ * RY + row) * RX;
+  for (int lx = blockIdx.x * blockDim.x + threadIdx.x; lx < RX; lx += gridDim.x * blockDim.x) {
+    const int gx = sx + lx;
+    d[lx] = (row_in && gx >= 0 && gx < VX) ? src[gx] : 0.f;
+  }
+}
+
 // One owner thread per output voxel of the box; loops over the batch's windows in index order.
 // seg*w and the accumulate are separate roundings (__fmul_rn / __fadd_rn) exactly like `seg *= w; out += seg`.
 __global__ void __launch_bounds__(128)
@@ -298,6 +317,17 @@ extern "C" int mmseg_swi_gather(const float* volume, int32_t C, int32_t VZ, int3
   swi_gather_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       volume, C, VZ, VY, VX, starts_dev, RZ, RY, RX, dst, dst_cbt, dst_lo_off, cb, fmt);
   return check_launch("swi_gather_kernel");
+}
+
+extern "C" int mmseg_swi_gather_ncdhw(const float* volume, int32_t C, int32_t VZ, int32_t VY, int32_t VX,
+                                      const int32_t* starts_dev, int32_t n_win, int32_t RZ, int32_t RY, int32_t RX,
+                                      float* dst, void* stream) {
+  if (!volume || !starts_dev || !dst || n_win < 1 || C < 1 || RZ * RY > 65535 || n_win * C > 65535)
+    return fail(MMSEG_ERR_INVALID_ARG, "swi_gather_ncdhw: bad arguments");
+  dim3 grid((RX + 127) / 128, RZ * RY, n_win * C);
+  swi_gather_ncdhw_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(volume, C, VZ, VY, VX, starts_dev, RZ,
+                                                                                    RY, RX, dst);
+  return check_launch("swi_gather_ncdhw_kernel");
 }
 
 extern "C" int mmseg_swi_blend(const float* win_logits, const int32_t* starts_dev, int32_t n_win, int32_t K,

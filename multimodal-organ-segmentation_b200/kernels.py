@@ -479,6 +479,13 @@ def swi_gather(volume: Tensor, starts_dev: Tensor, n_win: int, roi: Tuple[int, i
                                _ptr(dst.t), dst.cbt, lo_off, cb, dst.fmt, _stream())
 
 
+def swi_gather_ncdhw(volume: Tensor, starts_dev: Tensor, n_win: int, roi: Tuple[int, int, int], dst: Tensor) -> None:
+    Cc, VZ, VY, VX = volume.shape
+    assert dst.dtype == torch.float32 and dst.is_contiguous() and dst.numel() >= n_win * Cc * roi[0] * roi[1] * roi[2]
+    _call("mmseg_swi_gather_ncdhw", _ptr(volume), Cc, VZ, VY, VX, _ptr(starts_dev), n_win, roi[0], roi[1], roi[2], _ptr(dst),
+          _stream())
+
+
 def swi_blend(win_logits: Tensor, starts_dev: Tensor, n_win: int, wz: Tensor, wy: Tensor, wx: Tensor, w_floor: float,
               out: Tensor, count: Tensor, box: Tuple[int, int, int, int, int, int]) -> None:
     K, VZ, VY, VX = out.shape

@@ -154,6 +154,15 @@ class SwinUNETRNet(nn.Module):
         self.decoder1 = UnetrUpBlock(F, F)
         self.out = UnetOutBlock(F, out_channels)
 
+    # what the sliding-window inferer reads to fuse the 1x1x1 head into its blend kernel
+    @property
+    def out_conv(self) -> nn.Conv3d:
+        return self.out.conv.conv
+
+    @property
+    def features(self) -> List[int]:
+        return [self.feature_size << i for i in range(5)]
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         raise RuntimeError("call the SwinUNETR wrapper: the forward runs in the sm_100a engine")
 
@@ -195,7 +204,6 @@ class SwinUNETR(nn.Module):
             self.__dict__.pop("_engine", None)
         return self
 
-    @property
     def engine(self) -> SwinUNETREngine:
         eng = self.__dict__.get("_engine")
         if eng is None:
@@ -208,10 +216,10 @@ class SwinUNETR(nn.Module):
             raise RuntimeError("mmseg_b200 modules run on CUDA (sm_100a) tensors only; there is no CPU fallback")
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             raise NotImplementedError("SwinUNETR is forward-only in the sm_100a path: wrap the call in torch.no_grad()")
-        out = self.engine.forward(x)
+        out = self.engine().forward(x)
         if return_features:
             n, _, Z, Y, X = x.shape
-            return out, self.engine.hidden_states(n, Z, Y, X, x.device)
+            return out, self.engine().hidden_states(n, Z, Y, X, x.device)
         return out
 
     def load_pretrained(self, path: str) -> None:

@@ -35,10 +35,14 @@ def _lin_w(lin) -> Tensor:
 
 
 class SwinUNETREngine:
-    def __init__(self, net, mode: str = "fp16"):
+    def __init__(self, net, mode: str = "fp16", weights_from: Optional["SwinUNETREngine"] = None):
+        """weights_from: another engine of the same net and mode whose packed weights this one reads (the extra batch
+        slots of the sliding-window inferer)."""
         if mode not in SWIN_MODES:
             raise ValueError(f"SwinUNETR numeric mode {mode!r}; choose from {sorted(SWIN_MODES)}")
-        self.net = net
+        self.net = self.module = net       # `module`: the name the sliding-window inferer uses
+        self.mode = mode
+        self._weights_from = weights_from
         self.nm = SWIN_MODES[mode]
         self._packed: Optional[Dict[str, PackedConv]] = None
         self._packed_version = None
@@ -49,6 +53,8 @@ class SwinUNETREngine:
 
     # ---------------------------------------------------------------- weights
     def _pack(self) -> Dict[str, PackedConv]:
+        if self._weights_from is not None:
+            return self._weights_from._pack()
         net = self.net
         ver = _param_version(list(net.parameters()))
         if self._packed is not None and ver == self._packed_version:
@@ -99,6 +105,7 @@ class SwinUNETREngine:
         dims = [(Z >> l, Y >> l, X >> l) for l in range(6)]
         b = {"in": Blocked(n, (net.in_channels + 15) // 16 * 16, Z, Y, X, nm, device)}
         b["in"].t.zero_()
+        b["x32"] = torch.empty((n, net.in_channels, Z, Y, X), dtype=torch.float32, device=device)   # sliding-window batches
         # token path: stage s works on C = F * 2^s channels at dims[s + 1]
         for s in range(4):
             C_, d = F << s, dims[s + 1]
@@ -130,6 +137,13 @@ class SwinUNETREngine:
 
     def input_buffer(self, n: int, Z: int, Y: int, X: int, device) -> Blocked:
         return self._buffers(n, Z, Y, X, device)["in"]
+
+    def gather_windows(self, volume: Tensor, starts_dev: Tensor, n: int, roi) -> None:
+        """Sliding-window gather of n windows of `volume` [C, VZ, VY, VX]: the blocked 16-bit copy feeds encoder1, the
+        fp32 batch feeds the patch embedding (which reads the image itself)."""
+        b = self._buffers(n, roi[0], roi[1], roi[2], volume.device)
+        K.swi_gather(volume, starts_dev, n, roi, b["in"])
+        K.swi_gather_ncdhw(volume, starts_dev, n, roi, b["x32"])
 
     # ---------------------------------------------------------------- pieces
     def _gemm(self, src: Blocked, segs, pw: PackedConv, dst, f32: bool, dst_cbt: int, dst_c0: int = 0) -> None:
@@ -180,14 +194,18 @@ class SwinUNETREngine:
 
     # ---------------------------------------------------------------- forward
     @torch.no_grad()
-    def forward_blocked(self, n: int, Z: int, Y: int, X: int, x: Tensor, logits: Optional[Tensor]):
-        """x: the NCDHW fp32 input (the patch embedding reads it directly; the blocked copy in b['in'] feeds encoder1)."""
+    def forward_blocked(self, n: int, Z: int, Y: int, X: int, logits: Optional[Tensor], device=None, x: Optional[Tensor] = None):
+        """x: the NCDHW fp32 input (the patch embedding reads it directly; the blocked copy in b['in'] feeds encoder1);
+        None = the window batch gather_windows() left in the engine.  logits None: returns the last feature map (the
+        caller fuses the 1x1x1 head into its consumer)."""
         _lib.require_device()
         net = self.net
         F = net.feature_size
-        device = x.device
+        device = x.device if x is not None else (logits.device if logits is not None else device)
         P = self._pack()
         b = self._buffers(n, Z, Y, X, device)
+        if x is None:
+            x = b["x32"]
         if self._ws is None:
             self._ws = _Workspace(device)
         vit = net.swinViT
@@ -274,7 +292,7 @@ class SwinUNETREngine:
             raise ValueError(f"expected {self.net.in_channels} input channels, got {cin}")
         K.pack_ncdhw(x, self.input_buffer(n, Z, Y, X, x.device))
         logits = torch.empty((n, self.net.out_channels, Z, Y, X), dtype=torch.float32, device=x.device)
-        return self.forward_blocked(n, Z, Y, X, x, logits)
+        return self.forward_blocked(n, Z, Y, X, logits, x=x)
 
     def hidden_states(self, n: int, Z: int, Y: int, X: int, device) -> List[Tensor]:
         """The five swinViT outputs of the last forward as NCDHW fp32 (reference swin_unetr.py:129-130)."""

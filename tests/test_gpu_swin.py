@@ -59,3 +59,7 @@ def test_residual_instnorm_act():
 @pytest.mark.parametrize("size,mode", [(64, "fp16"), (64, "bf16"), (96, "fp16")])
 def test_swin_unetr_vs_oracle(size, mode):
     _c().swin_unetr_case(size=size, mode=mode)
+
+
+def test_swin_unetr_sliding_window():
+    _c().swin_sliding_window_case()
