@@ -118,17 +118,77 @@ swin_layernorm_kernel(float* __restrict__ xs, const float* __restrict__ add, con
   }
 }
 
+// Warp-per-token variant for the deep stages (few tokens, C >= 192): lane l owns channel blocks l, l+32, ...; the
+// thread-per-token kernel would leave most SMs idle there (216 tokens x 384 channels on one warp's worth of threads).
+__global__ void __launch_bounds__(256)
+swin_layernorm_warp_kernel(float* __restrict__ xs, const float* __restrict__ add, const float* __restrict__ gamma,
+                           const float* __restrict__ beta, void* __restrict__ dst, int n_img, int cb, size_t nvox,
+                           int dst_cbt, int dst_cb_off, float eps, int fp16) {
+  const size_t tok = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (tok >= (size_t)n_img * nvox) return;
+  const int img = (int)(tok / nvox);
+  const size_t v = tok - (size_t)img * nvox;
+  const size_t bs = nvox * 8;
+  float* px = xs + (size_t)img * cb * bs + v * 8;
+  const float* pa = add ? add + (size_t)img * cb * bs + v * 8 : nullptr;
+  float s = 0.f;
+  for (int b = lane; b < cb; b += 32) {
+    float a[8];
+    ld8f(px + b * bs, a);
+    if (pa) {
+      float y[8];
+      ld8f(pa + b * bs, y);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] += y[i];
+      st8f(px + b * bs, a);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+  }
+  if (!dst) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float inv_c = 1.f / (float)(cb * 8);
+  const float mean = s * inv_c;
+  float q = 0.f;
+  for (int b = lane; b < cb; b += 32) {
+    float a[8];
+    ld8f(px + b * bs, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = a[i] - mean; q = fmaf(d, d, q); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * inv_c + eps);
+  uint16_t* pd = reinterpret_cast<uint16_t*>(dst);
+  const size_t dbase = ((size_t)img * dst_cbt + dst_cb_off) * bs + v * 8;
+  for (int b = lane; b < cb; b += 32) {
+    float a[8];
+    ld8f(px + b * bs, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float y = (a[i] - mean) * rstd;
+      if (gamma) y = fmaf(y, gamma[b * 8 + i], beta ? beta[b * 8 + i] : 0.f);
+      a[i] = y;
+    }
+    store8_act(pd, dbase + b * bs, 0, a, fp16 != 0);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ patch merging
 // MONAI PatchMerging (v1, 3-D): the eight gathered sub-grids in its legacy order, concatenated on channels, LayerNorm(8C)
 // with affine; the bias-free Linear(8C -> 2C) that follows is a 1x1x1 GEMM on the conv kernel.
 __constant__ int kMergeOff[8][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {0, 1, 0}, {0, 0, 1}, {1, 1, 1}};
 
-__global__ void __launch_bounds__(128)
+// One warp per output token: lane l owns the (octant, channel block) pairs l, l+32, ... of the 8C-channel row.
+__global__ void __launch_bounds__(256)
 swin_merge_ln_kernel(const float* __restrict__ xs, const float* __restrict__ gamma, const float* __restrict__ beta,
                      void* __restrict__ dst, int n_img, int cb, int Z, int Y, int X, float eps, int fp16) {
   const int Zo = Z / 2, Yo = Y / 2, Xo = X / 2;
   const size_t nout = (size_t)Zo * Yo * Xo, nvox = (size_t)Z * Y * X;
-  const size_t tok = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t tok = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (tok >= (size_t)n_img * nout) return;
   const int img = (int)(tok / nout);
   const size_t v = tok - (size_t)img * nout;
@@ -136,40 +196,42 @@ swin_merge_ln_kernel(const float* __restrict__ xs, const float* __restrict__ gam
   const size_t r = v / Xo;
   const int yo = (int)(r % Yo), zo = (int)(r / Yo);
   const float* base = xs + (size_t)img * cb * nvox * 8;
-  size_t off[8];
-#pragma unroll
-  for (int o = 0; o < 8; ++o)
-    off[o] = (((size_t)(2 * zo + kMergeOff[o][0]) * Y + (2 * yo + kMergeOff[o][1])) * X + (2 * xo + kMergeOff[o][2])) * 8;
+  const int npair = 8 * cb;
+  auto src_of = [&](int p) -> const float* {
+    const int o = p / cb, b = p - o * cb;
+    const size_t off = (((size_t)(2 * zo + kMergeOff[o][0]) * Y + (2 * yo + kMergeOff[o][1])) * X + (2 * xo + kMergeOff[o][2])) * 8;
+    return base + (size_t)b * nvox * 8 + off;
+  };
   float s = 0.f;
-  for (int o = 0; o < 8; ++o)
-    for (int b = 0; b < cb; ++b) {
-      float a[8];
-      ld8f(base + (size_t)b * nvox * 8 + off[o], a);
+  for (int p = lane; p < npair; p += 32) {
+    float a[8];
+    ld8f(src_of(p), a);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s += a[i];
-    }
+    for (int i = 0; i < 8; ++i) s += a[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float inv_c = 1.f / (float)(cb * 64);
   const float mean = s * inv_c;
   float q = 0.f;
-  for (int o = 0; o < 8; ++o)
-    for (int b = 0; b < cb; ++b) {
-      float a[8];
-      ld8f(base + (size_t)b * nvox * 8 + off[o], a);
+  for (int p = lane; p < npair; p += 32) {
+    float a[8];
+    ld8f(src_of(p), a);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { const float d = a[i] - mean; q = fmaf(d, d, q); }
-    }
+    for (int i = 0; i < 8; ++i) { const float d = a[i] - mean; q = fmaf(d, d, q); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q * inv_c + eps);
   uint16_t* pd = reinterpret_cast<uint16_t*>(dst);
-  const size_t dbase = (size_t)img * (8 * cb) * nout * 8 + v * 8;
-  for (int o = 0; o < 8; ++o)
-    for (int b = 0; b < cb; ++b) {
-      float a[8];
-      ld8f(base + (size_t)b * nvox * 8 + off[o], a);
-      const int ch = (o * cb + b) * 8;
+  const size_t dbase = (size_t)img * npair * nout * 8 + v * 8;
+  for (int p = lane; p < npair; p += 32) {
+    float a[8];
+    ld8f(src_of(p), a);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = fmaf((a[i] - mean) * rstd, gamma[ch + i], beta[ch + i]);
-      store8_act(pd, dbase + (size_t)(o * cb + b) * nout * 8, 0, a, fp16 != 0);
-    }
+    for (int i = 0; i < 8; ++i) a[i] = fmaf((a[i] - mean) * rstd, gamma[p * 8 + i], beta[p * 8 + i]);
+    store8_act(pd, dbase + (size_t)p * nout * 8, 0, a, fp16 != 0);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ window attention
@@ -497,8 +559,14 @@ extern "C" int mmseg_swin_layernorm(float* xs, const float* add, const float* ga
     return fail(MMSEG_ERR_INVALID_ARG, "swin_layernorm: bad arguments");
   if (elem_fmt != MMSEG_FMT_BF16 && elem_fmt != MMSEG_FMT_FP16) return fail(MMSEG_ERR_INVALID_ARG, "swin_layernorm: elem_fmt");
   const size_t tok = (size_t)n_img * voxels;
-  swin_layernorm_kernel<<<(unsigned)((tok + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      xs, add, gamma, beta, dst, n_img, cb, (size_t)voxels, dst_cbt, dst_cb_off, eps, elem_fmt == MMSEG_FMT_FP16);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cb >= 24 || tok < 4096) {   // deep stages: a warp per token
+    swin_layernorm_warp_kernel<<<(unsigned)((tok + 7) / 8), 256, 0, st>>>(
+        xs, add, gamma, beta, dst, n_img, cb, (size_t)voxels, dst_cbt, dst_cb_off, eps, elem_fmt == MMSEG_FMT_FP16);
+  } else {
+    swin_layernorm_kernel<<<(unsigned)((tok + 127) / 128), 128, 0, st>>>(
+        xs, add, gamma, beta, dst, n_img, cb, (size_t)voxels, dst_cbt, dst_cb_off, eps, elem_fmt == MMSEG_FMT_FP16);
+  }
   return check_launch("swin_layernorm_kernel");
 }
 
@@ -509,7 +577,7 @@ extern "C" int mmseg_swin_merge_ln(const float* xs, const float* gamma, const fl
   if ((Z | Y | X) & 1) return fail(MMSEG_ERR_UNSUPPORTED, "swin_merge_ln: odd extents (the zero-padded merge) are not built");
   if (elem_fmt != MMSEG_FMT_BF16 && elem_fmt != MMSEG_FMT_FP16) return fail(MMSEG_ERR_INVALID_ARG, "swin_merge_ln: elem_fmt");
   const size_t tok = (size_t)n_img * (Z / 2) * (Y / 2) * (X / 2);
-  swin_merge_ln_kernel<<<(unsigned)((tok + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  swin_merge_ln_kernel<<<(unsigned)((tok + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       xs, gamma, beta, dst, n_img, cb, Z, Y, X, eps, elem_fmt == MMSEG_FMT_FP16);
   return check_launch("swin_merge_ln_kernel");
 }

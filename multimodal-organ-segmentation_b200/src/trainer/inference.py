@@ -314,7 +314,9 @@ class SlidingWindowInferer:
                         slot["stream"].synchronize()
                         g = torch.cuda.CUDAGraph()
                         l0 = K.LAUNCHES[0]
-                        with torch.cuda.graph(g, stream=slot["stream"]):
+                        # thread_local: only this thread's calls are checked against the capture — a CUDA call from
+                        # another host thread (a DataLoader pin-memory thread, NVML samplers, ...) must not invalidate it
+                        with torch.cuda.graph(g, stream=slot["stream"], capture_error_mode="thread_local"):
                             self._forward_batch(st, slot, volume, n)
                         slot["launches"][gkey] = K.LAUNCHES[0] - l0
                         if len(slot["graphs"]) >= 8:      # bounded: volumes of many shapes do not pile up graphs

@@ -174,7 +174,7 @@ class Trainer:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             static_loss = self.train_step(static_x, static_y)
 
         params = [p for p in self.model.parameters() if p.requires_grad]
