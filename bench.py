@@ -104,7 +104,7 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------------ CPU legs
 REF_CROP = (192, 192, 144)     # exactly 18 windows (3 x 3 x 2): one step of the reference arm (>= 18)
-HEADLINE_DEFAULT = "fp16m"     # fastest mode that met all four north_star gates on B200 (see `parity` in the bench line)
+HEADLINE_DEFAULT = "fp16i"     # fastest mode that met all four north_star gates on B200 (see `parity` in the bench line)
 
 
 def plain_unet_state_dict(features=FEATURES, cin=2, cout=8):

@@ -16,6 +16,8 @@ fall into the axis-0 slab it owns, finalises that slab and the uint8 labels are 
 import math
 from typing import Callable, List, Optional, Sequence, Tuple
 
+import contextlib
+import gc
 import os
 
 import torch
@@ -27,6 +29,23 @@ Tensor = torch.Tensor
 
 
 # ------------------------------------------------------------------------------------------ window arithmetic (host)
+
+@contextlib.contextmanager
+def capture_guard():
+    """No cyclic garbage collection while a stream is capturing: collecting an unreachable inferer of an earlier call
+    there would destroy ITS CUDA graphs (cudaGraphExecDestroy / cudaFree of the graph pool), which CUDA forbids during a
+    capture and which invalidates it ("operation failed due to a previous error during capture").  torch.cuda.graph no
+    longer runs gc.collect() itself, so collect first, then keep the collector off for the duration of the capture."""
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was_enabled:
+            gc.enable()
+
+
 def _scan_interval(image_size, roi_size, overlap) -> List[int]:
     out = []
     for im, r in zip(image_size, roi_size):
@@ -316,7 +335,7 @@ class SlidingWindowInferer:
                         l0 = K.LAUNCHES[0]
                         # thread_local: only this thread's calls are checked against the capture — a CUDA call from
                         # another host thread (a DataLoader pin-memory thread, NVML samplers, ...) must not invalidate it
-                        with torch.cuda.graph(g, stream=slot["stream"], capture_error_mode="thread_local"):
+                        with capture_guard(), torch.cuda.graph(g, stream=slot["stream"], capture_error_mode="thread_local"):
                             self._forward_batch(st, slot, volume, n)
                         slot["launches"][gkey] = K.LAUNCHES[0] - l0
                         if len(slot["graphs"]) >= 8:      # bounded: volumes of many shapes do not pile up graphs

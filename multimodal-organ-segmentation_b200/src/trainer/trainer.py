@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from ..models.build import load_checkpoint, save_checkpoint
-from .inference import predict_volume, sliding_window_inference
+from .inference import capture_guard, predict_volume, sliding_window_inference
 from .losses import get_loss
 from .metrics import DiceMetric, get_metrics
 from ...parallel import GradBucketReducer
@@ -174,7 +174,7 @@ class Trainer:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+        with capture_guard(), torch.cuda.graph(graph, capture_error_mode="thread_local"):
             static_loss = self.train_step(static_x, static_y)
 
         params = [p for p in self.model.parameters() if p.requires_grad]
