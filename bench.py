@@ -765,8 +765,9 @@ def swin_measure(dev, steps=5, warmup=3, cpu=True):
     m = SwinUNETR(in_channels=2, out_channels=8, feature_size=48).eval()
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     m = m.to(dev)
-    res = {"metric": "SwinUNETR-48 forward patches/s (2-channel 96^3, fp16 operands / fp32 accumulate)",
-           "config": "BASELINE.json configs[3] (forward only: the backward of SwinUNETR is not built)", "peak_tflops": tf_peak,
+    res = {"metric": "SwinUNETR-48 forward patches/s (2-channel 96^3, fp16 operands / fp32 accumulate) + bf16 training step",
+           "config": "BASELINE.json configs[3] (SwinUNETR feature_size 48, early fusion, 96^3 CT+PET, forward / backward)",
+           "peak_tflops": tf_peak,
            "batches": []}
     g = torch.Generator(device="cpu").manual_seed(3)
     for B in (1, 4):
@@ -813,6 +814,44 @@ def swin_measure(dev, steps=5, warmup=3, cpu=True):
                                    "sample": f"one 96^3 forward through the oracle ({cpu_s:.1f} s)"}
             log(f"[swin] vs oracle: {res['parity_vs_oracle']}; CPU forward {cpu_s:.1f} s")
         del x, out
+    # training step (forward + DiceCE + backward + fused AdamW), B = 1 and 2: every op an autograd.Function over the kernels
+    try:
+        from mmseg_b200.optim import FusedAdamW
+        from mmseg_b200.src.trainer.losses import DiceCELoss
+        m.train()
+        crit = DiceCELoss()
+        opt = FusedAdamW(m.parameters(), lr=1e-4)
+        res["train"] = []
+        for B in (1, 2):
+            x = torch.randn((B, 2, 96, 96, 96), generator=g).to(dev)
+            y = torch.randint(0, 8, (B, 96, 96, 96), generator=g).to(dev)
+
+            def step():
+                loss = crit(m(x), y)
+                loss.backward()
+                opt.step()
+                opt.zero_grad()
+                return loss
+
+            for _ in range(warmup):
+                loss = step()
+            torch.cuda.synchronize()
+            l0 = K.LAUNCHES[0]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                loss = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            res["train"].append({"batch": B, "ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "loss": loss.item(),
+                                 "kernel_launches_per_step": (K.LAUNCHES[0] - l0) // steps,
+                                 "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30})
+            log(f"[swin] train B={B}: {ms:.1f} ms/step -> {B / (ms * 1e-3):.1f} samples/s, loss {loss.item():.4f}")
+            del x, y
+    except Exception as e:   # never allowed to break the line
+        torch.cuda.synchronize()
+        res["train"] = {"error": f"{type(e).__name__}: {e}"}
     del m
     torch.cuda.empty_cache()
     return res

@@ -468,6 +468,7 @@ typedef struct {
   int32_t qkv_cbt, out_cbt, out_cb_off;
   float scale;            /* head_dim^-0.5                                                                                 */
   int32_t elem_fmt;
+  float* lse;             /* optional [n_img][heads][windows][352] fp32: log2-domain log-sum-exp rows for the backward      */
 } mmseg_swin_attn_args;
 int mmseg_swin_window_attention(const mmseg_swin_attn_args* args, void* stream);
 /* UnetResBlock tail (MONAI dynunet_block.UnetResBlock, the block of every SwinUNETR encoder / decoder stage):
@@ -477,6 +478,36 @@ int mmseg_instnorm_residual_act(const void* a, int32_t a_is_f32, const float* a_
                                 const float* r_mean_rstd, int32_t r_cbt, int32_t r_cb_off, void* dst, int32_t dst_cbt,
                                 int32_t dst_cb_off, int32_t n_img, int32_t cb, int64_t voxels, float slope, int32_t elem_fmt,
                                 void* stream);
+
+/*
+ * SwinUNETR training: the backward ops autograd issues for loss.backward() (reference src/trainer/trainer.py:243) through
+ * monai.networks.nets.SwinUNETR (src/models/backbones/swin_unetr.py:80-117).  bf16 operands, fp32 stream gradients.
+ */
+/* LayerNorm forward that also saves (mean, rstd) per token: xs_out = xs_in (+ add16, blocked bf16); ln16 = LN(xs_out). */
+int mmseg_swin_ln_fwd_train(const float* xs_in, const void* add16, const float* gamma, const float* beta, float* xs_out,
+                            void* ln16, float* stats /* [tokens][2] */, int32_t n_img, int32_t cb, int64_t voxels, float eps,
+                            void* stream);
+/* native_layer_norm_backward (input gradient): dxs_out = (dxs_in | 0) + LN'(dy16); dxs16 = bf16 copy of dxs_out. */
+int mmseg_swin_ln_bwd(const float* xs, const float* stats, const void* dy16, const float* gamma, const float* dxs_in,
+                      float* dxs_out, void* dxs16, int32_t n_img, int32_t cb, int64_t voxels, void* stream);
+/* native_layer_norm_backward (weight / bias gradients): partial [n_chunks][C][2] = (sum dy*xhat, sum dy) per chunk. */
+int mmseg_swin_ln_param_grad(const float* xs, const float* stats, const void* dy16, float* partial, int32_t n_chunks,
+                             int32_t n_img, int32_t cb, int64_t voxels, void* stream);
+/* gelu_backward (MLPBlock, exact erf form) and the LeakyReLU mask of the UnetResBlock tail (out = dy * (y > 0 ? 1 : slope)). */
+int mmseg_gelu_bwd(const void* x16, const void* dy16, void* dx16, int64_t n_elems, void* stream);
+int mmseg_lrelu_mask_mul(const void* y16, const void* dy16, void* out16, int64_t n_elems, float slope, void* stream);
+/* PatchMerging gather (xs -> [8 slots x C] channels at half resolution, fp32 blocked) and its transpose (backward). */
+int mmseg_swin_merge_gather(const float* xs, float* cat, int32_t n_img, int32_t cb, int32_t Z, int32_t Y, int32_t X, void* stream);
+int mmseg_swin_merge_scatter(const float* dcat, float* dxs, int32_t n_img, int32_t cb, int32_t Z, int32_t Y, int32_t X,
+                             void* stream);
+/* convolution_backward (weight, bias) of the patch embedding: partial [n_chunks][F][8 Cin + 1]. */
+int mmseg_swin_patch_embed_wgrad(const float* x, const float* dxs, float* partial, int32_t n_chunks, int32_t n_img, int32_t Cin,
+                                 int32_t F, int32_t Z, int32_t Y, int32_t X, void* stream);
+/* Backward of mmseg_swin_window_attention (args as in the forward, `out` = the forward output, `lse` = its saved rows):
+ * dqkv (blocked bf16 like qkv), dtable partial [n_img][windows][heads][table rows], dbias partial [n_img][windows][heads][32]
+ * (dk | dv of the zero-padded tokens, i.e. their share of the qkv-bias gradient). */
+int mmseg_swin_window_attention_bwd(const mmseg_swin_attn_args* args, const void* dout, int32_t dout_cbt, int32_t dout_cb_off,
+                                    const float* lse, void* dqkv, float* dtable, float* dbias, void* stream);
 
 #ifdef __cplusplus
 }

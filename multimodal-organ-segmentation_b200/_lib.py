@@ -90,7 +90,7 @@ class SwinAttnArgs(C.Structure):
         ("window", C.c_int32 * 3), ("shift", C.c_int32 * 3),
         ("heads", C.c_int32), ("head_dim", C.c_int32),
         ("qkv_cbt", C.c_int32), ("out_cbt", C.c_int32), ("out_cb_off", C.c_int32),
-        ("scale", C.c_float), ("elem_fmt", C.c_int32),
+        ("scale", C.c_float), ("elem_fmt", C.c_int32), ("lse", C.c_void_p),
     ]
 
 
@@ -152,6 +152,15 @@ SYMBOLS = {
     "mmseg_swin_window_attention": (C.c_int, [C.POINTER(SwinAttnArgs), _vp]),
     "mmseg_instnorm_residual_act": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i64,
                                               _f32, _i32, _vp]),
+    "mmseg_swin_ln_fwd_train": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _f32, _vp]),
+    "mmseg_swin_ln_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp]),
+    "mmseg_swin_ln_param_grad": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp]),
+    "mmseg_gelu_bwd": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "mmseg_lrelu_mask_mul": (C.c_int, [_vp, _vp, _vp, _i64, _f32, _vp]),
+    "mmseg_swin_merge_gather": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "mmseg_swin_merge_scatter": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "mmseg_swin_patch_embed_wgrad": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "mmseg_swin_window_attention_bwd": (C.c_int, [C.POINTER(SwinAttnArgs), _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mmseg_maxpool3d_2": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
 }
 

@@ -248,6 +248,7 @@ struct SwinAttnK {
   void* out;
   const float* table;      // [table_len][heads]
   const float* qkv_bias;   // [3C] or NULL
+  float* lse;              // optional [img][head][window][352]: log2-domain log-sum-exp rows (saved for the backward)
   int n_img, D, H, W;
   int ws0, ws1, ws2;       // actual window (min(configured, extent))
   int cw1, cw2;            // configured window extents along h, w (relative-position radix)
@@ -466,6 +467,11 @@ __global__ void __launch_bounds__(256) swin_window_attention_kernel(const SwinAt
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float i0 = 1.f / l0, i1 = 1.f / l1;
+    if (k.lse && t == 0) {
+      float* lr = k.lse + (((size_t)img * k.heads + head) * gridDim.x + win) * kAttnMaxTok;
+      lr[q0 + g] = m0 + log2f(l0);
+      lr[q0 + g + 8] = m1 + log2f(l1);
+    }
     const int p0 = (q0 + g) < n_tok ? sPos[q0 + g] : -1, p1 = (q0 + g + 8) < n_tok ? sPos[q0 + g + 8] : -1;
 #pragma unroll
     for (int nd = 0; nd < 2; ++nd) {
@@ -588,7 +594,7 @@ extern "C" int mmseg_swin_window_attention(const mmseg_swin_attn_args* a, void* 
     return fail(MMSEG_ERR_INVALID_ARG, "swin_window_attention: bad extents");
   if (a->head_dim != 16) return fail(MMSEG_ERR_UNSUPPORTED, "swin_window_attention: head_dim %d (built for 16)", a->head_dim);
   SwinAttnK k;
-  k.qkv = a->qkv; k.out = a->out; k.table = a->table; k.qkv_bias = a->qkv_bias;
+  k.qkv = a->qkv; k.out = a->out; k.table = a->table; k.qkv_bias = a->qkv_bias; k.lse = a->lse;
   k.n_img = a->n_img; k.D = a->D; k.H = a->H; k.W = a->W;
   const int ext[3] = {a->D, a->H, a->W};
   int ws[3], ss[3], pp[3];

@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from ....swin_engine import SWIN_MODES, SwinUNETREngine
+from ....swin_train import swin_unetr_train_forward
 
 
 class _ConvOnly(nn.Module):
@@ -187,7 +188,7 @@ class SwinUNETR(nn.Module):
             unsupported.append("use_v2=True")
         if unsupported:
             raise NotImplementedError("SwinUNETR options without an sm_100a kernel: " + ", ".join(unsupported))
-        # dropout / drop-path: identity in eval; the inference path ignores the rates (training is not built)
+        # dropout / drop-path: identity in eval; training needs rates of 0 (the reference's defaults)
         self.drop_rates = (drop_rate, attn_drop_rate, dropout_path_rate)
         self.img_size = img_size
         self.in_channels, self.out_channels, self.feature_size = in_channels, out_channels, feature_size
@@ -214,8 +215,13 @@ class SwinUNETR(nn.Module):
                 ) -> Union[torch.Tensor, Tuple[torch.Tensor, List[torch.Tensor]]]:
         if not x.is_cuda:
             raise RuntimeError("mmseg_b200 modules run on CUDA (sm_100a) tensors only; there is no CPU fallback")
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("SwinUNETR is forward-only in the sm_100a path: wrap the call in torch.no_grad()")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training: every op is an autograd.Function over the bf16 kernels (swin_train.py)
+            if return_features:
+                raise NotImplementedError("return_features is an inference-path option")
+            if self.training and any(r > 0 for r in self.drop_rates):
+                raise NotImplementedError("SwinUNETR dropout / drop-path in training mode is not built (rates must be 0)")
+            return swin_unetr_train_forward(self.model, x)
         out = self.engine().forward(x)
         if return_features:
             n, _, Z, Y, X = x.shape

@@ -153,7 +153,10 @@ class Trainer:
         finally:
             train_engine.ACTIVE_REDUCER = None
         if armed:
-            self.reducer.finish()
+            if any(self.reducer._ready):
+                self.reducer.finish()
+            else:   # a model whose backward is plain autograd over kernel ops (SwinUNETR): .grad is populated, exchange it now
+                self.reducer.reduce_gradients()
         if step_optimizer:
             self.optimizer.step()
             self.optimizer.zero_grad()      # set_to_none: the next backward hands over fresh gradient tensors

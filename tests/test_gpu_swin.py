@@ -63,3 +63,27 @@ def test_swin_unetr_vs_oracle(size, mode):
 
 def test_swin_unetr_sliding_window():
     _c().swin_sliding_window_case()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(with_add=False), dict(channels=384, dims=(3, 3, 3), n=1)])
+def test_layernorm_backward(kw):
+    _c().ln_backward_case(**kw)
+
+
+def test_gelu_merge_patch_embed_backward():
+    _c().gelu_merge_patch_backward_case()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(shift=False), dict(dims=(6, 6, 6), heads=3, shift=True),
+                                dict(dims=(14, 14, 14), heads=1, shift=True, n=2)])
+def test_window_attention_backward(kw):
+    _c().window_attention_backward_case(**kw)
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 48), (48, 48)])
+def test_unet_res_block_backward(cin, cout):
+    _c().res_block_backward_case(cin, cout)
+
+
+def test_swin_unetr_training_step_vs_fp64_autograd():
+    _c().swin_train_step_case()
