@@ -844,10 +844,19 @@ def swin_measure(dev, steps=5, warmup=3, cpu=True):
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / steps
+            K.PROFILE = []
+            step()
+            torch.cuda.synchronize()
+            prof, K.PROFILE = K.PROFILE, None
+            kms = {}
+            for name, info, a, b in prof:
+                kms[name] = kms.get(name, 0.0) + a.elapsed_time(b)
             res["train"].append({"batch": B, "ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "loss": loss.item(),
+                                 "kernel_ms": {k: round(v, 3) for k, v in sorted(kms.items(), key=lambda kv: -kv[1])[:12]},
                                  "kernel_launches_per_step": (K.LAUNCHES[0] - l0) // steps,
                                  "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30})
-            log(f"[swin] train B={B}: {ms:.1f} ms/step -> {B / (ms * 1e-3):.1f} samples/s, loss {loss.item():.4f}")
+            log(f"[swin] train B={B}: {ms:.1f} ms/step -> {B / (ms * 1e-3):.1f} samples/s, loss {loss.item():.4f}; top: "
+                + ", ".join(f"{k[6:]} {v:.2f}" for k, v in sorted(kms.items(), key=lambda kv: -kv[1])[:8]))
             del x, y
     except Exception as e:   # never allowed to break the line
         torch.cuda.synchronize()

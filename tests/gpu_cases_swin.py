@@ -445,3 +445,44 @@ def swin_train_step_case(size=64, n=1):
     # Every backward kernel is checked tightly on its own above; here: the loss, the bound and the gradient norms.
     norm_ratio = [(p.grad.norm().item() / sd64[name].grad.norm().item()) for name, p in m.named_parameters()]
     assert rl < 1e-3 and med < 0.3 and worst < 0.45 and 0.8 < min(norm_ratio) and max(norm_ratio) < 1.25
+
+
+def swin_trainer_case(tmp_dir):
+    """The reference-facing Trainer with model.name = swin_unetr (main.py --mode train / inference): train() through the
+    kernel autograd path, validation, predict_array() through the sliding-window engine."""
+    import numpy as np
+    from mmseg_b200.src.models.build import build_model
+    from mmseg_b200.src.trainer import Trainer
+    torch.manual_seed(0)
+    cfg = {"model": {"name": "swin_unetr", "in_channels": 2, "out_channels": 4,
+                     "backbone": {"feature_size": 48, "img_size": [32, 32, 32]}, "fusion": {"type": "early"},
+                     "head": {"dropout": 0.0}},
+           "data": {"modalities": ["CT", "PET"]},
+           "hardware": {"device": "cuda", "mixed_precision": True},
+           "training": {"epochs": 2, "accumulation_steps": 1,
+                        "optimizer": {"name": "adamw", "lr": 1e-3, "weight_decay": 1e-5},
+                        "scheduler": {"name": "cosine"}, "loss": {"name": "dice_ce"},
+                        "checkpoint": {"save_last": True, "save_best": False}},
+           "inference": {"batch_size": 2, "sliding_window": {"roi_size": [64, 64, 64], "overlap": 0.25}},
+           "experiment": {"output_dir": str(tmp_dir), "name": "swin"}}
+    g = torch.Generator().manual_seed(5)
+
+    def batches(n):
+        out = []
+        for _ in range(n):
+            lab = torch.randint(0, 4, (1, 8, 8, 8), generator=g).repeat_interleave(8, 1).repeat_interleave(8, 2).repeat_interleave(8, 3)
+            img = torch.randn(1, 2, 64, 64, 64, generator=g) * 0.3 + lab[:, None].float()
+            out.append({"image": img, "label": lab})
+        return out
+    tr = Trainer(cfg, build_model(cfg), train_loader=batches(6), val_loader=batches(1))
+    hist = tr.train()
+    assert all(np.isfinite(v) for v in hist["train_loss"] + hist["val_loss"])
+    assert hist["train_loss"][1] < hist["train_loss"][0], hist
+    vol = batches(1)[0]["image"][0].numpy().astype(np.float32)[:, :, :, :64]
+    pred = tr.predict_array(vol)
+    assert pred.shape == (64, 64, 64) and pred.dtype == np.uint8
+    with torch.no_grad():
+        direct = tr.model(torch.from_numpy(vol)[None].cuda()).argmax(1)[0].cpu().numpy()
+    agree = float((pred == direct).mean())
+    print(f"[swin trainer] losses {hist['train_loss']} val dice {hist['val_dice']}; predict_array vs direct forward labels {agree * 100:.3f}%")
+    assert agree > 0.995

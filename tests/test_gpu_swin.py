@@ -87,3 +87,7 @@ def test_unet_res_block_backward(cin, cout):
 
 def test_swin_unetr_training_step_vs_fp64_autograd():
     _c().swin_train_step_case()
+
+
+def test_swin_unetr_trainer_train_validate_predict(tmp_path):
+    _c().swin_trainer_case(tmp_path)
