@@ -123,6 +123,115 @@ swin_ln_bwd_kernel(const float* __restrict__ xs, const float* __restrict__ stats
   }
 }
 
+// Warp-per-token variants for the deep stages (C >= 192, few tokens): lane l owns channel blocks l, l + 32, ...
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+swin_ln_fwd_train_warp_kernel(const float* __restrict__ xs_in, const void* __restrict__ add16, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float* __restrict__ xs_out, void* __restrict__ ln,
+                              float* __restrict__ stats, int n_img, int cb, size_t nvox, float eps) {
+  const size_t tok = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (tok >= (size_t)n_img * nvox) return;
+  const int img = (int)(tok / nvox);
+  const size_t v = tok - (size_t)img * nvox;
+  const size_t bs = nvox * 8;
+  const size_t base = (size_t)img * cb * bs + v * 8;
+  float s = 0.f;
+  for (int b = lane; b < cb; b += 32) {
+    float a[8];
+    ld8(xs_in + base + b * bs, a);
+    if (add16) {
+      float y[8];
+      load8_act(add16, base + b * bs, y, false);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] += y[i];
+    }
+    if (xs_out != xs_in || add16) st8(xs_out + base + b * bs, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+  }
+  s = warp_sum(s);
+  const float inv_c = 1.f / (float)(cb * 8);
+  const float mean = s * inv_c;
+  float q = 0.f;
+  for (int b = lane; b < cb; b += 32) {
+    float a[8];
+    ld8(xs_out + base + b * bs, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = a[i] - mean; q = fmaf(d, d, q); }
+  }
+  q = warp_sum(q);
+  const float rstd = rsqrtf(q * inv_c + eps);
+  if (stats && lane == 0) { stats[tok * 2] = mean; stats[tok * 2 + 1] = rstd; }
+  if (!ln) return;
+  for (int b = lane; b < cb; b += 32) {
+    float a[8];
+    ld8(xs_out + base + b * bs, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float y = (a[i] - mean) * rstd;
+      if (gamma) y = fmaf(y, gamma[b * 8 + i], beta ? beta[b * 8 + i] : 0.f);
+      a[i] = y;
+    }
+    store8_act(ln, base + b * bs, 0, a, false);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+swin_ln_bwd_warp_kernel(const float* __restrict__ xs, const float* __restrict__ stats, const void* __restrict__ dy16,
+                        const float* __restrict__ gamma, const float* __restrict__ dxs_in, float* __restrict__ dxs_out,
+                        void* __restrict__ dxs16, int n_img, int cb, size_t nvox) {
+  const size_t tok = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (tok >= (size_t)n_img * nvox) return;
+  const int img = (int)(tok / nvox);
+  const size_t v = tok - (size_t)img * nvox;
+  const size_t bs = nvox * 8;
+  const size_t base = (size_t)img * cb * bs + v * 8;
+  float mean = 0.f, rstd = 0.f, m1 = 0.f, m2 = 0.f;
+  if (dy16) {
+    mean = stats[tok * 2];
+    rstd = stats[tok * 2 + 1];
+    for (int b = lane; b < cb; b += 32) {
+      float a[8], g[8];
+      ld8(xs + base + b * bs, a);
+      load8_act(dy16, base + b * bs, g, false);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float gp = gamma ? g[i] * gamma[b * 8 + i] : g[i];
+        m1 += gp;
+        m2 = fmaf(gp, (a[i] - mean) * rstd, m2);
+      }
+    }
+    const float inv_c = 1.f / (float)(cb * 8);
+    m1 = warp_sum(m1) * inv_c;
+    m2 = warp_sum(m2) * inv_c;
+  }
+  for (int b = lane; b < cb; b += 32) {
+    float d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = 0.f;
+    if (dxs_in) ld8(dxs_in + base + b * bs, d);
+    if (dy16) {
+      float a[8], g[8];
+      ld8(xs + base + b * bs, a);
+      load8_act(dy16, base + b * bs, g, false);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float gp = gamma ? g[i] * gamma[b * 8 + i] : g[i];
+        d[i] += rstd * (gp - m1 - (a[i] - mean) * rstd * m2);
+      }
+    }
+    if (dxs_out) st8(dxs_out + base + b * bs, d);
+    if (dxs16) store8_act(dxs16, base + b * bs, 0, d, false);
+  }
+}
+
 // dgamma[c] = sum_tokens dy * xhat, dbeta[c] = sum_tokens dy: grid (chunks, cb); partial[chunk][C][2], summed by the caller
 // in chunk order (deterministic).
 __global__ void __launch_bounds__(256)
@@ -534,8 +643,12 @@ extern "C" int mmseg_swin_ln_fwd_train(const float* xs_in, const void* add16, co
   if (!xs_in || !xs_out || n_img < 1 || cb < 1 || voxels < 1 || (beta && !gamma))
     return fail(MMSEG_ERR_INVALID_ARG, "swin_ln_fwd_train: bad arguments");
   const size_t tok = (size_t)n_img * voxels;
-  swin_ln_fwd_train_kernel<<<(unsigned)((tok + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      xs_in, add16, gamma, beta, xs_out, ln16, stats, n_img, cb, (size_t)voxels, eps);
+  if (cb >= 24 || tok < 4096)
+    swin_ln_fwd_train_warp_kernel<<<(unsigned)((tok + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        xs_in, add16, gamma, beta, xs_out, ln16, stats, n_img, cb, (size_t)voxels, eps);
+  else
+    swin_ln_fwd_train_kernel<<<(unsigned)((tok + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        xs_in, add16, gamma, beta, xs_out, ln16, stats, n_img, cb, (size_t)voxels, eps);
   return check_launch("swin_ln_fwd_train_kernel");
 }
 
@@ -545,8 +658,12 @@ extern "C" int mmseg_swin_ln_bwd(const float* xs, const float* stats, const void
   if ((!dxs_out && !dxs16) || n_img < 1 || cb < 1 || voxels < 1 || (dy16 && (!xs || !stats)) || (!dy16 && !dxs_in))
     return fail(MMSEG_ERR_INVALID_ARG, "swin_ln_bwd: bad arguments");
   const size_t tok = (size_t)n_img * voxels;
-  swin_ln_bwd_kernel<<<(unsigned)((tok + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      xs, stats, dy16, gamma, dxs_in, dxs_out, dxs16, n_img, cb, (size_t)voxels);
+  if (cb >= 24 || tok < 4096)
+    swin_ln_bwd_warp_kernel<<<(unsigned)((tok + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        xs, stats, dy16, gamma, dxs_in, dxs_out, dxs16, n_img, cb, (size_t)voxels);
+  else
+    swin_ln_bwd_kernel<<<(unsigned)((tok + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        xs, stats, dy16, gamma, dxs_in, dxs_out, dxs16, n_img, cb, (size_t)voxels);
   return check_launch("swin_ln_bwd_kernel");
 }
 

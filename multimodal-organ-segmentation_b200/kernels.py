@@ -663,6 +663,22 @@ def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt
     n_cig, n_cot = len(groups), cout_pad // ntc
     assert n_cig <= _lib.MAX_WGRAD_GROUPS
     TX, TY, TZ = _plan_wgrad_tile(x.X, x.Y, x.Z, ksize, cig // 8, ntc // 8)
+    if ksize == 3 and os.environ.get("MMSEG_WGRAD_TZ", "auto") != "8":
+        # z extent of a tile: every tile issues the MMAs (and loads) of TZ + 2 input planes for TZ output planes, so a
+        # longer z run cuts the halo overhead (TZ = 8: 25 %, 32: 6 %) as long as the persistent CTAs stay balanced
+        forced = os.environ.get("MMSEG_WGRAD_TZ", "auto")
+        ctas = max(1, 148 // (n_cig * n_cot))
+        txy = -(-x.X // TX) * -(-x.Y // TY) * x.n_img
+        best = None
+        for tz in ([int(forced)] if forced != "auto" else (8, 12, 16, 24, 32, 48, 64, 96, 128)):
+            if tz > max(x.Z, 8):
+                continue
+            tz = min(tz, x.Z)
+            nt = txy * -(-x.Z // tz)
+            planes = -(-nt // min(nt, ctas)) * (tz + 2)          # input planes swept by the busiest CTA
+            if best is None or planes < best[0]:
+                best = (planes, tz)
+        TZ = best[1]
     n_tiles = -(-x.X // TX) * -(-x.Y // TY) * -(-x.Z // TZ) * x.n_img
     n_part = max(1, min(n_tiles, 148 // (n_cig * n_cot)))
     ncols = ksize * ksize * ntc
