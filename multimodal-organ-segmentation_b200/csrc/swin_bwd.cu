@@ -3,7 +3,8 @@
 // token LayerNorm forward-with-statistics / backward / parameter gradients, GELU backward, the LeakyReLU mask of the
 // UnetResBlock tail, patch-merging gather / scatter, patch-embedding weight gradient and the window-attention backward.
 // bf16 operands, fp32 residual-stream gradients.  Every buffer is written by exactly one thread (no global float atomics);
-// the relative-position-bias gradient is accumulated per CTA in shared memory and reduced across CTAs in a fixed order.
+// the relative-position-bias gradient is accumulated per CTA in shared memory in fixed point (exact integer adds) and reduced
+// across CTAs in a fixed order.
 #include <cuda_bf16.h>
 #include <stdint.h>
 
@@ -426,15 +427,20 @@ swin_patch_embed_wgrad_kernel(const float* __restrict__ x, const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ window attention backward
-// One CTA = one (window, head, image), like the forward.  Probabilities are recomputed from q, k, the bias table and the
-// saved log-sum-exp rows; delta_i = dO_i . O_i.  Pass A (one query per thread): dq_i and the bias-table gradient
-// (shared-memory accumulation, one partial table per CTA); pass B (one key per thread): dk_j, dv_j.  Padded tokens
-// contribute their dk / dv to the qkv-bias gradient (their k / v ARE the bias).
+// One CTA = one (window, head, image), like the forward; head_dim = 16, so every score-shaped product is ONE
+// mma.sync.m16n8k16 per 16 x 8 tile.  Probabilities are recomputed from q, k, the bias table and the saved log-sum-exp rows;
+// delta_i = dO_i . O_i.
+//   pass A (a warp owns 16 queries, walks the keys 16 at a time):  S = Q K^T and dP = dO V^T on the tensor cores, dS = P (dP -
+//           delta) in the accumulator fragments -> bias-table gradient (shared-memory accumulation, one partial table per
+//           CTA) and, re-used as the A fragments of a second MMA, dQ += dS K;
+//   pass B (a warp owns 16 keys, walks the queries): S^T = K Q^T and dP^T = V dO^T, then dK += dS^T Q and dV += P^T dO.
+// Padded tokens (MONAI pads AFTER norm1: their k / v ARE the qkv bias) contribute their dk / dv to the qkv-bias gradient;
+// padded queries are cropped from the output, so their rows carry no gradient.
 struct SwinAttnBwdK {
   const void* qkv;
   const void* out;        // forward output O (bf16)
   const void* dout;       // dO (bf16)
-  const float* lse;       // [img][head][win][352] natural-log-sum-exp in the log2 domain
+  const float* lse;       // [img][head][win][352] log-sum-exp rows in the log2 domain
   const float* table;
   const float* qkv_bias;
   void* dqkv;             // bf16 blocked, same shape as qkv
@@ -448,22 +454,52 @@ struct SwinAttnBwdK {
 };
 
 constexpr int kBwdTok = 352;
+constexpr int kBwdRS = 24;     // halfs per row of the row-major operand copies (conflict-free fragment loads)
+constexpr int kBwdTS = 360;    // halfs per row of the transposed copies
+constexpr int kBwdThreads = 384;
+constexpr size_t kBwdSmem = (size_t)4 * kBwdTok * kBwdRS * 2 + (size_t)3 * 16 * kBwdTS * 2 + 2 * 2200 * 4 + 32 + 2 * kBwdTok * 4 +
+                            kBwdTok * 4 + kBwdTok * 2 + kBwdTok + 32 * 4 + 64;
 
-__global__ void __launch_bounds__(384) swin_window_attention_bwd_kernel(const SwinAttnBwdK k) {
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void load_afrag(const uint16_t* base, int row0, int g, int t, uint32_t (&a)[4]) {
+  a[0] = *reinterpret_cast<const uint32_t*>(base + (row0 + g) * kBwdRS + 2 * t);
+  a[1] = *reinterpret_cast<const uint32_t*>(base + (row0 + g + 8) * kBwdRS + 2 * t);
+  a[2] = *reinterpret_cast<const uint32_t*>(base + (row0 + g) * kBwdRS + 2 * t + 8);
+  a[3] = *reinterpret_cast<const uint32_t*>(base + (row0 + g + 8) * kBwdRS + 2 * t + 8);
+}
+
+__global__ void __launch_bounds__(kBwdThreads) swin_window_attention_bwd_kernel(const SwinAttnBwdK k) {
   extern __shared__ __align__(16) uint8_t smem[];
-  float* sQ = reinterpret_cast<float*>(smem);            // [352][16]
-  float* sK = sQ + kBwdTok * 16;
-  float* sV = sK + kBwdTok * 16;
-  float* sdO = sV + kBwdTok * 16;
-  float* sTab = sdO + kBwdTok * 16;                      // bias (log2 domain), 2200
-  float* sdTab = sTab + 2200;                            // gradient accumulation, 2200
-  float* sLse = sdTab + 2200;                            // [352]
-  float* sDelta = sLse + kBwdTok;                        // [352]
-  int* sPos = reinterpret_cast<int*>(sDelta + kBwdTok);  // [352]
+  uint16_t* sQ = reinterpret_cast<uint16_t*>(smem);          // [352][24] bf16, row = token
+  uint16_t* sK = sQ + kBwdTok * kBwdRS;
+  uint16_t* sV = sK + kBwdTok * kBwdRS;
+  uint16_t* sdO = sV + kBwdTok * kBwdRS;
+  uint16_t* sKt = sdO + kBwdTok * kBwdRS;                    // [16][360] bf16, row = dim
+  uint16_t* sQt = sKt + 16 * kBwdTS;
+  uint16_t* sdOt = sQt + 16 * kBwdTS;
+  float* sTab = reinterpret_cast<float*>(sdOt + 16 * kBwdTS);  // bias (log2 domain), 2200
+  // gradient accumulation in int32 fixed point: 32-bit integer shared-memory atomics are native (fp32 / 64-bit ones are CAS
+  // loops) and exact, so the bias-table gradient is bitwise reproducible whatever the order the warps arrive in.  The scale
+  // comes from a per-CTA bound: |dS_ij| <= |dO_i| |v_j| + |delta_i|, at most 343 addends per table entry.
+  int* sdTab = reinterpret_cast<int*>(sTab + 2200);            // 2200 x int32
+  unsigned* sMax = reinterpret_cast<unsigned*>(sdTab + 2200);  // max |dO_i|^2, max |v_j|^2, max |delta_i| (float bits), scale
+  float* sLse = reinterpret_cast<float*>(sdTab + 2200 + 8);    // [352]
+  float* sDelta = sLse + kBwdTok;                              // [352]
+  int* sPos = reinterpret_cast<int*>(sDelta + kBwdTok);        // [352]
   int16_t* sBase = reinterpret_cast<int16_t*>(sPos + kBwdTok);
   uint8_t* sReg = reinterpret_cast<uint8_t*>(sBase + kBwdTok);
+  float* sPad = reinterpret_cast<float*>(smem + kBwdSmem - 32 * 4 - 16);   // dk | dv of the padded tokens
 
   const int n_tok = k.ws0 * k.ws1 * k.ws2;
+  const int np = (n_tok + 15) & ~15;
   const int nW1 = k.Hp / k.ws1, nW2 = k.Wp / k.ws2;
   const int win = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
   const int w2 = win % nW2, w1 = (win / nW2) % nW1, w0 = win / (nW2 * nW1);
@@ -474,8 +510,10 @@ __global__ void __launch_bounds__(384) swin_window_attention_bwd_kernel(const Sw
 
   for (int i = tid; i < k.table_len; i += blockDim.x) {
     sTab[i] = k.table[(size_t)i * k.heads + head] * 1.4426950408889634f;
-    sdTab[i] = 0.f;
+    sdTab[i] = 0;
   }
+  if (tid < 32) sPad[tid] = 0.f;
+  if (tid < 8) sMax[tid] = 0u;
   for (int i = tid; i < kBwdTok; i += blockDim.x) {
     int pos = -2, base = 0, reg = 0;
     if (i < n_tok) {
@@ -502,124 +540,229 @@ __global__ void __launch_bounds__(384) swin_window_attention_bwd_kernel(const Sw
   }
   __syncthreads();
   const uint16_t* qkv = reinterpret_cast<const uint16_t*>(k.qkv);
-  // q, k, v, dO rows as fp32 in shared memory; delta = dO . O
-  for (int e = tid; e < n_tok * 8; e += blockDim.x) {
+  // q, k, v, dO rows (bf16) and the transposed copies the second-stage MMAs read as B operands
+  for (int e = tid; e < np * 8; e += blockDim.x) {
     const int i = e >> 3, part = e & 7;            // part: 0,1 q | 2,3 k | 4,5 v | 6,7 dO
     const int which = part >> 1, half = part & 1;
     const int pos = sPos[i];
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    uint4 u = make_uint4(0, 0, 0, 0);
     if (which < 3) {
       const int ch0 = which * C + head * 16 + half * 8;
       if (pos >= 0) {
-        load8_act(qkv, (((size_t)img * k.qkv_cbt + (ch0 >> 3)) * nvox + pos) * 8, v, false);
-      } else if (k.qkv_bias) {
+        u = *reinterpret_cast<const uint4*>(qkv + (((size_t)img * k.qkv_cbt + (ch0 >> 3)) * nvox + pos) * 8);
+      } else if (pos == -1 && k.qkv_bias) {
+        float b[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(k.qkv_bias[ch0 + j]));
+        for (int j = 0; j < 8; ++j) b[j] = k.qkv_bias[ch0 + j];
+        u = cvt8_from_f32(b, false);
       }
     } else if (pos >= 0) {
-      load8_act(k.dout, (((size_t)img * k.dout_cbt + k.dout_cb_off + head * 2 + half) * nvox + pos) * 8, v, false);
+      u = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(k.dout) +
+                                          (((size_t)img * k.dout_cbt + k.dout_cb_off + head * 2 + half) * nvox + pos) * 8);
     }
-    float* dstp = (which == 0 ? sQ : which == 1 ? sK : which == 2 ? sV : sdO) + i * 16 + half * 8;
+    uint16_t* rowp = (which == 0 ? sQ : which == 1 ? sK : which == 2 ? sV : sdO) + i * kBwdRS + half * 8;
+    *reinterpret_cast<uint4*>(rowp) = u;
+    if (which != 2) {
+      uint16_t* tp = (which == 0 ? sQt : which == 1 ? sKt : sdOt);
+      const uint16_t* h = reinterpret_cast<const uint16_t*>(&u);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dstp[j] = v[j];
+      for (int j = 0; j < 8; ++j) tp[(half * 8 + j) * kBwdTS + i] = h[j];
+    }
   }
   const size_t row0 = (((size_t)img * k.heads + head) * gridDim.x + win) * kBwdTok;
-  for (int i = tid; i < n_tok; i += blockDim.x) sLse[i] = k.lse[row0 + i];
+  for (int i = tid; i < np; i += blockDim.x) sLse[i] = i < n_tok ? k.lse[row0 + i] : 0.f;
   __syncthreads();
-  for (int i = tid; i < n_tok; i += blockDim.x) {
+  for (int i = tid; i < np; i += blockDim.x) {
     const int pos = sPos[i];
     float d = 0.f;
     if (pos >= 0) {
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        float o[8];
+        float o[8], g8[8];
         load8_act(k.out, (((size_t)img * k.out_cbt + k.out_cb_off + head * 2 + half) * nvox + pos) * 8, o, false);
+        cvt8_to_f32(*reinterpret_cast<const uint4*>(sdO + i * kBwdRS + half * 8), g8, false);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d = fmaf(o[j], sdO[i * 16 + half * 8 + j], d);
+        for (int j = 0; j < 8; ++j) d = fmaf(o[j], g8[j], d);
       }
     }
     sDelta[i] = d;
+    float g16[16], v16[16];
+    cvt8_to_f32(*reinterpret_cast<const uint4*>(sdO + i * kBwdRS), g16, false);
+    cvt8_to_f32(*reinterpret_cast<const uint4*>(sdO + i * kBwdRS + 8), g16 + 8, false);
+    cvt8_to_f32(*reinterpret_cast<const uint4*>(sV + i * kBwdRS), v16, false);
+    cvt8_to_f32(*reinterpret_cast<const uint4*>(sV + i * kBwdRS + 8), v16 + 8, false);
+    float ng = 0.f, nv = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { ng = fmaf(g16[j], g16[j], ng); nv = fmaf(v16[j], v16[j], nv); }
+    atomicMax(&sMax[0], __float_as_uint(ng));      // non-negative floats order like their bit patterns
+    atomicMax(&sMax[1], __float_as_uint(nv));
+    atomicMax(&sMax[2], __float_as_uint(fabsf(d)));
   }
   __syncthreads();
+  if (tid == 0) {
+    const float bound = sqrtf(__uint_as_float(sMax[0])) * sqrtf(__uint_as_float(sMax[1])) + __uint_as_float(sMax[2]);
+    reinterpret_cast<float*>(sMax)[3] = bound > 0.f ? 1073741824.f / (343.f * bound) : 0.f;   // 2^30 / (addends * bound)
+  }
+  __syncthreads();
+  const float fix = reinterpret_cast<const float*>(sMax)[3];
 
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int n_warps = blockDim.x >> 5;
+  const int n_tiles = np >> 4;
   uint16_t* dqkv = reinterpret_cast<uint16_t*>(k.dqkv);
-  // ---- pass A: one query row per thread -> dq, bias-table gradient
-  for (int i = tid; i < n_tok; i += blockDim.x) {
-    const int pos = sPos[i];
-    if (pos < 0) continue;                         // a padded query's output is cropped: no gradient flows through its row
-    float q[16], dO[16], dq[16];
+
+  // ---- pass A: 16 queries per warp -> dq, bias-table gradient
+  for (int qt = warp; qt < n_tiles; qt += n_warps) {
+    const int q0 = qt * 16;
+    uint32_t qa[4], ga[4];
+    load_afrag(sQ, q0, g, t, qa);
+    load_afrag(sdO, q0, g, t, ga);
+    const int i0 = q0 + g, i1 = q0 + g + 8;
+    const bool v0 = sPos[i0] >= 0, v1 = sPos[i1] >= 0;
+    const float lse0 = sLse[i0], lse1 = sLse[i1], de0 = sDelta[i0], de1 = sDelta[i1];
+    const int bq0 = sBase[i0] + k.centre, bq1 = sBase[i1] + k.centre;
+    const int rq0 = sReg[i0], rq1 = sReg[i1];
+    float dq[2][4];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { q[j] = sQ[i * 16 + j]; dO[j] = sdO[i * 16 + j]; dq[j] = 0.f; }
-    const float lse = sLse[i], delta = sDelta[i];
-    const int bq = sBase[i] + k.centre, rq = sReg[i];
-    for (int j = 0; j < n_tok; ++j) {
-      float s = 0.f, dp = 0.f;
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int c = 0; c < 16; ++c) { s = fmaf(q[c], sK[j * 16 + c], s); dp = fmaf(dO[c], sV[j * 16 + c], dp); }
-      const int ti = bq - sBase[j];
-      float sl = fmaf(s, k.scale_log2e, sTab[ti]);
-      if (shifted && sReg[j] != rq) sl -= 144.26950408889634f;
-      const float p = exp2f(sl - lse);
-      const float ds = p * (dp - delta);
-      atomicAdd(&sdTab[ti], ds);
+      for (int b = 0; b < 4; ++b) dq[a][b] = 0.f;
+    for (int key0 = 0; key0 < np; key0 += 16) {
+      float ds[2][4];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) dq[c] = fmaf(ds, sK[j * 16 + c], dq[c]);
-    }
+      for (int nt = 0; nt < 2; ++nt) {
+        const int kr = key0 + nt * 8 + g;           // B-fragment row of this lane
+        float sc[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_bf16(sc, qa, *reinterpret_cast<const uint32_t*>(sK + kr * kBwdRS + 2 * t),
+                 *reinterpret_cast<const uint32_t*>(sK + kr * kBwdRS + 2 * t + 8));
+        mma_bf16(dp, ga, *reinterpret_cast<const uint32_t*>(sV + kr * kBwdRS + 2 * t),
+                 *reinterpret_cast<const uint32_t*>(sV + kr * kBwdRS + 2 * t + 8));
 #pragma unroll
-    for (int c = 0; c < 16; ++c) dq[c] *= k.scale;
-#pragma unroll
-    for (int half = 0; half < 2; ++half)
-      store8_act(dqkv, (((size_t)img * k.qkv_cbt + ((head * 16 + half * 8) >> 3)) * nvox + pos) * 8, 0, dq + half * 8, false);
-  }
-  // ---- pass B: one key per thread -> dk, dv
-  float padk[16], padv[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) { padk[c] = 0.f; padv[c] = 0.f; }
-  for (int j = tid; j < n_tok; j += blockDim.x) {
-    float kk[16], vv[16], dk[16], dv[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) { kk[c] = sK[j * 16 + c]; vv[c] = sV[j * 16 + c]; dk[c] = 0.f; dv[c] = 0.f; }
-    const int bk = sBase[j], rk = sReg[j];
-    for (int i = 0; i < n_tok; ++i) {
-      if (sPos[i] < 0) continue;                   // padded queries carry no gradient
-      float s = 0.f, dp = 0.f;
-#pragma unroll
-      for (int c = 0; c < 16; ++c) { s = fmaf(sQ[i * 16 + c], kk[c], s); dp = fmaf(sdO[i * 16 + c], vv[c], dp); }
-      float sl = fmaf(s, k.scale_log2e, sTab[sBase[i] + k.centre - bk]);
-      if (shifted && sReg[i] != rk) sl -= 144.26950408889634f;
-      const float p = exp2f(sl - sLse[i]);
-      const float ds = p * (dp - sDelta[i]);
-#pragma unroll
-      for (int c = 0; c < 16; ++c) { dk[c] = fmaf(ds, sQ[i * 16 + c], dk[c]); dv[c] = fmaf(p, sdO[i * 16 + c], dv[c]); }
-    }
-#pragma unroll
-    for (int c = 0; c < 16; ++c) dk[c] *= k.scale;
-    const int pos = sPos[j];
-    if (pos >= 0) {
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        store8_act(dqkv, (((size_t)img * k.qkv_cbt + ((C + head * 16 + half * 8) >> 3)) * nvox + pos) * 8, 0, dk + half * 8, false);
-        store8_act(dqkv, (((size_t)img * k.qkv_cbt + ((2 * C + head * 16 + half * 8) >> 3)) * nvox + pos) * 8, 0, dv + half * 8, false);
+        for (int j = 0; j < 2; ++j) {
+          const int key = key0 + nt * 8 + 2 * t + j;
+          float d0 = 0.f, d1 = 0.f;
+          if (key < n_tok) {
+            const int bk = sBase[key], rk = sReg[key];
+            if (v0) {
+              float sl = fmaf(sc[j], k.scale_log2e, sTab[bq0 - bk]);
+              if (shifted && rk != rq0) sl -= 144.26950408889634f;
+              d0 = exp2f(sl - lse0) * (dp[j] - de0);
+              atomicAdd(&sdTab[bq0 - bk], __float2int_rn(d0 * fix));
+            }
+            if (v1) {
+              float sl = fmaf(sc[2 + j], k.scale_log2e, sTab[bq1 - bk]);
+              if (shifted && rk != rq1) sl -= 144.26950408889634f;
+              d1 = exp2f(sl - lse1) * (dp[2 + j] - de1);
+              atomicAdd(&sdTab[bq1 - bk], __float2int_rn(d1 * fix));
+            }
+          }
+          ds[nt][j] = d0;
+          ds[nt][2 + j] = d1;
+        }
       }
-    } else {
+      uint32_t pa[4] = {pack_bf16(ds[0][0], ds[0][1]), pack_bf16(ds[0][2], ds[0][3]), pack_bf16(ds[1][0], ds[1][1]),
+                        pack_bf16(ds[1][2], ds[1][3])};
 #pragma unroll
-      for (int c = 0; c < 16; ++c) { padk[c] += dk[c]; padv[c] += dv[c]; }
+      for (int nd = 0; nd < 2; ++nd)
+        mma_bf16(dq[nd], pa, *reinterpret_cast<const uint32_t*>(sKt + (nd * 8 + g) * kBwdTS + key0 + 2 * t),
+                 *reinterpret_cast<const uint32_t*>(sKt + (nd * 8 + g) * kBwdTS + key0 + 2 * t + 8));
+    }
+    const int p0 = sPos[i0], p1 = sPos[i1];
+#pragma unroll
+    for (int nd = 0; nd < 2; ++nd) {
+      const size_t cbase = ((size_t)img * k.qkv_cbt + head * 2 + nd) * nvox;
+      if (p0 >= 0) *reinterpret_cast<uint32_t*>(dqkv + (cbase + p0) * 8 + 2 * t) = pack_bf16(dq[nd][0] * k.scale, dq[nd][1] * k.scale);
+      if (p1 >= 0) *reinterpret_cast<uint32_t*>(dqkv + (cbase + p1) * 8 + 2 * t) = pack_bf16(dq[nd][2] * k.scale, dq[nd][3] * k.scale);
     }
   }
-  // padded tokens -> qkv-bias gradient: fixed-order reduction over the CTA's threads (shared memory reused after a sync)
-  __syncthreads();
-  float* red = sQ;                                 // [384][32] floats = 48 KB >= needs 352*16*... reuse sQ..sV region
-  for (int c = 0; c < 16; ++c) { red[tid * 32 + c] = padk[c]; red[tid * 32 + 16 + c] = padv[c]; }
+
+  // ---- pass B: 16 keys per warp -> dk, dv
+  for (int kt = warp; kt < n_tiles; kt += n_warps) {
+    const int k0 = kt * 16;
+    uint32_t ka[4], va[4];
+    load_afrag(sK, k0, g, t, ka);
+    load_afrag(sV, k0, g, t, va);
+    const int j0 = k0 + g, j1 = k0 + g + 8;
+    const bool kv0 = j0 < n_tok, kv1 = j1 < n_tok;
+    const int bk0 = sBase[j0], bk1 = sBase[j1], rk0 = sReg[j0], rk1 = sReg[j1];
+    float dk[2][4], dv[2][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) { dk[a][b] = 0.f; dv[a][b] = 0.f; }
+    for (int q0 = 0; q0 < np; q0 += 16) {
+      float pT[2][4], dsT[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int qr = q0 + nt * 8 + g;
+        float sc[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_bf16(sc, ka, *reinterpret_cast<const uint32_t*>(sQ + qr * kBwdRS + 2 * t),
+                 *reinterpret_cast<const uint32_t*>(sQ + qr * kBwdRS + 2 * t + 8));
+        mma_bf16(dp, va, *reinterpret_cast<const uint32_t*>(sdO + qr * kBwdRS + 2 * t),
+                 *reinterpret_cast<const uint32_t*>(sdO + qr * kBwdRS + 2 * t + 8));
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int qi = q0 + nt * 8 + 2 * t + j;    // column = query
+          float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+          if (sPos[qi] >= 0) {
+            const int bq = sBase[qi] + k.centre, rq = sReg[qi];
+            const float lse = sLse[qi], de = sDelta[qi];
+            if (kv0) {
+              float sl = fmaf(sc[j], k.scale_log2e, sTab[bq - bk0]);
+              if (shifted && rq != rk0) sl -= 144.26950408889634f;
+              p0 = exp2f(sl - lse);
+              d0 = p0 * (dp[j] - de);
+            }
+            if (kv1) {
+              float sl = fmaf(sc[2 + j], k.scale_log2e, sTab[bq - bk1]);
+              if (shifted && rq != rk1) sl -= 144.26950408889634f;
+              p1 = exp2f(sl - lse);
+              d1 = p1 * (dp[2 + j] - de);
+            }
+          }
+          pT[nt][j] = p0; pT[nt][2 + j] = p1;
+          dsT[nt][j] = d0; dsT[nt][2 + j] = d1;
+        }
+      }
+      uint32_t pa[4] = {pack_bf16(pT[0][0], pT[0][1]), pack_bf16(pT[0][2], pT[0][3]), pack_bf16(pT[1][0], pT[1][1]),
+                        pack_bf16(pT[1][2], pT[1][3])};
+      uint32_t da[4] = {pack_bf16(dsT[0][0], dsT[0][1]), pack_bf16(dsT[0][2], dsT[0][3]), pack_bf16(dsT[1][0], dsT[1][1]),
+                        pack_bf16(dsT[1][2], dsT[1][3])};
+#pragma unroll
+      for (int nd = 0; nd < 2; ++nd) {
+        mma_bf16(dk[nd], da, *reinterpret_cast<const uint32_t*>(sQt + (nd * 8 + g) * kBwdTS + q0 + 2 * t),
+                 *reinterpret_cast<const uint32_t*>(sQt + (nd * 8 + g) * kBwdTS + q0 + 2 * t + 8));
+        mma_bf16(dv[nd], pa, *reinterpret_cast<const uint32_t*>(sdOt + (nd * 8 + g) * kBwdTS + q0 + 2 * t),
+                 *reinterpret_cast<const uint32_t*>(sdOt + (nd * 8 + g) * kBwdTS + q0 + 2 * t + 8));
+      }
+    }
+    const int p0 = kv0 ? sPos[j0] : -2, p1 = kv1 ? sPos[j1] : -2;
+#pragma unroll
+    for (int nd = 0; nd < 2; ++nd) {
+      const size_t kb = ((size_t)img * k.qkv_cbt + ((C + head * 16) >> 3) + nd) * nvox;
+      const size_t vb = ((size_t)img * k.qkv_cbt + ((2 * C + head * 16) >> 3) + nd) * nvox;
+      if (p0 >= 0) {
+        *reinterpret_cast<uint32_t*>(dqkv + (kb + p0) * 8 + 2 * t) = pack_bf16(dk[nd][0] * k.scale, dk[nd][1] * k.scale);
+        *reinterpret_cast<uint32_t*>(dqkv + (vb + p0) * 8 + 2 * t) = pack_bf16(dv[nd][0], dv[nd][1]);
+      } else if (p0 == -1) {
+        atomicAdd(&sPad[nd * 8 + 2 * t], dk[nd][0] * k.scale); atomicAdd(&sPad[nd * 8 + 2 * t + 1], dk[nd][1] * k.scale);
+        atomicAdd(&sPad[16 + nd * 8 + 2 * t], dv[nd][0]);      atomicAdd(&sPad[16 + nd * 8 + 2 * t + 1], dv[nd][1]);
+      }
+      if (p1 >= 0) {
+        *reinterpret_cast<uint32_t*>(dqkv + (kb + p1) * 8 + 2 * t) = pack_bf16(dk[nd][2] * k.scale, dk[nd][3] * k.scale);
+        *reinterpret_cast<uint32_t*>(dqkv + (vb + p1) * 8 + 2 * t) = pack_bf16(dv[nd][2], dv[nd][3]);
+      } else if (p1 == -1) {
+        atomicAdd(&sPad[nd * 8 + 2 * t], dk[nd][2] * k.scale); atomicAdd(&sPad[nd * 8 + 2 * t + 1], dk[nd][3] * k.scale);
+        atomicAdd(&sPad[16 + nd * 8 + 2 * t], dv[nd][2]);      atomicAdd(&sPad[16 + nd * 8 + 2 * t + 1], dv[nd][3]);
+      }
+    }
+  }
   __syncthreads();
   const size_t cta = ((size_t)img * gridDim.x + win) * k.heads + head;
-  if (tid < 32) {
-    float s = 0.f;
-    for (int t = 0; t < (int)blockDim.x; ++t) s += red[t * 32 + tid];
-    k.dbias[cta * 32 + tid] = s;
-  }
-  for (int i = tid; i < k.table_len; i += blockDim.x) k.dtable[cta * k.table_len + i] = sdTab[i];
+  if (tid < 32) k.dbias[cta * 32 + tid] = sPad[tid];
+  const float unfix = fix > 0.f ? 1.f / fix : 0.f;
+  for (int i = tid; i < k.table_len; i += blockDim.x) k.dtable[cta * k.table_len + i] = (float)sdTab[i] * unfix;
 }
 
 static int sm_count_b() {
@@ -763,13 +906,13 @@ extern "C" int mmseg_swin_window_attention_bwd(const mmseg_swin_attn_args* a, co
   k.centre = ((a->window[0] - 1) * (2 * a->window[1] - 1) + (a->window[1] - 1)) * (2 * a->window[2] - 1) + (a->window[2] - 1);
   k.scale = a->scale;
   k.scale_log2e = a->scale * 1.4426950408889634f;
-  const size_t smem = (size_t)kBwdTok * 16 * 4 * 4 + 2200 * 4 * 2 + kBwdTok * 4 * 2 + kBwdTok * 4 + kBwdTok * 2 + kBwdTok + 64;
+  const size_t smem = kBwdSmem;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(swin_window_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
   dim3 grid((unsigned)((pp[0] / ws[0]) * (pp[1] / ws[1]) * (pp[2] / ws[2])), (unsigned)a->heads, (unsigned)a->n_img);
-  swin_window_attention_bwd_kernel<<<grid, 384, smem, reinterpret_cast<cudaStream_t>(stream)>>>(k);
+  swin_window_attention_bwd_kernel<<<grid, kBwdThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(k);
   return check_launch("swin_window_attention_bwd_kernel");
 }
