@@ -269,10 +269,10 @@ class UNet3DEngine:
             return b
         f = self.module.features
         L = len(f)
-        if any(d % (1 << (L - 1)) for d in (Z, Y, X)):
-            raise NotImplementedError(
-                f"spatial size {(Z, Y, X)} is not divisible by {1 << (L - 1)}: the trilinear resize branch of "
-                "UpBlock3D (reference unet.py:108-109) is not implemented in the sm_100a path")
+        if min(Z, Y, X) >> (L - 1) < 1:
+            raise ValueError(f"spatial size {(Z, Y, X)} is too small for {L} resolution levels")
+        # sizes that are not divisible by 2^(L-1): MaxPool3d(2) floors, the ConvTranspose output (2 * floor) then differs from
+        # the skip and UpBlock3D resizes it trilinearly (reference unet.py:108-109) — see forward_blocked
         sp = self.nm.buffer          # per-buffer storage mode (hi-only vs hi + lo; mixed modes differ per buffer)
         b = {"in": Blocked(n, (self.module.in_channels + 15) // 16 * 16, Z, Y, X, sp("in"), device)}
         if self.in_packed:
@@ -289,6 +289,9 @@ class UNet3DEngine:
                 b[f"bott"] = Blocked(n, f[l], z, y, x, sp("bott"), device)
             if l > 0:
                 b[f"pool{l}"] = Blocked(n, f[l - 1], z, y, x, sp(f"pool{l}"), device)    # MaxPool3d(2) of level l-1
+            if l < L - 1 and ((Z >> l) & 1 or (Y >> l) & 1 or (X >> l) & 1):
+                # odd level: the up-sampled tensor (2 * floor) is produced here and resized into cat{l}
+                b[f"up{l}"] = Blocked(n, f[l], 2 * (z >> 1), 2 * (y >> 1), 2 * (x >> 1), sp(f"cat{l}"), device)
         self._bufs[key] = b
         return b
 
@@ -328,6 +331,10 @@ class UNet3DEngine:
                 name2 = "init_conv.conv2"
             if last:
                 r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[name2], b["bott"], norm=N[name2])
+            elif f"up{l}" in b:     # odd extents: MaxPool3d(2) floors — its own kernel instead of the fused 2x2x2 cells
+                r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[name2], b[f"cat{l}"], dst_c0=f[l], norm=N[name2])
+                K.maxpool3d_2(b[f"cat{l}"], b[f"pool{l + 1}"], f[l], src_c0=f[l])
+                r.launches += 1
             else:
                 r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[name2], b[f"cat{l}"], dst_c0=f[l],
                                 pooled=b[f"pool{l + 1}"], norm=N[name2])
@@ -335,7 +342,15 @@ class UNet3DEngine:
         cur = b["bott"]
         for j in range(L - 1):
             l = L - 2 - j
-            r.conv_transpose(cur, [(0, f[l + 1])], P[f"decoders.{j}.up"], b[f"cat{l}"], dst_c0=0)
+            if f"up{l}" in b:
+                # x.shape != skip.shape: F.interpolate(x, size=skip.shape[2:], mode="trilinear", align_corners=True)
+                # (reference unet.py:108-109) between the ConvTranspose and the concat
+                r.conv_transpose(cur, [(0, f[l + 1])], P[f"decoders.{j}.up"], b[f"up{l}"], dst_c0=0)
+                c = b[f"cat{l}"]
+                K.pack_ncdhw(K.trilinear_resize(b[f"up{l}"].to_ncdhw(), (c.Z, c.Y, c.X)), c, 0)
+                r.launches += 3
+            else:
+                r.conv_transpose(cur, [(0, f[l + 1])], P[f"decoders.{j}.up"], b[f"cat{l}"], dst_c0=0)
             r.conv_norm_act(b[f"cat{l}"], [(0, f[l]), (f[l], f[l])], P[f"decoders.{j}.conv1"], b[f"mid{l}"],
                             norm=N[f"decoders.{j}.conv1"])
             r.conv_norm_act(b[f"mid{l}"], [(0, f[l])], P[f"decoders.{j}.conv2"], b[f"dec{l}"],

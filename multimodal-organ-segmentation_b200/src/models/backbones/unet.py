@@ -174,9 +174,7 @@ class UpBlock3D(nn.Module):
             x = x.contiguous().float()
             skip = skip.contiguous().float()
             n, c, Z, Y, X = x.shape
-            if tuple(skip.shape[2:]) != (2 * Z, 2 * Y, 2 * X):
-                raise NotImplementedError("trilinear resize to the skip shape (reference unet.py:108-109) is not "
-                                          "implemented; use spatial sizes divisible by 2**levels")
+            resize = tuple(skip.shape[2:]) != (2 * Z, 2 * Y, 2 * X)     # reference unet.py:108-109
             half = c // 2
             inst = self.conv.norm_type == "instance"   # only InstanceNorm cancels the conv bias
             ver = (self.up.weight._version, self.conv.conv1.weight._version, self.conv.conv2.weight._version,
@@ -193,12 +191,18 @@ class UpBlock3D(nn.Module):
             r = self._runner
             src = Blocked(n, c, Z, Y, X, split, x.device)
             K.pack_ncdhw(x, src)
-            cat = Blocked(n, half + skip.shape[1], 2 * Z, 2 * Y, 2 * X, split, x.device)
+            SZ, SY, SX = (int(v) for v in skip.shape[2:])
+            cat = Blocked(n, half + skip.shape[1], SZ, SY, SX, split, x.device)
             K.pack_ncdhw(skip, cat, c0=half)
-            r.conv_transpose(src, [(0, c)], self._packed[1], cat, 0)
+            if resize:   # ConvTranspose at 2x, then F.interpolate(..., mode="trilinear", align_corners=True) to the skip's size
+                up = Blocked(n, half, 2 * Z, 2 * Y, 2 * X, split, x.device)
+                r.conv_transpose(src, [(0, c)], self._packed[1], up, 0)
+                K.pack_ncdhw(K.trilinear_resize(up.to_ncdhw(), (SZ, SY, SX)), cat, 0)
+            else:
+                r.conv_transpose(src, [(0, c)], self._packed[1], cat, 0)
             co = self.conv.out_channels
-            mid = Blocked(n, co, 2 * Z, 2 * Y, 2 * X, split, x.device)
-            out = Blocked(n, co, 2 * Z, 2 * Y, 2 * X, split, x.device)
+            mid = Blocked(n, co, SZ, SY, SX, split, x.device)
+            out = Blocked(n, co, SZ, SY, SX, split, x.device)
             r.conv_norm_act(cat, [(0, half), (half, skip.shape[1])], self._packed[2], mid, slope=self.conv.slope,
                             norm=self.conv.norm1)
             r.conv_norm_act(mid, [(0, co)], self._packed[3], out, slope=self.conv.slope, norm=self.conv.norm2)

@@ -1410,3 +1410,34 @@ def bidirectional_attention_grad_case(C=32, heads=4, shape=(4, 6, 6), n_img=2, s
     print(f"[BidirectionalCrossAttention grads C={C}] out={errs['out']:.1e} df1={errs['df1']:.1e} df2={errs['df2']:.1e} "
           f"worst parameter {max(v for k, v in errs.items() if '.' in k):.1e}", flush=True)
     assert errs["out"] < 4e-2 and worst < 1e-1, errs
+
+
+def unet_odd_size_case(shape=(25, 30, 21), features=(16, 32, 64), mode="parity", n_img=2):
+    """Spatial sizes that are not divisible by 2^(levels-1): MaxPool3d floors and UpBlock3D resizes the up-sampled tensor
+    trilinearly (align_corners=True) to the skip's shape (reference unet.py:108-109) — engine path vs the oracle, plus the
+    stand-alone UpBlock3D module against torch on the same weights."""
+    from mmseg_b200.src.models.backbones.unet import UNet3D, UpBlock3D
+    from oracle.models import unet3d_forward, up_block3d
+    torch.manual_seed(4)
+    m = UNet3D(in_channels=2, out_channels=8, features=list(features)).eval()
+    sd = {"backbone." + k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.randn(n_img, 2, *shape)
+    ref = unet3d_forward(sd, x)
+    m = m.to(DEV).set_numeric_mode(mode)
+    with torch.no_grad():
+        got = m(x.to(DEV)).cpu()
+    max_abs, rel_l2, agree = _metrics(got, ref)
+    print(f"[unet odd {shape} mode={mode}] max_abs={max_abs:.3e} rel_l2={rel_l2:.3e} label_agree={agree * 100:.4f}%", flush=True)
+    tol = mode_bounds(mode)
+    assert got.shape == ref.shape and max_abs <= tol[0] and rel_l2 <= tol[1] and agree >= tol[2], (max_abs, rel_l2, agree)
+    up = UpBlock3D(32, 16).eval()
+    usd = {"u." + k: v.clone() for k, v in up.state_dict().items()}
+    xx, skip = torch.randn(1, 32, 6, 7, 5), torch.randn(1, 16, 13, 15, 11)
+    want = up_block3d(usd, "u", xx, skip)
+    up = up.to(DEV)
+    up.numeric_mode = mode
+    with torch.no_grad():
+        got_u = up(xx.to(DEV), skip.to(DEV)).cpu()
+    e = ((got_u - want).norm() / want.norm()).item()
+    print(f"[UpBlock3D resize branch] rel_l2 {e:.2e}", flush=True)
+    assert got_u.shape == want.shape and e < (1e-3 if mode in ("parity", "fp16x3") else 3e-2)

@@ -149,6 +149,11 @@ def test_sliding_window_graphs_follow_weight_updates():
     _c().swi_weight_update_case()
 
 
+@pytest.mark.parametrize("mode", ["parity", "fp16m", "bf16"])
+def test_unet_odd_sizes_trilinear_resize_branch(mode):
+    _c().unet_odd_size_case(mode=mode)
+
+
 def test_pack_unpack_roundtrip():
     _c().pack_roundtrip_case()
 
