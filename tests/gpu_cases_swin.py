@@ -171,7 +171,8 @@ def swin_unetr_case(size=64, n=1, mode="fp16", feature_size=48, check_hidden=Tru
             elif "norm" in name and name.endswith("bias"):
                 p.normal_(0, 0.2)
     sd = {k: v.clone() for k, v in m.state_dict().items()}
-    x = torch.randn(n, 2, size, size, size)
+    shape = (size, size, size) if isinstance(size, int) else tuple(size)
+    x = torch.randn(n, 2, *shape)
     ref, hs = O.swin_unetr_forward(sd, x, return_hidden=True)
     m = m.cuda().set_numeric_mode(mode)
     with torch.no_grad():
@@ -406,8 +407,9 @@ def swin_train_step_case(size=64, n=1):
             if "relative_position_bias_table" in name:
                 p.normal_(0, 0.3)
     sd64 = {k: v.detach().double().clone().requires_grad_(v.is_floating_point()) for k, v in m.state_dict().items()}
-    x = torch.randn(n, 2, size, size, size)
-    y = torch.randint(0, 8, (n, size, size, size))
+    shape = (size, size, size) if isinstance(size, int) else tuple(size)
+    x = torch.randn(n, 2, *shape)
+    y = torch.randint(0, 8, (n, *shape))
     # oracle in fp64 with autograd (the oracle detaches its parameters: bypass that here)
     keep = O._p
     O._p = lambda sd, key, dtype: sd[key]

@@ -56,7 +56,7 @@ def test_residual_instnorm_act():
     _c().resnorm_case(channels=96, dims=(3, 3, 3), n=1, mode="bf16")
 
 
-@pytest.mark.parametrize("size,mode", [(64, "fp16"), (64, "bf16"), (96, "fp16")])
+@pytest.mark.parametrize("size,mode", [(64, "fp16"), (64, "bf16"), (96, "fp16"), ((64, 96, 128), "fp16")])
 def test_swin_unetr_vs_oracle(size, mode):
     _c().swin_unetr_case(size=size, mode=mode)
 
@@ -85,8 +85,9 @@ def test_unet_res_block_backward(cin, cout):
     _c().res_block_backward_case(cin, cout)
 
 
-def test_swin_unetr_training_step_vs_fp64_autograd():
-    _c().swin_train_step_case()
+@pytest.mark.parametrize("size,n", [(64, 1), ((64, 32, 96), 2)])
+def test_swin_unetr_training_step_vs_fp64_autograd(size, n):
+    _c().swin_train_step_case(size=size, n=n)
 
 
 def test_swin_unetr_trainer_train_validate_predict(tmp_path):
