@@ -211,6 +211,10 @@ typedef struct {
   int32_t gA_cbt, gA_cb_off, gP_cbt, gP_cb_off, dx_cbt, dx_cb_off;
   int32_t n_chunks;
   float gA_scale, slope;
+  const float* m12;        /* optional [n_img][cb*8][2] (apply only): dx = rstd * (g' - m12[0] - y^ * m12[1]) with these terms instead
+                              of the per-(image, channel) means of `partial` — how GroupNorm / BatchNorm / affine norms reuse the
+                              kernel: the caller folds gamma / beta into mean_rstd and combines the sums over the norm's
+                              reduction set (train_engine.py) */
 } mmseg_norm_bwd_args;
 int mmseg_instnorm_act_bwd_reduce(const mmseg_norm_bwd_args* args, void* stream);
 int mmseg_instnorm_act_bwd_apply(const mmseg_norm_bwd_args* args, void* stream);

@@ -66,7 +66,7 @@ class NormBwdArgs(C.Structure):
         ("n_img", C.c_int32), ("cb", C.c_int32), ("Z", C.c_int32), ("Y", C.c_int32), ("X", C.c_int32),
         ("gA_cbt", C.c_int32), ("gA_cb_off", C.c_int32), ("gP_cbt", C.c_int32), ("gP_cb_off", C.c_int32),
         ("dx_cbt", C.c_int32), ("dx_cb_off", C.c_int32), ("n_chunks", C.c_int32),
-        ("gA_scale", C.c_float), ("slope", C.c_float),
+        ("gA_scale", C.c_float), ("slope", C.c_float), ("m12", C.c_void_p),
     ]
 
 

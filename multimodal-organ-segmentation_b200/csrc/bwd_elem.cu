@@ -21,6 +21,7 @@ struct NormBwdK {
   __nv_bfloat16* dx;
   const float* chan_scale;
   const float* chan_bias;
+  const float* m12;   // optional [n_img][C][2]: the two subtraction terms, given instead of being re-reduced from `partial`
   int n_img, cb, Z, Y, X;
   int gA_cbt, gA_cb_off, gP_cbt, gP_cb_off, dx_cbt, dx_cb_off;
   int n_chunks;
@@ -210,9 +211,14 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(const NormBwdK k
   const int img = blk / k.cb, c = blk - img * k.cb;
   __shared__ float m12[16];
   if (threadIdx.x < 16) {
-    double s = 0.0;
-    for (int j = 0; j < k.n_chunks; ++j) s += (double)k.partial[((size_t)blk * k.n_chunks + j) * 16 + threadIdx.x];
-    m12[threadIdx.x] = (float)(s / ((double)k.Z * k.Y * k.X));
+    if (k.m12) {   // affine / group / batch norms: the caller combined the sums over the norm's reduction set (train_engine.py)
+      const int i = threadIdx.x & 7, which = threadIdx.x >> 3;
+      m12[threadIdx.x] = k.m12[((size_t)img * k.cb * 8 + c * 8 + i) * 2 + which];
+    } else {
+      double s = 0.0;
+      for (int j = 0; j < k.n_chunks; ++j) s += (double)k.partial[((size_t)blk * k.n_chunks + j) * 16 + threadIdx.x];
+      m12[threadIdx.x] = (float)(s / ((double)k.Z * k.Y * k.X));
+    }
   }
   __syncthreads();
   float mean[8], rstd[8], m1[8], m2[8];
@@ -311,6 +317,7 @@ static int fill_norm_bwd(const mmseg_norm_bwd_args* a, NormBwdK* k) {
   k->gA_cbt = a->gA_cbt; k->gA_cb_off = a->gA_cb_off; k->gP_cbt = a->gP_cbt; k->gP_cb_off = a->gP_cb_off;
   k->dx_cbt = a->dx_cbt; k->dx_cb_off = a->dx_cb_off; k->n_chunks = a->n_chunks;
   k->gA_scale = a->gA_scale; k->slope = a->slope; k->chan_scale = a->chan_scale; k->chan_bias = a->chan_bias;
+  k->m12 = a->m12;
   return MMSEG_OK;
 }
 

@@ -57,6 +57,13 @@ def norm_kind(norm) -> str:
     raise NotImplementedError(f"norm module {type(norm).__name__} has no sm_100a kernel")
 
 
+def norm_kind_train(norm) -> str:
+    """norm_kind for the TRAINING path: BatchNorm3d in train mode is allowed there (batch statistics)."""
+    if isinstance(norm, torch.nn.BatchNorm3d):
+        return "batch"
+    return norm_kind(norm)
+
+
 class ConvRunner:
     """conv (+ InstanceNorm statistics) -> finalize -> normalise/activate(/pool), on blocked buffers."""
 

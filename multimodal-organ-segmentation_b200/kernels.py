@@ -717,7 +717,8 @@ def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt
 def instnorm_act_bwd(raw: Tensor, mean_rstd: Tensor, n_img: int, channels: int, Z: int, Y: int, X: int,
                      gA: Optional[Blocked], gA_c0: int, gA_scale: float, gP: Optional[Blocked], gP_c0: int,
                      dx: Tensor, slope: float = 0.0, chan_scale: Optional[Tensor] = None,
-                     chan_bias: Optional[Tensor] = None, dx_cbt: Optional[int] = None, dx_cb_off: int = 0) -> None:
+                     chan_bias: Optional[Tensor] = None, dx_cbt: Optional[int] = None, dx_cb_off: int = 0,
+                     between=None) -> None:
     """dx (blocked bf16 [n_img, channels/8, Z, Y, X, 8]) = gradient of the raw conv output; see mmseg_norm_bwd_args.
     dx_cbt / dx_cb_off: dx is a channel-block range of a wider blocked buffer (dx_cbt blocks per image)."""
     a = _lib.NormBwdArgs()
@@ -739,6 +740,14 @@ def instnorm_act_bwd(raw: Tensor, mean_rstd: Tensor, n_img: int, channels: int, 
     if PROFILE is not None:
         _INFO[0] = {"bytes": n_img * channels * nvox * 4.0, "layer": f"bwd-reduce-c{channels}-{Z}-pool{int(gP is not None)}"}
     _call("mmseg_instnorm_act_bwd_reduce", C.byref(a), _stream())
+    m12 = None
+    if between is not None:
+        # affine / group / batch norms: the caller turns the per-(image, channel) sums [n_img, C, 2] = (sum g', sum g' y^) into
+        # the apply kernel's two subtraction terms (and takes its parameter gradients from the same sums)
+        sums = partial.view(n_img, channels // 8, n_chunks, 2, 8).sum(2).permute(0, 1, 3, 2).reshape(n_img, channels, 2)
+        m12 = between(sums).contiguous()
+        assert m12.dtype == torch.float32 and tuple(m12.shape) == (n_img, channels, 2)
+        a.m12 = m12.data_ptr()
     if PROFILE is not None:
         _INFO[0] = {"bytes": n_img * channels * nvox * 6.0, "layer": f"bwd-apply-c{channels}-{Z}-pool{int(gP is not None)}"}
     _call("mmseg_instnorm_act_bwd_apply", C.byref(a), _stream())

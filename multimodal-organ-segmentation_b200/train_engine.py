@@ -92,7 +92,15 @@ class TrainEngine:
     # ---------------------------------------------------------------- forward ops
     def conv_norm_act(self, name: str, src: Blocked, segs, conv, dst: Blocked, dst_c0: int = 0,
                       pooled: Optional[Blocked] = None, slope: float = 0.0, gspec=None, need_dgrad: bool = True,
-                      chan_scale: Optional[Tensor] = None, gate_ref=None):
+                      chan_scale: Optional[Tensor] = None, gate_ref=None, norm=None):
+        """norm: the block's norm module (reference unet.py:29-41).  None / InstanceNorm3d(affine=False): the fused path
+        below; GroupNorm / BatchNorm3d / Identity: `_conv_generic_norm_act`."""
+        from .engine import norm_kind_train
+        nk = norm_kind_train(norm)
+        if nk != "instance":
+            if chan_scale is not None or gate_ref is not None or gspec is not None:
+                raise NotImplementedError(f"training with norm={nk!r} together with Dropout3d / DualEncoder fusion is not built")
+            return self._conv_generic_norm_act(name, src, segs, conv, dst, dst_c0, pooled, slope, need_dgrad, norm, nk)
         n, Z, Y, X = src.n_img, src.Z, src.Y, src.X
         cout = conv.weight.shape[0]
         seg_ch = tuple(s[1] for s in segs)
@@ -119,6 +127,103 @@ class TrainEngine:
         self.tape.append(dict(kind="cna", name=name, src=src, segs=list(segs), conv=conv, dst=dst, dst_c0=dst_c0,
                               pooled=pooled, slope=slope, raw=raw, mr=mr, gspec=gspec, need_dgrad=need_dgrad,
                               chan_scale=chan_scale, gate_ref=gate_ref))
+
+
+    # ---------------------------------------------------------------- GroupNorm / BatchNorm3d / Identity blocks
+    def _conv_generic_norm_act(self, name, src, segs, conv, dst, dst_c0, pooled, slope, need_dgrad, norm, nk):
+        """ConvBlock3D half with model.backbone.norm = group | batch | anything else (Identity) — reference unet.py:29-41,
+        53-60.  The conv keeps its bias (only InstanceNorm cancels it); the statistics come from the conv epilogue's
+        partials and are combined over the norm's reduction set on [n, C] tensors; the apply kernel gets gamma folded into
+        rstd and beta as its shift.  BatchNorm3d in train mode uses batch statistics and updates its running buffers."""
+        n, Z, Y, X = src.n_img, src.Z, src.Y, src.X
+        nvox = Z * Y * X
+        cout = conv.weight.shape[0]
+        seg_ch = tuple(s_[1] for s_ in segs)
+        pw = self._packed(conv.weight, ("fwdb", seg_ch), lambda: K.PackPlan.forward(conv.weight, conv.bias, False, seg_ch))
+        a_cb = K.a_chunk_table(src, [s_[0] for s_ in segs], list(seg_ch), False)
+        tile = K.plan_conv_norm((X, Y, Z), n, pw, False, a_cb)
+        raw = self.saved(name + ".raw", (n, cout // 8, Z, Y, X, 8), torch.bfloat16)
+        stats = self.saved("ws.stats", (n * tile.tiles_per_img * cout * 2,), torch.float32)
+        K.conv3d(src, pw, a_cb, raw, _lib.OUT_BLOCKED_BF16, stats=stats, dst_cbt=cout // 8, tile=tile)
+        dev = raw.device
+        ones, zeros = torch.ones(cout, device=dev), torch.zeros(cout, device=dev)
+        gamma = norm.weight.detach().float() if getattr(norm, "weight", None) is not None else ones
+        beta = norm.bias.detach().float() if getattr(norm, "bias", None) is not None else zeros
+        stat_grad = True          # do the statistics depend on this batch (so that gradient flows through them)?
+        if nk == "none":
+            mean, rstd, stat_grad = zeros.expand(n, cout), ones.expand(n, cout), False
+        else:
+            st = stats[:n * tile.tiles_per_img * cout * 2].view(n, tile.tiles_per_img, cout, 2).double().sum(1)   # [n, C, 2]
+            if nk == "group":
+                G = norm.num_groups
+                sg = st.view(n, G, cout // G, 2).sum(2) / float(nvox * (cout // G))
+                mu = sg[..., 0]
+                var = (sg[..., 1] - mu * mu).clamp_min(0.0)
+                mean = mu.repeat_interleave(cout // G, 1).float()
+                rstd = (1.0 / torch.sqrt(var + norm.eps)).repeat_interleave(cout // G, 1).float()
+            elif norm.training or not norm.track_running_stats:      # BatchNorm3d with batch statistics
+                sb = st.sum(0) / float(n * nvox)
+                mu = sb[:, 0]
+                var = (sb[:, 1] - mu * mu).clamp_min(0.0)
+                if norm.track_running_stats:
+                    cnt = float(n * nvox)
+                    mom = norm.momentum if norm.momentum is not None else 1.0 / float(norm.num_batches_tracked.item() + 1)
+                    norm.running_mean.mul_(1 - mom).add_(mu.to(norm.running_mean.dtype), alpha=mom)
+                    norm.running_var.mul_(1 - mom).add_((var * cnt / max(cnt - 1.0, 1.0)).to(norm.running_var.dtype), alpha=mom)
+                    norm.num_batches_tracked += 1
+                mean = mu.float().expand(n, cout)
+                rstd = (1.0 / torch.sqrt(var + norm.eps)).float().expand(n, cout)
+            else:                                                    # BatchNorm3d in eval mode: running statistics
+                mean = norm.running_mean.detach().float().expand(n, cout)
+                rstd = (1.0 / torch.sqrt(norm.running_var.detach().float() + norm.eps)).expand(n, cout)
+                stat_grad = False
+        mean, rstd = mean.contiguous(), rstd.contiguous()
+        mr_fwd = torch.stack([mean, rstd * gamma], -1).contiguous()
+        shift = beta.expand(n, cout).contiguous()
+        K.instnorm_act_apply(raw, False, mr_fwd, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, 0, shift=shift)
+        self.tape.append(dict(kind="cna", name=name, src=src, segs=list(segs), conv=conv, dst=dst, dst_c0=dst_c0,
+                              pooled=pooled, slope=slope, raw=raw, mr=None, gspec=None, need_dgrad=need_dgrad,
+                              chan_scale=None, gate_ref=None, norm=norm, nk=nk, mean=mean, rstd=rstd, gamma=gamma, beta=beta,
+                              stat_grad=stat_grad))
+
+    def _bwd_generic_norm(self, op, draw_t, gA, gA_c0, gP):
+        """Backward of the norms above through the SAME two kernels as InstanceNorm: with (mean', rstd') = (mean - beta /
+        (rstd gamma), rstd gamma) the kernels' normalised value IS the pre-activation z = y^ gamma + beta, so their sums are
+        (sum h, sum h z) with h = g * act'(z); from those: dbeta = sum h, dgamma = sum h y^, and — combined over the norm's
+        reduction set R (the group's channels / all images / nothing) —
+            dx = rstd (h gamma - M1 - y^ M2),  M1 = mean_R(h gamma), M2 = mean_R(h gamma y^)
+               = rstd' (h - A - z B),          A = M1 / gamma - beta M2 / gamma^2,  B = M2 / gamma^2,
+        which is the apply kernel's formula with (A, B) as its two subtraction terms."""
+        norm, nk = op["norm"], op["nk"]
+        mean, rstd, gamma, beta = op["mean"], op["rstd"], op["gamma"], op["beta"]
+        src, conv = op["src"], op["conv"]
+        n, Z, Y, X = src.n_img, src.Z, src.Y, src.X
+        nvox = float(Z * Y * X)
+        cout = conv.weight.shape[0]
+        g_safe = torch.where(gamma.abs() < 1e-12, torch.full_like(gamma, 1e-12), gamma)
+        mr_b = torch.stack([mean - beta / (rstd * g_safe), rstd * g_safe], -1).contiguous()
+
+        def between(sums):                     # sums [n, C, 2] = (sum h, sum h z)
+            s_h, s_hz = sums[..., 0], sums[..., 1]
+            s_hy = (s_hz - beta * s_h) / g_safe
+            if getattr(norm, "weight", None) is not None:
+                self.grads[norm.weight] = s_hy.sum(0)
+            if getattr(norm, "bias", None) is not None:
+                self.grads[norm.bias] = s_h.sum(0)
+            if not op["stat_grad"]:
+                return torch.zeros_like(sums)
+            t1, t2 = s_h * gamma, s_hy * gamma
+            if nk == "group":
+                G = norm.num_groups
+                cnt = nvox * (cout // G)
+                M1 = (t1.view(n, G, -1).sum(2) / cnt).repeat_interleave(cout // G, 1)
+                M2 = (t2.view(n, G, -1).sum(2) / cnt).repeat_interleave(cout // G, 1)
+            else:                              # batch statistics: over images and voxels
+                M1 = (t1.sum(0) / (n * nvox)).expand(n, cout)
+                M2 = (t2.sum(0) / (n * nvox)).expand(n, cout)
+            return torch.stack([M1 / g_safe - beta * M2 / (g_safe * g_safe), M2 / (g_safe * g_safe)], -1)
+
+        K.instnorm_act_bwd(op["raw"], mr_b, n, cout, Z, Y, X, gA, gA_c0, 1.0, gP, 0, draw_t, op["slope"], between=between)
 
     def conv_transpose(self, name: str, src: Blocked, up, dst: Blocked):
         cin = up.weight.shape[0]
@@ -232,13 +337,20 @@ class TrainEngine:
             gate, i = op["gate_ref"]
             chan_scale = gate["w"][:, i:i + 1].expand(n, cout).contiguous()
             chan_bias = (gate["dpooled"][:, i * cout:(i + 1) * cout] / float(Z * Y * X)).contiguous()
-        K.instnorm_act_bwd(op["raw"], op["mr"], n, cout, Z, Y, X, gA, gA_c0, scale, gP, 0, draw_t, op["slope"],
-                           chan_scale, chan_bias)
+        generic = op.get("nk", "instance") != "instance"
+        if generic:
+            self._bwd_generic_norm(op, draw_t, gA, gA_c0, gP)
+        else:
+            K.instnorm_act_bwd(op["raw"], op["mr"], n, cout, Z, Y, X, gA, gA_c0, scale, gP, 0, draw_t, op["slope"],
+                               chan_scale, chan_bias)
         draw = _wrap(draw_t, n, cout, Z, Y, X)
         ks = conv.weight.shape[2]
         self._wgrad_async(conv.weight, dkey, src, op["segs"], draw_t, cout // 8, 0, cout, ks, conv.weight.shape)
-        if conv.bias is not None:  # cancelled exactly by the InstanceNorm mean subtraction
-            self.grads[conv.bias] = torch.zeros_like(conv.bias, dtype=torch.float32)
+        if conv.bias is not None:
+            if generic:   # the conv bias is live under every norm but InstanceNorm
+                self.grads[conv.bias] = self._channel_sums(draw, 0, cout)
+            else:         # cancelled exactly by the InstanceNorm mean subtraction
+                self.grads[conv.bias] = torch.zeros_like(conv.bias, dtype=torch.float32)
         if op["need_dgrad"]:
             segs = op["segs"]
             # (a single segment may have any channel count: the first layers' 1- or 2-channel input; the padded output
@@ -352,14 +464,15 @@ class TrainEngine:
             K.pack_ncdhw(x, a_in)
             self._inputs.append((a_in, cin))
             self.conv_norm_act("init.c1", a_in, [(0, cin)], m.init_conv.conv1, A("e0.mid", f[0], 0),
-                               need_dgrad=self._input_grad)
+                               need_dgrad=self._input_grad, norm=m.init_conv.norm1)
             for l in range(L):
                 blk = m.init_conv if l == 0 else m.encoders[l - 1].conv
                 if l > 0:
-                    self.conv_norm_act(f"e{l}.c1", self.A[f"pool{l}"], [(0, f[l - 1])], blk.conv1, A(f"e{l}.mid", f[l], l))
+                    self.conv_norm_act(f"e{l}.c1", self.A[f"pool{l}"], [(0, f[l - 1])], blk.conv1, A(f"e{l}.mid", f[l], l),
+                                       norm=blk.norm1)
                 dst, c0 = fused(l)
                 self.conv_norm_act(f"e{l}.c2", self.A[f"e{l}.mid"], [(0, f[l])], blk.conv2, dst, c0,
-                                   pooled=A(f"pool{l + 1}", f[l], l + 1) if l < L - 1 else None)
+                                   pooled=A(f"pool{l + 1}", f[l], l + 1) if l < L - 1 else None, norm=blk.norm2)
             decoders = m.decoders
         else:
             M, cpm = m.num_modalities, m.in_channels_per_modality
@@ -410,10 +523,11 @@ class TrainEngine:
             dec = decoders[j]
             cat = self.A[f"cat{l}"]
             self.conv_transpose(f"d{l}.up", cur, dec.up, cat)
-            self.conv_norm_act(f"d{l}.c1", cat, [(0, f[l]), (f[l], f[l])], dec.conv.conv1, A(f"d{l}.mid", f[l], l))
+            self.conv_norm_act(f"d{l}.c1", cat, [(0, f[l]), (f[l], f[l])], dec.conv.conv1, A(f"d{l}.mid", f[l], l),
+                               norm=dec.conv.norm1)
             last = l == 0
             self.conv_norm_act(f"d{l}.c2", self.A[f"d{l}.mid"], [(0, f[l])], dec.conv.conv2, A(f"d{l}.out", f[l], l),
-                               chan_scale=drop_scale if last else None)
+                               chan_scale=drop_scale if last else None, norm=dec.conv.norm2)
             cur = self.A[f"d{l}.out"]
         logits = torch.empty((n, m.out_channels, Z, Y, X), dtype=torch.float32, device=x.device)
         self.conv_logits("out", cur, m.out_conv, logits)

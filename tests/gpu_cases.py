@@ -1441,3 +1441,73 @@ def unet_odd_size_case(shape=(25, 30, 21), features=(16, 32, 64), mode="parity",
     e = ((got_u - want).norm() / want.norm()).item()
     print(f"[UpBlock3D resize branch] rel_l2 {e:.2e}", flush=True)
     assert got_u.shape == want.shape and e < (1e-3 if mode in ("parity", "fp16x3") else 3e-2)
+
+
+def unet_norm_training_case(norm="group", features=(16, 32), S=16, n_img=2):
+    """UNet3D training with model.backbone.norm = group | batch | none (reference unet.py:29-41): loss gradient of every
+    parameter (conv weights AND the now-live conv biases, norm gamma / beta) vs fp64 autograd of a torch restatement on the
+    same parameters; BatchNorm3d also has to leave the running statistics nn.BatchNorm3d would."""
+    from mmseg_b200.src.models.backbones.unet import UNet3D
+    torch.manual_seed(11)
+    m = UNet3D(in_channels=2, out_channels=4, features=list(features), norm=norm, dropout=0.0).train()
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if "norm" in name and name.endswith("weight"):
+                p.uniform_(0.6, 1.4)
+            elif "norm" in name and name.endswith("bias"):
+                p.normal_(0, 0.3)
+            p.copy_(p.to(torch.bfloat16).float()) if p.dim() > 1 else None
+    sd = {k: v.detach().double().clone().requires_grad_(v.is_floating_point()) for k, v in m.state_dict().items()}
+    x = torch.randn(n_img, 2, S, S, S).to(torch.bfloat16).float()
+    G = torch.randn(n_img, 4, S, S, S)
+    L = len(features)
+
+    def nrm(t, key):
+        if norm == "group":
+            return F.group_norm(t, 8, sd[key + ".weight"], sd[key + ".bias"], 1e-5)
+        if norm == "batch":
+            return F.batch_norm(t, None, None, sd[key + ".weight"], sd[key + ".bias"], True, 0.1, 1e-5)
+        return t
+
+    def block(t, pre):
+        for i in (1, 2):
+            t = F.relu(nrm(F.conv3d(t, sd[f"{pre}.conv{i}.weight"], sd[f"{pre}.conv{i}.bias"], padding=1), f"{pre}.norm{i}"))
+        return t
+
+    t = block(x.double(), "init_conv")
+    feats = [t]
+    for i in range(L - 1):
+        t = block(F.max_pool3d(t, 2), f"encoders.{i}.conv")
+        feats.append(t)
+    for j in range(L - 1):
+        skip = feats[L - 2 - j]
+        t = F.conv_transpose3d(t, sd[f"decoders.{j}.up.weight"], sd[f"decoders.{j}.up.bias"], stride=2)
+        t = block(torch.cat([t, skip], 1), f"decoders.{j}.conv")
+    ref = F.conv3d(t, sd["out_conv.weight"], sd["out_conv.bias"])
+    (ref * G.double()).sum().backward()
+    m = m.to(DEV)
+    out = m(x.to(DEV))
+    out.backward(G.to(DEV))
+    e_out = ((out.detach().cpu().double() - ref.detach()).norm() / ref.detach().norm()).item()
+    rows = []
+    wnorm = sd["out_conv.weight"].grad.norm().item()
+    for name, p in m.named_parameters():
+        assert p.grad is not None, name
+        r = sd[name].grad
+        if r.norm().item() < 1e-9 * wnorm:   # a conv bias in front of a batch-statistics BatchNorm: its true gradient is 0
+            assert p.grad.norm().item() < 2e-2 * wnorm, (name, p.grad.norm().item())
+            continue
+        rows.append((((p.grad.cpu().double() - r).norm() / r.norm().clamp_min(1e-30)).item(), name))
+    rows.sort(reverse=True)
+    print(f"[unet train norm={norm}] top: " + ", ".join(f"{n_}: {e:.2e}" for e, n_ in rows[:5]))
+    print(f"[unet train norm={norm}] logits rel {e_out:.2e}; parameter gradients rel-L2 worst {rows[0][0]:.2e} ({rows[0][1]}), "
+          f"median {rows[len(rows) // 2][0]:.2e}; biases: " + ", ".join(f"{n_.split('.')[-2]}.bias {e:.1e}" for e, n_ in rows if n_.endswith("conv1.bias"))[:200])
+    # bf16 floor of a two-level net with ReLU decisions (the InstanceNorm path shows the same 6-14 %, train_step_case)
+    assert e_out < 2e-2 and rows[0][0] < 0.3 and rows[len(rows) // 2][0] < 0.15
+    if norm == "batch":   # running statistics after one training step, as nn.BatchNorm3d leaves them
+        with torch.no_grad():
+            c1 = F.conv3d(x.double(), sd["init_conv.conv1.weight"], sd["init_conv.conv1.bias"], padding=1)
+            mu, var = c1.mean((0, 2, 3, 4)), c1.var((0, 2, 3, 4), unbiased=True)
+        rm, rv = m.init_conv.norm1.running_mean.cpu().double(), m.init_conv.norm1.running_var.cpu().double()
+        assert (rm - 0.1 * mu).abs().max().item() < 2e-3 and (rv - (0.9 + 0.1 * var)).abs().max().item() < 2e-3
+        assert int(m.init_conv.norm1.num_batches_tracked.item()) == 1

@@ -154,6 +154,11 @@ def test_unet_odd_sizes_trilinear_resize_branch(mode):
     _c().unet_odd_size_case(mode=mode)
 
 
+@pytest.mark.parametrize("norm", ["group", "batch", "none"])
+def test_unet_training_with_non_instance_norms(norm):
+    _c().unet_norm_training_case(norm)
+
+
 def test_pack_unpack_roundtrip():
     _c().pack_roundtrip_case()
 
