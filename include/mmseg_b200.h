@@ -413,6 +413,18 @@ int mmseg_modality_normalize(const float* src, float* dst, int32_t C, int64_t vo
 int mmseg_weights_repack(const float* w, const int32_t* n_off, const int32_t* k_off, void* dst, int32_t n_out, int32_t NT,
                          int32_t n_kc, int32_t n_kc_total, int32_t ksize, int32_t flip, int32_t hi_copies, int32_t has_lo,
                          int32_t fmt, float scale, void* stream);
+/* The same for a whole list of weights in ONE launch: descs = device array of mmseg_repack_desc (the per-weight arguments of
+ * mmseg_weights_repack; first_block = index of the weight's first 256-thread block), block_desc[b] = descriptor of block b. */
+typedef struct {
+  const float* w;
+  const int32_t* n_off;
+  const int32_t* k_off;
+  void* dst;
+  int32_t n_out, NT, n_kc, n_kc_total, ksize, flip, hi_copies, has_lo;
+  int64_t first_block;
+} mmseg_repack_desc;
+int mmseg_weights_repack_multi(const void* descs, int32_t n_descs, const int32_t* block_desc, int64_t n_blocks, int32_t fmt,
+                               float scale, void* stream);
 /* dst[i] = idx[i] >= 0 ? src[idx[i]] : 0 — conv bias padded / expanded to the GEMM columns (ConvTranspose: x8 taps). */
 int mmseg_gather_f32(const float* src, const int32_t* idx, float* dst, int32_t n, void* stream);
 

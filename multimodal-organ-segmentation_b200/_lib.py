@@ -56,6 +56,13 @@ class AdamwTensor(C.Structure):
                 ("n", C.c_int64)]
 
 
+class RepackDesc(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("n_off", C.c_void_p), ("k_off", C.c_void_p), ("dst", C.c_void_p),
+                ("n_out", C.c_int32), ("NT", C.c_int32), ("n_kc", C.c_int32), ("n_kc_total", C.c_int32),
+                ("ksize", C.c_int32), ("flip", C.c_int32), ("hi_copies", C.c_int32), ("has_lo", C.c_int32),
+                ("first_block", C.c_int64)]
+
+
 ADAMW_CHUNK = 8192
 
 
@@ -144,6 +151,7 @@ SYMBOLS = {
     "mmseg_channel_stats": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _vp, _vp]),
     "mmseg_modality_normalize": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "mmseg_weights_repack": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "mmseg_weights_repack_multi": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _f32, _vp]),
     "mmseg_gather_f32": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "mmseg_adamw_multi": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp]),
     "mmseg_swin_patch_embed": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -19,13 +19,12 @@ namespace mmseg {
 // Destination layout (conv_tc.cu): [n_ntiles][n_kc_total][taps2d][2 k halves][rows][8], rows = KZ*NT with the z taps
 // stored dz-DESCENDING (row = (KZ-1-dz)*NT + n_local); taps2d = 9 for k=3, 1 for k=1.
 // Split modes: the hi part is written `hi_copies` times at chunk offsets 0, n_kc, ...; the lo part (w - hi) once after.
-__global__ void __launch_bounds__(256)
-weights_repack_kernel(const float* __restrict__ w, const int* __restrict__ n_off, const int* __restrict__ k_off,
-                      uint4* __restrict__ dst, int n_out, int NT, int n_kc, int n_kc_total, int ksize, int flip,
-                      int hi_copies, int has_lo, int fp16, float scale) {
+__device__ __forceinline__ void repack_one(const float* __restrict__ w, const int* __restrict__ n_off,
+                                           const int* __restrict__ k_off, uint4* __restrict__ dst, int n_out, int NT, int n_kc,
+                                           int n_kc_total, int ksize, int flip, int hi_copies, int has_lo, int fp16, float scale,
+                                           long long idx) {
   const int taps = ksize * ksize * ksize;
   const long long total = (long long)n_out * n_kc * 2 * taps;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int tap = (int)(idx % taps);
   long long r = idx / taps;
@@ -65,6 +64,31 @@ weights_repack_kernel(const float* __restrict__ w, const int* __restrict__ n_off
     for (int c = 0; c < hi_copies; ++c) dst[at(kc + c * n_kc)] = hi;
     dst[at(kc + hi_copies * n_kc)] = lo;
   }
+}
+
+__global__ void __launch_bounds__(256)
+weights_repack_kernel(const float* __restrict__ w, const int* __restrict__ n_off, const int* __restrict__ k_off,
+                      uint4* __restrict__ dst, int n_out, int NT, int n_kc, int n_kc_total, int ksize, int flip,
+                      int hi_copies, int has_lo, int fp16, float scale) {
+  repack_one(w, n_off, k_off, dst, n_out, NT, n_kc, n_kc_total, ksize, flip, hi_copies, has_lo, fp16, scale,
+             (long long)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// Every weight of a model in ONE launch (a training step repacks ~90 operands; as separate launches they cost 0.6 - 1.5 ms of
+// launch latency): block b works on descriptor block_desc[b], at block offset b - first_block of that descriptor.
+struct RepackDesc {
+  const float* w;
+  const int* n_off;
+  const int* k_off;
+  uint4* dst;
+  int n_out, NT, n_kc, n_kc_total, ksize, flip, hi_copies, has_lo;
+  long long first_block;
+};
+__global__ void __launch_bounds__(256)
+weights_repack_multi_kernel(const RepackDesc* __restrict__ descs, const int* __restrict__ block_desc, int fp16, float scale) {
+  const RepackDesc d = descs[block_desc[blockIdx.x]];
+  repack_one(d.w, d.n_off, d.k_off, d.dst, d.n_out, d.NT, d.n_kc, d.n_kc_total, d.ksize, d.flip, d.hi_copies, d.has_lo, fp16,
+             scale, ((long long)blockIdx.x - d.first_block) * blockDim.x + threadIdx.x);
 }
 
 // dst[i] = idx[i] >= 0 ? src[idx[i]] : 0  (bias expanded / padded to the GEMM columns)
@@ -168,6 +192,17 @@ extern "C" int mmseg_weights_repack(const float* w, const int32_t* n_off, const 
       w, n_off, k_off, reinterpret_cast<uint4*>(dst), n_out, NT, n_kc, n_kc_total, ksize, flip ? 1 : 0, hi_copies,
       has_lo ? 1 : 0, fmt == MMSEG_FMT_FP16 ? 1 : 0, scale);
   return check_launch("weights_repack_kernel");
+}
+
+extern "C" int mmseg_weights_repack_multi(const void* descs, int32_t n_descs, const int32_t* block_desc, int64_t n_blocks,
+                                          int32_t fmt, float scale, void* stream) {
+  static_assert(sizeof(RepackDesc) == sizeof(mmseg_repack_desc), "mmseg_repack_desc layout");
+  if (!descs || !block_desc || n_descs < 1 || n_blocks < 1 || n_blocks > 2147483647LL)
+    return fail(MMSEG_ERR_INVALID_ARG, "weights_repack_multi: bad arguments");
+  if (fmt != MMSEG_FMT_BF16 && fmt != MMSEG_FMT_FP16) return fail(MMSEG_ERR_INVALID_ARG, "weights_repack_multi: fmt");
+  weights_repack_multi_kernel<<<(unsigned)n_blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const RepackDesc*>(descs), block_desc, fmt == MMSEG_FMT_FP16 ? 1 : 0, scale);
+  return check_launch("weights_repack_multi_kernel");
 }
 
 extern "C" int mmseg_gather_f32(const float* src, const int32_t* idx, float* dst, int32_t n, void* stream) {

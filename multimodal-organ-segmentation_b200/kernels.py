@@ -328,6 +328,42 @@ class PackPlan:
         return cls(w, n_off, k_off, 1, False, False, nt_cap, cin, cout)
 
 
+class PackBatch:
+    """mmseg_weights_repack_multi over a fixed list of PackPlans (same element format): one launch re-derives every packed
+    operand of a model from its live fp32 parameters — what a training step does before its forward (the per-weight
+    launches cost 0.6 ms of a 16.5 ms DualEncoder step and 1.5 ms of a SwinUNETR step)."""
+
+    def __init__(self, plans: Sequence["PackPlan"]):
+        self.plans = list(plans)
+        assert self.plans and len({p.nm.fmt for p in self.plans}) == 1
+        dev = self.plans[0].weight.device
+        descs = (_lib.RepackDesc * len(self.plans))()
+        block_desc: List[int] = []
+        for i, p in enumerate(self.plans):
+            pc, d = p.pc, descs[i]
+            d.w, d.n_off, d.k_off, d.dst = p.weight.data_ptr(), p.n_off.data_ptr(), p.k_off.data_ptr(), pc.w.data_ptr()
+            d.n_out, d.NT, d.n_kc, d.n_kc_total = pc.n_out, pc.NT, p.n_kc, pc.n_kchunks
+            d.ksize, d.flip, d.hi_copies, d.has_lo = p.ksize, int(p.flip), p.hi_copies, int(p.has_lo)
+            d.first_block = len(block_desc)
+            total = pc.n_out * p.n_kc * 2 * p.ksize ** 3
+            block_desc += [i] * ((total + 255) // 256)
+        raw = bytes(descs)
+        self.descs = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        self.block_desc = torch.tensor(block_desc, dtype=torch.int32, device=dev)
+        self.n_blocks = len(block_desc)
+        self.ptrs = tuple(p.weight.data_ptr() for p in self.plans)
+
+    def valid(self) -> bool:
+        return all(p.weight.data_ptr() == q for p, q in zip(self.plans, self.ptrs))
+
+    def run(self) -> None:
+        _call("mmseg_weights_repack_multi", _ptr(self.descs), len(self.plans), _ptr(self.block_desc), self.n_blocks,
+              self.plans[0].nm.fmt, 1.0, _stream())
+        for p in self.plans:
+            if p.pc.bias is not None:
+                _call("mmseg_gather_f32", _ptr(p.bias_src), _ptr(p.bias_idx), _ptr(p.pc.bias), p.pc.n_out, _stream())
+
+
 def a_chunk_table(src: Blocked, seg_c0: Sequence[int], seg_channels: Sequence[int], split) -> List[int]:
     """First channel block of every K chunk, in the order pack_conv_weight laid the chunks out."""
     nm = numeric_mode(split)

@@ -24,14 +24,42 @@ LRELU_SLOPE = 0.01
 _PLANS: Dict[Tuple, K.PackPlan] = {}
 
 
+_FRESH: Dict[Tuple, int] = {}      # plan key -> parameter version its packed operand was derived from
+_BATCHES: Dict[int, Tuple] = {}
+
+
 def _plan(param: Tensor, variant, make) -> K.PackedConv:
+    """Packed operand of `param`: re-derived by the step's batched repack (`_repack_all`), or by its own launch when the
+    plan is new."""
     key = (id(param), variant)
     plan = _PLANS.get(key)
     if plan is None or plan.weight.data_ptr() != param.data_ptr():
         if len(_PLANS) > 4096:
             _PLANS.clear()
+            _BATCHES.clear()
         plan = _PLANS[key] = make()
+        _BATCHES.clear()
+        _FRESH.pop(key, None)    # (an id can be re-used by a new parameter: the new plan has not run yet)
+    if _FRESH.get(key) == plan.weight._version:      # (detached views share the parameter's version counter)
+        return plan.pc
+    _FRESH[key] = plan.weight._version
     return plan.run()
+
+
+def _repack_all(net) -> None:
+    """One launch re-derives every packed operand of `net` from its live parameters (kernels.PackBatch)."""
+    ids = {id(p) for p in net.parameters()}
+    ent = _BATCHES.get(id(net))
+    if ent is None or not ent[0].valid():
+        live = {k: p for k, p in _PLANS.items() if k[0] in ids}
+        if not live:
+            return
+        ent = _BATCHES[id(net)] = (K.PackBatch(list(live.values())), list(live.keys()))
+    if all(_FRESH.get(k) == p.weight._version for k, p in zip(ent[1], ent[0].plans)):
+        return                                       # parameters unchanged since the last repack (gradient accumulation)
+    ent[0].run()
+    for k, p in zip(ent[1], ent[0].plans):
+        _FRESH[k] = p.weight._version
 
 
 def _B(t: Tensor) -> Blocked:
@@ -487,6 +515,7 @@ def swin_unetr_train_forward(net, x: Tensor) -> Tensor:
     win = tuple(net.window_size)
     vit = net.swinViT
     pe = vit.patch_embed.proj
+    _repack_all(net)
     xs = PatchEmbedFn.apply(x, pe.weight, pe.bias)
     hidden = [LayerNormFn.apply(xs, None, None, 1e-5)]
     for s in range(4):

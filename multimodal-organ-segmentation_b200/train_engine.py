@@ -50,15 +50,36 @@ class TrainEngine:
         self._buf_busy: Dict[str, object] = {}
         self._flip = 0
         self._plans: Dict[Tuple, K.PackPlan] = {}
+        self._batch = None
+        self._batch_keys: list = []
+        self._fresh: Dict[Tuple, int] = {}   # plan key -> parameter version its packed operand was derived from
 
     def _packed(self, param: Tensor, variant: str, make) -> K.PackedConv:
-        """Kernel-layout operand of `param` in form `variant`, re-derived from the live parameter by ONE repack launch
-        (kernels.PackPlan / mmseg_weights_repack): the tables and the packed buffer are built once per parameter."""
+        """Kernel-layout operand of `param` in form `variant`, re-derived from the live parameter by the step's ONE
+        batched repack launch (kernels.PackBatch / mmseg_weights_repack_multi, issued by `_repack_all` at the start of
+        the forward); a plan that did not exist yet at that point (first step) runs its own launch."""
         key = (id(param), variant)
         plan = self._plans.get(key)
         if plan is None or plan.weight.data_ptr() != param.data_ptr():
             plan = self._plans[key] = make()
+            self._batch = None
+            self._fresh.pop(key, None)
+        if self._fresh.get(key) == plan.weight._version:     # (detached views share the parameter's version counter)
+            return plan.pc
+        self._fresh[key] = plan.weight._version
         return plan.run()
+
+    def _repack_all(self) -> None:
+        """Every packed operand the previous step used, from the current parameters, in one launch."""
+        if not self._plans or os.environ.get("MMSEG_REPACK_BATCH", "1") != "1":
+            return
+        if self._batch is None or not self._batch.valid():
+            live = {k: p for k, p in self._plans.items()}
+            self._batch = K.PackBatch(list(live.values()))
+            self._batch_keys = list(live.keys())
+        self._batch.run()
+        for k, p in zip(self._batch_keys, self._batch.plans):
+            self._fresh[k] = p.weight._version
 
     # ---------------------------------------------------------------- buffers
     def _reset(self, n, Z, Y, X, device):
@@ -448,6 +469,7 @@ class TrainEngine:
         x = x.contiguous().float()
         n, _, Z, Y, X = x.shape
         self._reset(n, Z, Y, X, x.device)
+        self._repack_all()
         m = self.module
         f, L = m.features, len(m.features)
         if any(d % (1 << (L - 1)) for d in (Z, Y, X)):
