@@ -35,7 +35,23 @@ PROFILE: Optional[list] = None
 _INFO = [None]
 
 
+# MMSEG_NVTX=1: every C-ABI call is an NVTX range named after its entry point (+ the layer description when a per-kernel
+# profile is running), so that nsys / ncu timelines read in the path's own vocabulary
+NVTX = os.environ.get("MMSEG_NVTX", "0") == "1"
+
+
 def _call(name: str, *args) -> None:
+    if NVTX:
+        info = _INFO[0]
+        torch.cuda.nvtx.range_push(name if not info else f"{name} {info.get('layer', '')}")
+        try:
+            return _call_inner(name, *args)
+        finally:
+            torch.cuda.nvtx.range_pop()
+    return _call_inner(name, *args)
+
+
+def _call_inner(name: str, *args) -> None:
     prof = PROFILE
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

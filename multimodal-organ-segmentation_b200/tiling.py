@@ -6,6 +6,7 @@ small cycle model used to pick (TX, TY, TZ, NT, stages) per layer.  Hardware con
 an M=128, K=16 tcgen05.mma costs max(51, N/2) clk, i.e. the tensor pipe is only saturated for N >= ~104, which is why
 the kernel folds the three z taps into N (N = 3*NT for interior planes).
 """
+import os
 from dataclasses import dataclass
 from functools import lru_cache
 from typing import Optional
@@ -123,6 +124,8 @@ def plan_conv(X: int, Y: int, Z: int, n_img: int, n_kchunks: int, n_out: int, ks
                     mt = _cdiv(TX * TY * TZ, 128)
                     if mt * NT > TMEM_COLS:
                         break
+                    if mt in (3, 5, 7) and os.environ.get("MMSEG_K1_ODD_MT", "0") != "1":
+                        continue   # the flat epilogue's two-chunk pipeline spills 340 B for odd M-tile counts (ptxas log)
                 tc = tmem_cols(mt, TZ if h else 1, NT)
                 sb, stages = None, 0
                 # deep ring: one stage is a single small z-plane (a few KB) while a TMA round trip is ~1.5-2 us (a third
