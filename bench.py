@@ -822,7 +822,7 @@ def swin_measure(dev, steps=5, warmup=3, cpu=True):
         crit = DiceCELoss()
         opt = FusedAdamW(m.parameters(), lr=1e-4)
         res["train"] = []
-        for B in (1, 2):
+        for B in (1, 2, 4):
             x = torch.randn((B, 2, 96, 96, 96), generator=g).to(dev)
             y = torch.randint(0, 8, (B, 96, 96, 96), generator=g).to(dev)
 

@@ -343,6 +343,10 @@ static int plan_wgrad(const mmseg_wgrad_args* a, WgradPlan* out) {
   k.yplane_bytes = (uint32_t)a->TY * a->TX * 16u;
   if ((k.xplane_bytes >> 4) > 0x3FFF) return fail(MMSEG_ERR_INVALID_ARG, "wgrad: X plane too large for SBO");
   k.xslot_bytes = (uint32_t)KT * a->cig_blocks * k.xplane_bytes;
+  // every TMA destination (the KT x-shifted copies of an X plane, the ring slots) must be 128-byte aligned
+  if (((uint32_t)a->cig_blocks * k.xplane_bytes) & 127u)
+    return fail(MMSEG_ERR_INVALID_ARG, "wgrad: %d ci blocks x %u-byte X planes: the x-shifted copies would not be 128-byte aligned",
+                a->cig_blocks, k.xplane_bytes);
   k.yslot_bytes = (uint32_t)a->cot_blocks * k.yplane_bytes;
   k.ncols = KT * KT * a->cot_blocks * 8;
   if (k.ncols > 512) return fail(MMSEG_ERR_INVALID_ARG, "wgrad: %d TMEM columns > 512", k.ncols);

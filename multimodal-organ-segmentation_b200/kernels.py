@@ -702,8 +702,14 @@ def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt
     seg_ch = [s[1] for s in segs]
     seg_pad = [(s + 15) // 16 * 16 for s in seg_ch]
     cin = sum(seg_ch)
-    cig = _largest_divisor((32, 16) if ksize == 3 else (128, 64, 32, 16), seg_pad)
-    ntc = _largest_divisor((32, 16) if ksize == 3 else (256, 128, 64, 32, 16), [(cout_gemm + 15) // 16 * 16])
+    # channel groups: input channels per accumulator-row group (k3: 3 dx copies x cig <= 128 rows), output channels per
+    # MMA column group (k3: 3 dz taps x ntc <= 256 columns).  The 24- / 48- / 96-channel sizes serve SwinUNETR's widths
+    # (48 * 2^s): C = 48 gets (24, 48) = 72 of 128 rows and N = 144 instead of (16, 16) = 48 rows and N = 48.
+    cig = _largest_divisor((32, 24, 16) if ksize == 3 else (128, 96, 64, 48, 32, 16), seg_pad)
+    ntc = _largest_divisor((48, 32, 16) if ksize == 3 else (256, 192, 128, 96, 64, 48, 32, 16), [(cout_gemm + 15) // 16 * 16])
+    if os.environ.get("MMSEG_WGRAD_OLD_GROUPS", "0") == "1":
+        cig = _largest_divisor((32, 16) if ksize == 3 else (128, 64, 32, 16), seg_pad)
+        ntc = _largest_divisor((32, 16) if ksize == 3 else (256, 128, 64, 32, 16), [(cout_gemm + 15) // 16 * 16])
     cout_pad = (cout_gemm + 15) // 16 * 16
     groups, ci_map = [], []
     for (c0, s), sp in zip(segs, seg_pad):
