@@ -60,8 +60,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
                : "memory");
 }
 
+// Two CTAs per SM for head_dim <= 64 (256 TMEM columns and <= 113 KB of shared memory each): inside a CTA the score MMA, the
+// softmax and the P V MMA of a key tile are serialised, so a second resident CTA is what keeps the tensor pipe busy during
+// the other one's softmax (and the MUFU busy during its MMAs).
 template <int HD>
-__global__ void __launch_bounds__(kAThreads, 1)
+__global__ void __launch_bounds__(kAThreads, HD <= 64 ? 2 : 1)
 cross_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnKParams p) {
   constexpr uint32_t kPlane = kTile * 16;            // one channel block of a 128-token tile
@@ -157,14 +160,21 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const int key0 = t * kTile;
       // pass 1 over the score row (TMEM reads are cheap; keeps only 16 scores in registers at a time): row maximum
       float mx = -INFINITY;
+      const bool full = key0 + kTile <= p.n_tok;     // every key of this tile exists: no masking (all tiles but the last)
 #pragma unroll
       for (int c = 0; c < kTile / 16; ++c) {
         float sv[16];
         tmem_ld16(tmem_s + lane_off + c * 16, sv);
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (key0 + c * 16 + i < p.n_tok) mx = fmaxf(mx, sv[i] * p.scale_log2e);
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, sv[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (key0 + c * 16 + i < p.n_tok) mx = fmaxf(mx, sv[i]);
+        }
       }
+      mx *= p.scale_log2e;                           // (scale > 0: the maximum commutes with the scaling)
       const float m_new = fmaxf(m_run, mx);
       const float alpha = exp2f(m_run - m_new);      // 0 on the first tile (m_run = -inf)
       // pass 2: p = exp2(s - m), row sum, P as bf16 into the K-major operand layout [key block][row][16 B]
@@ -179,7 +189,8 @@ cross_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int key = key0 + c * 16 + hb * 8 + i;
-            pv[i] = key < p.n_tok ? exp2f(sv[hb * 8 + i] * p.scale_log2e - m_new) : 0.f;
+            const float e = exp2f(fmaf(sv[hb * 8 + i], p.scale_log2e, -m_new));
+            pv[i] = (full || key < p.n_tok) ? e : 0.f;
             rs += pv[i];
           }
           __nv_bfloat162 a = __floats2bfloat162_rn(pv[0], pv[1]), b = __floats2bfloat162_rn(pv[2], pv[3]);
