@@ -61,6 +61,9 @@ int mmseg_version(void);
 const char* mmseg_last_error(void);
 /* 1 when the process can see a CUDA device of compute capability 10.x, else 0 (never raises). */
 int mmseg_device_ok(void);
+/* sizeof() of the ABI's argument structs (0 mmseg_conv_args, 1 mmseg_wgrad_args, 2 mmseg_norm_args, 3 mmseg_norm_bwd_args,
+ * 4 mmseg_adamw_tensor, 5 mmseg_repack_desc, 6 mmseg_swin_attn_args; -1 otherwise): lets a binding verify its layout. */
+int mmseg_sizeof(int which);
 
 /*
  * Conv3d forward as a tcgen05/TMEM implicit GEMM fed by TMA halo tiles.

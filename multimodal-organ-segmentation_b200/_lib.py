@@ -107,6 +107,7 @@ SYMBOLS = {
     "mmseg_version": (C.c_int, []),
     "mmseg_last_error": (C.c_char_p, []),
     "mmseg_device_ok": (C.c_int, []),
+    "mmseg_sizeof": (C.c_int, [C.c_int]),
     "mmseg_conv3d_fwd": (C.c_int, [C.POINTER(ConvArgs), _vp]),
     "mmseg_conv3d_smem_bytes": (_i64, [C.POINTER(ConvArgs)]),
     "mmseg_conv3d_tiles_per_img": (_i32, [C.POINTER(ConvArgs)]),
@@ -182,6 +183,14 @@ for _name, (_res, _args) in SYMBOLS.items():
     _fn = getattr(lib, _name)  # AttributeError if the library does not export a declared symbol
     _fn.restype = _res
     _fn.argtypes = _args
+
+
+# the ctypes structures must have the layout the library was compiled with (a field appended on one side only would shift
+# every later argument silently)
+for _which, _struct in enumerate((ConvArgs, WgradArgs, NormArgs, NormBwdArgs, AdamwTensor, RepackDesc, SwinAttnArgs)):
+    if lib.mmseg_sizeof(_which) != C.sizeof(_struct):
+        raise ImportError(f"{_struct.__name__}: ctypes layout ({C.sizeof(_struct)} bytes) differs from libmmseg_b200.so "
+                          f"({lib.mmseg_sizeof(_which)} bytes): rebuild the library (make -C multimodal-organ-segmentation_b200/csrc)")
 
 
 def last_error() -> str:

@@ -657,6 +657,15 @@ def _largest_divisor(cands, values):
     raise ValueError(f"no channel group size in {cands} divides {values}")
 
 
+def wgrad_groups(ksize: int, seg_pad: Sequence[int], cout_pad: int) -> Tuple[int, int]:
+    """(input channels per accumulator-row group, output channels per MMA column group) of the wgrad kernel."""
+    if os.environ.get("MMSEG_WGRAD_OLD_GROUPS", "0") == "1":
+        return (_largest_divisor((32, 16) if ksize == 3 else (128, 64, 32, 16), seg_pad),
+                _largest_divisor((32, 16) if ksize == 3 else (256, 128, 64, 32, 16), [cout_pad]))
+    return (_largest_divisor((32, 24, 16) if ksize == 3 else (128, 96, 64, 48, 32, 16), seg_pad),
+            _largest_divisor((48, 32, 16) if ksize == 3 else (256, 192, 128, 96, 64, 48, 32, 16), [cout_pad]))
+
+
 @lru_cache(maxsize=None)
 def _plan_wgrad_tile(X: int, Y: int, Z: int, ksize: int, cig_blocks: int, cot_blocks: int) -> Tuple[int, int, int]:
     """(TX, TY, TZ) accepted by the library: largest K rows per plane (TX*TY, multiple of 16) that fits shared memory."""
@@ -705,11 +714,7 @@ def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt
     # channel groups: input channels per accumulator-row group (k3: 3 dx copies x cig <= 128 rows), output channels per
     # MMA column group (k3: 3 dz taps x ntc <= 256 columns).  The 24- / 48- / 96-channel sizes serve SwinUNETR's widths
     # (48 * 2^s): C = 48 gets (24, 48) = 72 of 128 rows and N = 144 instead of (16, 16) = 48 rows and N = 48.
-    cig = _largest_divisor((32, 24, 16) if ksize == 3 else (128, 96, 64, 48, 32, 16), seg_pad)
-    ntc = _largest_divisor((48, 32, 16) if ksize == 3 else (256, 192, 128, 96, 64, 48, 32, 16), [(cout_gemm + 15) // 16 * 16])
-    if os.environ.get("MMSEG_WGRAD_OLD_GROUPS", "0") == "1":
-        cig = _largest_divisor((32, 16) if ksize == 3 else (128, 64, 32, 16), seg_pad)
-        ntc = _largest_divisor((32, 16) if ksize == 3 else (256, 128, 64, 32, 16), [(cout_gemm + 15) // 16 * 16])
+    cig, ntc = wgrad_groups(ksize, seg_pad, (cout_gemm + 15) // 16 * 16)
     cout_pad = (cout_gemm + 15) // 16 * 16
     groups, ci_map = [], []
     for (c0, s), sp in zip(segs, seg_pad):

@@ -54,3 +54,11 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(d, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(d, f)
+
+
+def test_struct_layouts_match_the_library():
+    """Every argument struct of the ABI has the same size in the ctypes binding and in the compiled library."""
+    structs = (_lib.ConvArgs, _lib.WgradArgs, _lib.NormArgs, _lib.NormBwdArgs, _lib.AdamwTensor, _lib.RepackDesc, _lib.SwinAttnArgs)
+    for which, st in enumerate(structs):
+        assert _lib.lib.mmseg_sizeof(which) == ctypes.sizeof(st), st.__name__
+    assert _lib.lib.mmseg_sizeof(len(structs)) == -1

@@ -242,3 +242,56 @@ def test_epilogue_incremental_row_mapping():
                         yy -= PY
                         zz += 1
                     zz += dz128
+
+
+def test_k1_gemm_tiles_avoid_the_spilling_odd_m_tile_counts():
+    """conv3d_tc_kernel<MT, 1> spills 340 B for MT = 3, 5, 7 (conv_tc.ptxas.log): the planner never picks them."""
+    from mmseg_b200.tiling import plan_conv
+    for (X, n, kc, nout) in [(48, 4, 3, 144), (48, 4, 12, 48), (24, 4, 6, 288), (24, 1, 24, 96), (96, 4, 6, 48), (12, 2, 12, 576),
+                             (6, 4, 24, 1152), (3, 1, 48, 768), (48, 8, 4, 256)]:
+        t = plan_conv(X, X, X, n, kc, nout, 1)
+        assert t.mt not in (3, 5, 7), (X, n, kc, nout, t)
+
+
+def test_wgrad_channel_groups_and_alignment_rule():
+    import ctypes as C
+    from mmseg_b200 import _lib
+    from mmseg_b200 import kernels as K
+    # UNet widths keep (32, 32); SwinUNETR's 48 * 2^s widths get 24- / 48-channel groups instead of 16
+    assert K.wgrad_groups(3, [32], 32) == (32, 32) and K.wgrad_groups(3, [64, 64], 64) == (32, 32)
+    assert K.wgrad_groups(3, [48], 48) == (24, 48) and K.wgrad_groups(3, [96, 96], 96) == (32, 48)
+    assert K.wgrad_groups(1, [48], 144) == (48, 48) and K.wgrad_groups(1, [192], 48) == (96, 48)
+    assert K.wgrad_groups(3, [16], 32) == (16, 32)
+
+    def smem(TX, TY, cig, cot, ks=3, X=16, Y=16, Z=8):
+        a = _lib.WgradArgs()
+        a.n_img, a.Z, a.Y, a.X, a.ksize = 1, Z, Y, X, ks
+        a.TX, a.TY, a.TZ = TX, TY, 8
+        a.cig_blocks, a.cot_blocks, a.n_cig, a.n_cot = cig, cot, 1, 1
+        a.x_cbt, a.y_cbt, a.y_cb0, a.n_part = cig, cot, 0, 1
+        return _lib.lib.mmseg_conv3d_wgrad_smem_bytes(C.byref(a))
+
+    assert smem(16, 8, 4, 4) > 0
+    # 3 channel blocks x (8 + 2) x 10 voxels x 16 B = 4800 B per x-shifted copy: not a multiple of 128 -> rejected (TMA)
+    assert smem(10, 8, 3, 6) < 0 and "128-byte" in _lib.last_error()
+    assert smem(12, 12, 3, 6) > 0
+    # whatever the planner returns for the widths in use is accepted by the library
+    for (X, cig, cot, ks) in [(96, 3, 6, 3), (10, 3, 6, 3), (6, 3, 6, 3), (128, 4, 4, 3), (48, 6, 6, 1), (24, 12, 6, 1)]:
+        TX, TY, TZ = K._plan_wgrad_tile(X, X, X, ks, cig, cot)
+        assert smem(TX, TY, cig, cot, ks, X, X, X) > 0, (X, cig, cot, ks, TX, TY)
+
+
+def test_capture_guard_disables_gc_and_restores_it():
+    import gc
+    from mmseg_b200.src.trainer.inference import capture_guard
+    assert gc.isenabled()
+    with capture_guard():
+        assert not gc.isenabled()
+    assert gc.isenabled()
+    gc.disable()
+    try:
+        with capture_guard():
+            assert not gc.isenabled()
+        assert not gc.isenabled()       # it was off before: stays off
+    finally:
+        gc.enable()
