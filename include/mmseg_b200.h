@@ -366,6 +366,12 @@ int mmseg_channel_mean(const void* src, int32_t n_img, int32_t src_cbt, int32_t 
                        float* mean /* [n_img][cb*8] */, int32_t fmt, void* stream);
 int mmseg_gate_mlp(const float* pooled, const float* w1, const float* b1, const float* w2, const float* b2,
                    int32_t n_img, int32_t MC, int32_t H, int32_t M, float* weights /* [n_img][M] */, void* stream);
+/* Backward of the gate MLP (autograd through the Linear - ReLU - Linear - Softmax of CrossModalAttention.attention,
+ * dual_encoder.py:226-233): dweights [n_img][M] -> dpooled [n_img][MC], dw1 [H][MC], db1 [H], dw2 [M][H], db2 [M] (summed over the
+ * images).  workspace: (2 H + M) * n_img floats. */
+int mmseg_gate_mlp_bwd(const float* pooled, const float* w1, const float* b1, const float* w2, const float* b2,
+                       const float* dweights, int32_t n_img, int32_t MC, int32_t H, int32_t M, float* workspace, float* dpooled,
+                       float* dw1, float* db1, float* dw2, float* db2, void* stream);
 int mmseg_modality_combine(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_lo_off, int32_t M, int32_t cb,
                            int64_t voxels, const float* weights /* [n_img][M] or NULL */, float uniform_weight,
                            void* dst, int32_t dst_cbt, int32_t dst_cb_off, int32_t dst_lo_off, int32_t fmt, void* stream);

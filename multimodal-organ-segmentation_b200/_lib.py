@@ -141,6 +141,7 @@ SYMBOLS = {
     "mmseg_confusion_hist": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _vp]),
     "mmseg_channel_mean": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _i32, _vp]),
     "mmseg_gate_mlp": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "mmseg_gate_mlp_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mmseg_modality_combine": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _f32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "mmseg_modality_max": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i64, _vp, _i32, _i32, _vp]),
     "mmseg_swi_logits_blend": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp,

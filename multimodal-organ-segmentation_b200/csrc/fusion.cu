@@ -73,11 +73,15 @@ __global__ void gate_mlp_kernel(const float* __restrict__ pooled, const float* _
   float* lg = sh + H;
   const int img = blockIdx.x;
   const float* p = pooled + (size_t)img * MC;
-  for (int j = threadIdx.x; j < H; j += blockDim.x) {
-    float acc = b1[j];
+  // one warp per hidden unit, lanes along the M*C inputs (coalesced reads of the W1 row, fixed-order shuffle reduction)
+  for (int j = threadIdx.x >> 5; j < H; j += blockDim.x >> 5) {
     const float* w = w1 + (size_t)j * MC;
-    for (int k = 0; k < MC; ++k) acc = fmaf(w[k], p[k], acc);
-    hid[j] = acc > 0.f ? acc : 0.f;
+    float acc = 0.f;
+    for (int k = threadIdx.x & 31; k < MC; k += 32) acc = fmaf(w[k], p[k], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    acc += b1[j];
+    if ((threadIdx.x & 31) == 0) hid[j] = acc > 0.f ? acc : 0.f;
   }
   __syncthreads();
   for (int m = threadIdx.x; m < M; m += blockDim.x) {
@@ -93,6 +97,102 @@ __global__ void gate_mlp_kernel(const float* __restrict__ pooled, const float* _
     float se = 0.f;
     for (int m = 0; m < M; ++m) se += expf(lg[m] - mx);
     for (int m = 0; m < M; ++m) weights[(size_t)img * M + m] = expf(lg[m] - mx) / se;
+  }
+}
+
+// Backward of the gate MLP (autograd through nn.Linear - ReLU - nn.Linear - Softmax of CrossModalAttention.attention,
+// dual_encoder.py:226-233), given dweights [n_img, M] = d loss / d softmax output.  Two launches:
+//   _hidden (one block per image): recompute h and the softmax, ds = w * (dw - sum_m w dw), dh = (h > 0) * W2^T ds,
+//            dpooled = W1^T dh; keeps h, dh, ds for
+//   _params (grid over the weight elements): dW1 = sum_img dh p^T, db1 = sum_img dh, dW2 = sum_img ds h^T, db2 = sum_img ds.
+__global__ void gate_mlp_bwd_hidden_kernel(const float* __restrict__ pooled, const float* __restrict__ w1,
+                                           const float* __restrict__ b1, const float* __restrict__ w2,
+                                           const float* __restrict__ b2, const float* __restrict__ dweights, int MC, int H,
+                                           int M, float* __restrict__ hid_out, float* __restrict__ dh_out,
+                                           float* __restrict__ ds_out, float* __restrict__ dpooled) {
+  extern __shared__ float sh[];  // H hidden | H dh | M logits | M ds
+  float* hid = sh;
+  float* dh = sh + H;
+  float* lg = sh + 2 * H;
+  float* ds = lg + M;
+  const int img = blockIdx.x;
+  const float* p = pooled + (size_t)img * MC;
+  // one warp per hidden unit, lanes along the M*C inputs (coalesced reads of the W1 row, fixed-order shuffle reduction)
+  for (int j = threadIdx.x >> 5; j < H; j += blockDim.x >> 5) {
+    const float* w = w1 + (size_t)j * MC;
+    float acc = 0.f;
+    for (int k = threadIdx.x & 31; k < MC; k += 32) acc = fmaf(w[k], p[k], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    acc += b1[j];
+    if ((threadIdx.x & 31) == 0) hid[j] = acc > 0.f ? acc : 0.f;
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    float acc = b2[m];
+    const float* w = w2 + (size_t)m * H;
+    for (int k = 0; k < H; ++k) acc = fmaf(w[k], hid[k], acc);
+    lg[m] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mx = -INFINITY;
+    for (int m = 0; m < M; ++m) mx = fmaxf(mx, lg[m]);
+    float se = 0.f;
+    for (int m = 0; m < M; ++m) se += expf(lg[m] - mx);
+    float dot = 0.f;
+    for (int m = 0; m < M; ++m) {
+      lg[m] = expf(lg[m] - mx) / se;                  // softmax weight
+      dot = fmaf(lg[m], dweights[(size_t)img * M + m], dot);
+    }
+    for (int m = 0; m < M; ++m) {
+      ds[m] = lg[m] * (dweights[(size_t)img * M + m] - dot);
+      ds_out[(size_t)img * M + m] = ds[m];
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    float acc = 0.f;
+    for (int m = 0; m < M; ++m) acc = fmaf(ds[m], w2[(size_t)m * H + j], acc);
+    const float g = hid[j] > 0.f ? acc : 0.f;
+    dh[j] = g;
+    dh_out[(size_t)img * H + j] = g;
+    hid_out[(size_t)img * H + j] = hid[j];
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < MC; k += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < H; ++j) acc = fmaf(dh[j], w1[(size_t)j * MC + k], acc);
+    dpooled[(size_t)img * MC + k] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gate_mlp_bwd_params_kernel(const float* __restrict__ pooled, const float* __restrict__ hid, const float* __restrict__ dh,
+                           const float* __restrict__ ds, int n_img, int MC, int H, int M, float* __restrict__ dw1,
+                           float* __restrict__ db1, float* __restrict__ dw2, float* __restrict__ db2) {
+  const size_t n1 = (size_t)H * MC, n2 = (size_t)M * H;
+  const size_t total = n1 + H + n2 + M;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    if (i < n1) {
+      const int j = (int)(i / MC), k = (int)(i - (size_t)j * MC);
+      for (int b = 0; b < n_img; ++b) acc = fmaf(dh[(size_t)b * H + j], pooled[(size_t)b * MC + k], acc);
+      dw1[i] = acc;
+    } else if (i < n1 + H) {
+      const int j = (int)(i - n1);
+      for (int b = 0; b < n_img; ++b) acc += dh[(size_t)b * H + j];
+      db1[j] = acc;
+    } else if (i < n1 + H + n2) {
+      const size_t r = i - n1 - H;
+      const int m = (int)(r / H), j = (int)(r - (size_t)m * H);
+      for (int b = 0; b < n_img; ++b) acc = fmaf(ds[(size_t)b * M + m], hid[(size_t)b * H + j], acc);
+      dw2[r] = acc;
+    } else {
+      const int m = (int)(i - n1 - H - n2);
+      for (int b = 0; b < n_img; ++b) acc += ds[(size_t)b * M + m];
+      db2[m] = acc;
+    }
   }
 }
 
@@ -359,8 +459,30 @@ extern "C" int mmseg_gate_mlp(const float* pooled, const float* w1, const float*
     return fail(MMSEG_ERR_INVALID_ARG, "gate_mlp: bad arguments");
   const size_t sh = (size_t)(H + M) * sizeof(float);
   if (sh > 48 * 1024) return fail(MMSEG_ERR_UNSUPPORTED, "gate_mlp: hidden size too large");
-  gate_mlp_kernel<<<n_img, 256, sh, reinterpret_cast<cudaStream_t>(stream)>>>(pooled, w1, b1, w2, b2, MC, H, M, weights);
+  gate_mlp_kernel<<<n_img, 1024, sh, reinterpret_cast<cudaStream_t>(stream)>>>(pooled, w1, b1, w2, b2, MC, H, M, weights);
   return check_launch("gate_mlp_kernel");
+}
+
+extern "C" int mmseg_gate_mlp_bwd(const float* pooled, const float* w1, const float* b1, const float* w2, const float* b2,
+                                  const float* dweights, int32_t n_img, int32_t MC, int32_t H, int32_t M, float* workspace,
+                                  float* dpooled, float* dw1, float* db1, float* dw2, float* db2, void* stream) {
+  if (!pooled || !w1 || !b1 || !w2 || !b2 || !dweights || !workspace || !dpooled || !dw1 || !db1 || !dw2 || !db2 || n_img < 1 ||
+      MC < 1 || H < 1 || M < 1)
+    return fail(MMSEG_ERR_INVALID_ARG, "gate_mlp_bwd: bad arguments");
+  const size_t sh = (size_t)(2 * H + 2 * M) * sizeof(float);
+  if (sh > 48 * 1024) return fail(MMSEG_ERR_UNSUPPORTED, "gate_mlp_bwd: hidden size too large");
+  float* hid = workspace;                        // [n_img][H]
+  float* dh = hid + (size_t)n_img * H;           // [n_img][H]
+  float* ds = dh + (size_t)n_img * H;            // [n_img][M]
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  gate_mlp_bwd_hidden_kernel<<<n_img, 1024, sh, st>>>(pooled, w1, b1, w2, b2, dweights, MC, H, M, hid, dh, ds, dpooled);
+  int rc = check_launch("gate_mlp_bwd_hidden_kernel");
+  if (rc) return rc;
+  const size_t total = (size_t)H * MC + H + (size_t)M * H + M;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  gate_mlp_bwd_params_kernel<<<(unsigned)blocks, 256, 0, st>>>(pooled, hid, dh, ds, n_img, MC, H, M, dw1, db1, dw2, db2);
+  return check_launch("gate_mlp_bwd_params_kernel");
 }
 
 extern "C" int mmseg_modality_combine(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_lo_off, int32_t M,

@@ -28,7 +28,7 @@ def _ptr(t: Optional[Tensor]) -> C.c_void_p:
 
 
 # kernels launched by each C-ABI entry point (bench.py reports the count as `gpu_launches`)
-KERNELS_PER_CALL = {"mmseg_cross_attention_bwd": 3, "mmseg_adamw_multi": 2, "mmseg_channel_stats": 2, "mmseg_dicece_fwd": 2, "mmseg_channel_mean": 2, "mmseg_modality_dot": 2, "mmseg_tversky_fwd": 2}
+KERNELS_PER_CALL = {"mmseg_cross_attention_bwd": 3, "mmseg_adamw_multi": 2, "mmseg_gate_mlp_bwd": 2, "mmseg_channel_stats": 2, "mmseg_dicece_fwd": 2, "mmseg_channel_mean": 2, "mmseg_modality_dot": 2, "mmseg_tversky_fwd": 2}
 LAUNCHES = [0]
 # when a list, every C-ABI call is bracketed by CUDA events on the current stream: (name, info, ev0, ev1)
 PROFILE: Optional[list] = None
@@ -634,6 +634,19 @@ def gate_mlp(pooled: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor) -> 
     w1, b1, w2, b2 = f(w1), f(b1), f(w2), f(b2)
     _call("mmseg_gate_mlp", _ptr(pooled), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), n, MC, H, M, _ptr(out), _stream())
     return out
+
+
+def gate_mlp_bwd(pooled: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, dweights: Tensor):
+    """Backward of gate_mlp: returns (dpooled [n, MC], dW1, db1, dW2, db2) — fp32, parameter gradients summed over images."""
+    n, MC = pooled.shape
+    H, M = w1.shape[0], w2.shape[0]
+    dev = pooled.device
+    f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    ws, dpooled, dw1, db1, dw2, db2 = f((2 * H + M) * n), f(n, MC), f(H, MC), f(H), f(M, H), f(M)
+    c32 = lambda t: t.detach().float().contiguous()
+    _call("mmseg_gate_mlp_bwd", _ptr(c32(pooled)), _ptr(c32(w1)), _ptr(c32(b1)), _ptr(c32(w2)), _ptr(c32(b2)),
+          _ptr(c32(dweights)), n, MC, H, M, _ptr(ws), _ptr(dpooled), _ptr(dw1), _ptr(db1), _ptr(dw2), _ptr(db2), _stream())
+    return dpooled, dw1, db1, dw2, db2
 
 
 def modality_combine(src: Blocked, M: int, channels: int, dst: Blocked, dst_c0: int, weights: Optional[Tensor],

@@ -284,16 +284,11 @@ class TrainEngine:
         stack, M, C, att = op["stack"], op["M"], op["C"], op["att"]
         g = self.grad_of(op["dst"])
         dw = K.modality_dot(stack, M, C, g, op["dst_c0"])                     # [n, M]
-        # the gate MLP is a [n, M*C] -> [n, M] map (a few kFLOP): its backward runs through autograd on those tensors
-        with torch.enable_grad():
-            pooled = op["pooled"].detach().requires_grad_(True)
-            params = [att[2].weight, att[2].bias, att[4].weight, att[4].bias]
-            leaf = [p.detach().float().requires_grad_(True) for p in params]
-            h = torch.relu(torch.nn.functional.linear(pooled, leaf[0], leaf[1]))
-            w = torch.softmax(torch.nn.functional.linear(h, leaf[2], leaf[3]), dim=1)
-            grads = torch.autograd.grad(w, [pooled] + leaf, dw)
-        op["dpooled"] = grads[0]
-        for p, gp in zip(params, grads[1:]):
+        # backward of the gate MLP ([n, M*C] -> hidden -> [n, M] -> softmax) in two kernel launches
+        params = [att[2].weight, att[2].bias, att[4].weight, att[4].bias]
+        dpooled, dw1, db1, dw2, db2 = K.gate_mlp_bwd(op["pooled"], *params, dw)
+        op["dpooled"] = dpooled
+        for p, gp in zip(params, (dw1, db1, dw2, db2)):
             self.grads[p] = gp
 
     # ---------------------------------------------------------------- backward ops
