@@ -800,6 +800,12 @@ def instnorm_act_bwd(raw: Tensor, mean_rstd: Tensor, n_img: int, channels: int, 
     a = _lib.NormBwdArgs()
     nvox = Z * Y * X
     n_chunks = max(1, min(64, (nvox + 8191) // 8192))
+    rows = n_img * channels // 8
+    if rows * n_chunks > 296 and os.environ.get("MMSEG_BWD_WAVES", "1") == "1":
+        # the reduce kernel runs two 256-thread CTAs per SM: round its grid to whole waves of 296 CTAs (a 512-CTA grid — the
+        # 128^3, C = 32, B = 2 layers — otherwise spends its last 0.27 waves at half occupancy)
+        waves = max(1, round(rows * n_chunks / 296.0))
+        n_chunks = max(1, min(256, (296 * waves) // rows))
     partial = torch.empty((n_img * channels // 8, n_chunks, 16), dtype=torch.float32, device=raw.device)
     a.x, a.mean_rstd, a.partial, a.dx = raw.data_ptr(), mean_rstd.data_ptr(), partial.data_ptr(), dx.data_ptr()
     a.gA = gA.t.data_ptr() if gA is not None else None
