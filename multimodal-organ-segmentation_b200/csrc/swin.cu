@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <type_traits>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -263,7 +264,7 @@ constexpr int kAttnMaxTok = 352;       // 343 rounded up to 16
 constexpr int kAttnQS = 24;            // halfs per Q / K row (16 + pad: conflict-free fragment loads)
 constexpr int kAttnVS = 360;           // halfs per V^T row
 constexpr int kAttnTab = 2200;         // (2*7-1)^3 = 2197 table rows
-constexpr size_t kAttnSmem = (size_t)kAttnMaxTok * kAttnQS * 4 + 16 * kAttnVS * 2 + kAttnTab * 4 + kAttnMaxTok * 7;
+constexpr size_t kAttnSmem = (size_t)kAttnMaxTok * kAttnQS * 2 + 16 * kAttnVS * 2 + kAttnTab * 4 + kAttnMaxTok * 8 + 32 * 4 + 16;
 
 template <bool FP16>
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -296,13 +297,13 @@ __device__ __forceinline__ uint16_t cvt1(float v) {
 template <bool FP16>
 __global__ void __launch_bounds__(256) swin_window_attention_kernel(const SwinAttnK k) {
   extern __shared__ __align__(16) uint8_t attn_smem[];
-  uint16_t* sQ = reinterpret_cast<uint16_t*>(attn_smem);                 // [kAttnMaxTok][kAttnQS]
-  uint16_t* sK = sQ + kAttnMaxTok * kAttnQS;                             // [kAttnMaxTok][kAttnQS]
+  // (the Q fragments of a warp's 16 queries are read straight from global memory, once: no shared-memory copy — 40 KB per
+  // CTA instead of 57 KB lets five CTAs share an SM instead of three)
+  uint16_t* sK = reinterpret_cast<uint16_t*>(attn_smem);                 // [kAttnMaxTok][kAttnQS]
   uint16_t* sVt = sK + kAttnMaxTok * kAttnQS;                            // [16][kAttnVS]
   float* sTab = reinterpret_cast<float*>(sVt + 16 * kAttnVS);            // [kAttnTab] relative-position bias of this head
   int* sPos = reinterpret_cast<int*>(sTab + kAttnTab);                   // voxel index of the token, -1 = padded token
-  int16_t* sBase = reinterpret_cast<int16_t*>(sPos + kAttnMaxTok);       // relative-position code
-  uint8_t* sReg = reinterpret_cast<uint8_t*>(sBase + kAttnMaxTok);       // shift-mask region
+  int* sKey = sPos + kAttnMaxTok;                                        // relative-position code | shift-mask region << 16
 
   const int n_tok = k.ws0 * k.ws1 * k.ws2;
   const int np = (n_tok + 15) & ~15;
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(256) swin_window_attention_kernel(const SwinAt
   const bool shifted = (k.s0 | k.s1 | k.s2) != 0;
 
   for (int i = threadIdx.x; i < k.table_len; i += blockDim.x) sTab[i] = k.table[(size_t)i * k.heads + head] * 1.4426950408889634f;
-  for (int i = threadIdx.x; i < np; i += blockDim.x) {
+  for (int i = threadIdx.x; i < kAttnMaxTok + 32; i += blockDim.x) {   // (+32: the last 64-key block reads past np)
     int pos = -1, base = 0, reg = 0;
     if (i < n_tok) {
       const int t2 = i % k.ws2, t1 = (i / k.ws2) % k.ws1, t0 = i / (k.ws2 * k.ws1);
@@ -336,16 +337,15 @@ __global__ void __launch_bounds__(256) swin_window_attention_kernel(const SwinAt
         reg = (r0 * 3 + r1) * 3 + r2;
       }
     }
-    sPos[i] = pos;
-    sBase[i] = (int16_t)base;
-    sReg[i] = (uint8_t)reg;
+    if (i < kAttnMaxTok) sPos[i] = pos;
+    sKey[i] = base | (reg << 16);
   }
   __syncthreads();
   // gather q / k / v of this head: 2 channel blocks each (16 dims)
   const uint16_t* qkv = reinterpret_cast<const uint16_t*>(k.qkv);
-  for (int e = threadIdx.x; e < np * 6; e += blockDim.x) {
-    const int i = e / 6, part = e - i * 6;       // part: 0,1 = q blocks; 2,3 = k; 4,5 = v
-    const int which = part >> 1, half = part & 1;
+  for (int e = threadIdx.x; e < np * 4; e += blockDim.x) {
+    const int i = e >> 2, part = e & 3;          // part: 0,1 = k blocks; 2,3 = v
+    const int which = 1 + (part >> 1), half = part & 1;
     const int ch0 = which * C + head * 16 + half * 8;
     const int pos = i < n_tok ? sPos[i] : -2;
     uint4 u = make_uint4(0, 0, 0, 0);
@@ -357,9 +357,7 @@ __global__ void __launch_bounds__(256) swin_window_attention_kernel(const SwinAt
       for (int j = 0; j < 8; ++j) b[j] = k.qkv_bias[ch0 + j];
       u = cvt8_from_f32(b, FP16);
     }
-    if (which == 0) {
-      *reinterpret_cast<uint4*>(sQ + i * kAttnQS + half * 8) = u;
-    } else if (which == 1) {
+    if (which == 1) {
       *reinterpret_cast<uint4*>(sK + i * kAttnQS + half * 8) = u;
     } else {
       const uint16_t* h = reinterpret_cast<const uint16_t*>(&u);
@@ -376,12 +374,17 @@ __global__ void __launch_bounds__(256) swin_window_attention_kernel(const SwinAt
   for (int qt = warp; qt < n_qt; qt += (blockDim.x >> 5)) {
     const int q0 = qt * 16;
     uint32_t qa[4];
-    qa[0] = *reinterpret_cast<const uint32_t*>(sQ + (q0 + g) * kAttnQS + 2 * t);
-    qa[1] = *reinterpret_cast<const uint32_t*>(sQ + (q0 + g + 8) * kAttnQS + 2 * t);
-    qa[2] = *reinterpret_cast<const uint32_t*>(sQ + (q0 + g) * kAttnQS + 2 * t + 8);
-    qa[3] = *reinterpret_cast<const uint32_t*>(sQ + (q0 + g + 8) * kAttnQS + 2 * t + 8);
-    const int bq0 = sBase[q0 + g] + k.centre, bq1 = sBase[q0 + g + 8] + k.centre;
-    const int rq0 = sReg[q0 + g], rq1 = sReg[q0 + g + 8];
+    {
+      const int pq0 = (q0 + g) < n_tok ? sPos[q0 + g] : -1, pq1 = (q0 + g + 8) < n_tok ? sPos[q0 + g + 8] : -1;
+      const size_t qb = ((size_t)img * k.qkv_cbt + head * 2) * nvox;   // first of the head's two q channel blocks
+      // a padded query's row is cropped from the output: its q does not matter
+      qa[0] = pq0 >= 0 ? *reinterpret_cast<const uint32_t*>(qkv + (qb + pq0) * 8 + 2 * t) : 0u;
+      qa[1] = pq1 >= 0 ? *reinterpret_cast<const uint32_t*>(qkv + (qb + pq1) * 8 + 2 * t) : 0u;
+      qa[2] = pq0 >= 0 ? *reinterpret_cast<const uint32_t*>(qkv + (qb + nvox + pq0) * 8 + 2 * t) : 0u;
+      qa[3] = pq1 >= 0 ? *reinterpret_cast<const uint32_t*>(qkv + (qb + nvox + pq1) * 8 + 2 * t) : 0u;
+    }
+    const int bq0 = (sKey[q0 + g] & 0xffff) + k.centre, bq1 = (sKey[q0 + g + 8] & 0xffff) + k.centre;
+    const int rq0 = sKey[q0 + g] >> 16, rq1 = sKey[q0 + g + 8] >> 16;
     float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;
     float o[2][4];
 #pragma unroll
@@ -390,38 +393,46 @@ __global__ void __launch_bounds__(256) swin_window_attention_kernel(const SwinAt
       for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
     for (int kb = 0; kb < np; kb += 64) {
       float s[8][4];
+      // scores of 64 keys: scale (log2 domain), relative-position bias, shift mask, key padding.  FULL = every key of the
+      // block exists (all blocks but the last): no bounds checks.  The per-key code (base | region << 16) of the two keys a
+      // lane owns in an n-tile comes with one 8-byte load.
+      auto score_block = [&](auto full_c) {
+        constexpr bool FULL = decltype(full_c)::value;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int key0 = kb + nt * 8;
+        for (int nt = 0; nt < 8; ++nt) {
+          const int key0 = kb + nt * 8;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) s[nt][j] = 0.f;
-        if (key0 < np) {
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sK + (key0 + g) * kAttnQS + 2 * t);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sK + (key0 + g) * kAttnQS + 2 * t + 8);
-          mma16816<FP16>(s[nt], qa, b0, b1);
-        }
-        // scale (log2 domain), relative-position bias, shift mask, key padding
-        const int kc = key0 + 2 * t;
+          for (int j = 0; j < 4; ++j) s[nt][j] = 0.f;
+          if (FULL || key0 < np) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sK + (key0 + g) * kAttnQS + 2 * t);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sK + (key0 + g) * kAttnQS + 2 * t + 8);
+            mma16816<FP16>(s[nt], qa, b0, b1);
+          }
+          const int kc = key0 + 2 * t;
+          const int2 ki = *reinterpret_cast<const int2*>(sKey + kc);
+          const int kinfo[2] = {ki.x, ki.y};
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int key = kc + j;
-          if (key < n_tok) {
-            const int bk = sBase[key];
-            float v0 = fmaf(s[nt][j], k.scale_log2e, sTab[bq0 - bk]);
-            float v1 = fmaf(s[nt][2 + j], k.scale_log2e, sTab[bq1 - bk]);
-            if (shifted) {
-              const int rk = sReg[key];
-              if (rk != rq0) v0 -= 144.26950408889634f;   // -100 in the log2 domain
-              if (rk != rq1) v1 -= 144.26950408889634f;
+          for (int j = 0; j < 2; ++j) {
+            if (FULL || kc + j < n_tok) {
+              const int bk = kinfo[j] & 0xffff;
+              float v0 = fmaf(s[nt][j], k.scale_log2e, sTab[bq0 - bk]);
+              float v1 = fmaf(s[nt][2 + j], k.scale_log2e, sTab[bq1 - bk]);
+              if (shifted) {
+                const int rk = kinfo[j] >> 16;
+                v0 = rk == rq0 ? v0 : v0 - 144.26950408889634f;   // -100 in the log2 domain
+                v1 = rk == rq1 ? v1 : v1 - 144.26950408889634f;
+              }
+              s[nt][j] = v0;
+              s[nt][2 + j] = v1;
+            } else {
+              s[nt][j] = -1e30f;
+              s[nt][2 + j] = -1e30f;
             }
-            s[nt][j] = v0;
-            s[nt][2 + j] = v1;
-          } else {
-            s[nt][j] = -1e30f;
-            s[nt][2 + j] = -1e30f;
           }
         }
-      }
+      };
+      if (kb + 64 <= n_tok) score_block(std::true_type{});
+      else score_block(std::false_type{});
       float mx0 = m0, mx1 = m1;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {

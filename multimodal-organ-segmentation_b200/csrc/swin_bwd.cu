@@ -454,7 +454,7 @@ struct SwinAttnBwdK {
 };
 
 constexpr int kBwdTok = 352;
-constexpr int kBwdRS = 24;     // halfs per row of the row-major operand copies (conflict-free fragment loads)
+constexpr int kBwdRS = 16;     // halfs per row of the row-major operand copies (2-way conflicts on fragment loads, but two CTAs fit per SM)
 constexpr int kBwdTS = 360;    // halfs per row of the transposed copies
 constexpr int kBwdThreads = 384;
 constexpr size_t kBwdSmem = (size_t)4 * kBwdTok * kBwdRS * 2 + (size_t)3 * 16 * kBwdTS * 2 + 2 * 2200 * 4 + 32 + 2 * kBwdTok * 4 +
