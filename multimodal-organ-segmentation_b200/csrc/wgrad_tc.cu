@@ -12,6 +12,7 @@
 //   D[dy] (TMEM, fp32) = [(dx, ci)] x [(dz-descending, co)], kept resident while a PERSISTENT CTA sweeps many voxel
 //       tiles; each CTA then writes one partial and mmseg_wgrad_reduce sums the partials in a fixed order
 //       (deterministic split-K, no atomics) straight into the PyTorch-layout fp32 gradient.
+#include <cstdlib>
 #include <cuda.h>
 
 #include "common.h"
@@ -421,6 +422,73 @@ extern "C" int mmseg_conv3d_wgrad(const mmseg_wgrad_args* a, void* stream) {
   return check_launch("wgrad_tc_kernel");
 }
 
+// Conv3d 3x3x3 layers whose gradient is large and whose split-K is shallow (n_part < 16: 128 channels and up — where
+// the bytes of a step's weight gradients are).  The kernel above writes 4-byte elements 108 bytes apart (a warp's lanes
+// are output channels, 27 * Cin floats apart), so every 32-byte sector of dW is completed by 8 different blocks.  Here a
+// block owns, for 8 input channels and 8 output channels, ALL 27 taps — accumulator rows (dx, ci) x columns (dy, dz, co),
+// read as 32-byte segments — sums the partials in index order (fp64), transposes through shared memory and writes runs of
+// 8 * 27 consecutive floats of the PyTorch layout.
+constexpr int kRedRC = 8, kRedNC = 8, kRedElems = 3 * kRedRC * 9 * kRedNC;      // 1,728 elements per block
+constexpr int kRedPerThread = (kRedElems + 255) / 256;
+// element e of the block's tile, in LOAD order (row, 32-byte column segment, column) -> its slot in STORE order
+// (output channel, input channel, tap) and its offset inside one partial
+__device__ __forceinline__ void red_tile_elem(int e, int CIG, int NTc, int ncols, int cil0, int n0, int& off, int& slot) {
+  const int r = e / (9 * kRedNC), c = e - r * (9 * kRedNC);
+  const int dx = r / kRedRC, cil = r - dx * kRedRC;
+  const int seg = c / kRedNC, nl = c - seg * kRedNC;              // seg = dy * 3 + dzr (the partial's column order)
+  const int dy = seg / 3, dz = 2 - (seg - dy * 3);
+  off = (dx * CIG + cil0 + cil) * ncols + seg * NTc + n0 + nl;
+  slot = (nl * kRedRC + cil) * 27 + (dz * 3 + dy) * 3 + dx;
+}
+__global__ void __launch_bounds__(256, 4)
+wgrad_reduce_tile_kernel(const float* __restrict__ partial, int n_part, int ncols, int n_cot, int NTc, int CIG, int Cin,
+                         int Cout_gemm, const int* __restrict__ ci_of_pos, float* __restrict__ dst) {
+  __shared__ float tile[kRedElems];
+  int b = blockIdx.x;
+  const int n_nblk = NTc / kRedNC, n_rblk = CIG / kRedRC;
+  const int nblk = b % n_nblk; b /= n_nblk;
+  const int rblk = b % n_rblk;
+  const int pair = b / n_rblk;
+  const int cig = pair / n_cot, cot = pair - cig * n_cot;
+  const int cil0 = rblk * kRedRC, n0 = nblk * kRedNC;
+  const float* base = partial + (size_t)pair * n_part * 128 * ncols;
+  const size_t kstride = (size_t)128 * ncols;
+  int off[kRedPerThread];
+  float acc[kRedPerThread];           // n_part < 16 addends in index order: fp32 is exact enough (the deep split-K
+                                      // layers go through the fp64 kernel above)
+#pragma unroll
+  for (int i = 0; i < kRedPerThread; ++i) {
+    const int e = threadIdx.x + i * 256;
+    int slot;
+    red_tile_elem(e < kRedElems ? e : 0, CIG, NTc, ncols, cil0, n0, off[i], slot);
+    acc[i] = (e < kRedElems) ? base[off[i]] : 0.f;
+  }
+  for (int k = 1; k < n_part; ++k) {
+    float v[kRedPerThread];
+#pragma unroll
+    for (int i = 0; i < kRedPerThread; ++i) v[i] = base[(size_t)k * kstride + off[i]];
+#pragma unroll
+    for (int i = 0; i < kRedPerThread; ++i) acc[i] += v[i];
+  }
+#pragma unroll
+  for (int i = 0; i < kRedPerThread; ++i) {
+    const int e = threadIdx.x + i * 256;
+    if (e < kRedElems) {
+      int o, slot;
+      red_tile_elem(e, CIG, NTc, ncols, cil0, n0, o, slot);
+      tile[slot] = acc[i];
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < kRedElems; e += 256) {
+    const int nl = e / (kRedRC * 27), r = e - nl * (kRedRC * 27);
+    const int cil = r / 27, tap = r - cil * 27;
+    const int n = cot * NTc + n0 + nl;
+    const int ci = ci_of_pos[cig * CIG + cil0 + cil];
+    if (n < Cout_gemm && ci >= 0) dst[((size_t)n * Cin + ci) * 27 + tap] = tile[e];
+  }
+}
+
 extern "C" int mmseg_wgrad_reduce(const float* partial, int32_t n_part, int32_t ksize, int32_t cig_blocks,
                                   int32_t cot_blocks, int32_t n_cig, int32_t n_cot, int32_t Cin, int32_t Cout_gemm,
                                   int32_t Cout, int32_t transposed, const int32_t* ci_of_pos, float* dst, void* stream) {
@@ -434,6 +502,13 @@ extern "C" int mmseg_wgrad_reduce(const float* partial, int32_t n_part, int32_t 
   const long long blocks = (long long)n_cig * n_cot * ((valid_rows + R - 1) / R) * ((ncols + 31) / 32);
   if (blocks > 2147483647LL) return fail(MMSEG_ERR_INVALID_ARG, "wgrad_reduce: grid too large");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const bool tile_ok = [] { const char* e = getenv("MMSEG_WGRAD_REDUCE_TILE"); return !(e && e[0] == '0'); }();
+  if (tile_ok && KT == 3 && !transposed && n_part < 16) {     // cig_blocks * 8 and cot_blocks * 8 are multiples of 8
+    const long long tb = (long long)n_cig * n_cot * cig_blocks * cot_blocks;
+    wgrad_reduce_tile_kernel<<<(unsigned)tb, 256, 0, st>>>(partial, n_part, ncols, n_cot, cot_blocks * 8, cig_blocks * 8, Cin,
+                                                           Cout_gemm, ci_of_pos, dst);
+    return check_launch("wgrad_reduce_tile_kernel");
+  }
 #define MMSEG_RED(SV)                                                                                                  \
   wgrad_reduce_kernel<SV><<<(unsigned)blocks, 256, 0, st>>>(partial, n_part, ncols, n_cot, cot_blocks * 8, cig_blocks * 8, \
                                                             KT, Cin, Cout_gemm, Cout, transposed ? 1 : 0, ci_of_pos, dst)

@@ -218,6 +218,8 @@ def test_sliding_window_vs_oracle(kw):
     ((64, 256, (4, 4, 8)), dict(ks=1)),                           # ConvTranspose GEMM view
     ((32, 32, (24, 24, 24)), dict(n_img=2)),
     ((256, 128, (4, 4, 4)), dict(n_img=2)),
+    ((128, 128, (8, 8, 12)), {}),                                 # shallow split-K: tiled reduce (all 27 taps per block)
+    ((96, 48, (6, 6, 6)), dict(n_img=2)),                         # SwinUNETR widths: 24-row / 48-column groups
 ])
 def test_wgrad_tcgen05(args, kw):
     _c().wgrad_case(*args, **kw)

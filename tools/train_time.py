@@ -42,6 +42,9 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 print(f"{kind} S={S} B={B}: {ms:.2f} ms/step (host {1e3 * (time.time() - t0) / steps:.2f} ms) -> {B / ms * 1e3:.2f} samples/s; loss {l.item():.5f}")
+os.environ["MMSEG_WGRAD_SIDE_STREAM"] = "0"      # serialised: per-kernel times without overlap
+step()
+torch.cuda.synchronize()
 K.PROFILE = []
 step()
 torch.cuda.synchronize()
