@@ -489,6 +489,46 @@ wgrad_reduce_tile_kernel(const float* __restrict__ partial, int n_part, int ncol
   }
 }
 
+// The same for 1x1x1 convs / Linear layers (accumulator rows = input channels, columns = output channels, dW[co][ci]):
+// a 32 x 32 tile read along the columns, transposed through shared memory, written along ci.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_tile_k1_kernel(const float* __restrict__ partial, int n_part, int ncols, int n_cot, int NTc, int CIG, int Cin,
+                            int Cout_gemm, const int* __restrict__ ci_of_pos, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  int b = blockIdx.x;
+  const int n_nblk = (NTc + 31) / 32, n_rblk = (CIG + 31) / 32;
+  const int nblk = b % n_nblk; b /= n_nblk;
+  const int rblk = b % n_rblk;
+  const int pair = b / n_rblk;
+  const int cig = pair / n_cot, cot = pair - cig * n_cot;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = nblk * 32 + tx;
+  const float* base = partial + (size_t)pair * n_part * 128 * ncols + col;
+  const size_t kstride = (size_t)128 * ncols;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  bool ok[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) ok[j] = col < NTc && rblk * 32 + ty + 8 * j < CIG;
+  for (int k = 0; k < n_part; ++k) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = ok[j] ? base[(size_t)k * kstride + (size_t)(rblk * 32 + ty + 8 * j) * ncols] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] += v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tile[ty + 8 * j][tx] = acc[j];
+  __syncthreads();
+  const int cil = rblk * 32 + tx;
+  const int ci = cil < CIG ? ci_of_pos[cig * CIG + cil] : -1;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int nl = nblk * 32 + ty + 8 * j;
+    const int n = cot * NTc + nl;
+    if (nl < NTc && n < Cout_gemm && ci >= 0) dst[(size_t)n * Cin + ci] = tile[tx][ty + 8 * j];
+  }
+}
+
 extern "C" int mmseg_wgrad_reduce(const float* partial, int32_t n_part, int32_t ksize, int32_t cig_blocks,
                                   int32_t cot_blocks, int32_t n_cig, int32_t n_cot, int32_t Cin, int32_t Cout_gemm,
                                   int32_t Cout, int32_t transposed, const int32_t* ci_of_pos, float* dst, void* stream) {
@@ -508,6 +548,12 @@ extern "C" int mmseg_wgrad_reduce(const float* partial, int32_t n_part, int32_t 
     wgrad_reduce_tile_kernel<<<(unsigned)tb, 256, 0, st>>>(partial, n_part, ncols, n_cot, cot_blocks * 8, cig_blocks * 8, Cin,
                                                            Cout_gemm, ci_of_pos, dst);
     return check_launch("wgrad_reduce_tile_kernel");
+  }
+  if (tile_ok && KT == 1 && !transposed && n_part < 16) {
+    const long long tb = (long long)n_cig * n_cot * ((cig_blocks * 8 + 31) / 32) * ((cot_blocks * 8 + 31) / 32);
+    wgrad_reduce_tile_k1_kernel<<<(unsigned)tb, 256, 0, st>>>(partial, n_part, ncols, n_cot, cot_blocks * 8, cig_blocks * 8,
+                                                              Cin, Cout_gemm, ci_of_pos, dst);
+    return check_launch("wgrad_reduce_tile_k1_kernel");
   }
 #define MMSEG_RED(SV)                                                                                                  \
   wgrad_reduce_kernel<SV><<<(unsigned)blocks, 256, 0, st>>>(partial, n_part, ncols, n_cot, cot_blocks * 8, cig_blocks * 8, \
