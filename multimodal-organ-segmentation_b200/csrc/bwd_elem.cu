@@ -123,6 +123,15 @@ __device__ __forceinline__ void for_each_item(const NormBwdK& k, int img, int c,
 #pragma unroll
       for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
       const size_t v000 = ((size_t)(2 * zh) * k.Y + (2 * yh)) * k.X + (2 * xh);
+      // the cell's 8 gA vectors are only consumed in pass 2 (two in flight per thread there): request them now, next to
+      // the 8 loads of pass 1, without holding 32 more registers (the lane pair d & 1 shares a 32-byte sector)
+      if (k.gA) {
+#pragma unroll
+        for (int d = 0; d < 8; d += 2) {
+          const size_t v = v000 + ((size_t)(d >> 2) * k.Y + ((d >> 1) & 1)) * k.X;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(k.gA + abase + v * 8));
+        }
+      }
 #pragma unroll
       for (int d = 0; d < 8; ++d) {
         const size_t v = v000 + ((size_t)(d >> 2) * k.Y + ((d >> 1) & 1)) * k.X + (d & 1);
