@@ -19,7 +19,15 @@ from .numerics import NumericMode, mode as numeric_mode
 Tensor = torch.Tensor
 
 
+# torch.cuda.current_stream() walks through device-index resolution, is_available() and os.getenv on every call —
+# a quarter of the host time of a launch-bound step (tools/swin_host_prof.py); the raw-handle query is one C call
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_cur_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream() -> C.c_void_p:
+    if _raw_stream is not None and _cur_device is not None:
+        return C.c_void_p(_raw_stream(_cur_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -440,8 +448,7 @@ def conv3d(src: Blocked, pw: PackedConv, a_cb: Sequence[int], dst: Tensor, out_m
     assert pw.w.dtype == src.t.dtype, "weights and activations must share the 16-bit element format"
     a.flags = flags | (ROLL_FLAG if tile.roll else 0) | (ROLL_KPAIR_FLAG if (tile.roll and tile.kpb == 2) else 0) \
         | (_lib.CONV_FP16_FLAG if src.fmt == _lib.FMT_FP16 else 0)
-    for i, v in enumerate(a_cb):
-        a.a_cb[i] = v
+    a.a_cb[:len(a_cb)] = list(a_cb)
     if stats is not None:
         need = src.n_img * tile.tiles_per_img * pw.n_out * 2
         assert stats.numel() >= need and stats.dtype == torch.float32
@@ -712,15 +719,10 @@ def _plan_wgrad_tile(X: int, Y: int, Z: int, ksize: int, cig_blocks: int, cot_bl
     return best[1]
 
 
-_CI_MAPS: dict = {}
-
-
-def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt: int, dy_cb0: int, cout_gemm: int,
-                 ksize: int, weight_shape, transposed: bool = False) -> Tensor:
-    """dW (fp32, PyTorch weight layout `weight_shape`) of a conv whose input is `x` (channel segments `segs` in concat
-    order) and whose raw-output gradient is `dy` (blocked bf16, `dy_cbt` channel blocks per image, first block dy_cb0)."""
-    _lib.require_device()
-    assert not x.split and x.fmt == _lib.FMT_BF16, "the backward path runs in bf16 mode"
+@lru_cache(maxsize=None)
+def _wgrad_plan(segs: Tuple[Tuple[int, int], ...], X: int, Y: int, Z: int, n_img: int, cout_gemm: int, ksize: int,
+                tz_env: str, groups_env: str):
+    """Host-side plan of one wgrad launch (cached per layer shape: the accumulator-row map alone is O(Cin) Python)."""
     seg_ch = [s[1] for s in segs]
     seg_pad = [(s + 15) // 16 * 16 for s in seg_ch]
     cin = sum(seg_ch)
@@ -738,25 +740,40 @@ def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt
         ci_map.extend(base + i for i in range(s))
     n_cig, n_cot = len(groups), cout_pad // ntc
     assert n_cig <= _lib.MAX_WGRAD_GROUPS
-    TX, TY, TZ = _plan_wgrad_tile(x.X, x.Y, x.Z, ksize, cig // 8, ntc // 8)
-    if ksize == 3 and os.environ.get("MMSEG_WGRAD_TZ", "auto") != "8":
+    TX, TY, TZ = _plan_wgrad_tile(X, Y, Z, ksize, cig // 8, ntc // 8)
+    if ksize == 3 and tz_env != "8":
         # z extent of a tile: every tile issues the MMAs (and loads) of TZ + 2 input planes for TZ output planes, so a
         # longer z run cuts the halo overhead (TZ = 8: 25 %, 32: 6 %) as long as the persistent CTAs stay balanced
-        forced = os.environ.get("MMSEG_WGRAD_TZ", "auto")
         ctas = max(1, 148 // (n_cig * n_cot))
-        txy = -(-x.X // TX) * -(-x.Y // TY) * x.n_img
+        txy = -(-X // TX) * -(-Y // TY) * n_img
         best = None
-        for tz in ([int(forced)] if forced != "auto" else (8, 12, 16, 24, 32, 48, 64, 96, 128)):
-            if tz > max(x.Z, 8):
+        for tz in ([int(tz_env)] if tz_env != "auto" else (8, 12, 16, 24, 32, 48, 64, 96, 128)):
+            if tz > max(Z, 8):
                 continue
-            tz = min(tz, x.Z)
-            nt = txy * -(-x.Z // tz)
+            tz = min(tz, Z)
+            nt = txy * -(-Z // tz)
             planes = -(-nt // min(nt, ctas)) * (tz + 2)          # input planes swept by the busiest CTA
             if best is None or planes < best[0]:
                 best = (planes, tz)
         TZ = best[1]
-    n_tiles = -(-x.X // TX) * -(-x.Y // TY) * -(-x.Z // TZ) * x.n_img
+    n_tiles = -(-X // TX) * -(-Y // TY) * -(-Z // TZ) * n_img
     n_part = max(1, min(n_tiles, 148 // (n_cig * n_cot)))
+    return cin, cig, ntc, tuple(groups), tuple(ci_map), n_cig, n_cot, TX, TY, TZ, n_part
+
+
+_CI_MAPS: dict = {}
+
+
+def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt: int, dy_cb0: int, cout_gemm: int,
+                 ksize: int, weight_shape, transposed: bool = False) -> Tensor:
+    """dW (fp32, PyTorch weight layout `weight_shape`) of a conv whose input is `x` (channel segments `segs` in concat
+    order) and whose raw-output gradient is `dy` (blocked bf16, `dy_cbt` channel blocks per image, first block dy_cb0)."""
+    _lib.require_device()
+    assert not x.split and x.fmt == _lib.FMT_BF16, "the backward path runs in bf16 mode"
+    segs_key = tuple((int(c0), int(s_)) for c0, s_ in segs)
+    (cin, cig, ntc, groups, ci_map, n_cig, n_cot, TX, TY, TZ, n_part) = _wgrad_plan(
+        segs_key, x.X, x.Y, x.Z, x.n_img, cout_gemm, ksize,
+        os.environ.get("MMSEG_WGRAD_TZ", "auto"), os.environ.get("MMSEG_WGRAD_OLD_GROUPS", "0"))
     ncols = ksize * ksize * ntc
     partial = torch.empty((n_cig * n_cot, n_part, 128, ncols), dtype=torch.float32, device=x.t.device)
     a = _lib.WgradArgs()
@@ -773,7 +790,7 @@ def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt
                     "tile": (TX, TY, TZ, ntc, cig), "ctas": n_part * n_cig * n_cot}
     _call("mmseg_conv3d_wgrad", C.byref(a), _stream())
     dw = torch.empty(tuple(weight_shape), dtype=torch.float32, device=x.t.device)
-    key = (tuple(ci_map), n_cig * cig, str(x.t.device))
+    key = (segs_key, cig, x.t.device)
     cm = _CI_MAPS.get(key)
     if cm is None:  # cached: a host->device copy per call would also break CUDA-graph capture of the training step
         inv = [-1] * (n_cig * cig)            # accumulator row position -> weight input channel (-1: padding row)

@@ -281,6 +281,27 @@ def test_wgrad_channel_groups_and_alignment_rule():
         assert smem(TX, TY, cig, cot, ks, X, X, X) > 0, (X, cig, cot, ks, TX, TY)
 
 
+def test_wgrad_plan_rows_groups_and_split():
+    """The cached host plan of a wgrad launch: accumulator-row map of concat / padded inputs, split-K depth."""
+    from mmseg_b200 import kernels as K
+    plan = lambda segs, S, n, cout, ks=3: K._wgrad_plan(tuple(segs), S, S, S, n, cout, ks, "auto", "0")
+    # decoder concat [up 32 | skip 32] -> two 32-row groups at channel blocks 0 and 4, rows in concat order
+    cin, cig, ntc, groups, ci_map, n_cig, n_cot, TX, TY, TZ, n_part = plan([(0, 32), (32, 32)], 32, 2, 32)
+    assert (cin, cig, ntc, groups, n_cig, n_cot) == (64, 32, 32, (0, 4), 2, 1) and ci_map == tuple(range(64))
+    assert (TZ, n_part) == (8, 32)        # 32 tiles of 8 planes: fewer tiles than the 74 persistent CTAs per group pair
+    # first layer: 2 real channels padded to one 16-row group
+    cin, cig, ntc, groups, ci_map, n_cig, n_cot, *_ = plan([(0, 2)], 16, 1, 32)
+    assert (cin, cig, groups, ci_map, n_cig) == (2, 16, (0,), (0, 1), 1)
+    # two 8-channel segments stored 16 apart (each padded to a 16-row group): rows 0-7 and 16-23
+    cin, cig, ntc, groups, ci_map, *_ = plan([(0, 8), (16, 8)], 8, 1, 16)
+    assert (cin, cig, groups) == (16, 16, (0, 2)) and ci_map == tuple(range(8)) + tuple(range(16, 24))
+    # SwinUNETR width 48: 24-row groups; a deep layer (768 -> 768 at 3^3) is one partial per channel-group pair
+    cin, cig, ntc, groups, ci_map, n_cig, n_cot, TX, TY, TZ, n_part = plan([(0, 768)], 3, 2, 768)
+    assert (cig, ntc, n_cig, n_cot, n_part) == (32, 48, 24, 16, 1)
+    assert plan([(0, 48)], 48, 1, 48)[1:4] == (24, 48, (0, 3))
+    assert plan([(0, 64)], 8, 1, 256, ks=1)[1:3] == (64, 256)
+
+
 def test_capture_guard_disables_gc_and_restores_it():
     import gc
     from mmseg_b200.src.trainer.inference import capture_guard
