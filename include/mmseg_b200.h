@@ -225,6 +225,12 @@ int mmseg_instnorm_act_bwd_apply(const mmseg_norm_bwd_args* args, void* stream);
  * of CrossModalAttention (src/models/backbones/dual_encoder.py:251-252).  partial: [n_img*M*cb][n_chunks] fp32. */
 int mmseg_modality_dot(const void* x, int32_t x_cbt, const void* g, int32_t g_cbt, int32_t g_cb_off, int32_t n_img,
                        int32_t M, int32_t cb, int64_t voxels, float* partial, int32_t n_chunks, float* out, void* stream);
+/* The 27 shifted copies of ONE channel (channel block src_cb, lane src_lane of a blocked 16-bit tensor) as a 32-channel
+ * blocked tensor dst [n_img*4][Z][Y][X][8]: channel t = tap (dz*3+dy)*3+dx, zero outside the volume, channels 27..31 zero.
+ * The weight gradient of a 1-input-channel Conv3d(k3,p1) (the per-modality first layers,
+ * src/models/backbones/dual_encoder.py:62-71 -> unet.py:33-39) is then mmseg_conv3d_wgrad with ksize 1 on dst. */
+int mmseg_im2col_k3_c1(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_cb, int32_t src_lane, int32_t Z,
+                       int32_t Y, int32_t X, void* dst, void* stream);
 /* Gradient of a ConvTranspose3d(k2,s2) output (blocked, high resolution, channel blocks [src_cb_off, +cb)) -> its k=1
  * GEMM view at low resolution with channel = tap*C + co: the dY operand of the transposed conv's dgrad / wgrad. */
 int mmseg_unshuffle_k2s2(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_cb_off, int32_t cb, int32_t Z,

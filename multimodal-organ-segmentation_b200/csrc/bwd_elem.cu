@@ -244,6 +244,38 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(const NormBwdK k
   });
 }
 
+// Weight gradient of a 3x3x3 conv with ONE input channel (DualEncoder's per-modality first layers): as a wgrad GEMM its
+// accumulator has 3 live rows of 128 and still costs the MMAs of a 32-channel layer (0.33 ms at 2 x 128^3).  The 27
+// shifted copies of the channel are written as a 32-channel blocked tensor instead (channel t = tap (dz*3+dy)*3+dx, zero
+// outside the volume = the conv's padding, channels 27..31 zero); dW[co][0][tap] is then the k = 1 weight gradient of that
+// tensor, an HBM-bound GEMM.
+__global__ void __launch_bounds__(256)
+im2col_k3_c1_kernel(const uint16_t* __restrict__ src, int src_cbt, int src_cb, int src_lane, int Z, int Y, int X,
+                    uint16_t* __restrict__ dst) {
+  const int img = blockIdx.y;
+  const size_t nvox = (size_t)Z * Y * X;
+  const uint16_t* s = src + (size_t)(img * src_cbt + src_cb) * nvox * 8 + src_lane;
+  uint16_t* d = dst + (size_t)img * 4 * nvox * 8;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(v % X);
+    const size_t r = v / X;
+    const int y = (int)(r % Y), z = (int)(r / Y);
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = 0u;
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+      const int zz = z + t / 9 - 1, yy = y + (t / 3) % 3 - 1, xx = x + t % 3 - 1;
+      uint32_t val = 0u;
+      if (zz >= 0 && zz < Z && yy >= 0 && yy < Y && xx >= 0 && xx < X) val = s[(((size_t)zz * Y + yy) * X + xx) * 8];
+      w[t >> 1] |= val << ((t & 1) * 16);
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      *reinterpret_cast<uint4*>(d + ((size_t)b * nvox + v) * 8) = make_uint4(w[4 * b], w[4 * b + 1], w[4 * b + 2], w[4 * b + 3]);
+  }
+}
+
 // gradient of a ConvTranspose3d(k2,s2) output [n_img*src_cbt][2Z][2Y][2X][8] (channels cb_off*8 .. +C) ->
 // its GEMM view [n_img*8*cb][Z][Y][X][8] with channel = tap*C + co, tap = (dz*2 + dy)*2 + dx
 __global__ void __launch_bounds__(256)
@@ -374,6 +406,17 @@ extern "C" int mmseg_modality_dot(const void* x, int32_t x_cbt, const void* g, i
   const int n = n_img * M;
   modality_dot_final_kernel<<<(n + 63) / 64, 64, 0, st>>>(partial, n, cb * n_chunks, out);
   return check_launch("modality_dot_final_kernel");
+}
+
+extern "C" int mmseg_im2col_k3_c1(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_cb, int32_t src_lane,
+                                  int32_t Z, int32_t Y, int32_t X, void* dst, void* stream) {
+  if (!src || !dst || n_img < 1 || src_cbt < 1 || src_cb < 0 || src_cb >= src_cbt || src_lane < 0 || src_lane > 7 || Z < 1 ||
+      Y < 1 || X < 1)
+    return fail(MMSEG_ERR_INVALID_ARG, "im2col_k3_c1: bad arguments");
+  dim3 grid(gxb((size_t)Z * Y * X, n_img, 65535), (unsigned)n_img);
+  im2col_k3_c1_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint16_t*>(src), src_cbt, src_cb, src_lane, Z, Y, X, reinterpret_cast<uint16_t*>(dst));
+  return check_launch("im2col_k3_c1_kernel");
 }
 
 extern "C" int mmseg_unshuffle_k2s2(const void* src, int32_t n_img, int32_t src_cbt, int32_t src_cb_off, int32_t cb,

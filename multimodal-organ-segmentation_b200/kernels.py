@@ -762,6 +762,21 @@ def _wgrad_plan(segs: Tuple[Tuple[int, int], ...], X: int, Y: int, Z: int, n_img
 
 
 _CI_MAPS: dict = {}
+_IM2COL_WS: dict = {}
+
+
+def _im2col_workspace(numel: int, like: Tensor) -> Tensor:
+    """The 32-channel im2col tensor of a 1-channel first layer (268 MB at 2 x 128^3).  Eager steps reuse ONE buffer per
+    (device, stream) — uses are ordered on that stream; a fresh transient block of this size per step fragments the
+    side stream's allocator pool (measured: +4 ms per step from repeated cudaMalloc).  Inside a CUDA-graph capture the
+    buffer comes from the graph's own pool."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(numel, dtype=like.dtype, device=like.device)
+    key = (like.device, _stream().value, like.dtype)
+    ws = _IM2COL_WS.get(key)
+    if ws is None or ws.numel() < numel:
+        ws = _IM2COL_WS[key] = torch.empty(numel, dtype=like.dtype, device=like.device)
+    return ws[:numel]
 
 
 def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt: int, dy_cb0: int, cout_gemm: int,
@@ -771,6 +786,18 @@ def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt
     _lib.require_device()
     assert not x.split and x.fmt == _lib.FMT_BF16, "the backward path runs in bf16 mode"
     segs_key = tuple((int(c0), int(s_)) for c0, s_ in segs)
+    if ksize == 3 and not transposed and len(segs_key) == 1 and segs_key[0][1] == 1 \
+            and os.environ.get("MMSEG_WGRAD_IM2COL", "1") == "1":
+        # one input channel (DualEncoder's per-modality first layers): 3 live accumulator rows of 128 for the MMAs of a
+        # 32-channel layer — the 27 shifted copies as a 32-channel tensor + the k = 1 wgrad GEMM is HBM-bound instead
+        c0 = segs_key[0][0]
+        col = Blocked.__new__(Blocked)
+        col.n_img, col.channels, col.Z, col.Y, col.X, col.cb, col.cbt, col.lo_off = x.n_img, 32, x.Z, x.Y, x.X, 4, 4, 0
+        col.nm, col.fmt, col.split, col.packed_split = x.nm, x.fmt, False, False
+        col.t = _im2col_workspace(x.n_img * 32 * x.nvox, x.t).view(x.n_img, 4, x.Z, x.Y, x.X, 8)
+        _call("mmseg_im2col_k3_c1", _ptr(x.t), x.n_img, x.cbt, c0 // 8, c0 % 8, x.Z, x.Y, x.X, _ptr(col.t), _stream())
+        dw = conv3d_wgrad(col, [(0, 27)], dy, dy_cbt, dy_cb0, cout_gemm, 1, (weight_shape[0], 27, 1, 1, 1))
+        return dw.view(tuple(weight_shape))
     (cin, cig, ntc, groups, ci_map, n_cig, n_cot, TX, TY, TZ, n_part) = _wgrad_plan(
         segs_key, x.X, x.Y, x.Z, x.n_img, cout_gemm, ksize,
         os.environ.get("MMSEG_WGRAD_TZ", "auto"), os.environ.get("MMSEG_WGRAD_OLD_GROUPS", "0"))

@@ -220,6 +220,7 @@ def test_sliding_window_vs_oracle(kw):
     ((256, 128, (4, 4, 4)), dict(n_img=2)),
     ((128, 128, (8, 8, 12)), {}),                                 # shallow split-K: tiled reduce (all 27 taps per block)
     ((96, 48, (6, 6, 6)), dict(n_img=2)),                         # SwinUNETR widths: 24-row / 48-column groups
+    ((1, 16, (4, 6, 10)), dict(segs=[(8, 1)])),                   # one channel in block 1: im2col + k=1 wgrad path
 ])
 def test_wgrad_tcgen05(args, kw):
     _c().wgrad_case(*args, **kw)
