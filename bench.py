@@ -573,6 +573,7 @@ def train_measure(steps, warmup, world, rank, dev, use_graph=True, cpu=False, wh
     from mmseg_b200 import kernels as K
     from mmseg_b200.src.models.build import build_model
     from mmseg_b200.src.trainer.trainer import Trainer
+    torch.cuda.reset_peak_memory_stats(dev)   # peak_mem_gb since here (live buffers of an earlier workload included)
     W = TRAIN_WORKLOADS[which]
     M, TRAIN_B = W["M"], W["B"]
     torch.manual_seed(0)                       # identical replicas
@@ -823,6 +824,7 @@ def swin_measure(dev, steps=5, warmup=3, cpu=True):
         opt = FusedAdamW(m.parameters(), lr=1e-4)
         res["train"] = []
         for B in (1, 2, 4):
+            torch.cuda.reset_peak_memory_stats(dev)     # peak_mem_gb is this batch size's, not the whole process's
             x = torch.randn((B, 2, 96, 96, 96), generator=g).to(dev)
             y = torch.randint(0, 8, (B, 96, 96, 96), generator=g).to(dev)
 
