@@ -44,14 +44,8 @@ def _train_step_forward(model: nn.Module, kind: str, x: torch.Tensor) -> torch.T
     blk = getattr(model, "init_conv", None)
     if blk is not None and getattr(blk, "activation", "relu") == "gelu":
         raise NotImplementedError("training with activation='gelu' is not built (the backward kernels cover ReLU / LeakyReLU)")
-    if blk is not None and getattr(blk, "norm_type", "instance") != "instance":
-        # model.backbone.norm = batch | group | none trains through the same kernels (train_engine._conv_generic_norm_act);
-        # the DualEncoder fusion ops and Dropout3d are wired for the reference's default norm only
-        if kind != "unet":
-            raise NotImplementedError(f"training DualEncoder with model.backbone.norm={blk.norm_type!r} is not built: the "
-                                      "fusion backward is wired for InstanceNorm3d (the reference's default)")
-        if model.training and isinstance(model.dropout, nn.Dropout3d) and model.dropout.p > 0:
-            raise NotImplementedError(f"training with model.backbone.norm={blk.norm_type!r} and Dropout3d > 0 is not built")
+    # model.backbone.norm = batch | group | none trains through the same kernels (train_engine._conv_generic_norm_act), for
+    # UNet3D and DualEncoder (every fusion type), with or without Dropout3d
     eng = model.__dict__.get("_train_engine")
     if eng is None:
         eng = model.__dict__["_train_engine"] = TrainEngine(model, kind)

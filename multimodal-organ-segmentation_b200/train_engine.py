@@ -119,9 +119,8 @@ class TrainEngine:
         from .engine import norm_kind_train
         nk = norm_kind_train(norm)
         if nk != "instance":
-            if chan_scale is not None or gate_ref is not None or gspec is not None:
-                raise NotImplementedError(f"training with norm={nk!r} together with Dropout3d / DualEncoder fusion is not built")
-            return self._conv_generic_norm_act(name, src, segs, conv, dst, dst_c0, pooled, slope, need_dgrad, norm, nk)
+            return self._conv_generic_norm_act(name, src, segs, conv, dst, dst_c0, pooled, slope, need_dgrad, norm, nk,
+                                               gspec=gspec, chan_scale=chan_scale, gate_ref=gate_ref)
         n, Z, Y, X = src.n_img, src.Z, src.Y, src.X
         cout = conv.weight.shape[0]
         seg_ch = tuple(s[1] for s in segs)
@@ -151,7 +150,8 @@ class TrainEngine:
 
 
     # ---------------------------------------------------------------- GroupNorm / BatchNorm3d / Identity blocks
-    def _conv_generic_norm_act(self, name, src, segs, conv, dst, dst_c0, pooled, slope, need_dgrad, norm, nk):
+    def _conv_generic_norm_act(self, name, src, segs, conv, dst, dst_c0, pooled, slope, need_dgrad, norm, nk,
+                               gspec=None, chan_scale=None, gate_ref=None):
         """ConvBlock3D half with model.backbone.norm = group | batch | anything else (Identity) — reference unet.py:29-41,
         53-60.  The conv keeps its bias (only InstanceNorm cancels it); the statistics come from the conv epilogue's
         partials and are combined over the norm's reduction set on [n, C] tensors; the apply kernel gets gamma folded into
@@ -199,15 +199,17 @@ class TrainEngine:
                 rstd = (1.0 / torch.sqrt(norm.running_var.detach().float() + norm.eps)).expand(n, cout)
                 stat_grad = False
         mean, rstd = mean.contiguous(), rstd.contiguous()
-        mr_fwd = torch.stack([mean, rstd * gamma], -1).contiguous()
-        shift = beta.expand(n, cout).contiguous()
-        K.instnorm_act_apply(raw, False, mr_fwd, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, 0, shift=shift)
+        scale_fwd, shift = rstd * gamma, beta.expand(n, cout)
+        if chan_scale is not None:      # Dropout3d's per-(sample, channel) factor s >= 0: s * act(z) = act(s * z)
+            scale_fwd, shift = scale_fwd * chan_scale, shift * chan_scale
+        mr_fwd = torch.stack([mean, scale_fwd], -1).contiguous()
+        K.instnorm_act_apply(raw, False, mr_fwd, n, cout, Z, Y, X, dst, dst_c0, slope, pooled, 0, shift=shift.contiguous())
         self.tape.append(dict(kind="cna", name=name, src=src, segs=list(segs), conv=conv, dst=dst, dst_c0=dst_c0,
-                              pooled=pooled, slope=slope, raw=raw, mr=None, gspec=None, need_dgrad=need_dgrad,
-                              chan_scale=None, gate_ref=None, norm=norm, nk=nk, mean=mean, rstd=rstd, gamma=gamma, beta=beta,
-                              stat_grad=stat_grad))
+                              pooled=pooled, slope=slope, raw=raw, mr=None, gspec=gspec, need_dgrad=need_dgrad,
+                              chan_scale=chan_scale, gate_ref=gate_ref, norm=norm, nk=nk, mean=mean, rstd=rstd, gamma=gamma,
+                              beta=beta, stat_grad=stat_grad))
 
-    def _bwd_generic_norm(self, op, draw_t, gA, gA_c0, gP):
+    def _bwd_generic_norm(self, op, draw_t, gA, gA_c0, gP, scale=1.0, chan_scale=None, chan_bias=None):
         """Backward of the norms above through the SAME two kernels as InstanceNorm: with (mean', rstd') = (mean - beta /
         (rstd gamma), rstd gamma) the kernels' normalised value IS the pre-activation z = y^ gamma + beta, so their sums are
         (sum h, sum h z) with h = g * act'(z); from those: dbeta = sum h, dgamma = sum h y^, and — combined over the norm's
@@ -244,7 +246,10 @@ class TrainEngine:
                 M2 = (t2.sum(0) / (n * nvox)).expand(n, cout)
             return torch.stack([M1 / g_safe - beta * M2 / (g_safe * g_safe), M2 / (g_safe * g_safe)], -1)
 
-        K.instnorm_act_bwd(op["raw"], mr_b, n, cout, Z, Y, X, gA, gA_c0, 1.0, gP, 0, draw_t, op["slope"], between=between)
+        # h = (scale * chan_scale * gA [+ routed gP] + chan_bias) * act'(z): the fused gradient's share of this modality
+        # (mean / add: `scale`; attention gate: its weight and the pooled-mean term), Dropout3d's factor
+        K.instnorm_act_bwd(op["raw"], mr_b, n, cout, Z, Y, X, gA, gA_c0, scale, gP, 0, draw_t, op["slope"],
+                           chan_scale, chan_bias, between=between)
 
     def conv_transpose(self, name: str, src: Blocked, up, dst: Blocked):
         cin = up.weight.shape[0]
@@ -355,7 +360,7 @@ class TrainEngine:
             chan_bias = (gate["dpooled"][:, i * cout:(i + 1) * cout] / float(Z * Y * X)).contiguous()
         generic = op.get("nk", "instance") != "instance"
         if generic:
-            self._bwd_generic_norm(op, draw_t, gA, gA_c0, gP)
+            self._bwd_generic_norm(op, draw_t, gA, gA_c0, gP, scale, chan_scale, chan_bias)
         else:
             K.instnorm_act_bwd(op["raw"], op["mr"], n, cout, Z, Y, X, gA, gA_c0, scale, gP, 0, draw_t, op["slope"],
                                chan_scale, chan_bias)
@@ -503,12 +508,12 @@ class TrainEngine:
                 self._inputs.append((a_in, cpm))
                 enc = m.encoders[i]
                 self.conv_norm_act(f"m{i}.init.c1", a_in, [(0, cpm)], enc["init_conv"].conv1, A(f"m{i}.e0.mid", f[0], 0),
-                                   need_dgrad=self._input_grad)
+                                   need_dgrad=self._input_grad, norm=enc["init_conv"].norm1)
                 for l in range(L):
                     blk = enc["init_conv"] if l == 0 else enc["blocks"][l - 1].conv
                     if l > 0:
                         self.conv_norm_act(f"m{i}.e{l}.c1", self.A[f"m{i}.pool{l}"], [(0, f[l - 1])], blk.conv1,
-                                           A(f"m{i}.e{l}.mid", f[l], l))
+                                           A(f"m{i}.e{l}.mid", f[l], l), norm=blk.norm1)
                     gspec = None
                     if m.fusion_type == "attention":   # scale / bias tables come from the gate op's backward
                         fd, fc0 = fused(l)
@@ -518,7 +523,8 @@ class TrainEngine:
                         gspec = (self.grad_of(fd), fc0, scale)
                     self.conv_norm_act(f"m{i}.e{l}.c2", self.A[f"m{i}.e{l}.mid"], [(0, f[l])], blk.conv2,
                                        self.A[f"stack{l}"], i * f[l],
-                                       pooled=A(f"m{i}.pool{l + 1}", f[l], l + 1) if l < L - 1 else None, gspec=gspec)
+                                       pooled=A(f"m{i}.pool{l + 1}", f[l], l + 1) if l < L - 1 else None, gspec=gspec,
+                                       norm=blk.norm2)
                     if m.fusion_type == "attention":
                         enc_last.setdefault(l, []).append((self.tape[-1], i))
             for l in range(L):

@@ -503,41 +503,66 @@ def _ref_train_step(kind, sd, cfgkw, x, y, dtype=torch.float64):
     return train_step(kind, sd, cfgkw, x, y, dtype)
 
 
-def train_step_case(kind="unet", features=(16, 32, 64), S=16, n_img=2, fusion="late", M=2, seed=0):
+def train_step_case(kind="unet", features=(16, 32, 64), S=16, n_img=2, fusion="late", M=2, seed=0, norm="instance",
+                    dropout=0.0):
     """Full training step through the kernels (forward, DiceCE, backward) vs fp64 autograd over the oracle maths."""
     from mmseg_b200.src.models.backbones.unet import UNet3D
     from mmseg_b200.src.models.backbones.dual_encoder import DualEncoder
     from mmseg_b200.src.trainer.losses import DiceCELoss
     torch.manual_seed(seed)
     if kind == "unet":
-        m = UNet3D(in_channels=2, out_channels=8, features=list(features))
+        m = UNet3D(in_channels=2, out_channels=8, features=list(features), norm=norm, dropout=dropout)
         cin = 2
     else:
-        m = DualEncoder(num_modalities=M, out_channels=8, features=list(features), fusion_type=fusion)
+        m = DualEncoder(num_modalities=M, out_channels=8, features=list(features), fusion_type=fusion, norm=norm,
+                        dropout=dropout)
         cin = M
+    if norm != "instance":
+        with torch.no_grad():
+            for name, p in m.named_parameters():     # non-trivial affine parameters
+                if ".norm" in name and name.endswith("weight"):
+                    p.uniform_(0.6, 1.4)
+                elif ".norm" in name and name.endswith("bias"):
+                    p.normal_(0, 0.3)
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     x = torch.randn(n_img, cin, S, S, S)
     y = torch.randint(0, 8, (n_img, S, S, S))
-    ref_loss, ref_g, ref_logits = _ref_train_step(kind, sd, dict(L=len(features), M=M, fusion=fusion), x, y)
+    drop = None
+    if dropout > 0:      # the Dropout3d mask the model will draw (its first use of the CUDA generator in the forward)
+        torch.cuda.manual_seed(777)
+        drop = torch.empty((n_img, features[0]), dtype=torch.float32, device=DEV).bernoulli_(1 - dropout) / (1 - dropout)
+        assert 0 < (drop == 0).sum().item() < drop.numel()
+    ref_loss, ref_g, ref_logits = _ref_train_step(kind, sd, dict(L=len(features), M=M, fusion=fusion, norm=norm, drop=drop), x, y)
     m = m.to(DEV).train()
     crit = DiceCELoss()
+    torch.cuda.manual_seed(777)
     logits = m(x.to(DEV))
     loss = crit(logits, y.to(DEV))
     loss.backward()
     torch.cuda.synchronize()
     rel_loss = abs(loss.item() - ref_loss) / abs(ref_loss)
-    print(f"[train {kind} {features} S={S} n={n_img} fusion={fusion}] loss {loss.item():.6f} vs {ref_loss:.6f} (rel {rel_loss:.2e})", flush=True)
+    print(f"[train {kind} {features} S={S} n={n_img} fusion={fusion} norm={norm}] loss {loss.item():.6f} vs {ref_loss:.6f} (rel {rel_loss:.2e})", flush=True)
     worst = 0.0
+    wnorm = ref_g["out_conv.weight"].norm().item()
     for name, p in m.named_parameters():
         g, r = p.grad.detach().cpu().double(), ref_g[name]
         if name.endswith(".bias") and ".conv" in name and "out_conv" not in name and "fusion_proj" not in name \
                 and "fusion_layers" not in name:
-            assert g.abs().max().item() == 0.0   # cancelled by InstanceNorm; the reference's value is rounding noise
-            continue
+            if norm == "instance":
+                assert g.abs().max().item() == 0.0   # cancelled by InstanceNorm; the reference's value is rounding noise
+                continue
+            if r.norm().item() < 1e-9 * wnorm:       # in front of a batch-statistics BatchNorm the true gradient is 0
+                assert g.norm().item() < 2e-2 * wnorm, (name, g.norm().item())
+                continue
         rel = ((g - r).norm() / (r.norm() + 1e-30)).item()
-        worst = max(worst, rel)
         print(f"    {name:44s} |g|={r.norm().item():.3e} rel_l2={rel:.3e}", flush=True)
         assert torch.isfinite(g).all()
+        if r.norm().item() < 1e-3 * wnorm:
+            # a gradient three orders below the head's (e.g. the deepest gate MLP under BatchNorm) sits inside the bf16
+            # noise of the activations it is computed from: bound its absolute error instead of the relative one
+            assert (g - r).norm().item() < 1e-3 * wnorm, (name, (g - r).norm().item())
+            continue
+        worst = max(worst, rel)
     print(f"    worst grad rel-L2 {worst:.3e}", flush=True)
     assert rel_loss < 1e-2
     # bf16 activations and gradients end to end: the REFERENCE itself under torch.autocast(bfloat16) shows 0.08-0.16

@@ -248,6 +248,13 @@ def test_conv_transpose_backward():
     (("dual", (16, 32), 16, 1), dict(fusion="add", M=3)),
     (("dual", (16, 32), 16, 2), dict(fusion="attention")),
     (("dual", (16, 32), 16, 1), dict(fusion="attention", M=4)),
+    # model.backbone.norm != instance through DualEncoder's fusions, and Dropout3d (the mask is reproduced from the seed)
+    (("dual", (16, 32), 16, 2), dict(fusion="late", norm="group")),
+    (("dual", (16, 32), 16, 2), dict(fusion="attention", norm="batch")),
+    (("dual", (16, 32), 16, 2), dict(fusion="concat", norm="none")),
+    (("dual", (16, 32), 16, 2), dict(fusion="add", norm="group", dropout=0.4)),
+    (("unet", (16, 32), 16, 2), dict(norm="batch", dropout=0.4)),
+    (("unet", (16, 32), 16, 2), dict(dropout=0.4)),
 ])
 def test_training_step_vs_fp64_autograd(args, kw):
     _c().train_step_case(*args, **kw)
