@@ -775,6 +775,8 @@ def _im2col_workspace(numel: int, like: Tensor) -> Tensor:
     key = (like.device, _stream().value, like.dtype)
     ws = _IM2COL_WS.get(key)
     if ws is None or ws.numel() < numel:
+        if len(_IM2COL_WS) >= 4:      # streams come and go with their engines: do not pin a buffer per dead stream
+            _IM2COL_WS.clear()        # (a dropped buffer returns to its stream's pool, where reuse is stream-ordered)
         ws = _IM2COL_WS[key] = torch.empty(numel, dtype=like.dtype, device=like.device)
     return ws[:numel]
 
