@@ -27,8 +27,11 @@ instnorm_finalize_kernel(const float* __restrict__ part, int n_img, int tiles, i
   const int img = idx / C, c = idx - img * C;
   const float* p = part + ((size_t)img * tiles * C + c) * 2;
   double s1 = 0.0, s2 = 0.0;
+  // the loads of 8 iterations are in flight together (a lane walks up to 60 partial rows, each a different sector: the
+  // rolled loop paid one L2 / DRAM latency per row, ~14 us per launch); the additions keep their order, bit for bit
+#pragma unroll 8
   for (int t = lane; t < tiles; t += 32) {
-    const float2 v = *reinterpret_cast<const float2*>(p + (size_t)t * C * 2);
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p + (size_t)t * C * 2));
     s1 += (double)v.x;
     s2 += (double)v.y;
   }
