@@ -795,7 +795,7 @@ def conv3d_wgrad(x: Blocked, segs: Sequence[Tuple[int, int]], dy: Tensor, dy_cbt
         c0 = segs_key[0][0]
         col = Blocked.__new__(Blocked)
         col.n_img, col.channels, col.Z, col.Y, col.X, col.cb, col.cbt, col.lo_off = x.n_img, 32, x.Z, x.Y, x.X, 4, 4, 0
-        col.nm, col.fmt, col.split, col.packed_split = x.nm, x.fmt, False, False
+        col.nm, col.fmt, col.split, col.packed_split = getattr(x, "nm", None), x.fmt, False, False
         col.t = _im2col_workspace(x.n_img * 32 * x.nvox, x.t).view(x.n_img, 4, x.Z, x.Y, x.X, 8)
         _call("mmseg_im2col_k3_c1", _ptr(x.t), x.n_img, x.cbt, c0 // 8, c0 % 8, x.Z, x.Y, x.X, _ptr(col.t), _stream())
         dw = conv3d_wgrad(col, [(0, 27)], dy, dy_cbt, dy_cb0, cout_gemm, 1, (weight_shape[0], 27, 1, 1, 1))
